@@ -1,0 +1,468 @@
+/*
+ * tensor_dil_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the block arithmetic that the Aces4 SIP runtime runs on its hot path:
+ * the ten bind(c) routines of src/sip/tensor_algebra/tensor_dil_omp.F90 (D. Lyakh), the scalar
+ * block loops of src/sip/dynamic_data/block.cpp, the label->permutation logic of
+ * src/sip/worker/interpreter.cpp and the block ownership arithmetic of
+ * src/sip/static_data/array_table.cpp + src/sip/mpi/data_distribution.cpp.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product (libsipgpu.so) never links, loads or calls it.
+ *
+ * PARITY PINNING: the reference itself cannot be built here (no Fortran compiler, no MPI, no JVM
+ * for the SIAL compiler -- see DESIGN.md), so this restatement is pinned against the reference's
+ * own known-answer tests (test/test_basic_sial.cpp, test/test_sial.cpp, test/test_*.F), restated
+ * in tests/test_oracle_golden.py, and cross-checked against numpy.einsum on random patterns.
+ *
+ * Every function cites the reference lines it follows.  All scalars are passed by pointer, which
+ * is ABI-identical to the C++ by-reference prototypes in tensor_ops_c_prototypes.h:41-178.
+ * Layout everywhere: dense, column-major (first index fastest), FP64, 32-bit extents.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <stdint.h>
+
+#define ORACLE_MAX_RANK 32 /* tensor_dil_omp.F90:59 max_tensor_rank */
+
+/* ---- pluggable dgemm (Fortran ABI).  Default: the naive loop of tensor_block_pcontract's
+ * arithmetic (F90:940-1179 computes the same sums, cache-blocked).  bench.py plugs OpenBLAS's
+ * dgemm_ here so that the CPU baseline is "permute -> BLAS dgemm -> permute" like F90:762. ---- */
+typedef void (*dgemm_fn)(const char*, const char*, const int*, const int*, const int*, const double*,
+                         const double*, const int*, const double*, const int*, const double*, double*,
+                         const int*);
+static dgemm_fn g_dgemm = 0;
+void oracle_set_dgemm(void* fn) { g_dgemm = (dgemm_fn)fn; }
+
+/* D(lld x lrd, col-major) += L'^T * R' with L' = [lcd x lld], R' = [lcd x lrd] (contracted index
+ * fastest in both): exactly dgemm('T','N',lld,lrd,lcd,1,L',lcd,R',lcd,1,D,lld)  (F90:762). */
+static void gemm_tn_acc(long long lld, long long lrd, long long lcd, const double* ltp, const double* rtp,
+                        double* dtp) {
+    if (g_dgemm) {
+        int m = (int)lld, n = (int)lrd, k = (int)lcd;
+        double one = 1.0;
+        g_dgemm("T", "N", &m, &n, &k, &one, ltp, &k, rtp, &k, &one, dtp, &m);
+        return;
+    }
+#pragma omp parallel for schedule(static) collapse(2) if (lld * lrd * lcd > 65536)
+    for (long long r = 0; r < lrd; ++r)
+        for (long long l = 0; l < lld; ++l) {
+            const double* a = ltp + l * lcd;
+            const double* b = rtp + r * lcd;
+            double s = 0.0;
+            for (long long c = 0; c < lcd; ++c) s += a[c] * b[c];
+            dtp[l + lld * r] += s;
+        }
+}
+
+/* F90:65-85 tensor_size_by_shape */
+long long oracle_tensor_size_by_shape_(const int* num_dim, const int* dims, int* ierr) {
+    long long sz = 1;
+    *ierr = 0;
+    if (*num_dim > 0) {
+        for (int i = 0; i < *num_dim; ++i) sz *= dims[i];
+        if (sz <= 0) *ierr = 2;
+    } else if (*num_dim < 0) {
+        *ierr = 1;
+        sz = 0;
+    }
+    return sz;
+}
+
+/* F90:1183-1233 merge_sort_key_int_: stable bottom-up merge sort of trn[1..ni] by key[trn[i]]
+ * (1-based item numbers, key is indexed by item number); trn[0] carries the permutation sign. */
+static void merge_sort_key_int(int ni, const int* key /*1-based via key[-1+i]*/, int* trn /*0..ni*/) {
+    if (ni <= 1) return;
+    int* prm = (int*)malloc(sizeof(int) * (size_t)(ni + 1));
+    for (int n = 1; n < ni; n *= 2) {
+        int m = 2 * n;
+        for (int i = 1; i <= ni; i += m) {
+            int k1 = i, k2 = i + n, k3, k4;
+            if (k2 > ni) { k2 = ni + 1; k3 = 0; k4 = 0; }
+            else { k3 = i + n; k4 = (ni + 1 < i + m) ? ni + 1 : i + m; }
+            int kf = ((ni + 1 < i + m) ? ni + 1 : i + m) - i, l = 0;
+            while (l < kf) {
+                if (k3 >= k4) { while (l < kf) prm[i + l++] = trn[k1++]; }
+                else if (k1 >= k2) { while (l < kf) prm[i + l++] = trn[k3++]; }
+                else {
+                    if (key[trn[k1] - 1] - key[trn[k3] - 1] > 0) {
+                        prm[i + l] = trn[k3++];
+                        trn[0] = (1 - 2 * ((k2 - k1) % 2)) * trn[0];
+                    } else prm[i + l] = trn[k1++];
+                    ++l;
+                }
+            }
+        }
+        for (int i = 1; i <= ni; ++i) trn[i] = prm[i];
+    }
+    free(prm);
+}
+
+/* F90:87-142 get_contraction_ptrn: label triple [d..|l..|r..] -> Lyakh pattern (1-based,
+ * +p = goes to destination position p, -q = contracted with position q of the other operand). */
+void oracle_get_contraction_ptrn_(const int* drank_, const int* lrank_, const int* rrank_, const int* aces_ptrn,
+                                  int* my_ptrn, int* ierr) {
+    int drank = *drank_, lrank = *lrank_, rrank = *rrank_;
+    *ierr = 0;
+    if (!(drank >= 0 && lrank >= 0 && rrank >= 0)) { *ierr = 1; return; }
+    int m = lrank + rrank, n = drank + m;
+    if (n % 2 != 0) { *ierr = 2; return; }
+    if (m <= 0) { if (drank > 0) *ierr = 3; return; }
+    int* trn = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+    trn[0] = +1;
+    for (int i = 1; i <= n; ++i) trn[i] = i;
+    merge_sort_key_int(n, aces_ptrn, trn);
+    for (int i = 1; i <= n - 1; i += 2) { /* every label exactly twice (F90:106-116) */
+        if (aces_ptrn[trn[i] - 1] == aces_ptrn[trn[i + 1] - 1]) {
+            if (i > 1 && aces_ptrn[trn[i] - 1] == aces_ptrn[trn[i - 1] - 1]) { *ierr = 5; free(trn); return; }
+        } else { *ierr = 4; free(trn); return; }
+    }
+    for (int i = 1; i <= n - 1; i += 2) { /* F90:118-128 */
+        int j = trn[i], k = trn[i + 1];
+        if (j <= drank && k > drank) my_ptrn[k - drank - 1] = j;
+        else if (j > drank && j <= drank + lrank && k > drank + lrank) {
+            my_ptrn[j - drank - 1] = -(k - (drank + lrank));
+            my_ptrn[k - drank - 1] = -(j - drank);
+        } else { *ierr = 6; free(trn); return; }
+    }
+    free(trn);
+}
+
+static long long block_size(int rank, const int* ext) {
+    long long s = 1;
+    for (int i = 0; i < rank; ++i) s *= ext[i];
+    return s;
+}
+
+/* F90:144-191 tensor_block_init_ */
+void oracle_tensor_block_init__(const int* nthreads, double* t, const int* rank, const int* ext, const double* val,
+                                int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank == 0) { t[0] = *val; return; }
+    if (*rank < 0) { *ierr = -1; return; }
+    long long n = block_size(*rank, ext);
+    for (long long i = 0; i < n; ++i) t[i] = *val;
+}
+
+/* F90:193-228 tensor_block_scale_ */
+void oracle_tensor_block_scale__(const int* nthreads, double* t, const int* rank, const int* ext, const double* fac,
+                                 int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank == 0) { t[0] *= *fac; return; }
+    if (*rank < 0) { *ierr = -1; return; }
+    long long n = block_size(*rank, ext);
+    for (long long i = 0; i < n; ++i) t[i] = t[i] * (*fac);
+}
+
+/* F90:230-269 tensor_block_norm2_ (squared Frobenius norm) */
+double oracle_tensor_block_norm2__(const int* nthreads, const double* t, const int* rank, const int* ext, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank == 0) return t[0] * t[0];
+    if (*rank < 0) { *ierr = -1; return 0.0; }
+    long long n = block_size(*rank, ext);
+    double v = 0.0;
+    for (long long i = 0; i < n; ++i) v += t[i] * t[i];
+    return v;
+}
+
+/* F90:271-330 tensor_block_slice_: slice[idx] = tens[beg+idx] */
+void oracle_tensor_block_slice__(const int* nthreads, const int* rank_, const double* t, const int* t_ext, double* s,
+                                 const int* s_ext, const int* beg, int* ierr) {
+    (void)nthreads;
+    int rank = *rank_;
+    *ierr = 0;
+    if (rank == 0) { s[0] = t[0]; return; }
+    if (rank < 0) { *ierr = 1; return; }
+    long long bin[ORACLE_MAX_RANK], n = block_size(rank, s_ext), b = 1;
+    int im[ORACLE_MAX_RANK];
+    for (int i = 0; i < rank; ++i) { bin[i] = b; b *= t_ext[i]; im[i] = 0; }
+    long long lin = 0;
+    for (int i = 0; i < rank; ++i) lin += (long long)beg[i] * bin[i];
+    for (long long lo = 0; lo < n; ++lo) {
+        s[lo] = t[lin];
+        for (int i = 0; i < rank; ++i) {
+            if (im[i] + 1 < s_ext[i]) { im[i]++; lin += bin[i]; break; }
+            lin -= (long long)im[i] * bin[i];
+            im[i] = 0;
+        }
+    }
+}
+
+/* F90:332-392 tensor_block_insert_: tens[beg+idx] = slice[idx] */
+void oracle_tensor_block_insert__(const int* nthreads, const int* rank_, double* t, const int* t_ext, const double* s,
+                                  const int* s_ext, const int* beg, int* ierr) {
+    (void)nthreads;
+    int rank = *rank_;
+    *ierr = 0;
+    if (rank == 0) { t[0] = s[0]; return; }
+    if (rank < 0) { *ierr = 1; return; }
+    long long bout[ORACLE_MAX_RANK], n = block_size(rank, s_ext), b = 1;
+    int im[ORACLE_MAX_RANK];
+    for (int i = 0; i < rank; ++i) { bout[i] = b; b *= t_ext[i]; im[i] = 0; }
+    long long lout = 0;
+    for (int i = 0; i < rank; ++i) lout += (long long)beg[i] * bout[i];
+    for (long long li = 0; li < n; ++li) {
+        t[lout] = s[li];
+        for (int i = 0; i < rank; ++i) {
+            if (im[i] + 1 < s_ext[i]) { im[i]++; lout += bout[i]; break; }
+            lout -= (long long)im[i] * bout[i];
+            im[i] = 0;
+        }
+    }
+}
+
+/* F90:394-436 tensor_block_add_: t0 += t1*fac (multiply skipped when |fac-1| <= 1e-13) */
+void oracle_tensor_block_add__(const int* nthreads, const int* rank, const int* ext, double* t0, const double* t1,
+                               const double* fac, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank == 0) { t0[0] = t0[0] + t1[0] * (*fac); return; }
+    if (*rank < 0) { *ierr = -1; return; }
+    long long n = block_size(*rank, ext);
+    if (fabs(*fac - 1.0) > 1e-13) {
+#pragma omp parallel for schedule(static) if (n > 65536)
+        for (long long i = 0; i < n; ++i) t0[i] = t0[i] + t1[i] * (*fac);
+    } else {
+#pragma omp parallel for schedule(static) if (n > 65536)
+        for (long long i = 0; i < n; ++i) t0[i] = t0[i] + t1[i];
+    }
+}
+
+/* F90:438-660 tensor_block_copy_: out[new position of idx] = in[idx]; transp[0] = sign slot,
+ * transp[i] (i=1..rank) = NEW position of OLD dimension i, 1-based (semantics F90:475-497; the
+ * remainder of the Fortran routine is cache scheduling of the same assignment). */
+void oracle_tensor_block_copy__(const int* nthreads, const int* rank_, const int* ext, const int* transp,
+                                const double* in, double* out, int* ierr) {
+    (void)nthreads;
+    int rank = *rank_;
+    *ierr = 0;
+    if (rank < 0) { *ierr = rank; return; }
+    if (rank == 0) { out[0] = in[0]; return; }
+    int trivial = 1;
+    for (int i = 1; i <= rank; ++i) if (transp[i] != i) { trivial = 0; break; }
+    long long n = block_size(rank, ext);
+    if (trivial) { memcpy(out, in, sizeof(double) * (size_t)n); return; }
+    int n2o[ORACLE_MAX_RANK + 2];
+    long long bout[ORACLE_MAX_RANK + 1], b = 1;
+    for (int i = 1; i <= rank; ++i) n2o[transp[i]] = i;
+    for (int i = 1; i <= rank; ++i) { bout[n2o[i]] = b; b *= ext[n2o[i] - 1]; } /* F90:496 */
+    /* walk the input linearly; the last (slowest) input dimension is split over threads */
+    long long slow = ext[rank - 1], inner = n / slow;
+#pragma omp parallel for schedule(static) if (n > 65536)
+    for (long long s = 0; s < slow; ++s) {
+        int im[ORACLE_MAX_RANK];
+        for (int i = 0; i < rank; ++i) im[i] = 0;
+        long long lout = s * bout[rank];
+        const double* src = in + s * inner;
+        for (long long li = 0; li < inner; ++li) {
+            out[lout] = src[li];
+            for (int i = 0; i < rank - 1; ++i) {
+                if (im[i] + 1 < ext[i]) { im[i]++; lout += bout[i + 1]; break; }
+                lout -= (long long)im[i] * bout[i + 1];
+                im[i] = 0;
+            }
+        }
+    }
+}
+
+/* F90:910-938 tensor_block_fcontract: d += sum l[i]*r[i] */
+static int fcontract(long long dc, const double* l, const double* r, double* d) {
+    if (dc <= 0) return 1;
+    double v = 0.0;
+    for (long long i = 0; i < dc; ++i) v += l[i] * r[i];
+    *d += v;
+    return 0;
+}
+
+/* F90:861-896 contr_ptrn_ok */
+static int contr_ptrn_ok(const int* ptrn, int lr, int rr, int dr, const int* lext, const int* rext, const int* dext) {
+    int jl = dr + lr + rr;
+    if (jl <= 0) return 1;
+    int jbus[3 * ORACLE_MAX_RANK];
+    for (int i = 0; i < jl; ++i) jbus[i] = 0;
+    for (int j0 = 1; j0 <= lr; ++j0) {
+        int j1 = ptrn[j0 - 1];
+        if (j1 > 0 && j1 <= dr) {
+            jbus[j1 - 1]++; jbus[dr + j0 - 1]++;
+            if (lext[j0 - 1] != dext[j1 - 1]) return 0;
+        } else if (j1 < 0 && -j1 <= rr) {
+            jbus[dr + lr - j1 - 1]++;
+            if (lext[j0 - 1] != rext[-j1 - 1]) return 0;
+        } else return 0;
+    }
+    for (int j0 = lr + 1; j0 <= lr + rr; ++j0) {
+        int j1 = ptrn[j0 - 1];
+        if (j1 > 0 && j1 <= dr) {
+            jbus[j1 - 1]++; jbus[dr + j0 - 1]++;
+            if (rext[j0 - lr - 1] != dext[j1 - 1]) return 0;
+        } else if (j1 < 0 && -j1 <= lr) {
+            jbus[dr - j1 - 1]++;
+            if (rext[j0 - lr - 1] != lext[-j1 - 1]) return 0;
+        } else return 0;
+    }
+    for (int i = 0; i < jl; ++i) if (jbus[i] != 1) return 0;
+    return 1;
+}
+
+static int perm_trivial(int n, const int* trn /*0..n*/) {
+    for (int i = 1; i <= n; ++i) if (trn[i] != i) return 0;
+    return 1;
+}
+
+/* F90:799-859 determine_index_permutations, exported for tests of the planner:
+ * lo2n/ro2n/do2n have rank+1 entries (slot 0 = sign), dims[3] = {lld, lrd, lcd},
+ * transp[3] = {ltransp, rtransp, dtransp}. */
+void oracle_determine_index_permutations(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext,
+                                         int drank, const int* dext, int* lo2n, int* ro2n, int* do2n,
+                                         long long* dims, int* transp) {
+    long long lld = 1, lrd = 1, lcd = 1;
+    int j1;
+    (void)dext;
+    transp[0] = transp[1] = transp[2] = 0;
+    if (drank > 0) {
+        do2n[0] = +1; j1 = 0;
+        for (int j0 = 1; j0 <= lrank + rrank; ++j0) if (ptrn[j0 - 1] > 0) do2n[++j1] = ptrn[j0 - 1];
+        transp[2] = !perm_trivial(j1, do2n);
+    }
+    if (rrank > 0) {
+        ro2n[0] = +1; j1 = 0;
+        for (int j0 = 1; j0 <= rrank; ++j0) if (ptrn[lrank + j0 - 1] < 0) { ro2n[j0] = ++j1; lcd *= rext[j0 - 1]; }
+        for (int j0 = 1; j0 <= rrank; ++j0) if (ptrn[lrank + j0 - 1] > 0) { ro2n[j0] = ++j1; lrd *= rext[j0 - 1]; }
+        transp[1] = !perm_trivial(j1, ro2n);
+    }
+    if (lrank > 0) {
+        int jkey[ORACLE_MAX_RANK], jtrn0[ORACLE_MAX_RANK + 1], jtrn1[ORACLE_MAX_RANK + 1];
+        lo2n[0] = +1; j1 = 0;
+        for (int j0 = 1; j0 <= lrank; ++j0)
+            if (ptrn[j0 - 1] < 0) { ++j1; jtrn1[j1] = j0; jkey[j1 - 1] = abs(ptrn[j0 - 1]); }
+        jtrn0[0] = +1;
+        for (int j = 1; j <= j1; ++j) jtrn0[j] = j;
+        merge_sort_key_int(j1, jkey, jtrn0); /* align L's contracted dims with R's order (F90:846) */
+        for (int j0 = 1; j0 <= j1; ++j0) lo2n[jtrn1[jtrn0[j0]]] = j0;
+        for (int j0 = 1; j0 <= lrank; ++j0) if (ptrn[j0 - 1] > 0) { lo2n[j0] = ++j1; lld *= lext[j0 - 1]; }
+        transp[0] = !perm_trivial(j1, lo2n);
+    }
+    dims[0] = lld; dims[1] = lrd; dims[2] = lcd;
+}
+
+/* F90:662-796 tensor_block_contract_: ASSIGN semantics (destination zeroed at F90:752),
+ * permute L / permute R / GEMM('T','N') / permute D. */
+void oracle_tensor_block_contract__(const int* nthreads, const int* ptrn, const double* L, const int* lrank_,
+                                    const int* lext, const double* R, const int* rrank_, const int* rext, double* D,
+                                    const int* drank_, const int* dext, int* ierr) {
+    int lrank = *lrank_, rrank = *rrank_, drank = *drank_;
+    *ierr = 0;
+    if (!(lrank >= 0 && lrank <= ORACLE_MAX_RANK && rrank >= 0 && rrank <= ORACLE_MAX_RANK && drank >= 0 &&
+          drank <= ORACLE_MAX_RANK)) { *ierr = -1; return; }
+    if (!contr_ptrn_ok(ptrn, lrank, rrank, drank, lext, rext, dext)) { *ierr = 1; return; }
+    int lo2n[ORACLE_MAX_RANK + 1], ro2n[ORACLE_MAX_RANK + 1], do2n[ORACLE_MAX_RANK + 1], transp[3];
+    long long dims[3];
+    oracle_determine_index_permutations(ptrn, lrank, lext, rrank, rext, drank, dext, lo2n, ro2n, do2n, dims, transp);
+    long long lsize = block_size(lrank, lext), rsize = block_size(rrank, rext), dsize = block_size(drank, dext);
+    long long lld = dims[0], lrd = dims[1], lcd = dims[2];
+    const double *ltp = L, *rtp = R;
+    double *lbuf = 0, *rbuf = 0, *dbuf = 0, *dtp = D;
+    if (transp[0]) {
+        lbuf = (double*)malloc(sizeof(double) * (size_t)lsize);
+        oracle_tensor_block_copy__(nthreads, &lrank, lext, lo2n, L, lbuf, ierr);
+        ltp = lbuf;
+    }
+    if (transp[1] && !*ierr) {
+        rbuf = (double*)malloc(sizeof(double) * (size_t)rsize);
+        oracle_tensor_block_copy__(nthreads, &rrank, rext, ro2n, R, rbuf, ierr);
+        rtp = rbuf;
+    }
+    if (transp[2]) { dbuf = (double*)malloc(sizeof(double) * (size_t)dsize); dtp = dbuf; }
+    if (!*ierr) {
+        for (long long k = 0; k < dsize; ++k) dtp[k] = 0.0; /* F90:752 */
+        if (drank > 0 && lrank > 0 && rrank > 0) gemm_tn_acc(lld, lrd, lcd, ltp, rtp, dtp);
+        else if (drank == 0 && lrank > 0 && rrank > 0) { dtp[0] = 0.0; *ierr = fcontract(lcd, ltp, rtp, dtp); }
+        else if (drank > 0 && lrank > 0 && rrank == 0) oracle_tensor_block_add__(nthreads, &drank, dext, dtp, ltp, rtp, ierr);
+        else if (drank > 0 && lrank == 0 && rrank > 0) oracle_tensor_block_add__(nthreads, &drank, dext, dtp, rtp, ltp, ierr);
+        else if (drank == 0 && lrank == 0 && rrank == 0) dtp[0] = ltp[0] * rtp[0];
+    }
+    if (transp[2] && !*ierr) { /* F90:782-785: D' dims are dext(do2n(1..)) */
+        int pext[ORACLE_MAX_RANK];
+        for (int k = 1; k <= drank; ++k) pext[k - 1] = dext[do2n[k] - 1];
+        oracle_tensor_block_copy__(nthreads, &drank, pext, do2n, dtp, D, ierr);
+    }
+    free(lbuf); free(rbuf); free(dbuf);
+}
+
+/* ---- block.cpp scalar loops (the interpreter's own elementwise ops) ---- */
+void oracle_block_fill(double* d, long long n, double v) { for (long long i = 0; i < n; ++i) d[i] = v; }             /* block.cpp:153-176 */
+void oracle_block_scale(double* d, long long n, double f) { for (long long i = 0; i < n; ++i) d[i] *= f; }           /* block.cpp:179-186 */
+void oracle_block_scale_and_copy(double* d, const double* s, long long n, double f) { for (long long i = 0; i < n; ++i) d[i] = s[i] * f; } /* :189-202 */
+void oracle_block_increment(double* d, long long n, double delta) { for (long long i = 0; i < n; ++i) d[i] += delta; } /* :206-213 */
+void oracle_block_accumulate(double* d, const double* s, long long n) { for (long long i = 0; i < n; ++i) d[i] += s[i]; } /* :259-268 */
+/* interpreter.cpp:1929-1932 / 1992-1995: d = l + sign*r */
+void oracle_block_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
+    for (long long i = 0; i < n; ++i) d[i] = (sign > 0) ? l[i] + r[i] : l[i] - r[i];
+}
+
+/* interpreter.cpp:2049-2084 permute_rhs_to_lhs + block.cpp:227-231: 0-based old->new permutation
+ * from labels, then the 1-based "dmitry_permute" with the sign slot.  Returns 0 on success. */
+int oracle_permutation_from_labels(int rank, const int* lhs_labels, const int* rhs_labels, int* transp /*rank+1*/) {
+    transp[0] = 1;
+    for (int i = 0; i < rank; ++i) {
+        int j = 0;
+        while (j < rank && rhs_labels[j] != lhs_labels[i]) ++j;
+        if (j >= rank) return 1; /* "illegal transpose" */
+        transp[j + 1] = i + 1;
+    }
+    return 0;
+}
+
+/* lhs[lhs_labels] = rhs[rhs_labels]  (block_permute_op, interpreter.cpp:656-679) */
+int oracle_block_permute(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels, const double* rhs,
+                         double* lhs) {
+    int transp[ORACLE_MAX_RANK + 1], ierr = 0, nth = 8;
+    if (oracle_permutation_from_labels(rank, lhs_labels, rhs_labels, transp)) return 1;
+    oracle_tensor_block_copy__(&nth, &rank, rhs_ext, transp, rhs, lhs, &ierr);
+    return ierr;
+}
+
+/* D[dlab] = L[llab] * R[rlab] by labels: interpreter.cpp:1210-1262 (handle_contraction) */
+int oracle_block_contract_labels(int drank, const int* dext, const int* dlab, double* D, int lrank, const int* lext,
+                                 const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
+                                 const double* R) {
+    int aces[3 * ORACLE_MAX_RANK], ptrn[2 * ORACLE_MAX_RANK], ierr = 0, nth = 8, k = 0;
+    for (int i = 0; i < drank; ++i) aces[k++] = dlab[i];
+    for (int i = 0; i < lrank; ++i) aces[k++] = llab[i];
+    for (int i = 0; i < rrank; ++i) aces[k++] = rlab[i];
+    oracle_get_contraction_ptrn_(&drank, &lrank, &rrank, aces, ptrn, &ierr);
+    if (ierr) return 100 + ierr;
+    oracle_tensor_block_contract__(&nth, ptrn, L, &lrank, lext, R, &rrank, rext, D, &drank, dext, &ierr);
+    return ierr;
+}
+
+/* ---- ownership arithmetic ----
+ * array_table.cpp:50-97: slice sizes are running products of segment counts with the LAST index
+ * fastest (the loop runs pos = rank-1 .. 0); block_number = sum slice[i]*(idx[i]-lower[i]). */
+long long oracle_block_number(int rank, const int* nseg, const int* lower, const int* idx) {
+    long long slice[ORACLE_MAX_RANK], s = 1, res = 0;
+    for (int p = rank - 1; p >= 0; --p) { slice[p] = s; s *= nseg[p]; }
+    for (int i = 0; i < rank; ++i) res += slice[i] * (idx[i] - lower[i]);
+    return res;
+}
+void oracle_block_num2id(int rank, const int* nseg, const int* lower, long long num, int* idx) {
+    long long slice[ORACLE_MAX_RANK], s = 1;
+    for (int p = rank - 1; p >= 0; --p) { slice[p] = s; s *= nseg[p]; }
+    for (int i = 0; i < rank; ++i) { long long q = num / slice[i]; idx[i] = (int)q + lower[i]; num -= q * slice[i]; }
+}
+/* data_distribution.cpp:74-82: cyclic over the owners */
+int oracle_block_owner(long long block_number, int nowners) { return (int)(block_number % nowners); }
+
+/* ---- the reference's own synthetic fills (qm/tests/fill_block_cyclic.f, fill_block_sequential.f) ---- */
+void oracle_fill_block_cyclic(double* d, long long n, double start) {
+    double v = start;
+    for (long long i = 0; i < n; ++i) { d[i] = v; if (v == 20.0) v = 0.0; v += 1.0; }
+}
+void oracle_fill_block_sequential(double* d, long long n, double start) {
+    double v = start;
+    for (long long i = 0; i < n; ++i) { d[i] = v; v += 1.0; }
+}
