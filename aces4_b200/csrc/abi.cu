@@ -1,0 +1,505 @@
+// abi.cu -- the extern "C" entry points of include/sipgpu.h (boundaries 1-3) and the host-side
+// orchestration of the contraction: pattern analysis -> Shape -> one fused-kernel launch.
+#include <map>
+#include <vector>
+
+#include "contract.h"
+#include "elementwise.h"
+#include "plan.h"
+
+namespace sipgpu {
+namespace {
+
+long long volume(int rank, const int* ext) {
+    long long n = 1;
+    for (int i = 0; i < rank; ++i) n *= ext[i];
+    return n;
+}
+
+// d[i] = alpha * s[i] * r[0] + beta * d[i]   (tensor x rank-0 block: F90:771-774)
+__global__ void __launch_bounds__(256) scal_dev_kernel(double* __restrict__ d, const double* __restrict__ s, long long n,
+                                                       const double* __restrict__ r, double alpha, double beta) {
+    const double f = alpha * r[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        d[i] = (beta != 0.0) ? f * s[i] + beta * d[i] : f * s[i];
+}
+
+int scaled_by_device_scalar(double* d, const double* s, long long n, const double* r, double alpha, double beta) {
+    long long b = (n + 255) / 256;
+    if (b > ctx().num_sms * 8) b = ctx().num_sms * 8;
+    scal_dev_kernel<<<(int)b, 256, 0, ctx().stream>>>(d, s, n, r, alpha, beta);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+struct TempBlock {  // pool block released at scope exit (stream order keeps it alive for queued kernels)
+    double* p = nullptr;
+    ~TempBlock() { if (p) pool_free(p); }
+    int get(long long n) {
+        p = pool_alloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        return p ? SIPGPU_OK : SIPGPU_E_NOMEM;
+    }
+};
+
+int tiles_of(const Shape& s) {
+    int bm, bn;
+    contract_tile_dims(0, &bm, &bn);
+    return ((s.M + bm - 1) / bm) * ((s.N + bn - 1) / bn);
+}
+
+// rank-0 special cases of tensor_block_contract_ (F90:764-780)
+int contract_degenerate(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                        const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    if (!contr_ptrn_ok(ptrn, lrank, rrank, drank, lext, rext, dext)) return 1;
+    if (drank == 0 && lrank == 0 && rrank == 0) {  // scalar * scalar
+        return scaled_by_device_scalar(D, L, 1, R, alpha, beta);
+    }
+    if (drank == 0) {  // full contraction to a scalar: permute L into R's index order, then a dot product
+        int transp[33];
+        transp[0] = 1;
+        bool trivial = true;
+        for (int j = 0; j < lrank; ++j) {
+            transp[j + 1] = -ptrn[j];
+            trivial = trivial && transp[j + 1] == j + 1;
+        }
+        const long long n = volume(lrank, lext);
+        TempBlock tmp;
+        const double* lp = L;
+        if (!trivial) {
+            SIP_TRY(tmp.get(n));
+            SIP_TRY(permute_block(lrank, lext, transp, L, tmp.p));
+            lp = tmp.p;
+        }
+        if (alpha != 1.0) {  // D = beta*D + alpha*dot: fold alpha through a scaled scratch result
+            SIP_TRY(ew_dot_device(lp, R, n, ctx().d_reduce + 1, 0.0));
+            return scaled_by_device_scalar(D, ctx().d_reduce + 1, 1, ctx().d_reduce + 2, alpha, beta);
+        }
+        return ew_dot_device(lp, R, n, D, beta);
+    }
+    // tensor * rank-0 block: D[ptrn[j]] <- T dim j, times the scalar
+    const bool l_is_tensor = lrank > 0;
+    const double* T = l_is_tensor ? L : R;
+    const double* S = l_is_tensor ? R : L;
+    const int trank = l_is_tensor ? lrank : rrank;
+    const int* text = l_is_tensor ? lext : rext;
+    const int* tp = l_is_tensor ? ptrn : ptrn + lrank;
+    int transp[33];
+    transp[0] = 1;
+    bool trivial = true;
+    for (int j = 0; j < trank; ++j) {
+        transp[j + 1] = tp[j];
+        trivial = trivial && tp[j] == j + 1;
+    }
+    const long long n = volume(trank, text);
+    if (trivial) return scaled_by_device_scalar(D, T, n, S, alpha, beta);
+    TempBlock tmp;
+    SIP_TRY(tmp.get(n));
+    SIP_TRY(permute_block(trank, text, transp, T, tmp.p));
+    return scaled_by_device_scalar(D, tmp.p, n, S, alpha, beta);
+}
+
+int contract_device(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                    const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    SIP_TRY(ensure_init());
+    if (!L || !R || !D || lrank < 0 || rrank < 0 || drank < 0 || lrank > 32 || rrank > 32 || drank > 32) return SIPGPU_E_ARG;
+    if (lrank == 0 || rrank == 0 || drank == 0)
+        return contract_degenerate(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+    ContractArgs a;
+    memset(&a, 0, sizeof(a));
+    SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &a.s0));
+    a.nprob = 1;
+    a.total_tiles = tiles_of(a.s0);
+    a.alpha = alpha;
+    a.beta = beta;
+    a.p0.L = L;
+    a.p0.R = R;
+    a.p0.D = D;
+    return launch_contract(a, a.s0.a_kc, a.s0.b_kc);
+}
+
+int contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                     const int* dext, const double* const* L, const double* const* R, double* const* D, double alpha,
+                     double beta) {
+    SIP_TRY(ensure_init());
+    if (n < 0 || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank)
+        return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    // distinct extent tuples -> Shapes (a pardo body has a handful of them: segment sizes are few)
+    std::map<std::vector<int>, int> shape_ids;
+    std::vector<Shape> shapes;
+    std::vector<int> pshape(n);
+    for (int i = 0; i < n; ++i) {
+        std::vector<int> key(lext + (size_t)i * lrank, lext + (size_t)(i + 1) * lrank);
+        key.insert(key.end(), rext + (size_t)i * rrank, rext + (size_t)(i + 1) * rrank);
+        key.insert(key.end(), dext + (size_t)i * drank, dext + (size_t)(i + 1) * drank);
+        auto it = shape_ids.find(key);
+        if (it == shape_ids.end()) {
+            Shape s;
+            SIP_TRY(build_shape(ptrn, lrank, lext + (size_t)i * lrank, rrank, rext + (size_t)i * rrank, drank,
+                                dext + (size_t)i * drank, &s));
+            it = shape_ids.emplace(key, (int)shapes.size()).first;
+            shapes.push_back(s);
+        }
+        pshape[i] = it->second;
+    }
+    for (int variant = 0; variant < 4; ++variant) {
+        const bool a_kc = variant & 1, b_kc = variant & 2;
+        std::vector<Problem> probs;
+        std::vector<int> prefix(1, 0);
+        for (int i = 0; i < n; ++i) {
+            const Shape& s = shapes[pshape[i]];
+            if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc) continue;
+            if (!L[i] || !R[i] || !D[i]) return SIPGPU_E_ARG;
+            probs.push_back(Problem{L[i], R[i], D[i], pshape[i], 0});
+            prefix.push_back(prefix.back() + tiles_of(s));
+        }
+        if (probs.empty()) continue;
+        const size_t b_probs = sizeof(Problem) * probs.size(), b_shapes = sizeof(Shape) * shapes.size(),
+                     b_prefix = sizeof(int) * prefix.size();
+        const size_t off_shapes = (b_probs + 255) & ~(size_t)255, off_prefix = off_shapes + ((b_shapes + 255) & ~(size_t)255);
+        void *h, *d;
+        SIP_TRY(scratch_reserve(off_prefix + b_prefix, &h, &d));
+        memcpy(h, probs.data(), b_probs);
+        memcpy((char*)h + off_shapes, shapes.data(), b_shapes);
+        memcpy((char*)h + off_prefix, prefix.data(), b_prefix);
+        SIP_CUDA(cudaMemcpyAsync(d, h, off_prefix + b_prefix, cudaMemcpyHostToDevice, ctx().stream));
+        ContractArgs a;
+        memset(&a, 0, sizeof(a));
+        a.probs = (const Problem*)d;
+        a.shapes = (const Shape*)((char*)d + off_shapes);
+        a.tile_prefix = (const int*)((char*)d + off_prefix);
+        a.nprob = (int)probs.size();
+        a.total_tiles = prefix.back();
+        a.alpha = alpha;
+        a.beta = beta;
+        SIP_TRY(launch_contract(a, a_kc, b_kc));
+    }
+    return SIPGPU_OK;
+}
+
+int labels_to_ptrn(int drank, const int* dlab, int lrank, const int* llab, int rrank, const int* rlab, int* ptrn) {
+    int aces[96], k = 0;
+    if (drank < 0 || lrank < 0 || rrank < 0 || drank + lrank + rrank > 96) return SIPGPU_E_ARG;
+    for (int i = 0; i < drank; ++i) aces[k++] = dlab[i];
+    for (int i = 0; i < lrank; ++i) aces[k++] = llab[i];
+    for (int i = 0; i < rrank; ++i) aces[k++] = rlab[i];
+    const int e = get_contraction_ptrn(drank, lrank, rrank, aces, ptrn);
+    if (e) {
+        set_error("illegal contraction label pattern (get_contraction_ptrn ierr=%d)", e);
+        return SIPGPU_E_PATTERN;
+    }
+    return SIPGPU_OK;
+}
+
+// host-pointer staging for boundary 1
+struct Staged {
+    double* d = nullptr;
+    long long n = 0;
+    ~Staged() { if (d) pool_free(d); }
+    int up(const double* h, long long n_) {
+        n = n_;
+        d = pool_alloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        if (!d) return SIPGPU_E_NOMEM;
+        if (h && n > 0) SIP_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx().stream));
+        return SIPGPU_OK;
+    }
+    int down(double* h) {
+        SIP_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
+        SIP_CUDA(cudaStreamSynchronize(ctx().stream));
+        return SIPGPU_OK;
+    }
+};
+
+}  // namespace
+}  // namespace sipgpu
+
+using namespace sipgpu;
+
+#define B1_TRY(call)                       \
+    do {                                   \
+        int rc__ = (call);                 \
+        if (rc__ != 0) { *ierr = rc__; return; } \
+    } while (0)
+
+extern "C" {
+
+// ------------------------------------------------ boundary 1 ------------------------------------------------
+long long tensor_size_by_shape_(int* num_dim, int* dims, int* ierr) {
+    long long sz = 1;
+    *ierr = 0;
+    if (*num_dim > 0) {
+        for (int i = 0; i < *num_dim; ++i) sz *= dims[i];
+        if (sz <= 0) *ierr = 2;
+    } else if (*num_dim < 0) {
+        *ierr = 1;
+        sz = 0;
+    }
+    return sz;
+}
+
+void get_contraction_ptrn_(int* drank, int* lrank, int* rrank, int* aces_ptrn, int* my_ptrn, int* ierr) {
+    *ierr = get_contraction_ptrn(*drank, *lrank, *rrank, aces_ptrn, my_ptrn);
+}
+
+void tensor_block_init__(int* nthreads, double* tens, int* rank, int* ext, double* val, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = -1; return; }
+    B1_TRY(ensure_init());
+    const long long n = volume(*rank, ext);
+    Staged t;
+    B1_TRY(t.up(nullptr, n));
+    B1_TRY(ew_fill(t.d, n, *val));
+    B1_TRY(t.down(tens));
+}
+
+void tensor_block_scale__(int* nthreads, double* tens, int* rank, int* ext, double* fac, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = -1; return; }
+    B1_TRY(ensure_init());
+    const long long n = volume(*rank, ext);
+    Staged t;
+    B1_TRY(t.up(tens, n));
+    B1_TRY(ew_scale(t.d, n, *fac));
+    B1_TRY(t.down(tens));
+}
+
+double tensor_block_norm2__(int* nthreads, double* tens, int* rank, int* ext, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = -1; return 0.0; }
+    if ((*ierr = ensure_init()) != 0) return 0.0;
+    const long long n = volume(*rank, ext);
+    Staged t;
+    if ((*ierr = t.up(tens, n)) != 0) return 0.0;
+    double r = 0.0;
+    *ierr = ew_dot(t.d, t.d, n, &r);
+    return r;
+}
+
+void tensor_block_slice__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice, int* slice_ext,
+                          int* ext_beg, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = 1; return; }
+    B1_TRY(ensure_init());
+    Staged t, s;
+    B1_TRY(t.up(tens, volume(*rank, tens_ext)));
+    B1_TRY(s.up(nullptr, volume(*rank, slice_ext)));
+    B1_TRY(ew_slice(*rank, t.d, tens_ext, s.d, slice_ext, ext_beg));
+    B1_TRY(s.down(slice));
+}
+
+void tensor_block_insert__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice, int* slice_ext,
+                           int* ext_beg, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = 1; return; }
+    B1_TRY(ensure_init());
+    Staged t, s;
+    B1_TRY(t.up(tens, volume(*rank, tens_ext)));
+    B1_TRY(s.up(slice, volume(*rank, slice_ext)));
+    B1_TRY(ew_insert(*rank, t.d, tens_ext, s.d, slice_ext, ext_beg));
+    B1_TRY(t.down(tens));
+}
+
+void tensor_block_add__(const int* nthreads, const int* rank, int* ext, double* tens0, double* tens1, const double* fac,
+                        int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = -1; return; }
+    B1_TRY(ensure_init());
+    const long long n = volume(*rank, ext);
+    Staged t0, t1;
+    B1_TRY(t0.up(tens0, n));
+    B1_TRY(t1.up(tens1, n));
+    B1_TRY(ew_axpy(t0.d, t1.d, n, *fac));
+    B1_TRY(t0.down(tens0));
+}
+
+void tensor_block_copy__(int* nthreads, int* rank, int* ext, int* dim_transp, double* tens_in, double* tens_out,
+                         int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*rank < 0) { *ierr = *rank; return; }
+    B1_TRY(ensure_init());
+    const long long n = volume(*rank, ext);
+    Staged in, out;
+    B1_TRY(in.up(tens_in, n));
+    B1_TRY(out.up(nullptr, n));
+    B1_TRY(permute_block(*rank, ext, dim_transp, in.d, out.d));
+    B1_TRY(out.down(tens_out));
+}
+
+void tensor_block_contract__(int* nthreads, int* contr_ptrn, double* ltens, int* lrank, int* lext, double* rtens,
+                             int* rrank, int* rext, double* dtens, int* drank, int* dext, int* ierr) {
+    (void)nthreads;
+    *ierr = 0;
+    if (*lrank < 0 || *rrank < 0 || *drank < 0 || *lrank > 32 || *rrank > 32 || *drank > 32) { *ierr = -1; return; }
+    B1_TRY(ensure_init());
+    if (!contr_ptrn_ok(contr_ptrn, *lrank, *rrank, *drank, lext, rext, dext)) { *ierr = 1; return; }
+    Staged l, r, d;
+    B1_TRY(l.up(ltens, volume(*lrank, lext)));
+    B1_TRY(r.up(rtens, volume(*rrank, rext)));
+    B1_TRY(d.up(nullptr, volume(*drank, dext)));
+    B1_TRY(contract_device(contr_ptrn, l.d, *lrank, lext, r.d, *rrank, rext, d.d, *drank, dext, 1.0, 0.0));
+    B1_TRY(d.down(dtens));
+}
+
+// ------------------------------------------------ boundary 2 ------------------------------------------------
+int _init_gpu(int* devid, int* my_rank) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available; libsipgpu has no CPU fallback");
+        return SIPGPU_E_NODEVICE;
+    }
+    const int dev = (my_rank ? *my_rank : 0) % ndev;  // the reference hard-codes rank 0 (interpreter.cpp:84-88)
+    SIP_TRY(sipgpu_init(dev));
+    if (devid) *devid = dev;
+    return SIPGPU_OK;
+}
+int _finalize_gpu(void) { return sipgpu_finalize(); }
+double* _gpu_allocate(const int n) { return sipgpu_block_alloc(n, 1); }
+int _gpu_free(double* g) { return pool_free(g); }
+int _gpu_host_to_device(double* c_addr, double* g_addr, const int n) { return sipgpu_h2d(g_addr, c_addr, n); }
+int _gpu_device_to_host(double* c_addr, double* g_addr, const int n) { return sipgpu_d2h(c_addr, g_addr, n); }
+int _gpu_device_to_device(double* dst, double* src, const int n) {
+    SIP_TRY(ensure_init());
+    if (n < 0) return SIPGPU_E_ARG;
+    SIP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx().stream));
+    return SIPGPU_OK;
+}
+int _gpu_double_memset(double* g, double value, const int n) { return ew_fill(g, n, value); }
+int _gpu_selfmultiply(double* x, const double alpha, const int n) { return ew_scale(x, n, alpha); }
+int _gpu_axpy(double* y, double* x, const double alpha, const int n) { return ew_axpy(y, x, n, alpha); }
+int _gpu_permute(double* y, const int ny, const int* y_dims, const int* y_inds, double* x, const int nx, const int* x_dims,
+                 const int* x_inds) {
+    (void)y_dims;
+    if (ny != nx) return SIPGPU_E_ARG;
+    return sipgpu_block_permute_labels(nx, x_dims, y_inds, x_inds, x, y);
+}
+int _gpu_contract(double* y, const int ny, const int* y_dims, const int* y_inds, double* x1, const int n1, const int* x1_dims,
+                  const int* x1_inds, double* x2, const int n2, const int* x2_dims, const int* x2_inds) {
+    return sipgpu_block_contract_labels(ny, y_dims, y_inds, y, n1, x1_dims, x1_inds, x1, n2, x2_dims, x2_inds, x2, 1.0, 0.0);
+}
+
+// ------------------------------------------------ boundary 3 ------------------------------------------------
+int sipgpu_block_fill(double* d, long long n, double v) { return ew_fill(d, n, v); }
+int sipgpu_block_scale(double* d, long long n, double f) { return ew_scale(d, n, f); }
+int sipgpu_block_scale_and_copy(double* d, const double* s, long long n, double f) { return ew_scale_copy(d, s, n, f); }
+int sipgpu_block_increment(double* d, long long n, double delta) { return ew_increment(d, n, delta); }
+int sipgpu_block_accumulate(double* d, const double* s, long long n) { return ew_axpy(d, s, n, 1.0); }
+int sipgpu_block_axpy(double* d, const double* s, long long n, double f) { return ew_axpy(d, s, n, f); }
+int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
+    return ew_add_sub(d, l, r, n, sign);
+}
+int sipgpu_block_norm2(const double* t, long long n, double* out) { return ew_dot(t, t, n, out); }
+int sipgpu_block_dot(const double* l, const double* r, long long n, double* out) { return ew_dot(l, r, n, out); }
+int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {
+    return ew_slice(rank, t, t_ext, s, s_ext, beg);
+}
+int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg) {
+    return ew_insert(rank, t, t_ext, s, s_ext, beg);
+}
+int sipgpu_block_permute(int rank, const int* ext, const int* transp, const double* in, double* out) {
+    return permute_block(rank, ext, transp, in, out);
+}
+int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels, const double* rhs,
+                                double* lhs) {
+    if (rank < 0 || rank > 32) return SIPGPU_E_ARG;
+    int transp[33];
+    SIP_TRY(permutation_from_labels(rank, lhs_labels, rhs_labels, transp));
+    return permute_block(rank, rhs_ext, transp, rhs, lhs);
+}
+int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                          const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    const int rc = contract_device(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+    if (rc == 1) {
+        set_error("invalid contraction pattern for these extents (contr_ptrn_ok)");
+        return SIPGPU_E_PATTERN;
+    }
+    return rc;
+}
+int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, double* D, int lrank, const int* lext,
+                                 const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
+                                 const double* R, double alpha, double beta) {
+    int ptrn[64];
+    SIP_TRY(labels_to_ptrn(drank, dlab, lrank, llab, rrank, rlab, ptrn));
+    return sipgpu_block_contract(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+}
+int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                            const int* dext, const double* const* L, const double* const* R, double* const* D,
+                            double alpha, double beta) {
+    const int rc = contract_batched(n, ptrn, lrank, rrank, drank, lext, rext, dext, L, R, D, alpha, beta);
+    return rc == 1 ? SIPGPU_E_PATTERN : rc;
+}
+
+int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
+                    double* C, int ldc) {
+    SIP_TRY(ensure_init());
+    if (m < 1 || n < 1 || k < 1 || lda < k || ldb < k || ldc < m || !A || !B || !C) return SIPGPU_E_ARG;
+    ContractArgs a;
+    memset(&a, 0, sizeof(a));
+    Shape& s = a.s0;
+    s.M = m; s.N = n; s.K = k;
+    s.nm = s.nn = s.nk = 1;
+    s.mext[0] = m; s.msL[0] = lda; s.msD[0] = 1;
+    s.next[0] = n; s.nsR[0] = ldb; s.nsD[0] = ldc;
+    s.kext[0] = k; s.ksL[0] = 1; s.ksR[0] = 1;
+    s.a_kc = s.b_kc = 1;
+    a.nprob = 1;
+    a.total_tiles = tiles_of(s);
+    a.alpha = alpha;
+    a.beta = beta;
+    a.p0.L = A; a.p0.R = B; a.p0.D = C;
+    return launch_contract(a, true, true);
+}
+
+// ---- host-only planner views (no device needed): used by the CPU tests of the host logic ----
+int sipgpu_debug_contract_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank,
+                                const int* dext, int* shape_ints /* sizeof(Shape)/4 */) {
+    Shape s;
+    const int rc = build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &s);
+    if (rc == 0) memcpy(shape_ints, &s, sizeof(s));
+    return rc;
+}
+int sipgpu_debug_shape_ints(void) { return (int)(sizeof(Shape) / sizeof(int)); }
+int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab, int cap) {
+    return sipgpu::permute_plan_debug(rank, ext, transp, meta, rtab, wtab, cap);
+}
+
+int sipgpu_dmma_peak_probe(int iters, double* tflops_out) {
+    SIP_TRY(ensure_init());
+    return dmma_probe(iters, tflops_out);
+}
+
+int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out) {
+    SIP_TRY(ensure_init());
+    Ctx& c = ctx();
+    const long long n = (long long)(bytes / 16) * 2;
+    double *a = nullptr, *b = nullptr;
+    SIP_CUDA(cudaMalloc(&a, n * 8));
+    SIP_CUDA(cudaMalloc(&b, n * 8));
+    SIP_CUDA(cudaMemsetAsync(a, 0, n * 8, c.stream));
+    cudaEvent_t e0, e1;
+    SIP_CUDA(cudaEventCreate(&e0));
+    SIP_CUDA(cudaEventCreate(&e1));
+    ew_copy_probe(b, a, n);
+    SIP_CUDA(cudaEventRecord(e0, c.stream));
+    for (int r = 0; r < reps; ++r) ew_copy_probe(b, a, n);
+    SIP_CUDA(cudaEventRecord(e1, c.stream));
+    SIP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SIP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs_out = 2.0 * n * 8 * reps / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    return SIPGPU_OK;
+}
+
+}  // extern "C"

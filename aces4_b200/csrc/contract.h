@@ -1,0 +1,24 @@
+// contract.h -- launch interface of the fused DMMA contraction kernel (contract.cu).
+#pragma once
+#include "plan.h"
+
+namespace sipgpu {
+
+struct ContractArgs {
+    const Problem* probs;    // device work-list, or nullptr: use the inline p0/s0 (single block, no upload)
+    const Shape* shapes;     // device
+    const int* tile_prefix;  // device, nprob+1 entries (exclusive prefix sum of tiles per block)
+    int nprob;
+    int total_tiles;
+    double alpha, beta;
+    Problem p0;
+    Shape s0;
+};
+
+// CTA tile of the kernel variant (for the host-side tile count)
+void contract_tile_dims(int variant, int* bm, int* bn);
+// variant = (a_kc, b_kc): which operand tiles are K-contiguous
+int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc);
+int dmma_probe(int iters, double* tflops);
+
+}  // namespace sipgpu

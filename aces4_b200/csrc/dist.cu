@@ -1,0 +1,184 @@
+// dist.cu -- distributed / served arrays over NVLink peer memory (boundary 4).
+//
+// Reference protocol being replaced: SialOpsParallel::get / put_replace / put_accumulate
+// (sial_ops_parallel.cpp:132-171,232-284,332-408) talk to dedicated single-threaded server ranks over MPI:
+// 3 messages + 2 acks per put, a temp buffer and a serial `data_[i] += to_add[i]` loop at the owner
+// (server_block.cpp:53-62).  Here there are no servers: every GPU owns the blocks whose number is
+// congruent to its rank (block-cyclic, data_distribution.cpp:74-82; numbering array_table.cpp:50-97, LAST
+// index fastest), keeps them resident in one HBM slab, and exports the slab through CUDA IPC.  A get is a
+// peer read, a put a peer write, and put += a red.global.add.f64 stream straight into the owner's HBM over
+// NVLink -- many writers are safe because the adds are atomic and commutative (the reference's arrival
+// order is non-deterministic too).  Section barriers are the caller's (stream sync + process barrier).
+#include <vector>
+
+#include "elementwise.h"
+
+struct sipgpu_array {
+    int rank = 0;
+    int my_rank = 0, world = 1;
+    int nseg[sipgpu::kMaxRank];
+    std::vector<int> seg_ext[sipgpu::kMaxRank];
+    long long slice[sipgpu::kMaxRank];  // block-number strides, last index fastest
+    long long nblocks = 0;
+    std::vector<long long> block_off;   // element offset of each block inside its owner's slab
+    std::vector<long long> slab_elems;  // per owner
+    std::vector<double*> base;          // per owner: slab base as mapped into this process
+    std::vector<char> opened;           // base[r] came from cudaIpcOpenMemHandle
+};
+
+using namespace sipgpu;
+
+namespace {
+constexpr long long kBlockAlign = 32;  // doubles (256 B): keeps every block 16-byte-vector and sector aligned
+
+int check_idx(const sipgpu_array* a, const int* idx) {
+    if (!a || !idx) return SIPGPU_E_ARG;
+    for (int i = 0; i < a->rank; ++i)
+        if (idx[i] < 1 || idx[i] > a->nseg[i]) return SIPGPU_E_ARG;
+    return SIPGPU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_rank, int world, sipgpu_array** out) {
+    if (rank < 1 || rank > kMaxRank || !nseg || !seg_ext || !out || world < 1 || my_rank < 0 || my_rank >= world)
+        return SIPGPU_E_ARG;
+    SIP_TRY(ensure_init());
+    sipgpu_array* a = new sipgpu_array();
+    a->rank = rank;
+    a->my_rank = my_rank;
+    a->world = world;
+    const int* e = seg_ext;
+    long long nb = 1;
+    for (int i = 0; i < rank; ++i) {
+        if (nseg[i] < 1) { delete a; return SIPGPU_E_ARG; }
+        a->nseg[i] = nseg[i];
+        a->seg_ext[i].assign(e, e + nseg[i]);
+        e += nseg[i];
+        nb *= nseg[i];
+    }
+    long long s = 1;
+    for (int p = rank - 1; p >= 0; --p) { a->slice[p] = s; s *= nseg[p]; }  // array_table.cpp:50-73
+    a->nblocks = nb;
+    a->block_off.resize(nb);
+    a->slab_elems.assign(world, 0);
+    for (long long b = 0; b < nb; ++b) {
+        long long rem = b, sz = 1;
+        for (int i = 0; i < rank; ++i) {  // num2id, array_table.cpp:83-97
+            const long long q = rem / a->slice[i];
+            sz *= a->seg_ext[i][q];
+            rem -= q * a->slice[i];
+        }
+        const int owner = (int)(b % world);
+        a->block_off[b] = a->slab_elems[owner];
+        a->slab_elems[owner] += (sz + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+    }
+    a->base.assign(world, nullptr);
+    a->opened.assign(world, 0);
+    const size_t bytes = sizeof(double) * (size_t)(a->slab_elems[my_rank] > 0 ? a->slab_elems[my_rank] : kBlockAlign);
+    void* p = nullptr;
+    // a dedicated cudaMalloc (not the pool): the IPC handle must name exactly this allocation
+    cudaError_t ce = cudaMalloc(&p, bytes);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        set_error("distributed array slab: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(ce));
+        delete a;
+        return SIPGPU_E_NOMEM;
+    }
+    a->base[my_rank] = (double*)p;
+    SIP_CUDA(cudaMemsetAsync(p, 0, bytes, ctx().stream));  // new server blocks are zero (disk_backed_block_map.cpp:150-183)
+    *out = a;
+    return SIPGPU_OK;
+}
+
+int sipgpu_array_destroy(sipgpu_array* a) {
+    if (!a) return SIPGPU_OK;
+    cudaStreamSynchronize(ctx().stream);
+    for (int r = 0; r < a->world; ++r) {
+        if (!a->base[r]) continue;
+        if (a->opened[r]) cudaIpcCloseMemHandle(a->base[r]);
+        else if (r == a->my_rank) cudaFree(a->base[r]);
+    }
+    delete a;
+    return SIPGPU_OK;
+}
+
+int sipgpu_array_export(sipgpu_array* a, void* handle_bytes) {
+    if (!a || !handle_bytes) return SIPGPU_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == SIPGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SIP_CUDA(cudaIpcGetMemHandle(&h, a->base[a->my_rank]));
+    memcpy(handle_bytes, &h, sizeof(h));
+    return SIPGPU_OK;
+}
+
+int sipgpu_array_attach(sipgpu_array* a, int peer_rank, const void* handle_bytes, int peer_device) {
+    if (!a || peer_rank < 0 || peer_rank >= a->world || !handle_bytes) return SIPGPU_E_ARG;
+    if (peer_rank == a->my_rank) return SIPGPU_OK;
+    (void)peer_device;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_bytes, sizeof(h));
+    void* p = nullptr;
+    SIP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    a->base[peer_rank] = (double*)p;
+    a->opened[peer_rank] = 1;
+    return SIPGPU_OK;
+}
+
+long long sipgpu_array_block_number(const sipgpu_array* a, const int* idx) {
+    if (check_idx(a, idx) != SIPGPU_OK) return -1;
+    long long b = 0;
+    for (int i = 0; i < a->rank; ++i) b += a->slice[i] * (idx[i] - 1);  // array_table.cpp:75-81 (lower = 1)
+    return b;
+}
+int sipgpu_array_block_owner(const sipgpu_array* a, long long b) {
+    if (!a || b < 0 || b >= a->nblocks) return -1;
+    return (int)(b % a->world);  // data_distribution.cpp:74-82
+}
+long long sipgpu_array_block_size(const sipgpu_array* a, const int* idx) {
+    if (check_idx(a, idx) != SIPGPU_OK) return -1;
+    long long sz = 1;
+    for (int i = 0; i < a->rank; ++i) sz *= a->seg_ext[i][idx[i] - 1];
+    return sz;
+}
+double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx) {
+    const long long b = sipgpu_array_block_number(a, idx);
+    if (b < 0) return nullptr;
+    double* base = a->base[b % a->world];
+    if (!base) {
+        set_error("distributed array: slab of rank %d is not attached", (int)(b % a->world));
+        return nullptr;
+    }
+    return base + a->block_off[b];
+}
+
+int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
+    double* src = sipgpu_array_block_ptr(a, idx);
+    if (!src || !g_dst) return src ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    const long long n = sipgpu_array_block_size(a, idx);
+    // peer read over NVLink when the owner is remote (UVA resolves the direction)
+    SIP_CUDA(cudaMemcpyAsync(g_dst, src, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx().stream));
+    return SIPGPU_OK;
+}
+int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
+    double* dst = sipgpu_array_block_ptr(a, idx);
+    if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    const long long n = sipgpu_array_block_size(a, idx);
+    SIP_CUDA(cudaMemcpyAsync(dst, g_src, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx().stream));
+    return SIPGPU_OK;
+}
+int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src) {
+    double* dst = sipgpu_array_block_ptr(a, idx);
+    if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
+}
+int sipgpu_array_fill_local(sipgpu_array* a, double v) {
+    if (!a) return SIPGPU_E_ARG;
+    return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
+}
+size_t sipgpu_array_local_bytes(const sipgpu_array* a) {
+    return a ? sizeof(double) * (size_t)a->slab_elems[a->my_rank] : 0;
+}
+
+}  // extern "C"

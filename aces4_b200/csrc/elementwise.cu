@@ -1,0 +1,230 @@
+// elementwise.cu -- HBM-bound block ops: the scalar loops of src/sip/dynamic_data/block.cpp:132-268,
+// interpreter.cpp:1874-1997 (block add/subtract) and tensor_dil_omp.F90:144-436 (init, scale, norm2,
+// slice, insert, add) as vectorised grid-stride kernels.  Algorithmic bytes: fill 8n, scale 16n,
+// scale_and_copy 16n, axpy/accumulate 24n, add_sub 24n, norm2 8n, dot 16n.
+#include "elementwise.h"
+
+namespace sipgpu {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long n_items) {
+    long long b = (n_items + kThreads - 1) / kThreads;
+    const long long cap = (long long)ctx().num_sms * 8;  // 8 resident CTAs of 256 threads per SM
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+enum Op { FILL, SCALE, SCALE_COPY, INCR, AXPY, ADDSUB };
+
+template <int OP>
+__device__ __forceinline__ double apply(double d, double a, double b, double f) {
+    if (OP == FILL) return f;
+    if (OP == SCALE) return d * f;
+    if (OP == SCALE_COPY) return a * f;
+    if (OP == INCR) return d + f;
+    if (OP == AXPY) return d + a * f;
+    return f > 0 ? a + b : a - b;  // ADDSUB: d = l +- r
+}
+
+// d[i] = op(d[i], a[i], b[i], f).  Main body in 16-byte vectors when all pointers are 16-byte aligned.
+template <int OP>
+__global__ void __launch_bounds__(kThreads) ew_kernel(double* __restrict__ d, const double* __restrict__ a,
+                                                      const double* __restrict__ b, long long n, double f, int vec) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    constexpr bool RD = (OP == SCALE || OP == INCR || OP == AXPY);
+    constexpr bool RA = (OP == SCALE_COPY || OP == AXPY || OP == ADDSUB);
+    constexpr bool RB = (OP == ADDSUB);
+    if (vec) {
+        const long long n2 = n >> 1;
+        double2* d2 = reinterpret_cast<double2*>(d);
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        const double2* b2 = reinterpret_cast<const double2*>(b);
+        for (long long i = tid; i < n2; i += nthr) {
+            double2 x = RD ? d2[i] : make_double2(0, 0);
+            double2 y = RA ? a2[i] : make_double2(0, 0);
+            double2 z = RB ? b2[i] : make_double2(0, 0);
+            d2[i] = make_double2(apply<OP>(x.x, y.x, z.x, f), apply<OP>(x.y, y.y, z.y, f));
+        }
+        if (tid == 0 && (n & 1)) {
+            const long long i = n - 1;
+            d[i] = apply<OP>(RD ? d[i] : 0.0, RA ? a[i] : 0.0, RB ? b[i] : 0.0, f);
+        }
+    } else {
+        for (long long i = tid; i < n; i += nthr)
+            d[i] = apply<OP>(RD ? d[i] : 0.0, RA ? a[i] : 0.0, RB ? b[i] : 0.0, f);
+    }
+}
+
+template <int OP>
+int run_ew(double* d, const double* a, const double* b, long long n, double f) {
+    if (n < 0 || !d) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    SIP_TRY(ensure_init());
+    const uintptr_t bits = (uintptr_t)d | (uintptr_t)a | (uintptr_t)b;
+    const int vec = (bits & 15) == 0;
+    ew_kernel<OP><<<grid_for(vec ? (n + 1) / 2 : n), kThreads, 0, ctx().stream>>>(d, a, b, n, f, vec);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+// two-stage deterministic reduction: sum_i a[i]*b[i]  (b == a gives norm2)
+__global__ void __launch_bounds__(kThreads) dot_partial_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                               long long n, double* __restrict__ partial) {
+    __shared__ double sm[kThreads / 32];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s += a[i] * b[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) t += sm[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void dot_final_kernel(const double* __restrict__ partial, int np, double* __restrict__ out, double prev_scale) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+        out[0] = prev_scale * out[0] + t;
+    }
+}
+
+// slice[idx] = tens[beg+idx] (GATHER) / tens[beg+idx] = slice[idx] (SCATTER): F90:271-392
+struct SliceArgs {
+    int rank;
+    int s_ext[kMaxRank];
+    int t_stride[kMaxRank];
+    long long t_base;
+    long long n;
+};
+template <bool GATHER>
+__global__ void __launch_bounds__(kThreads) slice_kernel(double* __restrict__ t, double* __restrict__ s,
+                                                         const __grid_constant__ SliceArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        long long lin = i, off = a.t_base;
+#pragma unroll 1
+        for (int d = 0; d < a.rank; ++d) {
+            const long long q = lin / a.s_ext[d];
+            off += (lin - q * a.s_ext[d]) * a.t_stride[d];
+            lin = q;
+        }
+        if (GATHER) s[i] = t[off]; else t[off] = s[i];
+    }
+}
+
+}  // namespace
+
+int ew_fill(double* d, long long n, double v) { return run_ew<FILL>(d, nullptr, nullptr, n, v); }
+int ew_scale(double* d, long long n, double f) { return run_ew<SCALE>(d, nullptr, nullptr, n, f); }
+int ew_scale_copy(double* d, const double* s, long long n, double f) { return run_ew<SCALE_COPY>(d, s, nullptr, n, f); }
+int ew_increment(double* d, long long n, double delta) { return run_ew<INCR>(d, nullptr, nullptr, n, delta); }
+int ew_axpy(double* d, const double* s, long long n, double f) { return run_ew<AXPY>(d, s, nullptr, n, f); }
+int ew_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
+    return run_ew<ADDSUB>(d, l, r, n, sign);
+}
+
+int ew_dot_device(const double* a, const double* b, long long n, double* d_out, double prev_scale) {
+    if (n < 0 || !a || !b) return SIPGPU_E_ARG;
+    SIP_TRY(ensure_init());
+    Ctx& c = ctx();
+    int np = grid_for(n);
+    if (np > 1024) np = 1024;
+    double* partial = c.d_reduce + 8;
+    dot_partial_kernel<<<np, kThreads, 0, c.stream>>>(a, b, n, partial);
+    dot_final_kernel<<<1, 256, 0, c.stream>>>(partial, np, d_out, prev_scale);
+    SIP_CUDA(cudaGetLastError());
+    count_launch(2);
+    return SIPGPU_OK;
+}
+
+int ew_dot(const double* a, const double* b, long long n, double* result_host) {
+    Ctx& c = ctx();
+    SIP_TRY(ensure_init());
+    SIP_TRY(ew_dot_device(a, b, n, c.d_reduce, 0.0));
+    SIP_CUDA(cudaMemcpyAsync(c.h_reduce, c.d_reduce, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    SIP_CUDA(cudaStreamSynchronize(c.stream));
+    *result_host = c.h_reduce[0];
+    return SIPGPU_OK;
+}
+
+static int slice_common(bool gather, int rank, double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {
+    if (rank < 0 || rank > 32 || !t || !s) return SIPGPU_E_ARG;
+    SIP_TRY(ensure_init());
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    long long stride = 1, n = 1, base = 0;
+    int r = 0;
+    for (int d = 0; d < rank; ++d) {
+        if (s_ext[d] <= 0 || beg[d] < 0 || beg[d] + s_ext[d] > t_ext[d]) return SIPGPU_E_ARG;
+        base += beg[d] * stride;
+        if (s_ext[d] != 1) {
+            if (r >= kMaxRank) return SIPGPU_E_ARG;
+            a.s_ext[r] = s_ext[d];
+            a.t_stride[r] = (int)stride;
+            ++r;
+        }
+        n *= s_ext[d];
+        stride *= t_ext[d];
+        if (stride >= (1LL << 31)) return SIPGPU_E_ARG;
+    }
+    a.rank = r;
+    a.t_base = base;
+    a.n = n;
+    if (gather)
+        slice_kernel<true><<<grid_for(n), kThreads, 0, ctx().stream>>>(t, s, a);
+    else
+        slice_kernel<false><<<grid_for(n), kThreads, 0, ctx().stream>>>(t, s, a);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+int ew_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {
+    return slice_common(true, rank, const_cast<double*>(t), t_ext, s, s_ext, beg);
+}
+int ew_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg) {
+    return slice_common(false, rank, t, t_ext, const_cast<double*>(s), s_ext, beg);
+}
+
+// d[i] += s[i] with red.global.add.f64: many-writer accumulate into a (possibly peer-mapped) owner block.
+__global__ void __launch_bounds__(kThreads) red_add_kernel(double* __restrict__ d, const double* __restrict__ s, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(s[i]) : "memory");
+}
+int ew_red_add(double* d, const double* s, long long n) {
+    if (n < 0 || !d || !s) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    SIP_TRY(ensure_init());
+    red_add_kernel<<<grid_for(n), kThreads, 0, ctx().stream>>>(d, s, n);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+// read+write copy for the bandwidth probe
+__global__ void __launch_bounds__(kThreads) copy_kernel(double2* __restrict__ d, const double2* __restrict__ s, long long n2) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+int ew_copy_probe(double* d, const double* s, long long n) {
+    copy_kernel<<<grid_for(n / 2), kThreads, 0, ctx().stream>>>((double2*)d, (const double2*)s, n / 2);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+}  // namespace sipgpu

@@ -1,0 +1,25 @@
+// elementwise.h -- launch interface of the HBM-bound block kernels (elementwise.cu).
+#pragma once
+#include "common.h"
+
+namespace sipgpu {
+
+int ew_fill(double* d, long long n, double v);
+int ew_scale(double* d, long long n, double f);
+int ew_scale_copy(double* d, const double* s, long long n, double f);
+int ew_increment(double* d, long long n, double delta);
+int ew_axpy(double* d, const double* s, long long n, double f);
+int ew_add_sub(double* d, const double* l, const double* r, long long n, double sign);
+int ew_dot(const double* a, const double* b, long long n, double* result_host);  // blocking
+// d_out[0] = prev_scale*d_out[0] + sum a*b, asynchronous (device result)
+int ew_dot_device(const double* a, const double* b, long long n, double* d_out, double prev_scale);
+int ew_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg);
+int ew_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg);
+int ew_red_add(double* d, const double* s, long long n);
+int ew_copy_probe(double* d, const double* s, long long n);
+
+// permute.cu
+int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out);
+int permute_plan_debug(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab, int cap);
+
+}  // namespace sipgpu

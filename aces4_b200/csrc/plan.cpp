@@ -1,0 +1,191 @@
+// plan.cpp -- host planner (see plan.h).  Pure integer work on <= 18 labels; runs on the calling thread.
+#include "plan.h"
+
+#include <algorithm>
+
+namespace sipgpu {
+
+int get_contraction_ptrn(int drank, int lrank, int rrank, const int* aces, int* my_ptrn) {
+    if (drank < 0 || lrank < 0 || rrank < 0) return 1;
+    const int m = lrank + rrank, n = drank + m;
+    if (n % 2 != 0) return 2;
+    if (m <= 0) return drank > 0 ? 3 : 0;
+    if (n > 3 * 32) return 1;
+    int pos[96];
+    for (int i = 0; i < n; ++i) pos[i] = i;
+    // stable order by label: equal labels keep D < L < R position order (what the reference's merge sort yields)
+    std::stable_sort(pos, pos + n, [&](int a, int b) { return aces[a] < aces[b]; });
+    for (int i = 0; i + 1 < n; i += 2) {  // every label exactly twice (F90:106-116)
+        if (aces[pos[i]] != aces[pos[i + 1]]) return 4;
+        if (i > 0 && aces[pos[i]] == aces[pos[i - 1]]) return 5;
+    }
+    for (int i = 0; i + 1 < n; i += 2) {  // F90:118-128
+        const int j = pos[i] + 1, k = pos[i + 1] + 1;  // 1-based, j < k
+        if (j <= drank && k > drank) {
+            my_ptrn[k - drank - 1] = j;  // free index: operand position -> destination position
+        } else if (j > drank && j <= drank + lrank && k > drank + lrank) {
+            my_ptrn[j - drank - 1] = -(k - (drank + lrank));  // contracted: L position <-> R position
+            my_ptrn[k - drank - 1] = -(j - drank);
+        } else {
+            return 6;
+        }
+    }
+    return 0;
+}
+
+bool contr_ptrn_ok(const int* p, int lr, int rr, int dr, const int* lext, const int* rext, const int* dext) {
+    int seen[3 * 32] = {0};
+    if (dr + lr + rr > 96) return false;
+    for (int j = 1; j <= lr; ++j) {
+        const int q = p[j - 1];
+        if (q > 0 && q <= dr) {
+            seen[q - 1]++, seen[dr + j - 1]++;
+            if (lext[j - 1] != dext[q - 1]) return false;
+        } else if (q < 0 && -q <= rr) {
+            seen[dr + lr - q - 1]++;
+            if (lext[j - 1] != rext[-q - 1]) return false;
+        } else {
+            return false;
+        }
+    }
+    for (int j = 1; j <= rr; ++j) {
+        const int q = p[lr + j - 1];
+        if (q > 0 && q <= dr) {
+            seen[q - 1]++, seen[dr + lr + j - 1]++;
+            if (rext[j - 1] != dext[q - 1]) return false;
+        } else if (q < 0 && -q <= lr) {
+            seen[dr - q - 1]++;
+            if (rext[j - 1] != lext[-q - 1]) return false;
+            if (p[-q - 1] != -j) return false;  // the two halves of a contracted pair must name each other
+        } else {
+            return false;
+        }
+    }
+    for (int i = 0; i < dr + lr + rr; ++i)
+        if (seen[i] != 1) return false;
+    return true;
+}
+
+namespace {
+struct Dim {
+    int ext, s0, s1;
+};
+
+// drop extent-1 dims, then merge neighbours that are contiguous in both tensors
+int tidy(Dim* d, int n) {
+    int w = 0;
+    for (int i = 0; i < n; ++i)
+        if (d[i].ext != 1) d[w++] = d[i];
+    n = w;
+    w = 0;
+    for (int i = 0; i < n; ++i) {
+        if (w > 0 && (long long)d[w - 1].s0 * d[w - 1].ext == d[i].s0 && (long long)d[w - 1].s1 * d[w - 1].ext == d[i].s1)
+            d[w - 1].ext *= d[i].ext;
+        else
+            d[w++] = d[i];
+    }
+    return w;
+}
+}  // namespace
+
+int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank, const int* dext,
+                Shape* out) {
+    if (lrank < 1 || rrank < 1 || drank < 1 || lrank > 32 || rrank > 32 || drank > 32) return SIPGPU_E_ARG;
+    if (!contr_ptrn_ok(ptrn, lrank, rrank, drank, lext, rext, dext)) return 1;
+    long long sL[32], sR[32], sD[32], s = 1;
+    for (int i = 0; i < lrank; ++i) { sL[i] = s; s *= lext[i]; }
+    if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
+    s = 1;
+    for (int i = 0; i < rrank; ++i) { sR[i] = s; s *= rext[i]; }
+    if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
+    s = 1;
+    for (int i = 0; i < drank; ++i) { sD[i] = s; s *= dext[i]; }
+    if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
+
+    Dim md[32], nd[32], kd[32];
+    int nm = 0, nn = 0, nk = 0;
+    long long M = 1, N = 1, K = 1;
+    for (int j = 0; j < lrank; ++j)
+        if (ptrn[j] > 0) { md[nm++] = {lext[j], (int)sL[j], (int)sD[ptrn[j] - 1]}; M *= lext[j]; }
+    for (int j = 0; j < rrank; ++j) {
+        const int q = ptrn[lrank + j];
+        if (q > 0) { nd[nn++] = {rext[j], (int)sR[j], (int)sD[q - 1]}; N *= rext[j]; }
+        else { kd[nk++] = {rext[j], (int)sL[-q - 1], (int)sR[j]}; K *= rext[j]; }
+    }
+    // Order of the contracted group is free (any order consistent between L and R gives the same sums up to
+    // rounding).  Put the stride-1 dimension of an operand first so that its K-runs are contiguous: R's if R's
+    // fastest (non-unit) dimension is contracted, else L's.  m and n groups already ascend in L / R stride.
+    auto min_stride = [](const Dim* d, int n, bool second) {
+        int best = INT32_MAX;
+        for (int i = 0; i < n; ++i)
+            if (d[i].ext != 1) best = std::min(best, second ? d[i].s1 : d[i].s0);
+        return best;
+    };
+    const int kminL = min_stride(kd, nk, false), kminR = min_stride(kd, nk, true);
+    const int mminL = min_stride(md, nm, false), nminR = min_stride(nd, nn, false);
+    const bool r_k_fast = kminR < nminR, l_k_fast = kminL < mminL;
+    if (!r_k_fast && l_k_fast)
+        std::stable_sort(kd, kd + nk, [](const Dim& a, const Dim& b) { return a.s0 < b.s0; });
+    nm = tidy(md, nm);
+    nn = tidy(nd, nn);
+    nk = tidy(kd, nk);
+    if (nm > kMaxRank || nn > kMaxRank || nk > kMaxRank) return SIPGPU_E_ARG;
+
+    Shape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.M = (int)M; sh.N = (int)N; sh.K = (int)K;
+    sh.nm = nm; sh.nn = nn; sh.nk = nk;
+    for (int i = 0; i < nm; ++i) { sh.mext[i] = md[i].ext; sh.msL[i] = md[i].s0; sh.msD[i] = md[i].s1; }
+    for (int i = 0; i < nn; ++i) { sh.next[i] = nd[i].ext; sh.nsR[i] = nd[i].s0; sh.nsD[i] = nd[i].s1; }
+    for (int i = 0; i < nk; ++i) { sh.kext[i] = kd[i].ext; sh.ksL[i] = kd[i].s0; sh.ksR[i] = kd[i].s1; }
+    sh.a_kc = (nk > 0 && sh.ksL[0] == 1) ? 1 : 0;
+    sh.b_kc = (nk > 0 && sh.ksR[0] == 1) ? 1 : 0;
+    *out = sh;
+    return 0;
+}
+
+int permutation_from_labels(int rank, const int* lhs_labels, const int* rhs_labels, int* transp) {
+    transp[0] = 1;
+    for (int i = 0; i < rank; ++i) {
+        int j = 0;
+        while (j < rank && rhs_labels[j] != lhs_labels[i]) ++j;
+        if (j >= rank) return SIPGPU_E_PATTERN;  // "illegal transpose" (interpreter.cpp:2049-2084)
+        transp[j + 1] = i + 1;
+    }
+    // each rhs dim must have received exactly one destination
+    int cnt[32] = {0};
+    for (int j = 0; j < rank; ++j) {
+        if (transp[j + 1] < 1 || transp[j + 1] > rank) return SIPGPU_E_PATTERN;
+        if (cnt[transp[j + 1] - 1]++) return SIPGPU_E_PATTERN;
+    }
+    return 0;
+}
+
+int build_perm_shape(int rank, const int* ext, const int* transp, PermShape* out) {
+    if (rank < 1 || rank > 32) return SIPGPU_E_ARG;
+    int oext[32];
+    bool used[32] = {false};
+    for (int i = 0; i < rank; ++i) {
+        const int np = transp[i + 1];
+        if (np < 1 || np > rank || used[np - 1] || ext[i] <= 0) return SIPGPU_E_ARG;
+        used[np - 1] = true;
+        oext[np - 1] = ext[i];
+    }
+    long long ostr[32], s = 1;
+    for (int i = 0; i < rank; ++i) { ostr[i] = s; s *= oext[i]; }
+    if (s >= (1LL << 31)) return SIPGPU_E_ARG;
+    Dim d[32];
+    long long is = 1;
+    for (int i = 0; i < rank; ++i) { d[i] = {ext[i], (int)is, (int)ostr[transp[i + 1] - 1]}; is *= ext[i]; }
+    int n = tidy(d, rank);
+    if (n > kMaxRank) return SIPGPU_E_ARG;
+    PermShape p;
+    memset(&p, 0, sizeof(p));
+    p.rank = n;
+    p.total = s;
+    for (int i = 0; i < n; ++i) { p.ext[i] = d[i].ext; p.in_stride[i] = d[i].s0; p.out_stride[i] = d[i].s1; }
+    *out = p;
+    return 0;
+}
+
+}  // namespace sipgpu

@@ -1,0 +1,193 @@
+/*
+ * sipgpu.h -- C ABI of libsipgpu.so: the B200 (sm_100a) block-tensor backend for the Aces4 SIP runtime.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, and NEVER calls exit(): failures are
+ * reported through `ierr` out-parameters (boundary 1) or int return codes (boundaries 2-4, 0 = success,
+ * see SIPGPU_E_*).  There is no CPU fallback anywhere behind this header: a call made without a usable
+ * CUDA device fails with SIPGPU_E_NODEVICE.
+ *
+ * Conventions (identical to the reference): FP64 elements, 32-bit extents, dense
+ * column-major blocks (first index fastest), rank <= SIPGPU_MAX_RANK, segment numbers 1-based.
+ *
+ * Paths cited below are relative to the reference checkout (UFParLab/aces4).
+ */
+#ifndef SIPGPU_H_
+#define SIPGPU_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIPGPU_MAX_RANK 6 /* src/sip/core/aces_defs.h:13 MAX_RANK */
+
+enum {
+    SIPGPU_OK = 0,
+    SIPGPU_E_NODEVICE = 100, /* no CUDA device / driver: the product path has no CPU fallback */
+    SIPGPU_E_CUDA = 101,     /* a CUDA runtime call failed; sipgpu_last_error() has the text */
+    SIPGPU_E_ARG = 102,      /* bad rank / extents / null pointer */
+    SIPGPU_E_PATTERN = 103,  /* illegal label pattern (label not exactly twice, trace, ...) */
+    SIPGPU_E_NOMEM = 104,    /* device pool exhausted */
+    SIPGPU_E_STATE = 105     /* library not initialised / wrong distributed-array section mode */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary 1 -- the libtensordil ABI (HOST pointers).  Same names, argument order and by-reference
+ * scalars as src/sip/tensor_algebra/tensor_ops_c_prototypes.h:41-178, so an unmodified aces4 links
+ * this library in place of tensor_dil_omp.F90.  Operands are staged to the device, the sm_100a
+ * kernels run, results are staged back; the call returns when the host buffers are valid.
+ * `nthreads` is accepted and ignored.  ierr: 0 = success, otherwise the reference's own codes where it
+ * defines them, else SIPGPU_E_*.
+ * --------------------------------------------------------------------------------------------- */
+long long tensor_size_by_shape_(int* num_dim, int* dims, int* ierr);           /* tensor_dil_omp.F90:65-85   */
+void get_contraction_ptrn_(int* drank, int* lrank, int* rrank, int* aces_ptrn, /* tensor_dil_omp.F90:87-142  */
+                           int* my_ptrn, int* ierr);
+void tensor_block_init__(int* nthreads, double* tens, int* rank, int* ext, double* val, int* ierr);   /* F90:144-191 */
+void tensor_block_scale__(int* nthreads, double* tens, int* rank, int* ext, double* fac, int* ierr);  /* F90:193-228 */
+double tensor_block_norm2__(int* nthreads, double* tens, int* rank, int* ext, int* ierr);             /* F90:230-269 */
+void tensor_block_slice__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice,       /* F90:271-330 */
+                          int* slice_ext, int* ext_beg, int* ierr);
+void tensor_block_insert__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice,      /* F90:332-392 */
+                           int* slice_ext, int* ext_beg, int* ierr);
+void tensor_block_add__(const int* nthreads, const int* rank, int* ext, double* tens0, double* tens1, /* F90:394-436 */
+                        const double* fac, int* ierr);
+void tensor_block_copy__(int* nthreads, int* rank, int* ext, int* dim_transp, double* tens_in,        /* F90:438-660 */
+                         double* tens_out, int* ierr);
+void tensor_block_contract__(int* nthreads, int* contr_ptrn, double* ltens, int* lrank, int* lext,    /* F90:662-796 */
+                             double* rtens, int* rrank, int* rext, double* dtens, int* drank, int* dext,
+                             int* ierr);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary 2 -- the device-block ABI (DEVICE pointers, resident blocks).  Same names and arguments as
+ * src/sip/cuda/gpu_super_instructions.h:26-126 (+ _finalize_gpu, gpu_super_instructions.cu:64-70), but
+ * extern "C", returning a status instead of void, backed by a slab pool instead of cudaMalloc per block,
+ * and asynchronous on the library's compute stream (ordering between calls is preserved; only
+ * _gpu_device_to_host blocks until the host buffer is valid).  _gpu_allocate returns NULL on failure.
+ * --------------------------------------------------------------------------------------------- */
+int _init_gpu(int* devid, int* my_rank);   /* device = *my_rank % device_count; *devid receives it */
+int _finalize_gpu(void);
+double* _gpu_allocate(const int num_elems);                               /* zero-filled, like the reference */
+int _gpu_free(double* g_addr);
+int _gpu_host_to_device(double* c_addr, double* g_addr, const int num_elems);
+int _gpu_device_to_host(double* c_addr, double* g_addr, const int num_elems);
+int _gpu_device_to_device(double* dst, double* src, const int num_elems);
+int _gpu_double_memset(double* g_addr, double value, const int num_elems);
+int _gpu_selfmultiply(double* x, const double alpha, const int num_elems); /* x *= alpha  */
+int _gpu_axpy(double* y, double* x, const double alpha, const int num_elems); /* y += alpha*x */
+int _gpu_permute(double* y, const int ny, const int* y_dims, const int* y_inds, /* y[y_inds] = x[x_inds] */
+                 double* x, const int nx, const int* x_dims, const int* x_inds);
+int _gpu_contract(double* y, const int ny, const int* y_dims, const int* y_inds, /* y = x1 * x2 (assign) */
+                  double* x1, const int n1, const int* x1_dims, const int* x1_inds,
+                  double* x2, const int n2, const int* x2_dims, const int* x2_inds);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary 3 -- resident / batched extension (what a device-aware SialOps or super-instruction calls).
+ * Blocks live in the device pool; ops are asynchronous on the compute stream.
+ * --------------------------------------------------------------------------------------------- */
+int sipgpu_init(int device);               /* idempotent; selects the device, creates streams + pool */
+int sipgpu_finalize(void);
+int sipgpu_device(void);                   /* current device ordinal or -1 */
+const char* sipgpu_last_error(void);
+int sipgpu_sync(void);                     /* wait for the compute stream */
+void* sipgpu_stream(void);                 /* cudaStream_t of the compute stream (for event timing) */
+long long sipgpu_kernel_launches(void);    /* number of sm_100a kernels this library has launched */
+
+/* pool (replaces _gpu_allocate's cudaMalloc per block and Block's `new double[]`, block.cpp:28-79) */
+int sipgpu_pool_reserve(size_t bytes);     /* pre-grow the arena */
+double* sipgpu_block_alloc(long long num_elems, int zero);
+int sipgpu_block_free(double* g_addr);
+int sipgpu_pool_stats(size_t* bytes_reserved, size_t* bytes_in_use, size_t* n_live_blocks);
+int sipgpu_h2d(double* g_dst, const double* h_src, long long n);   /* async when h_src is pinned */
+int sipgpu_d2h(double* h_dst, const double* g_src, long long n);   /* blocking */
+void* sipgpu_host_alloc(size_t bytes);     /* pinned host memory */
+int sipgpu_host_free(void* p);
+
+/* elementwise block ops of src/sip/dynamic_data/block.cpp:132-268 and interpreter.cpp:1874-1997 */
+int sipgpu_block_fill(double* d, long long n, double v);                          /* block.cpp:153-176 */
+int sipgpu_block_scale(double* d, long long n, double f);                         /* block.cpp:179-186 */
+int sipgpu_block_scale_and_copy(double* d, const double* s, long long n, double f); /* block.cpp:189-202 */
+int sipgpu_block_increment(double* d, long long n, double delta);                 /* block.cpp:206-213 */
+int sipgpu_block_accumulate(double* d, const double* s, long long n);             /* block.cpp:259-268 */
+int sipgpu_block_axpy(double* d, const double* s, long long n, double f);         /* F90:394-436      */
+int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign); /* interpreter.cpp:1929,1992 */
+int sipgpu_block_norm2(const double* t, long long n, double* result_host);        /* F90:230-269 (blocking) */
+int sipgpu_block_dot(const double* l, const double* r, long long n, double* result_host); /* F90:910-938 (blocking) */
+int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg);
+int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg);
+
+/* permute: out[new position of idx] = in[idx]; transp[0] = sign slot (ignored), transp[i] = NEW position
+ * (1-based) of OLD dimension i -- the "dmitry_permute" vector of block.cpp:227-231 / F90:438-660. */
+int sipgpu_block_permute(int rank, const int* ext, const int* transp, const double* in, double* out);
+/* lhs[lhs_labels] = rhs[rhs_labels]  (block_permute_op, interpreter.cpp:656-679, 2049-2084) */
+int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels,
+                                const double* rhs, double* lhs);
+
+/* contraction with the Lyakh pattern of get_contraction_ptrn_ (F90:662-796).  D = alpha*L*R + beta*D;
+ * the reference op is alpha = 1, beta = 0 (assign, F90:752).  beta != 0 is the fused-accumulate
+ * extension (contract followed by block_add / put +=). */
+int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                          const int* rext, double* D, int drank, const int* dext, double alpha, double beta);
+/* D[dlab] = L[llab] * R[rlab] by labels (handle_contraction, interpreter.cpp:1210-1262) */
+int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, double* D, int lrank, const int* lext,
+                                 const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
+                                 const double* R, double alpha, double beta);
+
+/* Batched contraction: n blocks in ONE launch per kernel variant.  All problems share rank/pattern
+ * (`ptrn`), extents may differ per problem: lext/rext/dext are [n][rank] row-major arrays; L/R/D are
+ * arrays of n device pointers; alpha/beta apply to all.  This is the pardo-body work-list entry point
+ * (block-sparse batching of many small blocks per launch). */
+int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                            const int* dext, const double* const* L, const double* const* R, double* const* D,
+                            double alpha, double beta);
+
+/* Raw strided-batched GEMM view of the contraction core, for micro-benchmarks of the DMMA kernel:
+ * C(m x n, col-major, ldc) = alpha * A^T * B + beta*C with A = [k x m] (lda), B = [k x n] (ldb): exactly the
+ * dgemm('T','N',...) of F90:762. */
+int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+                    double beta, double* C, int ldc);
+/* register-resident DMMA issue-rate probe: returns achieved TFLOP/s of mma.sync.m8n8k4.f64 on all SMs */
+int sipgpu_dmma_peak_probe(int iters, double* tflops_out);
+/* device copy bandwidth probe (GB/s, read+write) over a buffer of `bytes` */
+int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out);
+
+/* host-only views of the planner (no device needed; used by the CPU tests of the host logic) */
+int sipgpu_debug_contract_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank,
+                                const int* dext, int* shape_ints);
+int sipgpu_debug_shape_ints(void);
+int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab,
+                              int cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * Boundary 4 -- distributed / served arrays (SialOpsParallel method set, src/sip/worker/
+ * sial_ops_parallel.cpp:39-99,132-171,232-284,332-408,549-565; owner rule data_distribution.cpp:19-82 and
+ * array_table.cpp:50-97).  One process per GPU; every GPU is worker AND owner (no server ranks).  Each
+ * rank exports its slab of the array through CUDA IPC; peers map it and get / put / put+= go directly
+ * over NVLink (peer loads, peer stores, red.global.add.f64).  The bootstrap exchange of the IPC handles
+ * is done by the caller (torch.distributed / MPI): the library only produces and consumes opaque bytes.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sipgpu_array sipgpu_array; /* opaque */
+
+#define SIPGPU_IPC_HANDLE_BYTES 64
+
+/* nseg[rank]: number of segments per index; seg_ext: concatenated extents per index (sum nseg entries).
+ * Blocks are numbered as array_table.cpp:75-81 (LAST index fastest) and owned by block_number % world. */
+int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_rank, int world, sipgpu_array** out);
+int sipgpu_array_destroy(sipgpu_array* a);
+int sipgpu_array_export(sipgpu_array* a, void* handle_bytes /* SIPGPU_IPC_HANDLE_BYTES */);
+int sipgpu_array_attach(sipgpu_array* a, int peer_rank, const void* handle_bytes, int peer_device);
+long long sipgpu_array_block_number(const sipgpu_array* a, const int* idx /* 1-based segment numbers */);
+int sipgpu_array_block_owner(const sipgpu_array* a, long long block_number);
+long long sipgpu_array_block_size(const sipgpu_array* a, const int* idx);
+/* device address of block `idx` in its OWNER's slab as mapped into this process (peer memory when remote) */
+double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx);
+int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst);            /* SialOpsParallel::get            */
+int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src);      /* ::put_replace                   */
+int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src); /* ::put_accumulate (atomic)  */
+int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* put_initialize on owned blocks  */
+size_t sipgpu_array_local_bytes(const sipgpu_array* a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIPGPU_H_ */
