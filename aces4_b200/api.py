@@ -88,6 +88,8 @@ def lib():
                                                    C.c_double]
         L.sipgpu_contract_batched.argtypes = [C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.sipgpu_contract_chained.argtypes = [C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
+                                              c_int_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.sipgpu_dgemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_double, C.c_void_p, C.c_int]
         L.sipgpu_dmma_peak_probe.argtypes = [C.c_int, c_dbl_p]
@@ -405,8 +407,11 @@ def contract_batched(ptrn, Ls, Rs, Ds, alpha=1.0, beta=0.0):
 class BatchedContraction:
     """A prepared work-list (pointer and extent arrays marshalled once) that can be re-launched cheaply."""
 
-    def __init__(self, ptrn, lshapes, rshapes, dshapes, lptrs, rptrs, dptrs):
-        self.n = len(lptrs)
+    def __init__(self, ptrn, lshapes, rshapes, dshapes, lptrs, rptrs, dptrs, chain_start=None):
+        """Without chain_start: n independent blocks.  With chain_start (n+1 offsets into lptrs/rptrs): destination i
+        is the sum over the operand pairs chain_start[i]..chain_start[i+1]-1 (sipgpu_contract_chained)."""
+        self.n = len(dptrs)
+        self.chain = None if chain_start is None else np.ascontiguousarray(chain_start, dtype=np.int32)
         self.ptrn = _ia(ptrn)
         self.lrank, self.rrank, self.drank = len(lshapes[0]), len(rshapes[0]), len(dshapes[0])
         self.lext = np.ascontiguousarray(lshapes, dtype=np.int32)
@@ -415,6 +420,13 @@ class BatchedContraction:
         self.L, self.R, self.D = _ptr_array(lptrs), _ptr_array(rptrs), _ptr_array(dptrs)
 
     def launch(self, alpha=1.0, beta=0.0):
+        if self.chain is not None:
+            _check(lib().sipgpu_contract_chained(self.n, self.ptrn, self.lrank, self.rrank, self.drank,
+                                                 self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
+                                                 self.dext.ctypes.data_as(c_int_p), self.chain.ctypes.data_as(c_int_p),
+                                                 self.L, self.R, self.D, float(alpha), float(beta)),
+                   "sipgpu_contract_chained")
+            return
         _check(lib().sipgpu_contract_batched(self.n, self.ptrn, self.lrank, self.rrank, self.drank,
                                              self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
                                              self.dext.ctypes.data_as(c_int_p), self.L, self.R, self.D, float(alpha),

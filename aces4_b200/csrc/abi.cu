@@ -112,15 +112,17 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
     a.beta = beta;
-    a.p0.L = L;
-    a.p0.R = R;
+    a.pair0.L = L;
+    a.pair0.R = R;
     a.p0.D = D;
+    a.p0.chain_len = 1;
     return launch_contract(a, a.s0.a_kc, a.s0.b_kc);
 }
 
-int contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
-                     const int* dext, const double* const* L, const double* const* R, double* const* D, double alpha,
-                     double beta) {
+// n destination blocks; destination i sums the operand pairs chain_start[i] .. chain_start[i+1]-1 of L[]/R[].
+int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                     const int* dext, const int* chain_start, const double* const* L, const double* const* R,
+                     double* const* D, double alpha, double beta) {
     SIP_TRY(ensure_init());
     if (n < 0 || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank)
         return SIPGPU_E_ARG;
@@ -146,27 +148,36 @@ int contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, co
     for (int variant = 0; variant < 4; ++variant) {
         const bool a_kc = variant & 1, b_kc = variant & 2;
         std::vector<Problem> probs;
+        std::vector<Pair> pairs;
         std::vector<int> prefix(1, 0);
         for (int i = 0; i < n; ++i) {
             const Shape& s = shapes[pshape[i]];
             if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc) continue;
-            if (!L[i] || !R[i] || !D[i]) return SIPGPU_E_ARG;
-            probs.push_back(Problem{L[i], R[i], D[i], pshape[i], 0});
+            const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+            if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+            probs.push_back(Problem{D[i], pshape[i], (int)pairs.size(), c1 - c0, 0});
+            for (int c = c0; c < c1; ++c) {
+                if (!L[c] || !R[c]) return SIPGPU_E_ARG;
+                pairs.push_back(Pair{L[c], R[c]});
+            }
             prefix.push_back(prefix.back() + tiles_of(s));
         }
         if (probs.empty()) continue;
-        const size_t b_probs = sizeof(Problem) * probs.size(), b_shapes = sizeof(Shape) * shapes.size(),
-                     b_prefix = sizeof(int) * prefix.size();
-        const size_t off_shapes = (b_probs + 255) & ~(size_t)255, off_prefix = off_shapes + ((b_shapes + 255) & ~(size_t)255);
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_probs = sizeof(Problem) * probs.size(), b_pairs = sizeof(Pair) * pairs.size(),
+                     b_shapes = sizeof(Shape) * shapes.size(), b_prefix = sizeof(int) * prefix.size();
+        const size_t off_pairs = up(b_probs), off_shapes = off_pairs + up(b_pairs), off_prefix = off_shapes + up(b_shapes);
         void *h, *d;
         SIP_TRY(scratch_reserve(off_prefix + b_prefix, &h, &d));
         memcpy(h, probs.data(), b_probs);
+        memcpy((char*)h + off_pairs, pairs.data(), b_pairs);
         memcpy((char*)h + off_shapes, shapes.data(), b_shapes);
         memcpy((char*)h + off_prefix, prefix.data(), b_prefix);
         SIP_CUDA(cudaMemcpyAsync(d, h, off_prefix + b_prefix, cudaMemcpyHostToDevice, ctx().stream));
         ContractArgs a;
         memset(&a, 0, sizeof(a));
         a.probs = (const Problem*)d;
+        a.pairs = (const Pair*)((char*)d + off_pairs);
         a.shapes = (const Shape*)((char*)d + off_shapes);
         a.tile_prefix = (const int*)((char*)d + off_prefix);
         a.nprob = (int)probs.size();
@@ -433,7 +444,14 @@ int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, do
 int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                             const int* dext, const double* const* L, const double* const* R, double* const* D,
                             double alpha, double beta) {
-    const int rc = contract_batched(n, ptrn, lrank, rrank, drank, lext, rext, dext, L, R, D, alpha, beta);
+    const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, nullptr, L, R, D, alpha, beta);
+    return rc == 1 ? SIPGPU_E_PATTERN : rc;
+}
+int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                            const int* dext, const int* chain_start, const double* const* L, const double* const* R,
+                            double* const* D, double alpha, double beta) {
+    if (!chain_start) return SIPGPU_E_ARG;
+    const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, chain_start, L, R, D, alpha, beta);
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
 
@@ -454,7 +472,7 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
     a.total_tiles = tiles_of(s);
     a.alpha = alpha;
     a.beta = beta;
-    a.p0.L = A; a.p0.R = B; a.p0.D = C;
+    a.pair0.L = A; a.pair0.R = B; a.p0.D = C; a.p0.chain_len = 1;
     return launch_contract(a, true, true);
 }
 

@@ -15,7 +15,7 @@ namespace sipgpu {
 namespace {
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -58,35 +58,49 @@ struct Cfg {
     static constexpr bool A_KC = A_KC_, B_KC = B_KC_;
     static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = 16;
     static constexpr int NT = 32 * WARPS_M * WARPS_N;
+    static constexpr int KWIN = 2048;    // k offsets are tabulated for a window of this many contracted elements
     static constexpr int LDK = BK + 4;   // K-contiguous tile: [row][k], row stride 20 doubles (conflict-free frags)
     static constexpr int LDAM = BM + 4;  // M-contiguous tile: [k][m]
     static constexpr int LDBN = BN + 4;
     static constexpr int A_ELEMS = A_KC ? BM * LDK : BK * LDAM;
     static constexpr int B_ELEMS = B_KC ? BN * LDK : BK * LDBN;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 +
-                                   (size_t)STAGES * 2 * BK * 4;
+    // cp.async items per thread per stage (one 8-byte element each)
+    static constexpr int A_ITEMS = A_KC ? BM / (NT / BK) : BK / (NT / BM);
+    static constexpr int B_ITEMS = B_KC ? BN / (NT / BK) : BK / (NT / BN);
+    static constexpr int ITEMS = A_ITEMS + B_ITEMS;
+    static constexpr int MMA_GROUPS = (BK / 4) * MF;  // groups of NF DMMAs per stage
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)2 * KWIN * 4;
     static_assert(NT % BK == 0 && NT % BM == 0 && NT % BN == 0, "load mapping");
     static_assert(BM % (NT / BK) == 0 && BN % (NT / BK) == 0 && BK % (NT / BM) == 0 && BK % (NT / BN) == 0, "passes");
+    static_assert(ITEMS <= MMA_GROUPS, "one load item is issued after each group of DMMAs");
+    static_assert(KWIN % BK == 0, "window");
 };
 
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 contract_kernel(const __grid_constant__ ContractArgs args) {
     constexpr int BM = C::BM, BN = C::BN, BK = C::BK, NT = C::NT, STAGES = C::STAGES, MF = C::MF, NF = C::NF;
+    constexpr int KWIN = C::KWIN;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
     int* mOffL = reinterpret_cast<int*>(tiles + (size_t)STAGES * C::STAGE_ELEMS);
     int* mOffD = mOffL + BM;
     int* nOffR = mOffD + BM;
     int* nOffD = nOffR + BN;
-    int* kOffL = nOffD + BN;           // [STAGES][BK]
-    int* kOffR = kOffL + STAGES * BK;  // [STAGES][BK]
+    int* kOffL = nOffD + BN;  // [KWIN]
+    int* kOffR = kOffL + KWIN;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
     const int wm = (warp % C::WARPS_M) * (MF * 8), wn = (warp / C::WARPS_M) * (NF * 8);
     const double alpha = args.alpha, beta = args.beta;
+
+    // per-thread constants of the global->shared mapping
+    const int a_fix = C::A_KC ? tid % BK : tid % BM;  // the k lane (K-contiguous) or the m lane (M-contiguous)
+    const int a_var = C::A_KC ? tid / BK : tid / BM;  // first row / first k of the passes
+    const int b_fix = C::B_KC ? tid % BK : tid % BN;
+    const int b_var = C::B_KC ? tid / BK : tid / BN;
 
     for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
         // ---- which block of the work-list does this tile belong to? (uniform binary search) ----
@@ -101,15 +115,15 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
         }
         const Problem* pr = args.probs ? args.probs + p : &args.p0;
         const Shape* sh = args.probs ? args.shapes + pr->shape : &args.s0;
+        const Pair* chain = args.probs ? args.pairs + pr->chain_begin : &args.pair0;
+        const int chain_len = pr->chain_len;
         const int local = tile - (args.nprob > 1 ? __ldg(args.tile_prefix + p) : 0);
         const int M = sh->M, N = sh->N, K = sh->K;
         const int tiles_m = (M + BM - 1) / BM;
         const int m0 = (local % tiles_m) * BM, n0 = (local / tiles_m) * BN;
-        const double* __restrict__ Lp = pr->L;
-        const double* __restrict__ Rp = pr->R;
         double* __restrict__ Dp = pr->D;
         const int nk = sh->nk;
-        const int ksteps = (K + BK - 1) / BK;
+        const int nwin = (K + KWIN - 1) / KWIN;
 
         __syncthreads();  // previous tile fully consumed (tables + stages)
         // ---- offset tables: the input/output permutes of F90:731-743,782-785 as address arithmetic ----
@@ -128,64 +142,6 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 nOffD[j] = oD;
             }
         }
-        for (int i = tid; i < STAGES * BK; i += NT) {
-            const int k = i;  // steps 0..STAGES-1 occupy ring slots 0..STAGES-1
-            int oL = -1, oR = -1;
-            if (k < K) decompose2(k, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
-            kOffL[i] = oL;
-            kOffR[i] = oR;
-        }
-        __syncthreads();
-
-        auto load_stage = [&](int step, int slot) {
-            double* as = tiles + (size_t)slot * C::STAGE_ELEMS;
-            double* bs = as + C::A_ELEMS;
-            const int* kl_ = kOffL + slot * BK;
-            const int* kr_ = kOffR + slot * BK;
-            (void)step;
-            if constexpr (C::A_KC) {
-                const int kl = tid % BK, r0 = tid / BK;
-                const int ko = kl_[kl];
-#pragma unroll
-                for (int ps = 0; ps < BM / (NT / BK); ++ps) {
-                    const int row = r0 + ps * (NT / BK);
-                    const int mo = mOffL[row];
-                    const bool v = (mo | ko) >= 0;
-                    cp_async8(as + row * C::LDK + kl, Lp + (v ? mo + ko : 0), v);
-                }
-            } else {
-                const int ml = tid % BM, kk0 = tid / BM;
-                const int mo = mOffL[ml];
-#pragma unroll
-                for (int ps = 0; ps < BK / (NT / BM); ++ps) {
-                    const int kk = kk0 + ps * (NT / BM);
-                    const int ko = kl_[kk];
-                    const bool v = (mo | ko) >= 0;
-                    cp_async8(as + kk * C::LDAM + ml, Lp + (v ? mo + ko : 0), v);
-                }
-            }
-            if constexpr (C::B_KC) {
-                const int kl = tid % BK, r0 = tid / BK;
-                const int ko = kr_[kl];
-#pragma unroll
-                for (int ps = 0; ps < BN / (NT / BK); ++ps) {
-                    const int row = r0 + ps * (NT / BK);
-                    const int no = nOffR[row];
-                    const bool v = (no | ko) >= 0;
-                    cp_async8(bs + row * C::LDK + kl, Rp + (v ? no + ko : 0), v);
-                }
-            } else {
-                const int nl = tid % BN, kk0 = tid / BN;
-                const int no = nOffR[nl];
-#pragma unroll
-                for (int ps = 0; ps < BK / (NT / BN); ++ps) {
-                    const int kk = kk0 + ps * (NT / BN);
-                    const int ko = kr_[kk];
-                    const bool v = (no | ko) >= 0;
-                    cp_async8(bs + kk * C::LDBN + nl, Rp + (v ? no + ko : 0), v);
-                }
-            }
-        };
 
         double acc[MF][NF][2];
 #pragma unroll
@@ -193,47 +149,108 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
 #pragma unroll
             for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) {
-            if (s < ksteps) load_stage(s, s);
-            cp_async_commit();
-        }
+        for (int cp = 0; cp < chain_len; ++cp) {
+            const double* __restrict__ Lp = chain[cp].L;
+            const double* __restrict__ Rp = chain[cp].R;
+            for (int w = 0; w < nwin; ++w) {
+                const int kbase = w * KWIN;
+                const int kcount = min(KWIN, K - kbase);
+                const int ksteps = (kcount + BK - 1) / BK;
+                if (cp == 0 || nwin > 1) {
+                    // k offsets of this window (contracted-index permute as address arithmetic); -1 pads the tail
+                    if (cp > 0 || w > 0) __syncthreads();  // loads that read the previous window's table are issued
+                    for (int i = tid; i < ksteps * BK; i += NT) {
+                        int oL = -1, oR = -1;
+                        if (i < kcount) decompose2(kbase + i, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
+                        kOffL[i] = oL;
+                        kOffR[i] = oR;
+                    }
+                }
+                __syncthreads();  // tables visible; every warp is done with the stages of the previous pair/window
 
-        for (int j = 0; j < ksteps; ++j) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            const int jn = j + STAGES - 1;
-            if (jn < ksteps) load_stage(jn, jn % STAGES);
-            cp_async_commit();
-            // k offsets of step j+STAGES go to ring slot j%STAGES (its previous content, step j, was consumed by
-            // the loads issued STAGES-1 iterations ago); they are read after the next __syncthreads().
-            if (tid < BK) {
-                const int k = (j + STAGES) * BK + tid;
-                int oL = -1, oR = -1;
-                if (k < K) decompose2(k, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
-                kOffL[(j % STAGES) * BK + tid] = oL;
-                kOffR[(j % STAGES) * BK + tid] = oR;
-            }
-            const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
-            const double* bs = as + C::A_ELEMS;
+                // one 8-byte cp.async of stage `step` (item IT of C::ITEMS); zero-fills out-of-range elements
+                auto issue_item = [&](int it, int step, double* as, double* bs, int mo_fix, int no_fix) {
+                    const int kb = step * BK;
+                    if (it < C::A_ITEMS) {
+                        if constexpr (C::A_KC) {
+                            const int row = a_var + it * (NT / BK);
+                            const int ko = kOffL[kb + a_fix], mo = mOffL[row];
+                            const bool v = (mo | ko) >= 0;
+                            cp_async8(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
+                        } else {
+                            const int kk = a_var + it * (NT / BM);
+                            const int ko = kOffL[kb + kk];
+                            const bool v = (mo_fix | ko) >= 0;
+                            cp_async8(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
+                        }
+                    } else {
+                        const int ib = it - C::A_ITEMS;
+                        if constexpr (C::B_KC) {
+                            const int row = b_var + ib * (NT / BK);
+                            const int ko = kOffR[kb + b_fix], no = nOffR[row];
+                            const bool v = (no | ko) >= 0;
+                            cp_async8(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
+                        } else {
+                            const int kk = b_var + ib * (NT / BN);
+                            const int ko = kOffR[kb + kk];
+                            const bool v = (no_fix | ko) >= 0;
+                            cp_async8(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
+                        }
+                    }
+                };
+                const int mo_fix = C::A_KC ? 0 : mOffL[a_fix];
+                const int no_fix = C::B_KC ? 0 : nOffR[b_fix];
+
 #pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                double a[MF], b[NF];
+                for (int s = 0; s < STAGES - 1; ++s) {
+                    if (s < ksteps) {
+                        double* as = tiles + (size_t)s * C::STAGE_ELEMS;
 #pragma unroll
-                for (int mi = 0; mi < MF; ++mi)
-                    a[mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
-                                    : as[(kk * 4 + t4) * C::LDAM + wm + mi * 8 + g];
+                        for (int it = 0; it < C::ITEMS; ++it) issue_item(it, s, as, as + C::A_ELEMS, mo_fix, no_fix);
+                    }
+                    cp_async_commit();
+                }
+
+                for (int j = 0; j < ksteps; ++j) {
+                    cp_async_wait<STAGES - 2>();
+                    __syncthreads();
+                    const int jn = j + STAGES - 1;
+                    const bool do_load = jn < ksteps;
+                    double* ls = tiles + (size_t)(jn % STAGES) * C::STAGE_ELEMS;
+                    const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
+                    const double* bs = as + C::A_ELEMS;
+                    double a[2][MF], b[2][NF];
+                    auto load_frags = [&](int kk, int buf) {
 #pragma unroll
-                for (int ni = 0; ni < NF; ++ni)
-                    b[ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
-                                    : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
+                        for (int mi = 0; mi < MF; ++mi)
+                            a[buf][mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
+                                                 : as[(kk * 4 + t4) * C::LDAM + wm + mi * 8 + g];
 #pragma unroll
-                for (int mi = 0; mi < MF; ++mi)
+                        for (int ni = 0; ni < NF; ++ni)
+                            b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
+                                                 : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
+                    };
+                    load_frags(0, 0);
 #pragma unroll
-                    for (int ni = 0; ni < NF; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    for (int kk = 0; kk < BK / 4; ++kk) {
+                        if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
+#pragma unroll
+                        for (int mi = 0; mi < MF; ++mi) {
+#pragma unroll
+                            for (int ni = 0; ni < NF; ++ni)
+                                dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
+                            // the next stage's loads ride in the shadow of the DMMA pipe: one item per DMMA group
+                            constexpr int every = C::MMA_GROUPS / C::ITEMS;
+                            const int grp = kk * MF + mi;
+                            if (grp % every == 0 && grp / every < C::ITEMS && do_load)
+                                issue_item(grp / every, jn, ls, ls + C::A_ELEMS, mo_fix, no_fix);
+                        }
+                    }
+                    cp_async_commit();
+                }
+                cp_async_wait<0>();
             }
         }
-        cp_async_wait<0>();
 
         // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
 #pragma unroll

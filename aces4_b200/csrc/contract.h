@@ -5,13 +5,15 @@
 namespace sipgpu {
 
 struct ContractArgs {
-    const Problem* probs;    // device work-list, or nullptr: use the inline p0/s0 (single block, no upload)
+    const Problem* probs;    // device work-list, or nullptr: use the inline p0/pair0/s0 (single block, no upload)
+    const Pair* pairs;       // device
     const Shape* shapes;     // device
     const int* tile_prefix;  // device, nprob+1 entries (exclusive prefix sum of tiles per block)
     int nprob;
     int total_tiles;
     double alpha, beta;
     Problem p0;
+    Pair pair0;
     Shape s0;
 };
 

@@ -23,11 +23,20 @@ struct Shape {
     int a_kc, b_kc;  // operand's stride-1 dimension is contracted (K-contiguous) vs free (M/N-contiguous)
 };
 
-struct Problem {
+// One destination block and the chain of (L, R) operand pairs summed into it:
+//   D = alpha * sum_p L_p * R_p + beta * D        (all pairs share the Shape)
+// A chain is how a block-sparse contraction over a segmented contracted index reaches the kernel: the sum over
+// contracted SEGMENTS (the `do`-loop + `put +=` of a pardo body) runs inside one tile's accumulators, so the
+// destination is written once instead of read-modify-written once per segment.
+struct Pair {
     const double* L;
     const double* R;
+};
+struct Problem {
     double* D;
-    int shape;  // index into the launch's Shape array
+    int shape;        // index into the launch's Shape array
+    int chain_begin;  // first Pair of the chain
+    int chain_len;
     int pad;
 };
 

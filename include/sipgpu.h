@@ -141,6 +141,16 @@ int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int dr
                             const int* dext, const double* const* L, const double* const* R, double* const* D,
                             double alpha, double beta);
 
+/* Chained (block-sparse) contraction: destination i receives the SUM over the operand pairs
+ * chain_start[i] .. chain_start[i+1]-1 of L[]/R[] (all pairs of a destination share its extents):
+ *   D_i = alpha * sum_c L_c * R_c + beta * D_i.
+ * This is a pardo body of the form `do k: T = A[..k..]*B[..k..]; put D += T` (e.g. rlccd_rhf.sialx:342-355,
+ * 482-556) executed destination-stationary: the sum over contracted segments stays in the tile accumulators and
+ * every destination block is written once. */
+int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                            const int* dext, const int* chain_start, const double* const* L, const double* const* R,
+                            double* const* D, double alpha, double beta);
+
 /* Raw strided-batched GEMM view of the contraction core, for micro-benchmarks of the DMMA kernel:
  * C(m x n, col-major, ldc) = alpha * A^T * B + beta*C with A = [k x m] (lda), B = [k x n] (ldb): exactly the
  * dgemm('T','N',...) of F90:762. */

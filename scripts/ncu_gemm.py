@@ -1,0 +1,30 @@
+"""Tiny driver for ncu captures of the contraction kernel: a few launches of one shape."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import aces4_b200 as sip
+api = sip.api
+sip.init(0)
+mode = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+if mode == "gemm":
+    A, B, C = api.DeviceBlock((n, n)).fill(0.5), api.DeviceBlock((n, n)).fill(0.25), api.DeviceBlock((n, n))
+    for _ in range(3):
+        api.dgemm_tn(n, n, n, A, n, B, n, C, n)
+elif mode == "ring":
+    v, o = 50, 20
+    nb = n
+    Ls = [api.DeviceBlock((v, o, v, o)).fill(0.5) for _ in range(8)]
+    Rs = [api.DeviceBlock((v, o, v, o)).fill(0.25) for _ in range(8)]
+    Ds = [api.DeviceBlock((v, o, v, o)) for _ in range(nb)]
+    ptrn, _ = api.get_contraction_ptrn([1, 2, 3, 4], [1, 2, 5, 6], [5, 6, 3, 4])
+    bc = api.BatchedContraction(ptrn, [(v, o, v, o)] * nb, [(v, o, v, o)] * nb, [(v, o, v, o)] * nb,
+                                [Ls[i % 8].ptr for i in range(nb)], [Rs[(i * 3) % 8].ptr for i in range(nb)], [d.ptr for d in Ds])
+    for _ in range(3):
+        bc.launch()
+elif mode == "permute":
+    shape = (64, 64, 64, 64) if n >= 64 else (50, 20, 50, 20)
+    a, b = api.DeviceBlock(shape).fill(1.0), api.DeviceBlock(shape)
+    for transp in ([1, 3, 4, 1, 2], [1, 2, 1, 4, 3], [1, 4, 3, 2, 1]):
+        for _ in range(2):
+            api.permute(a, transp, out=b)
+sip.sync()

@@ -335,7 +335,54 @@ def test_batched_heterogeneous(sip, oracle):
         assert relerr(d.to_numpy(), 2.0 * ref) <= TOL
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (200, 77, 333), (1, 500, 64), (1000, 1000, 1000), (129, 257, 17)])
+def test_chained_block_sparse(sip, oracle):
+    # hh-ladder body (rlccd_rhf.sialx:342-355): T2new[a,i,b,j] += T2old[a,i1,b,j1] * V[i,i1,j,j1] summed over the
+    # (i1,j1) SEGMENTS inside one launch; ragged segment extents per destination
+    rng = np.random.default_rng(31)
+    pyrng = random.Random(31)
+    dlab, llab, rlab = [1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6]
+    ptrn, ierr = sip.get_contraction_ptrn(dlab, llab, rlab)
+    assert ierr == 0
+    lsh, rsh, dsh, lp, rp, dp, chain, refs, keep = [], [], [], [], [], [], [0], [], []
+    for dest in range(11):
+        e = {k: pyrng.choice([4, 6, 9, 16]) for k in range(1, 7)}
+        nchain = pyrng.randint(1, 5)
+        ref = np.zeros([e[x] for x in dlab], order="F")
+        for c in range(nchain):
+            L = rand_block(rng, tuple(e[x] for x in llab))
+            R = rand_block(rng, tuple(e[x] for x in rlab))
+            r1, oerr = oracle.contract_labels(dlab, [e[x] for x in dlab], llab, L, rlab, R)
+            assert oerr == 0
+            ref += r1
+            dl, dr = sip.DeviceBlock.from_numpy(L), sip.DeviceBlock.from_numpy(R)
+            keep += [dl, dr]
+            lp.append(dl.ptr), rp.append(dr.ptr)
+        chain.append(len(lp))
+        d = sip.DeviceBlock([e[x] for x in dlab])
+        keep.append(d)
+        dp.append(d)
+        lsh.append([e[x] for x in llab]), rsh.append([e[x] for x in rlab]), dsh.append([e[x] for x in dlab])
+        refs.append(ref)
+    bc = sip.BatchedContraction(ptrn, lsh, rsh, dsh, lp, rp, [d.ptr for d in dp], chain_start=chain)
+    bc.launch()
+    for d, ref in zip(dp, refs):
+        assert relerr(d.to_numpy(), ref) <= TOL
+    bc.launch(alpha=0.5, beta=1.0)
+    for d, ref in zip(dp, refs):
+        assert relerr(d.to_numpy(), 1.5 * ref) <= TOL
+
+
+def test_long_contracted_index_windows(sip):
+    # K larger than the kernel's k-offset window (2048): several windows per tile, ragged tail
+    rng = np.random.default_rng(41)
+    L = rand_block(rng, (70, 75, 9))    # [c1, c2, m]  K = 5250
+    R = rand_block(rng, (75, 11, 70))   # [c2, n, c1]
+    out = sip.contract_labels([3, 4], [9, 11], [1, 2, 3], sip.DeviceBlock.from_numpy(L), [2, 4, 1],
+                              sip.DeviceBlock.from_numpy(R)).to_numpy()
+    assert relerr(out, np.einsum("abm,bna->mn", L, R)) <= TOL
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (200, 77, 333), (1, 500, 64), (1000, 1000, 1000), (129, 257, 17), (64, 64, 5000)])
 def test_dgemm_tn_view(sip, m, n, k):
     rng = np.random.default_rng(m + n + k)
     A = rand_block(rng, (k, m))
