@@ -116,7 +116,8 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
     a.pair0.R = R;
     a.p0.D = D;
     a.p0.chain_len = 1;
-    return launch_contract(a, a.s0.a_kc, a.s0.b_kc);
+    const bool vec = a.s0.vec && (((uintptr_t)L | (uintptr_t)R) & 15) == 0;
+    return launch_contract(a, a.s0.a_kc, a.s0.b_kc, vec);
 }
 
 // n destination blocks; destination i sums the operand pairs chain_start[i] .. chain_start[i+1]-1 of L[]/R[].
@@ -145,8 +146,8 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         }
         pshape[i] = it->second;
     }
-    for (int variant = 0; variant < 4; ++variant) {
-        const bool a_kc = variant & 1, b_kc = variant & 2;
+    for (int variant = 0; variant < 8; ++variant) {
+        const bool a_kc = variant & 1, b_kc = variant & 2, vec = variant & 4;
         std::vector<Problem> probs;
         std::vector<Pair> pairs;
         std::vector<int> prefix(1, 0);
@@ -155,6 +156,9 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
             if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc) continue;
             const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
             if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+            bool pvec = s.vec != 0;
+            for (int c = c0; c < c1 && pvec; ++c) pvec = (((uintptr_t)L[c] | (uintptr_t)R[c]) & 15) == 0;
+            if (pvec != vec) continue;
             probs.push_back(Problem{D[i], pshape[i], (int)pairs.size(), c1 - c0, 0});
             for (int c = c0; c < c1; ++c) {
                 if (!L[c] || !R[c]) return SIPGPU_E_ARG;
@@ -184,7 +188,7 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         a.total_tiles = prefix.back();
         a.alpha = alpha;
         a.beta = beta;
-        SIP_TRY(launch_contract(a, a_kc, b_kc));
+        SIP_TRY(launch_contract(a, a_kc, b_kc, vec));
     }
     return SIPGPU_OK;
 }
@@ -473,7 +477,8 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
     a.alpha = alpha;
     a.beta = beta;
     a.pair0.L = A; a.pair0.R = B; a.p0.D = C; a.p0.chain_len = 1;
-    return launch_contract(a, true, true);
+    s.vec = (k % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) ? 1 : 0;
+    return launch_contract(a, true, true, s.vec != 0);
 }
 
 // ---- host-only planner views (no device needed): used by the CPU tests of the host logic ----

@@ -31,6 +31,10 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc,
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
 }
+template <bool VEC>
+__device__ __forceinline__ void cp_async_item(double* smem_dst, const double* gsrc, bool valid) {
+    if constexpr (VEC) cp_async16(smem_dst, gsrc, valid); else cp_async8(smem_dst, gsrc, valid);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -52,29 +56,33 @@ __device__ __forceinline__ void decompose2(int lin, int nd, const int* ext, cons
     }
 }
 
-template <int WARPS_M_, int WARPS_N_, int MF_, int NF_, int STAGES_, bool A_KC_, bool B_KC_>
+template <int WARPS_M_, int WARPS_N_, int MF_, int NF_, int BK_, int STAGES_, bool A_KC_, bool B_KC_, bool VEC_>
 struct Cfg {
     static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MF = MF_, NF = NF_, STAGES = STAGES_;
-    static constexpr bool A_KC = A_KC_, B_KC = B_KC_;
-    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = 16;
+    static constexpr bool A_KC = A_KC_, B_KC = B_KC_, VEC = VEC_;
+    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = BK_;
     static constexpr int NT = 32 * WARPS_M * WARPS_N;
     static constexpr int KWIN = 2048;    // k offsets are tabulated for a window of this many contracted elements
-    static constexpr int LDK = BK + 4;   // K-contiguous tile: [row][k], row stride 20 doubles (conflict-free frags)
+    static constexpr int LDK = BK + 4;   // K-contiguous tile: [row][k]; stride = 4 mod 16 doubles -> conflict-free frags
     static constexpr int LDAM = BM + 4;  // M-contiguous tile: [k][m]
     static constexpr int LDBN = BN + 4;
     static constexpr int A_ELEMS = A_KC ? BM * LDK : BK * LDAM;
     static constexpr int B_ELEMS = B_KC ? BN * LDK : BK * LDBN;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    // cp.async items per thread per stage (one 8-byte element each)
-    static constexpr int A_ITEMS = A_KC ? BM / (NT / BK) : BK / (NT / BM);
-    static constexpr int B_ITEMS = B_KC ? BN / (NT / BK) : BK / (NT / BN);
+    // global->shared mapping: each cp.async item moves V consecutive doubles (16 bytes when VEC) along the
+    // operand's contiguous direction; a thread keeps that lane fixed and walks the other direction in passes
+    static constexpr int V = VEC ? 2 : 1;
+    static constexpr int A_LANES = (A_KC ? BK : BM) / V, B_LANES = (B_KC ? BK : BN) / V;
+    static constexpr int A_ITEMS = (A_KC ? BM : BK) / (NT / A_LANES);
+    static constexpr int B_ITEMS = (B_KC ? BN : BK) / (NT / B_LANES);
     static constexpr int ITEMS = A_ITEMS + B_ITEMS;
     static constexpr int MMA_GROUPS = (BK / 4) * MF;  // groups of NF DMMAs per stage
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)2 * KWIN * 4;
-    static_assert(NT % BK == 0 && NT % BM == 0 && NT % BN == 0, "load mapping");
-    static_assert(BM % (NT / BK) == 0 && BN % (NT / BK) == 0 && BK % (NT / BM) == 0 && BK % (NT / BN) == 0, "passes");
-    static_assert(ITEMS <= MMA_GROUPS, "one load item is issued after each group of DMMAs");
-    static_assert(KWIN % BK == 0, "window");
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)4 * KWIN * 4;
+    static_assert(NT % A_LANES == 0 && NT % B_LANES == 0, "load mapping");
+    static_assert((A_KC ? BM : BK) % (NT / A_LANES) == 0 && (B_KC ? BN : BK) % (NT / B_LANES) == 0, "passes");
+    static_assert(ITEMS <= MMA_GROUPS && MMA_GROUPS % ITEMS == 0, "load items are spread evenly over the DMMA groups");
+    static_assert(KWIN % BK == 0 && LDK % 16 == 4 && LDAM % 16 == 4 && LDBN % 16 == 4, "window / bank layout");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 template <class C>
@@ -88,8 +96,8 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
     int* mOffD = mOffL + BM;
     int* nOffR = mOffD + BM;
     int* nOffD = nOffR + BN;
-    int* kOffL = nOffD + BN;  // [KWIN]
-    int* kOffR = kOffL + KWIN;
+    int* kOffL = nOffD + BN;  // [2][KWIN]: double-buffered by segment parity when K spans several windows
+    int* kOffR = kOffL + 2 * KWIN;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -97,10 +105,10 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
     const double alpha = args.alpha, beta = args.beta;
 
     // per-thread constants of the global->shared mapping
-    const int a_fix = C::A_KC ? tid % BK : tid % BM;  // the k lane (K-contiguous) or the m lane (M-contiguous)
-    const int a_var = C::A_KC ? tid / BK : tid / BM;  // first row / first k of the passes
-    const int b_fix = C::B_KC ? tid % BK : tid % BN;
-    const int b_var = C::B_KC ? tid / BK : tid / BN;
+    const int a_fix = (tid % C::A_LANES) * C::V;  // the k lane (K-contiguous) or the m lane (M-contiguous)
+    const int a_var = tid / C::A_LANES;           // first row / first k of the passes
+    const int b_fix = (tid % C::B_LANES) * C::V;
+    const int b_var = tid / C::B_LANES;
 
     for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
         // ---- which block of the work-list does this tile belong to? (uniform binary search) ----
@@ -149,108 +157,138 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
 #pragma unroll
             for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        for (int cp = 0; cp < chain_len; ++cp) {
-            const double* __restrict__ Lp = chain[cp].L;
-            const double* __restrict__ Rp = chain[cp].R;
-            for (int w = 0; w < nwin; ++w) {
-                const int kbase = w * KWIN;
-                const int kcount = min(KWIN, K - kbase);
-                const int ksteps = (kcount + BK - 1) / BK;
-                if (cp == 0 || nwin > 1) {
-                    // k offsets of this window (contracted-index permute as address arithmetic); -1 pads the tail
-                    if (cp > 0 || w > 0) __syncthreads();  // loads that read the previous window's table are issued
-                    for (int i = tid; i < ksteps * BK; i += NT) {
-                        int oL = -1, oR = -1;
-                        if (i < kcount) decompose2(kbase + i, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
-                        kOffL[i] = oL;
-                        kOffR[i] = oR;
-                    }
-                }
-                __syncthreads();  // tables visible; every warp is done with the stages of the previous pair/window
-
-                // one 8-byte cp.async of stage `step` (item IT of C::ITEMS); zero-fills out-of-range elements
-                auto issue_item = [&](int it, int step, double* as, double* bs, int mo_fix, int no_fix) {
-                    const int kb = step * BK;
-                    if (it < C::A_ITEMS) {
-                        if constexpr (C::A_KC) {
-                            const int row = a_var + it * (NT / BK);
-                            const int ko = kOffL[kb + a_fix], mo = mOffL[row];
-                            const bool v = (mo | ko) >= 0;
-                            cp_async8(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
-                        } else {
-                            const int kk = a_var + it * (NT / BM);
-                            const int ko = kOffL[kb + kk];
-                            const bool v = (mo_fix | ko) >= 0;
-                            cp_async8(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
-                        }
-                    } else {
-                        const int ib = it - C::A_ITEMS;
-                        if constexpr (C::B_KC) {
-                            const int row = b_var + ib * (NT / BK);
-                            const int ko = kOffR[kb + b_fix], no = nOffR[row];
-                            const bool v = (no | ko) >= 0;
-                            cp_async8(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
-                        } else {
-                            const int kk = b_var + ib * (NT / BN);
-                            const int ko = kOffR[kb + kk];
-                            const bool v = (no_fix | ko) >= 0;
-                            cp_async8(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
-                        }
-                    }
-                };
-                const int mo_fix = C::A_KC ? 0 : mOffL[a_fix];
-                const int no_fix = C::B_KC ? 0 : nOffR[b_fix];
-
-#pragma unroll
-                for (int s = 0; s < STAGES - 1; ++s) {
-                    if (s < ksteps) {
-                        double* as = tiles + (size_t)s * C::STAGE_ELEMS;
-#pragma unroll
-                        for (int it = 0; it < C::ITEMS; ++it) issue_item(it, s, as, as + C::A_ELEMS, mo_fix, no_fix);
-                    }
-                    cp_async_commit();
-                }
-
-                for (int j = 0; j < ksteps; ++j) {
-                    cp_async_wait<STAGES - 2>();
-                    __syncthreads();
-                    const int jn = j + STAGES - 1;
-                    const bool do_load = jn < ksteps;
-                    double* ls = tiles + (size_t)(jn % STAGES) * C::STAGE_ELEMS;
-                    const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
-                    const double* bs = as + C::A_ELEMS;
-                    double a[2][MF], b[2][NF];
-                    auto load_frags = [&](int kk, int buf) {
-#pragma unroll
-                        for (int mi = 0; mi < MF; ++mi)
-                            a[buf][mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
-                                                 : as[(kk * 4 + t4) * C::LDAM + wm + mi * 8 + g];
-#pragma unroll
-                        for (int ni = 0; ni < NF; ++ni)
-                            b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
-                                                 : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
-                    };
-                    load_frags(0, 0);
-#pragma unroll
-                    for (int kk = 0; kk < BK / 4; ++kk) {
-                        if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
-#pragma unroll
-                        for (int mi = 0; mi < MF; ++mi) {
-#pragma unroll
-                            for (int ni = 0; ni < NF; ++ni)
-                                dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
-                            // the next stage's loads ride in the shadow of the DMMA pipe: one item per DMMA group
-                            constexpr int every = C::MMA_GROUPS / C::ITEMS;
-                            const int grp = kk * MF + mi;
-                            if (grp % every == 0 && grp / every < C::ITEMS && do_load)
-                                issue_item(grp / every, jn, ls, ls + C::A_ELEMS, mo_fix, no_fix);
-                        }
-                    }
-                    cp_async_commit();
-                }
-                cp_async_wait<0>();
+        // ---- the K loop runs over SEGMENTS = (operand pair of the chain) x (k-offset window) as ONE software
+        // pipeline: stages keep flowing across pair boundaries, so a chain costs no drain/refill per block ----
+        const int nseg = chain_len * nwin;
+        const int last_steps = (K - (nwin - 1) * KWIN + BK - 1) / BK;
+        auto seg_steps = [&](int seg) { return (nwin == 1 || (seg % nwin) == nwin - 1) ? last_steps : KWIN / BK; };
+        const int total_steps = chain_len * ((nwin - 1) * (KWIN / BK) + last_steps);
+        // k offsets of one window (contracted-index permute as address arithmetic); -1 pads the ragged tail
+        auto fill_ktable = [&](int seg, int buf) {
+            const int kbase = (seg % nwin) * KWIN;
+            const int kcount = min(KWIN, K - kbase);
+            const int nfill = seg_steps(seg) * BK;
+            for (int i = tid; i < nfill; i += NT) {
+                int oL = -1, oR = -1;
+                if (i < kcount) decompose2(kbase + i, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
+                kOffL[buf * KWIN + i] = oL;
+                kOffR[buf * KWIN + i] = oR;
             }
+        };
+        fill_ktable(0, 0);
+        if (nwin > 1) fill_ktable(1, 1);  // nwin > 1 implies nseg > 1
+        __syncthreads();
+
+        const int mo_fix = C::A_KC ? 0 : mOffL[a_fix];
+        const int no_fix = C::B_KC ? 0 : nOffR[b_fix];
+
+        // load cursor: the (segment, step) whose tiles are fetched next
+        int l_seg = 0, l_ks = 0, l_steps = seg_steps(0);
+        const double* __restrict__ Lp = chain[0].L;
+        const double* __restrict__ Rp = chain[0].R;
+        const int* kl_tab = kOffL;
+        const int* kr_tab = kOffR;
+        auto advance_load_cursor = [&]() {
+            if (++l_ks == l_steps) {
+                l_ks = 0;
+                ++l_seg;
+                if (l_seg < nseg) {
+                    l_steps = seg_steps(l_seg);
+                    const Pair pq = chain[l_seg / nwin];
+                    Lp = pq.L;
+                    Rp = pq.R;
+                    if (nwin > 1) {
+                        kl_tab = kOffL + (l_seg & 1) * KWIN;
+                        kr_tab = kOffR + (l_seg & 1) * KWIN;
+                    }
+                }
+            }
+        };
+        // one cp.async (8 bytes, or 16 when VEC) of the load cursor's step: item `it` of C::ITEMS; out-of-range
+        // elements are zero-filled.  With VEC the host guarantees even extents/strides along the contiguous
+        // direction, so both doubles of an item are valid or invalid together and 16-byte aligned.
+        auto issue_item = [&](int it, double* as, double* bs) {
+            const int kb = l_ks * BK;
+            if (it < C::A_ITEMS) {
+                if constexpr (C::A_KC) {
+                    const int row = a_var + it * (NT / C::A_LANES);
+                    const int ko = kl_tab[kb + a_fix], mo = mOffL[row];
+                    const bool v = (mo | ko) >= 0;
+                    cp_async_item<C::VEC>(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
+                } else {
+                    const int kk = a_var + it * (NT / C::A_LANES);
+                    const int ko = kl_tab[kb + kk];
+                    const bool v = (mo_fix | ko) >= 0;
+                    cp_async_item<C::VEC>(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
+                }
+            } else {
+                const int ib = it - C::A_ITEMS;
+                if constexpr (C::B_KC) {
+                    const int row = b_var + ib * (NT / C::B_LANES);
+                    const int ko = kr_tab[kb + b_fix], no = nOffR[row];
+                    const bool v = (no | ko) >= 0;
+                    cp_async_item<C::VEC>(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
+                } else {
+                    const int kk = b_var + ib * (NT / C::B_LANES);
+                    const int ko = kr_tab[kb + kk];
+                    const bool v = (no_fix | ko) >= 0;
+                    cp_async_item<C::VEC>(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
+                }
+            }
+        };
+
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < total_steps) {
+                double* as = tiles + (size_t)s * C::STAGE_ELEMS;
+#pragma unroll
+                for (int it = 0; it < C::ITEMS; ++it) issue_item(it, as, as + C::A_ELEMS);
+                advance_load_cursor();
+            }
+            cp_async_commit();
         }
+
+        for (int j = 0; j < total_steps; ++j) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            const int jn = j + STAGES - 1;
+            const bool do_load = jn < total_steps;
+            // entering a new segment: the table of the segment after it can be built now -- the last loads that read
+            // that buffer (segment l_seg-1) were issued before the barrier above
+            if (nwin > 1 && do_load && l_ks == 0 && l_seg + 1 < nseg && j > 0) fill_ktable(l_seg + 1, (l_seg + 1) & 1);
+            double* ls = tiles + (size_t)(jn % STAGES) * C::STAGE_ELEMS;
+            const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
+            const double* bs = as + C::A_ELEMS;
+            double a[2][MF], b[2][NF];
+            auto load_frags = [&](int kk, int buf) {
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+                    a[buf][mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
+                                         : as[(kk * 4 + t4) * C::LDAM + wm + mi * 8 + g];
+#pragma unroll
+                for (int ni = 0; ni < NF; ++ni)
+                    b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
+                                         : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
+            };
+            load_frags(0, 0);
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi) {
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni)
+                        dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
+                    // the next stage's loads ride in the shadow of the DMMA pipe: one item per few DMMA groups
+                    constexpr int every = C::MMA_GROUPS / C::ITEMS;
+                    const int grp = kk * MF + mi;
+                    if (grp % every == 0 && grp / every < C::ITEMS && do_load) issue_item(grp / every, ls, ls + C::A_ELEMS);
+                }
+            }
+            cp_async_commit();
+            if (do_load) advance_load_cursor();
+        }
+        cp_async_wait<0>();
 
         // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
 #pragma unroll
@@ -296,12 +334,19 @@ void contract_tile_dims(int variant, int* bm, int* bn) {
     *bn = 128;
 }
 
-int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc) {
+int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec) {
     const int ctas = ctx().num_sms;
-    if (a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 4, true, true>>(a, ctas);
-    if (a_kc && !b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 4, true, false>>(a, ctas);
-    if (!a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 4, false, true>>(a, ctas);
-    return launch_cfg<Cfg<2, 4, 8, 4, 4, false, false>>(a, ctas);
+    // 128x128 CTA tile, 8 warps of 64x32, BK = 32 double-buffered (one barrier per 32 contracted elements)
+    if (vec) {
+        if (a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, true, true>>(a, ctas);
+        if (a_kc && !b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, false, true>>(a, ctas);
+        if (!a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, true, true>>(a, ctas);
+        return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, false, true>>(a, ctas);
+    }
+    if (a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, true, false>>(a, ctas);
+    if (a_kc && !b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, false, false>>(a, ctas);
+    if (!a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, true, false>>(a, ctas);
+    return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, false, false>>(a, ctas);
 }
 
 // ---------------- register-resident DMMA issue-rate probe (roofline denominator for the FP64 tensor pipe) ------

@@ -140,6 +140,12 @@ int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const in
     for (int i = 0; i < nk; ++i) { sh.kext[i] = kd[i].ext; sh.ksL[i] = kd[i].s0; sh.ksR[i] = kd[i].s1; }
     sh.a_kc = (nk > 0 && sh.ksL[0] == 1) ? 1 : 0;
     sh.b_kc = (nk > 0 && sh.ksR[0] == 1) ? 1 : 0;
+    // 16-byte fetches need the contiguous direction of each operand to be a unit-stride dimension of even extent:
+    // every other stride of that operand is then a multiple of it (even), so element pairs never straddle a
+    // dimension boundary and stay 16-byte aligned (given a 16-byte aligned block).
+    const bool a_vec = sh.a_kc ? (sh.kext[0] % 2 == 0) : (nm > 0 && sh.msL[0] == 1 && sh.mext[0] % 2 == 0);
+    const bool b_vec = sh.b_kc ? (sh.kext[0] % 2 == 0) : (nn > 0 && sh.nsR[0] == 1 && sh.next[0] % 2 == 0);
+    sh.vec = (a_vec && b_vec) ? 1 : 0;
     *out = sh;
     return 0;
 }

@@ -21,6 +21,8 @@ struct Shape {
     int next[kMaxRank], nsR[kMaxRank], nsD[kMaxRank];
     int kext[kMaxRank], ksL[kMaxRank], ksR[kMaxRank];
     int a_kc, b_kc;  // operand's stride-1 dimension is contracted (K-contiguous) vs free (M/N-contiguous)
+    int vec;         // both operands may be fetched as 16-byte pairs along their contiguous direction
+    int pad;
 };
 
 // One destination block and the chain of (L, R) operand pairs summed into it:

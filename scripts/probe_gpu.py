@@ -109,7 +109,17 @@ bc = api.BatchedContraction(ptrn, [(50, 20, 50, 20)] * n, [(50, 20, 50, 20)] * n
 ms = time_ms(lambda: bc.launch(), reps=3, warm=1)
 out["batched_ring_256x(1000^3)"] = {"ms": ms, "tflops": n * 2e9 / ms / 1e9}
 print("batched ring 256 blocks", out["batched_ring_256x(1000^3)"], flush=True)
-del Ls, Rs, Ds
+# chained: 148 destination blocks, each the sum of 12 operand pairs (ring term over 12 contracted segments)
+nd, cl = 148, 12
+Ds2 = Ds[:nd]
+chain = [i * cl for i in range(nd + 1)]
+bc2 = api.BatchedContraction(ptrn, [(50, 20, 50, 20)] * nd, [(50, 20, 50, 20)] * nd, [(50, 20, 50, 20)] * nd,
+                             [Ls[(i * 5) % 16].ptr for i in range(nd * cl)], [Rs[(i * 3) % 16].ptr for i in range(nd * cl)],
+                             [d.ptr for d in Ds2], chain_start=chain)
+ms = time_ms(lambda: bc2.launch(), reps=3, warm=1)
+out["chained_ring_148x12x(1000^3)"] = {"ms": ms, "tflops": nd * cl * 2e9 / ms / 1e9}
+print("chained ring 148 dest x 12 pairs", out["chained_ring_148x12x(1000^3)"], flush=True)
+del Ls, Rs, Ds, Ds2
 
 # permutes: all 24 patterns at (50,20,50,20) and 32^4, 64^4
 perm = {}
