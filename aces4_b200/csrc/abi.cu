@@ -44,7 +44,7 @@ struct TempBlock {  // pool block released at scope exit (stream order keeps it 
 
 int tiles_of(const Shape& s) {
     int bm, bn;
-    contract_tile_dims(0, &bm, &bn);
+    contract_tile_dims(s.tile, &bm, &bn);
     return ((s.M + bm - 1) / bm) * ((s.N + bn - 1) / bn);
 }
 
@@ -108,6 +108,7 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
     ContractArgs a;
     memset(&a, 0, sizeof(a));
     SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &a.s0));
+    a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
     a.nprob = 1;
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
@@ -117,7 +118,7 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
     a.p0.D = D;
     a.p0.chain_len = 1;
     const bool vec = a.s0.vec && (((uintptr_t)L | (uintptr_t)R) & 15) == 0;
-    return launch_contract(a, a.s0.a_kc, a.s0.b_kc, vec);
+    return launch_contract(a, a.s0.a_kc, a.s0.b_kc, vec, a.s0.tile);
 }
 
 // n destination blocks; destination i sums the operand pairs chain_start[i] .. chain_start[i+1]-1 of L[]/R[].
@@ -141,19 +142,21 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
             Shape s;
             SIP_TRY(build_shape(ptrn, lrank, lext + (size_t)i * lrank, rrank, rext + (size_t)i * rrank, drank,
                                 dext + (size_t)i * drank, &s));
+            s.tile = contract_pick_tile(s.M, s.N);
             it = shape_ids.emplace(key, (int)shapes.size()).first;
             shapes.push_back(s);
         }
         pshape[i] = it->second;
     }
-    for (int variant = 0; variant < 8; ++variant) {
+    for (int variant = 0; variant < 16; ++variant) {
         const bool a_kc = variant & 1, b_kc = variant & 2, vec = variant & 4;
+        const int tile = variant >> 3;
         std::vector<Problem> probs;
         std::vector<Pair> pairs;
         std::vector<int> prefix(1, 0);
         for (int i = 0; i < n; ++i) {
             const Shape& s = shapes[pshape[i]];
-            if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc) continue;
+            if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc || s.tile != tile) continue;
             const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
             if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
             bool pvec = s.vec != 0;
@@ -188,7 +191,7 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         a.total_tiles = prefix.back();
         a.alpha = alpha;
         a.beta = beta;
-        SIP_TRY(launch_contract(a, a_kc, b_kc, vec));
+        SIP_TRY(launch_contract(a, a_kc, b_kc, vec, tile));
     }
     return SIPGPU_OK;
 }
@@ -478,7 +481,9 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
     a.beta = beta;
     a.pair0.L = A; a.pair0.R = B; a.p0.D = C; a.p0.chain_len = 1;
     s.vec = (k % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) ? 1 : 0;
-    return launch_contract(a, true, true, s.vec != 0);
+    s.tile = contract_pick_tile(m, n);
+    a.total_tiles = tiles_of(s);
+    return launch_contract(a, true, true, s.vec != 0, s.tile);
 }
 
 // ---- host-only planner views (no device needed): used by the CPU tests of the host logic ----

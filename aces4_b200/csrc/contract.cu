@@ -72,15 +72,16 @@ struct Cfg {
     // global->shared mapping: each cp.async item moves V consecutive doubles (16 bytes when VEC) along the
     // operand's contiguous direction; a thread keeps that lane fixed and walks the other direction in passes
     static constexpr int V = VEC ? 2 : 1;
+    // LANES threads span the contiguous direction, PER = NT / LANES rows (or k's) are covered per pass; threads
+    // beyond PER*LANES idle (only when BN is not a divisor of NT, e.g. the 128x80 tile)
     static constexpr int A_LANES = (A_KC ? BK : BM) / V, B_LANES = (B_KC ? BK : BN) / V;
-    static constexpr int A_ITEMS = (A_KC ? BM : BK) / (NT / A_LANES);
-    static constexpr int B_ITEMS = (B_KC ? BN : BK) / (NT / B_LANES);
+    static constexpr int A_PER = NT / A_LANES, B_PER = NT / B_LANES;
+    static constexpr int A_ITEMS = ((A_KC ? BM : BK) + A_PER - 1) / A_PER;
+    static constexpr int B_ITEMS = ((B_KC ? BN : BK) + B_PER - 1) / B_PER;
     static constexpr int ITEMS = A_ITEMS + B_ITEMS;
     static constexpr int MMA_GROUPS = (BK / 4) * MF;  // groups of NF DMMAs per stage
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)4 * KWIN * 4;
-    static_assert(NT % A_LANES == 0 && NT % B_LANES == 0, "load mapping");
-    static_assert((A_KC ? BM : BK) % (NT / A_LANES) == 0 && (B_KC ? BN : BK) % (NT / B_LANES) == 0, "passes");
-    static_assert(ITEMS <= MMA_GROUPS && MMA_GROUPS % ITEMS == 0, "load items are spread evenly over the DMMA groups");
+    static_assert(A_PER >= 1 && B_PER >= 1, "load mapping");
     static_assert(KWIN % BK == 0 && LDK % 16 == 4 && LDAM % 16 == 4 && LDBN % 16 == 4, "window / bank layout");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -179,8 +180,8 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
         if (nwin > 1) fill_ktable(1, 1);  // nwin > 1 implies nseg > 1
         __syncthreads();
 
-        const int mo_fix = C::A_KC ? 0 : mOffL[a_fix];
-        const int no_fix = C::B_KC ? 0 : nOffR[b_fix];
+        const int mo_fix = (C::A_KC || a_var >= C::A_PER) ? 0 : mOffL[a_fix];
+        const int no_fix = (C::B_KC || b_var >= C::B_PER) ? 0 : nOffR[b_fix];
 
         // load cursor: the (segment, step) whose tiles are fetched next
         int l_seg = 0, l_ks = 0, l_steps = seg_steps(0);
@@ -211,28 +212,36 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
             const int kb = l_ks * BK;
             if (it < C::A_ITEMS) {
                 if constexpr (C::A_KC) {
-                    const int row = a_var + it * (NT / C::A_LANES);
-                    const int ko = kl_tab[kb + a_fix], mo = mOffL[row];
-                    const bool v = (mo | ko) >= 0;
-                    cp_async_item<C::VEC>(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
+                    const int row = a_var + it * C::A_PER;
+                    if ((BM % C::A_PER == 0 && NT % C::A_LANES == 0) || (row < BM && a_var < C::A_PER)) {
+                        const int ko = kl_tab[kb + a_fix], mo = mOffL[row];
+                        const bool v = (mo | ko) >= 0;
+                        cp_async_item<C::VEC>(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
+                    }
                 } else {
-                    const int kk = a_var + it * (NT / C::A_LANES);
-                    const int ko = kl_tab[kb + kk];
-                    const bool v = (mo_fix | ko) >= 0;
-                    cp_async_item<C::VEC>(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
+                    const int kk = a_var + it * C::A_PER;
+                    if ((BK % C::A_PER == 0 && NT % C::A_LANES == 0) || (kk < BK && a_var < C::A_PER)) {
+                        const int ko = kl_tab[kb + kk];
+                        const bool v = (mo_fix | ko) >= 0;
+                        cp_async_item<C::VEC>(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
+                    }
                 }
             } else {
                 const int ib = it - C::A_ITEMS;
                 if constexpr (C::B_KC) {
-                    const int row = b_var + ib * (NT / C::B_LANES);
-                    const int ko = kr_tab[kb + b_fix], no = nOffR[row];
-                    const bool v = (no | ko) >= 0;
-                    cp_async_item<C::VEC>(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
+                    const int row = b_var + ib * C::B_PER;
+                    if ((BN % C::B_PER == 0 && NT % C::B_LANES == 0) || (row < BN && b_var < C::B_PER)) {
+                        const int ko = kr_tab[kb + b_fix], no = nOffR[row];
+                        const bool v = (no | ko) >= 0;
+                        cp_async_item<C::VEC>(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
+                    }
                 } else {
-                    const int kk = b_var + ib * (NT / C::B_LANES);
-                    const int ko = kr_tab[kb + kk];
-                    const bool v = (no_fix | ko) >= 0;
-                    cp_async_item<C::VEC>(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
+                    const int kk = b_var + ib * C::B_PER;
+                    if ((BK % C::B_PER == 0 && NT % C::B_LANES == 0) || (kk < BK && b_var < C::B_PER)) {
+                        const int ko = kr_tab[kb + kk];
+                        const bool v = (no_fix | ko) >= 0;
+                        cp_async_item<C::VEC>(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
+                    }
                 }
             }
         };
@@ -280,9 +289,12 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                     for (int ni = 0; ni < NF; ++ni)
                         dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
                     // the next stage's loads ride in the shadow of the DMMA pipe: one item per few DMMA groups
-                    constexpr int every = C::MMA_GROUPS / C::ITEMS;
                     const int grp = kk * MF + mi;
-                    if (grp % every == 0 && grp / every < C::ITEMS && do_load) issue_item(grp / every, ls, ls + C::A_ELEMS);
+                    if (do_load) {
+#pragma unroll
+                        for (int it = grp * C::ITEMS / C::MMA_GROUPS; it < (grp + 1) * C::ITEMS / C::MMA_GROUPS; ++it)
+                            issue_item(it, ls, ls + C::A_ELEMS);
+                    }
                 }
             }
             cp_async_commit();
@@ -328,25 +340,42 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
 
 }  // namespace
 
-void contract_tile_dims(int variant, int* bm, int* bn) {
-    (void)variant;
+// Tile menu: 0 = 128x128 (8 warps of 64x32), 1 = 128x80 (8 warps of 32x40: N = 400 = o*o segments tile exactly)
+void contract_tile_dims(int tile, int* bm, int* bn) {
     *bm = 128;
-    *bn = 128;
+    *bn = tile == 1 ? 80 : 128;
+}
+int contract_pick_tile(int M, int N) {
+    long long best = -1;
+    int pick = 0;
+    for (int t = 0; t < 2; ++t) {
+        int bm, bn;
+        contract_tile_dims(t, &bm, &bn);
+        const long long padded = (long long)((M + bm - 1) / bm) * bm * (long long)((N + bn - 1) / bn) * bn;
+        if (best < 0 || padded < best) { best = padded; pick = t; }  // ties keep the larger tile (listed first)
+    }
+    return pick;
 }
 
-int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec) {
-    const int ctas = ctx().num_sms;
-    // 128x128 CTA tile, 8 warps of 64x32, BK = 32 double-buffered (one barrier per 32 contracted elements)
+template <int WM, int WN, int MF, int NF>
+int launch_tile(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int ctas) {
     if (vec) {
-        if (a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, true, true>>(a, ctas);
-        if (a_kc && !b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, false, true>>(a, ctas);
-        if (!a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, true, true>>(a, ctas);
-        return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, false, true>>(a, ctas);
+        if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, true, true>>(a, ctas);
+        if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, false, true>>(a, ctas);
+        if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, true, true>>(a, ctas);
+        return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, false, true>>(a, ctas);
     }
-    if (a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, true, false>>(a, ctas);
-    if (a_kc && !b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, true, false, false>>(a, ctas);
-    if (!a_kc && b_kc) return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, true, false>>(a, ctas);
-    return launch_cfg<Cfg<2, 4, 8, 4, 32, 2, false, false, false>>(a, ctas);
+    if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, true, false>>(a, ctas);
+    if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, false, false>>(a, ctas);
+    if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, true, false>>(a, ctas);
+    return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, false, false>>(a, ctas);
+}
+
+int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile) {
+    const int ctas = ctx().num_sms;
+    // BK = 32 double-buffered (one barrier per 32 contracted elements)
+    if (tile == 1) return launch_tile<4, 2, 4, 5>(a, a_kc, b_kc, vec, ctas);
+    return launch_tile<2, 4, 8, 4>(a, a_kc, b_kc, vec, ctas);
 }
 
 // ---------------- register-resident DMMA issue-rate probe (roofline denominator for the FP64 tensor pipe) ------

@@ -18,10 +18,11 @@ struct ContractArgs {
 };
 
 // CTA tile of the kernel variant (for the host-side tile count)
-void contract_tile_dims(int variant, int* bm, int* bn);
+void contract_tile_dims(int tile, int* bm, int* bn);
 // variant = (a_kc, b_kc): which operand tiles are K-contiguous; vec: 16-byte cp.async (Shape::vec and 16-byte
 // aligned operand pointers)
-int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec);
+int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile);
+int contract_pick_tile(int M, int N);
 int dmma_probe(int iters, double* tflops);
 
 }  // namespace sipgpu

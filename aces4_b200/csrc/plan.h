@@ -22,7 +22,7 @@ struct Shape {
     int kext[kMaxRank], ksL[kMaxRank], ksR[kMaxRank];
     int a_kc, b_kc;  // operand's stride-1 dimension is contracted (K-contiguous) vs free (M/N-contiguous)
     int vec;         // both operands may be fetched as 16-byte pairs along their contiguous direction
-    int pad;
+    int tile;        // CTA tile of the kernel menu (contract_pick_tile), set by the launcher
 };
 
 // One destination block and the chain of (L, R) operand pairs summed into it:

@@ -120,6 +120,31 @@ ms = time_ms(lambda: bc2.launch(), reps=3, warm=1)
 out["chained_ring_148x12x(1000^3)"] = {"ms": ms, "tflops": nd * cl * 2e9 / ms / 1e9}
 print("chained ring 148 dest x 12 pairs", out["chained_ring_148x12x(1000^3)"], flush=True)
 del Ls, Rs, Ds, Ds2
+# pp-ladder stand-in: Y[mu,i,nu,j] = sum_{lambda,sigma segs} aoint[lambda,mu,sigma,nu] * T[lambda,i,sigma,j]
+# (M = 2500, N = 400, K = 2500 per pair): 74 destinations x 6 pairs
+nd, cl = 74, 6
+ao = [api.DeviceBlock((50, 50, 50, 50)).fill(0.5) for _ in range(4)]
+tt = [api.DeviceBlock((50, 20, 50, 20)).fill(0.25) for _ in range(8)]
+yy = [api.DeviceBlock((50, 20, 50, 20)) for _ in range(nd)]
+ptrn_pp, _ = api.get_contraction_ptrn([1, 2, 3, 4], [5, 1, 6, 3], [5, 2, 6, 4])
+bc3 = api.BatchedContraction(ptrn_pp, [(50, 50, 50, 50)] * nd, [(50, 20, 50, 20)] * nd, [(50, 20, 50, 20)] * nd,
+                             [ao[(i * 3) % 4].ptr for i in range(nd * cl)], [tt[(i * 5) % 8].ptr for i in range(nd * cl)],
+                             [d.ptr for d in yy], chain_start=[i * cl for i in range(nd + 1)])
+ms = time_ms(lambda: bc3.launch(), reps=3, warm=1)
+out["chained_ppladder_74x6x(2500x400x2500)"] = {"ms": ms, "tflops": nd * cl * 2.0 * 2500 * 400 * 2500 / ms / 1e9}
+print("chained pp ladder", out["chained_ppladder_74x6x(2500x400x2500)"], flush=True)
+# hh ladder: M = 2500, N = 400, K = 400 per pair, 9 pairs
+nd, cl = 296, 9
+vo = [api.DeviceBlock((20, 20, 20, 20)).fill(0.5) for _ in range(9)]
+ptrn_hh, _ = api.get_contraction_ptrn([1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6])
+yy2 = [api.DeviceBlock((50, 20, 50, 20)) for _ in range(nd)]
+bc4 = api.BatchedContraction(ptrn_hh, [(50, 20, 50, 20)] * nd, [(20, 20, 20, 20)] * nd, [(50, 20, 50, 20)] * nd,
+                             [tt[(i * 5) % 8].ptr for i in range(nd * cl)], [vo[i % 9].ptr for i in range(nd * cl)],
+                             [d.ptr for d in yy2], chain_start=[i * cl for i in range(nd + 1)])
+ms = time_ms(lambda: bc4.launch(), reps=3, warm=1)
+out["chained_hhladder_296x9x(2500x400x400)"] = {"ms": ms, "tflops": nd * cl * 2.0 * 2500 * 400 * 400 / ms / 1e9}
+print("chained hh ladder", out["chained_hhladder_296x9x(2500x400x400)"], flush=True)
+del ao, tt, yy, yy2, vo
 
 # permutes: all 24 patterns at (50,20,50,20) and 32^4, 64^4
 perm = {}
