@@ -75,6 +75,13 @@ def lib():
         L.sipgpu_block_axpy.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]
         L.sipgpu_block_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
         L.sipgpu_block_add_sub.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double]
+        L.sipgpu_block_fill_hash.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_ulonglong, C.c_double]
+        L.sipgpu_block_dot_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.sipgpu_layout_block_number.argtypes = [C.c_int, c_int_p, c_int_p]
+        L.sipgpu_layout_block_number.restype = C.c_longlong
+        L.sipgpu_layout_block_owner.argtypes = [C.c_longlong, C.c_int]
+        L.sipgpu_array_local_base.argtypes = [C.c_void_p]
+        L.sipgpu_array_local_base.restype = C.c_void_p
         L.sipgpu_block_norm2.argtypes = [C.c_void_p, C.c_longlong, c_dbl_p]
         L.sipgpu_block_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, c_dbl_p]
         L.sipgpu_block_slice.argtypes = [C.c_int, C.c_void_p, c_int_p, C.c_void_p, c_int_p, c_int_p]
@@ -315,6 +322,10 @@ class DeviceBlock:
         _check(lib().sipgpu_block_scale(self.ptr, self.size, float(f)))
         return self
 
+    def fill_hash(self, seed, tag, scale=1.0):
+        _check(lib().sipgpu_block_fill_hash(self.ptr, self.size, int(seed), int(tag), float(scale)))
+        return self
+
     def increment(self, d):
         _check(lib().sipgpu_block_increment(self.ptr, self.size, float(d)))
         return self
@@ -464,6 +475,25 @@ def insert_block(t, s, beg):
 # ----------------------------------------------------------------------------------------------------
 # Boundary 4: distributed arrays
 # ----------------------------------------------------------------------------------------------------
+def layout_block_number(nseg, idx):
+    """array_table.cpp:75-81 (LAST index fastest, segments 1-based); host-only."""
+    return int(lib().sipgpu_layout_block_number(len(nseg), _ia(nseg), _ia(idx)))
+
+
+def layout_block_owner(number, world):
+    """data_distribution.cpp:74-82; host-only."""
+    return int(lib().sipgpu_layout_block_owner(int(number), int(world)))
+
+
+def partition_blocks(nseg, world):
+    """owner -> list of 1-based block index tuples, in block-number order (the destinations a rank computes)."""
+    out = [[] for _ in range(world)]
+    for idx in np.ndindex(*nseg):
+        idx1 = tuple(int(x) + 1 for x in idx)
+        out[layout_block_owner(layout_block_number(nseg, idx1), world)].append(idx1)
+    return out
+
+
 class DistArray:
     """A distributed/served SIAL array: blocks owned block-cyclically by the ranks (one rank per GPU), slabs
     mapped across processes with CUDA IPC.  `exchange` is a callable all_gather(bytes) -> list[bytes]
@@ -522,6 +552,9 @@ class DistArray:
 
     def fill_local(self, v):
         _check(lib().sipgpu_array_fill_local(self.h, float(v)), "sipgpu_array_fill_local")
+
+    def local_base(self):
+        return int(lib().sipgpu_array_local_base(self.h) or 0)
 
     def local_bytes(self):
         return int(lib().sipgpu_array_local_bytes(self.h))

@@ -414,6 +414,12 @@ int sipgpu_block_axpy(double* d, const double* s, long long n, double f) { retur
 int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
     return ew_add_sub(d, l, r, n, sign);
 }
+int sipgpu_block_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale) {
+    return ew_fill_hash(d, n, seed, tag, scale);
+}
+int sipgpu_block_dot_accumulate(const double* l, const double* r, long long n, double* d_scalar) {
+    return ew_dot_device(l, r, n, d_scalar, 1.0);
+}
 int sipgpu_block_norm2(const double* t, long long n, double* out) { return ew_dot(t, t, n, out); }
 int sipgpu_block_dot(const double* l, const double* r, long long n, double* out) { return ew_dot(l, r, n, out); }
 int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {

@@ -41,6 +41,21 @@ int check_idx(const sipgpu_array* a, const int* idx) {
 
 extern "C" {
 
+// host-only layout arithmetic (no device needed): array_table.cpp:50-97, data_distribution.cpp:74-82
+long long sipgpu_layout_block_number(int rank, const int* nseg, const int* idx) {
+    if (rank < 1 || rank > kMaxRank || !nseg || !idx) return -1;
+    long long s = 1, b = 0;
+    for (int p = rank - 1; p >= 0; --p) {
+        if (idx[p] < 1 || idx[p] > nseg[p]) return -1;
+        b += s * (idx[p] - 1);
+        s *= nseg[p];
+    }
+    return b;
+}
+int sipgpu_layout_block_owner(long long block_number, int world) {
+    return (block_number < 0 || world < 1) ? -1 : (int)(block_number % world);
+}
+
 int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_rank, int world, sipgpu_array** out) {
     if (rank < 1 || rank > kMaxRank || !nseg || !seg_ext || !out || world < 1 || my_rank < 0 || my_rank >= world)
         return SIPGPU_E_ARG;
@@ -177,6 +192,7 @@ int sipgpu_array_fill_local(sipgpu_array* a, double v) {
     if (!a) return SIPGPU_E_ARG;
     return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
 }
+double* sipgpu_array_local_base(sipgpu_array* a) { return a ? a->base[a->my_rank] : nullptr; }
 size_t sipgpu_array_local_bytes(const sipgpu_array* a) {
     return a ? sizeof(double) * (size_t)a->slab_elems[a->my_rank] : 0;
 }

@@ -215,6 +215,29 @@ int ew_red_add(double* d, const double* s, long long n) {
     return SIPGPU_OK;
 }
 
+// Seeded synthetic fill: d[i] = scale * uniform(-1,1) from splitmix64((seed ^ tag) + (i+1)*golden).  Pure integer
+// arithmetic + exact conversions, so the CPU oracle's restatement (oracle_fill_hash) is bit-identical.
+__global__ void __launch_bounds__(kThreads) fill_hash_kernel(double* __restrict__ d, long long n, unsigned long long key,
+                                                             double scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long z = key + (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double u = __dsub_rn(__dmul_rn((double)(z >> 11), 0x1.0p-52), 1.0);  // exact, in [-1, 1)
+        d[i] = __dmul_rn(scale, u);
+    }
+}
+int ew_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale) {
+    if (n < 0 || !d) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    SIP_TRY(ensure_init());
+    fill_hash_kernel<<<grid_for(n), kThreads, 0, ctx().stream>>>(d, n, seed ^ tag, scale);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
 // read+write copy for the bandwidth probe
 __global__ void __launch_bounds__(kThreads) copy_kernel(double2* __restrict__ d, const double2* __restrict__ s, long long n2) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)

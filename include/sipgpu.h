@@ -111,7 +111,11 @@ int sipgpu_block_increment(double* d, long long n, double delta);               
 int sipgpu_block_accumulate(double* d, const double* s, long long n);             /* block.cpp:259-268 */
 int sipgpu_block_axpy(double* d, const double* s, long long n, double f);         /* F90:394-436      */
 int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign); /* interpreter.cpp:1929,1992 */
-int sipgpu_block_norm2(const double* t, long long n, double* result_host);        /* F90:230-269 (blocking) */
+/* synthetic inputs: d[i] = scale * uniform(-1,1) from splitmix64((seed ^ tag) + (i+1)*0x9E3779B97F4A7C15) */
+int sipgpu_block_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale);
+int sipgpu_block_norm2(const double* t, long long n, double* result_host);
+/* d_scalar[0] += sum l*r, asynchronous, result stays on the device (energy accumulation over many blocks) */
+int sipgpu_block_dot_accumulate(const double* l, const double* r, long long n, double* d_scalar);        /* F90:230-269 (blocking) */
 int sipgpu_block_dot(const double* l, const double* r, long long n, double* result_host); /* F90:910-938 (blocking) */
 int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg);
 int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg);
@@ -196,6 +200,10 @@ int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src);     
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src); /* ::put_accumulate (atomic)  */
 int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* put_initialize on owned blocks  */
 size_t sipgpu_array_local_bytes(const sipgpu_array* a);
+double* sipgpu_array_local_base(sipgpu_array* a);   /* this rank's slab (its owned blocks, contiguous) */
+/* host-only layout arithmetic (no device needed) */
+long long sipgpu_layout_block_number(int rank, const int* nseg, const int* idx);
+int sipgpu_layout_block_owner(long long block_number, int world);
 
 #ifdef __cplusplus
 }

@@ -204,3 +204,9 @@ def block_num2id(nseg, lower, num):
 
 def block_owner(num, nowners):
     return lib().oracle_block_owner(C.c_longlong(num), nowners)
+
+
+def fill_hash(shape, seed, tag, scale=1.0):
+    a = np.empty(shape, dtype=np.float64, order="F")
+    lib().oracle_fill_hash(_dp(a), C.c_longlong(a.size), C.c_ulonglong(seed), C.c_ulonglong(tag), C.c_double(scale))
+    return a

@@ -466,3 +466,19 @@ void oracle_fill_block_sequential(double* d, long long n, double start) {
     double v = start;
     for (long long i = 0; i < n; ++i) { d[i] = v; v += 1.0; }
 }
+
+/* ---- seeded synthetic inputs of the benchmark workloads: splitmix64 of
+ * (seed ^ tag) + (i+1)*golden -> uniform [-1,1) * scale.  Integer arithmetic + exact conversions, so the CUDA
+ * fill kernel (sipgpu_block_fill_hash) produces the same bits. ---- */
+void oracle_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale) {
+    unsigned long long key = seed ^ tag;
+    for (long long i = 0; i < n; ++i) {
+        unsigned long long z = key + (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        volatile double u = (double)(z >> 11) * 0x1.0p-52;
+        u = u - 1.0;
+        d[i] = scale * u;
+    }
+}
