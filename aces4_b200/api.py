@@ -33,7 +33,8 @@ class SipGpuError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libsipgpu.so")
+    # SIPGPU_LIB: development override (kernel-tuning experiments load an alternative build of the SAME sources)
+    return os.environ.get("SIPGPU_LIB") or os.path.join(_HERE, "lib", "libsipgpu.so")
 
 
 def build(force=False, verbose=False):

@@ -10,6 +10,12 @@
 // prefix-summed tile list, so thousands of small heterogeneous blocks cost one launch.
 #include "contract.h"
 
+#include <stdlib.h>
+
+#ifndef SIP_LOAD_DIV
+#define SIP_LOAD_DIV 2  // loads of stage j+1 are spread over the first 1/SIP_LOAD_DIV of stage j's DMMA groups
+#endif
+
 namespace sipgpu {
 
 namespace {
@@ -80,8 +86,11 @@ struct Cfg {
     static constexpr int B_ITEMS = ((B_KC ? BN : BK) + B_PER - 1) / B_PER;
     static constexpr int ITEMS = A_ITEMS + B_ITEMS;
     static constexpr int MMA_GROUPS = (BK / 4) * MF;  // groups of NF DMMAs per stage
+    // the next stage's cp.async items are issued during the first LOAD_GROUPS groups only: the tail of the stage
+    // is latency slack, so the barrier that opens the next stage does not wait for loads still in flight
+    static constexpr int LOAD_GROUPS = MMA_GROUPS / SIP_LOAD_DIV > 0 ? MMA_GROUPS / SIP_LOAD_DIV : 1;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)4 * KWIN * 4;
-    static_assert(A_PER >= 1 && B_PER >= 1, "load mapping");
+    static_assert(A_PER >= 1 && B_PER >= 1 && LOAD_GROUPS + 1 <= MMA_GROUPS, "load mapping");
     static_assert(KWIN % BK == 0 && LDK % 16 == 4 && LDAM % 16 == 4 && LDBN % 16 == 4, "window / bank layout");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -205,44 +214,49 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 }
             }
         };
-        // one cp.async (8 bytes, or 16 when VEC) of the load cursor's step: item `it` of C::ITEMS; out-of-range
-        // elements are zero-filled.  With VEC the host guarantees even extents/strides along the contiguous
-        // direction, so both doubles of an item are valid or invalid together and 16-byte aligned.
-        auto issue_item = [&](int it, double* as, double* bs) {
+        // One cp.async item (8 bytes, or 16 when VEC) of the load cursor's step = item `it` of C::ITEMS; out-of-range
+        // elements are zero-filled.  With VEC the host guarantees even extents/strides along the contiguous direction,
+        // so both doubles of an item are valid or invalid together and 16-byte aligned.  The element offset of an
+        // item is (stage-constant part) + (per-item part), both read from the offset tables: item_guard() says
+        // whether this thread has the item, item_lookup() reads its per-item table entry, item_issue() consumes it.
+        // In the main loop the lookup of item it+1 is issued before the cp.async of item it, so the dependent
+        // address arithmetic never waits on shared memory in front of the DMMAs of an in-order warp.
+        auto item_guard = [&](int it) -> bool {
+            if (it < C::A_ITEMS) {
+                const int x = a_var + it * C::A_PER;
+                return (((C::A_KC ? BM : BK) % C::A_PER == 0) && NT % C::A_LANES == 0) || (x < (C::A_KC ? BM : BK) && a_var < C::A_PER);
+            }
+            const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
+            return (((C::B_KC ? BN : BK) % C::B_PER == 0) && NT % C::B_LANES == 0) || (x < (C::B_KC ? BN : BK) && b_var < C::B_PER);
+        };
+        auto item_lookup = [&](int it) -> int {
+            if (!item_guard(it)) return -1;
+            if (args.dbg & 2) return 0;
             const int kb = l_ks * BK;
             if (it < C::A_ITEMS) {
-                if constexpr (C::A_KC) {
-                    const int row = a_var + it * C::A_PER;
-                    if ((BM % C::A_PER == 0 && NT % C::A_LANES == 0) || (row < BM && a_var < C::A_PER)) {
-                        const int ko = kl_tab[kb + a_fix], mo = mOffL[row];
-                        const bool v = (mo | ko) >= 0;
-                        cp_async_item<C::VEC>(as + row * C::LDK + a_fix, Lp + (v ? mo + ko : 0), v);
-                    }
-                } else {
-                    const int kk = a_var + it * C::A_PER;
-                    if ((BK % C::A_PER == 0 && NT % C::A_LANES == 0) || (kk < BK && a_var < C::A_PER)) {
-                        const int ko = kl_tab[kb + kk];
-                        const bool v = (mo_fix | ko) >= 0;
-                        cp_async_item<C::VEC>(as + kk * C::LDAM + a_fix, Lp + (v ? mo_fix + ko : 0), v);
-                    }
-                }
+                const int x = a_var + it * C::A_PER;
+                return C::A_KC ? mOffL[x] : kl_tab[kb + x];
+            }
+            const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
+            return C::B_KC ? nOffR[x] : kr_tab[kb + x];
+        };
+        // stage-constant part: the k offset of this thread's lane (K-contiguous) or its m/n offset (M/N-contiguous)
+        auto stage_fix_a = [&]() -> int { return C::A_KC ? (a_var < C::A_PER ? kl_tab[l_ks * BK + a_fix] : -1) : mo_fix; };
+        auto stage_fix_b = [&]() -> int { return C::B_KC ? (b_var < C::B_PER ? kr_tab[l_ks * BK + b_fix] : -1) : no_fix; };
+        auto item_issue = [&](int it, int per_item, int fix_a, int fix_b, double* as, double* bs) {
+            if (!item_guard(it)) return;
+            if (args.dbg & 1) return;
+            if (args.dbg & 2) { per_item = (it * 256 + tid) * 2; fix_a = fix_b = 0; }
+            if (it < C::A_ITEMS) {
+                const int x = a_var + it * C::A_PER;
+                const bool v = (per_item | fix_a) >= 0;
+                double* dst = C::A_KC ? as + x * C::LDK + a_fix : as + x * C::LDAM + a_fix;
+                cp_async_item<C::VEC>(dst, Lp + (v ? per_item + fix_a : 0), v);
             } else {
-                const int ib = it - C::A_ITEMS;
-                if constexpr (C::B_KC) {
-                    const int row = b_var + ib * C::B_PER;
-                    if ((BN % C::B_PER == 0 && NT % C::B_LANES == 0) || (row < BN && b_var < C::B_PER)) {
-                        const int ko = kr_tab[kb + b_fix], no = nOffR[row];
-                        const bool v = (no | ko) >= 0;
-                        cp_async_item<C::VEC>(bs + row * C::LDK + b_fix, Rp + (v ? no + ko : 0), v);
-                    }
-                } else {
-                    const int kk = b_var + ib * C::B_PER;
-                    if ((BK % C::B_PER == 0 && NT % C::B_LANES == 0) || (kk < BK && b_var < C::B_PER)) {
-                        const int ko = kr_tab[kb + kk];
-                        const bool v = (no_fix | ko) >= 0;
-                        cp_async_item<C::VEC>(bs + kk * C::LDBN + b_fix, Rp + (v ? no_fix + ko : 0), v);
-                    }
-                }
+                const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
+                const bool v = (per_item | fix_b) >= 0;
+                double* dst = C::B_KC ? bs + x * C::LDK + b_fix : bs + x * C::LDBN + b_fix;
+                cp_async_item<C::VEC>(dst, Rp + (v ? per_item + fix_b : 0), v);
             }
         };
 
@@ -250,12 +264,20 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
         for (int s = 0; s < STAGES - 1; ++s) {
             if (s < total_steps) {
                 double* as = tiles + (size_t)s * C::STAGE_ELEMS;
+                {
+                    const int fa = stage_fix_a(), fb = stage_fix_b();
 #pragma unroll
-                for (int it = 0; it < C::ITEMS; ++it) issue_item(it, as, as + C::A_ELEMS);
+                    for (int it = 0; it < C::ITEMS; ++it) item_issue(it, item_lookup(it), fa, fb, as, as + C::A_ELEMS);
+                }
                 advance_load_cursor();
             }
             cp_async_commit();
         }
+
+        // compute cursor: which steps are the ragged LAST step of an operand pair (only ceil(rem/4) of its BK/4
+        // DMMA k-steps hold contracted elements; the rest is zero padding and is skipped)
+        const int last_kk = (K - (nwin - 1) * KWIN - (last_steps - 1) * BK + 3) / 4;
+        int c_win = 0, c_ks = 0, c_steps = seg_steps(0);
 
         for (int j = 0; j < total_steps; ++j) {
             cp_async_wait<STAGES - 2>();
@@ -268,6 +290,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
             double* ls = tiles + (size_t)(jn % STAGES) * C::STAGE_ELEMS;
             const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
             const double* bs = as + C::A_ELEMS;
+            const int kk_lim = (c_ks == c_steps - 1 && c_win == nwin - 1) ? last_kk : BK / 4;
             double a[2][MF], b[2][NF];
             auto load_frags = [&](int kk, int buf) {
 #pragma unroll
@@ -279,30 +302,65 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                     b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
                                          : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
             };
-            load_frags(0, 0);
+            if (kk_lim == BK / 4) {
+                // ---- full step: BK/4 x MF groups of NF DMMAs, fully unrolled ----
+                int fix_a = -1, fix_b = -1, pre = -1;
+                if (do_load) {
+                    fix_a = stage_fix_a();
+                    fix_b = stage_fix_b();
+                    pre = item_lookup(0);
+                }
+                load_frags(0, 0);
 #pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
+                for (int kk = 0; kk < BK / 4; ++kk) {
+                    if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
 #pragma unroll
-                for (int mi = 0; mi < MF; ++mi) {
+                    for (int mi = 0; mi < MF; ++mi) {
 #pragma unroll
-                    for (int ni = 0; ni < NF; ++ni)
-                        dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
-                    // the next stage's loads ride in the shadow of the DMMA pipe: one item per few DMMA groups
-                    const int grp = kk * MF + mi;
-                    if (do_load) {
+                        for (int ni = 0; ni < NF; ++ni)
+                            dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
+                        // the next stage's loads ride in the shadow of the DMMA pipe: groups 1..LOAD_GROUPS carry
+                        // the cp.async items (the table entry of each item was fetched one group earlier)
+                        const int grp = kk * MF + mi;
+                        if (do_load && grp >= 1 && grp <= C::LOAD_GROUPS) {
 #pragma unroll
-                        for (int it = grp * C::ITEMS / C::MMA_GROUPS; it < (grp + 1) * C::ITEMS / C::MMA_GROUPS; ++it)
-                            issue_item(it, ls, ls + C::A_ELEMS);
+                            for (int it = (grp - 1) * C::ITEMS / C::LOAD_GROUPS; it < grp * C::ITEMS / C::LOAD_GROUPS; ++it) {
+                                const int cur = pre;
+                                if (it + 1 < C::ITEMS) pre = item_lookup(it + 1);
+                                item_issue(it, cur, fix_a, fix_b, ls, ls + C::A_ELEMS);
+                            }
+                        }
                     }
+                }
+            } else {
+                // ---- ragged last step of an operand pair: loads first, then only the k-steps that hold data ----
+                if (do_load) {
+                    const int fa = stage_fix_a(), fb = stage_fix_b();
+#pragma unroll
+                    for (int it = 0; it < C::ITEMS; ++it) item_issue(it, item_lookup(it), fa, fb, ls, ls + C::A_ELEMS);
+                }
+#pragma unroll 1
+                for (int kk = 0; kk < kk_lim; ++kk) {
+                    load_frags(kk, 0);
+#pragma unroll
+                    for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NF; ++ni)
+                            dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[0][mi], b[0][ni]);
                 }
             }
             cp_async_commit();
             if (do_load) advance_load_cursor();
+            if (++c_ks == c_steps) {
+                c_ks = 0;
+                if (++c_win == nwin) c_win = 0;
+                c_steps = (c_win == nwin - 1) ? last_steps : KWIN / BK;
+            }
         }
         cp_async_wait<0>();
 
         // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
+        if (!(args.dbg & 4) || acc[0][0][0] == 123.456)
 #pragma unroll
         for (int mi = 0; mi < MF; ++mi) {
             const int mo = mOffD[wm + mi * 8 + g];
@@ -332,6 +390,12 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
     }
     int grid = a.total_tiles < max_ctas ? a.total_tiles : max_ctas;
     if (grid < 1) return SIPGPU_OK;
+    static const int dbg = getenv("SIPGPU_DBG") ? atoi(getenv("SIPGPU_DBG")) : 0;
+    if (dbg) {
+        ContractArgs b = a;
+        b.dbg = dbg;
+        contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(b);
+    } else
     contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(a);
     SIP_CUDA(cudaGetLastError());
     count_launch();
@@ -374,6 +438,11 @@ int launch_tile(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int ctas)
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile) {
     const int ctas = ctx().num_sms;
     // BK = 32 double-buffered (one barrier per 32 contracted elements)
+    static const int warps16 = getenv("SIPGPU_WARPS16") ? atoi(getenv("SIPGPU_WARPS16")) : 0;  // tuning experiment
+    if (warps16) {
+        if (tile == 1) return launch_tile<8, 2, 2, 5>(a, a_kc, b_kc, vec, ctas);
+        return launch_tile<4, 4, 4, 4>(a, a_kc, b_kc, vec, ctas);
+    }
     if (tile == 1) return launch_tile<4, 2, 4, 5>(a, a_kc, b_kc, vec, ctas);
     return launch_tile<2, 4, 8, 4>(a, a_kc, b_kc, vec, ctas);
 }
