@@ -8,13 +8,21 @@
 // tcgen05 has no f64 kind), and the output permute (+ optional accumulate) is folded into the epilogue
 // scatter.  A launch processes a whole work-list of blocks (block-sparse batching): persistent CTAs walk a
 // prefix-summed tile list, so thousands of small heterogeneous blocks cost one launch.
+//
+// Structure (round-1 ablation, scripts/micro/dmma_ablate.cu: a loop that only does LDS.64 + DMMA reaches 99 % of
+// the DMMA issue-rate peak, the same loop with the gather addressing and cp.async issue woven into the DMMA
+// warps stalls at 90 %): the CTA is WARP-SPECIALISED.
+//   * warpgroup 0 (4 warps, 56 registers after setmaxnreg.dec) is the PRODUCER: it resolves the work-list,
+//     builds the offset tables, and streams operand tiles into a 4-stage shared-memory ring with cp.async
+//     (zero-filled at ragged edges); each stage is published through an mbarrier that the cp.async engine
+//     itself arrives on (cp.async.mbarrier.arrive.noinc);
+//   * warpgroups 1-2 (8 warps, 224 registers after setmaxnreg.inc) are the CONSUMERS: wait(full) -> LDS.64
+//     fragments -> DMMA -> arrive(empty), nothing else in the loop, then the epilogue scatter.  There is no
+//     CTA-wide barrier in steady state, and the producer refills the ring for the next tile while the
+//     consumers are still storing the previous one.
 #include "contract.h"
 
 #include <stdlib.h>
-
-#ifndef SIP_LOAD_DIV
-#define SIP_LOAD_DIV 2  // loads of stage j+1 are spread over the first 1/SIP_LOAD_DIV of stage j's DMMA groups
-#endif
 
 namespace sipgpu {
 
@@ -30,22 +38,39 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 template <bool VEC>
 __device__ __forceinline__ void cp_async_item(double* smem_dst, const double* gsrc, bool valid) {
     if constexpr (VEC) cp_async16(smem_dst, gsrc, valid); else cp_async8(smem_dst, gsrc, valid);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+
+// ---- mbarrier helpers (shared::cta, 64-bit objects) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrive-on triggered when all cp.async issued so far by this thread have landed in shared memory
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n"
+        " bra WAIT_%=;\n"
+        "DONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 // linear index -> element offset in up to two tensors, over the (collapsed) dims of one index group
 __device__ __forceinline__ void decompose2(int lin, int nd, const int* ext, const int* s0, const int* s1, int& o0,
@@ -62,12 +87,26 @@ __device__ __forceinline__ void decompose2(int lin, int nd, const int* ext, cons
     }
 }
 
-template <int WARPS_M_, int WARPS_N_, int MF_, int NF_, int BK_, int STAGES_, bool A_KC_, bool B_KC_, bool VEC_>
+constexpr int kProducerThreads = 128;
+constexpr int kProducerRegs = 56, kConsumerRegs = 224;  // 128*56 + 256*224 = 384*168 registers
+
+// what the consumers need to know about a tile (written by the producer, double-buffered by tile parity)
+struct TileInfo {
+    double* D;
+    int total_steps;     // ring stages this tile consumes (0 = no more tiles)
+    int steps_per_pair;  // stages per operand pair of the chain
+    int last_kk;         // DMMA k-steps (of 4) that hold data in the LAST stage of a pair
+    int pad;
+};
+
+template <int WARPS_M_, int WARPS_N_, int MF_, int NF_, bool A_KC_, bool B_KC_, bool VEC_>
 struct Cfg {
-    static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MF = MF_, NF = NF_, STAGES = STAGES_;
+    static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MF = MF_, NF = NF_;
     static constexpr bool A_KC = A_KC_, B_KC = B_KC_, VEC = VEC_;
-    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = BK_;
-    static constexpr int NT = 32 * WARPS_M * WARPS_N;
+    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = 16, STAGES = 4;
+    static constexpr int NC = 32 * WARPS_M * WARPS_N;  // consumer threads
+    static constexpr int NP = kProducerThreads;
+    static constexpr int NT = NP + NC;
     static constexpr int KWIN = 2048;    // k offsets are tabulated for a window of this many contracted elements
     static constexpr int LDK = BK + 4;   // K-contiguous tile: [row][k]; stride = 4 mod 16 doubles -> conflict-free frags
     static constexpr int LDAM = BM + 4;  // M-contiguous tile: [k][m]
@@ -75,22 +114,20 @@ struct Cfg {
     static constexpr int A_ELEMS = A_KC ? BM * LDK : BK * LDAM;
     static constexpr int B_ELEMS = B_KC ? BN * LDK : BK * LDBN;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    // global->shared mapping: each cp.async item moves V consecutive doubles (16 bytes when VEC) along the
-    // operand's contiguous direction; a thread keeps that lane fixed and walks the other direction in passes
+    // global->shared mapping of the producer: each cp.async item moves V consecutive doubles (16 bytes when VEC)
+    // along the operand's contiguous direction; a thread keeps that lane fixed and walks the other direction
     static constexpr int V = VEC ? 2 : 1;
-    // LANES threads span the contiguous direction, PER = NT / LANES rows (or k's) are covered per pass; threads
-    // beyond PER*LANES idle (only when BN is not a divisor of NT, e.g. the 128x80 tile)
     static constexpr int A_LANES = (A_KC ? BK : BM) / V, B_LANES = (B_KC ? BK : BN) / V;
-    static constexpr int A_PER = NT / A_LANES, B_PER = NT / B_LANES;
+    static constexpr int A_PER = NP / A_LANES, B_PER = NP / B_LANES;
     static constexpr int A_ITEMS = ((A_KC ? BM : BK) + A_PER - 1) / A_PER;
     static constexpr int B_ITEMS = ((B_KC ? BN : BK) + B_PER - 1) / B_PER;
-    static constexpr int ITEMS = A_ITEMS + B_ITEMS;
-    static constexpr int MMA_GROUPS = (BK / 4) * MF;  // groups of NF DMMAs per stage
-    // the next stage's cp.async items are issued during the first LOAD_GROUPS groups only: the tail of the stage
-    // is latency slack, so the barrier that opens the next stage does not wait for loads still in flight
-    static constexpr int LOAD_GROUPS = MMA_GROUPS / SIP_LOAD_DIV > 0 ? MMA_GROUPS / SIP_LOAD_DIV : 1;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * 8 + (size_t)(2 * BM + 2 * BN) * 4 + (size_t)4 * KWIN * 4;
-    static_assert(A_PER >= 1 && B_PER >= 1 && LOAD_GROUPS + 1 <= MMA_GROUPS, "load mapping");
+    // shared memory: [stages][tables x2 parities][k tables][tile info x2][mbarriers]
+    static constexpr size_t OFF_TABLES = (size_t)STAGES * STAGE_ELEMS * 8;
+    static constexpr size_t OFF_KTAB = OFF_TABLES + (size_t)2 * (2 * BM + 2 * BN) * 4;
+    static constexpr size_t OFF_INFO = OFF_KTAB + (size_t)2 * KWIN * 4;
+    static constexpr size_t OFF_BARS = OFF_INFO + 2 * sizeof(TileInfo);
+    static constexpr size_t SMEM = OFF_BARS + (size_t)(2 * STAGES + 4) * 8;
+    static_assert(NC == 256 && A_PER >= 1 && B_PER >= 1, "thread mapping");
     static_assert(KWIN % BK == 0 && LDK % 16 == 4 && LDAM % 16 == 4 && LDBN % 16 == 4, "window / bank layout");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
@@ -98,201 +135,199 @@ struct Cfg {
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 contract_kernel(const __grid_constant__ ContractArgs args) {
-    constexpr int BM = C::BM, BN = C::BN, BK = C::BK, NT = C::NT, STAGES = C::STAGES, MF = C::MF, NF = C::NF;
-    constexpr int KWIN = C::KWIN;
+    constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, MF = C::MF, NF = C::NF, KWIN = C::KWIN;
+    constexpr int NP = C::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    int* mOffL = reinterpret_cast<int*>(tiles + (size_t)STAGES * C::STAGE_ELEMS);
-    int* mOffD = mOffL + BM;
-    int* nOffR = mOffD + BM;
-    int* nOffD = nOffR + BN;
-    int* kOffL = nOffD + BN;  // [2][KWIN]: double-buffered by segment parity when K spans several windows
-    int* kOffR = kOffL + 2 * KWIN;
+    int* tabs = reinterpret_cast<int*>(smem_raw + C::OFF_TABLES);   // per parity: mOffL[BM] mOffD[BM] nOffR[BN] nOffD[BN]
+    int* kOffL = reinterpret_cast<int*>(smem_raw + C::OFF_KTAB);    // [KWIN]
+    int* kOffR = kOffL + KWIN;
+    TileInfo* info = reinterpret_cast<TileInfo*>(smem_raw + C::OFF_INFO);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + C::OFF_BARS);
+    unsigned long long* full = bars;                 // [STAGES]  producer -> consumers (cp.async completion)
+    unsigned long long* empty = bars + STAGES;       // [STAGES]  consumers -> producer
+    unsigned long long* tab_full = bars + 2 * STAGES;  // [2]     tables + TileInfo of a tile are written
+    unsigned long long* tab_empty = tab_full + 2;      // [2]     consumers are done with them (epilogue finished)
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
-    const int wm = (warp % C::WARPS_M) * (MF * 8), wn = (warp / C::WARPS_M) * (NF * 8);
-    const double alpha = args.alpha, beta = args.beta;
-
-    // per-thread constants of the global->shared mapping
-    const int a_fix = (tid % C::A_LANES) * C::V;  // the k lane (K-contiguous) or the m lane (M-contiguous)
-    const int a_var = tid / C::A_LANES;           // first row / first k of the passes
-    const int b_fix = (tid % C::B_LANES) * C::V;
-    const int b_var = tid / C::B_LANES;
-
-    for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-        // ---- which block of the work-list does this tile belong to? (uniform binary search) ----
-        int p = 0;
-        if (args.nprob > 1) {
-            int lo = 0, hi = args.nprob;  // tile_prefix[lo] <= tile < tile_prefix[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(args.tile_prefix + mid) <= tile) lo = mid; else hi = mid;
-            }
-            p = lo;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, NP);
+            mbar_init(empty + s, C::NC / 32);
         }
-        const Problem* pr = args.probs ? args.probs + p : &args.p0;
-        const Shape* sh = args.probs ? args.shapes + pr->shape : &args.s0;
-        const Pair* chain = args.probs ? args.pairs + pr->chain_begin : &args.pair0;
-        const int chain_len = pr->chain_len;
-        const int local = tile - (args.nprob > 1 ? __ldg(args.tile_prefix + p) : 0);
-        const int M = sh->M, N = sh->N, K = sh->K;
-        const int tiles_m = (M + BM - 1) / BM;
-        const int m0 = (local % tiles_m) * BM, n0 = (local / tiles_m) * BN;
-        double* __restrict__ Dp = pr->D;
-        const int nk = sh->nk;
-        const int nwin = (K + KWIN - 1) / KWIN;
-
-        __syncthreads();  // previous tile fully consumed (tables + stages)
-        // ---- offset tables: the input/output permutes of F90:731-743,782-785 as address arithmetic ----
-        for (int i = tid; i < BM + BN; i += NT) {
-            if (i < BM) {
-                const int m = m0 + i;
-                int oL = -1, oD = -1;
-                if (m < M) decompose2(m, sh->nm, sh->mext, sh->msL, sh->msD, oL, oD);
-                mOffL[i] = oL;
-                mOffD[i] = oD;
-            } else {
-                const int j = i - BM, n = n0 + j;
-                int oR = -1, oD = -1;
-                if (n < N) decompose2(n, sh->nn, sh->next, sh->nsR, sh->nsD, oR, oD);
-                nOffR[j] = oR;
-                nOffD[j] = oD;
-            }
+        for (int p = 0; p < 2; ++p) {
+            mbar_init(tab_full + p, NP);
+            mbar_init(tab_empty + p, C::NC / 32);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
 
-        double acc[MF][NF][2];
-#pragma unroll
-        for (int i = 0; i < MF; ++i)
-#pragma unroll
-            for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        // ---- the K loop runs over SEGMENTS = (operand pair of the chain) x (k-offset window) as ONE software
-        // pipeline: stages keep flowing across pair boundaries, so a chain costs no drain/refill per block ----
-        const int nseg = chain_len * nwin;
-        const int last_steps = (K - (nwin - 1) * KWIN + BK - 1) / BK;
-        auto seg_steps = [&](int seg) { return (nwin == 1 || (seg % nwin) == nwin - 1) ? last_steps : KWIN / BK; };
-        const int total_steps = chain_len * ((nwin - 1) * (KWIN / BK) + last_steps);
-        // k offsets of one window (contracted-index permute as address arithmetic); -1 pads the ragged tail
-        auto fill_ktable = [&](int seg, int buf) {
-            const int kbase = (seg % nwin) * KWIN;
-            const int kcount = min(KWIN, K - kbase);
-            const int nfill = seg_steps(seg) * BK;
-            for (int i = tid; i < nfill; i += NT) {
-                int oL = -1, oR = -1;
-                if (i < kcount) decompose2(kbase + i, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
-                kOffL[buf * KWIN + i] = oL;
-                kOffR[buf * KWIN + i] = oR;
+    if (tid < NP) {
+        // =====================================  PRODUCER  =====================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kProducerRegs));
+        const int a_fix = (tid % C::A_LANES) * C::V;  // the k lane (K-contiguous) or the m lane (M-contiguous)
+        const int a_var = tid / C::A_LANES;           // first row / first k of the passes
+        const int b_fix = (tid % C::B_LANES) * C::V;
+        const int b_var = tid / C::B_LANES;
+        int ring = 0;  // stages produced so far (all tiles)
+        int tcount = 0;
+        for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
+            const int par = tcount & 1;
+            int* mOffL = tabs + par * (2 * BM + 2 * BN);
+            int* mOffD = mOffL + BM;
+            int* nOffR = mOffD + BM;
+            int* nOffD = nOffR + BN;
+            // the consumers must have finished the epilogue of the tile that used this parity (2 tiles ago)
+            if (tcount >= 2) mbar_wait(tab_empty + par, ((tcount >> 1) - 1) & 1);
+            if (tile >= args.total_tiles) {
+                if (tid == 0) info[par].total_steps = 0;
+                mbar_arrive(tab_full + par);
+                break;
             }
-        };
-        fill_ktable(0, 0);
-        if (nwin > 1) fill_ktable(1, 1);  // nwin > 1 implies nseg > 1
-        __syncthreads();
+            // ---- which block of the work-list does this tile belong to? (uniform binary search) ----
+            int p = 0;
+            if (args.nprob > 1) {
+                int lo = 0, hi = args.nprob;  // tile_prefix[lo] <= tile < tile_prefix[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(args.tile_prefix + mid) <= tile) lo = mid; else hi = mid;
+                }
+                p = lo;
+            }
+            const Problem* pr = args.probs ? args.probs + p : &args.p0;
+            const Shape* sh = args.probs ? args.shapes + pr->shape : &args.s0;
+            const Pair* chain = args.probs ? args.pairs + pr->chain_begin : &args.pair0;
+            const int chain_len = pr->chain_len;
+            const int local = tile - (args.nprob > 1 ? __ldg(args.tile_prefix + p) : 0);
+            const int M = sh->M, N = sh->N, K = sh->K;
+            const int tiles_m = (M + BM - 1) / BM;
+            const int m0 = (local % tiles_m) * BM, n0 = (local / tiles_m) * BN;
+            const int nk = sh->nk;
+            const int nwin = (K + KWIN - 1) / KWIN;
+            const int last_steps = (K - (nwin - 1) * KWIN + BK - 1) / BK;
+            const int steps_per_pair = (nwin - 1) * (KWIN / BK) + last_steps;
 
-        const int mo_fix = (C::A_KC || a_var >= C::A_PER) ? 0 : mOffL[a_fix];
-        const int no_fix = (C::B_KC || b_var >= C::B_PER) ? 0 : nOffR[b_fix];
+            // ---- offset tables: the input/output permutes of F90:731-743,782-785 as address arithmetic ----
+            for (int i = tid; i < BM + BN; i += NP) {
+                if (i < BM) {
+                    const int m = m0 + i;
+                    int oL = -1, oD = -1;
+                    if (m < M) decompose2(m, sh->nm, sh->mext, sh->msL, sh->msD, oL, oD);
+                    mOffL[i] = oL;
+                    mOffD[i] = oD;
+                } else {
+                    const int j = i - BM, n = n0 + j;
+                    int oR = -1, oD = -1;
+                    if (n < N) decompose2(n, sh->nn, sh->next, sh->nsR, sh->nsD, oR, oD);
+                    nOffR[j] = oR;
+                    nOffD[j] = oD;
+                }
+            }
+            if (tid == 0) {
+                TileInfo ti;
+                ti.D = pr->D;
+                ti.total_steps = chain_len * steps_per_pair;
+                ti.steps_per_pair = steps_per_pair;
+                ti.last_kk = (K - (nwin - 1) * KWIN - (last_steps - 1) * BK + 3) / 4;
+                ti.pad = 0;
+                info[par] = ti;
+            }
+            mbar_arrive(tab_full + par);  // release: tables + info are visible to whoever waits on this phase
 
-        // load cursor: the (segment, step) whose tiles are fetched next
-        int l_seg = 0, l_ks = 0, l_steps = seg_steps(0);
-        const double* __restrict__ Lp = chain[0].L;
-        const double* __restrict__ Rp = chain[0].R;
-        const int* kl_tab = kOffL;
-        const int* kr_tab = kOffR;
-        auto advance_load_cursor = [&]() {
-            if (++l_ks == l_steps) {
-                l_ks = 0;
-                ++l_seg;
-                if (l_seg < nseg) {
-                    l_steps = seg_steps(l_seg);
-                    const Pair pq = chain[l_seg / nwin];
-                    Lp = pq.L;
-                    Rp = pq.R;
-                    if (nwin > 1) {
-                        kl_tab = kOffL + (l_seg & 1) * KWIN;
-                        kr_tab = kOffR + (l_seg & 1) * KWIN;
+            // k offsets of one window (contracted-index permute as address arithmetic); -1 pads the ragged tail.
+            // Single buffer: only producer threads read it, between two producer-only barriers.
+            auto fill_ktable = [&](int win) {
+                producer_bar_sync();  // every producer thread is done reading the previous window
+                const int kbase = win * KWIN;
+                const int kcount = min(KWIN, K - kbase);
+                const int nfill = (win == nwin - 1 ? last_steps : KWIN / BK) * BK;
+                for (int i = tid; i < nfill; i += NP) {
+                    int oL = -1, oR = -1;
+                    if (i < kcount) decompose2(kbase + i, nk, sh->kext, sh->ksL, sh->ksR, oL, oR);
+                    kOffL[i] = oL;
+                    kOffR[i] = oR;
+                }
+                producer_bar_sync();  // (also orders the m/n tables written above before their first use below)
+            };
+            fill_ktable(0);
+            const int mo_fix = (C::A_KC || a_var >= C::A_PER) ? 0 : mOffL[a_fix];
+            const int no_fix = (C::B_KC || b_var >= C::B_PER) ? 0 : nOffR[b_fix];
+
+            for (int c = 0; c < chain_len; ++c) {
+                const Pair pq = chain[c];
+                const double* __restrict__ Lp = pq.L;
+                const double* __restrict__ Rp = pq.R;
+                for (int win = 0; win < nwin; ++win) {
+                    if (nwin > 1) fill_ktable(win);
+                    const int steps = win == nwin - 1 ? last_steps : KWIN / BK;
+                    for (int ks = 0; ks < steps; ++ks, ++ring) {
+                        const int stage = ring % STAGES;
+                        mbar_wait(empty + stage, ((ring / STAGES) & 1) ^ 1);  // slot free (first lap passes at once)
+                        double* as = tiles + (size_t)stage * C::STAGE_ELEMS;
+                        double* bs = as + C::A_ELEMS;
+                        const int kb = ks * BK;
+                        // One cp.async item = V consecutive doubles of the operand's contiguous direction; elements
+                        // outside the block (ragged tile edges, K tail) are zero-filled.  With VEC the planner
+                        // guarantees even extents/strides along that direction, so both doubles of an item are valid
+                        // or invalid together and 16-byte aligned.
+                        if (a_var < C::A_PER) {
+                            const int fix = C::A_KC ? kOffL[kb + a_fix] : mo_fix;
+#pragma unroll
+                            for (int it = 0; it < C::A_ITEMS; ++it) {
+                                const int x = a_var + it * C::A_PER;  // row (K-contiguous) or k (M-contiguous)
+                                if ((C::A_KC ? BM : BK) % C::A_PER == 0 || x < (C::A_KC ? BM : BK)) {
+                                    const int per = C::A_KC ? mOffL[x] : kOffL[kb + x];
+                                    const bool v = (per | fix) >= 0;
+                                    double* dst = C::A_KC ? as + x * C::LDK + a_fix : as + x * C::LDAM + a_fix;
+                                    cp_async_item<C::VEC>(dst, Lp + (v ? per + fix : 0), v);
+                                }
+                            }
+                        }
+                        if (b_var < C::B_PER) {
+                            const int fix = C::B_KC ? kOffR[kb + b_fix] : no_fix;
+#pragma unroll
+                            for (int it = 0; it < C::B_ITEMS; ++it) {
+                                const int x = b_var + it * C::B_PER;
+                                if ((C::B_KC ? BN : BK) % C::B_PER == 0 || x < (C::B_KC ? BN : BK)) {
+                                    const int per = C::B_KC ? nOffR[x] : kOffR[kb + x];
+                                    const bool v = (per | fix) >= 0;
+                                    double* dst = C::B_KC ? bs + x * C::LDK + b_fix : bs + x * C::LDBN + b_fix;
+                                    cp_async_item<C::VEC>(dst, Rp + (v ? per + fix : 0), v);
+                                }
+                            }
+                        }
+                        mbar_arrive_cp_async(full + stage);
                     }
                 }
             }
-        };
-        // One cp.async item (8 bytes, or 16 when VEC) of the load cursor's step = item `it` of C::ITEMS; out-of-range
-        // elements are zero-filled.  With VEC the host guarantees even extents/strides along the contiguous direction,
-        // so both doubles of an item are valid or invalid together and 16-byte aligned.  The element offset of an
-        // item is (stage-constant part) + (per-item part), both read from the offset tables: item_guard() says
-        // whether this thread has the item, item_lookup() reads its per-item table entry, item_issue() consumes it.
-        // In the main loop the lookup of item it+1 is issued before the cp.async of item it, so the dependent
-        // address arithmetic never waits on shared memory in front of the DMMAs of an in-order warp.
-        auto item_guard = [&](int it) -> bool {
-            if (it < C::A_ITEMS) {
-                const int x = a_var + it * C::A_PER;
-                return (((C::A_KC ? BM : BK) % C::A_PER == 0) && NT % C::A_LANES == 0) || (x < (C::A_KC ? BM : BK) && a_var < C::A_PER);
-            }
-            const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
-            return (((C::B_KC ? BN : BK) % C::B_PER == 0) && NT % C::B_LANES == 0) || (x < (C::B_KC ? BN : BK) && b_var < C::B_PER);
-        };
-        auto item_lookup = [&](int it) -> int {
-            if (!item_guard(it)) return -1;
-            if (args.dbg & 2) return 0;
-            const int kb = l_ks * BK;
-            if (it < C::A_ITEMS) {
-                const int x = a_var + it * C::A_PER;
-                return C::A_KC ? mOffL[x] : kl_tab[kb + x];
-            }
-            const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
-            return C::B_KC ? nOffR[x] : kr_tab[kb + x];
-        };
-        // stage-constant part: the k offset of this thread's lane (K-contiguous) or its m/n offset (M/N-contiguous)
-        auto stage_fix_a = [&]() -> int { return C::A_KC ? (a_var < C::A_PER ? kl_tab[l_ks * BK + a_fix] : -1) : mo_fix; };
-        auto stage_fix_b = [&]() -> int { return C::B_KC ? (b_var < C::B_PER ? kr_tab[l_ks * BK + b_fix] : -1) : no_fix; };
-        auto item_issue = [&](int it, int per_item, int fix_a, int fix_b, double* as, double* bs) {
-            if (!item_guard(it)) return;
-            if (args.dbg & 1) return;
-            if (args.dbg & 2) { per_item = (it * 256 + tid) * 2; fix_a = fix_b = 0; }
-            if (it < C::A_ITEMS) {
-                const int x = a_var + it * C::A_PER;
-                const bool v = (per_item | fix_a) >= 0;
-                double* dst = C::A_KC ? as + x * C::LDK + a_fix : as + x * C::LDAM + a_fix;
-                cp_async_item<C::VEC>(dst, Lp + (v ? per_item + fix_a : 0), v);
-            } else {
-                const int x = b_var + (it - C::A_ITEMS) * C::B_PER;
-                const bool v = (per_item | fix_b) >= 0;
-                double* dst = C::B_KC ? bs + x * C::LDK + b_fix : bs + x * C::LDBN + b_fix;
-                cp_async_item<C::VEC>(dst, Rp + (v ? per_item + fix_b : 0), v);
-            }
-        };
-
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) {
-            if (s < total_steps) {
-                double* as = tiles + (size_t)s * C::STAGE_ELEMS;
-                {
-                    const int fa = stage_fix_a(), fb = stage_fix_b();
-#pragma unroll
-                    for (int it = 0; it < C::ITEMS; ++it) item_issue(it, item_lookup(it), fa, fb, as, as + C::A_ELEMS);
-                }
-                advance_load_cursor();
-            }
-            cp_async_commit();
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else {
+        // =====================================  CONSUMERS  =====================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kConsumerRegs));
+        const int ctid = tid - NP, lane = ctid & 31, warp = ctid >> 5;
+        const int g = lane >> 2, t4 = lane & 3;
+        const int wm = (warp % C::WARPS_M) * (MF * 8), wn = (warp / C::WARPS_M) * (NF * 8);
+        const double alpha = args.alpha, beta = args.beta;
+        int ring = 0;  // stages consumed so far (all tiles)
+        for (int tcount = 0;; ++tcount) {
+            const int par = tcount & 1;
+            mbar_wait(tab_full + par, (tcount >> 1) & 1);
+            const int total_steps = info[par].total_steps;
+            if (total_steps == 0) break;
+            const int steps_per_pair = info[par].steps_per_pair;
+            const int last_kk = info[par].last_kk;
 
-        // compute cursor: which steps are the ragged LAST step of an operand pair (only ceil(rem/4) of its BK/4
-        // DMMA k-steps hold contracted elements; the rest is zero padding and is skipped)
-        const int last_kk = (K - (nwin - 1) * KWIN - (last_steps - 1) * BK + 3) / 4;
-        int c_win = 0, c_ks = 0, c_steps = seg_steps(0);
+            double acc[MF][NF][2];
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        for (int j = 0; j < total_steps; ++j) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads();
-            const int jn = j + STAGES - 1;
-            const bool do_load = jn < total_steps;
-            // entering a new segment: the table of the segment after it can be built now -- the last loads that read
-            // that buffer (segment l_seg-1) were issued before the barrier above
-            if (nwin > 1 && do_load && l_ks == 0 && l_seg + 1 < nseg && j > 0) fill_ktable(l_seg + 1, (l_seg + 1) & 1);
-            double* ls = tiles + (size_t)(jn % STAGES) * C::STAGE_ELEMS;
-            const double* as = tiles + (size_t)(j % STAGES) * C::STAGE_ELEMS;
-            const double* bs = as + C::A_ELEMS;
-            const int kk_lim = (c_ks == c_steps - 1 && c_win == nwin - 1) ? last_kk : BK / 4;
             double a[2][MF], b[2][NF];
-            auto load_frags = [&](int kk, int buf) {
+            auto load_frags = [&](const double* as, int kk, int buf) {
+                const double* bs = as + C::A_ELEMS;
 #pragma unroll
                 for (int mi = 0; mi < MF; ++mi)
                     a[buf][mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
@@ -302,81 +337,76 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                     b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
                                          : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
             };
-            if (kk_lim == BK / 4) {
-                // ---- full step: BK/4 x MF groups of NF DMMAs, fully unrolled ----
-                int fix_a = -1, fix_b = -1, pre = -1;
-                if (do_load) {
-                    fix_a = stage_fix_a();
-                    fix_b = stage_fix_b();
-                    pre = item_lookup(0);
+            auto mma_step = [&](int buf) {
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[buf][mi], b[buf][ni]);
+            };
+            auto stage_ptr = [&](int r) { return tiles + (size_t)(r % STAGES) * C::STAGE_ELEMS; };
+
+            // invariant at the top of every step: the stage is full and its first fragments are in buffer 0
+            mbar_wait(full + ring % STAGES, (ring / STAGES) & 1);
+            load_frags(stage_ptr(ring), 0, 0);
+            int c_ks = 0;
+            for (int j = 0; j < total_steps; ++j, ++ring) {
+                const double* as = stage_ptr(ring);
+                const bool more = j + 1 < total_steps;
+                const int kk_lim = (c_ks == steps_per_pair - 1) ? last_kk : BK / 4;
+                if (++c_ks == steps_per_pair) c_ks = 0;
+                if (kk_lim == BK / 4) {
+#pragma unroll
+                    for (int kk = 0; kk < BK / 4; ++kk) {
+                        if (kk + 1 < BK / 4) {
+                            load_frags(as, kk + 1, (kk + 1) & 1);
+                        } else if (more) {
+                            // the first fragments of the NEXT stage ride under the last k-step of this one
+                            mbar_wait(full + (ring + 1) % STAGES, ((ring + 1) / STAGES) & 1);
+                            load_frags(stage_ptr(ring + 1), 0, 0);
+                        }
+                        mma_step(kk & 1);
+                    }
+                } else {
+                    // ragged last stage of an operand pair: only the k-steps that hold contracted elements
+                    mma_step(0);
+#pragma unroll 1
+                    for (int kk = 1; kk < kk_lim; ++kk) {
+                        load_frags(as, kk, 1);
+                        mma_step(1);
+                    }
+                    if (more) {
+                        mbar_wait(full + (ring + 1) % STAGES, ((ring + 1) / STAGES) & 1);
+                        load_frags(stage_ptr(ring + 1), 0, 0);
+                    }
                 }
-                load_frags(0, 0);
+                // every LDS of this stage has been consumed by an issued DMMA: hand the slot back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + ring % STAGES);
+            }
+
+            // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
+            const int* mOffD = tabs + par * (2 * BM + 2 * BN) + BM;
+            const int* nOffD = mOffD + BM + BN;
+            double* __restrict__ Dp = info[par].D;
 #pragma unroll
-                for (int kk = 0; kk < BK / 4; ++kk) {
-                    if (kk + 1 < BK / 4) load_frags(kk + 1, (kk + 1) & 1);
+            for (int mi = 0; mi < MF; ++mi) {
+                const int mo = mOffD[wm + mi * 8 + g];
 #pragma unroll
-                    for (int mi = 0; mi < MF; ++mi) {
+                for (int ni = 0; ni < NF; ++ni) {
 #pragma unroll
-                        for (int ni = 0; ni < NF; ++ni)
-                            dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[kk & 1][mi], b[kk & 1][ni]);
-                        // the next stage's loads ride in the shadow of the DMMA pipe: groups 1..LOAD_GROUPS carry
-                        // the cp.async items (the table entry of each item was fetched one group earlier)
-                        const int grp = kk * MF + mi;
-                        if (do_load && grp >= 1 && grp <= C::LOAD_GROUPS) {
-#pragma unroll
-                            for (int it = (grp - 1) * C::ITEMS / C::LOAD_GROUPS; it < grp * C::ITEMS / C::LOAD_GROUPS; ++it) {
-                                const int cur = pre;
-                                if (it + 1 < C::ITEMS) pre = item_lookup(it + 1);
-                                item_issue(it, cur, fix_a, fix_b, ls, ls + C::A_ELEMS);
-                            }
+                    for (int c = 0; c < 2; ++c) {
+                        const int no = nOffD[wn + ni * 8 + 2 * t4 + c];
+                        if ((mo | no) >= 0) {
+                            double* dst = Dp + (size_t)(mo + no);
+                            double v = alpha * acc[mi][ni][c];
+                            if (beta != 0.0) v += beta * *dst;
+                            *dst = v;
                         }
                     }
                 }
-            } else {
-                // ---- ragged last step of an operand pair: loads first, then only the k-steps that hold data ----
-                if (do_load) {
-                    const int fa = stage_fix_a(), fb = stage_fix_b();
-#pragma unroll
-                    for (int it = 0; it < C::ITEMS; ++it) item_issue(it, item_lookup(it), fa, fb, ls, ls + C::A_ELEMS);
-                }
-#pragma unroll 1
-                for (int kk = 0; kk < kk_lim; ++kk) {
-                    load_frags(kk, 0);
-#pragma unroll
-                    for (int mi = 0; mi < MF; ++mi)
-#pragma unroll
-                        for (int ni = 0; ni < NF; ++ni)
-                            dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[0][mi], b[0][ni]);
-                }
             }
-            cp_async_commit();
-            if (do_load) advance_load_cursor();
-            if (++c_ks == c_steps) {
-                c_ks = 0;
-                if (++c_win == nwin) c_win = 0;
-                c_steps = (c_win == nwin - 1) ? last_steps : KWIN / BK;
-            }
-        }
-        cp_async_wait<0>();
-
-        // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
-        if (!(args.dbg & 4) || acc[0][0][0] == 123.456)
-#pragma unroll
-        for (int mi = 0; mi < MF; ++mi) {
-            const int mo = mOffD[wm + mi * 8 + g];
-#pragma unroll
-            for (int ni = 0; ni < NF; ++ni) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int no = nOffD[wn + ni * 8 + 2 * t4 + c];
-                    if ((mo | no) >= 0) {
-                        double* dst = Dp + (size_t)(mo + no);
-                        double v = alpha * acc[mi][ni][c];
-                        if (beta != 0.0) v += beta * *dst;
-                        *dst = v;
-                    }
-                }
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tab_empty + par);
         }
     }
 }
@@ -390,12 +420,6 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
     }
     int grid = a.total_tiles < max_ctas ? a.total_tiles : max_ctas;
     if (grid < 1) return SIPGPU_OK;
-    static const int dbg = getenv("SIPGPU_DBG") ? atoi(getenv("SIPGPU_DBG")) : 0;
-    if (dbg) {
-        ContractArgs b = a;
-        b.dbg = dbg;
-        contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(b);
-    } else
     contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(a);
     SIP_CUDA(cudaGetLastError());
     count_launch();
@@ -424,25 +448,19 @@ int contract_pick_tile(int M, int N) {
 template <int WM, int WN, int MF, int NF>
 int launch_tile(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int ctas) {
     if (vec) {
-        if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, true, true>>(a, ctas);
-        if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, false, true>>(a, ctas);
-        if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, true, true>>(a, ctas);
-        return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, false, true>>(a, ctas);
+        if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, true, true, true>>(a, ctas);
+        if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, true, false, true>>(a, ctas);
+        if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, false, true, true>>(a, ctas);
+        return launch_cfg<Cfg<WM, WN, MF, NF, false, false, true>>(a, ctas);
     }
-    if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, true, false>>(a, ctas);
-    if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, true, false, false>>(a, ctas);
-    if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, true, false>>(a, ctas);
-    return launch_cfg<Cfg<WM, WN, MF, NF, 32, 2, false, false, false>>(a, ctas);
+    if (a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, true, true, false>>(a, ctas);
+    if (a_kc && !b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, true, false, false>>(a, ctas);
+    if (!a_kc && b_kc) return launch_cfg<Cfg<WM, WN, MF, NF, false, true, false>>(a, ctas);
+    return launch_cfg<Cfg<WM, WN, MF, NF, false, false, false>>(a, ctas);
 }
 
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile) {
     const int ctas = ctx().num_sms;
-    // BK = 32 double-buffered (one barrier per 32 contracted elements)
-    static const int warps16 = getenv("SIPGPU_WARPS16") ? atoi(getenv("SIPGPU_WARPS16")) : 0;  // tuning experiment
-    if (warps16) {
-        if (tile == 1) return launch_tile<8, 2, 2, 5>(a, a_kc, b_kc, vec, ctas);
-        return launch_tile<4, 4, 4, 4>(a, a_kc, b_kc, vec, ctas);
-    }
     if (tile == 1) return launch_tile<4, 2, 4, 5>(a, a_kc, b_kc, vec, ctas);
     return launch_tile<2, 4, 8, 4>(a, a_kc, b_kc, vec, ctas);
 }

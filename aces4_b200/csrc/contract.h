@@ -12,7 +12,6 @@ struct ContractArgs {
     int nprob;
     int total_tiles;
     double alpha, beta;
-    int dbg;  // development ablation flags (SIPGPU_DBG): 1 = no cp.async, 2 = trivial addressing, 4 = no epilogue
     Problem p0;
     Pair pair0;
     Shape s0;
