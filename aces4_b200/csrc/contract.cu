@@ -24,14 +24,29 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+#include <utility>
+
 namespace sipgpu {
 
 namespace {
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+// fragment load with a compile-time byte offset; volatile so that its place between the DMMAs is kept
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];\n" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // 8-byte cp.async with zero-fill when !valid (src-size 0: nothing is read)
@@ -325,63 +340,89 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
 #pragma unroll
                 for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+            // Fragment addressing: per thread one base address for A and one for B inside a stage; the (mi, kk) /
+            // (ni, kk) part is a compile-time immediate.  The LDS.64 of k-step kk+1 are hand-interleaved with the
+            // DMMAs of k-step kk (one load after every second DMMA, volatile asm keeps the order), so a fragment is
+            // always loaded a full k-step before the DMMA that consumes it.
+            const unsigned tiles_s = (unsigned)__cvta_generic_to_shared(tiles);
+            const unsigned a_thr = 8u * (C::A_KC ? (wm + g) * C::LDK + t4 : t4 * C::LDAM + wm + g);
+            const unsigned b_thr = 8u * (C::A_ELEMS + (C::B_KC ? (wn + g) * C::LDK + t4 : t4 * C::LDBN + wn + g));
+            constexpr int A_MI = 8 * (C::A_KC ? 8 * C::LDK : 8), A_KK = 8 * (C::A_KC ? 4 : 4 * C::LDAM);
+            constexpr int B_NI = 8 * (C::B_KC ? 8 * C::LDK : 8), B_KK = 8 * (C::B_KC ? 4 : 4 * C::LDBN);
+            auto stage_addr = [&](int r) { return tiles_s + (unsigned)(r % STAGES) * (unsigned)(C::STAGE_ELEMS * 8); };
             double a[2][MF], b[2][NF];
-            auto load_frags = [&](const double* as, int kk, int buf) {
-                const double* bs = as + C::A_ELEMS;
-#pragma unroll
-                for (int mi = 0; mi < MF; ++mi)
-                    a[buf][mi] = C::A_KC ? as[(wm + mi * 8 + g) * C::LDK + kk * 4 + t4]
-                                         : as[(kk * 4 + t4) * C::LDAM + wm + mi * 8 + g];
-#pragma unroll
-                for (int ni = 0; ni < NF; ++ni)
-                    b[buf][ni] = C::B_KC ? bs[(wn + ni * 8 + g) * C::LDK + kk * 4 + t4]
-                                         : bs[(kk * 4 + t4) * C::LDBN + wn + ni * 8 + g];
+            // load fragment number f (0..MF+NF-1) of k-step KK into buffer BUF
+            auto load_frag = [&](unsigned st, auto kk_c, auto buf_c, auto f_c) {
+                constexpr int KK = decltype(kk_c)::value, BUF = decltype(buf_c)::value, F = decltype(f_c)::value;
+                if constexpr (F < MF) a[BUF][F] = lds_f64<F * A_MI + KK * A_KK>(st + a_thr);
+                else b[BUF][F - MF] = lds_f64<(F - MF) * B_NI + KK * B_KK>(st + b_thr);
             };
-            auto mma_step = [&](int buf) {
-#pragma unroll
-                for (int mi = 0; mi < MF; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < NF; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[buf][mi], b[buf][ni]);
+            auto load_frags_all = [&](unsigned st, auto kk_c, auto buf_c) {
+                [&]<int... F>(std::integer_sequence<int, F...>) {
+                    (load_frag(st, kk_c, buf_c, std::integral_constant<int, F>{}), ...);
+                }(std::make_integer_sequence<int, MF + NF>{});
             };
-            auto stage_ptr = [&](int r) { return tiles + (size_t)(r % STAGES) * C::STAGE_ELEMS; };
+            // the DMMAs of k-step buffer BUF; if PREF, the fragments of (st_next, KKN) are loaded into the other buffer
+            // on the way (one LDS.64 after every second DMMA)
+            auto mma_step = [&](auto buf_c, auto pref_c, unsigned st_next, auto kkn_c) {
+                constexpr int BUF = decltype(buf_c)::value;
+                constexpr bool PREF = decltype(pref_c)::value;
+                [&]<int... Q>(std::integer_sequence<int, Q...>) {
+                    (([&] {
+                         constexpr int mi = Q / NF, ni = Q % NF;
+                         dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[BUF][mi], b[BUF][ni]);
+                         if constexpr (PREF && (Q % 2 == 1) && (Q / 2 < MF + NF))
+                             load_frag(st_next, kkn_c, std::integral_constant<int, 1 - BUF>{}, std::integral_constant<int, Q / 2>{});
+                     }()),
+                     ...);
+                }(std::make_integer_sequence<int, MF * NF>{});
+                static_assert(MF * NF / 2 >= MF + NF, "not enough DMMA slots to carry the next fragments");
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            using I3 = std::integral_constant<int, 3>;
+            static_assert(BK == 16, "the k-step schedule below is written for 4 DMMA k-steps per stage");
 
             // invariant at the top of every step: the stage is full and its first fragments are in buffer 0
             mbar_wait(full + ring % STAGES, (ring / STAGES) & 1);
-            load_frags(stage_ptr(ring), 0, 0);
+            load_frags_all(stage_addr(ring), I0{}, I0{});
             int c_ks = 0;
             for (int j = 0; j < total_steps; ++j, ++ring) {
-                const double* as = stage_ptr(ring);
+                const unsigned st = stage_addr(ring);
                 const bool more = j + 1 < total_steps;
                 const int kk_lim = (c_ks == steps_per_pair - 1) ? last_kk : BK / 4;
                 if (++c_ks == steps_per_pair) c_ks = 0;
                 if (kk_lim == BK / 4) {
-#pragma unroll
-                    for (int kk = 0; kk < BK / 4; ++kk) {
-                        if (kk + 1 < BK / 4) {
-                            load_frags(as, kk + 1, (kk + 1) & 1);
-                        } else if (more) {
-                            // the first fragments of the NEXT stage ride under the last k-step of this one
-                            mbar_wait(full + (ring + 1) % STAGES, ((ring + 1) / STAGES) & 1);
-                            load_frags(stage_ptr(ring + 1), 0, 0);
-                        }
-                        mma_step(kk & 1);
+                    mma_step(I0{}, std::true_type{}, st, I1{});
+                    mma_step(I1{}, std::true_type{}, st, I2{});
+                    mma_step(I0{}, std::true_type{}, st, I3{});
+                    if (more) {
+                        // the first fragments of the NEXT stage ride under the last k-step of this one
+                        mbar_wait(full + (ring + 1) % STAGES, ((ring + 1) / STAGES) & 1);
+                        mma_step(I1{}, std::true_type{}, stage_addr(ring + 1), I0{});
+                    } else {
+                        mma_step(I1{}, std::false_type{}, st, I0{});
                     }
                 } else {
                     // ragged last stage of an operand pair: only the k-steps that hold contracted elements
-                    mma_step(0);
-#pragma unroll 1
-                    for (int kk = 1; kk < kk_lim; ++kk) {
-                        load_frags(as, kk, 1);
-                        mma_step(1);
+                    mma_step(I0{}, std::false_type{}, st, I0{});
+                    if (kk_lim > 1) {
+                        load_frags_all(st, I1{}, I1{});
+                        mma_step(I1{}, std::false_type{}, st, I0{});
+                    }
+                    if (kk_lim > 2) {
+                        load_frags_all(st, I2{}, I0{});
+                        mma_step(I0{}, std::false_type{}, st, I0{});
                     }
                     if (more) {
                         mbar_wait(full + (ring + 1) % STAGES, ((ring + 1) / STAGES) & 1);
-                        load_frags(stage_ptr(ring + 1), 0, 0);
+                        load_frags_all(stage_addr(ring + 1), I0{}, I0{});
                     }
                 }
                 // every LDS of this stage has been consumed by an issued DMMA: hand the slot back
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty + ring % STAGES);
+                if (elect_one()) mbar_arrive(empty + ring % STAGES);
             }
 
             // ---- epilogue: D[perm(m,n)] = alpha*acc (+ beta*D): the output permute of F90:782-785 as a scatter ----
@@ -406,7 +447,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(tab_empty + par);
+            if (elect_one()) mbar_arrive(tab_empty + par);
         }
     }
 }
