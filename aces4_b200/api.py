@@ -88,6 +88,8 @@ def lib():
         L.sipgpu_block_slice.argtypes = [C.c_int, C.c_void_p, c_int_p, C.c_void_p, c_int_p, c_int_p]
         L.sipgpu_block_insert.argtypes = [C.c_int, C.c_void_p, c_int_p, C.c_void_p, c_int_p, c_int_p]
         L.sipgpu_block_permute.argtypes = [C.c_int, c_int_p, c_int_p, C.c_void_p, C.c_void_p]
+        L.sipgpu_permute_batched.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_double]
         L.sipgpu_block_permute_labels.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, C.c_void_p, C.c_void_p]
         L.sipgpu_block_contract.argtypes = [c_int_p, C.c_void_p, C.c_int, c_int_p, C.c_void_p, C.c_int, c_int_p,
                                             C.c_void_p, C.c_int, c_int_p, C.c_double, C.c_double]
@@ -367,6 +369,15 @@ def permute(src, transp, out=None):
         out = DeviceBlock(new_ext)
     _check(lib().sipgpu_block_permute(src.rank, _ia(src.shape), _ia(transp), src.ptr, out.ptr), "sipgpu_block_permute")
     return out
+
+
+def permute_batched(srcs, transp, outs, alpha=1.0, beta=0.0):
+    """outs[i] = alpha * permuted(srcs[i]) + beta * outs[i] for n blocks of identical shape in ONE launch."""
+    shape = srcs[0].shape
+    _check(lib().sipgpu_permute_batched(len(srcs), len(shape), _ia(shape), _ia(transp), _ptr_array([b.ptr for b in srcs]),
+                                        _ptr_array([b.ptr for b in outs]), float(alpha), float(beta)),
+           "sipgpu_permute_batched")
+    return outs
 
 
 def permute_labels(lhs_labels, rhs_labels, rhs, out=None):

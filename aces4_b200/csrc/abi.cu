@@ -431,6 +431,10 @@ int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, 
 int sipgpu_block_permute(int rank, const int* ext, const int* transp, const double* in, double* out) {
     return permute_block(rank, ext, transp, in, out);
 }
+int sipgpu_permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in,
+                           double* const* out, double alpha, double beta) {
+    return permute_batched(n, rank, ext, transp, in, out, alpha, beta);
+}
 int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels, const double* rhs,
                                 double* lhs) {
     if (rank < 0 || rank > 32) return SIPGPU_E_ARG;

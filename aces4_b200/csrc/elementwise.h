@@ -21,6 +21,8 @@ int ew_copy_probe(double* d, const double* s, long long n);
 
 // permute.cu
 int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out);
+int permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in, double* const* out,
+                    double alpha, double beta);
 int permute_plan_debug(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab, int cap);
 
 }  // namespace sipgpu

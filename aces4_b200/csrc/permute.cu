@@ -33,51 +33,123 @@ struct PermArgs {
     const int4* wtab;  // output order: {out offset, position in the tile (input order), ragged coords, -}
 };
 
+// the blocks of one launch: n (in, out) pairs that share the plan; n == 1 travels inline (no upload)
+struct PermBatch {
+    const double* const* in;  // device arrays of n pointers, or nullptr: use in0/out0
+    double* const* out;
+    const double* in0;
+    double* out0;
+    int n;
+    double alpha, beta;  // ACC variants: out = alpha * permuted(in) + beta * out
+};
+
 __device__ __forceinline__ int skew(int e) { return e + (e >> 5); }
 
-__global__ void __launch_bounds__(kPT) permute_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                      const __grid_constant__ PermArgs a) {
+constexpr int kNoLimit = 1 << 15;   // ragged tile extents are < 2^15 (build_plan_host), so this bound never bites
+constexpr int kInvalid = 0xffff;    // ragged-coordinate marker of a slot beyond the tile volume: fails every bound
+
+// A CTA is persistent over (block, tile) work items.  The position of an element inside a tile is the same in every
+// tile, so each thread reads ITS table entries (EPT elements: offsets in the input, in the output and in the staged
+// tile) ONCE into registers; the tile loop itself is table-free: EPT independent coalesced loads in flight per
+// thread, one barrier, EPT coalesced stores.  (The first version re-read the tables per element and tile: every
+// global load hung off a table load, and the kernel sat at 60 % of the copy bandwidth on long-scoreboard stalls.)
+template <int EPT, bool RAG, bool ACC>
+__global__ void __launch_bounds__(kPT, (EPT == 4 ? 4 : EPT == 8 ? 3 : 2) - (RAG || ACC ? 1 : 0)) permute_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
-    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        long long t = tile;
-        int bin = 0, bout = 0, lim0 = 1 << 16, lim1 = 1 << 16;
+    int r_off[EPT], w_off[EPT], w_pos[EPT], r_rag[RAG ? EPT : 1], w_rag[RAG ? EPT : 1];
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+        const int e = tid + u * kPT;
+        r_off[u] = w_off[u] = w_pos[u] = 0;
+        if (RAG) r_rag[u] = w_rag[u] = kInvalid;
+        if (e < a.V) {
+            const int2 r = __ldg(a.rtab + e);
+            const int4 w = __ldg(a.wtab + e);
+            r_off[u] = r.x;
+            w_off[u] = w.x;
+            w_pos[u] = skew(w.y);
+            if (RAG) { r_rag[u] = r.y; w_rag[u] = w.z; }
+        }
+    }
+    // is slot u of this thread a real element of the tile (and, for ragged tiles, inside the block)?
+    auto r_ok = [&](int u, int lim0, int lim1) {
+        if constexpr (RAG) return (r_rag[u] & 0xffff) < lim0 && (r_rag[u] >> 16) < lim1;
+        else return tid + u * kPT < a.V;
+    };
+    auto w_ok = [&](int u, int lim0, int lim1) {
+        if constexpr (RAG) return (w_rag[u] & 0xffff) < lim0 && (w_rag[u] >> 16) < lim1;
+        else return tid + u * kPT < a.V;
+    };
+    const long long total = a.ntiles * b.n;
+    for (long long work = blockIdx.x; work < total; work += gridDim.x) {
+        const int blk = (int)(work / a.ntiles);
+        long long t = work - (long long)blk * a.ntiles;
+        int bin = 0, bout = 0, lim0 = kNoLimit, lim1 = kNoLimit;
 #pragma unroll 1
         for (int d = 0; d < a.rank; ++d) {
             const int c = (int)(t % a.ntile[d]);
             t /= a.ntile[d];
             bin += c * a.tstep_in[d];
             bout += c * a.tstep_out[d];
-            if (d == a.rag_dim[0]) lim0 = min(a.rag_te[0], a.rag_ext[0] - c * a.rag_te[0]);
-            if (d == a.rag_dim[1]) lim1 = min(a.rag_te[1], a.rag_ext[1] - c * a.rag_te[1]);
+            if (RAG) {
+                if (d == a.rag_dim[0]) lim0 = min(a.rag_te[0], a.rag_ext[0] - c * a.rag_te[0]);
+                if (d == a.rag_dim[1]) lim1 = min(a.rag_te[1], a.rag_ext[1] - c * a.rag_te[1]);
+            }
         }
-        const double* src = in + bin;
-        double* dst = out + bout;
-        constexpr int U = 4;
-        for (int e0 = tid; e0 < a.V; e0 += kPT * U) {
-            double v[U];
-            bool ok[U];
+        const double* __restrict__ src = (b.in ? b.in[blk] : b.in0) + bin;
+        double* __restrict__ dst = (b.in ? b.out[blk] : b.out0) + bout;
+        double v[EPT];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * kPT;
-                ok[u] = false;
-                if (e < a.V) {
-                    const int2 r = __ldg(a.rtab + e);
-                    ok[u] = (r.y & 0xffff) < lim0 && (r.y >> 16) < lim1;
-                    if (ok[u]) v[u] = __ldg(src + r.x);
-                }
+        for (int u = 0; u < EPT; ++u) {
+            const bool ok = r_ok(u, lim0, lim1);
+            if (ok) v[u] = __ldg(src + r_off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) sm[skew(tid + u * kPT)] = v[u];
+        __syncthreads();
+        if (ACC) {
+            double o[EPT];
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const bool ok = w_ok(u, lim0, lim1);
+                if (ok) o[u] = dst[w_off[u]];
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u]) sm[skew(e0 + u * kPT)] = v[u];
-        }
-        __syncthreads();
-        for (int e = tid; e < a.V; e += kPT) {
-            const int4 w = __ldg(a.wtab + e);
-            if ((w.z & 0xffff) < lim0 && (w.z >> 16) < lim1) dst[w.x] = sm[skew(w.y)];
+            for (int u = 0; u < EPT; ++u) {
+                const bool ok = w_ok(u, lim0, lim1);
+                if (ok) dst[w_off[u]] = b.alpha * sm[w_pos[u]] + b.beta * o[u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const bool ok = w_ok(u, lim0, lim1);
+                if (ok) dst[w_off[u]] = sm[w_pos[u]];
+            }
         }
         __syncthreads();
     }
+}
+
+template <int EPT>
+int launch_perm(const PermArgs& a, const PermBatch& b, bool acc, int grid, size_t smem, cudaStream_t st) {
+    const bool rag = a.rag_dim[0] >= 0;
+    if (rag) {
+        if (acc) permute_kernel<EPT, true, true><<<grid, kPT, smem, st>>>(a, b);
+        else permute_kernel<EPT, true, false><<<grid, kPT, smem, st>>>(a, b);
+    } else {
+        if (acc) permute_kernel<EPT, false, true><<<grid, kPT, smem, st>>>(a, b);
+        else permute_kernel<EPT, false, false><<<grid, kPT, smem, st>>>(a, b);
+    }
+    return SIPGPU_OK;
+}
+
+inline int skew_host(int e) { return e + (e >> 5); }
+// d = alpha * s + beta * d for the degenerate (identity) permutation
+int ew_axpby(double* d, const double* s, long long n, double alpha, double beta) {
+    if (beta == 0.0) return ew_scale_copy(d, s, n, alpha);
+    if (beta != 1.0) SIP_TRY(ew_scale(d, n, beta));
+    return ew_axpy(d, s, n, alpha);
 }
 
 struct PlanEntry {
@@ -234,18 +306,26 @@ int permute_plan_debug(int rank, const int* ext, const int* transp, long long* m
     return SIPGPU_OK;
 }
 
-int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out) {
-    if (rank < 0 || !in || !out) return SIPGPU_E_ARG;
+// n blocks of identical shape and permutation: out_i = alpha * permuted(in_i) + beta * out_i in ONE launch.
+// alpha = 1, beta = 0 is the plain transpose (tensor_block_copy_); beta != 0 is the fused permute-accumulate of
+// `X[b,j,a,i] += R[a,i,b,j]` bodies (interpreter.cpp:1874-1997 permutes into a temp block and adds).
+int permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in, double* const* out,
+                    double alpha, double beta) {
+    if (n < 0 || rank < 0 || !in || !out) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
     SIP_TRY(ensure_init());
     Ctx& c = ctx();
-    if (rank == 0) {
-        SIP_CUDA(cudaMemcpyAsync(out, in, sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-        return SIPGPU_OK;
-    }
+    for (int i = 0; i < n; ++i)
+        if (!in[i] || !out[i]) return SIPGPU_E_ARG;
+    const bool acc = !(alpha == 1.0 && beta == 0.0);
     PermShape ps;
-    SIP_TRY(build_perm_shape(rank, ext, transp, &ps));
-    if (ps.rank <= 1) {  // identity after collapsing: straight copy (F90:478-491)
-        SIP_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * (size_t)ps.total, cudaMemcpyDeviceToDevice, c.stream));
+    if (rank == 0) { ps.rank = 0; ps.total = 1; }
+    else SIP_TRY(build_perm_shape(rank, ext, transp, &ps));
+    if (ps.rank <= 1) {  // identity after collapsing: straight copy (F90:478-491) or axpby
+        for (int i = 0; i < n; ++i) {
+            if (!acc) SIP_CUDA(cudaMemcpyAsync(out[i], in[i], sizeof(double) * (size_t)ps.total, cudaMemcpyDeviceToDevice, c.stream));
+            else SIP_TRY(ew_axpby(out[i], in[i], ps.total, alpha, beta));
+        }
         return SIPGPU_OK;
     }
     int keyv[1 + 3 * kMaxRank] = {ps.rank};
@@ -262,14 +342,43 @@ int permute_block(int rank, const int* ext, const int* transp, const double* in,
         it = cache().emplace(key, pe).first;
     }
     const PermArgs& a = it->second.args;
-    long long grid = a.ntiles;
-    const long long cap = (long long)c.num_sms * 8;
-    if (grid > cap) grid = cap;
-    const size_t smem = sizeof(double) * (size_t)(a.V + (a.V >> 5) + 1);
-    permute_kernel<<<(int)grid, kPT, smem, c.stream>>>(in, out, a);
+    PermBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n = n;
+    b.alpha = alpha;
+    b.beta = beta;
+    if (n == 1) {
+        b.in0 = in[0];
+        b.out0 = out[0];
+    } else {
+        void *h, *d;
+        SIP_TRY(scratch_reserve(sizeof(void*) * 2 * (size_t)n, &h, &d));
+        memcpy(h, in, sizeof(void*) * n);
+        memcpy((char*)h + sizeof(void*) * n, out, sizeof(void*) * n);
+        SIP_CUDA(cudaMemcpyAsync(d, h, sizeof(void*) * 2 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+        b.in = (const double* const*)d;
+        b.out = (double* const*)((char*)d + sizeof(void*) * n);
+    }
+    const int ept = a.V <= 4 * kPT ? 4 : a.V <= 8 * kPT ? 8 : 16;
+    const size_t smem = sizeof(double) * (size_t)(skew_host(ept * kPT) + 1);  // every thread parks all its EPT slots
+    // persistent CTAs: as many as fit per SM (registers: 4-6 of 256 threads; shared memory: 227 KB / tile)
+    long long per_sm = (long long)(200 * 1024) / (long long)(smem + 1024);
+    const long long reg_cap = (ept == 4 ? 4 : ept == 8 ? 3 : 2) - ((acc || a.rag_dim[0] >= 0) ? 1 : 0);
+    if (per_sm > reg_cap) per_sm = reg_cap;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = a.ntiles * n;
+    if (grid > c.num_sms * per_sm) grid = c.num_sms * per_sm;
+    if (ept == 4) SIP_TRY(launch_perm<4>(a, b, acc, (int)grid, smem, c.stream));
+    else if (ept == 8) SIP_TRY(launch_perm<8>(a, b, acc, (int)grid, smem, c.stream));
+    else SIP_TRY(launch_perm<16>(a, b, acc, (int)grid, smem, c.stream));
     SIP_CUDA(cudaGetLastError());
     count_launch();
     return SIPGPU_OK;
+}
+
+int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out) {
+    if (rank < 0 || !in || !out) return SIPGPU_E_ARG;
+    return permute_batched(1, rank, ext, transp, &in, &out, 1.0, 0.0);
 }
 
 }  // namespace sipgpu

@@ -127,6 +127,13 @@ int sipgpu_block_permute(int rank, const int* ext, const int* transp, const doub
 int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels,
                                 const double* rhs, double* lhs);
 
+/* n blocks of identical extents and permutation in ONE launch: out_i = alpha * permuted(in_i) + beta * out_i.
+ * alpha = 1, beta = 0 is n transposes; beta != 0 is the fused permute-accumulate that handle_block_add
+ * (interpreter.cpp:1874-1997) performs as "permute into a temp block, then add" (e.g. the
+ * `T2new[b,j,a,i] += R[a,i,b,j]` bodies of rlccd_rhf.sialx:558-603).  in/out are HOST arrays of n device pointers. */
+int sipgpu_permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in,
+                           double* const* out, double alpha, double beta);
+
 /* contraction with the Lyakh pattern of get_contraction_ptrn_ (F90:662-796).  D = alpha*L*R + beta*D;
  * the reference op is alpha = 1, beta = 0 (assign, F90:752).  beta != 0 is the fused-accumulate
  * extension (contract followed by block_add / put +=). */

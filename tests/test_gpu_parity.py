@@ -151,6 +151,34 @@ def test_permutes_other_ranks(sip, oracle, rank):
         assert np.array_equal(out, oracle.block_copy(a, transp)), (shape, perm)
 
 
+@pytest.mark.parametrize("shape", [(50, 20, 50, 20), (13, 30, 7, 9), (64, 64, 16, 3), (70, 70, 70)])
+def test_permute_batched_and_accumulate(sip, oracle, shape):
+    """n blocks per launch, plain and fused permute-accumulate (out = alpha * P(in) + beta * out), incl. tiles of
+    every element-per-thread class and ragged tiles."""
+    rng = np.random.default_rng(11)
+    pyrng = random.Random(5)
+    n = 7
+    for trial in range(6):
+        perm = list(range(len(shape)))
+        pyrng.shuffle(perm)
+        transp = [1] + [p + 1 for p in perm]
+        new_shape = [0] * len(shape)
+        for i, p in enumerate(perm):
+            new_shape[p] = shape[i]
+        ins = [rand_block(rng, shape) for _ in range(n)]
+        outs0 = [rand_block(rng, new_shape) for _ in range(n)]
+        d_in = [sip.DeviceBlock.from_numpy(x) for x in ins]
+        d_out = [sip.DeviceBlock.from_numpy(x) for x in outs0]
+        sip.permute_batched(d_in, transp, d_out)
+        for x, d in zip(ins, d_out):
+            assert np.array_equal(d.to_numpy(), oracle.block_copy(x, transp)), (shape, perm)
+        d_out = [sip.DeviceBlock.from_numpy(x) for x in outs0]
+        sip.permute_batched(d_in, transp, d_out, alpha=-0.5, beta=2.0)
+        for x, o, d in zip(ins, outs0, d_out):
+            ref = -0.5 * oracle.block_copy(x, transp) + 2.0 * o
+            assert relerr(d.to_numpy(), ref) <= 1e-14, (shape, perm)
+
+
 def test_permute_host_abi_and_large(sip, oracle):
     rng = np.random.default_rng(3)
     a = rand_block(rng, (50, 20, 50, 20))
