@@ -109,6 +109,7 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
     memset(&a, 0, sizeof(a));
     SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &a.s0));
     a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
+    if (contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) < ctx().num_sms) a.s0.tile = kSmallTile;  // spread a small block
     a.nprob = 1;
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
@@ -148,7 +149,13 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         }
         pshape[i] = it->second;
     }
-    for (int variant = 0; variant < 16; ++variant) {
+    {   // a work-list that cannot fill the SMs with large tiles runs on 64x64 tiles (two CTAs per SM)
+        long long total = 0;
+        for (int i = 0; i < n; ++i) total += contract_tile_count(shapes[pshape[i]].M, shapes[pshape[i]].N, shapes[pshape[i]].tile);
+        if (total < ctx().num_sms)
+            for (Shape& sh : shapes) sh.tile = kSmallTile;
+    }
+    for (int variant = 0; variant < 24; ++variant) {
         const bool a_kc = variant & 1, b_kc = variant & 2, vec = variant & 4;
         const int tile = variant >> 3;
         std::vector<Problem> probs;
@@ -492,6 +499,7 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
     a.pair0.L = A; a.pair0.R = B; a.p0.D = C; a.p0.chain_len = 1;
     s.vec = (k % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) ? 1 : 0;
     s.tile = contract_pick_tile(m, n);
+    if (contract_tile_count(m, n, s.tile) < ctx().num_sms) s.tile = kSmallTile;
     a.total_tiles = tiles_of(s);
     return launch_contract(a, true, true, s.vec != 0, s.tile);
 }

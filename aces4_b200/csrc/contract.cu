@@ -142,13 +142,17 @@ struct Cfg {
     static constexpr size_t OFF_INFO = OFF_KTAB + (size_t)2 * KWIN * 4;
     static constexpr size_t OFF_BARS = OFF_INFO + 2 * sizeof(TileInfo);
     static constexpr size_t SMEM = OFF_BARS + (size_t)(2 * STAGES + 4) * 8;
-    static_assert(NC == 256 && A_PER >= 1 && B_PER >= 1, "thread mapping");
+    // 8 consumer warps: one CTA per SM, registers rebalanced with setmaxnreg (56 / 224).  4 consumer warps (the 64x64
+    // tile for launches with fewer tiles than SMs): two CTAs per SM, 56 / 200.
+    static constexpr int MIN_CTAS = NC == 256 ? 1 : 2;
+    static constexpr int CONSUMER_REGS = NC == 256 ? kConsumerRegs : 200;  // 128*(56+200) = 256*128: half an SM
+    static_assert((NC == 256 || NC == 128) && A_PER >= 1 && B_PER >= 1, "thread mapping");
     static_assert(KWIN % BK == 0 && LDK % 16 == 4 && LDAM % 16 == 4 && LDBN % 16 == 4, "window / bank layout");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS)
 contract_kernel(const __grid_constant__ ContractArgs args) {
     constexpr int BM = C::BM, BN = C::BN, BK = C::BK, STAGES = C::STAGES, MF = C::MF, NF = C::NF, KWIN = C::KWIN;
     constexpr int NP = C::NP;
@@ -320,7 +324,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
         asm volatile("cp.async.wait_all;\n" ::: "memory");
     } else {
         // =====================================  CONSUMERS  =====================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kConsumerRegs));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::CONSUMER_REGS));
         const int ctid = tid - NP, lane = ctid & 31, warp = ctid >> 5;
         const int g = lane >> 2, t4 = lane & 3;
         const int wm = (warp % C::WARPS_M) * (MF * 8), wn = (warp / C::WARPS_M) * (NF * 8);
@@ -459,6 +463,7 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
         SIP_CUDA(cudaFuncSetAttribute(contract_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_set = true;
     }
+    max_ctas *= C::MIN_CTAS;
     int grid = a.total_tiles < max_ctas ? a.total_tiles : max_ctas;
     if (grid < 1) return SIPGPU_OK;
     contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(a);
@@ -469,10 +474,17 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
 
 }  // namespace
 
-// Tile menu: 0 = 128x128 (8 warps of 64x32), 1 = 128x80 (8 warps of 32x40: N = 400 = o*o segments tile exactly)
+// Tile menu: 0 = 128x128 (8 consumer warps of 64x32), 1 = 128x80 (8 warps of 32x40: N = 400 = o*o segments tile
+// exactly), 2 = 64x64 (4 consumer warps of 32x32, two CTAs per SM): chosen by the launcher when a launch has fewer
+// large tiles than SMs (single small blocks -- the one-block-per-opcode calls of an unmodified interpreter)
 void contract_tile_dims(int tile, int* bm, int* bn) {
-    *bm = 128;
-    *bn = tile == 1 ? 80 : 128;
+    *bm = tile == 2 ? 64 : 128;
+    *bn = tile == 1 ? 80 : tile == 2 ? 64 : 128;
+}
+long long contract_tile_count(int M, int N, int tile) {
+    int bm, bn;
+    contract_tile_dims(tile, &bm, &bn);
+    return (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn);
 }
 int contract_pick_tile(int M, int N) {
     long long best = -1;
@@ -502,6 +514,7 @@ int launch_tile(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int ctas)
 
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile) {
     const int ctas = ctx().num_sms;
+    if (tile == 2) return launch_tile<2, 2, 4, 4>(a, a_kc, b_kc, vec, ctas);
     if (tile == 1) return launch_tile<4, 2, 4, 5>(a, a_kc, b_kc, vec, ctas);
     return launch_tile<2, 4, 8, 4>(a, a_kc, b_kc, vec, ctas);
 }

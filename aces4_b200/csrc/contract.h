@@ -23,6 +23,8 @@ void contract_tile_dims(int tile, int* bm, int* bn);
 // aligned operand pointers)
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile);
 int contract_pick_tile(int M, int N);
+long long contract_tile_count(int M, int N, int tile);
+constexpr int kSmallTile = 2;  // 64x64, for launches that cannot fill the SMs with large tiles
 int dmma_probe(int iters, double* tflops);
 
 }  // namespace sipgpu

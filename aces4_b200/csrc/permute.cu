@@ -54,7 +54,7 @@ constexpr int kInvalid = 0xffff;    // ragged-coordinate marker of a slot beyond
 // thread, one barrier, EPT coalesced stores.  (The first version re-read the tables per element and tile: every
 // global load hung off a table load, and the kernel sat at 60 % of the copy bandwidth on long-scoreboard stalls.)
 template <int EPT, bool RAG, bool ACC>
-__global__ void __launch_bounds__(kPT, (EPT == 4 ? 4 : EPT == 8 ? 3 : 2) - (RAG || ACC ? 1 : 0)) permute_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b) {
+__global__ void __launch_bounds__(kPT, (EPT <= 4 ? 4 : EPT <= 8 ? 3 : 2) - (RAG || ACC ? 1 : 0)) permute_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     int r_off[EPT], w_off[EPT], w_pos[EPT], r_rag[RAG ? EPT : 1], w_rag[RAG ? EPT : 1];
@@ -176,6 +176,12 @@ int build_plan_host(const PermShape& ps, PermArgs* out, std::vector<int2>& rt, s
             const int d = order[i];
             int c = (int)((need + cur - 1) / cur);
             if (c > ps.ext[d]) c = ps.ext[d];
+            // a short dimension is taken whole (run still <= 64 elements): full-length contiguous runs and no ragged
+            // remainder tile, e.g. extent 50 is one run of 50 rather than 32 + 18
+            if (c < ps.ext[d] && cur * ps.ext[d] <= 64) c = ps.ext[d];
+            // otherwise prefer the next divisor of the extent (no ragged remainder) while the run stays <= 64
+            for (int q = c; q < ps.ext[d] && cur * q <= 64; ++q)
+                if (ps.ext[d] % q == 0) { c = q; break; }
             if (c > te[d]) te[d] = c;
             cur *= te[d];
         }
@@ -191,6 +197,9 @@ int build_plan_host(const PermShape& ps, PermArgs* out, std::vector<int2>& rt, s
             if (te[d] < ps.ext[d]) {
                 int c = te[d] * 2;
                 if (c > ps.ext[d]) c = ps.ext[d];
+                // step to a divisor of the extent when one is near (keeps the dimension free of ragged tiles)
+                for (int q = te[d] + 1; q <= 3 * te[d] && q <= ps.ext[d]; ++q)
+                    if (ps.ext[d] % q == 0 && ps.ext[d] % te[d] == 0) { c = q; break; }
                 if (vol() / te[d] * c > kWidenTo) return false;
                 te[d] = c;
                 return true;
@@ -359,18 +368,25 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
         b.in = (const double* const*)d;
         b.out = (double* const*)((char*)d + sizeof(void*) * n);
     }
-    const int ept = a.V <= 4 * kPT ? 4 : a.V <= 8 * kPT ? 8 : 16;
+    int ept = 16;
+    for (int cand : {4, 6, 8, 10, 12})
+        if (a.V <= cand * kPT) { ept = cand; break; }
     const size_t smem = sizeof(double) * (size_t)(skew_host(ept * kPT) + 1);  // every thread parks all its EPT slots
     // persistent CTAs: as many as fit per SM (registers: 4-6 of 256 threads; shared memory: 227 KB / tile)
     long long per_sm = (long long)(200 * 1024) / (long long)(smem + 1024);
-    const long long reg_cap = (ept == 4 ? 4 : ept == 8 ? 3 : 2) - ((acc || a.rag_dim[0] >= 0) ? 1 : 0);
+    const long long reg_cap = (ept <= 4 ? 4 : ept <= 8 ? 3 : 2) - ((acc || a.rag_dim[0] >= 0) ? 1 : 0);
     if (per_sm > reg_cap) per_sm = reg_cap;
     if (per_sm < 1) per_sm = 1;
     long long grid = a.ntiles * n;
     if (grid > c.num_sms * per_sm) grid = c.num_sms * per_sm;
-    if (ept == 4) SIP_TRY(launch_perm<4>(a, b, acc, (int)grid, smem, c.stream));
-    else if (ept == 8) SIP_TRY(launch_perm<8>(a, b, acc, (int)grid, smem, c.stream));
-    else SIP_TRY(launch_perm<16>(a, b, acc, (int)grid, smem, c.stream));
+    switch (ept) {
+        case 4: SIP_TRY(launch_perm<4>(a, b, acc, (int)grid, smem, c.stream)); break;
+        case 6: SIP_TRY(launch_perm<6>(a, b, acc, (int)grid, smem, c.stream)); break;
+        case 8: SIP_TRY(launch_perm<8>(a, b, acc, (int)grid, smem, c.stream)); break;
+        case 10: SIP_TRY(launch_perm<10>(a, b, acc, (int)grid, smem, c.stream)); break;
+        case 12: SIP_TRY(launch_perm<12>(a, b, acc, (int)grid, smem, c.stream)); break;
+        default: SIP_TRY(launch_perm<16>(a, b, acc, (int)grid, smem, c.stream)); break;
+    }
     SIP_CUDA(cudaGetLastError());
     count_launch();
     return SIPGPU_OK;

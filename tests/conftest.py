@@ -18,3 +18,21 @@ def oracle():
 
     o.lib()
     return o
+
+
+def sial_patterns():
+    """The distinct contraction label patterns of the reference's SIAL programs (tests/golden/
+    sial_contraction_patterns.txt, produced by scripts/extract_sial_patterns.py from src/sialx/qm):
+    list of (dlabels, llabels, rlabels, kinds-by-label dict, where)."""
+    out = []
+    path = os.path.join(ROOT, "tests", "golden", "sial_contraction_patterns.txt")
+    for line in open(path):
+        if line.startswith("#") or not line.strip():
+            continue
+        d, l, r, kinds, count, where = line.split()
+        labs = []
+        for c in d + l + r:
+            if c not in labs:
+                labs.append(c)
+        out.append((d, l, r, dict(zip(labs, kinds)), where))
+    return out

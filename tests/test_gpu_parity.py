@@ -273,6 +273,23 @@ def test_sial_cc_patterns(sip, oracle, o, v):
         check_contraction(sip, oracle, rng, [num[c] for c in dl], [num[c] for c in ll], [num[c] for c in rl], ext)
 
 
+@pytest.mark.parametrize("sizes", [dict(o=4, v=6, p=5, n=7, x=2, s=2), dict(o=20, v=24, p=9, n=13, x=1, s=3)])
+def test_all_sial_patterns_golden(sip, oracle, sizes):
+    """All 170 distinct contraction patterns of the reference's CC / (T) / EOM SIAL programs (tests/golden/
+    sial_contraction_patterns.txt) through the fused kernel, against the oracle, at 1e-10."""
+    from conftest import sial_patterns
+
+    rng = np.random.default_rng(sizes["o"])
+    oracle.use_openblas(8)
+    try:
+        for d, l, r, kinds, where in sial_patterns():
+            num = {c: i + 1 for i, c in enumerate(kinds)}
+            ext = {num[c]: sizes[k] for c, k in kinds.items()}
+            check_contraction(sip, oracle, rng, [num[c] for c in d], [num[c] for c in l], [num[c] for c in r], ext)
+    finally:
+        oracle.use_naive_gemm()
+
+
 @pytest.mark.parametrize("s", [16, 24])
 def test_sweep_rank4_full_cross_product_sample(sip, oracle, s):
     # config 4 of BASELINE.json: D[p0..p3] = L[..]*R[..], 2 contracted indices, sampled across destination
