@@ -485,6 +485,58 @@ def insert_block(t, s, beg):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Boundary 3b: elementwise CC super-instructions on device blocks (reference calling convention)
+# ----------------------------------------------------------------------------------------------------
+def set_predefined_int_array(name, values):
+    _check(lib().sipgpu_set_predefined_int_array(name.encode(), len(values), _ia(values)), "sipgpu_set_predefined_int_array")
+
+
+def _si_arg(block, index_values=None):
+    """The 6-tuple (array_slot, rank, index_values, size, extents, data) of one super-instruction argument."""
+    rank = block.rank if block.shape != () else 0
+    iv = list(index_values) if index_values is not None else [1] * max(rank, 1)
+    return [C.byref(C.c_int(0)), C.byref(C.c_int(rank)), _ia(iv), C.byref(C.c_int(block.size)), _ia(block.shape or (1,)),
+            C.c_void_p(block.ptr)]
+
+
+def _si_call(fn, what, *blocks_and_ivs):
+    args = []
+    for blk, iv in blocks_and_ivs:
+        args += _si_arg(blk, iv)
+    ierr = C.c_int(0)
+    rc = fn(*args, C.byref(ierr))
+    assert rc == ierr.value
+    return rc
+
+
+def si_energy_denominator_rhf(block, index_values, fock):
+    return _si_call(lib().sipgpu_si_energy_denominator_rhf, "energy_denominator_rhf", (block, index_values), (fock, None))
+
+
+def si_stripi(x, iv0, y, iv1):
+    return _si_call(lib().sipgpu_si_stripi, "stripi", (x, iv0), (y, iv1))
+
+
+def si_anti_symm_o(block, index_values):
+    return _si_call(lib().sipgpu_si_anti_symm_o, "anti_symm_o", (block, index_values))
+
+
+def si_anti_symm_v(block, index_values):
+    return _si_call(lib().sipgpu_si_anti_symm_v, "anti_symm_v", (block, index_values))
+
+
+def si_return_sval(block, scalar_block):
+    args = _si_arg(block) + [C.byref(C.c_int(0)), C.byref(C.c_int(0)), _ia([1]), C.byref(C.c_int(1)), _ia([1]),
+                             C.c_void_p(scalar_block.ptr)]
+    ierr = C.c_int(0)
+    return lib().sipgpu_si_return_sval(*args, C.byref(ierr))
+
+
+def si_invert_diagonal(a1, a2):
+    return _si_call(lib().sipgpu_si_invert_diagonal, "invert_diagonal", (a1, None), (a2, None))
+
+
+# ----------------------------------------------------------------------------------------------------
 # Boundary 4: distributed arrays
 # ----------------------------------------------------------------------------------------------------
 def layout_block_number(nseg, idx):

@@ -479,6 +479,43 @@ int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int dr
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
 
+// ---- boundary 3b: elementwise CC super-instructions (superinstr.cu), reference calling convention ----
+int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) { return si_set_int_array(name, n, values); }
+#define SI_RETURN(expr)                   \
+    do {                                  \
+        const int rc__ = (expr);          \
+        if (ierr) *ierr = rc__;           \
+        return rc__;                      \
+    } while (0)
+int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
+                                     int*, int*, int* extents_1, double* data_1, int* ierr) {
+    if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_energy_denominator_rhf(*rank_0, index_values_0, extents_0, data_0, *rank_1, extents_1, data_1));
+}
+int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
+                     int* index_values_1, int*, int* extents_1, double* data_1, int* ierr) {
+    if (!rank_0 || !rank_1 || *rank_0 != *rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_stripi(*rank_0, index_values_0, extents_0, data_0, index_values_1, extents_1, data_1));
+}
+int sipgpu_si_anti_symm_o(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
+    if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_anti_symm_o(*rank_0, index_values_0, extents_0, data_0));
+}
+int sipgpu_si_anti_symm_v(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
+    if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_anti_symm_v(*rank_0, index_values_0, extents_0, data_0));
+}
+int sipgpu_si_return_sval(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
+                          double* data_1, int* ierr) {
+    if (!rank_0 || !rank_1 || *rank_1 != 0) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_return_sval(*rank_0, extents_0, data_0, data_1));
+}
+int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
+                              double* data_1, int* ierr) {
+    if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SI_RETURN(si_invert_diagonal(*rank_0, *rank_1, extents_0, data_0, data_1));
+}
+
 int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
                     double* C, int ldc) {
     SIP_TRY(ensure_init());

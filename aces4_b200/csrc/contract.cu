@@ -204,13 +204,19 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 mbar_arrive(tab_full + par);
                 break;
             }
-            // ---- which block of the work-list does this tile belong to? (uniform binary search) ----
+            // ---- which block of the work-list does this tile belong to?  32-way search: every lane probes one split
+            // point of the prefix-sum array, so a work-list of 32K blocks costs 3 dependent loads instead of 15 ----
             int p = 0;
             if (args.nprob > 1) {
+                const int lane = tid & 31;
                 int lo = 0, hi = args.nprob;  // tile_prefix[lo] <= tile < tile_prefix[hi]
                 while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(args.tile_prefix + mid) <= tile) lo = mid; else hi = mid;
+                    const int step = (hi - lo + 31) / 32;
+                    const int idx = lo + (lane + 1) * step;
+                    const bool le = idx < hi && __ldg(args.tile_prefix + idx) <= tile;
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, le));  // monotone: the lanes with `le` are a prefix
+                    lo += cnt * step;
+                    hi = min(hi, lo + step);
                 }
                 p = lo;
             }

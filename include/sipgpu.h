@@ -180,6 +180,37 @@ int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long 
                               int cap);
 
 /* ---------------------------------------------------------------------------------------------
+ * Boundary 3b -- elementwise CC super-instructions on DEVICE blocks, with the reference's super-instruction
+ * calling convention (src/sip/worker/special_instructions.h:27-97): per argument the 6-tuple
+ * (array_slot, rank, index_values, size, extents, data) passed by reference, then ierr.  `data` are DEVICE
+ * pointers (resident blocks); everything else is host memory.  ierr: 0 = ok, else SIPGPU_E_*; the int return
+ * value repeats it.  The routines are asynchronous on the compute stream.  They replace the Fortran routines
+ * named in each comment; the maintainer registers them under the same SIAL names.
+ * The predefined int array "moa_seg_ranges" that the Fortran code fetches through the sip_interface upcall
+ * (sip_interface.h:17-35) is registered once per run with sipgpu_set_predefined_int_array.
+ * --------------------------------------------------------------------------------------------- */
+int sipgpu_set_predefined_int_array(const char* name, int n, const int* values);
+/* qm-generic/energy_denominator_rhf.F:15-460  (special energy_denominator_rhf ur): array_0 /= eps(Fock diagonal);
+ * array_0 rank 2, 4 or 6; array_1 = Fock array, rank 1 (diagonal) or 2 (full matrix, device) */
+int sipgpu_si_energy_denominator_rhf(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                                     int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
+                                     int* ierr);
+/* qm/utility/stripi.F (special stripi ru): array_1 (one index thick in its stripped dimensions) = the matching
+ * strip of array_0; ranks 2-4 */
+int sipgpu_si_stripi(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                     int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1, int* ierr);
+/* qm/utility/anti_symm_o.F / anti_symm_v.F: antisymmetrise a rank-4 block [a,i,b,j] in (i,j) / (a,b) in place */
+int sipgpu_si_anti_symm_o(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0, int* ierr);
+int sipgpu_si_anti_symm_v(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0, int* ierr);
+/* qm/utility/return_sval.F (special return_sval rw): device scalar data_1[0] = last element of the rank-1/2 block */
+int sipgpu_si_return_sval(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                          int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1, int* ierr);
+/* qm/utility/invert_diagonal.F (special invert_diagonal ur): array_0 /= array_1 where array_1 != 0; ranks 3, 5 */
+int sipgpu_si_invert_diagonal(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                              int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
+                              int* ierr);
+
+/* ---------------------------------------------------------------------------------------------
  * Boundary 4 -- distributed / served arrays (SialOpsParallel method set, src/sip/worker/
  * sial_ops_parallel.cpp:39-99,132-171,232-284,332-408,549-565; owner rule data_distribution.cpp:19-82 and
  * array_table.cpp:50-97).  One process per GPU; every GPU is worker AND owner (no server ranks).  Each

@@ -22,8 +22,8 @@ c_dbl_p = C.POINTER(C.c_double)
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "tensor_dil_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("tensor_dil_oracle.c", "super_instr_oracle.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -210,3 +210,37 @@ def fill_hash(shape, seed, tag, scale=1.0):
     a = np.empty(shape, dtype=np.float64, order="F")
     lib().oracle_fill_hash(_dp(a), C.c_longlong(a.size), C.c_ulonglong(seed), C.c_ulonglong(tag), C.c_double(scale))
     return a
+
+
+# ----------------------------------------------------------------------------------------------------
+# elementwise CC super-instructions (oracle/super_instr_oracle.c); blocks are modified IN PLACE like the reference
+# ----------------------------------------------------------------------------------------------------
+def si_energy_denominator_rhf(block, index_values, fock, moa_seg_ranges):
+    fock = np.asfortranarray(fock, dtype=np.float64)
+    ierr = lib().oracle_si_energy_denominator_rhf(block.ndim, _ia(index_values), _ia(block.shape), _dp(block), fock.ndim,
+                                                  fock.shape[0], _dp(fock), _ia(moa_seg_ranges))
+    return ierr
+
+
+def si_stripi(x, iv0, y_shape, iv1, moa_seg_ranges):
+    y = np.zeros(y_shape, order="F")
+    ierr = lib().oracle_si_stripi(x.ndim, _ia(iv0), _ia(x.shape), _dp(x), _ia(iv1), _ia(y_shape), _dp(y), _ia(moa_seg_ranges))
+    return y, ierr
+
+
+def si_anti_symm_o(block, index_values, moa_seg_ranges):
+    return lib().oracle_si_anti_symm_o(block.ndim, _ia(index_values), _ia(block.shape), _dp(block), _ia(moa_seg_ranges))
+
+
+def si_anti_symm_v(block, index_values, moa_seg_ranges):
+    return lib().oracle_si_anti_symm_v(block.ndim, _ia(index_values), _ia(block.shape), _dp(block), _ia(moa_seg_ranges))
+
+
+def si_return_sval(block):
+    out = C.c_double(0)
+    ierr = lib().oracle_si_return_sval(block.ndim, _ia(block.shape), _dp(block), C.byref(out))
+    return out.value, ierr
+
+
+def si_invert_diagonal(a1, a2):
+    return lib().oracle_si_invert_diagonal(a1.ndim, a2.ndim, _ia(a1.shape), _dp(a1), _dp(a2))

@@ -21,6 +21,18 @@ elif mode == "ring":
                                 [Ls[i % 8].ptr for i in range(nb)], [Rs[(i * 3) % 8].ptr for i in range(nb)], [d.ptr for d in Ds])
     for _ in range(3):
         bc.launch()
+elif mode == "small":
+    # block-sparse batching regime: nb blocks of s^4 (GEMM (s^2)^3) in one launch
+    s_ = n
+    nb = 37 * 24
+    Ls = [api.DeviceBlock((s_,) * 4).fill(0.5) for _ in range(8)]
+    Rs = [api.DeviceBlock((s_,) * 4).fill(0.25) for _ in range(8)]
+    Ds = [api.DeviceBlock((s_,) * 4) for _ in range(nb)]
+    ptrn, _ = api.get_contraction_ptrn([1, 2, 3, 4], [1, 2, 5, 6], [5, 6, 3, 4])
+    bc = api.BatchedContraction(ptrn, [(s_,) * 4] * nb, [(s_,) * 4] * nb, [(s_,) * 4] * nb,
+                                [Ls[i % 8].ptr for i in range(nb)], [Rs[(i * 3) % 8].ptr for i in range(nb)], [d.ptr for d in Ds])
+    for _ in range(3):
+        bc.launch()
 elif mode == "permute":
     shape = (64, 64, 64, 64) if n >= 64 else (50, 20, 50, 20)
     a, b = api.DeviceBlock(shape).fill(1.0), api.DeviceBlock(shape)

@@ -70,6 +70,7 @@ for s in sizes + ["ragged"]:
         ptrn, ierr = api.get_contraction_ptrn([num[c] for c in d], [num[c] for c in l], [num[c] for c in r])
         assert ierr == 0
         nb = int(max(1, min(2048, np.ceil(30e9 / flops))))
+        nb = 37 * int(np.ceil(nb / 37))  # whole waves of tiles on 148 SMs (4 | tiles per block at uniform s)
         pool = 8
         Ls = [api.DeviceBlock(lsh).fill_hash(1, i, 1.0) for i in range(pool)]
         Rs = [api.DeviceBlock(rsh).fill_hash(2, i, 1.0) for i in range(pool)]

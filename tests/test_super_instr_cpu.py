@@ -1,0 +1,127 @@
+"""CPU tests of the super-instruction oracle (oracle/super_instr_oracle.c) against independent numpy statements of
+energy_denominator_rhf.F, stripi.F, anti_symm_o/v.F, return_sval.F and invert_diagonal.F."""
+import numpy as np
+import pytest
+
+SEGS = [3, 4, 2, 5]  # moa_seg_ranges: extents of the MO segments; global offsets 0, 3, 7, 9
+
+
+def offs(iv):
+    return [sum(SEGS[: v - 1]) for v in iv]
+
+
+@pytest.mark.parametrize("fock_rank", [1, 2])
+@pytest.mark.parametrize("iv", [(1, 2), (2, 1, 3, 4), (4, 4, 1, 2)])
+def test_energy_denominator(oracle, fock_rank, iv):
+    rng = np.random.default_rng(len(iv) + fock_rank)
+    n = sum(SEGS)
+    diag = np.sort(rng.uniform(-2.0, 3.0, n)) + np.arange(n)  # distinct orbital energies
+    fock = diag.copy() if fock_rank == 1 else np.asfortranarray(np.diag(diag) + 1e-3 * rng.uniform(-1, 1, (n, n)))
+    if fock_rank == 2:
+        diag = np.diag(fock).copy()
+    shape = [SEGS[v - 1] for v in iv]
+    blk = np.asfortranarray(rng.uniform(-1, 1, shape))
+    ref = blk.copy()
+    o = offs(iv)
+    for idx in np.ndindex(*shape):
+        e = [diag[idx[d] + o[d]] for d in range(len(iv))]
+        eps = (e[1] - e[0]) if len(iv) == 2 else (e[1] + e[3] - e[0] - e[2])
+        ref[idx] = ref[idx] / eps
+    assert oracle.si_energy_denominator_rhf(blk, iv, fock, SEGS) == 0
+    assert np.array_equal(blk, ref)
+
+
+def test_energy_denominator_rank6_simple_indices(oracle):
+    rng = np.random.default_rng(6)
+    n = sum(SEGS)
+    fock = np.asfortranarray(np.diag(np.arange(1.0, n + 1) * 1.5))
+    iv = (2, 1, 3, 2, 5, 7)          # last two are simple indices (extent 1): offset = value - 1
+    shape = [4, 3, 2, 4, 1, 1]
+    blk = np.asfortranarray(rng.uniform(-1, 1, shape))
+    ref = blk.copy()
+    o = offs(iv[:4]) + [iv[4] - 1, iv[5] - 1]
+    d = np.diag(fock)
+    for idx in np.ndindex(*shape):
+        e = [d[idx[k] + o[k]] for k in range(6)]
+        ref[idx] /= e[1] + e[3] + e[5] - e[0] - e[2] - e[4]
+    assert oracle.si_energy_denominator_rhf(blk, iv, fock, SEGS) == 0
+    assert np.array_equal(blk, ref)
+    assert oracle.si_energy_denominator_rhf(np.zeros((2, 2, 2), order="F"), (1, 1, 1), fock, SEGS) == 1  # rank 3: unsupported
+
+
+def test_stripi(oracle):
+    rng = np.random.default_rng(1)
+    # TSaiai[a2,i1,a,j1] (segments 2,1,4,2) -> tppps[a2,i1,a,jj] with the simple index jj = global occupied index
+    iv0 = (2, 1, 4, 2)
+    x = np.asfortranarray(rng.uniform(-1, 1, [SEGS[v - 1] for v in iv0]))
+    for jj in (4, 5, 6, 7):  # global range of segment 2 is 4..7
+        y, ierr = oracle.si_stripi(x, iv0, (4, 3, 5, 1), (2, 1, 4, jj), SEGS)
+        assert ierr == 0
+        assert np.array_equal(y[..., 0], x[..., jj - 4])
+    assert oracle.si_stripi(x, iv0, (4, 3, 5, 1), (2, 1, 4, 8), SEGS)[1] == 2  # the reference aborts: index outside the block
+    # rank 3 with TWO stripped dimensions: a size-1 segment in the middle + the simple index
+    segs = [3, 1, 4]
+    x3 = np.asfortranarray(rng.uniform(-1, 1, (3, 1, 4)))
+    lib_y, ierr = oracle.si_stripi(x3, (1, 2, 3), (3, 1, 1), (1, 2, 6), segs)
+    assert ierr == 0 and np.array_equal(lib_y[:, 0, 0], x3[:, 0, 6 - 5])
+
+
+def test_anti_symm(oracle):
+    rng = np.random.default_rng(2)
+    segs = [4, 3]
+    for iv in ((1, 2, 1, 2), (1, 1, 1, 1)):
+        shape = [segs[v - 1] for v in iv]
+        x0 = np.asfortranarray(rng.uniform(-1, 1, shape))
+        xo = x0.copy(order="F")
+        assert oracle.si_anti_symm_o(xo, iv, segs) == 0
+        ref = x0.copy()
+        for a, i, b, j in np.ndindex(*shape):
+            if i < j:
+                ref[a, j, b, i] = -x0[a, i, b, j]
+        for a, i, b, j in np.ndindex(*shape):
+            if i == j or a == b:
+                ref[a, i, b, j] = 0.0
+        assert np.array_equal(xo, ref)
+        xv = x0.copy(order="F")
+        assert oracle.si_anti_symm_v(xv, iv, segs) == 0
+        ref = x0.copy()
+        for a, i, b, j in np.ndindex(*shape):
+            if a < b:
+                ref[b, i, a, j] = -x0[a, i, b, j]
+        for a, i, b, j in np.ndindex(*shape):
+            if i == j or a == b:
+                ref[a, i, b, j] = 0.0
+        assert np.array_equal(xv, ref)
+    assert oracle.si_anti_symm_o(np.zeros((2, 2), order="F"), (1, 1), segs) == 1
+
+
+def test_anti_symm_v_simple_index_case(oracle):
+    # i range == 1:1 (anti_symm_v.F special case): mirror and write -0.0 on the a == b diagonal, i == j is NOT zeroed
+    segs = [1, 3]
+    iv = (2, 1, 2, 1)
+    x0 = np.asfortranarray(np.arange(1.0, 10.0).reshape(3, 1, 3, 1, order="F"))
+    x = x0.copy(order="F")
+    assert oracle.si_anti_symm_v(x, iv, segs) == 0
+    for a in range(3):
+        for b in range(3):
+            if a < b:
+                assert x[b, 0, a, 0] == -x0[a, 0, b, 0] and x[a, 0, b, 0] == x0[a, 0, b, 0]
+        assert x[a, 0, a, 0] == 0.0 and np.signbit(x[a, 0, a, 0])
+
+
+def test_return_sval_and_invert_diagonal(oracle):
+    rng = np.random.default_rng(3)
+    a = np.asfortranarray(rng.uniform(-1, 1, (1, 1)))
+    assert oracle.si_return_sval(a) == (a[0, 0], 0)
+    v = np.asfortranarray(rng.uniform(-1, 1, (5,)))
+    assert oracle.si_return_sval(v) == (v[4], 0)          # doreturn1: array1(a2)
+    m = np.asfortranarray(rng.uniform(-1, 1, (3, 4)))
+    assert oracle.si_return_sval(m) == (m[2, 3], 0)        # doreturn2: array1(a2,b2)
+    for shape in ((3, 4, 2), (2, 3, 1, 2, 3)):
+        a1 = np.asfortranarray(rng.uniform(-1, 1, shape))
+        a2 = np.asfortranarray(rng.uniform(-1, 1, shape))
+        a2[tuple(0 for _ in shape)] = 0.0
+        ref = np.where(a2 != 0.0, a1 / np.where(a2 != 0.0, a2, 1.0), a1)
+        assert oracle.si_invert_diagonal(a1, a2) == 0
+        assert np.array_equal(a1, ref)
+    assert oracle.si_invert_diagonal(np.zeros((2, 2), order="F"), np.zeros((2, 2), order="F")) == 1
