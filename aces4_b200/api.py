@@ -398,6 +398,22 @@ def contract(ptrn, L, R, dext, out=None, alpha=1.0, beta=0.0):
     return out
 
 
+def contract_sliced(ptrn, L, lext, lbeg, R, rext, rbeg, dext, out=None, dbeg=None, alpha=1.0, beta=0.0):
+    """D = alpha * L[slice] * R[slice] + beta * D where L / R (/ out when dbeg is given) are PARENT arrays and
+    (ext, beg) select the block inside them (beg None: the operand is a dense block of extents ext)."""
+    if out is None:
+        out = DeviceBlock(dext)
+    def par(blk, beg):
+        return (_ia(blk.shape), _ia(beg)) if beg is not None else (None, None)
+    lp, lb = par(L, lbeg)
+    rp, rb = par(R, rbeg)
+    dp, db = par(out, dbeg)
+    _check(lib().sipgpu_block_contract_sliced(_ia(ptrn), C.c_void_p(L.ptr), len(lext), _ia(lext), lp, lb, C.c_void_p(R.ptr),
+                                              len(rext), _ia(rext), rp, rb, C.c_void_p(out.ptr), len(dext), _ia(dext), dp, db,
+                                              C.c_double(alpha), C.c_double(beta)), "sipgpu_block_contract_sliced")
+    return out
+
+
 def contract_labels(dlab, dext, llab, L, rlab, R, out=None, alpha=1.0, beta=0.0):
     """D[dlab] = alpha * L[llab]*R[rlab] + beta*D  (handle_contraction; reference op is alpha=1, beta=0)."""
     if out is None:

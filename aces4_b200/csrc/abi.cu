@@ -99,27 +99,54 @@ int contract_degenerate(const int* ptrn, const double* L, int lrank, const int* 
     return scaled_by_device_scalar(D, tmp.p, n, S, alpha, beta);
 }
 
-int contract_device(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
-                    const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+// Every operand may be a slice of a larger dense array: (*par = parent extents, *beg = 0-based first element of the
+// slice in the parent; nullptr = dense block).
+int contract_device_sliced(const int* ptrn, const double* L, int lrank, const int* lext, const int* lpar, const int* lbeg,
+                           const double* R, int rrank, const int* rext, const int* rpar, const int* rbeg, double* D, int drank,
+                           const int* dext, const int* dpar, const int* dbeg, double alpha, double beta) {
     SIP_TRY(ensure_init());
     if (!L || !R || !D || lrank < 0 || rrank < 0 || drank < 0 || lrank > 32 || rrank > 32 || drank > 32) return SIPGPU_E_ARG;
-    if (lrank == 0 || rrank == 0 || drank == 0)
+    if (lrank == 0 || rrank == 0 || drank == 0) {
+        if (lpar || rpar || dpar) return SIPGPU_E_ARG;  // scalar-operand forms take dense blocks only
         return contract_degenerate(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+    }
+    auto base_offset = [](int rank, const int* ext, const int* par, const int* beg, long long* off) {
+        *off = 0;
+        if (!par) return beg ? SIPGPU_E_ARG : SIPGPU_OK;
+        long long s = 1;
+        for (int i = 0; i < rank; ++i) {
+            const int b = beg ? beg[i] : 0;
+            if (b < 0 || b + ext[i] > par[i]) return SIPGPU_E_ARG;
+            *off += s * b;
+            s *= par[i];
+        }
+        return SIPGPU_OK;
+    };
+    long long ol, orr, od;
+    SIP_TRY(base_offset(lrank, lext, lpar, lbeg, &ol));
+    SIP_TRY(base_offset(rrank, rext, rpar, rbeg, &orr));
+    SIP_TRY(base_offset(drank, dext, dpar, dbeg, &od));
     ContractArgs a;
     memset(&a, 0, sizeof(a));
-    SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &a.s0));
+    SIP_TRY(build_shape_strided(ptrn, lrank, lext, lpar, rrank, rext, rpar, drank, dext, dpar, &a.s0));
     a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
     if (contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) < ctx().num_sms) a.s0.tile = kSmallTile;  // spread a small block
     a.nprob = 1;
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
     a.beta = beta;
-    a.pair0.L = L;
-    a.pair0.R = R;
-    a.p0.D = D;
+    a.pair0.L = L + ol;
+    a.pair0.R = R + orr;
+    a.p0.D = D + od;
     a.p0.chain_len = 1;
-    const bool vec = a.s0.vec && (((uintptr_t)L | (uintptr_t)R) & 15) == 0;
+    const bool vec = a.s0.vec && (((uintptr_t)a.pair0.L | (uintptr_t)a.pair0.R) & 15) == 0;
     return launch_contract(a, a.s0.a_kc, a.s0.b_kc, vec, a.s0.tile);
+}
+
+int contract_device(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                    const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    return contract_device_sliced(ptrn, L, lrank, lext, nullptr, nullptr, R, rrank, rext, nullptr, nullptr, D, drank, dext,
+                                  nullptr, nullptr, alpha, beta);
 }
 
 // n destination blocks; destination i sums the operand pairs chain_start[i] .. chain_start[i+1]-1 of L[]/R[].
@@ -464,6 +491,14 @@ int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, do
     int ptrn[64];
     SIP_TRY(labels_to_ptrn(drank, dlab, lrank, llab, rrank, rlab, ptrn));
     return sipgpu_block_contract(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+}
+int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, const int* lext, const int* lparent_ext,
+                                 const int* lbeg, const double* R, int rrank, const int* rext, const int* rparent_ext,
+                                 const int* rbeg, double* D, int drank, const int* dext, const int* dparent_ext,
+                                 const int* dbeg, double alpha, double beta) {
+    const int rc = contract_device_sliced(ptrn, L, lrank, lext, lparent_ext, lbeg, R, rrank, rext, rparent_ext, rbeg, D, drank,
+                                          dext, dparent_ext, dbeg, alpha, beta);
+    return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
 int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                             const int* dext, const double* const* L, const double* const* R, double* const* D,

@@ -90,16 +90,37 @@ int tidy(Dim* d, int n) {
 
 int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank, const int* dext,
                 Shape* out) {
+    return build_shape_strided(ptrn, lrank, lext, nullptr, rrank, rext, nullptr, drank, dext, nullptr, out);
+}
+
+// As build_shape, but every operand may be a SLICE of a larger dense array: *par are the extents of the parent array
+// (nullptr: the block is dense).  Strides come from the parent, extents from the slice; the caller offsets the base
+// pointer to the slice's first element.  This is how `T[a,i,mu,j] = T2[a,i,b,j] * ca[mu,b]` reads the block of the
+// static array `ca` in place instead of extracting it first (contiguous_array_manager.cpp:202-230, F90:271-330).
+int build_shape_strided(const int* ptrn, int lrank, const int* lext, const int* lpar, int rrank, const int* rext,
+                        const int* rpar, int drank, const int* dext, const int* dpar, Shape* out) {
     if (lrank < 1 || rrank < 1 || drank < 1 || lrank > 32 || rrank > 32 || drank > 32) return SIPGPU_E_ARG;
     if (!contr_ptrn_ok(ptrn, lrank, rrank, drank, lext, rext, dext)) return 1;
     long long sL[32], sR[32], sD[32], s = 1;
-    for (int i = 0; i < lrank; ++i) { sL[i] = s; s *= lext[i]; }
+    bool even_l = true, even_r = true;  // all non-unit strides even (16-byte fetches stay aligned row to row)
+    for (int i = 0; i < lrank; ++i) {
+        if (lpar && lpar[i] < lext[i]) return SIPGPU_E_ARG;
+        sL[i] = s; s *= lpar ? lpar[i] : lext[i];
+        if (sL[i] != 1 && (sL[i] & 1)) even_l = false;
+    }
     if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
     s = 1;
-    for (int i = 0; i < rrank; ++i) { sR[i] = s; s *= rext[i]; }
+    for (int i = 0; i < rrank; ++i) {
+        if (rpar && rpar[i] < rext[i]) return SIPGPU_E_ARG;
+        sR[i] = s; s *= rpar ? rpar[i] : rext[i];
+        if (sR[i] != 1 && (sR[i] & 1)) even_r = false;
+    }
     if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
     s = 1;
-    for (int i = 0; i < drank; ++i) { sD[i] = s; s *= dext[i]; }
+    for (int i = 0; i < drank; ++i) {
+        if (dpar && dpar[i] < dext[i]) return SIPGPU_E_ARG;
+        sD[i] = s; s *= dpar ? dpar[i] : dext[i];
+    }
     if (s <= 0 || s >= (1LL << 31)) return SIPGPU_E_ARG;
 
     Dim md[32], nd[32], kd[32];
@@ -145,7 +166,7 @@ int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const in
     // dimension boundary and stay 16-byte aligned (given a 16-byte aligned block).
     const bool a_vec = sh.a_kc ? (sh.kext[0] % 2 == 0) : (nm > 0 && sh.msL[0] == 1 && sh.mext[0] % 2 == 0);
     const bool b_vec = sh.b_kc ? (sh.kext[0] % 2 == 0) : (nn > 0 && sh.nsR[0] == 1 && sh.next[0] % 2 == 0);
-    sh.vec = (a_vec && b_vec) ? 1 : 0;
+    sh.vec = (a_vec && b_vec && (!lpar || even_l) && (!rpar || even_r)) ? 1 : 0;
     *out = sh;
     return 0;
 }

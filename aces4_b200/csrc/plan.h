@@ -50,6 +50,8 @@ int get_contraction_ptrn(int drank, int lrank, int rrank, const int* aces_ptrn, 
 // Requires lrank,rrank,drank >= 1 (rank-0 operands are routed to the dot/axpy kernels by the caller).
 int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank, const int* dext,
                 Shape* out);
+int build_shape_strided(const int* ptrn, int lrank, const int* lext, const int* lpar, int rrank, const int* rext,
+                        const int* rpar, int drank, const int* dext, const int* dpar, Shape* out);
 bool contr_ptrn_ok(const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                    const int* dext);
 

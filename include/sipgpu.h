@@ -144,6 +144,15 @@ int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, do
                                  const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
                                  const double* R, double alpha, double beta);
 
+/* Contraction whose operands may be SLICES of larger dense (static / contiguous) arrays, read and written in place:
+ * X points to the parent array, Xparent_ext are its extents, Xbeg the 0-based first element of the block inside it
+ * (both NULL: X is a dense block).  Replaces "extract_slice into a temp block, contract, free" for every use of a
+ * static array block such as ca[mu,p] (contiguous_array_manager.cpp:162-230, block.cpp:272-323, F90:271-392). */
+int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, const int* lext, const int* lparent_ext,
+                                 const int* lbeg, const double* R, int rrank, const int* rext, const int* rparent_ext,
+                                 const int* rbeg, double* D, int drank, const int* dext, const int* dparent_ext,
+                                 const int* dbeg, double alpha, double beta);
+
 /* Batched contraction: n blocks in ONE launch per kernel variant.  All problems share rank/pattern
  * (`ptrn`), extents may differ per problem: lext/rext/dext are [n][rank] row-major arrays; L/R/D are
  * arrays of n device pointers; alpha/beta apply to all.  This is the pardo-body work-list entry point

@@ -319,6 +319,38 @@ def test_ragged_and_eom_shapes(sip, oracle):
     check_contraction(sip, oracle, rng, [1], [1, 2, 3], [3, 2], {1: 33, 2: 12, 3: 7})
 
 
+def test_contract_sliced_static_arrays(sip, oracle):
+    """Operands that are blocks of a static (contiguous) array, read in place: the reference extracts the block
+    (tensor_block_slice_, F90:271-330), contracts and frees it; the fused kernel reads the parent array through its
+    strides.  Half transformation T[a,i,mu,j] = T2[a,i,b,j] * ca[mu,b] with ca a (norb x nmo) static array, and a
+    destination written in place as a slice (insert fused as well)."""
+    rng = np.random.default_rng(21)
+    norb, nmo, v, o = 37, 44, 12, 5
+    ca = rand_block(rng, (norb, nmo))
+    T2 = rand_block(rng, (v, o, v, o))
+    dca, dT2 = sip.DeviceBlock.from_numpy(ca), sip.DeviceBlock.from_numpy(T2)
+    ptrn, ierr = sip.get_contraction_ptrn([1, 2, 5, 4], [1, 2, 3, 4], [5, 3])
+    assert ierr == 0
+    for (mu0, nmu, b0) in ((0, 13, 5), (13, 13, 17), (26, 11, 32), (1, 12, 20)):  # even / odd offsets and extents
+        ca_blk, ierr = oracle.block_slice(ca, (nmu, v), (mu0, b0))  # what the reference does first (block.cpp:272-297)
+        assert ierr == 0 and np.array_equal(ca_blk, ca[mu0:mu0 + nmu, b0:b0 + v])
+        ref, ierr = oracle.block_contract(ptrn, T2, ca_blk, (v, o, nmu, o))
+        assert ierr == 0
+        got = sip.contract_sliced(ptrn, dT2, (v, o, v, o), None, dca, (nmu, v), (mu0, b0), (v, o, nmu, o))
+        assert relerr(got.to_numpy(), ref) <= 1e-10
+        # destination as a slice of a larger array [v, o, norb, o], accumulate form
+        big = rand_block(rng, (v, o, norb, o))
+        dbig = sip.DeviceBlock.from_numpy(big)
+        sip.contract_sliced(ptrn, dT2, (v, o, v, o), None, dca, (nmu, v), (mu0, b0), (v, o, nmu, o), out=dbig,
+                            dbeg=(0, 0, mu0, 0), alpha=0.5, beta=1.0)
+        want = big.copy(order="F")
+        want[:, :, mu0:mu0 + nmu, :] += 0.5 * ref
+        assert relerr(dbig.to_numpy(), want) <= 1e-10
+    # a slice that does not fit its parent is an argument error, not a wild read
+    with pytest.raises(sip.SipGpuError):
+        sip.contract_sliced(ptrn, dT2, (v, o, v, o), None, dca, (13, v), (30, 0), (v, o, 13, o))
+
+
 def test_scalar_operand_cases(sip, oracle):
     # F90:764-780: rank-0 operands
     rng = np.random.default_rng(11)
