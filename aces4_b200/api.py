@@ -131,6 +131,10 @@ def lib():
         L.sipgpu_array_fill_local.argtypes = [C.c_void_p, C.c_double]
         L.sipgpu_array_local_bytes.argtypes = [C.c_void_p]
         L.sipgpu_array_local_bytes.restype = C.c_size_t
+        L.sipgpu_wl_begin.argtypes = [C.c_int]
+        L.sipgpu_wl_set_limits.argtypes = [C.c_longlong, C.c_longlong]
+        L.sipgpu_wl_stats.argtypes = [C.POINTER(C.c_longlong)]
+        L.sipgpu_wl_last_plan.argtypes = [C.c_int, c_int_p, c_int_p]
         _LIB = L
     return _LIB
 
@@ -470,6 +474,58 @@ class BatchedContraction:
                                              self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
                                              self.dext.ctypes.data_as(c_int_p), self.L, self.R, self.D, float(alpha),
                                              float(beta)), "sipgpu_contract_batched")
+
+
+# ----------------------------------------------------------------------------------------------------
+# Boundary 3c: deferred op stream (worklist.cu) -- record the per-block calls of a pardo body, launch them batched
+# ----------------------------------------------------------------------------------------------------
+WL_STAT_NAMES = ("recorded", "scheduled", "levels", "launches", "fused_accumulates", "chains", "chain_pairs",
+                 "temps_elided", "flushes")
+
+
+def wl_begin(dry=False):
+    _check(lib().sipgpu_wl_begin(1 if dry else 0), "sipgpu_wl_begin")
+
+
+def wl_flush():
+    _check(lib().sipgpu_wl_flush(), "sipgpu_wl_flush")
+
+
+def wl_end():
+    _check(lib().sipgpu_wl_end(), "sipgpu_wl_end")
+    return wl_stats()
+
+
+def wl_stats():
+    out = (C.c_longlong * 9)()
+    _check(lib().sipgpu_wl_stats(out), "sipgpu_wl_stats")
+    return dict(zip(WL_STAT_NAMES, [int(x) for x in out]))
+
+
+def wl_last_plan():
+    """(level, unit) per recorded op of the most recent flush, in program order."""
+    n = lib().sipgpu_wl_last_plan(0, None, None)
+    lv, un = (C.c_int * max(1, n))(), (C.c_int * max(1, n))()
+    lib().sipgpu_wl_last_plan(n, lv, un)
+    return list(lv)[:n], list(un)[:n]
+
+
+class recording:
+    """`with api.recording(): ...` -- every asynchronous block op issued inside is deferred and batched at exit."""
+
+    def __init__(self, dry=False):
+        self.dry, self.stats = dry, None
+
+    def __enter__(self):
+        wl_begin(self.dry)
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is None:
+            self.stats = wl_end()
+        else:
+            lib().sipgpu_wl_end()
+        return False
 
 
 def dgemm_tn(m, n, k, A, lda, B, ldb, Cblk, ldc, alpha=1.0, beta=0.0):

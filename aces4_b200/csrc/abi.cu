@@ -7,6 +7,10 @@
 #include "elementwise.h"
 #include "plan.h"
 
+#include <array>
+#include <vector>
+#include "worklist.h"
+
 namespace sipgpu {
 namespace {
 
@@ -149,6 +153,8 @@ int contract_device(const int* ptrn, const double* L, int lrank, const int* lext
                                   nullptr, nullptr, alpha, beta);
 }
 
+}  // namespace
+
 // n destination blocks; destination i sums the operand pairs chain_start[i] .. chain_start[i+1]-1 of L[]/R[].
 int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                      const int* dext, const int* chain_start, const double* const* L, const double* const* R,
@@ -230,6 +236,8 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
     return SIPGPU_OK;
 }
 
+namespace {
+
 int labels_to_ptrn(int drank, const int* dlab, int lrank, const int* llab, int rrank, const int* rlab, int* ptrn) {
     int aces[96], k = 0;
     if (drank < 0 || lrank < 0 || rrank < 0 || drank + lrank + rrank > 96) return SIPGPU_E_ARG;
@@ -250,6 +258,7 @@ struct Staged {
     long long n = 0;
     ~Staged() { if (d) pool_free(d); }
     int up(const double* h, long long n_) {
+        SIP_TRY(wl_flush());  // host-pointer calls are blocking: drain a pending recording first
         n = n_;
         d = pool_alloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
         if (!d) return SIPGPU_E_NOMEM;
@@ -415,18 +424,19 @@ int _init_gpu(int* devid, int* my_rank) {
 }
 int _finalize_gpu(void) { return sipgpu_finalize(); }
 double* _gpu_allocate(const int n) { return sipgpu_block_alloc(n, 1); }
-int _gpu_free(double* g) { return pool_free(g); }
+int _gpu_free(double* g) { return sipgpu_block_free(g); }
 int _gpu_host_to_device(double* c_addr, double* g_addr, const int n) { return sipgpu_h2d(g_addr, c_addr, n); }
 int _gpu_device_to_host(double* c_addr, double* g_addr, const int n) { return sipgpu_d2h(c_addr, g_addr, n); }
 int _gpu_device_to_device(double* dst, double* src, const int n) {
-    SIP_TRY(ensure_init());
     if (n < 0) return SIPGPU_E_ARG;
+    if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, dst, src, nullptr, n, 1.0);
+    SIP_TRY(ensure_init());
     SIP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx().stream));
     return SIPGPU_OK;
 }
-int _gpu_double_memset(double* g, double value, const int n) { return ew_fill(g, n, value); }
-int _gpu_selfmultiply(double* x, const double alpha, const int n) { return ew_scale(x, n, alpha); }
-int _gpu_axpy(double* y, double* x, const double alpha, const int n) { return ew_axpy(y, x, n, alpha); }
+int _gpu_double_memset(double* g, double value, const int n) { return sipgpu_block_fill(g, n, value); }
+int _gpu_selfmultiply(double* x, const double alpha, const int n) { return sipgpu_block_scale(x, n, alpha); }
+int _gpu_axpy(double* y, double* x, const double alpha, const int n) { return sipgpu_block_axpy(y, x, n, alpha); }
 int _gpu_permute(double* y, const int ny, const int* y_dims, const int* y_inds, double* x, const int nx, const int* x_dims,
                  const int* x_inds) {
     (void)y_dims;
@@ -439,34 +449,81 @@ int _gpu_contract(double* y, const int ny, const int* y_dims, const int* y_inds,
 }
 
 // ------------------------------------------------ boundary 3 ------------------------------------------------
-int sipgpu_block_fill(double* d, long long n, double v) { return ew_fill(d, n, v); }
-int sipgpu_block_scale(double* d, long long n, double f) { return ew_scale(d, n, f); }
-int sipgpu_block_scale_and_copy(double* d, const double* s, long long n, double f) { return ew_scale_copy(d, s, n, f); }
-int sipgpu_block_increment(double* d, long long n, double delta) { return ew_increment(d, n, delta); }
-int sipgpu_block_accumulate(double* d, const double* s, long long n) { return ew_axpy(d, s, n, 1.0); }
-int sipgpu_block_axpy(double* d, const double* s, long long n, double f) { return ew_axpy(d, s, n, f); }
+// While a work-list recording is open (sipgpu_wl_begin) the asynchronous ops below are recorded instead of launched.
+int sipgpu_block_fill(double* d, long long n, double v) {
+    return wl_active() ? wl_rec_ew(WL_FILL, d, nullptr, nullptr, n, v) : ew_fill(d, n, v);
+}
+int sipgpu_block_scale(double* d, long long n, double f) {
+    return wl_active() ? wl_rec_ew(WL_SCALE, d, nullptr, nullptr, n, f) : ew_scale(d, n, f);
+}
+int sipgpu_block_scale_and_copy(double* d, const double* s, long long n, double f) {
+    if (wl_active()) return s ? wl_rec_ew(WL_SCALE_COPY, d, s, nullptr, n, f) : SIPGPU_E_ARG;
+    return ew_scale_copy(d, s, n, f);
+}
+int sipgpu_block_increment(double* d, long long n, double delta) {
+    return wl_active() ? wl_rec_ew(WL_INCR, d, nullptr, nullptr, n, delta) : ew_increment(d, n, delta);
+}
+int sipgpu_block_axpy(double* d, const double* s, long long n, double f) {
+    if (wl_active()) return s ? wl_rec_ew(WL_AXPY, d, s, nullptr, n, f) : SIPGPU_E_ARG;
+    return ew_axpy(d, s, n, f);
+}
+int sipgpu_block_accumulate(double* d, const double* s, long long n) { return sipgpu_block_axpy(d, s, n, 1.0); }
 int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
+    if (wl_active()) return (l && r) ? wl_rec_ew(WL_ADDSUB, d, l, r, n, sign) : SIPGPU_E_ARG;
     return ew_add_sub(d, l, r, n, sign);
 }
 int sipgpu_block_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale) {
+    if (wl_active())
+        return wl_rec_opaque([=] { return ew_fill_hash(d, n, seed, tag, scale); }, {{d, sizeof(double) * (size_t)n, WL_W}});
     return ew_fill_hash(d, n, seed, tag, scale);
 }
 int sipgpu_block_dot_accumulate(const double* l, const double* r, long long n, double* d_scalar) {
+    if (wl_active())
+        return wl_rec_opaque([=] { return ew_dot_device(l, r, n, d_scalar, 1.0); },
+                             {{l, sizeof(double) * (size_t)n, WL_R}, {r, sizeof(double) * (size_t)n, WL_R}, {d_scalar, 8, WL_RW}});
     return ew_dot_device(l, r, n, d_scalar, 1.0);
 }
-int sipgpu_block_norm2(const double* t, long long n, double* out) { return ew_dot(t, t, n, out); }
-int sipgpu_block_dot(const double* l, const double* r, long long n, double* out) { return ew_dot(l, r, n, out); }
+int sipgpu_block_norm2(const double* t, long long n, double* out) {
+    SIP_TRY(wl_flush());
+    return ew_dot(t, t, n, out);
+}
+int sipgpu_block_dot(const double* l, const double* r, long long n, double* out) {
+    SIP_TRY(wl_flush());
+    return ew_dot(l, r, n, out);
+}
 int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {
+    if (wl_active()) {
+        if (rank < 0 || rank > kMaxRank || !t || !s || !t_ext || !s_ext || !beg) return SIPGPU_E_ARG;
+        std::array<int, kMaxRank> te{}, se{}, bg{};
+        for (int i = 0; i < rank; ++i) te[i] = t_ext[i], se[i] = s_ext[i], bg[i] = beg[i];
+        return wl_rec_opaque([=] { return ew_slice(rank, t, te.data(), s, se.data(), bg.data()); },
+                             {{t, sizeof(double) * (size_t)volume(rank, t_ext), WL_R}, {s, sizeof(double) * (size_t)volume(rank, s_ext), WL_W}});
+    }
     return ew_slice(rank, t, t_ext, s, s_ext, beg);
 }
 int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg) {
+    if (wl_active()) {
+        if (rank < 0 || rank > kMaxRank || !t || !s || !t_ext || !s_ext || !beg) return SIPGPU_E_ARG;
+        std::array<int, kMaxRank> te{}, se{}, bg{};
+        for (int i = 0; i < rank; ++i) te[i] = t_ext[i], se[i] = s_ext[i], bg[i] = beg[i];
+        return wl_rec_opaque([=] { return ew_insert(rank, t, te.data(), s, se.data(), bg.data()); },
+                             {{t, sizeof(double) * (size_t)volume(rank, t_ext), WL_RW}, {s, sizeof(double) * (size_t)volume(rank, s_ext), WL_R}});
+    }
     return ew_insert(rank, t, t_ext, s, s_ext, beg);
 }
 int sipgpu_block_permute(int rank, const int* ext, const int* transp, const double* in, double* out) {
+    if (wl_active() && rank >= 1 && rank <= kMaxRank) return wl_rec_permute(rank, ext, transp, in, out, 1.0, 0.0);
+    SIP_TRY(wl_flush());
     return permute_block(rank, ext, transp, in, out);
 }
 int sipgpu_permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in,
                            double* const* out, double alpha, double beta) {
+    if (wl_active() && rank >= 1 && rank <= kMaxRank) {
+        if (n < 0 || (n && (!in || !out))) return SIPGPU_E_ARG;
+        for (int i = 0; i < n; ++i) SIP_TRY(wl_rec_permute(rank, ext, transp, in[i], out[i], alpha, beta));
+        return SIPGPU_OK;
+    }
+    SIP_TRY(wl_flush());
     return permute_batched(n, rank, ext, transp, in, out, alpha, beta);
 }
 int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels, const double* rhs,
@@ -474,10 +531,39 @@ int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_lab
     if (rank < 0 || rank > 32) return SIPGPU_E_ARG;
     int transp[33];
     SIP_TRY(permutation_from_labels(rank, lhs_labels, rhs_labels, transp));
-    return permute_block(rank, rhs_ext, transp, rhs, lhs);
+    return sipgpu_block_permute(rank, rhs_ext, transp, rhs, lhs);
 }
 int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
                           const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    if (wl_active()) {
+        int rc;
+        if (lrank >= 1 && rrank >= 1 && drank >= 1 && lrank <= kMaxRank && rrank <= kMaxRank && drank <= kMaxRank) {
+            rc = wl_rec_contract(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
+        } else {  // scalar-operand forms (F90:764-780): not batchable, scheduled as they are
+            if (!L || !R || !D || lrank < 0 || rrank < 0 || drank < 0 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank)
+                return SIPGPU_E_ARG;
+            if (!contr_ptrn_ok(ptrn, lrank, rrank, drank, lext, rext, dext)) {
+                rc = 1;
+            } else {
+                std::array<int, 2 * kMaxRank> pt{};
+                std::array<int, kMaxRank> le{}, re{}, de{};
+                for (int i = 0; i < lrank + rrank; ++i) pt[i] = ptrn[i];
+                for (int i = 0; i < lrank; ++i) le[i] = lext[i];
+                for (int i = 0; i < rrank; ++i) re[i] = rext[i];
+                for (int i = 0; i < drank; ++i) de[i] = dext[i];
+                rc = wl_rec_opaque(
+                    [=] { return contract_device(pt.data(), L, lrank, le.data(), R, rrank, re.data(), D, drank, de.data(), alpha, beta); },
+                    {{L, sizeof(double) * (size_t)volume(lrank, lext), WL_R},
+                     {R, sizeof(double) * (size_t)volume(rrank, rext), WL_R},
+                     {D, sizeof(double) * (size_t)volume(drank, dext), beta != 0.0 ? WL_RW : WL_W}});
+            }
+        }
+        if (rc == 1) {
+            set_error("invalid contraction pattern for these extents (contr_ptrn_ok)");
+            return SIPGPU_E_PATTERN;
+        }
+        return rc;
+    }
     const int rc = contract_device(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
     if (rc == 1) {
         set_error("invalid contraction pattern for these extents (contr_ptrn_ok)");
@@ -496,6 +582,41 @@ int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, co
                                  const int* lbeg, const double* R, int rrank, const int* rext, const int* rparent_ext,
                                  const int* rbeg, double* D, int drank, const int* dext, const int* dparent_ext,
                                  const int* dbeg, double alpha, double beta) {
+    if (wl_active()) {
+        if (!L || !R || !D || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank)
+            return SIPGPU_E_ARG;
+        struct Cap {
+            int ptrn[2 * kMaxRank], ext[3][kMaxRank], par[3][kMaxRank], beg[3][kMaxRank];
+            bool has_par[3], has_beg[3];
+        } c;
+        memset(&c, 0, sizeof(c));
+        const int ranks[3] = {lrank, rrank, drank};
+        const int* exts[3] = {lext, rext, dext};
+        const int* pars[3] = {lparent_ext, rparent_ext, dparent_ext};
+        const int* begs[3] = {lbeg, rbeg, dbeg};
+        size_t bytes[3];
+        for (int i = 0; i < lrank + rrank; ++i) c.ptrn[i] = ptrn[i];
+        for (int t = 0; t < 3; ++t) {
+            c.has_par[t] = pars[t] != nullptr;
+            c.has_beg[t] = begs[t] != nullptr;
+            for (int i = 0; i < ranks[t]; ++i) {
+                c.ext[t][i] = exts[t][i];
+                if (pars[t]) c.par[t][i] = pars[t][i];
+                if (begs[t]) c.beg[t][i] = begs[t][i];
+            }
+            bytes[t] = sizeof(double) * (size_t)volume(ranks[t], pars[t] ? pars[t] : exts[t]);  // the whole parent array
+        }
+        return wl_rec_opaque(
+            [=] {
+                const int rc = contract_device_sliced(c.ptrn, L, lrank, c.ext[0], c.has_par[0] ? c.par[0] : nullptr,
+                                                      c.has_beg[0] ? c.beg[0] : nullptr, R, rrank, c.ext[1],
+                                                      c.has_par[1] ? c.par[1] : nullptr, c.has_beg[1] ? c.beg[1] : nullptr, D, drank,
+                                                      c.ext[2], c.has_par[2] ? c.par[2] : nullptr, c.has_beg[2] ? c.beg[2] : nullptr,
+                                                      alpha, beta);
+                return rc == 1 ? SIPGPU_E_PATTERN : rc;
+            },
+            {{L, bytes[0], WL_R}, {R, bytes[1], WL_R}, {D, bytes[2], (beta != 0.0 || dparent_ext) ? WL_RW : WL_W}});
+    }
     const int rc = contract_device_sliced(ptrn, L, lrank, lext, lparent_ext, lbeg, R, rrank, rext, rparent_ext, rbeg, D, drank,
                                           dext, dparent_ext, dbeg, alpha, beta);
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
@@ -503,6 +624,7 @@ int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, co
 int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                             const int* dext, const double* const* L, const double* const* R, double* const* D,
                             double alpha, double beta) {
+    SIP_TRY(wl_flush());  // already a work-list: runs as it is, after whatever was recorded before it
     const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, nullptr, L, R, D, alpha, beta);
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
@@ -510,6 +632,7 @@ int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int dr
                             const int* dext, const int* chain_start, const double* const* L, const double* const* R,
                             double* const* D, double alpha, double beta) {
     if (!chain_start) return SIPGPU_E_ARG;
+    SIP_TRY(wl_flush());
     const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, chain_start, L, R, D, alpha, beta);
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
@@ -525,34 +648,41 @@ int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) 
 int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                                      int*, int*, int* extents_1, double* data_1, int* ierr) {
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());  // super-instructions run in program order after the recorded ops
     SI_RETURN(si_energy_denominator_rhf(*rank_0, index_values_0, extents_0, data_0, *rank_1, extents_1, data_1));
 }
 int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                      int* index_values_1, int*, int* extents_1, double* data_1, int* ierr) {
     if (!rank_0 || !rank_1 || *rank_0 != *rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());
     SI_RETURN(si_stripi(*rank_0, index_values_0, extents_0, data_0, index_values_1, extents_1, data_1));
 }
 int sipgpu_si_anti_symm_o(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());
     SI_RETURN(si_anti_symm_o(*rank_0, index_values_0, extents_0, data_0));
 }
 int sipgpu_si_anti_symm_v(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());
     SI_RETURN(si_anti_symm_v(*rank_0, index_values_0, extents_0, data_0));
 }
 int sipgpu_si_return_sval(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                           double* data_1, int* ierr) {
     if (!rank_0 || !rank_1 || *rank_1 != 0) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());
     SI_RETURN(si_return_sval(*rank_0, extents_0, data_0, data_1));
 }
 int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                               double* data_1, int* ierr) {
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
+    SIP_TRY(wl_flush());
     SI_RETURN(si_invert_diagonal(*rank_0, *rank_1, extents_0, data_0, data_1));
 }
 
 int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
                     double* C, int ldc) {
+    SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (m < 1 || n < 1 || k < 1 || lda < k || ldb < k || ldc < m || !A || !B || !C) return SIPGPU_E_ARG;
     ContractArgs a;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "common.h"
+#include "worklist.h"
 
 namespace sipgpu {
 
@@ -210,10 +211,14 @@ using namespace sipgpu;
 extern "C" {
 
 int sipgpu_init(int device) { return init_on(device); }
-int sipgpu_finalize(void) { return finalize_all(); }
+int sipgpu_finalize(void) {
+    if (sipgpu_wl_recording()) sipgpu_wl_end();
+    return finalize_all();
+}
 int sipgpu_device(void) { return g_ctx.inited ? g_ctx.device : -1; }
 const char* sipgpu_last_error(void) { return g_err; }
 int sipgpu_sync(void) {
+    SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     SIP_CUDA(cudaStreamSynchronize(g_ctx.stream));
     return SIPGPU_OK;
@@ -227,6 +232,7 @@ int sipgpu_pool_reserve(size_t bytes) {
 }
 double* sipgpu_block_alloc(long long n, int zero) {
     if (n < 0) return nullptr;
+    if (wl_active()) return wl_alloc(n, zero);  // a temp of the recorded stream; zeroing becomes a recorded fill
     double* p = pool_alloc(sizeof(double) * (size_t)n);
     if (p && zero && n > 0) {
         if (cudaMemsetAsync(p, 0, sizeof(double) * (size_t)n, g_ctx.stream) != cudaSuccess) {
@@ -237,7 +243,7 @@ double* sipgpu_block_alloc(long long n, int zero) {
     }
     return p;
 }
-int sipgpu_block_free(double* p) { return pool_free(p); }
+int sipgpu_block_free(double* p) { return wl_active() ? wl_free(p) : pool_free(p); }
 int sipgpu_pool_stats(size_t* reserved, size_t* in_use, size_t* n_live) {
     if (reserved) *reserved = g_pool.reserved;
     if (in_use) *in_use = g_pool.in_use;
@@ -245,12 +251,14 @@ int sipgpu_pool_stats(size_t* reserved, size_t* in_use, size_t* n_live) {
     return SIPGPU_OK;
 }
 int sipgpu_h2d(double* g_dst, const double* h_src, long long n) {
+    SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (n < 0 || (n && (!g_dst || !h_src))) return SIPGPU_E_ARG;
     SIP_CUDA(cudaMemcpyAsync(g_dst, h_src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, g_ctx.stream));
     return SIPGPU_OK;
 }
 int sipgpu_d2h(double* h_dst, const double* g_src, long long n) {
+    SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (n < 0 || (n && (!h_dst || !g_src))) return SIPGPU_E_ARG;
     SIP_CUDA(cudaMemcpyAsync(h_dst, g_src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, g_ctx.stream));

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "elementwise.h"
+#include "worklist.h"
 
 struct sipgpu_array {
     int rank = 0;
@@ -172,6 +173,7 @@ int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
     double* src = sipgpu_array_block_ptr(a, idx);
     if (!src || !g_dst) return src ? SIPGPU_E_ARG : SIPGPU_E_STATE;
     const long long n = sipgpu_array_block_size(a, idx);
+    if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, g_dst, src, nullptr, n, 1.0);  // peer loads inside the batched kernel
     // peer read over NVLink when the owner is remote (UVA resolves the direction)
     SIP_CUDA(cudaMemcpyAsync(g_dst, src, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx().stream));
     return SIPGPU_OK;
@@ -180,16 +182,19 @@ int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
     const long long n = sipgpu_array_block_size(a, idx);
+    if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, dst, g_src, nullptr, n, 1.0);
     SIP_CUDA(cudaMemcpyAsync(dst, g_src, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx().stream));
     return SIPGPU_OK;
 }
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src) {
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0);
     return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
 }
 int sipgpu_array_fill_local(sipgpu_array* a, double v) {
     if (!a) return SIPGPU_E_ARG;
+    if (wl_active()) return wl_rec_ew(WL_FILL, a->base[a->my_rank], nullptr, nullptr, a->slab_elems[a->my_rank], v);
     return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
 }
 double* sipgpu_array_local_base(sipgpu_array* a) { return a ? a->base[a->my_rank] : nullptr; }

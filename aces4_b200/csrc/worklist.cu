@@ -1,0 +1,760 @@
+// worklist.cu -- deferred op stream ("SIAL front-end for batching").
+//
+// The reference interpreter dispatches ONE block operation per opcode (interpreter.cpp:98-910): inside a pardo body
+// such as rlccd_rhf.sialx:342-355
+//        do i1 / do j1:  T[a,i,b,j] = T2old[a,i1,b,j1]*V[i,i1,j,j1];  Taibj[a,i,b,j] += T[a,i,b,j]
+// it allocates a temp block, runs one contraction, runs one add, frees the temp -- thousands of times per pardo, each
+// a separate kernel launch if the device ABI is called naively.  Rebuilding the interpreter is out of scope; instead
+// the library lets the unchanged interpreter keep issuing the same per-block calls and defers them:
+//
+//   sipgpu_wl_begin()            at pardo entry (or once per SIAL section)
+//   ... the usual sipgpu_block_* / _gpu_* / sipgpu_array_* calls are RECORDED with their read/write sets ...
+//   sipgpu_wl_end()              at sip_barrier / endpardo (sial_ops_parallel.cpp:39-99): schedule + launch
+//
+// Scheduling (host, O(n log n)):
+//   A. temp forwarding: `T = L*R` (or `T = permute(X)`) whose only consumer is `D += f*T` and whose temp is freed
+//      becomes one fused op `D += f*L*R` (the fused accumulate of contract.cu / the fused permute-accumulate of
+//      permute.cu); the temp is never written.
+//   B. chain fusion: consecutive accumulating contractions into the same destination with the same pattern and
+//      extents become one chained problem -- the sum over contracted SEGMENTS stays in the tile accumulators and the
+//      destination block is written once (sipgpu_contract_chained).
+//   C. levelisation: read/write hazards on device address intervals (RAW, WAR, WAW; red.add accumulates commute with
+//      each other) give every op a level; ops of one level are independent.
+//   D. emission: per level ONE launch per kernel family -- all contractions that share (pattern, alpha, beta) through
+//      the persistent tile walker, all permutes that share (extents, permutation), ALL elementwise ops and put +=
+//      through one descriptor-driven kernel.
+// Program-order semantics are preserved exactly; only floating-point summation order inside fused chains differs
+// from op-at-a-time execution (as it does between the reference's own BLAS builds).
+//
+// A "dry" recording (no device) exists so the scheduler -- pure host logic -- is covered by the CPU test suite.
+#include "worklist.h"
+
+#include <algorithm>
+#include <map>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "contract.h"
+#include "elementwise.h"
+
+namespace sipgpu {
+namespace {
+
+enum Kind { K_CONTRACT, K_PERMUTE, K_EW, K_OPAQUE };
+
+struct Op {
+    int kind = K_EW;
+    bool dead = false;
+    int level = 0;
+    int orig = 0;  // index in the recorded stream
+    double alpha = 1.0, beta = 0.0;
+    // contraction
+    int lrank = 0, rrank = 0, drank = 0;
+    int ptrn[2 * kMaxRank] = {0};
+    int lext[kMaxRank] = {0}, rext[kMaxRank] = {0}, dext[kMaxRank] = {0};
+    long long ln = 0, rn = 0, dn = 0;
+    std::vector<Pair> pairs;
+    double* D = nullptr;
+    // permute
+    int rank = 0;
+    int ext[kMaxRank] = {0};
+    int transp[kMaxRank + 1] = {0};
+    const double* in = nullptr;
+    // elementwise (dest = D, n = dn)
+    int ewop = 0;
+    const double *a = nullptr, *b = nullptr;
+    double f = 0.0;
+    // opaque
+    std::function<int()> fn;
+    std::vector<WlRange> ranges;
+};
+
+struct Temp {
+    long long n = 0;
+    bool freed = false;
+    bool fake = false;  // dry-mode address, not a pool block
+};
+
+struct State {
+    bool on = false, dry = false;
+    std::vector<Op> ops;
+    std::unordered_map<uintptr_t, Temp> temps;  // blocks allocated while recording
+    std::vector<double*> deferred_free;
+    size_t deferred_bytes = 0;
+    size_t max_ops = 1 << 16;
+    size_t max_deferred_bytes = (size_t)8 << 30;
+    uintptr_t fake_next = (uintptr_t)1 << 44;
+    bool in_flush = false;
+    // cumulative statistics since wl_begin
+    long long st_recorded = 0, st_scheduled = 0, st_levels = 0, st_launches = 0, st_fused_acc = 0, st_chains = 0,
+              st_chain_pairs = 0, st_flushes = 0, st_temps_elided = 0;
+    // plan of the last flush, indexed by recorded op
+    std::vector<int> last_level, last_unit;
+};
+State g;
+
+// ---- disjoint interval map over device addresses: last write / read / atomic level per byte range ----
+struct Lv {
+    int w = 0, r = 0, a = 0;
+};
+class IntervalMap {
+    struct Node {
+        uintptr_t end;
+        Lv lv;
+    };
+    std::map<uintptr_t, Node> m_;
+    void split(uintptr_t x) {
+        auto it = m_.upper_bound(x);
+        if (it == m_.begin()) return;
+        --it;
+        if (it->first < x && x < it->second.end) {
+            Node tail = it->second;
+            it->second.end = x;
+            m_.emplace(x, tail);
+        }
+    }
+
+public:
+    template <typename F>
+    void visit(uintptr_t a, uintptr_t b, F f) {  // f(Lv&) over a partition of [a, b); gaps are materialised
+        if (a >= b) return;
+        split(a);
+        split(b);
+        uintptr_t cur = a;
+        auto it = m_.lower_bound(a);
+        while (cur < b) {
+            if (it == m_.end() || it->first > cur) {
+                const uintptr_t e = (it == m_.end() || it->first > b) ? b : it->first;
+                it = m_.emplace_hint(it, cur, Node{e, Lv{}});
+            }
+            f(it->second.lv);
+            cur = it->second.end;
+            ++it;
+        }
+    }
+};
+
+void ranges_of(const Op& o, std::vector<WlRange>& out) {
+    out.clear();
+    switch (o.kind) {
+        case K_CONTRACT:
+            for (const Pair& p : o.pairs) {
+                out.push_back({p.L, sizeof(double) * (size_t)o.ln, WL_R});
+                out.push_back({p.R, sizeof(double) * (size_t)o.rn, WL_R});
+            }
+            out.push_back({o.D, sizeof(double) * (size_t)o.dn, o.beta != 0.0 ? WL_RW : WL_W});
+            break;
+        case K_PERMUTE:
+            out.push_back({o.in, sizeof(double) * (size_t)o.dn, WL_R});
+            out.push_back({o.D, sizeof(double) * (size_t)o.dn, o.beta != 0.0 ? WL_RW : WL_W});
+            break;
+        case K_EW: {
+            const size_t nb = sizeof(double) * (size_t)o.dn;
+            const bool rd = o.ewop == WL_SCALE || o.ewop == WL_INCR || o.ewop == WL_AXPY;
+            if (o.a) out.push_back({o.a, nb, WL_R});
+            if (o.b) out.push_back({o.b, nb, WL_R});
+            out.push_back({o.D, nb, o.ewop == WL_REDADD ? WL_ATOMIC : (rd ? WL_RW : WL_W)});
+            break;
+        }
+        default:
+            out = o.ranges;
+    }
+}
+
+bool same_signature(const Op& x, const Op& y) {
+    return x.kind == K_CONTRACT && y.kind == K_CONTRACT && x.lrank == y.lrank && x.rrank == y.rrank && x.drank == y.drank &&
+           x.alpha == y.alpha && !memcmp(x.ptrn, y.ptrn, sizeof(int) * (x.lrank + x.rrank)) &&
+           !memcmp(x.lext, y.lext, sizeof(int) * x.lrank) && !memcmp(x.rext, y.rext, sizeof(int) * x.rrank) &&
+           !memcmp(x.dext, y.dext, sizeof(int) * x.drank);
+}
+
+// ---- the batched elementwise kernel: one launch for every fill / scale / copy / axpy / add / put += of a level ----
+struct EwDesc {
+    double* d;
+    const double* a;
+    const double* b;
+    long long n;
+    double f;
+    int op;
+    int chunk0;  // first chunk of this descriptor in the launch
+};
+constexpr int kEwThreads = 256;
+constexpr int kEwChunk = 8192;  // elements per CTA work item
+
+__device__ __forceinline__ double ew_apply(int op, double d, double a, double b, double f) {
+    switch (op) {
+        case WL_FILL: return f;
+        case WL_SCALE: return d * f;
+        case WL_SCALE_COPY: return a * f;
+        case WL_INCR: return d + f;
+        case WL_AXPY: return d + a * f;
+        default: return f > 0 ? a + b : a - b;
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads) ew_batched_kernel(const EwDesc* __restrict__ desc, int ndesc, int nchunks) {
+    __shared__ int s_idx;
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        if (threadIdx.x == 0) {  // last descriptor whose chunk0 <= chunk
+            int lo = 0, hi = ndesc - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (desc[mid].chunk0 <= chunk) lo = mid; else hi = mid - 1;
+            }
+            s_idx = lo;
+        }
+        __syncthreads();
+        const EwDesc e = desc[s_idx];
+        __syncthreads();
+        const long long base = (long long)(chunk - e.chunk0) * kEwChunk;
+        const int cnt = (int)min((long long)kEwChunk, e.n - base);
+        double* d = e.d + base;
+        const double* a = e.a ? e.a + base : nullptr;
+        const double* b = e.b ? e.b + base : nullptr;
+        const int op = e.op;
+        if (op == WL_REDADD) {
+            for (int i = threadIdx.x; i < cnt; i += kEwThreads)
+                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(a[i]) : "memory");
+            continue;
+        }
+        const bool rd = op == WL_SCALE || op == WL_INCR || op == WL_AXPY;
+        const bool vec = ((((uintptr_t)e.d | (uintptr_t)e.a | (uintptr_t)e.b) & 15) == 0);
+        if (vec) {
+            const int c2 = cnt >> 1;
+            double2* d2 = reinterpret_cast<double2*>(d);
+            const double2* a2 = reinterpret_cast<const double2*>(a);
+            const double2* b2 = reinterpret_cast<const double2*>(b);
+            constexpr int U = 4;
+            for (int i0 = threadIdx.x; i0 < c2; i0 += U * kEwThreads) {
+                double2 x[U], y[U], z[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * kEwThreads;
+                    x[u] = y[u] = z[u] = make_double2(0, 0);
+                    if (i < c2) {
+                        if (rd) x[u] = d2[i];
+                        if (a) y[u] = a2[i];
+                        if (b) z[u] = b2[i];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * kEwThreads;
+                    if (i < c2)
+                        d2[i] = make_double2(ew_apply(op, x[u].x, y[u].x, z[u].x, e.f), ew_apply(op, x[u].y, y[u].y, z[u].y, e.f));
+                }
+            }
+            if (threadIdx.x == 0 && (cnt & 1)) {
+                const int i = cnt - 1;
+                d[i] = ew_apply(op, rd ? d[i] : 0.0, a ? a[i] : 0.0, b ? b[i] : 0.0, e.f);
+            }
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += kEwThreads)
+                d[i] = ew_apply(op, rd ? d[i] : 0.0, a ? a[i] : 0.0, b ? b[i] : 0.0, e.f);
+        }
+    }
+}
+
+int launch_ew_batch(const std::vector<const Op*>& list) {
+    size_t k = 0;
+    while (k < list.size()) {
+        std::vector<EwDesc> descs;
+        long long chunks = 0;
+        for (; k < list.size() && descs.size() < 32768 && chunks < (1 << 28); ++k) {
+            const Op& o = *list[k];
+            if (o.dn <= 0) continue;
+            descs.push_back(EwDesc{o.D, o.a, o.b, o.dn, o.f, o.ewop, (int)chunks});
+            chunks += (o.dn + kEwChunk - 1) / kEwChunk;
+        }
+        if (descs.empty()) continue;
+        void *h, *d;
+        SIP_TRY(scratch_reserve(sizeof(EwDesc) * descs.size(), &h, &d));
+        memcpy(h, descs.data(), sizeof(EwDesc) * descs.size());
+        SIP_CUDA(cudaMemcpyAsync(d, h, sizeof(EwDesc) * descs.size(), cudaMemcpyHostToDevice, ctx().stream));
+        const int grid = (int)std::min<long long>(chunks, (long long)ctx().num_sms * 8);
+        ew_batched_kernel<<<grid, kEwThreads, 0, ctx().stream>>>((const EwDesc*)d, (int)descs.size(), (int)chunks);
+        SIP_CUDA(cudaGetLastError());
+        count_launch();
+        g.st_launches++;
+    }
+    return SIPGPU_OK;
+}
+
+int launch_contract_group(const std::vector<const Op*>& list) {
+    const Op& o0 = *list[0];
+    std::vector<int> lext, rext, dext, chain(1, 0);
+    std::vector<const double*> L, R;
+    std::vector<double*> D;
+    for (const Op* o : list) {
+        lext.insert(lext.end(), o->lext, o->lext + o->lrank);
+        rext.insert(rext.end(), o->rext, o->rext + o->rrank);
+        dext.insert(dext.end(), o->dext, o->dext + o->drank);
+        for (const Pair& p : o->pairs) {
+            L.push_back(p.L);
+            R.push_back(p.R);
+        }
+        chain.push_back((int)L.size());
+        D.push_back(o->D);
+    }
+    const long long before = ctx().launches;
+    SIP_TRY(contract_chained((int)list.size(), o0.ptrn, o0.lrank, o0.rrank, o0.drank, lext.data(), rext.data(), dext.data(),
+                             chain.data(), L.data(), R.data(), D.data(), o0.alpha, o0.beta));
+    g.st_launches += ctx().launches - before;
+    return SIPGPU_OK;
+}
+
+int launch_permute_group(const std::vector<const Op*>& list) {
+    const Op& o0 = *list[0];
+    std::vector<const double*> in;
+    std::vector<double*> out;
+    for (const Op* o : list) {
+        in.push_back(o->in);
+        out.push_back(o->D);
+    }
+    const long long before = ctx().launches;
+    SIP_TRY(permute_batched((int)list.size(), o0.rank, o0.ext, o0.transp, in.data(), out.data(), o0.alpha, o0.beta));
+    g.st_launches += ctx().launches - before;
+    return SIPGPU_OK;
+}
+
+struct Touch {
+    int op;
+    int mode;
+};
+
+// base addresses whose byte range overlaps the range of a DIFFERENT base (a slab-wide fill over block pointers, a
+// parent array and a block inside it): the per-base touch lists cannot see those conflicts, so the fusion passes
+// leave such blocks alone (the interval map of the levelisation handles them exactly)
+std::unordered_set<uintptr_t> g_aliased;
+
+bool written_between(const std::unordered_map<uintptr_t, std::vector<Touch>>& touch, const void* base, int lo, int hi) {
+    if (g_aliased.count((uintptr_t)base)) return true;
+    auto it = touch.find((uintptr_t)base);
+    if (it == touch.end()) return false;
+    for (const Touch& t : it->second)
+        if (t.op > lo && t.op < hi && (t.mode & (WL_W | WL_ATOMIC)) && !g.ops[t.op].dead) return true;
+    return false;
+}
+
+// a fused op reads its operands at the position it now occupies: keep the per-base touch lists truthful
+void add_touch(std::unordered_map<uintptr_t, std::vector<Touch>>& touch, const void* base, int op, int mode) {
+    std::vector<Touch>& v = touch[(uintptr_t)base];
+    auto it = std::lower_bound(v.begin(), v.end(), op, [](const Touch& t, int o) { return t.op < o; });
+    if (it != v.end() && it->op == op) it->mode |= mode;
+    else v.insert(it, Touch{op, mode});
+}
+
+int schedule_and_launch() {
+    std::vector<Op>& ops = g.ops;
+    const int n = (int)ops.size();
+    g.last_level.assign(n, 0);
+    g.last_unit.assign(n, 0);
+    for (int i = 0; i < n; ++i) g.last_unit[i] = i;
+    std::vector<WlRange> rs;
+
+    // touch lists by base address, program order, one entry per (op, base)
+    std::unordered_map<uintptr_t, std::vector<Touch>> touch;
+    touch.reserve((size_t)n * 3);
+    for (int i = 0; i < n; ++i) {
+        ranges_of(ops[i], rs);
+        for (const WlRange& r : rs) {
+            std::vector<Touch>& v = touch[(uintptr_t)r.p];
+            if (!v.empty() && v.back().op == i) v.back().mode |= r.mode;
+            else v.push_back({i, r.mode});
+        }
+    }
+
+    {   // aliasing sweep over [base, base + longest access)
+        std::unordered_map<uintptr_t, uintptr_t> span;
+        for (int i = 0; i < n; ++i) {
+            ranges_of(ops[i], rs);
+            for (const WlRange& r : rs) {
+                uintptr_t& e = span[(uintptr_t)r.p];
+                e = std::max(e, (uintptr_t)r.p + r.bytes);
+            }
+        }
+        std::vector<std::pair<uintptr_t, uintptr_t>> iv(span.begin(), span.end());
+        std::sort(iv.begin(), iv.end());
+        g_aliased.clear();
+        uintptr_t run_end = 0, run_base = 0;
+        for (const auto& x : iv) {
+            if (x.first < run_end) {
+                g_aliased.insert(x.first);
+                g_aliased.insert(run_base);
+            }
+            if (x.second > run_end) {
+                run_end = x.second;
+                run_base = x.first;
+            }
+        }
+    }
+    auto aliased = [&](const void* p) { return g_aliased.count((uintptr_t)p) != 0; };
+
+    // ---- pass A: forward a temp produced by a contraction / permute into its single accumulating consumer ----
+    for (int i = 0; i < n; ++i) {
+        Op& p = ops[i];
+        if (p.dead || (p.kind != K_CONTRACT && p.kind != K_PERMUTE) || p.beta != 0.0) continue;
+        auto ti = g.temps.find((uintptr_t)p.D);
+        if (ti == g.temps.end() || !ti->second.freed || ti->second.n != p.dn || aliased(p.D)) continue;
+        const std::vector<Touch>& tl = touch[(uintptr_t)p.D];
+        // [zero fills of the fresh block ...] producer, consumer -- nothing else may touch the temp
+        size_t k = 0;
+        while (k < tl.size() && tl[k].op < i && ops[tl[k].op].kind == K_EW && ops[tl[k].op].ewop == WL_FILL &&
+               ops[tl[k].op].dn == p.dn)
+            ++k;
+        if (k + 2 != tl.size() || tl[k].op != i) continue;
+        const int j = tl[k + 1].op;
+        Op& c = ops[j];
+        if (c.dead || c.kind != K_EW || c.ewop != WL_AXPY || c.a != p.D || c.D == p.D || c.dn != p.dn || aliased(c.D)) continue;
+        bool ok = true;
+        if (p.kind == K_CONTRACT) {
+            for (const Pair& pr : p.pairs)
+                ok = ok && pr.L != p.D && pr.R != p.D && pr.L != c.D && pr.R != c.D && !written_between(touch, pr.L, i, j) && !written_between(touch, pr.R, i, j);
+        } else {
+            ok = p.in != c.D && p.in != p.D && !written_between(touch, p.in, i, j);
+        }
+        if (!ok) continue;
+        double* dest = c.D;
+        const double f = c.f;
+        const int corig = c.orig;
+        c = p;  // the fused op sits at the consumer's position
+        c.orig = corig;
+        c.D = dest;
+        c.alpha = p.alpha * f;
+        c.beta = 1.0;
+        p.dead = true;
+        g.last_unit[i] = j;
+        if (c.kind == K_CONTRACT) {
+            for (const Pair& pr : c.pairs) {
+                add_touch(touch, pr.L, j, WL_R);
+                add_touch(touch, pr.R, j, WL_R);
+            }
+        } else {
+            add_touch(touch, c.in, j, WL_R);
+        }
+        for (size_t q = 0; q < k; ++q) {
+            ops[tl[q].op].dead = true;
+            g.last_unit[tl[q].op] = j;
+        }
+        g.st_fused_acc++;
+        g.st_temps_elided++;
+    }
+
+    // ---- pass B: chains of accumulating contractions into one destination ----
+    for (int i = 0; i < n; ++i) {
+        if (ops[i].dead || ops[i].kind != K_CONTRACT || aliased(ops[i].D)) continue;
+        const std::vector<Touch>& tl = touch[(uintptr_t)ops[i].D];
+        size_t pos = 0;
+        while (pos < tl.size() && tl[pos].op != i) ++pos;
+        std::vector<int> run(1, i);
+        for (size_t q = pos + 1; q < tl.size(); ++q) {
+            const Op& o = ops[tl[q].op];
+            if (o.dead) continue;
+            if (o.kind != K_CONTRACT || o.D != ops[i].D || o.beta != 1.0 || !same_signature(ops[i], o)) break;
+            run.push_back(tl[q].op);
+        }
+        if (run.size() < 2) continue;
+        const int last = run.back();
+        bool ok = true;
+        for (int m : run)
+            for (const Pair& pr : ops[m].pairs) {
+                ok = ok && pr.L != ops[i].D && pr.R != ops[i].D;
+                if (m != last) ok = ok && !written_between(touch, pr.L, m, last) && !written_between(touch, pr.R, m, last);
+            }
+        if (!ok) continue;
+        std::vector<Pair> all;
+        for (int m : run) all.insert(all.end(), ops[m].pairs.begin(), ops[m].pairs.end());
+        ops[last].pairs.swap(all);
+        ops[last].beta = ops[i].beta;
+        for (const Pair& pr : ops[last].pairs) {
+            add_touch(touch, pr.L, last, WL_R);
+            add_touch(touch, pr.R, last, WL_R);
+        }
+        for (int m : run)
+            if (m != last) {
+                ops[m].dead = true;
+                g.last_unit[m] = last;
+            }
+        g.st_chains++;
+        g.st_chain_pairs += (long long)ops[last].pairs.size();
+    }
+
+    // ---- pass B2: `D = 0` (put_initialize / a fresh zeroed block) directly followed by an accumulating contraction
+    // into the whole of D is the assign form of that contraction: the fill and the read of D both disappear ----
+    for (int i = 0; i < n; ++i) {
+        Op& o = ops[i];
+        if (o.dead || o.kind != K_CONTRACT || o.beta != 1.0 || aliased(o.D)) continue;
+        const std::vector<Touch>& tl = touch[(uintptr_t)o.D];
+        int prev = -1;
+        for (const Touch& t : tl) {
+            if (t.op >= i) break;
+            if (!ops[t.op].dead) prev = t.op;
+        }
+        if (prev < 0) continue;
+        const Op& f = ops[prev];
+        if (f.kind != K_EW || f.ewop != WL_FILL || f.f != 0.0 || f.D != o.D || f.dn != o.dn) continue;
+        ops[prev].dead = true;
+        g.last_unit[prev] = i;
+        o.beta = 0.0;
+    }
+    for (int i = 0; i < n; ++i) {  // resolve fusion chains to the surviving op
+        int u = g.last_unit[i];
+        while (g.last_unit[u] != u) u = g.last_unit[u];
+        g.last_unit[i] = u;
+    }
+
+    // ---- pass C: levels from address-interval hazards ----
+    IntervalMap im;
+    int nlevels = 0;
+    for (int i = 0; i < n; ++i) {
+        Op& o = ops[i];
+        if (o.dead) continue;
+        ranges_of(o, rs);
+        int lv = 0;
+        for (const WlRange& r : rs) {
+            const uintptr_t a = (uintptr_t)r.p, b = a + r.bytes;
+            if (r.mode == WL_R) im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.a)); });
+            else if (r.mode == WL_ATOMIC) im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.r)); });
+            else im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, std::max(x.r, x.a))); });
+        }
+        o.level = lv + 1;
+        nlevels = std::max(nlevels, o.level);
+        for (const WlRange& r : rs) {
+            const uintptr_t a = (uintptr_t)r.p, b = a + r.bytes;
+            if (r.mode == WL_R) im.visit(a, b, [&](Lv& x) { x.r = std::max(x.r, o.level); });
+            else if (r.mode == WL_ATOMIC) im.visit(a, b, [&](Lv& x) { x.a = std::max(x.a, o.level); });
+            else im.visit(a, b, [&](Lv& x) { x.w = o.level; x.r = std::max(x.r, r.mode == WL_RW ? o.level : 0); });
+        }
+    }
+    for (int i = 0; i < n; ++i) g.last_level[i] = ops[g.last_unit[i]].level;
+
+    // ---- pass D: emission, level by level ----
+    std::vector<std::vector<int>> by_level(nlevels + 1);
+    long long alive = 0;
+    for (int i = 0; i < n; ++i)
+        if (!ops[i].dead) {
+            by_level[ops[i].level].push_back(i);
+            ++alive;
+        }
+    g.st_scheduled += alive;
+    g.st_levels += nlevels;
+    if (g.dry) return SIPGPU_OK;
+    for (int lv = 1; lv <= nlevels; ++lv) {
+        std::map<std::vector<long long>, std::vector<const Op*>> cgroups, pgroups;
+        std::vector<const Op*> ew;
+        auto bits = [](double x) { long long b; memcpy(&b, &x, 8); return b; };
+        for (int i : by_level[lv]) {
+            const Op& o = ops[i];
+            if (o.kind == K_CONTRACT) {
+                std::vector<long long> key = {o.lrank, o.rrank, o.drank, bits(o.alpha), bits(o.beta)};
+                key.insert(key.end(), o.ptrn, o.ptrn + o.lrank + o.rrank);
+                cgroups[key].push_back(&o);
+            } else if (o.kind == K_PERMUTE) {
+                std::vector<long long> key = {o.rank, bits(o.alpha), bits(o.beta)};
+                key.insert(key.end(), o.ext, o.ext + o.rank);
+                key.insert(key.end(), o.transp, o.transp + o.rank + 1);
+                pgroups[key].push_back(&o);
+            } else if (o.kind == K_EW) {
+                ew.push_back(&o);
+            } else {
+                const long long before = ctx().launches;
+                SIP_TRY(o.fn());
+                g.st_launches += ctx().launches - before;
+            }
+        }
+        for (auto& kv : cgroups) SIP_TRY(launch_contract_group(kv.second));
+        for (auto& kv : pgroups) SIP_TRY(launch_permute_group(kv.second));
+        if (!ew.empty()) SIP_TRY(launch_ew_batch(ew));
+    }
+    return SIPGPU_OK;
+}
+
+void release_deferred() {
+    if (!g.dry)
+        for (double* p : g.deferred_free) pool_free(p);
+    g.deferred_free.clear();
+    g.deferred_bytes = 0;
+    g.temps.clear();
+}
+
+int push(Op&& o) {
+    o.orig = (int)g.ops.size();
+    g.ops.push_back(std::move(o));
+    g.st_recorded++;
+    if (g.ops.size() >= g.max_ops || g.deferred_bytes >= g.max_deferred_bytes) return wl_flush();
+    return SIPGPU_OK;
+}
+
+long long volume(int rank, const int* ext) {
+    long long v = 1;
+    for (int i = 0; i < rank; ++i) v *= ext[i];
+    return v;
+}
+
+}  // namespace
+
+bool wl_active() { return g.on && !g.in_flush; }
+bool wl_dry() { return g.on && g.dry; }
+
+int wl_flush() {
+    if (!g.on || g.in_flush) return SIPGPU_OK;
+    g.in_flush = true;  // entry points called from here (opaque closures, launchers) execute instead of recording
+    int rc = SIPGPU_OK;
+    if (!g.ops.empty()) {
+        if (!g.dry) rc = ensure_init();
+        if (rc == SIPGPU_OK) rc = schedule_and_launch();
+        g.st_flushes++;
+    }
+    g.ops.clear();
+    release_deferred();
+    g.in_flush = false;
+    return rc;
+}
+
+int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f) {
+    if (n < 0 || !d) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    Op o;
+    o.kind = K_EW;
+    o.ewop = op;
+    o.D = d;
+    o.a = a;
+    o.b = b;
+    o.dn = n;
+    o.f = f;
+    return push(std::move(o));
+}
+
+int wl_rec_permute(int rank, const int* ext, const int* transp, const double* in, double* out, double alpha, double beta) {
+    if (rank < 0 || rank > kMaxRank || !in || !out || (rank && (!ext || !transp))) return SIPGPU_E_ARG;
+    PermShape ps;
+    if (rank > 0) SIP_TRY(build_perm_shape(rank, ext, transp, &ps));  // validates the permutation
+    Op o;
+    o.kind = K_PERMUTE;
+    o.rank = rank;
+    for (int i = 0; i < rank; ++i) o.ext[i] = ext[i];
+    o.transp[0] = 1;
+    for (int i = 0; i < rank; ++i) o.transp[i + 1] = transp[i + 1];
+    o.in = in;
+    o.D = out;
+    o.dn = volume(rank, ext);
+    o.alpha = alpha;
+    o.beta = beta;
+    return push(std::move(o));
+}
+
+int wl_rec_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
+                    const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    if (!L || !R || !D || !ptrn || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank ||
+        drank > kMaxRank)
+        return SIPGPU_E_ARG;
+    Shape s;
+    SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &s));  // pattern errors surface at the call
+    Op o;
+    o.kind = K_CONTRACT;
+    o.lrank = lrank;
+    o.rrank = rrank;
+    o.drank = drank;
+    memcpy(o.ptrn, ptrn, sizeof(int) * (lrank + rrank));
+    memcpy(o.lext, lext, sizeof(int) * lrank);
+    memcpy(o.rext, rext, sizeof(int) * rrank);
+    memcpy(o.dext, dext, sizeof(int) * drank);
+    o.ln = volume(lrank, lext);
+    o.rn = volume(rrank, rext);
+    o.dn = volume(drank, dext);
+    o.pairs.push_back(Pair{L, R});
+    o.D = D;
+    o.alpha = alpha;
+    o.beta = beta;
+    return push(std::move(o));
+}
+
+int wl_rec_opaque(std::function<int()> fn, std::initializer_list<WlRange> ranges) {
+    Op o;
+    o.kind = K_OPAQUE;
+    o.fn = std::move(fn);
+    o.ranges.assign(ranges.begin(), ranges.end());
+    return push(std::move(o));
+}
+
+double* wl_alloc(long long n, int zero) {
+    if (n < 0) return nullptr;
+    double* p;
+    Temp t;
+    t.n = n;
+    if (g.dry) {
+        p = (double*)g.fake_next;
+        g.fake_next += (sizeof(double) * (size_t)(n > 0 ? n : 1) + 255) & ~(size_t)255;
+        t.fake = true;
+    } else {
+        p = pool_alloc(sizeof(double) * (size_t)n);
+        if (!p) return nullptr;
+    }
+    g.temps[(uintptr_t)p] = t;
+    if (zero && n > 0 && wl_rec_ew(WL_FILL, p, nullptr, nullptr, n, 0.0) != SIPGPU_OK) return nullptr;
+    return p;
+}
+
+int wl_free(double* p) {
+    if (!p) return SIPGPU_OK;
+    auto it = g.temps.find((uintptr_t)p);
+    size_t bytes = 0;
+    if (it != g.temps.end()) {
+        it->second.freed = true;
+        bytes = sizeof(double) * (size_t)it->second.n;
+    }
+    g.deferred_free.push_back(p);
+    g.deferred_bytes += bytes;
+    if (g.deferred_bytes >= g.max_deferred_bytes) return wl_flush();
+    return SIPGPU_OK;
+}
+
+}  // namespace sipgpu
+
+using namespace sipgpu;
+
+extern "C" {
+
+int sipgpu_wl_begin(int flags) {
+    if (g.on) {
+        set_error("sipgpu_wl_begin: a recording is already open");
+        return SIPGPU_E_STATE;
+    }
+    const bool dry = (flags & 1) != 0;
+    if (!dry) SIP_TRY(ensure_init());
+    g = State();
+    g.on = true;
+    g.dry = dry;
+    return SIPGPU_OK;
+}
+int sipgpu_wl_flush(void) { return wl_flush(); }
+int sipgpu_wl_end(void) {
+    if (!g.on) return SIPGPU_E_STATE;
+    const int rc = wl_flush();
+    g.on = false;
+    return rc;
+}
+int sipgpu_wl_recording(void) { return g.on ? (g.dry ? 2 : 1) : 0; }
+int sipgpu_wl_set_limits(long long max_ops, long long max_deferred_bytes) {
+    if (max_ops > 0) g.max_ops = (size_t)max_ops;
+    if (max_deferred_bytes > 0) g.max_deferred_bytes = (size_t)max_deferred_bytes;
+    return SIPGPU_OK;
+}
+int sipgpu_wl_stats(long long* out9) {
+    if (!out9) return SIPGPU_E_ARG;
+    const long long v[9] = {g.st_recorded, g.st_scheduled, g.st_levels, g.st_launches, g.st_fused_acc,
+                            g.st_chains,   g.st_chain_pairs, g.st_temps_elided, g.st_flushes};
+    memcpy(out9, v, sizeof(v));
+    return SIPGPU_OK;
+}
+int sipgpu_wl_last_plan(int cap, int* level_of_op, int* unit_of_op) {
+    const int n = (int)g.last_level.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        if (level_of_op) level_of_op[i] = g.last_level[i];
+        if (unit_of_op) unit_of_op[i] = g.last_unit[i];
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -220,6 +220,33 @@ int sipgpu_si_invert_diagonal(int* array_0, int* rank_0, int* index_values_0, in
                               int* ierr);
 
 /* ---------------------------------------------------------------------------------------------
+ * Boundary 3c -- deferred op stream: the batching front-end for pardo bodies.
+ * The reference interpreter dispatches one block operation per opcode (interpreter.cpp:98-910, e.g. the
+ * `do k: T = A*B; D += T` bodies of rlccd_rhf.sialx:342-355).  Between sipgpu_wl_begin() and sipgpu_wl_end()
+ * the asynchronous entry points of boundaries 2-4 (block alloc/free, fill/scale/copy/axpy/add, permute,
+ * contract, slice/insert, array get/put/put_accumulate, _gpu_* equivalents) are RECORDED with their
+ * read/write sets instead of launched.  A flush schedules the stream: temps that only feed an accumulate
+ * are forwarded (T = L*R; D += f*T  ->  D += f*L*R, the temp is never written), accumulating contractions
+ * into one destination are chained, hazards on device address intervals give levels, and each level is
+ * emitted as ONE launch per kernel family (worklist.cu).  Program-order semantics are preserved; blocking
+ * calls (d2h, dot, norm2, sync, host-pointer ABI) flush implicitly.  The natural call sites in the
+ * reference are pardo entry and SialOpsParallel::sip_barrier / endpardo (sial_ops_parallel.cpp:39-99).
+ * --------------------------------------------------------------------------------------------- */
+#define SIPGPU_WL_DRY 1 /* record and schedule on the host only (no device): planner tests */
+int sipgpu_wl_begin(int flags);
+int sipgpu_wl_flush(void);      /* schedule + launch what is recorded; recording continues */
+int sipgpu_wl_end(void);        /* flush and stop recording */
+int sipgpu_wl_recording(void);  /* 0 = off, 1 = recording, 2 = dry recording */
+/* automatic flush thresholds (0 = keep): recorded ops, bytes of temps whose free is deferred */
+int sipgpu_wl_set_limits(long long max_ops, long long max_deferred_bytes);
+/* out9 = {ops recorded, ops scheduled, levels, kernel launches, temp->accumulate fusions, chains,
+ *         operand pairs in chains, temps never written, flushes} since sipgpu_wl_begin */
+int sipgpu_wl_stats(long long* out9);
+/* plan of the most recent flush, per recorded op in program order: the level it ran in and the index of the
+ * op it was fused into (itself if not fused).  Returns the number of ops of that flush. */
+int sipgpu_wl_last_plan(int cap, int* level_of_op, int* unit_of_op);
+
+/* ---------------------------------------------------------------------------------------------
  * Boundary 4 -- distributed / served arrays (SialOpsParallel method set, src/sip/worker/
  * sial_ops_parallel.cpp:39-99,132-171,232-284,332-408,549-565; owner rule data_distribution.cpp:19-82 and
  * array_table.cpp:50-97).  One process per GPU; every GPU is worker AND owner (no server ranks).  Each

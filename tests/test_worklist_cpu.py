@@ -1,0 +1,250 @@
+"""CPU tests of the deferred op stream's scheduler (aces4_b200/csrc/worklist.cu) in DRY mode: ops are recorded with
+fake device addresses and scheduled on the host only.  What is checked is the host logic: temp forwarding
+(T = L*R; D += T  ->  D += L*R), chain fusion, zero-fill elimination, and -- on random op streams -- that the levels
+respect every read/write hazard of the recorded program order (an independent O(n^2) checker written here).
+No GPU needed; the numerical equivalence of recorded vs op-at-a-time execution is tests/test_gpu_worklist.py."""
+import random
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def sip():
+    import aces4_b200 as s
+
+    s.build()
+    return s.api
+
+
+class Rec:
+    """Mirror of the recorded stream kept by the test: (reads, writes) address ranges per op."""
+
+    def __init__(self, sip):
+        self.sip, self.ops = sip, []
+
+    def blk(self, shape):
+        return self.sip.DeviceBlock(shape)
+
+    @staticmethod
+    def rng(b):
+        return (b.ptr, b.ptr + 8 * b.size)
+
+    def note(self, reads, writes):
+        self.ops.append(([self.rng(b) for b in reads], [self.rng(b) for b in writes]))
+
+    def fill(self, d, v):
+        d.fill(v)
+        self.note([], [d])
+
+    def scale(self, d, f):
+        d.scale(f)
+        self.note([d], [d])
+
+    def axpy(self, d, s, f):
+        d.axpy(s, f)
+        self.note([d, s], [d])
+
+    def copy(self, d, s, f=1.0):
+        d.scale_and_copy(s, f)
+        self.note([s], [d])
+
+    def add_sub(self, d, l, r, sign):
+        d.set_add_sub(l, r, sign)
+        self.note([l, r], [d])
+
+    def permute(self, d, s, transp):
+        self.sip.permute(s, transp, out=d)
+        self.note([s], [d])
+
+    def contract(self, ptrn, L, R, D, beta=0.0, alpha=1.0):
+        self.sip.contract(ptrn, L, R, D.shape, out=D, alpha=alpha, beta=beta)
+        self.note([L, R] + ([D] if beta != 0.0 else []), [D])
+
+
+def overlap(a, b):
+    return a[0] < b[1] and b[0] < a[1]
+
+
+def check_plan(ops, level, unit):
+    """every conflicting pair (RAW, WAR, WAW) of the recorded order that was not fused into one unit is level-ordered"""
+    n = len(ops)
+    assert len(level) == n and len(unit) == n
+    for j in range(n):
+        rj, wj = ops[j]
+        for i in range(j):
+            if unit[i] == unit[j]:
+                continue
+            ri, wi = ops[i]
+            conflict = any(overlap(x, y) for x in wi for y in rj + wj) or any(overlap(x, y) for x in ri for y in wj)
+            if conflict:
+                assert level[i] < level[j], (i, j, level[i], level[j])
+
+
+def test_hhladder_body_becomes_one_chain(sip):
+    """rlccd_rhf.sialx:342-355: do i1, j1: T = T2old[a,i1,b,j1]*V[i,i1,j,j1]; Taibj += T  -> one chained problem"""
+    v, o, nseg = 8, 5, 3
+    ptrn, ierr = sip.get_contraction_ptrn([1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6])
+    assert ierr == 0
+    with sip.recording(dry=True) as rec:
+        T2 = [[sip.DeviceBlock((v, o, v, o)) for _ in range(nseg)] for _ in range(nseg)]
+        V = [[sip.DeviceBlock((o, o, o, o)) for _ in range(nseg)] for _ in range(nseg)]
+        D = sip.DeviceBlock((v, o, v, o))
+        D.fill(0.0)
+        for i1 in range(nseg):
+            for j1 in range(nseg):
+                T = sip.DeviceBlock((v, o, v, o))
+                sip.contract(ptrn, T2[i1][j1], V[i1][j1], (v, o, v, o), out=T)
+                D.accumulate(T)
+                T.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["recorded"] == 1 + 2 * nseg * nseg
+    assert st["fused_accumulates"] == nseg * nseg and st["temps_elided"] == nseg * nseg
+    assert st["chains"] == 1 and st["chain_pairs"] == nseg * nseg
+    assert st["scheduled"] == 1 and st["levels"] == 1      # the zero fill disappeared into beta = 0
+    assert len(set(unit)) == 1 and set(level) == {1}
+
+
+def test_temp_with_second_reader_is_not_forwarded(sip):
+    v = 6
+    ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        A, B, D, E = (sip.DeviceBlock((v, v)) for _ in range(4))
+        T = sip.DeviceBlock((v, v))
+        sip.contract(ptrn, A, B, (v, v), out=T)
+        D.accumulate(T)
+        E.accumulate(T)       # a second consumer: T must be materialised
+        T.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["fused_accumulates"] == 0 and st["scheduled"] == 3
+    assert level == [1, 2, 2]
+
+
+def test_operand_overwritten_between_producer_and_consumer_blocks_fusion(sip):
+    v = 6
+    ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        A, B, D = (sip.DeviceBlock((v, v)) for _ in range(3))
+        T = sip.DeviceBlock((v, v))
+        sip.contract(ptrn, A, B, (v, v), out=T)
+        A.fill(1.0)           # WAR on A: T must be computed from the OLD A
+        D.accumulate(T)
+        T.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["fused_accumulates"] == 0
+    assert level == [1, 2, 2]
+
+
+def test_unfreed_block_is_not_elided(sip):
+    v = 6
+    ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        A, B, D, T = (sip.DeviceBlock((v, v)) for _ in range(4))
+        sip.contract(ptrn, A, B, (v, v), out=T)
+        D.accumulate(T)       # T stays live after the recording: its value is observable
+        sip.wl_flush()
+        st = sip.wl_stats()
+    assert st["fused_accumulates"] == 0 and st["scheduled"] == 2
+
+
+def test_permute_accumulate_fusion_and_batching(sip):
+    """handle_block_add with differing labels: permute into a temp, then add (interpreter.cpp:1874-1997)"""
+    shape = (4, 3, 4, 3)
+    with sip.recording(dry=True):
+        X = [sip.DeviceBlock(shape) for _ in range(5)]
+        D = [sip.DeviceBlock(shape) for _ in range(5)]
+        for x, d in zip(X, D):
+            t = sip.DeviceBlock(shape)
+            sip.permute(x, [1, 3, 2, 1, 4], out=t)
+            d.axpy(t, -1.0)
+            t.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["fused_accumulates"] == 5 and st["scheduled"] == 5 and st["levels"] == 1
+    assert set(level) == {1}
+
+
+def test_pattern_error_surfaces_at_the_recording_call(sip):
+    with sip.recording(dry=True):
+        A, B, D = sip.DeviceBlock((4, 5)), sip.DeviceBlock((6, 4)), sip.DeviceBlock((4, 4))
+        ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+        with pytest.raises(sip.SipGpuError):
+            sip.contract(ptrn, A, B, (4, 4), out=D)   # contracted extents 5 vs 6
+        assert sip.wl_stats()["recorded"] == 0
+
+
+def test_nested_begin_is_an_error_and_compute_needs_a_device(sip):
+    sip.wl_begin(dry=True)
+    try:
+        assert sip.lib().sipgpu_wl_recording() == 2
+        assert sip.lib().sipgpu_wl_begin(1) == 105   # SIPGPU_E_STATE
+    finally:
+        sip.wl_end()
+    assert sip.lib().sipgpu_wl_recording() == 0
+    assert sip.lib().sipgpu_wl_end() == 105
+
+
+def test_auto_flush_limit(sip):
+    with sip.recording(dry=True):
+        sip.lib().sipgpu_wl_set_limits(10, 0)
+        a = sip.DeviceBlock((16,))
+        for k in range(35):
+            a.scale(1.5)
+        st = sip.wl_stats()
+    assert st["flushes"] >= 3 and st["recorded"] == 35
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_streams_respect_all_hazards(sip, seed):
+    rnd = random.Random(seed)
+    v = 4
+    p2, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        r = Rec(sip)
+        live = [r.blk((v, v)) for _ in range(6)]
+        temps = []
+        for step in range(160):
+            k = rnd.randrange(9)
+            pick = lambda: rnd.choice(live + temps)  # noqa: E731
+            if k == 0:
+                r.fill(pick(), 0.0 if rnd.random() < 0.5 else 2.0)
+            elif k == 1:
+                r.scale(pick(), 0.5)
+            elif k == 2:
+                d, s = pick(), pick()
+                if d is not s:
+                    r.axpy(d, s, rnd.choice([1.0, -1.0, 0.5]))
+            elif k == 3:
+                d, s = pick(), pick()
+                if d is not s:
+                    r.copy(d, s)
+            elif k == 4:
+                d, a, b = pick(), pick(), pick()
+                r.add_sub(d, a, b, rnd.choice([1.0, -1.0]))
+            elif k == 5:
+                d, s = pick(), pick()
+                if d is not s:
+                    r.permute(d, s, [1, 2, 1])
+            elif k in (6, 7):
+                d, a, b = pick(), pick(), pick()
+                if d is not a and d is not b:
+                    r.contract(p2, a, b, d, beta=rnd.choice([0.0, 1.0, 1.0]))
+            else:
+                # the interpreter's temp idiom: T = A*B ; D += T ; free T
+                a, b, d = pick(), pick(), rnd.choice(live)
+                t = r.blk((v, v))
+                r.contract(p2, a, b, t)
+                r.axpy(d, t, 1.0)
+                t.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["recorded"] == len(r.ops)
+    check_plan(r.ops, level, unit)
+    assert st["scheduled"] <= st["recorded"] and st["levels"] >= 1
