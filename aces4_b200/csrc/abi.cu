@@ -648,35 +648,83 @@ int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) 
 int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                                      int*, int*, int* extents_1, double* data_1, int* ierr) {
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());  // super-instructions run in program order after the recorded ops
+    if (wl_active()) {  // recorded with its read/write sets; runs at its scheduled position
+        const int r0 = *rank_0, r1 = *rank_1;
+        if (r0 < 0 || r0 > kMaxRank || r1 < 1 || r1 > 2 || !index_values_0 || !extents_0 || !extents_1 || !data_0 || !data_1)
+            SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv{}, e0{}, e1{};
+        for (int i = 0; i < r0; ++i) iv[i] = index_values_0[i], e0[i] = extents_0[i];
+        for (int i = 0; i < r1; ++i) e1[i] = extents_1[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_energy_denominator_rhf(r0, iv.data(), e0.data(), data_0, r1, e1.data(), data_1); },
+                                {{data_0, sizeof(double) * (size_t)volume(r0, extents_0), WL_RW},
+                                 {data_1, sizeof(double) * (size_t)volume(r1, extents_1), WL_R}}));
+    }
     SI_RETURN(si_energy_denominator_rhf(*rank_0, index_values_0, extents_0, data_0, *rank_1, extents_1, data_1));
 }
 int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                      int* index_values_1, int*, int* extents_1, double* data_1, int* ierr) {
     if (!rank_0 || !rank_1 || *rank_0 != *rank_1) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());
+    if (wl_active()) {
+        const int r = *rank_0;
+        if (r < 1 || r > kMaxRank || !index_values_0 || !index_values_1 || !extents_0 || !extents_1 || !data_0 || !data_1)
+            SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv0{}, iv1{}, e0{}, e1{};
+        for (int i = 0; i < r; ++i) iv0[i] = index_values_0[i], iv1[i] = index_values_1[i], e0[i] = extents_0[i], e1[i] = extents_1[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_stripi(r, iv0.data(), e0.data(), data_0, iv1.data(), e1.data(), data_1); },
+                                {{data_0, sizeof(double) * (size_t)volume(r, extents_0), WL_R},
+                                 {data_1, sizeof(double) * (size_t)volume(r, extents_1), WL_RW}}));
+    }
     SI_RETURN(si_stripi(*rank_0, index_values_0, extents_0, data_0, index_values_1, extents_1, data_1));
 }
 int sipgpu_si_anti_symm_o(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());
+    if (wl_active()) {
+        const int r = *rank_0;
+        if (r < 1 || r > kMaxRank || !index_values_0 || !extents_0 || !data_0) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv{}, e0{};
+        for (int i = 0; i < r; ++i) iv[i] = index_values_0[i], e0[i] = extents_0[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_anti_symm_o(r, iv.data(), e0.data(), data_0); },
+                                {{data_0, sizeof(double) * (size_t)volume(r, extents_0), WL_RW}}));
+    }
     SI_RETURN(si_anti_symm_o(*rank_0, index_values_0, extents_0, data_0));
 }
 int sipgpu_si_anti_symm_v(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());
+    if (wl_active()) {
+        const int r = *rank_0;
+        if (r < 1 || r > kMaxRank || !index_values_0 || !extents_0 || !data_0) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv{}, e0{};
+        for (int i = 0; i < r; ++i) iv[i] = index_values_0[i], e0[i] = extents_0[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_anti_symm_v(r, iv.data(), e0.data(), data_0); },
+                                {{data_0, sizeof(double) * (size_t)volume(r, extents_0), WL_RW}}));
+    }
     SI_RETURN(si_anti_symm_v(*rank_0, index_values_0, extents_0, data_0));
 }
 int sipgpu_si_return_sval(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                           double* data_1, int* ierr) {
     if (!rank_0 || !rank_1 || *rank_1 != 0) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());
+    if (wl_active()) {
+        const int r = *rank_0;
+        if (r < 1 || r > kMaxRank || !extents_0 || !data_0 || !data_1) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> e0{};
+        for (int i = 0; i < r; ++i) e0[i] = extents_0[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_return_sval(r, e0.data(), data_0, data_1); },
+                                {{data_0, sizeof(double) * (size_t)volume(r, extents_0), WL_R}, {data_1, sizeof(double), WL_W}}));
+    }
     SI_RETURN(si_return_sval(*rank_0, extents_0, data_0, data_1));
 }
 int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                               double* data_1, int* ierr) {
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
-    SIP_TRY(wl_flush());
+    if (wl_active()) {
+        const int r0 = *rank_0, r1 = *rank_1;
+        if (r0 < 1 || r0 > kMaxRank || !extents_0 || !data_0 || !data_1) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> e0{};
+        for (int i = 0; i < r0; ++i) e0[i] = extents_0[i];
+        const size_t nb = sizeof(double) * (size_t)volume(r0, extents_0);
+        SI_RETURN(wl_rec_opaque([=] { return si_invert_diagonal(r0, r1, e0.data(), data_0, data_1); },
+                                {{data_0, nb, WL_RW}, {data_1, nb, WL_R}}));
+    }
     SI_RETURN(si_invert_diagonal(*rank_0, *rank_1, extents_0, data_0, data_1));
 }
 

@@ -189,7 +189,7 @@ int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src) {
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
-    if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0);
+    if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0, a->world == 1);
     return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
 }
 int sipgpu_array_fill_local(sipgpu_array* a, double v) {

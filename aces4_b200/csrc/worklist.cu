@@ -65,6 +65,7 @@ struct Op {
     int ewop = 0;
     const double *a = nullptr, *b = nullptr;
     double f = 0.0;
+    bool exclusive = false;  // REDADD into memory no other process can touch (world == 1): may become a plain accumulate
     // opaque
     std::function<int()> fn;
     std::vector<WlRange> ranges;
@@ -406,7 +407,7 @@ int schedule_and_launch() {
         if (k + 2 != tl.size() || tl[k].op != i) continue;
         const int j = tl[k + 1].op;
         Op& c = ops[j];
-        if (c.dead || c.kind != K_EW || c.ewop != WL_AXPY || c.a != p.D || c.D == p.D || c.dn != p.dn || aliased(c.D)) continue;
+        if (c.dead || c.kind != K_EW || !(c.ewop == WL_AXPY || (c.ewop == WL_REDADD && c.exclusive)) || c.a != p.D || c.D == p.D || c.dn != p.dn || aliased(c.D)) continue;
         bool ok = true;
         if (p.kind == K_CONTRACT) {
             for (const Pair& pr : p.pairs)
@@ -416,7 +417,7 @@ int schedule_and_launch() {
         }
         if (!ok) continue;
         double* dest = c.D;
-        const double f = c.f;
+        const double f = c.ewop == WL_REDADD ? 1.0 : c.f;
         const int corig = c.orig;
         c = p;  // the fused op sits at the consumer's position
         c.orig = corig;
@@ -451,7 +452,14 @@ int schedule_and_launch() {
         for (size_t q = pos + 1; q < tl.size(); ++q) {
             const Op& o = ops[tl[q].op];
             if (o.dead) continue;
-            if (o.kind != K_CONTRACT || o.D != ops[i].D || o.beta != 1.0 || !same_signature(ops[i], o)) break;
+            if (o.kind != K_CONTRACT || o.D != ops[i].D || o.beta != 1.0) break;
+            // an accumulate with other extents (non-uniform contracted segments) or another alpha commutes with the
+            // chain: it stays where it is, the chain members on both sides of it are still gathered
+            // (only when the head itself accumulates: an assigning head would wipe what the skipped op added)
+            if (!same_signature(ops[i], o)) {
+                if (ops[i].beta != 1.0) break;
+                continue;
+            }
             run.push_back(tl[q].op);
         }
         if (run.size() < 2) continue;
@@ -612,7 +620,7 @@ int wl_flush() {
     return rc;
 }
 
-int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f) {
+int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f, bool exclusive) {
     if (n < 0 || !d) return SIPGPU_E_ARG;
     if (n == 0) return SIPGPU_OK;
     Op o;
@@ -623,6 +631,7 @@ int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, 
     o.b = b;
     o.dn = n;
     o.f = f;
+    o.exclusive = exclusive;
     return push(std::move(o));
 }
 

@@ -23,7 +23,9 @@ bool wl_dry();     // recording without a device (host-only planning, CPU tests)
 // Schedule and launch everything recorded so far; recording stays on.  Blocking entry points call this first.
 int wl_flush();
 
-int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f);
+// exclusive: a WL_REDADD whose destination no other process can reach (single-rank array) -- the scheduler may turn it
+// into the fused accumulate of the producing contraction
+int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f, bool exclusive = false);
 int wl_rec_permute(int rank, const int* ext, const int* transp, const double* in, double* out, double alpha, double beta);
 int wl_rec_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
                     const int* rext, double* D, int drank, const int* dext, double alpha, double beta);

@@ -1,0 +1,469 @@
+"""Minimal SIAL front-end for the block-contraction hot path.
+
+The reference compiles SIAL to `.siox` bytecode with a Java compiler (not available here) and interprets it one
+opcode at a time (src/sip/worker/interpreter.cpp:98-910).  This module is NOT that interpreter: it understands just the
+statement subset that the pardo bodies of the CC doubles equations use (src/sialx/qm/cc/rlccd_rhf.sialx:255-603) and
+turns them into the per-block calls the interpreter would issue -- in the same order, with the same temp-block
+lifetimes (temps die at the end of the loop iteration that created them, BlockManager::leave_scope) and the same
+pardo work distribution (iteration k of the where-true iterations of a barrier section runs on worker k mod nworkers,
+BalancedTaskAllocParallelPardoLoop::do_update, loop_manager.cpp:468-499; first index fastest, :434-452).
+
+Those calls go to a *backend*:
+  * DeviceBackend  -- libsipgpu through the C ABI; with `record=True` every pardo is wrapped in
+                      sipgpu_wl_begin()/sipgpu_wl_end(), so the op-at-a-time stream is scheduled into a few batched
+                      launches by aces4_b200/csrc/worklist.cu; with `record=False` every op is its own launch (the
+                      naive port of the interpreter onto a device ABI) -- the comparison the work-list exists for;
+  * the tests' OracleBackend (tests/sial_oracle_backend.py) -- the CPU oracle, for parity.
+
+Supported statements (case-insensitive keywords, `#` comments):
+    pardo i, j, ...  /  endpardo ...        do i / enddo i        where i < j   (<, <=, >, >=, ==, != on indices/ints)
+    request|get A[...]                      put|prepare A[...] = T[...]     put|prepare A[...] += T[...]
+    T[...] = number      T[...] = X[...]    T[...] = X[...] * Y[...]        T[...] += X[...]     T[...] -= X[...]
+    T[...] *= number     s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
+    execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
+Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `aoindex mu = 1: norb`; arrays
+`served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else raises SialSyntaxError.
+"""
+import itertools
+import re
+
+
+class SialSyntaxError(ValueError):
+    pass
+
+
+_KIND_BY_RANGE = {("baocc", "eaocc"): "o", ("bavirt", "eavirt"): "v", ("baocc", "eavirt"): "p", ("1", "norb"): "ao",
+                  ("bocc", "eocc"): "o", ("bvirt", "evirt"): "v"}
+_REF = r"([A-Za-z_]\w*)\s*\[([^\]]*)\]"
+_NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?"
+
+
+def _labels(s):
+    return tuple(x.strip() for x in s.split(",") if x.strip())
+
+
+class Program:
+    """Parsed SIAL fragment: declarations + a statement tree."""
+
+    def __init__(self, text):
+        self.index_kind, self.arrays, self.scalars = {}, {}, set()
+        self.body = []
+        stack = [self.body]
+        opens = []
+        for ln, raw in enumerate(text.splitlines(), 1):
+            line = raw.split("#", 1)[0].strip()
+            if not line:
+                continue
+            low = line.lower()
+            tok = low.split()
+            try:
+                st = self._parse(line, low, tok)
+            except SialSyntaxError as e:
+                raise SialSyntaxError(f"line {ln}: {e}: {raw.strip()!r}") from None
+            if st is None:
+                continue
+            if st[0] in ("pardo", "do"):
+                st = st + ([],)
+                stack[-1].append(st)
+                stack.append(st[-1])
+                opens.append(st[0])
+            elif st[0] in ("endpardo", "enddo"):
+                if not opens or opens.pop() != st[0][3:]:
+                    raise SialSyntaxError(f"line {ln}: unbalanced {st[0]}")
+                stack.pop()
+            else:
+                stack[-1].append(st)
+        if opens:
+            raise SialSyntaxError("unterminated " + opens[-1])
+
+    def _parse(self, line, low, tok):
+        kw = tok[0]
+        if kw in ("sial", "endsial", "proc", "endproc", "import"):
+            return None
+        if kw in ("moaindex", "aoindex", "moindex", "mobindex"):
+            m = re.match(r"\w+\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line)
+            if not m:
+                raise SialSyntaxError("bad index declaration")
+            kind = _KIND_BY_RANGE.get((m.group(2).lower(), m.group(3).lower()))
+            if kind is None:
+                raise SialSyntaxError("unsupported index range")
+            self.index_kind[m.group(1)] = kind
+            return None
+        if kw in ("served", "distributed", "temp", "local", "static"):
+            m = re.match(r"\w+\s+" + _REF, line)
+            if not m:
+                raise SialSyntaxError("bad array declaration")
+            self.arrays[m.group(1).lower()] = (kw, _labels(m.group(2)))
+            return None
+        if kw == "scalar":
+            self.scalars.add(tok[1])
+            return None
+        if kw == "pardo" or kw == "do":
+            return (kw, _labels(line.split(None, 1)[1]))
+        if kw in ("endpardo", "enddo"):
+            return (kw,)
+        if kw == "where":
+            m = re.match(r"where\s+(\w+)\s*(<=|>=|==|!=|<|>)\s*(\w+)", low)
+            if not m:
+                raise SialSyntaxError("unsupported where clause")
+            return ("where", m.group(1), m.group(2), m.group(3))
+        if kw in ("request", "get"):
+            m = re.match(r"\w+\s+" + _REF, line)
+            if not m:
+                raise SialSyntaxError("bad request")
+            return ("request", m.group(1).lower(), _labels(m.group(2)))
+        if kw in ("put", "prepare"):
+            m = re.match(r"\w+\s+" + _REF + r"\s*(\+?=)\s*" + _REF + r"\s*$", line)
+            if not m:
+                raise SialSyntaxError("bad put/prepare")
+            return ("put", m.group(1).lower(), _labels(m.group(2)), m.group(3), m.group(4).lower(), _labels(m.group(5)))
+        if kw == "execute":
+            if len(tok) < 2:
+                raise SialSyntaxError("bad execute")
+            args = [(m.group(1).lower(), _labels(m.group(2))) for m in re.finditer(_REF, line)]
+            bare = [t for t in re.sub(_REF, " ", line).split()[2:]]
+            return ("execute", tok[1], args, [b.lower() for b in bare])
+        if kw in ("sip_barrier", "server_barrier"):
+            return ("barrier",)
+        if kw == "collective":
+            m = re.match(r"collective\s+(\w+)\s*\+=\s*(\w+)", low)
+            if not m:
+                raise SialSyntaxError("bad collective")
+            return ("collective", m.group(1), m.group(2))
+        # block statements
+        m = re.match(_REF + r"\s*(\+=|-=|\*=|=)\s*(.+)$", line)
+        if m:
+            name, labs, op, rhs = m.group(1).lower(), _labels(m.group(2)), m.group(3), m.group(4).strip()
+            mm = re.match(_REF + r"\s*\*\s*" + _REF + r"\s*$", rhs)
+            if mm and op == "=":
+                return ("contract", name, labs, mm.group(1).lower(), _labels(mm.group(2)), mm.group(3).lower(),
+                        _labels(mm.group(4)))
+            mm = re.match(_REF + r"\s*$", rhs)
+            if mm and op in ("=", "+=", "-="):
+                return ("assign" if op == "=" else "add", name, labs, mm.group(1).lower(), _labels(mm.group(2)),
+                        -1.0 if op == "-=" else 1.0)
+            if re.match(_NUM + r"$", rhs) and op in ("=", "*="):
+                return ("fill" if op == "=" else "scale", name, labs, float(rhs.lower().replace("d", "e")))
+            raise SialSyntaxError("unsupported block statement")
+        # scalar statements
+        m = re.match(r"(\w+)\s*(\+=|-=|\*=|=)\s*(.+)$", line)
+        if m:
+            name, op, rhs = m.group(1).lower(), m.group(2), m.group(3).strip()
+            mm = re.match(_REF + r"\s*\*\s*" + _REF + r"\s*$", rhs)
+            if mm and op == "=":
+                return ("sdot", name, mm.group(1).lower(), _labels(mm.group(2)), mm.group(3).lower(), _labels(mm.group(4)))
+            if re.match(_NUM + r"$", rhs):
+                return ("sset" if op == "=" else {"+=": "sinc", "-=": "sinc", "*=": "smul"}[op], name,
+                        float(rhs) * (-1.0 if op == "-=" else 1.0))
+            if re.match(r"\w+$", rhs) and op in ("+=", "-=", "="):
+                return ("sadd" if op != "=" else "scopy", name, rhs.lower(), -1.0 if op == "-=" else 1.0)
+        raise SialSyntaxError("unsupported statement")
+
+
+class Walker:
+    """Executes a Program against a backend: the per-block call stream of one worker."""
+
+    def __init__(self, program, backend, segs, rank=0, world=1):
+        """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v."""
+        self.p, self.be, self.rank, self.world = program, backend, rank, world
+        self.segs = dict(segs)
+        if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
+            self.segs["p"] = list(self.segs["o"]) + list(self.segs["v"])
+        self.idx = {}            # index name -> current segment number (1-based)
+        self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
+        self.iteration = 0       # pardo iteration counter of the current barrier section
+        self.scalars = {s: 0.0 for s in program.scalars}
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _kind(self, lab):
+        try:
+            return self.p.index_kind[lab]
+        except KeyError:
+            raise SialSyntaxError(f"undeclared index {lab}") from None
+
+    def _nseg(self, lab):
+        return len(self.segs[self._kind(lab)])
+
+    def _segs_of(self, labs):
+        return tuple(self.idx[lab] for lab in labs)
+
+    def _shape(self, labs):
+        return tuple(self.segs[self._kind(lab)][self.idx[lab] - 1] for lab in labs)
+
+    def _is_remote(self, name):
+        return self.p.arrays.get(name, ("temp",))[0] in ("served", "distributed")
+
+    def _find(self, name, labs):
+        key = (name, self._segs_of(labs))
+        for sc in reversed(self.scopes):
+            if key in sc:
+                return sc[key]
+        return None
+
+    def _read(self, name, labs):
+        """(handle, labels it is stored with) of an operand block"""
+        if self._is_remote(name):
+            return self.be.array_block(name, self._segs_of(labs), self._shape(labs)), labs
+        h = self._find(name, labs)
+        if h is None:
+            raise SialSyntaxError(f"block {name}{list(labs)} read before it was written")
+        return h, labs
+
+    def _write(self, name, labs):
+        if self._is_remote(name):
+            raise SialSyntaxError(f"{name} is served/distributed: use put/prepare")
+        h = self._find(name, labs)
+        if h is None:
+            h = self.be.new_block(self._shape(labs))
+            self.scopes[-1][(name, self._segs_of(labs))] = h
+        return h
+
+    def _leave_scope(self):
+        for h in self.scopes.pop().values():
+            self.be.free(h)
+
+    # ---- execution -----------------------------------------------------------------------------------
+    def run(self):
+        self._block(self.p.body)
+        return self.scalars
+
+    def _block(self, stmts):
+        for st in stmts:
+            if getattr(self, "_x_" + st[0])(*st[1:]) is False:
+                return False
+        return True
+
+    def _x_where(self, a, op, b):
+        va = self.idx[a] if a in self.idx else int(a)
+        vb = self.idx[b] if b in self.idx else int(b)
+        return {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]
+
+    def _x_pardo(self, labs, body):
+        wheres = [s for s in body if s[0] == "where"]
+        rest = [s for s in body if s[0] != "where"]
+        self.be.begin_pardo()
+        ranges = [range(1, self._nseg(lab) + 1) for lab in reversed(labs)]   # first index fastest
+        for combo in itertools.product(*ranges):
+            for lab, v in zip(reversed(labs), combo):
+                self.idx[lab] = v
+            if not all(self._x_where(*w[1:]) for w in wheres):
+                continue
+            self.iteration += 1
+            if (self.iteration - 1) % self.world != self.rank:
+                continue
+            self.scopes.append({})
+            self._block(rest)
+            self._leave_scope()
+        for lab in labs:
+            del self.idx[lab]
+        self.be.end_pardo()
+
+    def _x_do(self, labs, body):
+        lab = labs[0]
+        for v in range(1, self._nseg(lab) + 1):
+            self.idx[lab] = v
+            self.scopes.append({})
+            ok = self._block(body)
+            self._leave_scope()
+            if ok is False:
+                continue
+        del self.idx[lab]
+
+    def _x_request(self, name, labs):
+        self.be.request(name, self._segs_of(labs), self._shape(labs))
+
+    def _x_fill(self, name, labs, v):
+        self.be.fill(self._write(name, labs), v)
+
+    def _x_scale(self, name, labs, f):
+        self.be.scale(self._write(name, labs), f)
+
+    def _x_assign(self, name, labs, src, slabs, _sign):
+        s, sl = self._read(src, slabs)
+        self.be.copy(self._write(name, labs), labs, s, sl)
+
+    def _x_add(self, name, labs, src, slabs, sign):
+        s, sl = self._read(src, slabs)
+        d = self._write(name, labs)
+        if tuple(sl) == tuple(labs):
+            self.be.axpy(d, s, sign)
+        else:   # handle_block_add: permute the rhs into a temp first (interpreter.cpp:1874-1997)
+            t = self.be.new_block(self._shape(labs))
+            self.be.copy(t, labs, s, sl)
+            self.be.axpy(d, t, sign)
+            self.be.free(t)
+
+    def _x_contract(self, name, labs, lname, llabs, rname, rlabs):
+        L, ll = self._read(lname, llabs)
+        R, rl = self._read(rname, rlabs)
+        self.be.contract(self._write(name, labs), labs, L, ll, R, rl)
+
+    def _x_put(self, arr, alabs, op, src, slabs):
+        s, sl = self._read(src, slabs)
+        if tuple(sl) != tuple(alabs):
+            raise SialSyntaxError("put/prepare needs matching labels on both sides")
+        (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._segs_of(alabs), s)
+
+    def _x_execute(self, fname, args, bare):
+        blocks = [self._read(n, labs)[0] if self._is_remote(n) else self._write(n, labs) for n, labs in args]
+        segs = [self._segs_of(labs) for _, labs in args]
+        kinds = [[self._kind(x) for x in labs] for _, labs in args]
+        self.be.execute(fname, blocks, segs, kinds, bare)
+
+    def _x_sdot(self, name, lname, llabs, rname, rlabs):
+        L, ll = self._read(lname, llabs)
+        R, rl = self._read(rname, rlabs)
+        self.scalars[name] = self.be.dot(L, ll, R, rl, self.scalars.get(name))
+
+    def _x_sset(self, name, v):
+        self.scalars[name] = self.be.scalar_set(self.scalars.get(name), v)
+
+    def _x_sinc(self, name, v):
+        self.scalars[name] = self.be.scalar_axpy(self.scalars[name], v, None)
+
+    def _x_smul(self, name, v):
+        self.scalars[name] = self.be.scalar_scale(self.scalars[name], v)
+
+    def _x_sadd(self, name, other, sign):
+        self.scalars[name] = self.be.scalar_axpy(self.scalars[name], sign, self.scalars[other])
+
+    def _x_scopy(self, name, other, _sign):
+        self.scalars[name] = self.be.scalar_set(self.scalars.get(name), self.scalars[other])
+
+    def _x_barrier(self):
+        self.iteration = 0           # interpreter.cpp:205-209
+        self.be.barrier()
+
+    def _x_collective(self, a, b):
+        self.scalars[a] = self.be.collective_sum(self.scalars[a], self.scalars[b])
+
+
+def label_numbers(*label_lists):
+    """labels -> small ints shared across the operands (the index-table slots the interpreter passes)"""
+    num = {}
+    for labs in label_lists:
+        for x in labs:
+            num.setdefault(x, len(num) + 1)
+    return [[num[x] for x in labs] for labs in label_lists]
+
+
+class DeviceBackend:
+    """The per-block calls of the walker on libsipgpu (C ABI).  Holds no arithmetic."""
+
+    def __init__(self, api, arrays, record=True, rank=0, world=1, barrier=None, allreduce=None):
+        """arrays: name -> api.DistArray (served/distributed arrays, created by the caller)"""
+        self.api, self.arrays, self.record = api, arrays, record
+        self.rank, self.world = rank, world
+        self._barrier, self._allreduce = barrier, allreduce
+        self.fock = None    # resident Fock diagonal block for `execute energy_denominator_rhf` (set by the caller)
+        self.cache = {}     # remote blocks fetched since the last barrier (sial_ops_parallel.cpp:41-47)
+        self.stats = []     # work-list statistics per pardo
+
+    # scalars are host floats except while a pardo accumulates into them on the device
+    def new_block(self, shape):
+        return self.api.DeviceBlock(shape)
+
+    def free(self, b):
+        b.free()
+
+    def begin_pardo(self):
+        if self.record:
+            self.api.wl_begin()
+
+    def end_pardo(self):
+        if self.record:
+            self.stats.append(self.api.wl_end())
+
+    def request(self, name, segs, shape):
+        self.array_block(name, segs, shape)
+
+    def array_block(self, name, segs, shape):
+        A = self.arrays[name]
+        if A.owner(segs) == self.rank:
+            return A.block_view(segs)          # resident: no copy at all
+        key = (name, segs)
+        if key not in self.cache:
+            self.cache[key] = A.get(segs)      # peer read over NVLink into the worker-side cache
+        return self.cache[key]
+
+    def fill(self, b, v):
+        b.fill(v)
+
+    def scale(self, b, f):
+        b.scale(f)
+
+    def axpy(self, d, s, f):
+        d.axpy(s, f)
+
+    def copy(self, d, dlabs, s, slabs):
+        if tuple(dlabs) == tuple(slabs):
+            d.scale_and_copy(s, 1.0)
+        else:
+            dn, sn = label_numbers(dlabs, slabs)
+            self.api.permute_labels(dn, sn, s, out=d)
+
+    def contract(self, d, dlabs, L, llabs, R, rlabs):
+        dn, ln, rn = label_numbers(dlabs, llabs, rlabs)
+        self.api.contract_labels(dn, d.shape, ln, L, rn, R, out=d)
+
+    def put(self, arr, segs, b):
+        self.arrays[arr].put(segs, b)
+
+    def put_accumulate(self, arr, segs, b):
+        self.arrays[arr].put_accumulate(segs, b)
+
+    def execute(self, fname, blocks, segs, kinds, bare):
+        if fname == "energy_denominator_rhf":
+            self.api.si_energy_denominator_rhf(blocks[0], segs[0], self.fock)
+        else:
+            raise SialSyntaxError(f"super-instruction {fname} is not on the device path")
+
+    def dot(self, L, llabs, R, rlabs, prev):
+        acc = prev if isinstance(prev, self.api.DeviceBlock) else self.api.DeviceBlock((1,), zero=True)
+        if tuple(llabs) != tuple(rlabs):
+            t = self.api.DeviceBlock(R.shape)
+            ln, rn = label_numbers(llabs, rlabs)
+            self.api.permute_labels(rn, ln, L, out=t)
+            L = t
+        acc.fill(0.0)
+        self.api._check(self.api.lib().sipgpu_block_dot_accumulate(L.ptr, R.ptr, L.size, acc.ptr))
+        return acc
+
+    def _val(self, s):
+        return float(s.to_numpy()[0]) if isinstance(s, self.api.DeviceBlock) else float(s)
+
+    def scalar_set(self, prev, v):
+        if isinstance(v, self.api.DeviceBlock):
+            out = prev if isinstance(prev, self.api.DeviceBlock) and prev is not v else self.api.DeviceBlock((1,))
+            out.scale_and_copy(v, 1.0)
+            return out
+        if isinstance(prev, self.api.DeviceBlock):
+            return prev.fill(v)
+        return float(v)
+
+    def scalar_axpy(self, s, f, other):
+        if other is None:
+            return s.increment(f) if isinstance(s, self.api.DeviceBlock) else s + f
+        if isinstance(other, self.api.DeviceBlock):
+            if not isinstance(s, self.api.DeviceBlock):
+                s = self.api.DeviceBlock((1,)).fill(float(s))
+            return s.axpy(other, f)
+        return s.increment(f * other) if isinstance(s, self.api.DeviceBlock) else s + f * other
+
+    def scalar_scale(self, s, f):
+        return s.scale(f) if isinstance(s, self.api.DeviceBlock) else s * f
+
+    def barrier(self):
+        self.api.sync()
+        if self._barrier:
+            self._barrier()
+        self.cache.clear()
+
+    def collective_sum(self, a, b):
+        v = self._val(b)
+        if self._allreduce:
+            v = self._allreduce(v)
+        return self._val(a) + v
+
+    def value(self, s):
+        return self._val(s)

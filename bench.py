@@ -339,6 +339,17 @@ def main():
                "sample": f"{len(s.dests)} destination blocks x all 5 terms ({s.flops / 1e9:.0f} GFLOP, {sec:.1f} s), oracle "
                          f"permute->OpenBLAS dgemm->permute + accumulate"}
 
+    # DRAM traffic of the dominant launch (the pp-ladder chain launch, ~76 % of the step) from the committed single-pass
+    # ncu capture of this same command at full size; null for development sizes
+    traffic = traffic_alg = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_ccsd_full.json")
+    if o_segs == O_SEGS and v_segs == V_SEGS and os.path.exists(tpath):
+        try:
+            dom = max(json.load(open(tpath))["launches"], key=lambda x: x["seconds"])
+            traffic, traffic_alg = dom["dram_bytes"] / world, dom["algorithmic_min_bytes"] / world
+        except Exception:
+            traffic = traffic_alg = None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -353,7 +364,9 @@ def main():
                          "achieved": k_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": k_tf / peak_tf if peak_tf else None,
                          "peak_source": "DMMA issue-rate probe measured in this run (MEASURED_PEAKS.json holds no FP64 figure)",
                          "kernel_share_of_step": k_share,
-                         "traffic": None},
+                         "traffic": traffic, "traffic_algorithmic_min": traffic_alg,
+                         "traffic_source": "profiles/r01_traffic_ccsd_full.json (ncu dram__bytes_read+write of the dominant "
+                                           "launch, the pp-ladder chain; bytes per launch per GPU)" if traffic else None},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -1,0 +1,228 @@
+// wl_pardo_bench.cpp -- the op-at-a-time call stream of three LCCD pardo bodies (rlccd_rhf.sialx: hhladder_ab :342-355,
+// phladder_ab pardo 1 :482-513 and pardo 3 :537-556) issued from C++ through the C ABI of libsipgpu.so, exactly as the
+// C++ interpreter would issue them (temp alloc, contract, scale, permute, put +=, free per statement), timed
+//   (a) eagerly -- one kernel launch per statement, and
+//   (b) inside sipgpu_wl_begin()/sipgpu_wl_end() per pardo -- the deferred op stream of worklist.cu.
+// No Python in the timed region: this is the host-overhead-free comparison the work-list exists for.
+//   build: g++ -O2 -std=c++17 wl_pardo_bench.cpp -I../../include -L../../aces4_b200/lib -lsipgpu -Wl,-rpath,... -o wl_pardo_bench
+//   usage: wl_pardo_bench <o_seg> <n_o_segs> <v_seg> <n_v_segs> [reps]
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "sipgpu.h"
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        int rc__ = (call);                                                                 \
+        if (rc__ != 0) {                                                                   \
+            fprintf(stderr, "%s failed (%d): %s\n", #call, rc__, sipgpu_last_error());     \
+            exit(1);                                                                       \
+        }                                                                                  \
+    } while (0)
+
+static int so, no, sv, nv;
+
+struct Arr {
+    sipgpu_array* h = nullptr;
+    int kinds[4];  // 0 = occupied, 1 = virtual
+    void create(const int k[4]) {
+        int nseg[4];
+        std::vector<int> ext;
+        for (int d = 0; d < 4; ++d) {
+            kinds[d] = k[d];
+            nseg[d] = k[d] ? nv : no;
+            for (int s = 0; s < nseg[d]; ++s) ext.push_back(k[d] ? sv : so);
+        }
+        CK(sipgpu_array_create(4, nseg, ext.data(), 0, 1, &h));
+    }
+    double* blk(int a, int b, int c, int d) {
+        const int idx[4] = {a, b, c, d};
+        double* p = sipgpu_array_block_ptr(h, idx);
+        if (!p) { fprintf(stderr, "block_ptr failed\n"); exit(1); }
+        return p;
+    }
+    long long size(int a, int b, int c, int d) {
+        const int idx[4] = {a, b, c, d};
+        return sipgpu_array_block_size(h, idx);
+    }
+    void fill_hash(unsigned long long tag) {
+        int n[4];
+        for (int d = 0; d < 4; ++d) n[d] = kinds[d] ? nv : no;
+        for (int a = 1; a <= n[0]; ++a)
+            for (int b = 1; b <= n[1]; ++b)
+                for (int c = 1; c <= n[2]; ++c)
+                    for (int d = 1; d <= n[3]; ++d) {
+                        const int idx[4] = {a, b, c, d};
+                        CK(sipgpu_block_fill_hash(blk(a, b, c, d), size(a, b, c, d), 0xACE54ull,
+                                                  (tag << 40) | (unsigned long long)sipgpu_array_block_number(h, idx), 0.1));
+                    }
+    }
+};
+
+static Arr T2old, T2new, Voooo, Vaaii, Viaai;
+
+static void ext4(int k0, int k1, int k2, int k3, int* e) {
+    const int k[4] = {k0, k1, k2, k3};
+    for (int d = 0; d < 4; ++d) e[d] = k[d] ? sv : so;
+}
+static long long vol(const int* e) { return (long long)e[0] * e[1] * e[2] * e[3]; }
+
+// labels: a=1 i=2 b=3 j=4 i1=5 j1=6 a1=7 b1=8
+static void hhladder() {
+    int eD[4], eL[4], eR[4];
+    ext4(1, 0, 1, 0, eD);
+    ext4(1, 0, 1, 0, eL);
+    ext4(0, 0, 0, 0, eR);
+    const int dl[4] = {1, 2, 3, 4}, ll[4] = {1, 5, 3, 6}, rl[4] = {2, 5, 4, 6};
+    for (int j1 = 1; j1 <= no; ++j1)
+        for (int i1 = 1; i1 <= no; ++i1)
+            for (int b = 1; b <= nv; ++b)
+                for (int a = 1; a <= nv; ++a) {   // pardo a, b, i1, j1 (first index fastest)
+                    const int idxL[4] = {a, i1, b, j1};
+                    const double* L = sipgpu_array_block_ptr(T2old.h, idxL);   // request T2old_ab[a,i1,b,j1]
+                    for (int i = 1; i <= no; ++i)
+                        for (int j = 1; j <= no; ++j) {
+                            const double* R = Voooo.blk(i, i1, j, j1);
+                            double* T = sipgpu_block_alloc(vol(eD), 0);
+                            CK(sipgpu_block_contract_labels(4, eD, dl, T, 4, eL, ll, L, 4, eR, rl, R, 1.0, 0.0));
+                            const int idxD[4] = {a, i, b, j};
+                            CK(sipgpu_array_put_accumulate(T2new.h, idxD, T));
+                            CK(sipgpu_block_free(T));
+                        }
+                }
+}
+
+static void phring3() {
+    int eD[4], eL[4], eR[4];
+    ext4(1, 0, 1, 0, eD);
+    ext4(1, 0, 1, 0, eL);
+    ext4(1, 1, 0, 0, eR);
+    // Taibj[a,i,b,j] = T2old[a,i1,b1,j]*Vaaii[b,b1,i1,i]
+    const int dl[4] = {1, 2, 3, 4}, ll[4] = {1, 5, 8, 4}, rl[4] = {3, 8, 5, 2};
+    const int pl[4] = {3, 4, 1, 2};  // T2aibj[b,j,a,i] = Taibj[a,i,b,j]
+    for (int b1 = 1; b1 <= nv; ++b1)
+        for (int i1 = 1; i1 <= no; ++i1)
+            for (int j = 1; j <= no; ++j)
+                for (int a = 1; a <= nv; ++a) {   // pardo a, j, i1, b1
+                    const double* L = T2old.blk(a, i1, b1, j);
+                    for (int i = 1; i <= no; ++i)
+                        for (int b = 1; b <= nv; ++b) {
+                            const double* R = Vaaii.blk(b, b1, i1, i);
+                            double* T = sipgpu_block_alloc(vol(eD), 0);
+                            CK(sipgpu_block_contract_labels(4, eD, dl, T, 4, eL, ll, L, 4, eR, rl, R, 1.0, 0.0));
+                            CK(sipgpu_block_scale(T, vol(eD), -1.0));
+                            double* T2 = sipgpu_block_alloc(vol(eD), 0);
+                            CK(sipgpu_block_permute_labels(4, eD, pl, dl, T, T2));
+                            const int idx1[4] = {a, i, b, j}, idx2[4] = {b, j, a, i};
+                            CK(sipgpu_array_put_accumulate(T2new.h, idx1, T));
+                            CK(sipgpu_array_put_accumulate(T2new.h, idx2, T2));
+                            CK(sipgpu_block_free(T));
+                            CK(sipgpu_block_free(T2));
+                        }
+                }
+}
+
+static void phring1() {
+    int eD[4], eY[4], eVa[4], eVi[4];
+    ext4(1, 0, 1, 0, eD);
+    ext4(1, 0, 1, 0, eY);
+    ext4(1, 1, 0, 0, eVa);
+    ext4(0, 1, 1, 0, eVi);
+    const long long n = vol(eD);
+    const int yl[4] = {1, 2, 7, 5};                                      // TYaiai[a,i,a1,i1]
+    const int val[4] = {7, 1, 2, 5}, vil[4] = {2, 1, 7, 5};              // Vaaii[a1,a,i,i1], Viaai[i,a,a1,i1]
+    const int dl[4] = {1, 2, 3, 4}, rl[4] = {7, 5, 3, 4};                // R1 = TY * T2old[a1,i1,b,j]
+    const int pl[4] = {3, 4, 1, 2};
+    for (int i = 1; i <= no; ++i)
+        for (int a = 1; a <= nv; ++a)
+            for (int b = 1; b <= nv; ++b)
+                for (int j = 1; j <= no; ++j) {   // pardo j, b, a, i
+                    double* Tacc = sipgpu_block_alloc(n, 0);
+                    CK(sipgpu_block_fill(Tacc, n, 0.0));
+                    for (int i1 = 1; i1 <= no; ++i1)
+                        for (int a1 = 1; a1 <= nv; ++a1) {
+                            double* TY = sipgpu_block_alloc(n, 0);
+                            CK(sipgpu_block_fill(TY, n, 0.0));
+                            double* Tt = sipgpu_block_alloc(n, 0);
+                            CK(sipgpu_block_permute_labels(4, eVa, yl, val, Vaaii.blk(a1, a, i, i1), Tt));
+                            CK(sipgpu_block_axpy(TY, Tt, n, -1.0));
+                            CK(sipgpu_block_free(Tt));
+                            Tt = sipgpu_block_alloc(n, 0);   // the interpreter re-creates the temp on assignment
+                            CK(sipgpu_block_permute_labels(4, eVi, yl, vil, Viaai.blk(i, a, a1, i1), Tt));
+                            CK(sipgpu_block_axpy(TY, Tt, n, 1.0));
+                            double* R1 = sipgpu_block_alloc(n, 0);
+                            CK(sipgpu_block_contract_labels(4, eD, dl, R1, 4, eY, yl, TY, 4, eD, rl, T2old.blk(a1, i1, b, j), 1.0, 0.0));
+                            CK(sipgpu_block_accumulate(Tacc, R1, n));
+                            CK(sipgpu_block_free(Tt));
+                            CK(sipgpu_block_free(TY));
+                            CK(sipgpu_block_free(R1));
+                        }
+                    double* R1t = sipgpu_block_alloc(n, 0);
+                    CK(sipgpu_block_permute_labels(4, eD, pl, dl, Tacc, R1t));
+                    const int idx1[4] = {a, i, b, j}, idx2[4] = {b, j, a, i};
+                    CK(sipgpu_array_put_accumulate(T2new.h, idx1, Tacc));
+                    CK(sipgpu_array_put_accumulate(T2new.h, idx2, R1t));
+                    CK(sipgpu_block_free(Tacc));
+                    CK(sipgpu_block_free(R1t));
+                }
+}
+
+static double checksum() {
+    double s = 0;
+    CK(sipgpu_block_norm2(sipgpu_array_local_base(T2new.h), (long long)(sipgpu_array_local_bytes(T2new.h) / 8), &s));
+    return s;
+}
+
+int main(int argc, char** argv) {
+    so = argc > 1 ? atoi(argv[1]) : 20;
+    no = argc > 2 ? atoi(argv[2]) : 2;
+    sv = argc > 3 ? atoi(argv[3]) : 50;
+    nv = argc > 4 ? atoi(argv[4]) : 4;
+    const int reps = argc > 5 ? atoi(argv[5]) : 3;
+    CK(sipgpu_init(0));
+    const int kT[4] = {1, 0, 1, 0}, kO[4] = {0, 0, 0, 0}, kVa[4] = {1, 1, 0, 0}, kVi[4] = {0, 1, 1, 0};
+    T2old.create(kT); T2new.create(kT); Voooo.create(kO); Vaaii.create(kVa); Viaai.create(kVi);
+    T2old.fill_hash(1); Voooo.fill_hash(3); Vaaii.fill_hash(6); Viaai.fill_hash(5);
+    CK(sipgpu_sync());
+    const double o = (double)so * no, v = (double)sv * nv;
+    const double flops = 2.0 * o * o * o * o * v * v + 2 * 2.0 * o * o * o * v * v * v;
+    void (*pardos[3])() = {hhladder, phring1, phring3};
+    double best[2] = {1e30, 1e30}, sum[2] = {0, 0};
+    long long launches[2] = {0, 0};
+    long long st[9] = {0};
+    for (int mode = 0; mode < 2; ++mode)
+        for (int r = 0; r < reps + 1; ++r) {
+            CK(sipgpu_array_fill_local(T2new.h, 0.0));
+            CK(sipgpu_sync());
+            const long long l0 = sipgpu_kernel_launches();
+            long long acc[9] = {0};
+            const auto t0 = std::chrono::steady_clock::now();
+            for (auto f : pardos) {
+                if (mode) CK(sipgpu_wl_begin(0));
+                f();
+                if (mode) {
+                    CK(sipgpu_wl_end());
+                    long long s9[9];
+                    CK(sipgpu_wl_stats(s9));
+                    for (int k = 0; k < 9; ++k) acc[k] += s9[k];
+                }
+            }
+            CK(sipgpu_sync());
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (r > 0 && sec < best[mode]) best[mode] = sec;
+            launches[mode] = sipgpu_kernel_launches() - l0;
+            sum[mode] = checksum();
+            if (mode) for (int k = 0; k < 9; ++k) st[k] = acc[k];
+        }
+    printf("{\"workload\": \"hhladder_ab + phladder_ab pardos 1,3 (rlccd_rhf.sialx) issued op-at-a-time from C++; o=%dx%d v=%dx%d\", "
+           "\"flops\": %.6e, \"op_at_a_time\": {\"seconds\": %.6f, \"tflops\": %.3f, \"kernel_launches\": %lld}, "
+           "\"recorded\": {\"seconds\": %.6f, \"tflops\": %.3f, \"kernel_launches\": %lld, \"ops_recorded\": %lld, "
+           "\"ops_scheduled\": %lld, \"levels\": %lld, \"fused_accumulates\": %lld, \"chains\": %lld, \"chain_pairs\": %lld, "
+           "\"temps_elided\": %lld, \"flushes\": %lld}, \"speedup\": %.3f, \"t2new_norm2_rel_diff\": %.3e}\n",
+           no, so, nv, sv, flops, best[0], flops / best[0] / 1e12, launches[0], best[1], flops / best[1] / 1e12, launches[1],
+           st[0], st[1], st[2], st[4], st[5], st[6], st[7], st[8], best[0] / best[1], std::fabs(sum[1] - sum[0]) / sum[0]);
+    return 0;
+}

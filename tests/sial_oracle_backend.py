@@ -1,0 +1,108 @@
+"""Oracle backend of the SIAL front-end walker (aces4_b200/sial_frontend.py): the same per-block call stream executed
+on the host with the CPU oracle (oracle/), blocks as numpy Fortran arrays.  Test infrastructure only."""
+import numpy as np
+
+
+class HostBlock:
+    def __init__(self, a):
+        self.a = a
+
+    @property
+    def shape(self):
+        return self.a.shape
+
+
+class OracleBackend:
+    def __init__(self, oracle, arrays, fock=None, moa_seg_ranges=None):
+        """arrays: name -> dict {segment tuple: ndarray}; missing blocks of a put target are created as zeros"""
+        self.o, self.arrays, self.fock, self.ranges = oracle, arrays, fock, moa_seg_ranges
+        self.calls = 0
+
+    def new_block(self, shape):
+        return HostBlock(np.full(shape, np.nan, order="F"))
+
+    def free(self, b):
+        b.a = None
+
+    def begin_pardo(self):
+        pass
+
+    def end_pardo(self):
+        pass
+
+    def request(self, name, segs, shape):
+        pass
+
+    def array_block(self, name, segs, shape):
+        A = self.arrays[name]
+        if segs not in A:
+            A[segs] = np.zeros(shape, order="F")
+        return HostBlock(A[segs])
+
+    def fill(self, b, v):
+        b.a[...] = v
+        self.calls += 1
+
+    def scale(self, b, f):
+        b.a *= f
+        self.calls += 1
+
+    def axpy(self, d, s, f):
+        d.a[...] = self.o.block_add(d.a, s.a, f)[0]
+        self.calls += 1
+
+    def copy(self, d, dlabs, s, slabs):
+        from aces4_b200.sial_frontend import label_numbers
+        if tuple(dlabs) == tuple(slabs):
+            d.a[...] = s.a
+        else:
+            dn, sn = label_numbers(dlabs, slabs)
+            d.a[...] = self.o.permute_labels(dn, sn, s.a)
+        self.calls += 1
+
+    def contract(self, d, dlabs, L, llabs, R, rlabs):
+        from aces4_b200.sial_frontend import label_numbers
+        dn, ln, rn = label_numbers(dlabs, llabs, rlabs)
+        out, ierr = self.o.contract_labels(dn, list(d.shape), ln, L.a, rn, R.a)
+        assert ierr == 0
+        d.a[...] = out
+        self.calls += 1
+
+    def put(self, arr, segs, b):
+        self.arrays[arr][segs] = np.array(b.a, order="F")
+
+    def put_accumulate(self, arr, segs, b):
+        A = self.arrays[arr]
+        if segs not in A:
+            A[segs] = np.zeros(b.shape, order="F")
+        A[segs] = self.o.block_add(A[segs], b.a, 1.0)[0]
+
+    def execute(self, fname, blocks, segs, kinds, bare):
+        assert fname == "energy_denominator_rhf"
+        assert self.o.si_energy_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, self.ranges) == 0
+
+    def dot(self, L, llabs, R, rlabs, prev):
+        from aces4_b200.sial_frontend import label_numbers
+        a = L.a
+        if tuple(llabs) != tuple(rlabs):
+            ln, rn = label_numbers(llabs, rlabs)
+            a = self.o.permute_labels(rn, ln, a)
+        return float(np.sum(a * R.a))
+
+    def scalar_set(self, prev, v):
+        return float(v)
+
+    def scalar_axpy(self, s, f, other):
+        return s + f if other is None else s + f * other
+
+    def scalar_scale(self, s, f):
+        return s * f
+
+    def barrier(self):
+        pass
+
+    def collective_sum(self, a, b):
+        return a + b
+
+    def value(self, s):
+        return float(s)

@@ -1,0 +1,229 @@
+"""GPU parity tests of the deferred op stream (aces4_b200/csrc/worklist.cu) and the SIAL front-end on the device
+backend: the SAME per-block call stream executed (a) op-at-a-time, (b) recorded and scheduled into batched launches,
+(c) on the CPU oracle.  Tolerance: 1e-10 relative on blocks (BASELINE.json north_star); recorded vs op-at-a-time differ
+only by the summation order inside fused chains."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def sip():
+    import aces4_b200 as s
+
+    s.init(0)
+    return s.api
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def run_stream(sip, seed, record, nops=220, v=12):
+    rnd = random.Random(seed)
+    rng = np.random.default_rng(seed)
+    p2, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    live = [sip.DeviceBlock.from_numpy(rng.uniform(-1, 1, (v, v))) for _ in range(6)]
+    if record:
+        sip.wl_begin()
+    for _ in range(nops):
+        k = rnd.randrange(10)
+        pick = lambda: rnd.choice(live)  # noqa: E731
+        if k == 0:
+            pick().fill(0.0 if rnd.random() < 0.5 else 0.25)
+        elif k == 1:
+            pick().scale(0.5)
+        elif k == 2:
+            d, s = pick(), pick()
+            if d is not s:
+                d.axpy(s, rnd.choice([1.0, -1.0, 0.5]))
+        elif k == 3:
+            d, s = pick(), pick()
+            if d is not s:
+                d.scale_and_copy(s, 0.75)
+        elif k == 4:
+            d, a, b = pick(), pick(), pick()
+            d.set_add_sub(a, b, rnd.choice([1.0, -1.0]))
+        elif k == 5:
+            d, s = pick(), pick()
+            if d is not s:
+                sip.permute(s, [1, 2, 1], out=d)
+        elif k in (6, 7):
+            d, a, b = pick(), pick(), pick()
+            if d is not a and d is not b:
+                sip.contract(p2, a, b, (v, v), out=d, alpha=0.125, beta=rnd.choice([0.0, 1.0, 1.0]))
+        elif k == 8:
+            a, b, d = pick(), pick(), pick()
+            t = sip.DeviceBlock((v, v))
+            sip.contract(p2, a, b, (v, v), out=t, alpha=0.125)
+            d.axpy(t, 1.0)
+            t.free()
+        else:
+            s, d = pick(), pick()
+            t = sip.DeviceBlock((v, v))
+            sip.permute(s, [1, 2, 1], out=t)
+            d.axpy(t, -0.5)
+            t.free()
+    stats = sip.wl_end() if record else None
+    out = [b.to_numpy() for b in live]
+    for b in live:
+        b.free()
+    return out, stats
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_streams_recorded_equal_op_at_a_time(sip, seed):
+    eager, _ = run_stream(sip, seed, record=False)
+    rec, st = run_stream(sip, seed, record=True)
+    for a, b in zip(rec, eager):
+        assert np.all(np.isfinite(b))
+        assert rel(a, b) <= 1e-12
+    assert st["scheduled"] < st["recorded"] and st["fused_accumulates"] > 0
+
+
+def test_implicit_flush_on_blocking_reads(sip):
+    a = sip.DeviceBlock.from_numpy(np.arange(24.0).reshape(4, 6))
+    with sip.recording():
+        a.scale(2.0)
+        before = sip.kernel_launches()
+        got = a.to_numpy()          # d2h is blocking: the recording is drained first
+        assert sip.kernel_launches() > before
+        assert np.array_equal(got, 2.0 * np.arange(24.0).reshape(4, 6))
+        a.increment(1.0)
+        assert abs(a.norm2() - float(np.sum((2.0 * np.arange(24.0) + 1.0) ** 2))) < 1e-9
+    assert sip.lib().sipgpu_wl_recording() == 0
+
+
+def test_hhladder_chain_matches_oracle(sip, oracle):
+    """do i1, j1: T = T2old[a,i1,b,j1]*V[i,i1,j,j1]; D += T (rlccd_rhf.sialx:342-355), one destination, 3x3 segments"""
+    v, o, n = 10, 6, 3
+    rng = np.random.default_rng(5)
+    T2 = [[rng.uniform(-1, 1, (v, o, v, o)) for _ in range(n)] for _ in range(n)]
+    V = [[rng.uniform(-1, 1, (o, o, o, o)) for _ in range(n)] for _ in range(n)]
+    dlab, llab, rlab = [1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6]
+    want = np.zeros((v, o, v, o), order="F")
+    for i1 in range(n):
+        for j1 in range(n):
+            t, ierr = oracle.contract_labels(dlab, [v, o, v, o], llab, T2[i1][j1], rlab, V[i1][j1])
+            assert ierr == 0
+            want += t
+    dT2 = [[sip.DeviceBlock.from_numpy(x) for x in row] for row in T2]
+    dV = [[sip.DeviceBlock.from_numpy(x) for x in row] for row in V]
+    D = sip.DeviceBlock((v, o, v, o))
+    launches0 = sip.kernel_launches()
+    with sip.recording() as rec:
+        D.fill(0.0)
+        for i1 in range(n):
+            for j1 in range(n):
+                t = sip.DeviceBlock((v, o, v, o))
+                sip.contract_labels(dlab, (v, o, v, o), llab, dT2[i1][j1], rlab, dV[i1][j1], out=t)
+                D.accumulate(t)
+                t.free()
+    assert rec.stats["chains"] == 1 and rec.stats["chain_pairs"] == n * n and rec.stats["scheduled"] == 1
+    assert sip.kernel_launches() - launches0 == 1        # 19 recorded ops -> ONE kernel launch
+    assert rel(D.to_numpy(), want) <= TOL
+
+
+def test_put_accumulate_stress_recorded(sip):
+    """Sial.put_accumulate_stress (test_sial.cpp:1072-1113): pardo k(1..20): put c[i,j] += a; += aa; += a; += aa with
+    a = i, aa = j  ->  every element of c[i,j] = 20*(2i+2j); here through the recorded stream (red.add commutes)."""
+    segs = [[2, 3, 2], [2, 3, 2]]
+    c = sip.DistArray(segs)
+    c.fill_local(0.0)
+    sip.sync()
+    with sip.recording() as rec:
+        for k in range(20):
+            for i in range(1, 4):
+                for j in range(1, 4):
+                    shape = c.block_shape((i, j))
+                    a, aa = sip.DeviceBlock(shape), sip.DeviceBlock(shape)
+                    a.fill(float(i))
+                    aa.fill(float(j))
+                    for blk in (a, aa, a, aa):
+                        c.put_accumulate((i, j), blk)
+                    a.free()
+                    aa.free()
+    assert rec.stats["levels"] == 2 and rec.stats["launches"] == 2     # all fills, then all red.adds
+    for i in range(1, 4):
+        for j in range(1, 4):
+            got = c.get((i, j)).to_numpy()
+            assert np.all(got == 20.0 * (2 * i + 2 * j))
+    c.destroy()
+
+
+def test_opaque_ops_keep_program_order(sip, oracle):
+    """slices of a static array, a scalar contraction and a sliced contraction inside a recording"""
+    rng = np.random.default_rng(11)
+    ca = rng.uniform(-1, 1, (9, 14))
+    x = rng.uniform(-1, 1, (9, 5))
+    dca, dx = sip.DeviceBlock.from_numpy(ca), sip.DeviceBlock.from_numpy(x)
+    with sip.recording():
+        s = sip.slice_block(dca, (9, 5), (0, 4))
+        s.axpy(dx, 2.0)
+        sip.insert_block(dca, s, (0, 4))
+        dca.scale(0.5)
+        s2 = sip.slice_block(dca, (9, 5), (0, 4))
+        got_s2 = s2.to_numpy()
+    want = ca.copy()
+    want[:, 4:9] += 2.0 * x
+    want *= 0.5
+    assert rel(dca.to_numpy(), want) <= 1e-15
+    assert rel(got_s2, want[:, 4:9]) <= 1e-15
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the SIAL front-end on the device backend
+# ---------------------------------------------------------------------------------------------------------------
+def device_arrays(sip, host_arrays, kinds, segs):
+    out = {}
+    for name, blocks in host_arrays.items():
+        A = sip.DistArray([segs[k] for k in kinds[name]])
+        for idx, b in blocks.items():
+            view = A.block_view(idx)
+            sip._check(sip.lib().sipgpu_h2d(view.ptr, sip._hp(np.asfortranarray(b)), view.size), "h2d")
+        sip.sync()
+        out[name] = A
+    return out
+
+
+@pytest.mark.parametrize("segs", [{"o": [4, 4, 5], "v": [6, 7, 6]}, {"o": [20, 20], "v": [50, 50]}])
+def test_lccd_sial_program_device_vs_oracle(sip, oracle, segs):
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+    from sial_oracle_backend import OracleBackend
+    from test_sial_frontend_cpu import KINDS, LCCD, make_arrays
+
+    host = make_arrays(oracle, segs)
+    small = sum(segs["v"]) < 40
+    if small:
+        ref_arrays = {k: {i: b.copy() for i, b in v.items()} for k, v in host.items()}
+        be_o = OracleBackend(oracle, ref_arrays)
+        e_ref = be_o.value(Walker(Program(LCCD), be_o, segs).run()["ecorrab"])
+    results = {}
+    for record in (False, True):
+        arrays = device_arrays(sip, host, KINDS, segs)
+        be = DeviceBackend(sip, arrays, record=record)
+        l0 = sip.kernel_launches()
+        scal = Walker(Program(LCCD), be, segs).run()
+        e = be.value(scal["ecorrab"])
+        launches = sip.kernel_launches() - l0
+        blocks = {idx: arrays["t2new_ab"].get(idx).to_numpy() for idx in host["t2new_ab"]}
+        results[record] = (blocks, e, launches, be.stats)
+        for A in arrays.values():
+            A.destroy()
+    (b0, e0, l0, _), (b1, e1, l1, st) = results[False], results[True]
+    for idx in b0:
+        assert rel(b1[idx], b0[idx]) <= TOL
+        if small:
+            assert rel(b1[idx], ref_arrays["t2new_ab"][idx]) <= TOL
+    assert abs(e1 - e0) <= TOL * abs(e0)
+    if small:
+        assert abs(e1 - e_ref) <= TOL * abs(e_ref)
+    assert l1 * 4 < l0, (l0, l1)      # the recorded stream needs far fewer launches than op-at-a-time
+    assert sum(s["chains"] for s in st) > 0 and sum(s["fused_accumulates"] for s in st) > 0

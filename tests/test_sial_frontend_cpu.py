@@ -1,0 +1,145 @@
+"""CPU tests of the SIAL front-end (aces4_b200/sial_frontend.py): the parser, the walker's loop/scope/where
+semantics and the pardo work distribution, executed on the ORACLE backend and compared with dense numpy.einsum of the
+LCCD doubles equations.  No GPU needed.  (The same SIAL text runs on the device backend in tests/test_gpu_worklist.py.)"""
+import os
+
+import numpy as np
+import pytest
+
+from aces4_b200.sial_frontend import Program, SialSyntaxError, Walker
+from sial_oracle_backend import OracleBackend
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LCCD = open(os.path.join(HERE, "golden", "lccd_doubles.sialx")).read()
+KINDS = {"vpiqj": "vovo", "voooo": "oooo", "viaai": "ovvo", "vaaii": "vvoo", "t2old_ab": "vovo", "t2new_ab": "vovo"}
+TAGS = {"vpiqj": 2, "voooo": 3, "viaai": 5, "vaaii": 6, "t2old_ab": 1}
+
+
+def make_arrays(oracle, segs, seed=0xACE54):
+    """name -> {segment tuple: block}, seeded like the synthetic workload (oracle.fill_hash)"""
+    arrays = {}
+    for name, kind in KINDS.items():
+        blocks = {}
+        nseg = [len(segs[k]) for k in kind]
+        for idx in np.ndindex(*nseg):
+            idx1 = tuple(i + 1 for i in idx)
+            shape = tuple(segs[k][i] for k, i in zip(kind, idx))
+            if name == "t2new_ab":
+                blocks[idx1] = np.zeros(shape, order="F")
+            else:
+                number = 0
+                for p in range(4):
+                    number = number * nseg[p] + idx[p]
+                blocks[idx1] = oracle.fill_hash(shape, seed, (TAGS[name] << 40) | number, 0.1)
+        arrays[name] = blocks
+    return arrays
+
+
+def dense(blocks, kind, segs):
+    offs = []
+    for k in kind:
+        o = [0]
+        for s in segs[k]:
+            o.append(o[-1] + s)
+        offs.append(o)
+    full = np.zeros([o[-1] for o in offs])
+    for idx, b in blocks.items():
+        sl = tuple(slice(offs[d][idx[d] - 1], offs[d][idx[d]]) for d in range(len(kind)))
+        full[sl] = b
+    return full
+
+
+def dense_reference(arrays, segs):
+    V = dense(arrays["vpiqj"], "vovo", segs)
+    Vo = dense(arrays["voooo"], "oooo", segs)
+    Via = dense(arrays["viaai"], "ovvo", segs)
+    Vaa = dense(arrays["vaaii"], "vvoo", segs)
+    T = dense(arrays["t2old_ab"], "vovo", segs)
+    sym = lambda X: X + np.transpose(X, (2, 3, 0, 1))  # noqa: E731
+    new = sym(0.5 * V)
+    new += np.einsum("akbl,ikjl->aibj", T, Vo)
+    TY = np.einsum("iack->aick", Via) - np.einsum("caik->aick", Vaa)
+    new += sym(np.einsum("aick,ckbj->aibj", TY, T))
+    W = np.einsum("ckai->ckia", T) - np.einsum("ciak->ckia", T)
+    new += sym(np.einsum("ckia,iabj->ckbj", W, Via))
+    new += sym(-np.einsum("akcj,bcki->aibj", T, Vaa))
+    e = np.einsum("aibj,aibj->", new, 2.0 * V - np.transpose(V, (0, 3, 2, 1)))
+    return new, e
+
+
+def test_parser_reads_the_lccd_fragment():
+    p = Program(LCCD)
+    assert p.index_kind["a1"] == "v" and p.index_kind["j1"] == "o"
+    assert p.arrays["t2new_ab"] == ("served", ("a", "i", "b", "j"))
+    pardos = [s for s in p.body if s[0] == "pardo"]
+    assert [s[1] for s in pardos] == [("a", "b", "i", "j"), ("a", "b", "i1", "j1"), ("j", "b", "a", "i"),
+                                      ("i1", "a1", "a", "i"), ("a", "j", "i1", "b1"), ("a", "i", "b", "j")]
+    hh = pardos[1][2]
+    assert hh[0] == ("request", "t2old_ab", ("a", "i1", "b", "j1"))
+    inner = hh[1][2][0][2]      # do i / do j body
+    assert inner[1] == ("contract", "taibj", ("a", "i", "b", "j"), "t2old_ab", ("a", "i1", "b", "j1"), "voooo",
+                        ("i", "i1", "j", "j1"))
+    assert inner[2] == ("put", "t2new_ab", ("a", "i", "b", "j"), "+=", "taibj", ("a", "i", "b", "j"))
+
+
+@pytest.mark.parametrize("bad", ["pardo a\n  Taibj[a] = 1.0\n", "x[i] = y[i] + z[i]\n", "where a ** b\n",
+                                 "moaindex q = 1: 7\n", "enddo i\n", "prepare A[i] -= T[i]\n"])
+def test_parser_rejects_what_it_does_not_understand(bad):
+    with pytest.raises(SialSyntaxError):
+        Program(bad)
+
+
+@pytest.mark.parametrize("segs", [{"o": [2, 3], "v": [3, 4]}, {"o": [3], "v": [2, 2, 3]}])
+def test_lccd_doubles_on_the_oracle_backend_match_dense_einsum(oracle, segs):
+    arrays = make_arrays(oracle, segs)
+    want, e_want = dense_reference(arrays, segs)
+    be = OracleBackend(oracle, arrays)
+    scal = Walker(Program(LCCD), be, segs).run()
+    got = dense(arrays["t2new_ab"], "vovo", segs)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+    assert abs(be.value(scal["ecorrab"]) - e_want) <= 1e-12 * abs(e_want)
+
+
+def test_pardo_work_distribution_partitions_the_iterations(oracle):
+    """two workers, each walking the whole program but executing only its iterations (loop_manager.cpp:468-499):
+    the union of their puts is the single-worker result, and each worker ran about half of the block ops"""
+    segs = {"o": [2, 3], "v": [3, 4]}
+    arrays1 = make_arrays(oracle, segs)
+    Walker(Program(LCCD), OracleBackend(oracle, arrays1), segs).run()
+    arrays2 = make_arrays(oracle, segs)
+    calls, e = [], 0.0
+    for r in range(2):
+        be = OracleBackend(oracle, arrays2)
+        # the energy pardo reads T2new after the barrier: run the residual pardos on both ranks first
+        prog = Program(LCCD.split("proc energy")[0])
+        Walker(prog, be, segs, rank=r, world=2).run()
+        calls.append(be.calls)
+    for idx, b in arrays1["t2new_ab"].items():
+        assert np.max(np.abs(arrays2["t2new_ab"][idx] - b)) <= 1e-12
+    assert abs(calls[0] - calls[1]) <= 0.1 * max(calls) and min(calls) > 0
+
+
+def test_where_clause_and_iteration_counter(oracle):
+    text = """
+    moaindex i = baocc: eaocc
+    moaindex j = baocc: eaocc
+    served A[i,j]
+    temp T[i,j]
+    pardo i, j
+        where i <= j
+        T[i,j] = 1.0
+        put A[i,j] += T[i,j]
+    endpardo i, j
+    """
+    segs = {"o": [2, 2, 3], "v": [1]}
+    seen = []
+    for r in range(3):
+        arrays = {"a": {}}
+        Walker(Program(text), OracleBackend(oracle, arrays), segs, rank=r, world=3).run()
+        seen.append(sorted(arrays["a"]))
+    every = sorted(x for s in seen for x in s)
+    assert every == sorted((i, j) for i in (1, 2, 3) for j in (1, 2, 3) if i <= j)
+    # first index fastest, k-th where-true iteration -> worker k mod 3
+    order = [(i, j) for j in (1, 2, 3) for i in (1, 2, 3) if i <= j]
+    for r in range(3):
+        assert seen[r] == sorted(order[r::3])

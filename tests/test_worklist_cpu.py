@@ -170,6 +170,26 @@ def test_permute_accumulate_fusion_and_batching(sip):
     assert set(level) == {1}
 
 
+@pytest.mark.parametrize("head_assigns", [False, True])
+def test_chain_skips_commuting_accumulates_of_other_extents(sip, head_assigns):
+    """non-uniform contracted segments: D += A1*B1 (k=3); D += A2*B2 (k=5); D += A3*B3 (k=3).  The k=3 pair is one
+    chain, the k=5 accumulate commutes with it -- unless the head ASSIGNS, which must not be moved past an accumulate."""
+    v = 6
+    ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        D = sip.DeviceBlock((v, v))
+        ops = [(sip.DeviceBlock((v, k)), sip.DeviceBlock((k, v))) for k in (3, 5, 3)]
+        for n, (a, b) in enumerate(ops):
+            sip.contract(ptrn, a, b, (v, v), out=D, beta=0.0 if (n == 0 and head_assigns) else 1.0)
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    if head_assigns:
+        assert st["chains"] == 0 and level == [1, 2, 3]
+    else:
+        assert st["chains"] == 1 and st["chain_pairs"] == 2 and unit == [2, 1, 2] and level == [2, 1, 2]
+
+
 def test_pattern_error_surfaces_at_the_recording_call(sip):
     with sip.recording(dry=True):
         A, B, D = sip.DeviceBlock((4, 5)), sip.DeviceBlock((6, 4)), sip.DeviceBlock((4, 4))
