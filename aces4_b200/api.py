@@ -131,6 +131,17 @@ def lib():
         L.sipgpu_array_fill_local.argtypes = [C.c_void_p, C.c_double]
         L.sipgpu_array_local_bytes.argtypes = [C.c_void_p]
         L.sipgpu_array_local_bytes.restype = C.c_size_t
+        L.sipgpu_persist_scalar.argtypes = [C.c_char_p, C.c_double]
+        L.sipgpu_restore_scalar.argtypes = [C.c_char_p, c_dbl_p]
+        L.sipgpu_persist_contiguous.argtypes = [C.c_char_p, C.c_void_p, C.c_int, c_int_p]
+        L.sipgpu_restore_contiguous.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), c_int_p, c_int_p]
+        L.sipgpu_persist_array.argtypes = [C.c_char_p, C.c_void_p]
+        L.sipgpu_restore_array.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.sipgpu_persist_count.argtypes = [c_int_p, c_int_p, c_int_p]
+        L.sipgpu_persist_checkpoint.argtypes = [C.c_char_p]
+        L.sipgpu_persist_init_from_checkpoint.argtypes = [C.c_char_p]
+        L.sipgpu_array_save.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sipgpu_array_load.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.sipgpu_wl_begin.argtypes = [C.c_int]
         L.sipgpu_wl_set_limits.argtypes = [C.c_longlong, C.c_longlong]
         L.sipgpu_wl_stats.argtypes = [C.POINTER(C.c_longlong)]
@@ -609,6 +620,45 @@ def si_invert_diagonal(a1, a2):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Persistence (worker_persistent_array_manager.cpp:34-260): label registry + checkpoint file in the reference format
+# ----------------------------------------------------------------------------------------------------
+def persist_scalar(label, value):
+    _check(lib().sipgpu_persist_scalar(label.encode(), float(value)), "sipgpu_persist_scalar")
+
+
+def restore_scalar(label):
+    v = C.c_double(0)
+    _check(lib().sipgpu_restore_scalar(label.encode(), C.byref(v)), "sipgpu_restore_scalar")
+    return v.value
+
+
+def persist_contiguous(label, block):
+    """Ownership of the pool block moves to the registry (the DeviceBlock handle is disowned)."""
+    _check(lib().sipgpu_persist_contiguous(label.encode(), block.ptr, block.rank, _ia(block.shape)), "sipgpu_persist_contiguous")
+    block.owned = False
+
+
+def restore_contiguous(label):
+    p, rank, ext = C.c_void_p(0), C.c_int(0), (C.c_int * 6)()
+    _check(lib().sipgpu_restore_contiguous(label.encode(), C.byref(p), C.byref(rank), ext), "sipgpu_restore_contiguous")
+    return DeviceBlock(tuple(ext)[: rank.value], ptr=p.value, owned=True)
+
+
+def persist_counts():
+    a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    lib().sipgpu_persist_count(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def persist_checkpoint(path):
+    _check(lib().sipgpu_persist_checkpoint(str(path).encode()), "sipgpu_persist_checkpoint")
+
+
+def persist_init_from_checkpoint(path):
+    _check(lib().sipgpu_persist_init_from_checkpoint(str(path).encode()), "sipgpu_persist_init_from_checkpoint")
+
+
+# ----------------------------------------------------------------------------------------------------
 # Boundary 4: distributed arrays
 # ----------------------------------------------------------------------------------------------------
 def layout_block_number(nseg, idx):
@@ -694,6 +744,25 @@ class DistArray:
 
     def local_bytes(self):
         return int(lib().sipgpu_array_local_bytes(self.h))
+
+    def save(self, data_path, index_path):
+        _check(lib().sipgpu_array_save(self.h, str(data_path).encode(), str(index_path).encode()), "sipgpu_array_save")
+
+    def load(self, data_path, index_path):
+        _check(lib().sipgpu_array_load(self.h, str(data_path).encode(), str(index_path).encode()), "sipgpu_array_load")
+
+    def persist(self, label):
+        """set_persistent: the array object (and its HBM slab) moves to the label registry."""
+        _check(lib().sipgpu_persist_array(label.encode(), self.h), "sipgpu_persist_array")
+        self.h = None
+
+    def restore(self, label):
+        """restore_persistent into this (freshly declared, same-layout) array: adopts the persisted slab."""
+        h = C.c_void_p(0)
+        _check(lib().sipgpu_restore_array(label.encode(), C.byref(h)), "sipgpu_restore_array")
+        if self.h:
+            lib().sipgpu_array_destroy(self.h)
+        self.h = h
 
     def destroy(self):
         if self.h:

@@ -9,6 +9,7 @@
 // peer read, a put a peer write, and put += a red.global.add.f64 stream straight into the owner's HBM over
 // NVLink -- many writers are safe because the adds are atomic and commutative (the reference's arrival
 // order is non-deterministic too).  Section barriers are the caller's (stream sync + process barrier).
+#include <algorithm>
 #include <vector>
 
 #include "elementwise.h"
@@ -197,6 +198,100 @@ int sipgpu_array_fill_local(sipgpu_array* a, double v) {
     if (wl_active()) return wl_rec_ew(WL_FILL, a->base[a->my_rank], nullptr, nullptr, a->slab_elems[a->my_rank], v);
     return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
 }
+// ---- persistence of the rank's slab (array_file.h:53-70 structure; one file pair per rank instead of MPI-IO) ----
+// data file  : <int chunk_size = slab elements><int num_servers = world><double>*          (ArrayFile header_val_t = int)
+// index file : <offset DENSE_INDEX = 77><offset nblocks><offset per block number>*        (offset_val_t = long long)
+//              offset = byte position of the block in THIS rank's data file, -1 (ABSENT_BLOCK_OFFSET) for blocks of peers
+int sipgpu_array_save(sipgpu_array* a, const char* data_path, const char* index_path) {
+    if (!a || !data_path || !index_path) return SIPGPU_E_ARG;
+    SIP_TRY(wl_flush());
+    SIP_TRY(ensure_init());
+    const long long n = a->slab_elems[a->my_rank];
+    if (n > 0x7fffffffLL) {
+        set_error("array_save: slab of %lld elements exceeds the int header of the file format; save per block range", n);
+        return SIPGPU_E_ARG;
+    }
+    FILE* f = fopen(data_path, "wb");
+    if (!f) { set_error("array_save: cannot open %s", data_path); return SIPGPU_E_ARG; }
+    const int header[2] = {(int)n, a->world};
+    bool ok = fwrite(header, sizeof(int), 2, f) == 2;
+    void* h = nullptr;
+    const size_t stage = (size_t)32 << 20;
+    if (cudaMallocHost(&h, stage) != cudaSuccess) { fclose(f); return cuda_fail(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__); }
+    int rc = SIPGPU_OK;
+    for (long long off = 0; off < n && ok; off += (long long)(stage / 8)) {
+        const size_t cnt = (size_t)std::min<long long>(n - off, (long long)(stage / 8));
+        if (cudaMemcpyAsync(h, a->base[a->my_rank] + off, cnt * 8, cudaMemcpyDeviceToHost, ctx().stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx().stream) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "array_save d2h", __FILE__, __LINE__);
+            break;
+        }
+        ok = fwrite(h, 8, cnt, f) == cnt;
+    }
+    cudaFreeHost(h);
+    fclose(f);
+    if (rc != SIPGPU_OK) return rc;
+    FILE* fi = fopen(index_path, "wb");
+    if (!fi) { set_error("array_save: cannot open %s", index_path); return SIPGPU_E_ARG; }
+    std::vector<long long> index(2 + (size_t)a->nblocks, -1);
+    index[0] = 77;
+    index[1] = a->nblocks;
+    for (long long b = 0; b < a->nblocks; ++b)
+        if (b % a->world == a->my_rank) index[2 + b] = (long long)(2 * sizeof(int)) + 8 * a->block_off[b];
+    ok = ok && fwrite(index.data(), sizeof(long long), index.size(), fi) == index.size();
+    fclose(fi);
+    if (!ok) { set_error("array_save: short write"); return SIPGPU_E_ARG; }
+    return SIPGPU_OK;
+}
+int sipgpu_array_load(sipgpu_array* a, const char* data_path, const char* index_path) {
+    if (!a || !data_path || !index_path) return SIPGPU_E_ARG;
+    SIP_TRY(wl_flush());
+    SIP_TRY(ensure_init());
+    FILE* fi = fopen(index_path, "rb");
+    if (!fi) { set_error("array_load: cannot open %s", index_path); return SIPGPU_E_ARG; }
+    std::vector<long long> index(2 + (size_t)a->nblocks);
+    const bool iok = fread(index.data(), sizeof(long long), index.size(), fi) == index.size();
+    fclose(fi);
+    if (!iok || index[0] != 77 || index[1] != a->nblocks) {
+        set_error("array_load: index of %s does not describe this array (dense index of %lld blocks expected)", index_path, a->nblocks);
+        return SIPGPU_E_ARG;
+    }
+    for (long long b = 0; b < a->nblocks; ++b) {
+        const long long want = (b % a->world == a->my_rank) ? (long long)(2 * sizeof(int)) + 8 * a->block_off[b] : -1;
+        if (index[2 + b] != want) {
+            set_error("array_load: block %lld is at offset %lld in the file, this layout needs %lld (different segments or world size)",
+                      b, index[2 + b], want);
+            return SIPGPU_E_ARG;
+        }
+    }
+    FILE* f = fopen(data_path, "rb");
+    if (!f) { set_error("array_load: cannot open %s", data_path); return SIPGPU_E_ARG; }
+    int header[2] = {0, 0};
+    const long long n = a->slab_elems[a->my_rank];
+    if (fread(header, sizeof(int), 2, f) != 2 || header[0] != (int)n || header[1] != a->world) {  // array_file.cpp:183-190
+        fclose(f);
+        set_error("array_load: header of %s (chunk_size %d, servers %d) does not match this array (%lld, %d)", data_path, header[0],
+                  header[1], n, a->world);
+        return SIPGPU_E_ARG;
+    }
+    void* h = nullptr;
+    const size_t stage = (size_t)32 << 20;
+    if (cudaMallocHost(&h, stage) != cudaSuccess) { fclose(f); return cuda_fail(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__); }
+    int rc = SIPGPU_OK;
+    for (long long off = 0; off < n; off += (long long)(stage / 8)) {
+        const size_t cnt = (size_t)std::min<long long>(n - off, (long long)(stage / 8));
+        if (fread(h, 8, cnt, f) != cnt) { set_error("array_load: %s is truncated", data_path); rc = SIPGPU_E_ARG; break; }
+        if (cudaMemcpyAsync(a->base[a->my_rank] + off, h, cnt * 8, cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx().stream) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "array_load h2d", __FILE__, __LINE__);
+            break;
+        }
+    }
+    cudaFreeHost(h);
+    fclose(f);
+    return rc;
+}
+
 double* sipgpu_array_local_base(sipgpu_array* a) { return a ? a->base[a->my_rank] : nullptr; }
 size_t sipgpu_array_local_bytes(const sipgpu_array* a) {
     return a ? sizeof(double) * (size_t)a->slab_elems[a->my_rank] : 0;

@@ -488,11 +488,11 @@ int schedule_and_launch() {
         g.st_chain_pairs += (long long)ops[last].pairs.size();
     }
 
-    // ---- pass B2: `D = 0` (put_initialize / a fresh zeroed block) directly followed by an accumulating contraction
-    // into the whole of D is the assign form of that contraction: the fill and the read of D both disappear ----
+    // ---- pass B2: `D = 0` (put_initialize / a fresh zeroed block) directly followed by an accumulating contraction or
+    // permute into the whole of D is the assign form of that op: the fill and the read of D both disappear ----
     for (int i = 0; i < n; ++i) {
         Op& o = ops[i];
-        if (o.dead || o.kind != K_CONTRACT || o.beta != 1.0 || aliased(o.D)) continue;
+        if (o.dead || (o.kind != K_CONTRACT && o.kind != K_PERMUTE) || o.beta != 1.0 || aliased(o.D)) continue;
         const std::vector<Touch>& tl = touch[(uintptr_t)o.D];
         int prev = -1;
         for (const Touch& t : tl) {
@@ -735,6 +735,17 @@ int sipgpu_wl_begin(int flags) {
     g = State();
     g.on = true;
     g.dry = dry;
+    if (!dry) {  // temps whose free is deferred may take up to 40 % of what is free now (capped at 64 GiB)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t pool_res = 0, pool_use = 0;
+            sipgpu_pool_stats(&pool_res, &pool_use, nullptr);
+            const size_t avail = free_b + (pool_res - pool_use);
+            g.max_deferred_bytes = std::min<size_t>((size_t)64 << 30, std::max<size_t>((size_t)1 << 30, avail / 10 * 4));
+        } else {
+            cudaGetLastError();
+        }
+    }
     return SIPGPU_OK;
 }
 int sipgpu_wl_flush(void) { return wl_flush(); }

@@ -275,6 +275,30 @@ int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g
 int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* put_initialize on owned blocks  */
 size_t sipgpu_array_local_bytes(const sipgpu_array* a);
 double* sipgpu_array_local_base(sipgpu_array* a);   /* this rank's slab (its owned blocks, contiguous) */
+/* ---- persistence ----
+ * Label registry = WorkerPersistentArrayManager::set_persistent / restore_persistent
+ * (src/sip/dynamic_data/worker_persistent_array_manager.cpp:34-155): objects marked persistent at the end of one SIAL
+ * program are handed to the next by label; scalars by value, contiguous arrays (a pool block) and distributed arrays by
+ * ownership transfer, so they stay resident in HBM.  restore removes the label; a repeated label overwrites (the
+ * replaced object is released).  SIPGPU_E_STATE when the label is unknown. */
+int sipgpu_persist_scalar(const char* label, double value);
+int sipgpu_restore_scalar(const char* label, double* value);
+int sipgpu_persist_contiguous(const char* label, double* dev_block, int rank, const int* ext);
+int sipgpu_restore_contiguous(const char* label, double** dev_block, int* rank, int* ext6 /* MAX_RANK entries */);
+int sipgpu_persist_array(const char* label, sipgpu_array* a);
+int sipgpu_restore_array(const char* label, sipgpu_array** a);
+int sipgpu_persist_count(int* nscalars, int* ncontiguous, int* narrays);
+/* checkpoint_persistent / init_from_checkpoint (:157-260): scalars + contiguous arrays of the registry in the
+ * reference's own byte format (little-endian stream of setup/io_utils.cpp:44-70,114-155), so checkpoints are
+ * interchangeable with the reference worker's.  init requires an empty registry (the reference CHECKs the same). */
+int sipgpu_persist_checkpoint(const char* filename);
+int sipgpu_persist_init_from_checkpoint(const char* filename);
+/* server-side array files (src/sip/mpi/array_file.h:53-70): this rank's slab as <int chunk_size><int num_servers>
+ * <double>* plus a dense index file <77><nblocks><byte offset per block number, -1 for blocks of other ranks>.
+ * load validates header and index against the array's layout and world size. */
+int sipgpu_array_save(sipgpu_array* a, const char* data_path, const char* index_path);
+int sipgpu_array_load(sipgpu_array* a, const char* data_path, const char* index_path);
+
 /* host-only layout arithmetic (no device needed) */
 long long sipgpu_layout_block_number(int rank, const int* nseg, const int* idx);
 int sipgpu_layout_block_owner(long long block_number, int world);

@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_worklist.py tests/test_gpu_persist.py -x -q > gpurun_out/pytest_wl.log 2>&1; echo "pytest wl+persist rc=$?"; tail -15 gpurun_out/pytest_wl.log
+( cd scripts/micro && g++ -O2 -std=c++17 wl_pardo_bench.cpp -I../../include -L../../aces4_b200/lib -lsipgpu -Wl,-rpath,'$ORIGIN/../../aces4_b200/lib' -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64 -o wl_pardo_bench ) || echo "build failed"
+: > gpurun_out/wl_pardo_bench.jsonl
+for cfg in "16 3 16 6" "8 4 24 6" "32 2 32 4" "20 2 50 4" "20 3 50 6"; do
+  timeout 600 scripts/micro/wl_pardo_bench $cfg 3 >> gpurun_out/wl_pardo_bench.jsonl 2>> gpurun_out/wl_pardo_bench.err; echo "cfg $cfg rc=$?"
+done
+cat gpurun_out/wl_pardo_bench.jsonl | cut -c1-900; tail -3 gpurun_out/wl_pardo_bench.err
+timeout 1200 python scripts/sweep.py > gpurun_out/sweep.log 2>&1; echo "sweep rc=$?"; tail -30 gpurun_out/sweep.log

@@ -1,0 +1,96 @@
+"""GPU tests of persistence: label hand-off of resident arrays between SIAL programs, the worker
+checkpoint file in the reference's byte format, and the per-rank array files."""
+import struct
+
+import numpy as np
+import pytest
+
+from test_persist_cpu import ref_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sip():
+    import aces4_b200 as s
+
+    s.init(0)
+    return s.api
+
+
+def test_contiguous_handoff_keeps_the_block_resident(sip):
+    a = np.asfortranarray(np.arange(60.0).reshape(3, 4, 5))
+    blk = sip.DeviceBlock.from_numpy(a)
+    ptr = blk.ptr
+    sip.persist_contiguous("ca", blk)
+    assert sip.persist_counts()[1] == 1
+    back = sip.restore_contiguous("ca")
+    assert back.ptr == ptr and back.shape == (3, 4, 5)      # ownership transfer, no copy
+    assert np.array_equal(back.to_numpy(), a)
+    with pytest.raises(sip.SipGpuError):
+        sip.restore_contiguous("ca")
+
+
+def test_checkpoint_with_arrays_round_trip_and_reference_bytes(sip, tmp_path):
+    rng = np.random.default_rng(3)
+    fock = np.asfortranarray(rng.uniform(-1, 1, (13, 13)))
+    ca = np.asfortranarray(rng.uniform(-1, 1, (13, 5)))
+    sip.persist_scalar("scf_energy", -75.58432674274046)
+    sip.persist_contiguous("fock_a", sip.DeviceBlock.from_numpy(fock))
+    sip.persist_contiguous("ca", sip.DeviceBlock.from_numpy(ca))
+    path = tmp_path / "worker.ckpt"
+    sip.persist_checkpoint(path)
+    want = ref_checkpoint({"scf_energy": -75.58432674274046},
+                          [("fock_a", fock.shape, fock.ravel(order="F").tolist()), ("ca", ca.shape, ca.ravel(order="F").tolist())])
+    assert path.read_bytes() == want
+    for label in ("fock_a", "ca"):
+        sip.restore_contiguous(label).free()
+    sip.restore_scalar("scf_energy")
+    sip.persist_init_from_checkpoint(path)                 # a restart
+    got = sip.restore_contiguous("fock_a")
+    assert got.shape == (13, 13, 1, 1, 1, 1) and np.array_equal(got.to_numpy().reshape(13, 13, order="F"), fock)
+    got = sip.restore_contiguous("ca")
+    assert np.array_equal(got.to_numpy().reshape(13, 5, order="F"), ca)
+    assert sip.restore_scalar("scf_energy") == -75.58432674274046
+
+
+def test_distributed_array_label_handoff_and_files(sip, tmp_path):
+    segs = [[3, 4], [2, 2, 3], [3, 4], [2, 2, 3]]
+    A = sip.DistArray(segs)
+    rng = np.random.default_rng(9)
+    blocks = {}
+    for idx in np.ndindex(2, 3, 2, 3):
+        idx1 = tuple(i + 1 for i in idx)
+        b = np.asfortranarray(rng.uniform(-1, 1, A.block_shape(idx1)))
+        blocks[idx1] = b
+        A.put(idx1, sip.DeviceBlock.from_numpy(b))
+    sip.sync()
+    base = A.local_base()
+    A.save(tmp_path / "job.T2.1.parr", tmp_path / "job.T2.1.parr_index")
+    # file structure: <int chunk_size><int servers><doubles>, index <77><nblocks><offsets>
+    raw = (tmp_path / "job.T2.1.parr").read_bytes()
+    chunk, servers = struct.unpack("<ii", raw[:8])
+    assert servers == 1 and chunk * 8 == len(raw) - 8 == A.local_bytes()
+    index = np.frombuffer((tmp_path / "job.T2.1.parr_index").read_bytes(), dtype="<i8")
+    assert index[0] == 77 and index[1] == 36 and len(index) == 38
+    for idx1, b in blocks.items():
+        off = int(index[2 + A.block_number(idx1)])
+        got = np.frombuffer(raw[off: off + 8 * b.size], dtype="<f8")
+        assert np.array_equal(got, b.ravel(order="F"))
+    # set_persistent / restore_persistent: the slab is adopted by the next program's array, no copy
+    A.persist("T2_amplitudes")
+    B = sip.DistArray(segs)
+    B.restore("T2_amplitudes")
+    assert B.local_base() == base
+    for idx1, b in blocks.items():
+        assert np.array_equal(B.get(idx1).to_numpy(), b)
+    # restart from the files into a fresh array; a different layout is rejected
+    Cc = sip.DistArray(segs)
+    Cc.load(tmp_path / "job.T2.1.parr", tmp_path / "job.T2.1.parr_index")
+    for idx1, b in blocks.items():
+        assert np.array_equal(Cc.get(idx1).to_numpy(), b)
+    Dd = sip.DistArray([[3, 4], [2, 2, 3], [4, 3], [2, 2, 3]])
+    with pytest.raises(sip.SipGpuError):
+        Dd.load(tmp_path / "job.T2.1.parr", tmp_path / "job.T2.1.parr_index")
+    for X in (B, Cc, Dd):
+        X.destroy()
