@@ -144,6 +144,7 @@ def lib():
         L.sipgpu_array_load.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.sipgpu_wl_begin.argtypes = [C.c_int]
         L.sipgpu_wl_set_limits.argtypes = [C.c_longlong, C.c_longlong]
+        L.sipgpu_wl_set_idle_flush.argtypes = [C.c_longlong]
         L.sipgpu_wl_stats.argtypes = [C.POINTER(C.c_longlong)]
         L.sipgpu_wl_last_plan.argtypes = [C.c_int, c_int_p, c_int_p]
         _LIB = L

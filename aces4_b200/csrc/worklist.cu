@@ -85,6 +85,7 @@ struct State {
     size_t deferred_bytes = 0;
     size_t max_ops = 1 << 16;
     size_t max_deferred_bytes = (size_t)8 << 30;
+    size_t idle_flush_ops = 4096;  // flush early when the device has run dry and at least this many ops are pending
     uintptr_t fake_next = (uintptr_t)1 << 44;
     bool in_flush = false;
     // cumulative statistics since wl_begin
@@ -94,6 +95,10 @@ struct State {
     std::vector<int> last_level, last_unit;
 };
 State g;
+// defaults applied at every sipgpu_wl_begin (0 = built-in); the setters change them when called outside a recording and
+// only the open recording when called inside one
+size_t cfg_max_ops = 0, cfg_max_deferred = 0;
+long long cfg_idle = -1;
 
 // ---- disjoint interval map over device addresses: last write / read / atomic level per byte range ----
 struct Lv {
@@ -591,6 +596,14 @@ int push(Op&& o) {
     g.ops.push_back(std::move(o));
     g.st_recorded++;
     if (g.ops.size() >= g.max_ops || g.deferred_bytes >= g.max_deferred_bytes) return wl_flush();
+    // Overlap recording with execution: when the compute stream has drained, hand it what has been recorded so far
+    // instead of letting the device idle until the end of the pardo.  Batches therefore grow with the time the device
+    // needs for the previous one (large blocks -> large batches, small blocks -> frequent flushes).
+    if (!g.dry && g.idle_flush_ops && g.ops.size() >= g.idle_flush_ops && (g.ops.size() & 511) == 0) {
+        const cudaError_t q = cudaStreamQuery(ctx().stream);
+        if (q == cudaSuccess) return wl_flush();
+        if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+    }
     return SIPGPU_OK;
 }
 
@@ -735,6 +748,8 @@ int sipgpu_wl_begin(int flags) {
     g = State();
     g.on = true;
     g.dry = dry;
+    if (cfg_max_ops) g.max_ops = cfg_max_ops;
+    if (cfg_idle >= 0) g.idle_flush_ops = (size_t)cfg_idle;
     if (!dry) {  // temps whose free is deferred may take up to 40 % of what is free now (capped at 64 GiB)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -746,6 +761,7 @@ int sipgpu_wl_begin(int flags) {
             cudaGetLastError();
         }
     }
+    if (cfg_max_deferred) g.max_deferred_bytes = cfg_max_deferred;
     return SIPGPU_OK;
 }
 int sipgpu_wl_flush(void) { return wl_flush(); }
@@ -757,8 +773,13 @@ int sipgpu_wl_end(void) {
 }
 int sipgpu_wl_recording(void) { return g.on ? (g.dry ? 2 : 1) : 0; }
 int sipgpu_wl_set_limits(long long max_ops, long long max_deferred_bytes) {
-    if (max_ops > 0) g.max_ops = (size_t)max_ops;
-    if (max_deferred_bytes > 0) g.max_deferred_bytes = (size_t)max_deferred_bytes;
+    if (max_ops > 0) (g.on ? g.max_ops : cfg_max_ops) = (size_t)max_ops;
+    if (max_deferred_bytes > 0) (g.on ? g.max_deferred_bytes : cfg_max_deferred) = (size_t)max_deferred_bytes;
+    return SIPGPU_OK;
+}
+int sipgpu_wl_set_idle_flush(long long min_ops) {  // 0 disables the flush-when-the-device-is-idle policy
+    if (g.on) g.idle_flush_ops = min_ops > 0 ? (size_t)min_ops : 0;
+    else cfg_idle = min_ops > 0 ? min_ops : 0;
     return SIPGPU_OK;
 }
 int sipgpu_wl_stats(long long* out9) {

@@ -237,8 +237,12 @@ int sipgpu_wl_begin(int flags);
 int sipgpu_wl_flush(void);      /* schedule + launch what is recorded; recording continues */
 int sipgpu_wl_end(void);        /* flush and stop recording */
 int sipgpu_wl_recording(void);  /* 0 = off, 1 = recording, 2 = dry recording */
-/* automatic flush thresholds (0 = keep): recorded ops, bytes of temps whose free is deferred */
+/* automatic flush thresholds (0 = keep): recorded ops, bytes of temps whose free is deferred.  The three setters
+ * change the open recording when called inside one, the defaults of later recordings otherwise. */
 int sipgpu_wl_set_limits(long long max_ops, long long max_deferred_bytes);
+/* A recording is also flushed early whenever the compute stream has drained and at least min_ops ops are pending, so
+ * that the device works on batch k while the host records batch k+1 (default 4096; 0 = only flush at the limits). */
+int sipgpu_wl_set_idle_flush(long long min_ops);
 /* out9 = {ops recorded, ops scheduled, levels, kernel launches, temp->accumulate fusions, chains,
  *         operand pairs in chains, temps never written, flushes} since sipgpu_wl_begin */
 int sipgpu_wl_stats(long long* out9);
