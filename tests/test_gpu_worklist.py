@@ -227,3 +227,31 @@ def test_lccd_sial_program_device_vs_oracle(sip, oracle, segs):
         assert abs(e1 - e_ref) <= TOL * abs(e_ref)
     assert l1 * 4 < l0, (l0, l1)      # the recorded stream needs far fewer launches than op-at-a-time
     assert sum(s["chains"] for s in st) > 0 and sum(s["fused_accumulates"] for s in st) > 0
+
+
+@pytest.mark.parametrize("dat", ["lccd_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "lccd_frozencore_test.dat",
+                                 "eom_water_dimer_test.dat", "second_ccsdpt_test.dat"])
+def test_lccd_sial_program_at_the_shapes_of_the_shipped_inputs(sip, oracle, dat):
+    """configs 1-3 of BASELINE.json: the energies need the integral/SCF stack (not buildable here), but the
+    block SHAPES of those runs come from the .dat segment tables (tests/golden/dat_segments.json): the LCCD doubles
+    program at exactly those occupied/virtual segments, seeded inputs, device (recorded) vs oracle at 1e-10."""
+    import json
+
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+    from sial_oracle_backend import OracleBackend
+    from test_sial_frontend_cpu import KINDS, LCCD, make_arrays
+
+    g = json.load(open(os.path.join(HERE, "golden", "dat_segments.json")))[dat]
+    segs = {"o": g["occ"], "v": g["virt"]}
+    host = make_arrays(oracle, segs)
+    ref_arrays = {k: {i: b.copy() for i, b in v.items()} for k, v in host.items()}
+    be_o = OracleBackend(oracle, ref_arrays)
+    e_ref = be_o.value(Walker(Program(LCCD), be_o, segs).run()["ecorrab"])
+    arrays = device_arrays(sip, host, KINDS, segs)
+    be = DeviceBackend(sip, arrays, record=True)
+    e = be.value(Walker(Program(LCCD), be, segs).run()["ecorrab"])
+    for idx, want in ref_arrays["t2new_ab"].items():
+        assert rel(arrays["t2new_ab"].get(idx).to_numpy(), want) <= TOL
+    assert abs(e - e_ref) <= 1e-9 * max(1.0, abs(e_ref))      # north_star: 1e-9 on energies
+    for A in arrays.values():
+        A.destroy()
