@@ -133,14 +133,25 @@ int contract_device_sliced(const int* ptrn, const double* L, int lrank, const in
     ContractArgs a;
     memset(&a, 0, sizeof(a));
     SIP_TRY(build_shape_strided(ptrn, lrank, lext, lpar, rrank, rext, rpar, drank, dext, dpar, &a.s0));
+    // D is a single element (all free indices have extent 1 -- e.g. the DIIS matrix element
+    // BB[k1,k2] = E[a,i,b,j,k1]*E[a,i,b,j,k2] with simple indices k1, k2) and the contracted elements are one contiguous
+    // run in both operands: that is a dot product for the reduction kernels, not a 1x1 tile for the tensor cores
+    if (a.s0.M == 1 && a.s0.N == 1 && a.s0.nk == 1 && a.s0.ksL[0] == 1 && a.s0.ksR[0] == 1 && !lpar && !rpar) {
+        if (alpha != 1.0) {
+            SIP_TRY(ew_dot_device(L + ol, R + orr, a.s0.K, ctx().d_reduce + 1, 0.0));
+            return scaled_by_device_scalar(D + od, ctx().d_reduce + 1, 1, ctx().d_reduce + 2, alpha, beta);
+        }
+        return ew_dot_device(L + ol, R + orr, a.s0.K, D + od, beta);
+    }
+    if (a.s0.M < a.s0.N && a.s0.M <= 64) a.s0 = swap_operands(a.s0);  // the small free dimension goes to the n side
     a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
     if (contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) < ctx().num_sms) a.s0.tile = kSmallTile;  // spread a small block
     a.nprob = 1;
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
     a.beta = beta;
-    a.pair0.L = L + ol;
-    a.pair0.R = R + orr;
+    a.pair0.L = a.s0.swapped ? R + orr : L + ol;
+    a.pair0.R = a.s0.swapped ? L + ol : R + orr;
     a.p0.D = D + od;
     a.p0.chain_len = 1;
     const bool vec = a.s0.vec && (((uintptr_t)a.pair0.L | (uintptr_t)a.pair0.R) & 15) == 0;
@@ -168,6 +179,13 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
     std::vector<Shape> shapes;
     std::vector<int> pshape(n);
     for (int i = 0; i < n; ++i) {
+        // work-lists are long runs of identical extents: compare with the previous problem before touching the map
+        if (i > 0 && !memcmp(lext + (size_t)i * lrank, lext + (size_t)(i - 1) * lrank, sizeof(int) * lrank) &&
+            !memcmp(rext + (size_t)i * rrank, rext + (size_t)(i - 1) * rrank, sizeof(int) * rrank) &&
+            !memcmp(dext + (size_t)i * drank, dext + (size_t)(i - 1) * drank, sizeof(int) * drank)) {
+            pshape[i] = pshape[i - 1];
+            continue;
+        }
         std::vector<int> key(lext + (size_t)i * lrank, lext + (size_t)(i + 1) * lrank);
         key.insert(key.end(), rext + (size_t)i * rrank, rext + (size_t)(i + 1) * rrank);
         key.insert(key.end(), dext + (size_t)i * drank, dext + (size_t)(i + 1) * drank);
@@ -176,6 +194,7 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
             Shape s;
             SIP_TRY(build_shape(ptrn, lrank, lext + (size_t)i * lrank, rrank, rext + (size_t)i * rrank, drank,
                                 dext + (size_t)i * drank, &s));
+            if (s.M < s.N && s.M <= 64) s = swap_operands(s);
             s.tile = contract_pick_tile(s.M, s.N);
             it = shape_ids.emplace(key, (int)shapes.size()).first;
             shapes.push_back(s);
@@ -188,24 +207,47 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         if (total < ctx().num_sms)
             for (Shape& sh : shapes) sh.tile = kSmallTile;
     }
-    for (int variant = 0; variant < 24; ++variant) {
+    // single-element destinations with contiguous contracted runs are dot products (see contract_device_sliced)
+    // (short dots stay in the batched tensor-core launch: two reduction launches per block would be launch-bound)
+    auto is_dot = [&](const Shape& s) { return alpha == 1.0 && s.M == 1 && s.N == 1 && s.K >= 16384 && s.nk == 1 && s.ksL[0] == 1 && s.ksR[0] == 1; };
+    for (int i = 0; i < n; ++i) {
+        const Shape& s = shapes[pshape[i]];
+        if (!is_dot(s)) continue;
+        const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+        if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+        for (int c = c0; c < c1; ++c) {
+            if (!L[c] || !R[c]) return SIPGPU_E_ARG;
+            SIP_TRY(ew_dot_device(L[c], R[c], s.K, D[i], c == c0 ? beta : 1.0));
+        }
+    }
+    // kernel variant of every problem: (a_kc, b_kc, 16-byte loads, tile)
+    std::vector<int> pvariant(n, -1);
+    bool used[40] = {false};
+    for (int i = 0; i < n; ++i) {
+        const Shape& s = shapes[pshape[i]];
+        if (is_dot(s)) continue;
+        const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+        if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+        bool pvec = s.vec != 0;
+        for (int c = c0; c < c1 && pvec; ++c) pvec = (((uintptr_t)L[c] | (uintptr_t)R[c]) & 15) == 0;
+        pvariant[i] = (s.a_kc ? 1 : 0) | (s.b_kc ? 2 : 0) | (pvec ? 4 : 0) | (s.tile << 3);
+        used[pvariant[i]] = true;
+    }
+    for (int variant = 0; variant < 40; ++variant) {
+        if (!used[variant]) continue;
         const bool a_kc = variant & 1, b_kc = variant & 2, vec = variant & 4;
         const int tile = variant >> 3;
         std::vector<Problem> probs;
         std::vector<Pair> pairs;
         std::vector<int> prefix(1, 0);
         for (int i = 0; i < n; ++i) {
+            if (pvariant[i] != variant) continue;
             const Shape& s = shapes[pshape[i]];
-            if ((s.a_kc != 0) != a_kc || (s.b_kc != 0) != b_kc || s.tile != tile) continue;
             const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
-            if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
-            bool pvec = s.vec != 0;
-            for (int c = c0; c < c1 && pvec; ++c) pvec = (((uintptr_t)L[c] | (uintptr_t)R[c]) & 15) == 0;
-            if (pvec != vec) continue;
             probs.push_back(Problem{D[i], pshape[i], (int)pairs.size(), c1 - c0, 0});
             for (int c = c0; c < c1; ++c) {
                 if (!L[c] || !R[c]) return SIPGPU_E_ARG;
-                pairs.push_back(Pair{L[c], R[c]});
+                pairs.push_back(s.swapped ? Pair{R[c], L[c]} : Pair{L[c], R[c]});
             }
             prefix.push_back(prefix.back() + tiles_of(s));
         }

@@ -118,14 +118,16 @@ template <int WARPS_M_, int WARPS_N_, int MF_, int NF_, bool A_KC_, bool B_KC_, 
 struct Cfg {
     static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, MF = MF_, NF = NF_;
     static constexpr bool A_KC = A_KC_, B_KC = B_KC_, VEC = VEC_;
-    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = 16, STAGES = 4;
+    static constexpr int BM = WARPS_M * MF * 8, BN = WARPS_N * NF * 8, BK = 16;
+    // 4-stage ring; the narrow two-CTAs-per-SM tiles (128x56, 128x24) take 3 so that two CTAs fit the 227 KB of an SM
+    static constexpr int STAGES = (WARPS_M * WARPS_N == 4 && BN < 64) ? 3 : 4;
     static constexpr int NC = 32 * WARPS_M * WARPS_N;  // consumer threads
     static constexpr int NP = kProducerThreads;
     static constexpr int NT = NP + NC;
     static constexpr int KWIN = 2048;    // k offsets are tabulated for a window of this many contracted elements
     static constexpr int LDK = BK + 4;   // K-contiguous tile: [row][k]; stride = 4 mod 16 doubles -> conflict-free frags
-    static constexpr int LDAM = BM + 4;  // M-contiguous tile: [k][m]
-    static constexpr int LDBN = BN + 4;
+    static constexpr int LDAM = BM + (20 - BM % 16) % 16;  // M-contiguous tile: [k][m]; stride = 4 mod 16 as well
+    static constexpr int LDBN = BN + (20 - BN % 16) % 16;
     static constexpr int A_ELEMS = A_KC ? BM * LDK : BK * LDAM;
     static constexpr int B_ELEMS = B_KC ? BN * LDK : BK * LDBN;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
@@ -381,12 +383,15 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                     (([&] {
                          constexpr int mi = Q / NF, ni = Q % NF;
                          dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[BUF][mi], b[BUF][ni]);
-                         if constexpr (PREF && (Q % 2 == 1) && (Q / 2 < MF + NF))
-                             load_frag(st_next, kkn_c, std::integral_constant<int, 1 - BUF>{}, std::integral_constant<int, Q / 2>{});
+                         // one prefetch LDS after every second DMMA where the warp tile has enough DMMAs to carry
+                         // them (MF*NF/2 >= MF+NF), after every DMMA for the narrow tiles
+                         constexpr int EVERY = (MF * NF / 2 >= MF + NF) ? 2 : 1;
+                         if constexpr (PREF && (Q % EVERY == EVERY - 1) && (Q / EVERY < MF + NF))
+                             load_frag(st_next, kkn_c, std::integral_constant<int, 1 - BUF>{}, std::integral_constant<int, Q / EVERY>{});
                      }()),
                      ...);
                 }(std::make_integer_sequence<int, MF * NF>{});
-                static_assert(MF * NF / 2 >= MF + NF, "not enough DMMA slots to carry the next fragments");
+                static_assert(MF * NF >= MF + NF, "not enough DMMA slots to carry the next fragments");
             };
             using I0 = std::integral_constant<int, 0>;
             using I1 = std::integral_constant<int, 1>;
@@ -481,11 +486,15 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
 }  // namespace
 
 // Tile menu: 0 = 128x128 (8 consumer warps of 64x32), 1 = 128x80 (8 warps of 32x40: N = 400 = o*o segments tile
-// exactly), 2 = 64x64 (4 consumer warps of 32x32, two CTAs per SM): chosen by the launcher when a launch has fewer
-// large tiles than SMs (single small blocks -- the one-block-per-opcode calls of an unmodified interpreter)
+// exactly), 2 = 64x64 (4 consumer warps of 32x32, two CTAs per SM): launches with fewer large tiles than SMs (single
+// small blocks -- the one-block-per-opcode calls of an unmodified interpreter) and blocks with both free dimensions
+// <= 64, 3 = 128x56 and 4 = 128x24 (4 consumer warps of 32x56 / 32x24, two CTAs per SM so that the epilogue of one
+// overlaps the DMMAs of the other): the skinny contractions D[a,i,b,j] = L[a,i,c,j]*R[c,b]
+// with one segment-sized free dimension (v = 50, o = 20) -- 68 of the 170 SIAL patterns, HBM-bound, where padding
+// N = 50 to 80 or 128 would turn a bandwidth-bound op into a (wasted-)compute-bound one.
 void contract_tile_dims(int tile, int* bm, int* bn) {
     *bm = tile == 2 ? 64 : 128;
-    *bn = tile == 1 ? 80 : tile == 2 ? 64 : 128;
+    *bn = tile == 1 ? 80 : tile == 2 ? 64 : tile == 3 ? 56 : tile == 4 ? 24 : 128;
 }
 long long contract_tile_count(int M, int N, int tile) {
     int bm, bn;
@@ -493,13 +502,16 @@ long long contract_tile_count(int M, int N, int tile) {
     return (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn);
 }
 int contract_pick_tile(int M, int N) {
-    long long best = -1;
+    // padded work x a per-tile efficiency penalty (shared-memory fragment loads per DMMA, operand re-reads)
+    static const double penalty[5] = {1.0, 1.0, 1.15, 1.10, 1.25};
+    double best = -1.0;
     int pick = 0;
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 5; ++t) {
         int bm, bn;
         contract_tile_dims(t, &bm, &bn);
-        const long long padded = (long long)((M + bm - 1) / bm) * bm * (long long)((N + bn - 1) / bn) * bn;
-        if (best < 0 || padded < best) { best = padded; pick = t; }  // ties keep the larger tile (listed first)
+        if (t >= 3 && N > 64) continue;  // the narrow tiles are for ONE segment-sized n dimension
+        const double cost = (double)((M + bm - 1) / bm) * bm * (double)((N + bn - 1) / bn) * bn * penalty[t];
+        if (best < 0 || cost < best) { best = cost; pick = t; }  // ties keep the tile listed first
     }
     return pick;
 }
@@ -520,6 +532,8 @@ int launch_tile(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int ctas)
 
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile) {
     const int ctas = ctx().num_sms;
+    if (tile == 4) return launch_tile<4, 1, 4, 3>(a, a_kc, b_kc, vec, ctas);
+    if (tile == 3) return launch_tile<4, 1, 4, 7>(a, a_kc, b_kc, vec, ctas);
     if (tile == 2) return launch_tile<2, 2, 4, 4>(a, a_kc, b_kc, vec, ctas);
     if (tile == 1) return launch_tile<4, 2, 4, 5>(a, a_kc, b_kc, vec, ctas);
     return launch_tile<2, 4, 8, 4>(a, a_kc, b_kc, vec, ctas);

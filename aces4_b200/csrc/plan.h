@@ -23,6 +23,7 @@ struct Shape {
     int a_kc, b_kc;  // operand's stride-1 dimension is contracted (K-contiguous) vs free (M/N-contiguous)
     int vec;         // both operands may be fetched as 16-byte pairs along their contiguous direction
     int tile;        // CTA tile of the kernel menu (contract_pick_tile), set by the launcher
+    int swapped;     // the launcher exchanged the roles of L and R (small free dimension becomes n): pairs are {R, L}
 };
 
 // One destination block and the chain of (L, R) operand pairs summed into it:
@@ -52,6 +53,9 @@ int build_shape(const int* ptrn, int lrank, const int* lext, int rrank, const in
                 Shape* out);
 int build_shape_strided(const int* ptrn, int lrank, const int* lext, const int* lpar, int rrank, const int* rext,
                         const int* rpar, int drank, const int* dext, const int* dpar, Shape* out);
+// The same contraction with the roles of the operands exchanged: D'(n,m) = sum_k R'(k,n) L'(k,m).  Used to put the
+// SMALL free dimension on the n side, where the narrow tiles of the kernel menu live.
+Shape swap_operands(const Shape& s);
 bool contr_ptrn_ok(const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                    const int* dext);
 

@@ -33,6 +33,24 @@ elif mode == "small":
                                 [Ls[i % 8].ptr for i in range(nb)], [Rs[(i * 3) % 8].ptr for i in range(nb)], [d.ptr for d in Ds])
     for _ in range(3):
         bc.launch()
+elif mode in ("skinny", "outer"):
+    # skinny: D[a,i,b,j] = L[a,i,c,j]*R[c,b] (68 of the 170 SIAL patterns: one segment-sized free + contracted index)
+    # outer : D[a,b] = L[a,i,c,j]*R[b,i,c,j] (rank-2 result of two rank-4 blocks: K = 20000, M = N = 50)
+    v, o, nb = 50, 20, n
+    if mode == "skinny":
+        dl, ll, rl = [1, 2, 3, 4], [1, 2, 5, 4], [5, 3]
+        lsh, rsh, dsh = (v, o, v, o), (v, v), (v, o, v, o)
+    else:
+        dl, ll, rl = [1, 2], [1, 3, 4, 5], [2, 3, 4, 5]
+        lsh, rsh, dsh = (v, o, v, o), (v, o, v, o), (v, v)
+    Ls = [api.DeviceBlock(lsh).fill(0.5) for _ in range(min(nb, 128))]
+    Rs = [api.DeviceBlock(rsh).fill(0.25) for _ in range(min(nb, 128))]
+    Ds = [api.DeviceBlock(dsh) for _ in range(min(nb, 128))]
+    ptrn, _ = api.get_contraction_ptrn(dl, ll, rl)
+    bc = api.BatchedContraction(ptrn, [lsh] * nb, [rsh] * nb, [dsh] * nb, [Ls[i % len(Ls)].ptr for i in range(nb)],
+                                [Rs[i % len(Rs)].ptr for i in range(nb)], [Ds[i % len(Ds)].ptr for i in range(nb)])
+    for _ in range(3):
+        bc.launch()
 elif mode == "permute":
     shape = (64, 64, 64, 64) if n >= 64 else (50, 20, 50, 20)
     a, b = api.DeviceBlock(shape).fill(1.0), api.DeviceBlock(shape)
