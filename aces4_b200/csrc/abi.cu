@@ -12,6 +12,9 @@
 #include "worklist.h"
 
 namespace sipgpu {
+int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& pshape, const int* chain_start,
+                 const double* const* L, const double* const* R, double* const* D, double alpha, double beta);
+
 namespace {
 
 long long volume(int rank, const int* ext) {
@@ -146,6 +149,16 @@ int contract_device_sliced(const int* ptrn, const double* L, int lrank, const in
     if (a.s0.M < a.s0.N && a.s0.M <= 64) a.s0 = swap_operands(a.s0);  // the small free dimension goes to the n side
     a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
     if (contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) < ctx().num_sms) a.s0.tile = kSmallTile;  // spread a small block
+    // one small destination with a long contracted range: split-K through the work-list path (dense D only: the
+    // beta pre-pass of the split treats D as one contiguous run)
+    if (!dpar && contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) * 2 <= ctx().num_sms * 2 && a.s0.K >= 2 * 4096) {
+        std::vector<Shape> shapes(1, a.s0);
+        std::vector<int> pshape(1, 0);
+        const double* Lp = L + ol;
+        const double* Rp = R + orr;
+        double* Dp = D + od;
+        return run_worklist(1, shapes, pshape, nullptr, &Lp, &Rp, &Dp, alpha, beta);
+    }
     a.nprob = 1;
     a.total_tiles = tiles_of(a.s0);
     a.alpha = alpha;
@@ -201,11 +214,19 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         }
         pshape[i] = it->second;
     }
-    {   // a work-list that cannot fill the SMs with large tiles runs on 64x64 tiles (two CTAs per SM)
-        long long total = 0;
-        for (int i = 0; i < n; ++i) total += contract_tile_count(shapes[pshape[i]].M, shapes[pshape[i]].N, shapes[pshape[i]].tile);
-        if (total < ctx().num_sms)
-            for (Shape& sh : shapes) sh.tile = kSmallTile;
+    return run_worklist(n, shapes, pshape, chain_start, L, R, D, alpha, beta);
+}
+
+// The launch half of a work-list: tile choice for under-filled launches, split-K, dot routing, one launch per kernel
+// variant.  shapes[pshape[i]] is the Shape of problem i (operand roles already swapped where Shape::swapped).
+int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& pshape, const int* chain_start,
+                 const double* const* L, const double* const* R, double* const* D, double alpha, double beta) {
+    long long total = 0;
+    for (int i = 0; i < n; ++i) total += contract_tile_count(shapes[pshape[i]].M, shapes[pshape[i]].N, shapes[pshape[i]].tile);
+    if (total < ctx().num_sms) {  // a work-list that cannot fill the SMs with large tiles runs on 64x64 tiles (two CTAs per SM)
+        for (Shape& sh : shapes) sh.tile = kSmallTile;
+        total = 0;
+        for (int i = 0; i < n; ++i) total += contract_tile_count(shapes[pshape[i]].M, shapes[pshape[i]].N, kSmallTile);
     }
     // single-element destinations with contiguous contracted runs are dot products (see contract_device_sliced)
     // (short dots stay in the batched tensor-core launch: two reduction launches per block would be launch-bound)
@@ -219,6 +240,38 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
             if (!L[c] || !R[c]) return SIPGPU_E_ARG;
             SIP_TRY(ew_dot_device(L[c], R[c], s.K, D[i], c == c0 ? beta : 1.0));
         }
+    }
+    // ---- split-K: a launch that leaves most CTA slots idle while every tile walks a long contracted range (rank-2
+    // results of rank-4 blocks: D[a,b] = L[a,i,c,j]*R[b,i,c,j], K = o*v*o per pair and a chain of pairs on top) is cut
+    // along the chain and along the k windows into `split` partial problems per destination; the partial sums meet in
+    // D through red.global.add.f64 (beta is applied to D by one batched pre-pass) ----
+    const int slots = ctx().num_sms * 2;  // small / narrow tiles run two CTAs per SM
+    std::vector<int> split(n, 1);
+    bool any_split = false;
+    if (total > 0 && total * 2 <= slots) {
+        const int want = (int)std::min<long long>(16, slots / total);
+        for (int i = 0; i < n; ++i) {
+            const Shape& s = shapes[pshape[i]];
+            if (is_dot(s)) continue;
+            const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+            const long long nwin = (s.K + kContractKWin - 1) / kContractKWin;
+            // at least 4096 contracted elements per part, so that a part is worth a tile's prologue and epilogue
+            const long long parts = std::min<long long>((long long)(c1 - c0) * nwin, (long long)(c1 - c0) * s.K / 4096);
+            split[i] = (int)std::max<long long>(1, std::min<long long>(want, parts));
+            any_split = any_split || split[i] > 1;
+        }
+    }
+    if (any_split) {
+        std::vector<double*> dd;
+        std::vector<long long> cnt;
+        for (int i = 0; i < n; ++i) {
+            const Shape& s = shapes[pshape[i]];
+            if (is_dot(s) || !D[i]) continue;
+            dd.push_back(D[i]);
+            cnt.push_back((long long)s.M * s.N);
+        }
+        // dense destinations only (a sliced destination never comes here: see contract_device_sliced)
+        if (beta != 1.0) SIP_TRY(ew_scale_many((int)dd.size(), dd.data(), cnt.data(), beta));
     }
     // kernel variant of every problem: (a_kc, b_kc, 16-byte loads, tile)
     std::vector<int> pvariant(n, -1);
@@ -244,12 +297,31 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
             if (pvariant[i] != variant) continue;
             const Shape& s = shapes[pshape[i]];
             const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
-            probs.push_back(Problem{D[i], pshape[i], (int)pairs.size(), c1 - c0, 0});
+            const int first_pair = (int)pairs.size(), len = c1 - c0;
             for (int c = c0; c < c1; ++c) {
                 if (!L[c] || !R[c]) return SIPGPU_E_ARG;
                 pairs.push_back(s.swapped ? Pair{R[c], L[c]} : Pair{L[c], R[c]});
             }
-            prefix.push_back(prefix.back() + tiles_of(s));
+            const int S = split[i];
+            if (S <= 1) {
+                probs.push_back(Problem{D[i], pshape[i], first_pair, len, 0});
+                prefix.push_back(prefix.back() + tiles_of(s));
+            } else if (len >= S) {  // cut the chain: part q takes pairs [q*len/S, (q+1)*len/S), every k window
+                for (int q = 0; q < S; ++q) {
+                    const int p0 = (int)((long long)q * len / S), p1 = (int)((long long)(q + 1) * len / S);
+                    probs.push_back(Problem{D[i], pshape[i], first_pair + p0, p1 - p0, 0});
+                    prefix.push_back(prefix.back() + tiles_of(s));
+                }
+            } else {  // fewer pairs than parts: every pair is cut along its k windows
+                const int nwin = (s.K + kContractKWin - 1) / kContractKWin;
+                const int per_pair = std::min(nwin, std::max(1, S / len));
+                for (int c = 0; c < len; ++c)
+                    for (int q = 0; q < per_pair; ++q) {
+                        const int w0 = (int)((long long)q * nwin / per_pair), w1 = (int)((long long)(q + 1) * nwin / per_pair);
+                        probs.push_back(Problem{D[i], pshape[i], first_pair + c, 1, per_pair > 1 ? (w0 | (w1 << 16)) : 0});
+                        prefix.push_back(prefix.back() + tiles_of(s));
+                    }
+            }
         }
         if (probs.empty()) continue;
         auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -273,6 +345,7 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
         a.total_tiles = prefix.back();
         a.alpha = alpha;
         a.beta = beta;
+        a.atomic = any_split ? 1 : 0;
         SIP_TRY(launch_contract(a, a_kc, b_kc, vec, tile));
     }
     return SIPGPU_OK;

@@ -233,7 +233,10 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
             const int nk = sh->nk;
             const int nwin = (K + KWIN - 1) / KWIN;
             const int last_steps = (K - (nwin - 1) * KWIN + BK - 1) / BK;
-            const int steps_per_pair = (nwin - 1) * (KWIN / BK) + last_steps;
+            // split-K: this problem covers the k windows [w0, w1) only (Problem::kwin, 0 = all of them)
+            const int w0 = pr->kwin ? (pr->kwin & 0xffff) : 0, w1 = pr->kwin ? (pr->kwin >> 16) : nwin;
+            const bool has_tail = w1 == nwin;
+            const int steps_per_pair = (w1 - w0 - (has_tail ? 1 : 0)) * (KWIN / BK) + (has_tail ? last_steps : 0);
 
             // ---- offset tables: the input/output permutes of F90:731-743,782-785 as address arithmetic ----
             for (int i = tid; i < BM + BN; i += NP) {
@@ -256,7 +259,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 ti.D = pr->D;
                 ti.total_steps = chain_len * steps_per_pair;
                 ti.steps_per_pair = steps_per_pair;
-                ti.last_kk = (K - (nwin - 1) * KWIN - (last_steps - 1) * BK + 3) / 4;
+                ti.last_kk = has_tail ? (K - (nwin - 1) * KWIN - (last_steps - 1) * BK + 3) / 4 : BK / 4;
                 ti.pad = 0;
                 info[par] = ti;
             }
@@ -277,7 +280,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 }
                 producer_bar_sync();  // (also orders the m/n tables written above before their first use below)
             };
-            fill_ktable(0);
+            fill_ktable(w0);
             const int mo_fix = (C::A_KC || a_var >= C::A_PER) ? 0 : mOffL[a_fix];
             const int no_fix = (C::B_KC || b_var >= C::B_PER) ? 0 : nOffR[b_fix];
 
@@ -285,8 +288,8 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 const Pair pq = chain[c];
                 const double* __restrict__ Lp = pq.L;
                 const double* __restrict__ Rp = pq.R;
-                for (int win = 0; win < nwin; ++win) {
-                    if (nwin > 1) fill_ktable(win);
+                for (int win = w0; win < w1; ++win) {
+                    if (w1 - w0 > 1) fill_ktable(win);
                     const int steps = win == nwin - 1 ? last_steps : KWIN / BK;
                     for (int ks = 0; ks < steps; ++ks, ++ring) {
                         const int stage = ring % STAGES;
@@ -455,8 +458,12 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                         if ((mo | no) >= 0) {
                             double* dst = Dp + (size_t)(mo + no);
                             double v = alpha * acc[mi][ni][c];
-                            if (beta != 0.0) v += beta * *dst;
-                            *dst = v;
+                            if (args.atomic) {  // split-K / split-chain partial sums: the launcher has applied beta
+                                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+                            } else {
+                                if (beta != 0.0) v += beta * *dst;
+                                *dst = v;
+                            }
                         }
                     }
                 }

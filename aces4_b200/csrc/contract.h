@@ -12,6 +12,7 @@ struct ContractArgs {
     int nprob;
     int total_tiles;
     double alpha, beta;
+    int atomic;  // epilogue adds alpha*acc with red.global.add.f64 (several problems share a destination: split-K)
     Problem p0;
     Pair pair0;
     Shape s0;
@@ -24,6 +25,7 @@ void contract_tile_dims(int tile, int* bm, int* bn);
 int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int tile);
 int contract_pick_tile(int M, int N);
 long long contract_tile_count(int M, int N, int tile);
+constexpr int kContractKWin = 2048;  // contracted elements per k window (Cfg::KWIN)
 constexpr int kSmallTile = 2;  // 64x64, for launches that cannot fill the SMs with large tiles
 int dmma_probe(int iters, double* tflops);
 

@@ -18,6 +18,8 @@ int ew_insert(int rank, double* t, const int* t_ext, const double* s, const int*
 int ew_red_add(double* d, const double* s, long long n);
 int ew_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale);
 int ew_copy_probe(double* d, const double* s, long long n);
+// worklist.cu: d_i = beta * d_i for n blocks in ONE launch (beta = 0: zero fill)
+int ew_scale_many(int n, double* const* d, const long long* cnt, double beta);
 
 // permute.cu
 int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out);

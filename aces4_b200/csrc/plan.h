@@ -40,7 +40,7 @@ struct Problem {
     int shape;        // index into the launch's Shape array
     int chain_begin;  // first Pair of the chain
     int chain_len;
-    int pad;
+    int kwin;  // split-K: k windows [kwin & 0xffff, kwin >> 16) of contract.cu's KWIN-element windows; 0 = the whole K
 };
 
 // F90:87-142.  Returns the reference's ierr (0 ok, 1..6).

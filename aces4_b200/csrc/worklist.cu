@@ -287,6 +287,28 @@ int launch_ew_batch(const std::vector<const Op*>& list) {
     return SIPGPU_OK;
 }
 
+}  // namespace
+
+// d_i = beta * d_i for n blocks in one launch (beta = 0: zero fill) -- the beta pre-pass of split-K contractions
+int ew_scale_many(int n, double* const* d, const long long* cnt, double beta) {
+    std::vector<Op> ops((size_t)n);
+    std::vector<const Op*> list;
+    for (int i = 0; i < n; ++i) {
+        ops[i].kind = K_EW;
+        ops[i].ewop = beta == 0.0 ? WL_FILL : WL_SCALE;
+        ops[i].D = d[i];
+        ops[i].dn = cnt[i];
+        ops[i].f = beta;
+        list.push_back(&ops[i]);
+    }
+    const long long keep = g.st_launches;
+    const int rc = launch_ew_batch(list);
+    g.st_launches = keep;
+    return rc;
+}
+
+namespace {
+
 int launch_contract_group(const std::vector<const Op*>& list) {
     const Op& o0 = *list[0];
     std::vector<int> lext, rext, dext, chain(1, 0);

@@ -559,3 +559,46 @@ def test_full_size_properties(sip):
     Tp = sip.permute_labels([6, 1, 5, 2], [1, 2, 5, 6], dT)  # T'[k,a,c,i]
     Zp = sip.contract_labels([3, 1, 4, 2], [v, v, o, o], [6, 1, 5, 2], Tp, [5, 6, 3, 4], dV)
     assert relerr(Zp.to_numpy(), np.transpose(ref, (2, 0, 3, 1))) <= TOL
+
+
+@pytest.mark.parametrize("case", ["single_windows", "single_ragged", "chain_pairs", "chain_windows"])
+def test_split_k_partial_sums(sip, oracle, case):
+    """few small destinations with a long contracted range (D[a,b] = L[a,i,c,j]*R[b,i,c,j], the (2,4,4) SIAL patterns):
+    the launcher cuts the chain / the k windows into partial problems that meet in D through red.add (abi.cu
+    run_worklist); alpha and beta must come out exactly as in the unsplit op."""
+    rng = np.random.default_rng(17)
+    dl, ll, rl = [1, 2], [1, 3, 4, 5], [2, 3, 4, 5]
+    if case == "single_windows":
+        shp, ndest, npair = (12, 20, 50, 20), 1, 1          # K = 20000: 10 k windows
+    elif case == "single_ragged":
+        shp, ndest, npair = (9, 13, 50, 13), 1, 1           # K = 8450: 4 full windows + 258
+    elif case == "chain_pairs":
+        shp, ndest, npair = (10, 10, 50, 10), 3, 24         # K = 5000 per pair, 24 pairs per destination
+    else:
+        shp, ndest, npair = (10, 20, 50, 20), 2, 2          # 2 pairs x 10 windows
+    a = shp[0]
+    alpha, beta = -0.75, 0.5
+    Ls = [rng.uniform(-1, 1, shp) for _ in range(ndest * npair)]
+    Rs = [rng.uniform(-1, 1, shp) for _ in range(ndest * npair)]
+    D0 = [rng.uniform(-1, 1, (a, a)) for _ in range(ndest)]
+    want = []
+    for d in range(ndest):
+        acc = np.zeros((a, a), order="F")
+        for p in range(npair):
+            t, ierr = oracle.contract_labels(dl, [a, a], ll, Ls[d * npair + p], rl, Rs[d * npair + p])
+            assert ierr == 0
+            acc += t
+        want.append(alpha * acc + beta * D0[d])
+    dL = [sip.DeviceBlock.from_numpy(x) for x in Ls]
+    dR = [sip.DeviceBlock.from_numpy(x) for x in Rs]
+    dD = [sip.DeviceBlock.from_numpy(x) for x in D0]
+    ptrn, _ = sip.get_contraction_ptrn(dl, ll, rl)
+    if ndest == 1 and npair == 1:
+        sip.contract(ptrn, dL[0], dR[0], (a, a), out=dD[0], alpha=alpha, beta=beta)
+    else:
+        bc = sip.BatchedContraction(ptrn, [shp] * ndest, [shp] * ndest, [(a, a)] * ndest, [b.ptr for b in dL], [b.ptr for b in dR],
+                                    [b.ptr for b in dD], chain_start=[d * npair for d in range(ndest + 1)])
+        bc.launch(alpha=alpha, beta=beta)
+    for d in range(ndest):
+        got = dD[d].to_numpy()
+        assert np.max(np.abs(got - want[d])) <= 1e-10 * np.max(np.abs(want[d]))
