@@ -447,26 +447,48 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
             const int* mOffD = tabs + par * (2 * BM + 2 * BN) + BM;
             const int* nOffD = mOffD + BM + BN;
             double* __restrict__ Dp = info[par].D;
+            // all destination offsets first (independent LDS), then the stores: the address of a store never waits on a
+            // table load; alpha == 1 (every reference op) skips the FP64 multiply, which shares its pipe with DMMA
+            int mo[MF], no[NF][2];
 #pragma unroll
-            for (int mi = 0; mi < MF; ++mi) {
-                const int mo = mOffD[wm + mi * 8 + g];
+            for (int mi = 0; mi < MF; ++mi) mo[mi] = mOffD[wm + mi * 8 + g];
 #pragma unroll
-                for (int ni = 0; ni < NF; ++ni) {
+            for (int ni = 0; ni < NF; ++ni) {
+                no[ni][0] = nOffD[wn + ni * 8 + 2 * t4];
+                no[ni][1] = nOffD[wn + ni * 8 + 2 * t4 + 1];
+            }
+            const bool unit_alpha = alpha == 1.0;
+            if (args.atomic) {  // split-K / split-chain partial sums: the launcher has applied beta
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int no = nOffD[wn + ni * 8 + 2 * t4 + c];
-                        if ((mo | no) >= 0) {
-                            double* dst = Dp + (size_t)(mo + no);
-                            double v = alpha * acc[mi][ni][c];
-                            if (args.atomic) {  // split-K / split-chain partial sums: the launcher has applied beta
-                                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
-                            } else {
-                                if (beta != 0.0) v += beta * *dst;
-                                *dst = v;
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if ((mo[mi] | no[ni][c]) >= 0) {
+                                const double v = unit_alpha ? acc[mi][ni][c] : alpha * acc[mi][ni][c];
+                                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(Dp + (size_t)(mo[mi] + no[ni][c])), "d"(v) : "memory");
                             }
-                        }
-                    }
-                }
+            } else if (beta == 0.0) {
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if ((mo[mi] | no[ni][c]) >= 0)
+                                Dp[(size_t)(mo[mi] + no[ni][c])] = unit_alpha ? acc[mi][ni][c] : alpha * acc[mi][ni][c];
+            } else {
+#pragma unroll
+                for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NF; ++ni)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if ((mo[mi] | no[ni][c]) >= 0) {
+                                double* dst = Dp + (size_t)(mo[mi] + no[ni][c]);
+                                *dst = alpha * acc[mi][ni][c] + beta * *dst;
+                            }
             }
             __syncwarp();
             if (elect_one()) mbar_arrive(tab_empty + par);
