@@ -329,6 +329,35 @@ def main():
         api.lib().sipgpu_host_free(h_in)
         api.lib().sipgpu_host_free(h_out)
 
+    # ---- block traffic over NVLink ("NVLink GB/s for get/put"): every rank fetches / accumulates the blocks
+    # owned by its neighbour, outside the timed regions; GB/s per GPU, mean over ranks ----
+    nvlink = None
+    if world > 1:
+        peer_blocks = [b for b in w.blocks if w.T2old.owner(b) == (rank + 1) % world][:96]
+        nbytes_blk = 8.0 * int(np.prod(w.T2old.block_shape(peer_blocks[0])))
+        tmp_blocks = [api.DeviceBlock(w.T2old.block_shape(b)) for b in peer_blocks]
+
+        def do_get():
+            for b, t in zip(peer_blocks, tmp_blocks):
+                w.T2old.get(b, out=t)
+
+        def do_put_acc():
+            for b, t in zip(peer_blocks, tmp_blocks):
+                w.Xs.put_accumulate(b, t)
+
+        do_get()
+        ms_get, _ = timed(1, do_get)
+        for t in tmp_blocks:
+            t.fill(0.0)          # adds zeros: Xs is scratch that the next iteration overwrites anyway
+        do_put_acc()
+        ms_put, _ = timed(1, do_put_acc)
+        vol = len(peer_blocks) * nbytes_blk
+        nvlink = {"get_GBps_per_gpu": vol / (ms_get * 1e-3) / 1e9, "put_accumulate_GBps_per_gpu": vol / (ms_put * 1e-3) / 1e9,
+                  "blocks": len(peer_blocks), "block_bytes": nbytes_blk,
+                  "how": "peer reads (cudaMemcpyAsync from the owner's IPC-mapped slab) / red.global.add.f64 into the owner's "
+                         "slab, all ranks concurrently towards rank+1, max over ranks of the elapsed time"}
+        del tmp_blocks
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
@@ -368,6 +397,7 @@ def main():
                          "traffic_source": "profiles/r01_traffic_ccsd_full.json (ncu dram__bytes_read+write of the dominant "
                                            "launch, the pp-ladder chain; bytes per launch per GPU)" if traffic else None},
             "cpu_baseline": cpu,
+            "nvlink": nvlink,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
