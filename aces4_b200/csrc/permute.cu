@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(kPT, (EPT <= 4 ? 4 : EPT <= 8 ? 3 : 2) - (RAG 
         else return tid + u * kPT < a.V;
     };
     const long long total = a.ntiles * b.n;
-    for (long long work = blockIdx.x; work < total; work += gridDim.x) {
+    // (block, tile) work item -> source / destination base and the ragged limits of the tile
+    auto decode = [&](long long work, const double*& src, double*& dst, int& lim0, int& lim1) {
         const int blk = (int)(work / a.ntiles);
         long long t = work - (long long)blk * a.ntiles;
-        int bin = 0, bout = 0, lim0 = kNoLimit, lim1 = kNoLimit;
+        int bin = 0, bout = 0;
+        lim0 = lim1 = kNoLimit;
 #pragma unroll 1
         for (int d = 0; d < a.rank; ++d) {
             const int c = (int)(t % a.ntile[d]);
@@ -97,37 +99,57 @@ __global__ void __launch_bounds__(kPT, (EPT <= 4 ? 4 : EPT <= 8 ? 3 : 2) - (RAG 
                 if (d == a.rag_dim[1]) lim1 = min(a.rag_te[1], a.rag_ext[1] - c * a.rag_te[1]);
             }
         }
-        const double* __restrict__ src = (b.in ? b.in[blk] : b.in0) + bin;
-        double* __restrict__ dst = (b.in ? b.out[blk] : b.out0) + bout;
-        double v[EPT];
+        src = (b.in ? b.in[blk] : b.in0) + bin;
+        dst = (b.in ? b.out[blk] : b.out0) + bout;
+    };
+    // Software pipeline over the persistent tile loop: the loads of tile t+1 are issued BEFORE the stores of tile t (the
+    // registers v[] are free as soon as tile t is parked in shared memory), so every CTA always has a tile's worth of
+    // loads in flight while it writes -- the load -> barrier -> store -> barrier sequence no longer serialises them.
+    long long work = blockIdx.x;
+    const double* src = nullptr;
+    double* dst = nullptr;
+    int lim0 = kNoLimit, lim1 = kNoLimit;
+    double v[EPT];
+    if (work < total) {
+        decode(work, src, dst, lim0, lim1);
 #pragma unroll
-        for (int u = 0; u < EPT; ++u) {
-            const bool ok = r_ok(u, lim0, lim1);
-            if (ok) v[u] = __ldg(src + r_off[u]);
-        }
+        for (int u = 0; u < EPT; ++u)
+            if (r_ok(u, lim0, lim1)) v[u] = __ldg(src + r_off[u]);
+    }
+    while (work < total) {
 #pragma unroll
         for (int u = 0; u < EPT; ++u) sm[skew(tid + u * kPT)] = v[u];
         __syncthreads();
+        double* __restrict__ cdst = dst;
+        const int clim0 = lim0, clim1 = lim1;
+        const long long next = work + gridDim.x;
+        if (next < total) {
+            decode(next, src, dst, lim0, lim1);
+#pragma unroll
+            for (int u = 0; u < EPT; ++u)
+                if (r_ok(u, lim0, lim1)) v[u] = __ldg(src + r_off[u]);
+        }
         if (ACC) {
             double o[EPT];
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
-                const bool ok = w_ok(u, lim0, lim1);
-                if (ok) o[u] = dst[w_off[u]];
+                const bool ok = w_ok(u, clim0, clim1);
+                if (ok) o[u] = cdst[w_off[u]];
             }
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
-                const bool ok = w_ok(u, lim0, lim1);
-                if (ok) dst[w_off[u]] = b.alpha * sm[w_pos[u]] + b.beta * o[u];
+                const bool ok = w_ok(u, clim0, clim1);
+                if (ok) cdst[w_off[u]] = b.alpha * sm[w_pos[u]] + b.beta * o[u];
             }
         } else {
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
-                const bool ok = w_ok(u, lim0, lim1);
-                if (ok) dst[w_off[u]] = sm[w_pos[u]];
+                const bool ok = w_ok(u, clim0, clim1);
+                if (ok) cdst[w_off[u]] = sm[w_pos[u]];
             }
         }
         __syncthreads();
+        work = next;
     }
 }
 
