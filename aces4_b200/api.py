@@ -142,6 +142,12 @@ def lib():
         L.sipgpu_persist_init_from_checkpoint.argtypes = [C.c_char_p]
         L.sipgpu_array_save.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.sipgpu_array_load.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sipgpu_array_track_accesses.argtypes = [C.c_void_p, C.c_int]
+        L.sipgpu_array_section_accesses.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong), c_int_p]
+        L.sipgpu_array_section_accesses.restype = C.c_longlong
+        L.sipgpu_array_section_reset.argtypes = [C.c_void_p]
+        L.sipgpu_consistency_validate.argtypes = [C.c_longlong, C.POINTER(C.c_longlong), c_int_p, c_int_p,
+                                                  C.POINTER(C.c_longlong)]
         L.sipgpu_wl_begin.argtypes = [C.c_int]
         L.sipgpu_wl_set_limits.argtypes = [C.c_longlong, C.c_longlong]
         L.sipgpu_wl_set_idle_flush.argtypes = [C.c_longlong]
@@ -662,6 +668,22 @@ def persist_init_from_checkpoint(path):
 # ----------------------------------------------------------------------------------------------------
 # Boundary 4: distributed arrays
 # ----------------------------------------------------------------------------------------------------
+ACCESS_GET, ACCESS_PUT, ACCESS_PUT_ACCUMULATE = 1, 2, 4
+
+
+def consistency_validate(entries):
+    """entries: [(block number, access bits, worker)] of one barrier section, all ranks.  Raises SipGpuError(E_STATE)
+    on an inconsistent block (distributed_block_consistency.cpp); host-only."""
+    n = len(entries)
+    b = (C.c_longlong * max(1, n))(*[int(e[0]) for e in entries])
+    f = (C.c_int * max(1, n))(*[int(e[1]) for e in entries])
+    w = (C.c_int * max(1, n))(*[int(e[2]) for e in entries])
+    bad = C.c_longlong(-1)
+    rc = lib().sipgpu_consistency_validate(n, b, f, w, C.byref(bad))
+    if rc != 0:
+        raise SipGpuError(f"inconsistent block {bad.value}: " + lib().sipgpu_last_error().decode(errors="replace"))
+
+
 def layout_block_number(nseg, idx):
     """array_table.cpp:75-81 (LAST index fastest, segments 1-based); host-only."""
     return int(lib().sipgpu_layout_block_number(len(nseg), _ia(nseg), _ia(idx)))
@@ -745,6 +767,19 @@ class DistArray:
 
     def local_bytes(self):
         return int(lib().sipgpu_array_local_bytes(self.h))
+
+    def track_accesses(self, on=True):
+        _check(lib().sipgpu_array_track_accesses(self.h, 1 if on else 0), "sipgpu_array_track_accesses")
+
+    def section_accesses(self):
+        """[(block number, access bits)] of what this rank did since the last barrier"""
+        n = lib().sipgpu_array_section_accesses(self.h, 0, None, None)
+        b, f = (C.c_longlong * max(1, n))(), (C.c_int * max(1, n))()
+        lib().sipgpu_array_section_accesses(self.h, n, b, f)
+        return list(zip(list(b)[:n], list(f)[:n]))
+
+    def section_reset(self):
+        _check(lib().sipgpu_array_section_reset(self.h), "sipgpu_array_section_reset")
 
     def save(self, data_path, index_path):
         _check(lib().sipgpu_array_save(self.h, str(data_path).encode(), str(index_path).encode()), "sipgpu_array_save")

@@ -10,6 +10,8 @@
 // NVLink -- many writers are safe because the adds are atomic and commutative (the reference's arrival
 // order is non-deterministic too).  Section barriers are the caller's (stream sync + process barrier).
 #include <algorithm>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 #include "elementwise.h"
@@ -26,6 +28,9 @@ struct sipgpu_array {
     std::vector<long long> slab_elems;  // per owner
     std::vector<double*> base;          // per owner: slab base as mapped into this process
     std::vector<char> opened;           // base[r] came from cudaIpcOpenMemHandle
+    // race detection (distributed_block_consistency.cpp): what THIS rank did to which block since the last barrier
+    bool track = false;
+    std::unordered_map<long long, int> touched;  // block number -> SIPGPU_ACCESS_* bits
 };
 
 using namespace sipgpu;
@@ -173,6 +178,7 @@ double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx) {
 int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
     double* src = sipgpu_array_block_ptr(a, idx);
     if (!src || !g_dst) return src ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_GET;
     const long long n = sipgpu_array_block_size(a, idx);
     if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, g_dst, src, nullptr, n, 1.0);  // peer loads inside the batched kernel
     // peer read over NVLink when the owner is remote (UVA resolves the direction)
@@ -182,6 +188,7 @@ int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
 int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
     const long long n = sipgpu_array_block_size(a, idx);
     if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, dst, g_src, nullptr, n, 1.0);
     SIP_CUDA(cudaMemcpyAsync(dst, g_src, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx().stream));
@@ -190,6 +197,7 @@ int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src) {
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT_ACCUMULATE;
     if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0, a->world == 1);
     return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
 }
@@ -198,6 +206,58 @@ int sipgpu_array_fill_local(sipgpu_array* a, double v) {
     if (wl_active()) return wl_rec_ew(WL_FILL, a->base[a->my_rank], nullptr, nullptr, a->slab_elems[a->my_rank], v);
     return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
 }
+// ---- race detection between barriers (distributed_block_consistency.cpp:25-175) ----
+// The reference checks every get / put / put += at the block's server against a state table.  Read as a whole, the
+// table accepts the accesses of one barrier section to one block iff  (a) a single worker made all of them, or
+// (b) all of them are GETs, or (c) all of them are PUT_ACCUMULATEs  -- the order inside a section does not matter.
+// Without servers the check is made at the barrier instead: every rank hands over what it touched
+// (sipgpu_array_section_accesses), the summaries are exchanged by the caller's barrier, and each rank validates the
+// union with sipgpu_consistency_validate (host-only arithmetic).
+int sipgpu_array_track_accesses(sipgpu_array* a, int on) {
+    if (!a) return SIPGPU_E_ARG;
+    a->track = on != 0;
+    a->touched.clear();
+    return SIPGPU_OK;
+}
+long long sipgpu_array_section_accesses(sipgpu_array* a, long long cap, long long* block_numbers, int* access_bits) {
+    if (!a) return -1;
+    std::map<long long, int> sorted(a->touched.begin(), a->touched.end());
+    long long k = 0;
+    for (const auto& kv : sorted) {
+        if (k < cap && block_numbers && access_bits) { block_numbers[k] = kv.first; access_bits[k] = kv.second; }
+        ++k;
+    }
+    return k;
+}
+int sipgpu_array_section_reset(sipgpu_array* a) {
+    if (!a) return SIPGPU_E_ARG;
+    a->touched.clear();  // sip_barrier: DistributedBlockConsistency::reset_consistency_status
+    return SIPGPU_OK;
+}
+int sipgpu_consistency_validate(long long n, const long long* block_numbers, const int* access_bits, const int* workers,
+                                long long* bad_block) {
+    if (n < 0 || (n && (!block_numbers || !access_bits || !workers))) return SIPGPU_E_ARG;
+    struct Agg { int bits = 0, worker = -1; bool multiple = false; };
+    std::map<long long, Agg> agg;
+    for (long long i = 0; i < n; ++i) {
+        if (access_bits[i] == 0) continue;
+        Agg& g = agg[block_numbers[i]];
+        g.bits |= access_bits[i];
+        if (g.worker >= 0 && g.worker != workers[i]) g.multiple = true;
+        g.worker = workers[i];
+    }
+    for (const auto& kv : agg) {
+        const Agg& g = kv.second;
+        if (g.multiple && g.bits != SIPGPU_ACCESS_GET && g.bits != SIPGPU_ACCESS_PUT_ACCUMULATE) {
+            if (bad_block) *bad_block = kv.first;
+            set_error("inconsistent block %lld: accessed by several workers between two barriers with access bits %d "
+                      "(only all-GET or all-PUT_ACCUMULATE may be shared)", kv.first, g.bits);
+            return SIPGPU_E_STATE;
+        }
+    }
+    return SIPGPU_OK;
+}
+
 // ---- persistence of the rank's slab (array_file.h:53-70 structure; one file pair per rank instead of MPI-IO) ----
 // data file  : <int chunk_size = slab elements><int num_servers = world><double>*          (ArrayFile header_val_t = int)
 // index file : <offset DENSE_INDEX = 77><offset nblocks><offset per block number>*        (offset_val_t = long long)

@@ -279,6 +279,21 @@ int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g
 int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* put_initialize on owned blocks  */
 size_t sipgpu_array_local_bytes(const sipgpu_array* a);
 double* sipgpu_array_local_base(sipgpu_array* a);   /* this rank's slab (its owned blocks, contiguous) */
+/* ---- race detection between barriers (src/sip/dynamic_data/distributed_block_consistency.cpp:25-175) ----
+ * The reference's server checks every get / put / put += against a per-block state table; read as a whole the table
+ * accepts the accesses of one barrier section to one block iff one worker made all of them, or all are GETs, or all
+ * are PUT_ACCUMULATEs.  Here every rank records what it touched (when tracking is on), the caller's sip_barrier
+ * exchanges the summaries, and each rank validates the union (host-only).  SIPGPU_E_STATE = inconsistent block. */
+#define SIPGPU_ACCESS_GET 1
+#define SIPGPU_ACCESS_PUT 2
+#define SIPGPU_ACCESS_PUT_ACCUMULATE 4
+int sipgpu_array_track_accesses(sipgpu_array* a, int on);
+/* blocks this rank touched since the last reset, ascending block number; returns their count (call with cap 0 first) */
+long long sipgpu_array_section_accesses(sipgpu_array* a, long long cap, long long* block_numbers, int* access_bits);
+int sipgpu_array_section_reset(sipgpu_array* a);   /* at sip_barrier (reset_consistency_status) */
+int sipgpu_consistency_validate(long long n, const long long* block_numbers, const int* access_bits, const int* workers,
+                                long long* bad_block);
+
 /* ---- persistence ----
  * Label registry = WorkerPersistentArrayManager::set_persistent / restore_persistent
  * (src/sip/dynamic_data/worker_persistent_array_manager.cpp:34-155): objects marked persistent at the end of one SIAL

@@ -244,3 +244,10 @@ def si_return_sval(block):
 
 def si_invert_diagonal(a1, a2):
     return lib().oracle_si_invert_diagonal(a1.ndim, a2.ndim, _ia(a1.shape), _dp(a1), _dp(a2))
+
+
+def block_consistency(ops, workers, sections):
+    """distributed_block_consistency.cpp:25-175 for ONE block: index of the first illegal operation, or -1."""
+    n = len(ops)
+    lib().oracle_block_consistency.restype = C.c_longlong
+    return int(lib().oracle_block_consistency(C.c_longlong(n), _ia(ops), _ia(workers), _ia(sections)))

@@ -482,3 +482,60 @@ void oracle_fill_hash(double* d, long long n, unsigned long long seed, unsigned 
         d[i] = scale * u;
     }
 }
+
+/* ---- distributed-block consistency (race detection at the block's owner):
+ * DistributedBlockConsistency::update_and_check_consistency, src/sip/dynamic_data/distributed_block_consistency.cpp:
+ * 25-175.  One block; ops[i] in {0 GET, 1 PUT, 2 PUT_ACCUMULATE} issued by workers[i] in barrier section sections[i]
+ * (non-decreasing).  Follows the reference's state table row by row (states NONE, READ, WRITE, ACCUMULATE,
+ * SINGLE_WORKER x worker in {OPEN, a worker, MULTIPLE}); returns the index of the first operation that makes the
+ * block inconsistent, or -1 if the whole sequence is legal. ---- */
+long long oracle_block_consistency(long long n, const int* ops, const int* workers, const int* sections) {
+    enum { M_NONE, M_READ, M_WRITE, M_ACC, M_SINGLE };
+    enum { W_OPEN = -1, W_MULTIPLE = -2 };
+    enum { GET = 0, PUT = 1, PUT_ACC = 2 };
+    int mode = M_NONE, prev = W_OPEN, last_section = 0;
+    for (long long i = 0; i < n; ++i) {
+        const int op = ops[i], w = workers[i];
+        if (sections[i] > last_section) { last_section = sections[i]; mode = M_NONE; prev = W_OPEN; }  /* :25-38 */
+        int nm = -1, nw = 0;
+        switch (mode) {
+        case M_NONE:                                                    /* NO: Rw Ww Aw */
+            if (prev != W_OPEN) return i;
+            nm = op == GET ? M_READ : op == PUT ? M_WRITE : M_ACC; nw = w;
+            break;
+        case M_READ:
+            if (prev == W_OPEN) return i;
+            if (prev == W_MULTIPLE) {                                   /* RM: RM X X */
+                if (op != GET) return i;
+                nm = M_READ; nw = W_MULTIPLE;
+            } else if (op == GET) {                                     /* Rw: Rw | RM */
+                nm = M_READ; nw = (w == prev) ? w : W_MULTIPLE;
+            } else {                                                    /* Rw: Sw for the same worker, X otherwise */
+                if (w != prev) return i;
+                nm = M_SINGLE; nw = w;
+            }
+            break;
+        case M_WRITE:                                                   /* Ww: Sw Sw Sw | X X X */
+            if (w != prev) return i;
+            nm = M_SINGLE; nw = w;
+            break;
+        case M_ACC:
+            if (prev == W_OPEN) return i;
+            if (prev == W_MULTIPLE) {                                   /* AM: X X AM */
+                if (op != PUT_ACC) return i;
+                nm = M_ACC; nw = W_MULTIPLE;
+            } else if (op == PUT_ACC) {                                 /* Aw: Aw | AM */
+                nm = M_ACC; nw = (w == prev) ? w : W_MULTIPLE;
+            } else {                                                    /* Aw: Sw for the same worker, X otherwise */
+                if (w != prev) return i;
+                nm = M_SINGLE; nw = w;
+            }
+            break;
+        default:                                                        /* Sw: Sw Sw Sw | X X X */
+            if (w != prev) return i;
+            nm = M_SINGLE; nw = w;
+        }
+        mode = nm; prev = nw;
+    }
+    return -1;
+}

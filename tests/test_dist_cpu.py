@@ -66,6 +66,21 @@ def _worker(rank, world, port, q):
         m = torch.tensor([10.0 + rank], dtype=torch.float64)
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
         assert m.item() == 10.0 + world - 1
+        # sip_barrier with race detection: every rank contributes what it touched in the section; all ranks validate the
+        # union (distributed_block_consistency.cpp rules).  Section 1: put += from both ranks into the same blocks and
+        # disjoint puts -> legal.  Section 2: rank 0 puts block 5, rank 1 gets it without a barrier -> inconsistent.
+        def barrier_validate(mine):
+            out = [None] * world
+            dist.all_gather_object(out, mine)
+            api.consistency_validate([(b, bits, r) for r, ent in enumerate(out) for b, bits in ent])
+
+        barrier_validate([(b, api.ACCESS_PUT_ACCUMULATE) for b in range(8)] + [(100 + rank, api.ACCESS_PUT)])
+        try:
+            barrier_validate([(5, api.ACCESS_PUT if rank == 0 else api.ACCESS_GET)])
+            raced = False
+        except api.SipGpuError:
+            raced = True
+        assert raced
         dist.barrier()
         q.put((rank, len(blocks)))
     finally:

@@ -94,3 +94,26 @@ def test_distributed_array_label_handoff_and_files(sip, tmp_path):
         Dd.load(tmp_path / "job.T2.1.parr", tmp_path / "job.T2.1.parr_index")
     for X in (B, Cc, Dd):
         X.destroy()
+
+
+def test_access_tracking_feeds_the_race_detector(sip):
+    """get / put / put += record what this rank touched between barriers (dist.cu); the summary goes through
+    sipgpu_consistency_validate together with a simulated second worker's summary."""
+    A = sip.DistArray([[2, 3], [2, 3]])
+    A.track_accesses(True)
+    blk = sip.DeviceBlock(A.block_shape((1, 2))).fill(1.0)
+    A.put_accumulate((1, 2), blk)
+    A.put_accumulate((1, 2), blk)
+    g = A.get((2, 1))
+    A.put((2, 2), sip.DeviceBlock(A.block_shape((2, 2))).fill(3.0))
+    mine = A.section_accesses()
+    n12, n21, n22 = A.block_number((1, 2)), A.block_number((2, 1)), A.block_number((2, 2))
+    assert sorted(mine) == sorted([(n12, sip.ACCESS_PUT_ACCUMULATE), (n21, sip.ACCESS_GET), (n22, sip.ACCESS_PUT)])
+    other_ok = [(n12, sip.ACCESS_PUT_ACCUMULATE, 1), (n21, sip.ACCESS_GET, 1)]
+    sip.consistency_validate([(b, f, 0) for b, f in mine] + other_ok)
+    with pytest.raises(sip.SipGpuError):
+        sip.consistency_validate([(b, f, 0) for b, f in mine] + [(n22, sip.ACCESS_GET, 1)])
+    A.section_reset()
+    assert A.section_accesses() == []
+    assert np.all(A.get((1, 2)).to_numpy() == 2.0) and g.shape == A.block_shape((2, 1))
+    A.destroy()
