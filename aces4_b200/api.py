@@ -148,6 +148,16 @@ def lib():
         L.sipgpu_array_section_reset.argtypes = [C.c_void_p]
         L.sipgpu_consistency_validate.argtypes = [C.c_longlong, C.POINTER(C.c_longlong), c_int_p, c_int_p,
                                                   C.POINTER(C.c_longlong)]
+        L.sipgpu_mirror_transition.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p]
+        L.sipgpu_mirror_create.argtypes = [C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p)]
+        L.sipgpu_mirror_destroy.argtypes = [C.c_void_p]
+        L.sipgpu_mirror_status.argtypes = [C.c_void_p]
+        L.sipgpu_mirror_access.argtypes = [C.c_void_p, C.c_int]
+        L.sipgpu_mirror_access.restype = C.c_void_p
+        L.sipgpu_mirror_host_ptr.argtypes = [C.c_void_p]
+        L.sipgpu_mirror_host_ptr.restype = C.c_void_p
+        L.sipgpu_mirror_device_ptr.argtypes = [C.c_void_p]
+        L.sipgpu_mirror_device_ptr.restype = C.c_void_p
         L.sipgpu_wl_begin.argtypes = [C.c_int]
         L.sipgpu_wl_set_limits.argtypes = [C.c_longlong, C.c_longlong]
         L.sipgpu_wl_set_idle_flush.argtypes = [C.c_longlong]
@@ -624,6 +634,54 @@ def si_return_sval(block, scalar_block):
 
 def si_invert_diagonal(a1, a2):
     return _si_call(lib().sipgpu_si_invert_diagonal, "invert_diagonal", (a1, None), (a2, None))
+
+
+# ----------------------------------------------------------------------------------------------------
+# Host/device coherence of one block (BlockManager::lazy_gpu_*, block_manager.cpp:340-441)
+# ----------------------------------------------------------------------------------------------------
+ON_HOST, ON_GPU, DIRTY_ON_HOST, DIRTY_ON_GPU = 1, 2, 4, 8
+READ_ON_DEVICE, WRITE_ON_DEVICE, UPDATE_ON_DEVICE, READ_ON_HOST, WRITE_ON_HOST, UPDATE_ON_HOST = range(6)
+
+
+def mirror_transition(bits, op):
+    """(rc, new bits, action) of the pure lazy_gpu_* state transition; host-only"""
+    nb, act = C.c_int(0), C.c_int(0)
+    rc = lib().sipgpu_mirror_transition(int(bits), int(op), C.byref(nb), C.byref(act))
+    return rc, nb.value, act.value
+
+
+class MirroredBlock:
+    """A block with a host copy (numpy, Fortran order) and/or a device copy kept coherent by the lazy_gpu_* rules."""
+
+    def __init__(self, host_array=None, shape=None):
+        self.host = None if host_array is None else np.asfortranarray(host_array, dtype=np.float64)
+        self.shape = tuple(self.host.shape) if self.host is not None else tuple(shape)
+        self.size = int(np.prod(self.shape))
+        h = C.c_void_p(0)
+        _check(lib().sipgpu_mirror_create(_hp(self.host) if self.host is not None else None, self.size, C.byref(h)),
+               "sipgpu_mirror_create")
+        self.h = h
+
+    def status(self):
+        return lib().sipgpu_mirror_status(self.h)
+
+    def on_device(self, op):
+        p = lib().sipgpu_mirror_access(self.h, op)
+        if not p:
+            raise SipGpuError("mirror access failed: " + lib().sipgpu_last_error().decode(errors="replace"))
+        return DeviceBlock(self.shape, ptr=p, owned=False)
+
+    def on_host(self, op):
+        p = lib().sipgpu_mirror_access(self.h, op)
+        if not p:
+            raise SipGpuError("mirror access failed: " + lib().sipgpu_last_error().decode(errors="replace"))
+        buf = (C.c_double * self.size).from_address(p)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.shape, order="F")
+
+    def destroy(self):
+        if self.h:
+            lib().sipgpu_mirror_destroy(self.h)
+            self.h = None
 
 
 # ----------------------------------------------------------------------------------------------------

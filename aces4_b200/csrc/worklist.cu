@@ -360,8 +360,10 @@ bool written_between(const std::unordered_map<uintptr_t, std::vector<Touch>>& to
     if (g_aliased.count((uintptr_t)base)) return true;
     auto it = touch.find((uintptr_t)base);
     if (it == touch.end()) return false;
-    for (const Touch& t : it->second)
-        if (t.op > lo && t.op < hi && (t.mode & (WL_W | WL_ATOMIC)) && !g.ops[t.op].dead) return true;
+    const std::vector<Touch>& v = it->second;  // sorted by op index
+    auto t = std::upper_bound(v.begin(), v.end(), lo, [](int o, const Touch& x) { return o < x.op; });
+    for (; t != v.end() && t->op < hi; ++t)
+        if ((t->mode & (WL_W | WL_ATOMIC)) && !g.ops[t->op].dead) return true;
     return false;
 }
 
@@ -383,25 +385,21 @@ int schedule_and_launch() {
 
     // touch lists by base address, program order, one entry per (op, base)
     std::unordered_map<uintptr_t, std::vector<Touch>> touch;
-    touch.reserve((size_t)n * 3);
+    std::unordered_map<uintptr_t, uintptr_t> span;  // base -> end of the longest access through it
+    touch.reserve((size_t)n * 2);
+    span.reserve((size_t)n * 2);
     for (int i = 0; i < n; ++i) {
         ranges_of(ops[i], rs);
         for (const WlRange& r : rs) {
             std::vector<Touch>& v = touch[(uintptr_t)r.p];
             if (!v.empty() && v.back().op == i) v.back().mode |= r.mode;
             else v.push_back({i, r.mode});
+            uintptr_t& e = span[(uintptr_t)r.p];
+            e = std::max(e, (uintptr_t)r.p + r.bytes);
         }
     }
 
     {   // aliasing sweep over [base, base + longest access)
-        std::unordered_map<uintptr_t, uintptr_t> span;
-        for (int i = 0; i < n; ++i) {
-            ranges_of(ops[i], rs);
-            for (const WlRange& r : rs) {
-                uintptr_t& e = span[(uintptr_t)r.p];
-                e = std::max(e, (uintptr_t)r.p + r.bytes);
-            }
-        }
         std::vector<std::pair<uintptr_t, uintptr_t>> iv(span.begin(), span.end());
         std::sort(iv.begin(), iv.end());
         g_aliased.clear();
@@ -445,12 +443,15 @@ int schedule_and_launch() {
         if (!ok) continue;
         double* dest = c.D;
         const double f = c.ewop == WL_REDADD ? 1.0 : c.f;
-        const int corig = c.orig;
-        c = p;  // the fused op sits at the consumer's position
+        const int corig = c.orig, porig = p.orig;
+        const double palpha = p.alpha;
+        c = std::move(p);  // the fused op sits at the consumer's position (the producer is dead from here on)
         c.orig = corig;
         c.D = dest;
-        c.alpha = p.alpha * f;
+        c.alpha = palpha * f;
         c.beta = 1.0;
+        p.orig = porig;
+        p.kind = K_EW;  // moved-from husk: never scheduled
         p.dead = true;
         g.last_unit[i] = j;
         if (c.kind == K_CONTRACT) {
@@ -540,26 +541,33 @@ int schedule_and_launch() {
     }
 
     // ---- pass C: levels from address-interval hazards ----
+    // A base whose range overlaps no other base's range (almost every block) keeps its state in a flat hash map; only
+    // aliased bases (slab-wide ops over blocks, parents of slices) go through the interval map.
     IntervalMap im;
+    std::unordered_map<uintptr_t, Lv> flat;
+    flat.reserve(span.size());
     int nlevels = 0;
+    auto visit = [&](const WlRange& r, auto f) {
+        const uintptr_t a = (uintptr_t)r.p;
+        if (g_aliased.count(a)) im.visit(a, a + r.bytes, f);
+        else f(flat[a]);
+    };
     for (int i = 0; i < n; ++i) {
         Op& o = ops[i];
         if (o.dead) continue;
         ranges_of(o, rs);
         int lv = 0;
         for (const WlRange& r : rs) {
-            const uintptr_t a = (uintptr_t)r.p, b = a + r.bytes;
-            if (r.mode == WL_R) im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.a)); });
-            else if (r.mode == WL_ATOMIC) im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.r)); });
-            else im.visit(a, b, [&](Lv& x) { lv = std::max(lv, std::max(x.w, std::max(x.r, x.a))); });
+            if (r.mode == WL_R) visit(r, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.a)); });
+            else if (r.mode == WL_ATOMIC) visit(r, [&](Lv& x) { lv = std::max(lv, std::max(x.w, x.r)); });
+            else visit(r, [&](Lv& x) { lv = std::max(lv, std::max(x.w, std::max(x.r, x.a))); });
         }
         o.level = lv + 1;
         nlevels = std::max(nlevels, o.level);
         for (const WlRange& r : rs) {
-            const uintptr_t a = (uintptr_t)r.p, b = a + r.bytes;
-            if (r.mode == WL_R) im.visit(a, b, [&](Lv& x) { x.r = std::max(x.r, o.level); });
-            else if (r.mode == WL_ATOMIC) im.visit(a, b, [&](Lv& x) { x.a = std::max(x.a, o.level); });
-            else im.visit(a, b, [&](Lv& x) { x.w = o.level; x.r = std::max(x.r, r.mode == WL_RW ? o.level : 0); });
+            if (r.mode == WL_R) visit(r, [&](Lv& x) { x.r = std::max(x.r, o.level); });
+            else if (r.mode == WL_ATOMIC) visit(r, [&](Lv& x) { x.a = std::max(x.a, o.level); });
+            else visit(r, [&](Lv& x) { x.w = o.level; x.r = std::max(x.r, r.mode == WL_RW ? o.level : 0); });
         }
     }
     for (int i = 0; i < n; ++i) g.last_level[i] = ops[g.last_unit[i]].level;

@@ -103,6 +103,24 @@ int sipgpu_d2h(double* h_dst, const double* g_src, long long n);   /* blocking *
 void* sipgpu_host_alloc(size_t bytes);     /* pinned host memory */
 int sipgpu_host_free(void* p);
 
+/* Host/device coherence of one block: the lazy_gpu_{read,write,update}_on_{device,host} transitions of
+ * src/sip/dynamic_data/block_manager.cpp:340-441 over the status bits of sip::Block (block.h:198-204).  For callers
+ * that do not carry the reference's Block class (Fortran super-instructions, other runtimes): the mirror owns the
+ * device copy (pool block) and, if it was created without a host buffer, a pinned host copy. */
+typedef struct sipgpu_mirror sipgpu_mirror;
+enum { SIPGPU_ON_HOST = 1, SIPGPU_ON_GPU = 2, SIPGPU_DIRTY_ON_HOST = 4, SIPGPU_DIRTY_ON_GPU = 8 };
+enum { SIPGPU_READ_ON_DEVICE = 0, SIPGPU_WRITE_ON_DEVICE, SIPGPU_UPDATE_ON_DEVICE,
+       SIPGPU_READ_ON_HOST, SIPGPU_WRITE_ON_HOST, SIPGPU_UPDATE_ON_HOST };
+/* pure state transition (host-only): action 0 none, 1 h2d, 2 d2h, 3 allocate device + h2d, 4 allocate host + d2h,
+ * 5 fresh zeroed device block, 6 fresh zeroed host block; SIPGPU_E_STATE where the reference fails */
+int sipgpu_mirror_transition(int status_bits, int op, int* new_status_bits, int* action);
+int sipgpu_mirror_create(double* host_or_null, long long num_elems, sipgpu_mirror** out);
+int sipgpu_mirror_destroy(sipgpu_mirror* m);
+int sipgpu_mirror_status(const sipgpu_mirror* m);
+double* sipgpu_mirror_access(sipgpu_mirror* m, int op);   /* pointer of the side that may now be used; NULL on error */
+double* sipgpu_mirror_host_ptr(sipgpu_mirror* m);
+double* sipgpu_mirror_device_ptr(sipgpu_mirror* m);
+
 /* elementwise block ops of src/sip/dynamic_data/block.cpp:132-268 and interpreter.cpp:1874-1997 */
 int sipgpu_block_fill(double* d, long long n, double v);                          /* block.cpp:153-176 */
 int sipgpu_block_scale(double* d, long long n, double f);                         /* block.cpp:179-186 */

@@ -251,3 +251,10 @@ def block_consistency(ops, workers, sections):
     n = len(ops)
     lib().oracle_block_consistency.restype = C.c_longlong
     return int(lib().oracle_block_consistency(C.c_longlong(n), _ia(ops), _ia(workers), _ia(sections)))
+
+
+def lazy_gpu_transition(bits, op):
+    """block_manager.cpp:340-441: (failed, new bits, action)"""
+    nb, act = C.c_int(0), C.c_int(0)
+    rc = lib().oracle_lazy_gpu_transition(int(bits), int(op), C.byref(nb), C.byref(act))
+    return rc, nb.value, act.value

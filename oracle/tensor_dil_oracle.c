@@ -539,3 +539,63 @@ long long oracle_block_consistency(long long n, const int* ops, const int* worke
     }
     return -1;
 }
+
+/* ---- host/device coherence of one block: BlockManager::lazy_gpu_{read,write,update}_on_{device,host},
+ * src/sip/dynamic_data/block_manager.cpp:340-441, one branch chain per function exactly as written there.
+ * bits: 1 onHost, 2 onGPU, 4 dirtyOnHost, 8 dirtyOnGPU (block.h:198-204).  op: 0 read_on_device, 1 write_on_device,
+ * 2 update_on_device, 3 read_on_host, 4 write_on_host, 5 update_on_host.  Returns 0 and the new bits + the transfer
+ * (0 none, 1 h2d, 2 d2h, 3 allocate gpu + h2d, 4 allocate host + d2h, 5 new gpu block, 6 new host block), or 1 where the
+ * reference calls fail(). ---- */
+int oracle_lazy_gpu_transition(int bits, int op, int* new_bits, int* action) {
+    int on_host = bits & 1, on_gpu = (bits >> 1) & 1, dirty_host = (bits >> 2) & 1, dirty_gpu = (bits >> 3) & 1;
+    int act = 0;
+    switch (op) {
+    case 0: /* lazy_gpu_read_on_device :340-353 */
+        if (!on_gpu && !on_host) return 1;
+        else if (!on_gpu) act = 3;
+        else if (dirty_host) act = 1;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_gpu = 1; dirty_host = 0;
+        break;
+    case 1: /* lazy_gpu_write_on_device :355-373 */
+        if (!on_gpu && !on_host) { act = 5; on_host = dirty_host = dirty_gpu = 0; }
+        else if (!on_gpu) act = 3;
+        else if (dirty_host) act = 1;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_gpu = 1; dirty_gpu = 1; dirty_host = 0;
+        break;
+    case 2: /* lazy_gpu_update_on_device :375-389 */
+        if (!on_gpu && !on_host) return 1;
+        else if (!on_gpu) act = 3;
+        else if (dirty_host) act = 1;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_gpu = 1; dirty_host = 0; dirty_gpu = 1;
+        break;
+    case 3: /* lazy_gpu_read_on_host :391-404 */
+        if (!on_gpu && !on_host) return 1;
+        else if (!on_host) act = 4;
+        else if (dirty_gpu) act = 2;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_host = 1; dirty_gpu = 0;
+        break;
+    case 4: /* lazy_gpu_write_on_host :406-425 */
+        if (!on_gpu && !on_host) { act = 6; on_gpu = dirty_host = dirty_gpu = 0; }
+        else if (!on_host) act = 4;
+        else if (dirty_gpu) act = 2;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_host = 1; dirty_host = 1; dirty_gpu = 0;
+        break;
+    case 5: /* lazy_gpu_update_on_host :427-441 */
+        if (!on_gpu && !on_host) return 1;
+        else if (!on_host) act = 4;
+        else if (dirty_gpu) act = 2;
+        else if (dirty_host && dirty_gpu) return 1;
+        on_host = 1; dirty_gpu = 0; dirty_host = 1;
+        break;
+    default:
+        return 1;
+    }
+    *new_bits = on_host | (on_gpu << 1) | (dirty_host << 2) | (dirty_gpu << 3);
+    *action = act;
+    return 0;
+}

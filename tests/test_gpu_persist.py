@@ -117,3 +117,33 @@ def test_access_tracking_feeds_the_race_detector(sip):
     assert A.section_accesses() == []
     assert np.all(A.get((1, 2)).to_numpy() == 2.0) and g.shape == A.block_shape((2, 1))
     A.destroy()
+
+
+def test_mirrored_block_coherence(sip):
+    """BlockManager::lazy_gpu_* semantics on real buffers: copies happen only when the side being used is missing or
+    stale, and the data seen on either side is always the latest write."""
+    a = np.asfortranarray(np.arange(24.0).reshape(4, 6))
+    m = sip.MirroredBlock(a)
+    assert m.status() == sip.ON_HOST
+    d = m.on_device(sip.READ_ON_DEVICE)                     # allocate + h2d
+    assert m.status() == sip.ON_HOST | sip.ON_GPU and np.array_equal(d.to_numpy(), a)
+    d = m.on_device(sip.UPDATE_ON_DEVICE)
+    d.scale(2.0)                                            # the device copy is now the newer one
+    assert m.status() & sip.DIRTY_ON_GPU
+    h = m.on_host(sip.READ_ON_HOST)                         # d2h because dirty on gpu
+    assert np.array_equal(h, 2.0 * a) and not (m.status() & sip.DIRTY_ON_GPU)
+    h = m.on_host(sip.WRITE_ON_HOST)
+    h[...] = 7.0                                            # host is newer
+    assert m.status() & sip.DIRTY_ON_HOST
+    d = m.on_device(sip.READ_ON_DEVICE)                     # h2d because dirty on host
+    assert np.all(d.to_numpy() == 7.0) and not (m.status() & sip.DIRTY_ON_HOST)
+    m.destroy()
+    # a block that exists nowhere: write_on_device creates it (zeroed) on the device, read_on_host brings it over
+    m2 = sip.MirroredBlock(shape=(3, 5))
+    with pytest.raises(sip.SipGpuError):
+        m2.on_device(sip.READ_ON_DEVICE)                    # "block allocated neither on host or gpu"
+    d = m2.on_device(sip.WRITE_ON_DEVICE)
+    d.increment(1.5)
+    assert m2.status() == sip.ON_GPU | sip.DIRTY_ON_GPU
+    assert np.all(m2.on_host(sip.READ_ON_HOST) == 1.5) and m2.status() == sip.ON_GPU | sip.ON_HOST
+    m2.destroy()
