@@ -123,7 +123,7 @@ def test_mirrored_block_coherence(sip):
     """BlockManager::lazy_gpu_* semantics on real buffers: copies happen only when the side being used is missing or
     stale, and the data seen on either side is always the latest write."""
     a = np.asfortranarray(np.arange(24.0).reshape(4, 6))
-    m = sip.MirroredBlock(a)
+    m = sip.MirroredBlock(a.copy(order="F"))               # the mirror writes back into ITS host buffer, not into `a`
     assert m.status() == sip.ON_HOST
     d = m.on_device(sip.READ_ON_DEVICE)                     # allocate + h2d
     assert m.status() == sip.ON_HOST | sip.ON_GPU and np.array_equal(d.to_numpy(), a)
