@@ -129,6 +129,8 @@ def lib():
         L.sipgpu_array_put.argtypes = [C.c_void_p, c_int_p, C.c_void_p]
         L.sipgpu_array_put_accumulate.argtypes = [C.c_void_p, c_int_p, C.c_void_p]
         L.sipgpu_array_fill_local.argtypes = [C.c_void_p, C.c_double]
+        for name in ("put_initialize", "put_increment", "put_scale"):
+            getattr(L, "sipgpu_array_" + name).argtypes = [C.c_void_p, c_int_p, C.c_double]
         L.sipgpu_array_local_bytes.argtypes = [C.c_void_p]
         L.sipgpu_array_local_bytes.restype = C.c_size_t
         L.sipgpu_persist_scalar.argtypes = [C.c_char_p, C.c_double]
@@ -816,6 +818,15 @@ class DistArray:
 
     def put_accumulate(self, idx, blk):
         _check(lib().sipgpu_array_put_accumulate(self.h, _ia(idx), blk.ptr), "sipgpu_array_put_accumulate")
+
+    def put_initialize(self, idx, v):
+        _check(lib().sipgpu_array_put_initialize(self.h, _ia(idx), float(v)), "sipgpu_array_put_initialize")
+
+    def put_increment(self, idx, d):
+        _check(lib().sipgpu_array_put_increment(self.h, _ia(idx), float(d)), "sipgpu_array_put_increment")
+
+    def put_scale(self, idx, f):
+        _check(lib().sipgpu_array_put_scale(self.h, _ia(idx), float(f)), "sipgpu_array_put_scale")
 
     def fill_local(self, v):
         _check(lib().sipgpu_array_fill_local(self.h, float(v)), "sipgpu_array_fill_local")

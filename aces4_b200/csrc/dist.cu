@@ -201,6 +201,31 @@ int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g
     if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0, a->world == 1);
     return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
 }
+// put_initialize / put_increment / put_scale (sial_ops_parallel.cpp:412-528): one scalar applied to one block at its
+// owner.  The reference sends {value, block id} to the server, which runs a serial loop; here the elementwise kernel
+// runs on the caller's stream directly on the owner's (possibly peer-mapped) block.  For the race detector they count
+// as put, put_accumulate and put respectively (distributed_block_consistency.cpp:60).
+int sipgpu_array_put_initialize(sipgpu_array* a, const int* idx, double value) {
+    double* dst = sipgpu_array_block_ptr(a, idx);
+    if (!dst) return SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
+    const long long n = sipgpu_array_block_size(a, idx);
+    return wl_active() ? wl_rec_ew(WL_FILL, dst, nullptr, nullptr, n, value) : ew_fill(dst, n, value);
+}
+int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta) {
+    double* dst = sipgpu_array_block_ptr(a, idx);
+    if (!dst) return SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT_ACCUMULATE;
+    const long long n = sipgpu_array_block_size(a, idx);
+    return wl_active() ? wl_rec_ew(WL_INCR, dst, nullptr, nullptr, n, delta) : ew_increment(dst, n, delta);
+}
+int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor) {
+    double* dst = sipgpu_array_block_ptr(a, idx);
+    if (!dst) return SIPGPU_E_STATE;
+    if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
+    const long long n = sipgpu_array_block_size(a, idx);
+    return wl_active() ? wl_rec_ew(WL_SCALE, dst, nullptr, nullptr, n, factor) : ew_scale(dst, n, factor);
+}
 int sipgpu_array_fill_local(sipgpu_array* a, double v) {
     if (!a) return SIPGPU_E_ARG;
     if (wl_active()) return wl_rec_ew(WL_FILL, a->base[a->my_rank], nullptr, nullptr, a->slab_elems[a->my_rank], v);

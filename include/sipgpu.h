@@ -294,7 +294,10 @@ double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx);
 int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst);            /* SialOpsParallel::get            */
 int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src);      /* ::put_replace                   */
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src); /* ::put_accumulate (atomic)  */
-int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* put_initialize on owned blocks  */
+int sipgpu_array_put_initialize(sipgpu_array* a, const int* idx, double value);  /* ::put_initialize :412-446, block = v */
+int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta);   /* ::put_increment  :448-487, block += d */
+int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor);      /* ::put_scale      :489-528, block *= f */
+int sipgpu_array_fill_local(sipgpu_array* a, double v);                          /* all owned blocks = v (array creation / `T2new = 0`) */
 size_t sipgpu_array_local_bytes(const sipgpu_array* a);
 double* sipgpu_array_local_base(sipgpu_array* a);   /* this rank's slab (its owned blocks, contiguous) */
 /* ---- race detection between barriers (src/sip/dynamic_data/distributed_block_consistency.cpp:25-175) ----

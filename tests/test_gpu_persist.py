@@ -147,3 +147,24 @@ def test_mirrored_block_coherence(sip):
     assert m2.status() == sip.ON_GPU | sip.DIRTY_ON_GPU
     assert np.all(m2.on_host(sip.READ_ON_HOST) == 1.5) and m2.status() == sip.ON_GPU | sip.ON_HOST
     m2.destroy()
+
+
+def test_put_initialize_increment_scale(sip):
+    """the scalar block ops of SialOpsParallel (sial_ops_parallel.cpp:412-528) at the owner, eager and recorded"""
+    A = sip.DistArray([[3, 4], [2, 5]])
+    A.track_accesses(True)
+    A.put_initialize((2, 2), 1.5)
+    A.put_increment((2, 2), 0.25)
+    A.put_scale((2, 2), -2.0)
+    assert np.all(A.get((2, 2)).to_numpy() == -3.5) and A.get((2, 2)).shape == (4, 5)
+    assert np.all(A.get((1, 1)).to_numpy() == 0.0)
+    bits = dict(A.section_accesses())
+    assert bits[A.block_number((2, 2))] == sip.ACCESS_PUT | sip.ACCESS_PUT_ACCUMULATE | sip.ACCESS_GET
+    with sip.recording() as rec:
+        for idx in ((1, 1), (1, 2), (2, 1)):
+            A.put_initialize(idx, 2.0)
+            A.put_increment(idx, 1.0)
+    assert rec.stats["launches"] == 2          # three fills in one launch, three increments in the next
+    for idx in ((1, 1), (1, 2), (2, 1)):
+        assert np.all(A.get(idx).to_numpy() == 3.0)
+    A.destroy()
