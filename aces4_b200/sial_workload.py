@@ -62,10 +62,25 @@ def iteration_flops(o_segs, v_segs):
     return sum(term_flops(t, o_segs, v_segs) for t in TERMS)
 
 
+def block_present(seed, number, density):
+    """Block sparsity of the amplitude array: block `number` of T2old exists iff a seeded hash of its
+    number falls below `density`.  splitmix64, identical on every rank and in the CPU restatement."""
+    if density >= 1.0:
+        return True
+    z = ((seed ^ 0xD5B10C) + (int(number) + 1) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 31
+    return (z >> 11) * (1.0 / (1 << 53)) < density
+
+
 class SyntheticCCSD:
     def __init__(self, o_segs, v_segs, rank=0, world=1, exchange=None, barrier=None, allreduce=None, seed=0xACE54,
-                 ao_pool=8, terms=None):
+                 ao_pool=8, terms=None, density=1.0):
         self.o_segs, self.v_segs = list(o_segs), list(v_segs)
+        self.density = float(density)
+        self.flops = 0.0   # algorithmic flops THIS RANK executes per iteration = sum over the operand pairs in its work-lists
+        self.term_flops_rank = {}
         self.rank, self.world = rank, world
         self.exchange, self.barrier, self.allreduce = exchange, barrier or (lambda: None), allreduce
         self.seed = seed
@@ -118,10 +133,24 @@ class SyntheticCCSD:
                 idx1 = tuple(x + 1 for x in idx)
                 A.block_view(idx1).fill_hash(self.seed, self._tag(name, A.block_number(idx1)), SCALE[name])
         for blk in self.mine:
-            self.T2old.block_view(blk).fill_hash(self.seed, self._tag("T2old", self.T2old.block_number(blk)),
-                                                 SCALE["T2old"])
+            if self.t2_present(blk):
+                self.T2old.block_view(blk).fill_hash(self.seed, self._tag("T2old", self.T2old.block_number(blk)),
+                                                     SCALE["T2old"])
+            else:
+                self.T2old.block_view(blk).fill(0.0)   # an absent block: never read by a work-list, zero for the W build
         api.sync()
         self.barrier()
+
+    def t2_present(self, idx):
+        return block_present(self.seed, self.T2old.block_number(idx), self.density)
+
+    def _operand_present(self, name, idx):
+        if name == "T2old":
+            return self.t2_present(idx)
+        if name == "W":   # W[c,k,a,i] = T2old[c,k,a,i] - T2old[c,i,a,k]
+            c, k, a, i = idx
+            return self.t2_present(idx) or self.t2_present((c, i, a, k))
+        return True
 
     def ao_block(self, lam, mu, sig, nu):
         """aoint[lambda,mu,sigma,nu] block from the seeded pool (keyed by extents and a hash of the block id)."""
@@ -158,26 +187,36 @@ class SyntheticCCSD:
             cranges = [range(1, (self.nv if _is_virtual(c) else self.no) + 1) for c in contracted]
             dest = self.Xs if t["sym"] else self.T2new
             lsh, rsh, dsh, lp, rp, dp, chain = [], [], [], [], [], [], [0]
+            empty = []   # destinations whose whole chain is absent (block sparsity)
             for blk in self.mine:
                 segs = dict(zip(dlab, blk))
                 first = True
                 for cseg in np.ndindex(*[len(r) for r in cranges]):
                     for c, s in zip(contracted, cseg):
                         segs[c] = s + 1
+                    if not (self._operand_present(t["L"], tuple(segs[c] for c in llab)) and
+                            self._operand_present(t["R"], tuple(segs[c] for c in rlab))):
+                        continue   # an absent amplitude block contributes nothing: the pair never reaches the device
                     pl, shl = self._operand(t["L"], llab, segs)
                     pr, shr = self._operand(t["R"], rlab, segs)
                     lp.append(pl), rp.append(pr)
+                    f = 2.0 * float(np.prod(dest.block_shape(blk))) * float(np.prod([self._seg_ext(c, segs[c]) for c in contracted]))
+                    self.flops += f
+                    self.term_flops_rank[t["name"]] = self.term_flops_rank.get(t["name"], 0.0) + f
                     if first:
                         lsh.append(shl), rsh.append(shr)
                         first = False
                     else:
                         # a chain shares ONE shape: with non-uniform contracted segments the chain is split below
                         assert shl == lsh[-1] and shr == rsh[-1], "non-uniform contracted segments: split the chain"
+                if first:
+                    empty.append(blk)
+                    continue
                 chain.append(len(lp))
                 dsh.append(dest.block_shape(blk))
                 dp.append(dest.block_ptr(blk))
-            bc = api.BatchedContraction(ptrn, lsh, rsh, dsh, lp, rp, dp, chain_start=chain) if self.mine else None
-            self.worklists.append((t, bc))
+            bc = api.BatchedContraction(ptrn, lsh, rsh, dsh, lp, rp, dp, chain_start=chain) if dp else None
+            self.worklists.append((t, bc, empty))
 
     # ------------------------------------------------------------------------------------------------
     def _temp(self, shape, k=0):
@@ -211,8 +250,13 @@ class SyntheticCCSD:
         for blk in self.mine:
             self.Xs.block_view(blk).scale_and_copy(self.arr["Vvovo"].block_view(blk), 0.5)
         first_direct = True
-        for t, bc in self.worklists:
+        for t, bc, empty in self.worklists:
+            if not t["sym"] and first_direct:
+                for blk in empty:   # destinations the first direct term does not write (their chain is absent)
+                    self.T2new.block_view(blk).fill(0.0)
             if bc is None:
+                if not t["sym"] and self.mine:
+                    first_direct = False
                 continue
             if self.before_launch:
                 self.before_launch(t)

@@ -23,6 +23,30 @@ def test_fill_hash_bit_identical(sip, oracle):
         assert np.all(np.abs(d) <= scale)
 
 
+def test_block_sparse_iteration_matches_cpu_restatement(sip, oracle):
+    """density 0.5: absent amplitude blocks never reach the device work-lists; the result equals the
+    dense restatement with those blocks zero, and the flop count is the sum over the pairs that exist."""
+    from aces4_b200.sial_workload import SyntheticCCSD, iteration_flops
+    from workload_ref import RefWorkload
+
+    o_segs, v_segs = [3, 3], [6, 6, 6]
+    w = SyntheticCCSD(o_segs, v_segs, density=0.5)
+    present = sum(w.t2_present(b) for b in w.blocks)
+    assert 0 < present < len(w.blocks)
+    assert 0.0 < w.flops < iteration_flops(o_segs, v_segs)
+    ref = RefWorkload(oracle, o_segs, v_segs, density=0.5)
+    e = w.iterate()
+    t2ref, eref = ref.iterate()
+    offs_v, offs_o = np.cumsum([0] + v_segs), np.cumsum([0] + o_segs)
+    scale = np.max(np.abs(t2ref))
+    for blk in w.blocks:
+        a, i, b, j = blk
+        got = w.T2new.block_view(blk).to_numpy()
+        want = t2ref[offs_v[a - 1]:offs_v[a], offs_o[i - 1]:offs_o[i], offs_v[b - 1]:offs_v[b], offs_o[j - 1]:offs_o[j]]
+        assert np.max(np.abs(got - want)) <= TOL * scale
+    assert abs(e - eref) <= 1e-9 * max(1.0, abs(eref))
+
+
 @pytest.mark.parametrize("o_segs,v_segs", [([3, 3], [8, 8, 8]), ([4], [6, 6])])
 def test_iteration_matches_cpu_restatement(sip, oracle, o_segs, v_segs):
     from aces4_b200.sial_workload import SyntheticCCSD, TERMS, iteration_flops

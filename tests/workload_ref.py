@@ -3,7 +3,7 @@ blocks (oracle.fill_hash), assembled into dense tensors, contracted with numpy.e
 the oracle's tensor_block_contract chain (contract into a temp, then +=, like the SIAL body).  Test infrastructure."""
 import numpy as np
 
-from aces4_b200.sial_workload import SCALE, TAG, TERMS
+from aces4_b200.sial_workload import SCALE, TAG, TERMS, block_present
 
 
 def _offsets(segs):
@@ -14,8 +14,9 @@ def _offsets(segs):
 
 
 class RefWorkload:
-    def __init__(self, oracle, o_segs, v_segs, seed=0xACE54, ao_pool=8):
+    def __init__(self, oracle, o_segs, v_segs, seed=0xACE54, ao_pool=8, density=1.0):
         self.oracle, self.o_segs, self.v_segs, self.seed, self.ao_pool = oracle, list(o_segs), list(v_segs), seed, ao_pool
+        self.density = density
         self.segs = {"v": self.v_segs, "o": self.o_segs}
         kinds = {"T2old": "vovo", "Vvovo": "vovo", "Voooo": "oooo", "TY": "vovo", "Vovvo": "ovvo", "Vvvoo": "vvoo"}
         self.kinds = kinds
@@ -37,6 +38,8 @@ class RefWorkload:
         for p in range(len(idx)):
             number = number * nseg[p] + (idx[p] - 1)  # last index fastest (array_table.cpp:50-97)
         shape = tuple(self.segs[k][i - 1] for k, i in zip(kind, idx))
+        if name == "T2old" and not block_present(self.seed, number, getattr(self, "density", 1.0)):
+            return np.zeros(shape, order="F")   # an absent block of the block-sparse amplitude array
         return self.oracle.fill_hash(shape, self.seed, self._tag(name, number), SCALE[name])
 
     def ao_block(self, lam, mu, sig, nu):
