@@ -414,6 +414,20 @@ def permute_batched(srcs, transp, outs, alpha=1.0, beta=0.0):
     return outs
 
 
+class BatchedPermute:
+    """A prepared batch (pointer arrays marshalled once) that can be re-launched cheaply: the ctypes conversion of a
+    thousand block pointers costs more than the kernel that permutes them."""
+
+    def __init__(self, srcs, transp, outs):
+        self.n, self.shape = len(srcs), tuple(srcs[0].shape)
+        self.ext, self.transp = _ia(self.shape), _ia(transp)
+        self.ins, self.outs = _ptr_array([b.ptr for b in srcs]), _ptr_array([b.ptr for b in outs])
+
+    def launch(self, alpha=1.0, beta=0.0):
+        _check(lib().sipgpu_permute_batched(self.n, len(self.shape), self.ext, self.transp, self.ins, self.outs, float(alpha),
+                                            float(beta)), "sipgpu_permute_batched")
+
+
 def permute_labels(lhs_labels, rhs_labels, rhs, out=None):
     """lhs[lhs_labels] = rhs[rhs_labels]  (block_permute_op)."""
     ext = {lab: e for lab, e in zip(rhs_labels, rhs.shape)}

@@ -83,15 +83,20 @@ __global__ void __launch_bounds__(kPT, (EPT <= 4 ? 4 : EPT <= 8 ? 3 : 2) - (RAG 
     };
     const long long total = a.ntiles * b.n;
     // (block, tile) work item -> source / destination base and the ragged limits of the tile
+    // 32-bit index arithmetic: a block has < 2^31 elements, so its tile count fits an int, and the (block, tile) split is
+    // one 32-bit division when the whole launch has < 2^31 work items (64-bit div/mod chains cost ~1000 cycles per tile,
+    // 12 % of a 2048-element tile)
+    const unsigned ntiles32 = (unsigned)a.ntiles;
     auto decode = [&](long long work, const double*& src, double*& dst, int& lim0, int& lim1) {
-        const int blk = (int)(work / a.ntiles);
-        long long t = work - (long long)blk * a.ntiles;
+        const int blk = total < (1LL << 31) ? (int)((unsigned)work / ntiles32) : (int)(work / a.ntiles);
+        unsigned t = (unsigned)(work - (long long)blk * a.ntiles);
         int bin = 0, bout = 0;
         lim0 = lim1 = kNoLimit;
 #pragma unroll 1
         for (int d = 0; d < a.rank; ++d) {
-            const int c = (int)(t % a.ntile[d]);
-            t /= a.ntile[d];
+            const unsigned q = t / (unsigned)a.ntile[d];
+            const int c = (int)(t - q * (unsigned)a.ntile[d]);
+            t = q;
             bin += c * a.tstep_in[d];
             bout += c * a.tstep_out[d];
             if (RAG) {

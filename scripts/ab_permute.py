@@ -32,8 +32,9 @@ for shape, n in (((16,) * 4, 1024), ((32,) * 4, 128), ((64,) * 4, 8), ((50, 20, 
         if p == (0, 1, 2, 3):
             continue
         transp = [1] + [x + 1 for x in p]
-        res.append(n * 16.0 * np.prod(shape) / time_ms(lambda: api.permute_batched(ins, transp, outs)) / 1e6)
-        acc.append(n * 24.0 * np.prod(shape) / time_ms(lambda: api.permute_batched(ins, transp, outs, alpha=0.5, beta=1.0)) / 1e6)
+        bp = api.BatchedPermute(ins, transp, outs)   # pointer arrays marshalled once: time the library, not ctypes
+        res.append(n * 16.0 * np.prod(shape) / time_ms(lambda: bp.launch()) / 1e6)
+        acc.append(n * 24.0 * np.prod(shape) / time_ms(lambda: bp.launch(alpha=0.5, beta=1.0)) / 1e6)
     out[str(shape)] = {"blocks": n, "min": round(min(res)), "median": round(float(np.median(res))), "max": round(max(res)),
                        "acc_median": round(float(np.median(acc)))}
     del ins, outs

@@ -51,6 +51,13 @@ elif mode in ("skinny", "outer"):
                                 [Rs[i % len(Rs)].ptr for i in range(nb)], [Ds[i % len(Ds)].ptr for i in range(nb)])
     for _ in range(3):
         bc.launch()
+elif mode == "permute16":
+    shape = (16, 16, 16, 16)
+    ins = [api.DeviceBlock(shape).fill(1.0) for _ in range(1024)]
+    outs = [api.DeviceBlock(shape) for _ in range(1024)]
+    for transp in ([1, 4, 3, 2, 1], [1, 2, 1, 4, 3]):
+        for _ in range(2):
+            api.permute_batched(ins, transp, outs)
 elif mode == "permute":
     shape = (64, 64, 64, 64) if n >= 64 else (50, 20, 50, 20)
     a, b = api.DeviceBlock(shape).fill(1.0), api.DeviceBlock(shape)

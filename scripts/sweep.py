@@ -106,7 +106,8 @@ for s in sizes:
         transp = [1] + [x + 1 for x in p]
         key = "".join(map(str, p))
         one[key] = 16.0 * s ** 4 / time_ms(lambda: api.permute(ins[0], transp, out=outs[0]), reps=7) / 1e6
-        bat[key] = n * 16.0 * s ** 4 / time_ms(lambda: api.permute_batched(ins, transp, outs), reps=3, warm=1) / 1e6
+        bp = api.BatchedPermute(ins, transp, outs)   # pointer arrays marshalled once: time the library, not ctypes
+        bat[key] = n * 16.0 * s ** 4 / time_ms(lambda: bp.launch(), reps=3, warm=1) / 1e6
     perm[str(s)] = {"blocks_per_launch": n, "one_block_gbs": one, "batched_gbs": bat}
     vb, v1 = list(bat.values()), list(one.values())
     print(f"permute s={s}: batched({n}) GB/s min/median/max {min(vb):.0f}/{np.median(vb):.0f}/{max(vb):.0f}; one block "
