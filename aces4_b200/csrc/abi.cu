@@ -346,6 +346,20 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
         a.alpha = alpha;
         a.beta = beta;
         a.atomic = any_split ? 1 : 0;
+        {   // lockstep throttle: only for launches whose tiles all walk the same number of ring stages
+            long long steps0 = -1;
+            bool uniform = true;
+            for (const Problem& pr : probs) {
+                const Shape& sh = shapes[pr.shape];
+                const int nwin = (sh.K + kContractKWin - 1) / kContractKWin;
+                const long long per_pair = (long long)(nwin - 1) * (kContractKWin / 16) + (sh.K - (nwin - 1) * kContractKWin + 15) / 16;
+                const long long st = pr.kwin ? -2 : per_pair * pr.chain_len;
+                if (steps0 == -1) steps0 = st;
+                if (st != steps0 || st < 0) { uniform = false; break; }
+            }
+            if (uniform && steps0 >= 4 * kSyncEvery && steps0 < (1LL << 30) && a.total_tiles >= ctx().num_sms)
+                a.sync_q = (int)((steps0 + kSyncEvery - 1) / kSyncEvery);
+        }
         SIP_TRY(launch_contract(a, a_kc, b_kc, vec, tile));
     }
     return SIPGPU_OK;

@@ -193,6 +193,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
         const int b_var = tid / C::B_LANES;
         int ring = 0;  // stages produced so far (all tiles)
         int tcount = 0;
+        bool lockstep = true;  // thread 0: still honouring the lockstep throttle
         for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
             const int par = tcount & 1;
             int* mOffL = tabs + par * (2 * BM + 2 * BN);
@@ -284,6 +285,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
             const int mo_fix = (C::A_KC || a_var >= C::A_PER) ? 0 : mOffL[a_fix];
             const int no_fix = (C::B_KC || b_var >= C::B_PER) ? 0 : nOffR[b_fix];
 
+            int jstage = 0;  // stages of THIS tile produced so far
             for (int c = 0; c < chain_len; ++c) {
                 const Pair pq = chain[c];
                 const double* __restrict__ Lp = pq.L;
@@ -291,7 +293,21 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
                 for (int win = w0; win < w1; ++win) {
                     if (w1 - w0 > 1) fill_ktable(win);
                     const int steps = win == nwin - 1 ? last_steps : KWIN / BK;
-                    for (int ks = 0; ks < steps; ++ks, ++ring) {
+                    for (int ks = 0; ks < steps; ++ks, ++ring, ++jstage) {
+                        if (args.sync_q && jstage % kSyncEvery == 0) {
+                            if (tid == 0) {
+                                const int q = jstage / kSyncEvery;
+                                int* ctr = args.sync_ctr + (size_t)tcount * args.sync_q;
+                                atomicAdd(ctr + q, 1);
+                                if (q >= kSyncWindow && lockstep) {
+                                    const int target = min((int)gridDim.x, args.total_tiles - tcount * (int)gridDim.x);
+                                    int budget = 1 << 16;   // never block progress: a stuck peer only costs the throttle
+                                    while (*(volatile int*)(ctr + q - kSyncWindow) < target && --budget) __nanosleep(100);
+                                    if (!budget) lockstep = false;
+                                }
+                            }
+                            producer_bar_sync();
+                        }
                         const int stage = ring % STAGES;
                         mbar_wait(empty + stage, ((ring / STAGES) & 1) ^ 1);  // slot free (first lap passes at once)
                         double* as = tiles + (size_t)stage * C::STAGE_ELEMS;
@@ -506,7 +522,20 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
     max_ctas *= C::MIN_CTAS;
     int grid = a.total_tiles < max_ctas ? a.total_tiles : max_ctas;
     if (grid < 1) return SIPGPU_OK;
-    contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(a);
+    ContractArgs args = a;
+    int* ctr = nullptr;
+    static const bool lockstep_enabled = [] { const char* e = getenv("SIPGPU_LOCKSTEP"); return !e || atoi(e) != 0; }();
+    if (args.sync_q > 0 && lockstep_enabled && grid > 1) {
+        const size_t rounds = ((size_t)a.total_tiles + grid - 1) / grid;
+        const size_t bytes = rounds * (size_t)args.sync_q * sizeof(int);
+        ctr = (int*)pool_alloc(bytes);
+        if (ctr && cudaMemsetAsync(ctr, 0, bytes, ctx().stream) == cudaSuccess) args.sync_ctr = ctr;
+        else args.sync_q = 0;
+    } else {
+        args.sync_q = 0;
+    }
+    contract_kernel<C><<<grid, C::NT, C::SMEM, ctx().stream>>>(args);
+    if (ctr) pool_free(ctr);  // recycled in stream order
     SIP_CUDA(cudaGetLastError());
     count_launch();
     return SIPGPU_OK;

@@ -13,6 +13,12 @@ struct ContractArgs {
     int total_tiles;
     double alpha, beta;
     int atomic;  // epilogue adds alpha*acc with red.global.add.f64 (several problems share a destination: split-K)
+    // Lockstep throttle (uniform work-lists only): every kSyncEvery ring stages the producers of all CTAs of a tile round
+    // announce their progress in sync_ctr[round * sync_q + step] and wait until the whole round has reached the step
+    // kSyncWindow steps back, so CTAs that share operand panels stay within a few hundred k-elements of each other and
+    // the panels are fetched from DRAM once instead of once per drifted-apart CTA.  sync_q = steps per tile, 0 = off.
+    int sync_q;
+    int* sync_ctr;
     Problem p0;
     Pair pair0;
     Shape s0;
@@ -26,6 +32,8 @@ int launch_contract(const ContractArgs& a, bool a_kc, bool b_kc, bool vec, int t
 int contract_pick_tile(int M, int N);
 long long contract_tile_count(int M, int N, int tile);
 constexpr int kContractKWin = 2048;  // contracted elements per k window (Cfg::KWIN)
+constexpr int kSyncEvery = 32;   // ring stages (of 16 contracted elements) between two lockstep points
+constexpr int kSyncWindow = 2;   // allowed lead, in lockstep points
 constexpr int kSmallTile = 2;  // 64x64, for launches that cannot fill the SMs with large tiles
 int dmma_probe(int iters, double* tflops);
 
