@@ -255,3 +255,27 @@ def test_lccd_sial_program_at_the_shapes_of_the_shipped_inputs(sip, oracle, dat)
     assert abs(e - e_ref) <= 1e-9 * max(1.0, abs(e_ref))      # north_star: 1e-9 on energies
     for A in arrays.values():
         A.destroy()
+
+
+def test_sliced_contractions_inside_a_recording(sip, oracle):
+    """half transformation with a static-array slice (T[a,i,mu,j] = T2[a,i,b,j]*ca[mu,b], read in place), accumulated
+    into a slice of a larger array -- recorded: the sliced contractions are scheduled as opaque ops with the byte
+    ranges of their parent arrays, so everything that touches the same parent stays in program order."""
+    rng = np.random.default_rng(33)
+    norb, nmo, v, o = 30, 40, 10, 6
+    ca = np.asfortranarray(rng.uniform(-1, 1, (norb, nmo)))
+    T2 = np.asfortranarray(rng.uniform(-1, 1, (v, o, v, o)))
+    big = np.asfortranarray(rng.uniform(-1, 1, (v, o, norb, o)))
+    dca, dT2, dbig = (sip.DeviceBlock.from_numpy(x) for x in (ca, T2, big))
+    ptrn, _ = sip.get_contraction_ptrn([1, 2, 5, 4], [1, 2, 3, 4], [5, 3])
+    want = big.copy(order="F")
+    with sip.recording() as rec:
+        for mu0, nmu, b0 in ((0, 10, 4), (10, 10, 14), (20, 10, 24)):
+            sip.contract_sliced(ptrn, dT2, (v, o, v, o), None, dca, (nmu, v), (mu0, b0), (v, o, nmu, o), out=dbig,
+                                dbeg=(0, 0, mu0, 0), alpha=0.5, beta=1.0)
+            blk, ierr = oracle.block_slice(ca, (nmu, v), (mu0, b0))
+            ref, ierr = oracle.block_contract(ptrn, T2, blk, (v, o, nmu, o))
+            want[:, :, mu0:mu0 + nmu, :] += 0.5 * ref
+        dbig.scale(2.0)
+    assert rec.stats["recorded"] == 4 and rec.stats["levels"] == 4     # all four touch the same parent array: serial
+    assert rel(dbig.to_numpy(), 2.0 * want) <= TOL
