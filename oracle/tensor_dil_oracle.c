@@ -10,10 +10,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
  * load this library.  The product (libsipgpu.so) never links, loads or calls it.
  *
- * PARITY PINNING: the reference itself cannot be built here (no Fortran compiler, no MPI, no JVM
- * for the SIAL compiler -- see DESIGN.md), so this restatement is pinned against the reference's
- * own known-answer tests (test/test_basic_sial.cpp, test/test_sial.cpp, test/test_*.F), restated
- * in tests/test_oracle_golden.py, and cross-checked against numpy.einsum on random patterns.
+ * PARITY PINNING: the Fortran kernels of the reference cannot be built here (no Fortran compiler), nor
+ * its interpreter (MPI, BLAS, the Java SIAL compiler -- see DESIGN.md).  This restatement is pinned
+ *  (1) against the reference's own known-answer tests (test/test_basic_sial.cpp, test/test_sial.cpp,
+ *      test/test_*.F), restated in tests/test_oracle_golden.py, and cross-checked against numpy.einsum;
+ *  (2) against the reference's own C++ wherever that compiles with g++ alone -- oracle/_ref, built in
+ *      place from /root/reference by `make ref`: the block loops and argument conventions of block.cpp,
+ *      the consistency state table, block numbering, the .dat reader and the checkpoint stream -- live
+ *      and through tests/golden/ref_vectors.json (tests/test_oracle_vs_ref_cpu.py).
+ * The Fortran loop nests (contract / copy / slice / insert / add) are pinned by (1) only.
  *
  * Every function cites the reference lines it follows.  All scalars are passed by pointer, which
  * is ABI-identical to the C++ by-reference prototypes in tensor_ops_c_prototypes.h:41-178.
