@@ -323,12 +323,14 @@ def main():
             w.store_t2new_to_host(h_out)
             return e
 
-        e2e_step()
-        ms_e2e, energy_e2e = timed(args.steps, e2e_step)
+        # The kernels are warm from region 1 and the copies go through pinned buffers, so no extra untimed pass; at most
+        # two end-to-end steps are timed (36 s each at full size) so that a large --steps stays bounded.
+        e2e_steps = max(1, min(args.steps, 2))
+        ms_e2e, energy_e2e = timed(e2e_steps, e2e_step)
         assert abs(energy_e2e - energy) <= 1e-9 * max(1.0, abs(energy)), (energy_e2e, energy)
-        e2e = {"value": flops / (ms_e2e / args.steps * 1e-3) / 1e12, "unit": "TFLOP/s",
+        e2e = {"value": flops / (ms_e2e / e2e_steps * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(reduce_sum(float(nbytes))), "d2h_bytes_per_step": int(reduce_sum(float(nbytes + 8))),
-               "ms_per_step": ms_e2e / args.steps}
+               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps}
         api.lib().sipgpu_host_free(h_in)
         api.lib().sipgpu_host_free(h_out)
 

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Second baseline, reference CODE on the same B200: the legacy CUDA backend of the reference
+(src/sip/cuda/gpu_super_instructions.cu, compiled unmodified for sm_100a: oracle/_ref/libaces4_ref_gpu.so) timed on the
+pair-level contractions of the five terms of the synthetic CCSD iteration (block shapes of bench.py: occ segments of 20,
+virt segments of 50), next to libsipgpu's `_gpu_contract` called the same way (one block pair per call, device pointers
+resident, synchronised after every call, as the reference does) and to libsipgpu's own batched path for the same pairs.
+
+    python scripts/ref_gpu_baseline.py [--reps 20] > gpurun_out/ref_gpu_baseline.json
+
+Not a bench.py line: the per-call figures are latency-dominated by construction of the legacy backend (three cudaMalloc of
+40 MB, seven device synchronisations and two DGEMMs per contraction); it is the reported "reference on a GPU" figure.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--o-seg", type=int, default=20)
+    ap.add_argument("--v-seg", type=int, default=50)
+    args = ap.parse_args()
+
+    import aces4_b200 as sip
+    from aces4_b200.sial_workload import TERMS
+    from oracle import ref_gpu
+
+    cases = []
+    for k, t in enumerate(TERMS):
+        labs = []
+        for c in t["dlab"] + t["llab"] + t["rlab"]:
+            if c not in labs:
+                labs.append(c)
+        num = {c: i + 1 for i, c in enumerate(labs)}
+        ext = {c: (args.v_seg if c in "abcd" else args.o_seg) for c in labs}
+        cases.append({"kind": "contract", "seed": 40 + k, "reps": args.reps, "name": t["name"],
+                      "y": ([ext[c] for c in t["dlab"]], [num[c] for c in t["dlab"]]),
+                      "x1": ([ext[c] for c in t["llab"]], [num[c] for c in t["llab"]]),
+                      "x2": ([ext[c] for c in t["rlab"]], [num[c] for c in t["rlab"]]),
+                      "flops": 2.0 * float(np.prod([ext[c] for c in labs]))})
+    ref_y, ref_s = ref_gpu.run_cases(cases, timeout=600)
+
+    sip.init(0)
+    api, L = sip.api, sip.api.lib()
+
+    def ia(v):
+        v = [int(x) for x in v] + [1] * (6 - len(v))
+        return (C.c_int * len(v))(*v)
+
+    rows = []
+    for case, want, rs in zip(cases, ref_y, ref_s):
+        x1, x2 = ref_gpu.case_inputs(case)
+        d1, d2 = api.DeviceBlock.from_numpy(x1), api.DeviceBlock.from_numpy(x2)
+        out = api.DeviceBlock(tuple(case["y"][0]), zero=True)
+
+        def one_call():
+            rc = L._gpu_contract(C.c_void_p(out.ptr), len(case["y"][0]), ia(case["y"][0]), ia(case["y"][1]),
+                                 C.c_void_p(d1.ptr), x1.ndim, ia(case["x1"][0]), ia(case["x1"][1]),
+                                 C.c_void_p(d2.ptr), x2.ndim, ia(case["x2"][0]), ia(case["x2"][1]))
+            assert rc == 0
+            sip.sync()
+
+        one_call()
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            one_call()
+        mine_s = (time.perf_counter() - t0) / args.reps
+        got = out.to_numpy()
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        # the same pair, 64 destinations in one batched launch (what the deferred op stream emits)
+        nb = 64
+        outs = [api.DeviceBlock(tuple(case["y"][0])) for _ in range(nb)]
+        ptrn, ierr = api.get_contraction_ptrn(case["y"][1], case["x1"][1], case["x2"][1])
+        assert ierr == 0
+        api.contract_batched(ptrn, [d1] * nb, [d2] * nb, outs)
+        sip.sync()
+        t0 = time.perf_counter()
+        api.contract_batched(ptrn, [d1] * nb, [d2] * nb, outs)
+        sip.sync()
+        batched_s = (time.perf_counter() - t0) / nb
+        rows.append({"term": case["name"], "gflop_per_pair": case["flops"] / 1e9,
+                     "reference_cuda_ms": rs * 1e3, "reference_cuda_tflops": case["flops"] / rs / 1e12,
+                     "sipgpu_per_call_ms": mine_s * 1e3, "sipgpu_per_call_tflops": case["flops"] / mine_s / 1e12,
+                     "sipgpu_batched_ms_per_pair": batched_s * 1e3, "sipgpu_batched_tflops": case["flops"] / batched_s / 1e12,
+                     "rel_err_vs_reference_cuda": err})
+    print(json.dumps({"what": "pair-level contractions of the synthetic CCSD terms: reference legacy CUDA backend "
+                              "(gpu_super_instructions.cu, unmodified, sm_100a) vs libsipgpu on the same B200",
+                      "o_seg": args.o_seg, "v_seg": args.v_seg, "reps": args.reps, "rows": rows}))
+
+
+if __name__ == "__main__":
+    main()
