@@ -47,7 +47,14 @@ def main():
                       "x1": ([ext[c] for c in t["llab"]], [num[c] for c in t["llab"]]),
                       "x2": ([ext[c] for c in t["rlab"]], [num[c] for c in t["rlab"]]),
                       "flops": 2.0 * float(np.prod([ext[c] for c in labs]))})
-    ref_y, ref_s = ref_gpu.run_cases(cases, timeout=600)
+    # the legacy backend stages every block through fixed 40 MB scratch buffers: the pp-ladder's 50^4 integral block (50 MB)
+    # is beyond it -- reported as such, not measured
+    fits = [all(int(np.prod(c[k][0])) <= ref_gpu.MAX_BLOCK_DOUBLES for k in ("y", "x1", "x2")) for c in cases]
+    got_y, got_s = ref_gpu.run_cases([c for c, ok in zip(cases, fits) if ok], timeout=600)
+    ref_y, ref_s = [], []
+    for ok in fits:
+        ref_y.append(got_y.pop(0) if ok else None)
+        ref_s.append(got_s.pop(0) if ok else None)
 
     sip.init(0)
     api, L = sip.api, sip.api.lib()
@@ -75,7 +82,7 @@ def main():
             one_call()
         mine_s = (time.perf_counter() - t0) / args.reps
         got = out.to_numpy()
-        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want))) if want is not None else None
         # the same pair, 64 destinations in one batched launch (what the deferred op stream emits)
         nb = 64
         outs = [api.DeviceBlock(tuple(case["y"][0])) for _ in range(nb)]
@@ -88,7 +95,9 @@ def main():
         sip.sync()
         batched_s = (time.perf_counter() - t0) / nb
         rows.append({"term": case["name"], "gflop_per_pair": case["flops"] / 1e9,
-                     "reference_cuda_ms": rs * 1e3, "reference_cuda_tflops": case["flops"] / rs / 1e12,
+                     "reference_cuda_ms": rs * 1e3 if rs else None,
+                     "reference_cuda_tflops": case["flops"] / rs / 1e12 if rs else None,
+                     "reference_cuda_note": None if rs else "operand block of 50 MB exceeds the legacy backend's 40 MB scratch buffers",
                      "sipgpu_per_call_ms": mine_s * 1e3, "sipgpu_per_call_tflops": case["flops"] / mine_s / 1e12,
                      "sipgpu_batched_ms_per_pair": batched_s * 1e3, "sipgpu_batched_tflops": case["flops"] / batched_s / 1e12,
                      "rel_err_vs_reference_cuda": err})
