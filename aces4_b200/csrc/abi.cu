@@ -368,16 +368,34 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
 namespace {
 
 int labels_to_ptrn(int drank, const int* dlab, int lrank, const int* llab, int rrank, const int* rlab, int* ptrn) {
-    int aces[96], k = 0;
+    int aces[3 + 96], k = 3;
     if (drank < 0 || lrank < 0 || rrank < 0 || drank + lrank + rrank > 96) return SIPGPU_E_ARG;
+    aces[0] = drank; aces[1] = lrank; aces[2] = rrank;
     for (int i = 0; i < drank; ++i) aces[k++] = dlab[i];
     for (int i = 0; i < lrank; ++i) aces[k++] = llab[i];
     for (int i = 0; i < rrank; ++i) aces[k++] = rlab[i];
-    const int e = get_contraction_ptrn(drank, lrank, rrank, aces, ptrn);
+    // a pardo body repeats a handful of label triples thousands of times: remember the last few conversions
+    struct Memo {
+        int n = 0;
+        int key[3 + 96], ptrn[96];
+    };
+    static Memo memo[4];
+    static int victim = 0;
+    for (const Memo& m : memo)
+        if (m.n == k && !memcmp(m.key, aces, sizeof(int) * k)) {
+            memcpy(ptrn, m.ptrn, sizeof(int) * (lrank + rrank));
+            return SIPGPU_OK;
+        }
+    const int e = get_contraction_ptrn(drank, lrank, rrank, aces + 3, ptrn);
     if (e) {
         set_error("illegal contraction label pattern (get_contraction_ptrn ierr=%d)", e);
         return SIPGPU_E_PATTERN;
     }
+    Memo& m = memo[victim];
+    victim = (victim + 1) & 3;
+    m.n = k;
+    memcpy(m.key, aces, sizeof(int) * k);
+    memcpy(m.ptrn, ptrn, sizeof(int) * (lrank + rrank));
     return SIPGPU_OK;
 }
 

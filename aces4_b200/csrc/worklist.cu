@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <map>
+#include <memory_resource>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -43,6 +44,24 @@ namespace {
 
 enum Kind { K_CONTRACT, K_PERMUTE, K_EW, K_OPAQUE };
 
+// Host allocation is a large share of the cost per recorded op (one operand-pair vector per contraction, one touch list
+// per block address, hash nodes).  Both the recorded stream and the scheduler's working set live in monotonic arenas
+// that are released wholesale: rec_mem() after every flush (all ops are gone by then), sched_mem() at the end of every
+// schedule_and_launch().
+// Each arena starts in a buffer that is allocated once and kept (release() rewinds to it), so steady-state recording does
+// not go to the heap at all; a recording that outgrows it spills into the default resource.
+std::pmr::monotonic_buffer_resource& rec_mem() {
+    static void* buf = malloc((size_t)8 << 20);
+    static std::pmr::monotonic_buffer_resource r(buf, buf ? (size_t)8 << 20 : 0);
+    return r;
+}
+std::pmr::monotonic_buffer_resource& sched_mem() {
+    static void* buf = malloc((size_t)16 << 20);
+    static std::pmr::monotonic_buffer_resource r(buf, buf ? (size_t)16 << 20 : 0);
+    return r;
+}
+using PairVec = std::pmr::vector<Pair>;
+
 struct Op {
     int kind = K_EW;
     bool dead = false;
@@ -54,7 +73,7 @@ struct Op {
     int ptrn[2 * kMaxRank] = {0};
     int lext[kMaxRank] = {0}, rext[kMaxRank] = {0}, dext[kMaxRank] = {0};
     long long ln = 0, rn = 0, dn = 0;
-    std::vector<Pair> pairs;
+    PairVec pairs{&rec_mem()};
     double* D = nullptr;
     // permute
     int rank = 0;
@@ -350,17 +369,19 @@ struct Touch {
     int op;
     int mode;
 };
+using TouchList = std::pmr::vector<Touch>;
+using TouchMap = std::pmr::unordered_map<uintptr_t, TouchList>;
 
 // base addresses whose byte range overlaps the range of a DIFFERENT base (a slab-wide fill over block pointers, a
 // parent array and a block inside it): the per-base touch lists cannot see those conflicts, so the fusion passes
 // leave such blocks alone (the interval map of the levelisation handles them exactly)
 std::unordered_set<uintptr_t> g_aliased;
 
-bool written_between(const std::unordered_map<uintptr_t, std::vector<Touch>>& touch, const void* base, int lo, int hi) {
+bool written_between(const TouchMap& touch, const void* base, int lo, int hi) {
     if (g_aliased.count((uintptr_t)base)) return true;
     auto it = touch.find((uintptr_t)base);
     if (it == touch.end()) return false;
-    const std::vector<Touch>& v = it->second;  // sorted by op index
+    const TouchList& v = it->second;  // sorted by op index
     auto t = std::upper_bound(v.begin(), v.end(), lo, [](int o, const Touch& x) { return o < x.op; });
     for (; t != v.end() && t->op < hi; ++t)
         if ((t->mode & (WL_W | WL_ATOMIC)) && !g.ops[t->op].dead) return true;
@@ -368,8 +389,8 @@ bool written_between(const std::unordered_map<uintptr_t, std::vector<Touch>>& to
 }
 
 // a fused op reads its operands at the position it now occupies: keep the per-base touch lists truthful
-void add_touch(std::unordered_map<uintptr_t, std::vector<Touch>>& touch, const void* base, int op, int mode) {
-    std::vector<Touch>& v = touch[(uintptr_t)base];
+void add_touch(TouchMap& touch, const void* base, int op, int mode) {
+    TouchList& v = touch[(uintptr_t)base];
     auto it = std::lower_bound(v.begin(), v.end(), op, [](const Touch& t, int o) { return t.op < o; });
     if (it != v.end() && it->op == op) it->mode |= mode;
     else v.insert(it, Touch{op, mode});
@@ -384,14 +405,17 @@ int schedule_and_launch() {
     std::vector<WlRange> rs;
 
     // touch lists by base address, program order, one entry per (op, base)
-    std::unordered_map<uintptr_t, std::vector<Touch>> touch;
-    std::unordered_map<uintptr_t, uintptr_t> span;  // base -> end of the longest access through it
+    struct Release {
+        ~Release() { sched_mem().release(); }
+    } release_at_exit;  // declared first: destroyed after every container below
+    TouchMap touch(&sched_mem());
+    std::pmr::unordered_map<uintptr_t, uintptr_t> span(&sched_mem());  // base -> end of the longest access through it
     touch.reserve((size_t)n * 2);
     span.reserve((size_t)n * 2);
     for (int i = 0; i < n; ++i) {
         ranges_of(ops[i], rs);
         for (const WlRange& r : rs) {
-            std::vector<Touch>& v = touch[(uintptr_t)r.p];
+            TouchList& v = touch[(uintptr_t)r.p];
             if (!v.empty() && v.back().op == i) v.back().mode |= r.mode;
             else v.push_back({i, r.mode});
             uintptr_t& e = span[(uintptr_t)r.p];
@@ -423,7 +447,7 @@ int schedule_and_launch() {
         if (p.dead || (p.kind != K_CONTRACT && p.kind != K_PERMUTE) || p.beta != 0.0) continue;
         auto ti = g.temps.find((uintptr_t)p.D);
         if (ti == g.temps.end() || !ti->second.freed || ti->second.n != p.dn || aliased(p.D)) continue;
-        const std::vector<Touch>& tl = touch[(uintptr_t)p.D];
+        const TouchList& tl = touch[(uintptr_t)p.D];
         // [zero fills of the fresh block ...] producer, consumer -- nothing else may touch the temp
         size_t k = 0;
         while (k < tl.size() && tl[k].op < i && ops[tl[k].op].kind == K_EW && ops[tl[k].op].ewop == WL_FILL &&
@@ -473,7 +497,7 @@ int schedule_and_launch() {
     // ---- pass B: chains of accumulating contractions into one destination ----
     for (int i = 0; i < n; ++i) {
         if (ops[i].dead || ops[i].kind != K_CONTRACT || aliased(ops[i].D)) continue;
-        const std::vector<Touch>& tl = touch[(uintptr_t)ops[i].D];
+        const TouchList& tl = touch[(uintptr_t)ops[i].D];
         size_t pos = 0;
         while (pos < tl.size() && tl[pos].op != i) ++pos;
         std::vector<int> run(1, i);
@@ -499,7 +523,12 @@ int schedule_and_launch() {
                 if (m != last) ok = ok && !written_between(touch, pr.L, m, last) && !written_between(touch, pr.R, m, last);
             }
         if (!ok) continue;
-        std::vector<Pair> all;
+        PairVec all(&rec_mem());
+        {
+            size_t total = 0;
+            for (int m : run) total += ops[m].pairs.size();
+            all.reserve(total);  // one allocation: the arena never takes memory back
+        }
         for (int m : run) all.insert(all.end(), ops[m].pairs.begin(), ops[m].pairs.end());
         ops[last].pairs.swap(all);
         ops[last].beta = ops[i].beta;
@@ -521,7 +550,7 @@ int schedule_and_launch() {
     for (int i = 0; i < n; ++i) {
         Op& o = ops[i];
         if (o.dead || (o.kind != K_CONTRACT && o.kind != K_PERMUTE) || o.beta != 1.0 || aliased(o.D)) continue;
-        const std::vector<Touch>& tl = touch[(uintptr_t)o.D];
+        const TouchList& tl = touch[(uintptr_t)o.D];
         int prev = -1;
         for (const Touch& t : tl) {
             if (t.op >= i) break;
@@ -544,7 +573,7 @@ int schedule_and_launch() {
     // A base whose range overlaps no other base's range (almost every block) keeps its state in a flat hash map; only
     // aliased bases (slab-wide ops over blocks, parents of slices) go through the interval map.
     IntervalMap im;
-    std::unordered_map<uintptr_t, Lv> flat;
+    std::pmr::unordered_map<uintptr_t, Lv> flat(&sched_mem());
     flat.reserve(span.size());
     int nlevels = 0;
     auto visit = [&](const WlRange& r, auto f) {
@@ -658,6 +687,7 @@ int wl_flush() {
         g.st_flushes++;
     }
     g.ops.clear();
+    rec_mem().release();  // every recorded op (the only user of this arena) is gone
     release_deferred();
     g.in_flush = false;
     return rc;
@@ -701,8 +731,31 @@ int wl_rec_contract(const int* ptrn, const double* L, int lrank, const int* lext
     if (!L || !R || !D || !ptrn || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank ||
         drank > kMaxRank)
         return SIPGPU_E_ARG;
-    Shape s;
-    SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &s));  // pattern errors surface at the call
+    {   // pattern errors surface at the call; the last few validated (pattern, extents) signatures are remembered, since
+        // a pardo body records the same ones thousands of times
+        struct Memo {
+            int n = 0;
+            int key[3 + 5 * kMaxRank];
+        };
+        static Memo memo[4];
+        static int victim = 0;
+        int key[3 + 5 * kMaxRank], k = 3;
+        key[0] = lrank; key[1] = rrank; key[2] = drank;
+        for (int i = 0; i < lrank + rrank; ++i) key[k++] = ptrn[i];
+        for (int i = 0; i < lrank; ++i) key[k++] = lext[i];
+        for (int i = 0; i < rrank; ++i) key[k++] = rext[i];
+        for (int i = 0; i < drank; ++i) key[k++] = dext[i];
+        bool known = false;
+        for (const Memo& m : memo) known = known || (m.n == k && !memcmp(m.key, key, sizeof(int) * k));
+        if (!known) {
+            Shape s;
+            SIP_TRY(build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &s));
+            Memo& m = memo[victim];
+            victim = (victim + 1) & 3;
+            m.n = k;
+            memcpy(m.key, key, sizeof(int) * k);
+        }
+    }
     Op o;
     o.kind = K_CONTRACT;
     o.lrank = lrank;
@@ -775,7 +828,21 @@ int sipgpu_wl_begin(int flags) {
     }
     const bool dry = (flags & 1) != 0;
     if (!dry) SIP_TRY(ensure_init());
-    g = State();
+    {   // a fresh state, but the op buffer and the plan arrays keep their capacity: growing them again in every pardo costs
+        // more in page faults on fresh memory than recording the ops does
+        std::vector<Op> ops = std::move(g.ops);
+        std::vector<int> lv = std::move(g.last_level), un = std::move(g.last_unit);
+        std::vector<double*> df = std::move(g.deferred_free);
+        ops.clear();
+        lv.clear();
+        un.clear();
+        df.clear();
+        g = State();
+        g.ops = std::move(ops);
+        g.last_level = std::move(lv);
+        g.last_unit = std::move(un);
+        g.deferred_free = std::move(df);
+    }
     g.on = true;
     g.dry = dry;
     if (cfg_max_ops) g.max_ops = cfg_max_ops;
