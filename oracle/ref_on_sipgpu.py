@@ -1,0 +1,94 @@
+"""The reference's own `sip::Block` code (block.cpp, compiled in place) running on the PRODUCT: oracle/_ref/
+libaces4_ref_on_sipgpu.so is the same set of reference objects as libaces4_ref.so, but block.cpp's three calls into
+`libtensordil` -- tensor_block_copy__, tensor_block_slice__, tensor_block_insert__ -- are resolved by libsipgpu.so
+(INTEGRATION.md level 0: link-time replacement, no source change).
+
+TEST INFRASTRUCTURE ONLY.  `run(cases)` executes in a child process (so that the oracle-linked variant of the same
+reference classes, which other tests load, never shares a process with this one):
+    {"op": "transpose", "ext": [...], "permute": [...], "seed": s}      Block::transpose_copy
+    {"op": "extract", "t_ext": [...], "s_ext": [...], "off": [...], "seed": s}   Block::extract_slice
+    {"op": "insert", ...same...}                                         Block::insert_slice
+returns the result arrays, or raises WorkerFailed with the reference's own failure text (sip::fail) -- which is what
+happens on a machine without a GPU: the product reports SIPGPU_E_NODEVICE through `ierr` and block.cpp:252 turns it into
+sip::fail, as for any other backend error.
+"""
+import os
+import pickle
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libaces4_ref_on_sipgpu.so")
+REFERENCE_ROOT = os.environ.get("ACES4_REFERENCE", "/root/reference")
+
+
+class WorkerFailed(RuntimeError):
+    pass
+
+
+def build(force=False):
+    have_src = os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "sip"))
+    product = os.path.join(_HERE, "..", "aces4_b200", "lib", "libsipgpu.so")
+    shim = os.path.join(_HERE, "ref_shim", "aces4_ref_shim.cpp")
+    if have_src and os.path.exists(product) and (force or not os.path.exists(_SO)
+                                                 or os.path.getmtime(_SO) < os.path.getmtime(shim)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref_on_sipgpu", f"REF={REFERENCE_ROOT}"])
+    return _SO if os.path.exists(_SO) else None
+
+
+def available():
+    try:
+        return build() is not None
+    except Exception:
+        return os.path.exists(_SO)
+
+
+def seeded(shape, seed):
+    return np.asfortranarray(np.random.default_rng(seed).uniform(-1.0, 1.0, size=tuple(shape)))
+
+
+def run(cases, timeout=120):
+    if build() is None:
+        raise WorkerFailed("oracle/_ref/libaces4_ref_on_sipgpu.so is not built and the reference checkout is absent")
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "cases.pkl"), os.path.join(tmp, "out.npz")
+        with open(fin, "wb") as f:
+            pickle.dump(cases, f)
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", fin, fout], capture_output=True, text=True,
+                           timeout=timeout)
+        if p.returncode != 0 or not os.path.exists(fout):
+            raise WorkerFailed(f"exit {p.returncode}: {(p.stderr or p.stdout)[-600:]}")
+        z = np.load(fout)
+        return [np.asfortranarray(z[f"y{k}"]) for k in range(len(cases))]
+
+
+def _worker(fin, fout):
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from oracle import ref
+
+    ref._SO = _SO                      # the same ctypes wrappers over the product-linked build
+    ref.build = lambda force=False: _SO
+    out = {}
+    for k, c in enumerate(pickle.load(open(fin, "rb"))):
+        try:
+            if c["op"] == "transpose":
+                y = ref.transpose_copy(seeded(c["ext"], c["seed"]), c["permute"])
+            elif c["op"] == "extract":
+                y = ref.extract_slice(seeded(c["t_ext"], c["seed"]), c["s_ext"], c["off"])
+            else:
+                y = ref.insert_slice(seeded(c["t_ext"], c["seed"]), seeded(c["s_ext"], c["seed"] + 1), c["off"])
+        except RuntimeError as e:
+            print(f"case {k} ({c['op']}): {e}", file=sys.stderr)
+            sys.exit(4)
+        out[f"y{k}"] = y
+    np.savez(fout, **out)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 4 and sys.argv[1] == "--worker":
+        _worker(sys.argv[2], sys.argv[3])
+    else:
+        print(__doc__)

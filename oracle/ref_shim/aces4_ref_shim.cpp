@@ -62,7 +62,12 @@
 #undef private
 
 
-// ---- the oracle's C restatement of the three Fortran kernels block.cpp needs (see header) ----
+// ---- the three Fortran kernels block.cpp calls ----
+// default build (libaces4_ref.so): forwarded to the oracle's C restatement (see header);
+// -DACES4_REF_LINK_SIPGPU (libaces4_ref_on_sipgpu.so): left undefined here and resolved by the PRODUCT, libsipgpu.so,
+// which exports them with the reference's names -- the reference's Block methods then run, unmodified, on the CUDA library
+// (INTEGRATION.md level 0), which is what tests/test_gpu_ref_block_on_sipgpu.py checks.
+#ifndef ACES4_REF_LINK_SIPGPU
 extern "C" {
 void oracle_tensor_block_copy__(const int* nthreads, const int* rank, const int* ext, const int* transp,
                                 const double* in, double* out, int* ierr);
@@ -81,6 +86,7 @@ void tensor_block_insert__(int& nthreads, int& rank, double* t, int* t_ext, doub
     oracle_tensor_block_insert__(&nthreads, &rank, t, t_ext, s, s_ext, beg0, &ierr);
 }
 }
+#endif
 
 namespace {
 

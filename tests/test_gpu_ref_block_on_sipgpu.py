@@ -1,0 +1,63 @@
+"""INTEGRATION.md level 0, executed: the REFERENCE's own `sip::Block::transpose_copy / extract_slice / insert_slice`
+(src/sip/dynamic_data/block.cpp:216-323, compiled in place, unmodified) linked against libsipgpu.so in place of
+libtensordil -- their calls to tensor_block_copy__ / tensor_block_slice__ / tensor_block_insert__ land in the CUDA library
+(oracle/_ref/libaces4_ref_on_sipgpu.so, `make -C oracle ref_on_sipgpu`; child process: oracle/ref_on_sipgpu.py).
+Results must equal the oracle's bit for bit (these operations only move data)."""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    from oracle import ref_on_sipgpu as r
+
+    if not r.available():
+        pytest.skip("oracle/_ref/libaces4_ref_on_sipgpu.so not built and no reference checkout here")
+    return r
+
+
+def cases():
+    out = [  # BasicSial.transpose_tmp, transpose4d_tmp, transpose4d_square_tmp (test_basic_sial.cpp:653-693,1285-1406)
+        {"op": "transpose", "ext": [8, 8, 8], "permute": [2, 0, 1], "seed": 1},
+        {"op": "transpose", "ext": [5, 5, 5, 1], "permute": [2, 1, 0, 3], "seed": 2},
+        {"op": "transpose", "ext": [8, 8, 8, 8], "permute": [2, 1, 0, 3], "seed": 3},
+        {"op": "transpose", "ext": [50, 20, 50, 20], "permute": [2, 3, 0, 1], "seed": 4},   # a bench-sized block (8 MB)
+    ]
+    for k, p in enumerate(itertools.permutations(range(4))):
+        out.append({"op": "transpose", "ext": [8, 5, 9, 6], "permute": list(p), "seed": 10 + k})
+    for k, (ext, p) in enumerate((([7, 5], [1, 0]), ([4, 6, 3], [1, 2, 0]), ([3, 2, 4, 2, 3], [4, 2, 0, 3, 1]),
+                                  ([2, 3, 2, 2, 3, 2], [5, 3, 1, 4, 0, 2]))):
+        out.append({"op": "transpose", "ext": ext, "permute": p, "seed": 50 + k})
+    rnd = np.random.default_rng(7)
+    for rank in range(1, 7):
+        for _ in range(3):
+            t_ext = [int(x) for x in rnd.integers(2, 7, size=rank)]
+            s_ext = [int(rnd.integers(1, e + 1)) for e in t_ext]
+            off = [int(rnd.integers(0, e - s + 1)) for e, s in zip(t_ext, s_ext)]
+            seed = int(rnd.integers(1, 1 << 30))
+            out.append({"op": "extract", "t_ext": t_ext, "s_ext": s_ext, "off": off, "seed": seed})
+            out.append({"op": "insert", "t_ext": t_ext, "s_ext": s_ext, "off": off, "seed": seed})
+    return out
+
+
+def test_reference_block_methods_run_on_the_cuda_library(rb, oracle):
+    cs = cases()
+    try:
+        got = rb.run(cs, timeout=120)
+    except rb.WorkerFailed as e:
+        pytest.fail(f"the reference's Block code failed on libsipgpu.so: {e}")
+    for c, y in zip(cs, got):
+        if c["op"] == "transpose":
+            want = oracle.block_copy(rb.seeded(c["ext"], c["seed"]), [1] + [p + 1 for p in c["permute"]])
+        elif c["op"] == "extract":
+            want, ierr = oracle.block_slice(rb.seeded(c["t_ext"], c["seed"]), c["s_ext"], c["off"])
+            assert ierr == 0
+        else:
+            want, ierr = oracle.block_insert(rb.seeded(c["t_ext"], c["seed"]), rb.seeded(c["s_ext"], c["seed"] + 1), c["off"])
+            assert ierr == 0
+        assert np.array_equal(y, want), c
+    print(f"{len(cs)} sip::Block calls (reference code) served by libsipgpu.so, all bit-identical to the oracle")

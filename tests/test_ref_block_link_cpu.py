@@ -1,0 +1,40 @@
+"""Link-level drop-in check, no GPU needed: the reference's own block.cpp (compiled in place) links against libsipgpu.so
+with nothing left undefined -- the product exports tensor_block_copy__/slice__/insert__ under the reference's names and
+calling convention (tensor_ops_c_prototypes.h:41-178) -- and, on a machine without a GPU, a call fails the way the
+reference fails for any backend error: non-zero `ierr` -> CHECK -> sip::fail (block.cpp:252), never a silent CPU result."""
+import ctypes as C
+import subprocess
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import aces4_b200 as s
+
+    s.build()
+    from oracle import ref_on_sipgpu as r
+
+    if not r.available():
+        pytest.skip("no reference checkout and no prebuilt oracle/_ref on this machine")
+    return r
+
+
+def test_reference_block_objects_link_against_the_product(rb):
+    so = rb.build()
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout
+    for sym in ("tensor_block_copy__", "tensor_block_slice__", "tensor_block_insert__"):
+        assert f"U {sym}" in undefined                      # imported, not defined by the test library itself
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True, check=True).stdout
+    assert "libsipgpu.so" in needed and "liboracle" not in needed
+    C.CDLL(so)                                              # every symbol resolves at load time (built with --no-undefined)
+
+
+def test_without_a_gpu_the_reference_fails_loudly_through_its_own_check(rb):
+    import aces4_b200 as s
+
+    if s.api.lib().sipgpu_init(-1) == 0:
+        pytest.skip("a GPU is present: the success path is tests/test_gpu_ref_block_on_sipgpu.py")
+    with pytest.raises(rb.WorkerFailed) as e:
+        rb.run([{"op": "transpose", "ext": [3, 4, 5], "permute": [2, 0, 1], "seed": 1}])
+    assert "error returned from tensor_block_copy_" in str(e.value)
