@@ -9,6 +9,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_sial_ops_device.cpp")
 
 
+# the public block-traffic methods of SialOpsParallel (src/sip/worker/sial_ops_parallel.h:47-73)
+SIAL_OPS_METHODS = ["sip_barrier", "create_distributed", "restore_distributed", "delete_distributed", "get", "put_replace",
+                    "put_accumulate", "put_initialize", "put_increment", "put_scale", "destroy_served", "request", "prequest",
+                    "prepare", "prepare_accumulate", "collective_sum", "assert_same", "broadcast_static", "set_persistent",
+                    "restore_persistent", "end_program"]
+
+
+def test_method_set_covers_sial_ops_parallel():
+    """every public method of the reference's SialOpsParallel has a same-named method in SialOpsDevice; where the
+    reference checkout is present the list above is re-derived from its header"""
+    import re
+
+    mine = open(os.path.join(ROOT, "include", "sial_ops_device.hpp")).read()
+    for name in SIAL_OPS_METHODS:
+        assert re.search(r"\b" + name + r"\s*\(", mine), name
+    ref = "/root/reference/src/sip/worker/sial_ops_parallel.h"
+    if os.path.exists(ref):
+        text = open(ref).read()
+        public = text[text.index("void sip_barrier"): text.index("void end_program")] + "void end_program();"
+        names = re.findall(r"^\s*(?:void|bool)\s+(\w+)\s*\(", public, flags=re.M)
+        assert names == SIAL_OPS_METHODS, names
+
+
 def test_header_compiles_standalone():
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), SRC])
 
