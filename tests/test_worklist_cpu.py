@@ -268,3 +268,27 @@ def test_random_streams_respect_all_hazards(sip, seed):
     assert st["recorded"] == len(r.ops)
     check_plan(r.ops, level, unit)
     assert st["scheduled"] <= st["recorded"] and st["levels"] >= 1
+
+
+def test_lccd_pardo_stream_dry_recording_counts_and_host_cost(sip, tmp_path):
+    """scripts/micro/wl_dry_bench.cpp: the op-at-a-time stream of two LCCD pardo bodies (34 992 ops at 3 x 6 segments)
+    recorded in dry mode from C++.  The fusion counts are exact properties of that stream: every `T = L*R; D += T` pair of
+    hhladder and both permuted accumulates' producers of phladder are forwarded (8 748 = 3 888 + 4 860 temps elided) and
+    hhladder's 324 destinations each become one chain.  The host cost per recorded op is asserted loosely (it is a
+    few tenths of a microsecond; the bound only catches an accidental return to per-op heap traffic or quadratic passes)."""
+    import json
+    import os
+    import subprocess
+
+    import aces4_b200
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.dirname(aces4_b200.lib_path())
+    exe = str(tmp_path / "wl_dry_bench")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "scripts", "micro", "wl_dry_bench.cpp"),
+                           "-I", os.path.join(root, "include"), "-L", lib_dir, "-lsipgpu", f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    out = json.loads(subprocess.run([exe, "16", "3", "16", "6", "3"], capture_output=True, text=True, check=True).stdout)
+    assert out["ops_recorded"] == 34992
+    assert out["fused_accumulates"] == 8748 and out["chains"] == 324
+    assert out["ops_scheduled"] < out["ops_recorded"]
+    assert out["us_per_op"] < 5.0, out
