@@ -39,7 +39,11 @@ enum {
  * kernels run, results are staged back; the call returns when the host buffers are valid.
  * `nthreads` is accepted and ignored.  ierr: 0 = success, otherwise the reference's own codes where it
  * defines them, else SIPGPU_E_*.
+ * A translation unit of aces4 that already includes tensor_ops_c_prototypes.h (block.cpp, interpreter.cpp) has these ten
+ * names declared with C++ reference parameters (`int&` -- the same ABI, another C++ type): it defines
+ * SIPGPU_NO_TENSORDIL_PROTOTYPES before including this header (INTEGRATION.md level 1).
  * --------------------------------------------------------------------------------------------- */
+#ifndef SIPGPU_NO_TENSORDIL_PROTOTYPES
 long long tensor_size_by_shape_(int* num_dim, int* dims, int* ierr);           /* tensor_dil_omp.F90:65-85   */
 void get_contraction_ptrn_(int* drank, int* lrank, int* rrank, int* aces_ptrn, /* tensor_dil_omp.F90:87-142  */
                            int* my_ptrn, int* ierr);
@@ -57,6 +61,7 @@ void tensor_block_copy__(int* nthreads, int* rank, int* ext, int* dim_transp, do
 void tensor_block_contract__(int* nthreads, int* contr_ptrn, double* ltens, int* lrank, int* lext,    /* F90:662-796 */
                              double* rtens, int* rrank, int* rext, double* dtens, int* drank, int* dext,
                              int* ierr);
+#endif /* SIPGPU_NO_TENSORDIL_PROTOTYPES */
 
 /* ---------------------------------------------------------------------------------------------
  * Boundary 2 -- the device-block ABI (DEVICE pointers, resident blocks).  Same names and arguments as

@@ -8,6 +8,10 @@ reference classes, which other tests load, never shares a process with this one)
     {"op": "transpose", "ext": [...], "permute": [...], "seed": s}      Block::transpose_copy
     {"op": "extract", "t_ext": [...], "s_ext": [...], "off": [...], "seed": s}   Block::extract_slice
     {"op": "insert", ...same...}                                         Block::insert_slice
+    {"op": "gpu_block", "ext": [...], "fill": x, "scale": f}             level 1 (libaces4_ref_l1_on_sipgpu.so, reference
+                                                                         built with HAVE_CUDA): Block::new_gpu_block ->
+                                                                         gpu_fill -> gpu_scale -> gpu_copy_data, read back;
+                                                                         result = stack of (fresh, filled*scale, copy)
 returns the result arrays, or raises WorkerFailed with the reference's own failure text (sip::fail) -- which is what
 happens on a machine without a GPU: the product reports SIPGPU_E_NODEVICE through `ierr` and block.cpp:252 turns it into
 sip::fail, as for any other backend error.
@@ -22,6 +26,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libaces4_ref_on_sipgpu.so")
+_SO_L1 = os.path.join(_HERE, "_ref", "libaces4_ref_l1_on_sipgpu.so")   # + HAVE_CUDA: the device half of sip::Block (level 1)
 REFERENCE_ROOT = os.environ.get("ACES4_REFERENCE", "/root/reference")
 
 
@@ -35,8 +40,8 @@ def build(force=False):
     shim = os.path.join(_HERE, "ref_shim", "aces4_ref_shim.cpp")
     if have_src and os.path.exists(product) and (force or not os.path.exists(_SO)
                                                  or os.path.getmtime(_SO) < os.path.getmtime(shim)):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref_on_sipgpu", f"REF={REFERENCE_ROOT}"])
-    return _SO if os.path.exists(_SO) else None
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref_on_sipgpu", "ref_l1", f"REF={REFERENCE_ROOT}"])
+    return _SO if os.path.exists(_SO) and os.path.exists(_SO_L1) else None
 
 
 def available():
@@ -69,12 +74,28 @@ def _worker(fin, fout):
     sys.path.insert(0, os.path.dirname(_HERE))
     from oracle import ref
 
-    ref._SO = _SO                      # the same ctypes wrappers over the product-linked build
-    ref.build = lambda force=False: _SO
+    cases = pickle.load(open(fin, "rb"))
+    level1 = any(c["op"] == "gpu_block" for c in cases)
+    so = _SO_L1 if level1 else _SO
+    ref._SO = so                       # the same ctypes wrappers over the product-linked build
+    ref.build = lambda force=False: so
     out = {}
-    for k, c in enumerate(pickle.load(open(fin, "rb"))):
+    for k, c in enumerate(cases):
         try:
-            if c["op"] == "transpose":
+            if c["op"] == "gpu_block":
+                import ctypes as C
+
+                n = int(np.prod(c["ext"]))
+                bufs = np.full((3, n), np.nan)
+                dp = C.POINTER(C.c_double)
+                rc = ref.lib().aces4ref_gpu_block_roundtrip(len(c["ext"]), ref._ia(c["ext"]), C.c_double(c["fill"]),
+                                                            C.c_double(c["scale"]), bufs[0].ctypes.data_as(dp),
+                                                            bufs[1].ctypes.data_as(dp), bufs[2].ctypes.data_as(dp))
+                if rc != 0:
+                    raise RuntimeError(f"aces4ref_gpu_block_roundtrip rc={rc} (2: _gpu_allocate gave no device block): "
+                                       + ref.lib().aces4ref_last_error().decode())
+                y = bufs
+            elif c["op"] == "transpose":
                 y = ref.transpose_copy(seeded(c["ext"], c["seed"]), c["permute"])
             elif c["op"] == "extract":
                 y = ref.extract_slice(seeded(c["t_ext"], c["seed"]), c["s_ext"], c["off"])

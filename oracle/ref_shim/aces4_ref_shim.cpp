@@ -60,6 +60,9 @@
 #include "interpreter.h"
 #include "sip_interface.h"
 #undef private
+#ifdef HAVE_CUDA
+#include "gpu_super_instructions.h"   // level-1 build: ref_shim/level1/gpu_super_instructions.h -> sipgpu.h
+#endif
 
 
 // ---- the three Fortran kernels block.cpp calls ----
@@ -264,6 +267,39 @@ long long aces4ref_block_number(int rank, const int* nseg, const int* lower, con
     });
     return num;
 }
+
+#ifdef HAVE_CUDA
+// ---- INTEGRATION.md level 1: the device half of sip::Block (block.cpp:377-429, compiled with HAVE_CUDA against the
+// replacement gpu_super_instructions.h of ref_shim/level1) on the product's `_gpu_*` entry points.
+// new_gpu_block (zero-filled by _gpu_allocate) -> gpu_fill(fill) -> gpu_scale(scale) -> a second block gpu_copy_data's it;
+// both are read back with the product's _gpu_device_to_host; returns 0, or 2 when no device block could be allocated. ----
+int aces4ref_gpu_block_roundtrip(int rank, const int* ext, double fill, double scale, double* fresh, double* filled_scaled,
+                                 double* copied) {
+    int rc = 0;
+    int g = guarded([&] {
+        sip::Block* a = sip::Block::new_gpu_block(make_shape(rank, ext));
+        sip::Block* b = sip::Block::new_gpu_block(make_shape(rank, ext));
+        if (!a->get_gpu_data() || !b->get_gpu_data() || !a->is_on_gpu() || a->is_on_host()) {
+            rc = 2;
+        } else {
+            const int n = a->size();
+            if (_gpu_device_to_host(fresh, a->get_gpu_data(), n)) rc = 3;
+            a->gpu_fill(fill);
+            a->gpu_scale(scale);
+            b->gpu_copy_data(a);
+            if (_gpu_device_to_host(filled_scaled, a->get_gpu_data(), n)) rc = 3;
+            if (_gpu_device_to_host(copied, b->get_gpu_data(), n)) rc = 3;
+            a->free_gpu_data();
+            if (a->get_gpu_data() || a->is_on_gpu()) rc = 4;
+            a->allocate_gpu_data();                      // a fresh device buffer for the same block
+            if (!a->get_gpu_data() || !a->is_on_gpu()) rc = 4;
+        }
+        delete a;   // ~Block frees the device buffers through _gpu_free
+        delete b;
+    });
+    return g ? 1 : rc;
+}
+#endif
 
 // ---- .dat files through the reference's SetupReader ----
 // Text dump (operator<< of SetupReader) of a setup file into buf; returns the length needed (excluding NUL) or -1.

@@ -38,3 +38,24 @@ def test_without_a_gpu_the_reference_fails_loudly_through_its_own_check(rb):
     with pytest.raises(rb.WorkerFailed) as e:
         rb.run([{"op": "transpose", "ext": [3, 4, 5], "permute": [2, 0, 1], "seed": 1}])
     assert "error returned from tensor_block_copy_" in str(e.value)
+
+
+def test_level1_reference_block_gpu_methods_link_against_the_product(rb):
+    """INTEGRATION.md level 1 at link level: block.cpp compiled with HAVE_CUDA against the replacement
+    gpu_super_instructions.h (oracle/ref_shim/level1: three lines around sipgpu.h) imports the `_gpu_*` names unmangled
+    and libsipgpu.so provides all of them."""
+    rb.build()
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", rb._SO_L1], capture_output=True, text=True, check=True).stdout
+    for sym in ("_gpu_allocate", "_gpu_free", "_gpu_double_memset", "_gpu_selfmultiply", "_gpu_device_to_device"):
+        assert f"U {sym}\n" in undefined, sym
+    C.CDLL(rb._SO_L1)
+
+
+def test_level1_without_a_gpu_no_device_block_is_handed_out(rb):
+    import aces4_b200 as s
+
+    if s.api.lib().sipgpu_init(-1) == 0:
+        pytest.skip("a GPU is present: the success path is tests/test_gpu_ref_block_on_sipgpu.py")
+    with pytest.raises(rb.WorkerFailed) as e:
+        rb.run([{"op": "gpu_block", "ext": [4, 3], "fill": 2.0, "scale": 0.5}])
+    assert "rc=2" in str(e.value)
