@@ -59,3 +59,18 @@ def test_level1_without_a_gpu_no_device_block_is_handed_out(rb):
     with pytest.raises(rb.WorkerFailed) as e:
         rb.run([{"op": "gpu_block", "ext": [4, 3], "fill": 2.0, "scale": 0.5}])
     assert "rc=2" in str(e.value)
+
+
+def test_level1_interpreter_compiles_against_the_replacement_header(rb):
+    """interpreter.cpp (reference, unmodified) with HAVE_CUDA and the level-1 replacement of gpu_super_instructions.h:
+    its `_init_gpu(&devid, &rank)` call (interpreter.cpp:84-88) type-checks against include/sipgpu.h"""
+    import os
+
+    src = os.path.join(rb.REFERENCE_ROOT, "src", "sip")
+    if not os.path.isdir(src):
+        pytest.skip("no reference checkout on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = ["-I" + os.path.join(root, "oracle", "ref_shim", "level1"), "-I" + os.path.join(root, "include")]
+    inc += ["-I" + os.path.join(src, d) for d in ("core", "cuda", "dynamic_data", "mpi", "setup", "static_data",
+                                                   "super_instructions", "tensor_algebra", "worker", ".")]
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-w", *inc, os.path.join(src, "worker", "interpreter.cpp")])
