@@ -40,6 +40,16 @@ def test_every_declared_symbol_is_exported(sip):
         assert hasattr(L, name), f"{name} declared in include/sipgpu.h but not exported by libsipgpu.so"
 
 
+def test_nothing_but_the_declared_abi_is_exported(sip):
+    """the dynamic symbol table is exactly include/sipgpu.h (aces4_b200/csrc/exports.map): no internal C++ symbol leaks"""
+    import subprocess
+    import aces4_b200
+
+    out = subprocess.check_output(["nm", "-D", "--defined-only", aces4_b200.lib_path()]).decode()
+    exported = {ln.split()[-1] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] in "TBD"}
+    assert exported == set(header_symbols()), (sorted(exported - set(header_symbols())), sorted(set(header_symbols()) - exported))
+
+
 def test_library_links_no_oracle():
     # the product must not link, load or call anything under oracle/
     import subprocess
