@@ -25,6 +25,14 @@ import sys
 import threading
 import time
 
+# The CPU arm runs two thread pools in turn -- the oracle's OpenMP loops (permutes, as in the reference's Fortran) and
+# OpenBLAS's own threads (dgemm).  With libgomp's default active wait policy the idle OpenMP workers spin through the
+# first milliseconds of every dgemm and take the cores away from it (measured: a pp-ladder block pair 82 ms vs 35 ms).
+# A reference build has one OpenMP runtime for both and no such conflict, so the baseline must not have it either.
+# Must be set before libgomp is loaded (torch, liboracle.so), hence here.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -252,24 +252,47 @@ void oracle_tensor_block_copy__(const int* nthreads, const int* rank_, const int
     long long n = block_size(rank, ext);
     if (trivial) { memcpy(out, in, sizeof(double) * (size_t)n); return; }
     int n2o[ORACLE_MAX_RANK + 2];
-    long long bout[ORACLE_MAX_RANK + 1], b = 1;
+    long long so[ORACLE_MAX_RANK], si[ORACLE_MAX_RANK], b = 1;   /* stride of INPUT dimension i in the output / in the input */
     for (int i = 1; i <= rank; ++i) n2o[transp[i]] = i;
-    for (int i = 1; i <= rank; ++i) { bout[n2o[i]] = b; b *= ext[n2o[i] - 1]; } /* F90:496 */
-    /* walk the input linearly; the last (slowest) input dimension is split over threads */
-    long long slow = ext[rank - 1], inner = n / slow;
+    for (int i = 1; i <= rank; ++i) { so[n2o[i] - 1] = b; b *= ext[n2o[i] - 1]; } /* F90:496 */
+    b = 1;
+    for (int i = 0; i < rank; ++i) { si[i] = b; b *= ext[i]; }
+    /* The Fortran routine is the same assignment under a cache-aware schedule ("regardless of the index permutation,
+     * it should be only two times slower than the direct copy", F90:441-442) and runs under OpenMP.  The restatement
+     * keeps that property, so that the CPU baseline timed by bench.py is not handicapped: the dimension that is fastest in
+     * the input (dimension 1) and the input dimension that becomes fastest in the output are walked in 32 x 32 tiles --
+     * both sides touch whole cache lines inside a tile -- and the remaining dimensions form the outer, parallel loop. */
+    const int dout = n2o[1] - 1;   /* input dimension that lands in output position 1 */
+    if (dout == 0) {               /* leading dimension stays in front: contiguous runs on both sides */
+        const long long run = ext[0], nouter = n / run;
 #pragma omp parallel for schedule(static) if (n > 65536)
-    for (long long s = 0; s < slow; ++s) {
-        int im[ORACLE_MAX_RANK];
-        for (int i = 0; i < rank; ++i) im[i] = 0;
-        long long lout = s * bout[rank];
-        const double* src = in + s * inner;
-        for (long long li = 0; li < inner; ++li) {
-            out[lout] = src[li];
-            for (int i = 0; i < rank - 1; ++i) {
-                if (im[i] + 1 < ext[i]) { im[i]++; lout += bout[i + 1]; break; }
-                lout -= (long long)im[i] * bout[i + 1];
-                im[i] = 0;
-            }
+        for (long long o = 0; o < nouter; ++o) {
+            long long rem = o, off = 0;
+            for (int i = 1; i < rank; ++i) { off += (rem % ext[i]) * so[i]; rem /= ext[i]; }
+            memcpy(out + off, in + o * run, sizeof(double) * (size_t)run);
+        }
+        return;
+    }
+    enum { TB = 32 };
+    const long long e0 = ext[0], e1 = ext[dout];
+    const long long nt0 = (e0 + TB - 1) / TB, nt1 = (e1 + TB - 1) / TB, nouter = n / (e0 * e1), total = nouter * nt0 * nt1;
+#pragma omp parallel for schedule(static) if (n > 65536)
+    for (long long w = 0; w < total; ++w) {
+        const long long t0 = w % nt0, t1 = (w / nt0) % nt1;
+        long long rem = w / (nt0 * nt1), bi = 0, bo = 0;
+        for (int i = 1; i < rank; ++i) {
+            if (i == dout) continue;
+            const long long x = rem % ext[i];
+            rem /= ext[i];
+            bi += x * si[i];
+            bo += x * so[i];
+        }
+        const long long i_lo = t0 * TB, i_hi = i_lo + TB < e0 ? i_lo + TB : e0;
+        const long long j_lo = t1 * TB, j_hi = j_lo + TB < e1 ? j_lo + TB : e1;
+        for (long long i = i_lo; i < i_hi; ++i) {
+            const double* src = in + bi + i;
+            double* dst = out + bo + i * so[0];
+            for (long long j = j_lo; j < j_hi; ++j) dst[j] = src[j * si[dout]];   /* so[dout] == 1 */
         }
     }
 }
