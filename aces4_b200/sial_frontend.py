@@ -17,9 +17,10 @@ Those calls go to a *backend*:
 
 Supported statements (case-insensitive keywords, `#` comments):
     pardo i, j, ...  /  endpardo ...        do i / enddo i        where i < j   (<, <=, >, >=, ==, != on indices/ints)
-    request|get A[...]                      put|prepare A[...] = T[...]     put|prepare A[...] += T[...]
+    request|get A[...]       put|prepare A[...] = T[...]      put|prepare A[...] += T[...]     put|prepare A[...] = number
     T[...] = number      T[...] = X[...]    T[...] = X[...] * Y[...]        T[...] += X[...]     T[...] -= X[...]
-    T[...] *= number     s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
+    T[...] = X[...] ^ Y[...] (outer product: the same opcode)               T[...] *= number     T[...] *= s
+    s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
     execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
 Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `aoindex mu = 1: norb`; arrays
 `served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else raises SialSyntaxError.
@@ -113,6 +114,9 @@ class Program:
                 raise SialSyntaxError("bad request")
             return ("request", m.group(1).lower(), _labels(m.group(2)))
         if kw in ("put", "prepare"):
+            m = re.match(r"\w+\s+" + _REF + r"\s*=\s*(" + _NUM + r")\s*$", line)
+            if m:
+                return ("put_init", m.group(1).lower(), _labels(m.group(2)), float(m.group(3).lower().replace("d", "e")))
             m = re.match(r"\w+\s+" + _REF + r"\s*(\+?=)\s*" + _REF + r"\s*$", line)
             if not m:
                 raise SialSyntaxError("bad put/prepare")
@@ -134,7 +138,7 @@ class Program:
         m = re.match(_REF + r"\s*(\+=|-=|\*=|=)\s*(.+)$", line)
         if m:
             name, labs, op, rhs = m.group(1).lower(), _labels(m.group(2)), m.group(3), m.group(4).strip()
-            mm = re.match(_REF + r"\s*\*\s*" + _REF + r"\s*$", rhs)
+            mm = re.match(_REF + r"\s*[\*\^]\s*" + _REF + r"\s*$", rhs)   # `^` (outer product) is the same opcode
             if mm and op == "=":
                 return ("contract", name, labs, mm.group(1).lower(), _labels(mm.group(2)), mm.group(3).lower(),
                         _labels(mm.group(4)))
@@ -144,6 +148,8 @@ class Program:
                         -1.0 if op == "-=" else 1.0)
             if re.match(_NUM + r"$", rhs) and op in ("=", "*="):
                 return ("fill" if op == "=" else "scale", name, labs, float(rhs.lower().replace("d", "e")))
+            if re.match(r"[A-Za-z_]\w*$", rhs) and op == "*=":
+                return ("scale_by", name, labs, rhs.lower())
             raise SialSyntaxError("unsupported block statement")
         # scalar statements
         m = re.match(r"(\w+)\s*(\+=|-=|\*=|=)\s*(.+)$", line)
@@ -278,6 +284,14 @@ class Walker:
     def _x_scale(self, name, labs, f):
         self.be.scale(self._write(name, labs), f)
 
+    def _x_scale_by(self, name, labs, scalar):
+        if scalar not in self.scalars:
+            raise SialSyntaxError(f"undeclared scalar {scalar}")
+        self.be.scale(self._write(name, labs), self.be.value(self.scalars[scalar]))
+
+    def _x_put_init(self, arr, alabs, v):
+        self.be.put_initialize(arr, self._segs_of(alabs), self._shape(alabs), v)
+
     def _x_assign(self, name, labs, src, slabs, _sign):
         s, sl = self._read(src, slabs)
         self.be.copy(self._write(name, labs), labs, s, sl)
@@ -411,6 +425,9 @@ class DeviceBackend:
 
     def put_accumulate(self, arr, segs, b):
         self.arrays[arr].put_accumulate(segs, b)
+
+    def put_initialize(self, arr, segs, shape, v):
+        self.arrays[arr].put_initialize(segs, v)
 
     def execute(self, fname, blocks, segs, kinds, bare):
         if fname == "energy_denominator_rhf":

@@ -77,6 +77,9 @@ class OracleBackend:
             A[segs] = np.zeros(b.shape, order="F")
         A[segs] = self.o.block_add(A[segs], b.a, 1.0)[0]
 
+    def put_initialize(self, arr, segs, shape, v):
+        self.arrays[arr][segs] = np.full(shape, float(v), order="F")
+
     def execute(self, fname, blocks, segs, kinds, bare):
         assert fname == "energy_denominator_rhf"
         assert self.o.si_energy_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, self.ranges) == 0

@@ -143,3 +143,65 @@ def test_where_clause_and_iteration_counter(oracle):
     order = [(i, j) for j in (1, 2, 3) for i in (1, 2, 3) if i <= j]
     for r in range(3):
         assert seen[r] == sorted(order[r::3])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CCSD-shaped statements: outer products, put = number, put += into a rank-2 array, block *= scalar variable
+# ---------------------------------------------------------------------------------------------------------------
+CCSD = open(os.path.join(HERE, "golden", "ccsd_tau_singles.sialx")).read()
+CCSD_KINDS = {"t2old_ab": "vovo", "tau_ab": "vovo", "vpiqj": "vovo", "t1a_old": "vo", "t1a_new": "vo", "fme_a": "vo"}
+
+
+def make_ccsd_arrays(oracle, segs, seed=0xACE54):
+    arrays = {}
+    for tag, (name, kind) in enumerate(CCSD_KINDS.items(), 1):
+        blocks = {}
+        nseg = [len(segs[k]) for k in kind]
+        for idx in np.ndindex(*nseg):
+            shape = tuple(segs[k][i] for k, i in zip(kind, idx))
+            number = 0
+            for p in range(len(kind)):
+                number = number * nseg[p] + idx[p]
+            filled = name in ("t2old_ab", "vpiqj", "t1a_old", "fme_a")
+            blocks[tuple(i + 1 for i in idx)] = (oracle.fill_hash(shape, seed, (tag << 40) | number, 0.1) if filled
+                                                 else np.full(shape, np.nan, order="F"))
+        arrays[name] = blocks
+    return arrays
+
+
+def test_parser_reads_the_ccsd_fragment():
+    p = Program(CCSD)
+    kinds = [s[0] for s in p.body]
+    assert kinds.count("pardo") == 4 and "sset" in kinds and kinds[-1] == "collective"
+    tau = p.body[3][2]                                   # the tau pardo (after `half = 0.5`)
+    assert [s[0] for s in tau] == ["request", "request", "request", "contract", "assign", "add", "put"]
+    assert tau[3][3:] == ("t1a_old", ("a", "i"), "t1a_old", ("b", "j"))          # `^` parsed as a contraction
+    assert p.body[0][2][0] == ("put_init", "t1a_new", ("a", "i"), 0.0)
+    singles = p.body[5][2][0][2][0][2]                   # pardo a,i / do b / do j
+    assert ("scale_by", "tai", ("a", "i"), "half") in singles
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_ccsd_fragment_on_the_oracle_backend_matches_dense_einsum(oracle, world):
+    segs = {"o": [3, 2], "v": [4, 3, 2]}
+    arrays = make_ccsd_arrays(oracle, segs)
+    T2 = dense(arrays["t2old_ab"], "vovo", segs)
+    V = dense(arrays["vpiqj"], "vovo", segs)
+    t1 = dense(arrays["t1a_old"], "vo", segs)
+    F = dense(arrays["fme_a"], "vo", segs)
+    prog = Program(CCSD)
+    esum = 0.0
+    # every "worker" walks the same program on the shared arrays, one barrier section at a time (the sections of this
+    # program are separated by barriers, so running the workers one after the other per program is NOT equivalent; the
+    # oracle backend is sequential, so emulate the sections by running each pardo for all ranks before the next one)
+    walkers = [Walker(prog, OracleBackend(oracle, arrays), segs, rank=r, world=world) for r in range(world)]
+    for st in prog.body:
+        for w in walkers:
+            w._block([st])
+    for w in walkers:
+        esum += w.be.value(w.scalars["esum"])
+    tau = T2 + np.einsum("ai,bj->aibj", t1, t1)
+    assert np.allclose(dense(arrays["tau_ab"], "vovo", segs), tau, rtol=1e-13, atol=1e-15)
+    assert np.allclose(dense(arrays["t1a_new"], "vo", segs), 0.5 * np.einsum("aibj,bj->ai", tau, F), rtol=1e-12, atol=1e-15)
+    e_ref = np.einsum("aibj,aibj->", 2.0 * V - np.transpose(V, (0, 3, 2, 1)), tau)
+    assert abs(esum - e_ref) <= 1e-12 * abs(e_ref)
