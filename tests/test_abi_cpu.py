@@ -50,6 +50,24 @@ def test_nothing_but_the_declared_abi_is_exported(sip):
     assert exported == set(header_symbols()), (sorted(exported - set(header_symbols())), sorted(set(header_symbols()) - exported))
 
 
+def test_header_is_plain_c99_and_links_from_c(sip, tmp_path):
+    """include/sipgpu.h is what a C or Fortran (iso_c_binding) caller sees: it must be valid C99 on its own, with and
+    without the libtensordil prototypes, and a C program must link against the library"""
+    import subprocess
+    import aces4_b200
+
+    src = tmp_path / "client.c"
+    src.write_text('#include "sipgpu.h"\n#include <stdio.h>\nint main(void) { printf("%d\\n", sipgpu_device()); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-DSIPGPU_NO_TENSORDIL_PROTOTYPES",
+                           "-I", inc, str(src)])
+    lib_dir = os.path.dirname(aces4_b200.lib_path())
+    exe = tmp_path / "client"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-L", lib_dir, "-lsipgpu", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+    assert subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip() in ("-1", "0")
+
+
 def test_library_links_no_oracle():
     # the product must not link, load or call anything under oracle/
     import subprocess
