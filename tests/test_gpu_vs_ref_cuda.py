@@ -109,6 +109,32 @@ def permute_cases():
     return cases
 
 
+def config4_cases():
+    """BASELINE.json config 4 shapes the legacy backend can hold (blocks <= 40 MB: segment sizes 16..40): rank-4 results with
+    two contracted indices under shuffled label orders, the ragged case (13, 30, 50, 64) and EOM-style rank-5 blocks with a
+    leading extent-1 index"""
+    import random
+
+    pyrng = random.Random(2024)
+    cases = []
+    for s in (16, 24, 32, 40):
+        for trial in range(4):
+            fl, fr, cc = [1, 2], [3, 4], [5, 6]
+            llab, rlab, dlab = fl + cc, fr + cc, fl + fr
+            pyrng.shuffle(llab), pyrng.shuffle(rlab), pyrng.shuffle(dlab)
+            cases.append({"kind": "contract", "seed": 3000 + 10 * s + trial, "where": f"s={s}",
+                          "y": ([s] * 4, dlab), "x1": ([s] * 4, llab), "x2": ([s] * 4, rlab)})
+    ext = {1: 13, 2: 30, 3: 50, 4: 64, 5: 9, 6: 11}
+    for trial, (dlab, llab, rlab) in enumerate((([1, 2, 3, 4], [1, 5, 2, 6], [6, 3, 5, 4]), ([4, 3, 2, 1], [5, 1, 6, 2], [3, 5, 4, 6]),
+                                                ([2, 4, 1, 3], [6, 5, 2, 1], [4, 6, 3, 5]))):
+        cases.append({"kind": "contract", "seed": 3500 + trial, "where": "ragged",
+                      "y": ([ext[c] for c in dlab], dlab), "x1": ([ext[c] for c in llab], llab), "x2": ([ext[c] for c in rlab], rlab)})
+    ext = {1: 8, 2: 5, 3: 8, 4: 5, 5: 8, 6: 5, 7: 1}
+    cases.append({"kind": "contract", "seed": 3600, "where": "EOM rank 5", "y": ([ext[c] for c in (7, 1, 2, 3, 4)], [7, 1, 2, 3, 4]),
+                  "x1": ([ext[c] for c in (7, 1, 5, 2, 6)], [7, 1, 5, 2, 6]), "x2": ([ext[c] for c in (6, 3, 5, 4)], [6, 3, 5, 4])})
+    return cases
+
+
 def run_reference(ref_gpu, cases):
     try:
         return ref_gpu.run_cases(cases, timeout=240)[0]
@@ -142,3 +168,11 @@ def test_permutations_equal_the_reference_cuda_backend(sip, ref_gpu, oracle):
         assert np.array_equal(got, w), (case["y"], case["x1"])        # a permutation moves bits: exact
         x1, _ = ref_gpu.case_inputs(case)
         assert np.array_equal(oracle.permute_labels(case["y"][1], case["x1"][1], x1), w)
+
+
+def test_config4_shapes_equal_the_reference_cuda_backend(sip, ref_gpu):
+    cases = config4_cases()
+    want = run_reference(ref_gpu, cases)
+    for case, w in zip(cases, want):
+        err = relerr(product_case(sip, ref_gpu, case), w)
+        assert err <= TOL, (case["where"], case["y"], case["x1"], case["x2"], err)
