@@ -6,7 +6,7 @@
 // UNMODIFIED, where it lies under /root/reference, with nvcc for sm_100a and links it with this shim and cuBLAS into
 // oracle/_ref/libaces4_ref_gpu.so.  It is the one implementation of this path's contraction and permutation that is
 // reference code AND runs in this environment (the CPU path is Fortran): reorderScatter of both operands into scratch
-// buffers, cublasDgemm, reorderGather into the destination (gpu_super_instructions.cu:400-570), three cudaMalloc of 40 MB
+// buffers, cublasDgemm, reorderGather into the destination (gpu_super_instructions.cu:369-586), three cudaMalloc of 40 MB
 // and seven device synchronisations per call, so blocks are limited to 40 MB (5 242 880 doubles).
 //
 // Used by tests/test_gpu_vs_ref_cuda.py (product `_gpu_contract` / `_gpu_permute` == reference `_gpu_contract` /

@@ -1,5 +1,5 @@
 """CPU pre-check of tests/test_gpu_vs_ref_cuda.py: the reference's legacy CUDA algorithm, emulated statement by statement
-in numpy (oracle/legacy_cuda_emulation.py, after src/sip/cuda/gpu_super_instructions.cu:330-660), agrees with the oracle on
+in numpy (oracle/legacy_cuda_emulation.py, after src/sip/cuda/gpu_super_instructions.cu:307-684), agrees with the oracle on
 every case the GPU test runs against the real thing."""
 import numpy as np
 
