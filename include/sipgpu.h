@@ -9,6 +9,10 @@
  * Conventions (identical to the reference): FP64 elements, 32-bit extents, dense
  * column-major blocks (first index fastest), rank <= SIPGPU_MAX_RANK, segment numbers 1-based.
  *
+ * Threading (the reference's contract for libtensordil, kept): the library is called from ONE thread per process --
+ * the SIP interpreter is single-threaded and runs one process per worker / per GPU -- and keeps process-global state
+ * (device, streams, block pool, the open recording).  It is not re-entrant; callers that add threads serialise the calls.
+ *
  * Paths cited below are relative to the reference checkout (UFParLab/aces4).
  */
 #ifndef SIPGPU_H_
