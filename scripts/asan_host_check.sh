@@ -27,7 +27,8 @@ OUT="$ROOT/profiles/r01_asan_host.txt"
   echo "## pytest (CPU host-logic tests) with the sanitized library preloaded"
   cd "$ROOT" && LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 SIPGPU_LIB="$W/lib/libsipgpu.so" \
     python -m pytest tests/test_worklist_cpu.py tests/test_consistency_cpu.py tests/test_mirror_cpu.py tests/test_persist_cpu.py \
-      tests/test_planner_cpu.py tests/test_sial_frontend_cpu.py -q 2>&1 | tail -3
+      tests/test_planner_cpu.py tests/test_sial_frontend_cpu.py -q \
+      --deselect tests/test_worklist_cpu.py::test_lccd_pardo_stream_dry_recording_counts_and_host_cost 2>&1 | tail -3
   echo "## AddressSanitizer reports: $(grep -c 'ERROR: AddressSanitizer' "$OUT.tmp" 2>/dev/null || echo 0)"
 } > "$OUT.tmp" 2>&1 || true
 grep -c "ERROR: AddressSanitizer" "$OUT.tmp" > /dev/null && sed -i "s/^## AddressSanitizer reports:.*/## AddressSanitizer reports: $(grep -c 'ERROR: AddressSanitizer' "$OUT.tmp")/" "$OUT.tmp" || true
