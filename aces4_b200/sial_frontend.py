@@ -22,8 +22,20 @@ Supported statements (case-insensitive keywords, `#` comments):
     T[...] = X[...] ^ Y[...] (outer product: the same opcode)               T[...] *= number     T[...] *= s
     s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
     execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
-Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `aoindex mu = 1: norb`; arrays
-`served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else raises SialSyntaxError.
+    proc NAME ... endproc NAME        call NAME
+Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `moaindex p = baocc: eavirt` /
+`aoindex mu = 1: norb`; arrays `served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else
+raises SialSyntaxError.
+
+An array declared over a `p` index (occupied followed by virtual, e.g. `served Vpiqj[p,i,q,j]`, `static ca[mu,p]`) is
+addressed with occupied or virtual labels as in the reference (`Vpiqj[a,i,b,j]`, `Vpiqj[i,i1,j,j1]`, `ca[mu,b]`): the
+segment number of a virtual label is shifted by the number of occupied segments.  `static` arrays are read block-wise
+through the backend (`array_block`), i.e. as slices of a resident array (contiguous_array_manager.cpp:162-230).
+
+Procedures: statements between `proc NAME` and `endproc` form a procedure; `call NAME` runs it; `Walker.run()` runs
+the main program (the statements outside procedures) and `Walker.run_proc(NAME)` one procedure (the test drivers use
+it for the `do kiter` loop of a CC program, whose `if`/`exit` are not in the subset).  A file that consists of
+procedures only (a fragment) is run in textual order.
 """
 import itertools
 import re
@@ -48,9 +60,11 @@ class Program:
 
     def __init__(self, text):
         self.index_kind, self.arrays, self.scalars = {}, {}, set()
-        self.body = []
-        stack = [self.body]
+        self.procs = {}           # name -> statement list (textual order kept: dicts are ordered)
+        main = []
+        stack = [main]
         opens = []
+        in_proc = None
         for ln, raw in enumerate(text.splitlines(), 1):
             line = raw.split("#", 1)[0].strip()
             if not line:
@@ -63,7 +77,18 @@ class Program:
                 raise SialSyntaxError(f"line {ln}: {e}: {raw.strip()!r}") from None
             if st is None:
                 continue
-            if st[0] in ("pardo", "do"):
+            if st[0] == "proc":
+                if in_proc is not None or opens or st[1] in self.procs:
+                    raise SialSyntaxError(f"line {ln}: misplaced or duplicate proc {st[1]}")
+                in_proc = st[1]
+                self.procs[in_proc] = []
+                stack = [self.procs[in_proc]]
+            elif st[0] == "endproc":
+                if in_proc is None or opens:
+                    raise SialSyntaxError(f"line {ln}: misplaced endproc")
+                in_proc = None
+                stack = [main]
+            elif st[0] in ("pardo", "do"):
                 st = st + ([],)
                 stack[-1].append(st)
                 stack.append(st[-1])
@@ -74,13 +99,21 @@ class Program:
                 stack.pop()
             else:
                 stack[-1].append(st)
-        if opens:
-            raise SialSyntaxError("unterminated " + opens[-1])
+        if opens or in_proc is not None:
+            raise SialSyntaxError("unterminated " + (opens[-1] if opens else "proc " + in_proc))
+        # a fragment (procedures only) runs in textual order; otherwise the body is the main program
+        self.body = main if main else [st for body in self.procs.values() for st in body]
 
     def _parse(self, line, low, tok):
         kw = tok[0]
-        if kw in ("sial", "endsial", "proc", "endproc", "import"):
+        if kw in ("sial", "endsial", "import"):
             return None
+        if kw in ("proc", "call"):
+            if len(tok) != 2:
+                raise SialSyntaxError("bad " + kw)
+            return (kw, tok[1])
+        if kw == "endproc":
+            return ("endproc",)
         if kw in ("moaindex", "aoindex", "moindex", "mobindex"):
             m = re.match(r"\w+\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line)
             if not m:
@@ -169,9 +202,13 @@ class Program:
 class Walker:
     """Executes a Program against a backend: the per-block call stream of one worker."""
 
-    def __init__(self, program, backend, segs, rank=0, world=1):
-        """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v."""
+    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None):
+        """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v.
+        index_base: {'o': baocc - 1, 'v': bavirt - 1, ...}: what to add to a loop's segment number to get the absolute
+        segment number of its index type -- the index values a super-instruction receives (the reference's loops run
+        over baocc..eaocc / bavirt..eavirt directly, interpreter.cpp:1011-1208)."""
         self.p, self.be, self.rank, self.world = program, backend, rank, world
+        self.index_base = dict(index_base or {})
         self.segs = dict(segs)
         if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
             self.segs["p"] = list(self.segs["o"]) + list(self.segs["v"])
@@ -197,7 +234,22 @@ class Walker:
         return tuple(self.segs[self._kind(lab)][self.idx[lab] - 1] for lab in labs)
 
     def _is_remote(self, name):
-        return self.p.arrays.get(name, ("temp",))[0] in ("served", "distributed")
+        return self.p.arrays.get(name, ("temp",))[0] in ("served", "distributed", "static")
+
+    def _array_segs(self, name, labs):
+        """block coordinates of `name[labs]` in the segment numbering of the array's DECLARED indices"""
+        decl = self.p.arrays[name][1]
+        if len(decl) != len(labs):
+            raise SialSyntaxError(f"{name} has rank {len(decl)}")
+        out = []
+        for d, lab in zip(decl, labs):
+            dk, k, v = self._kind(d), self._kind(lab), self.idx[lab]
+            if dk == "p" and k == "v":
+                v += len(self.segs["o"])
+            elif dk != k and not (dk == "p" and k == "o"):
+                raise SialSyntaxError(f"index {lab} ({k}) cannot address dimension {d} ({dk}) of {name}")
+            out.append(v)
+        return tuple(out)
 
     def _find(self, name, labs):
         key = (name, self._segs_of(labs))
@@ -209,7 +261,7 @@ class Walker:
     def _read(self, name, labs):
         """(handle, labels it is stored with) of an operand block"""
         if self._is_remote(name):
-            return self.be.array_block(name, self._segs_of(labs), self._shape(labs)), labs
+            return self.be.array_block(name, self._array_segs(name, labs), self._shape(labs)), labs
         h = self._find(name, labs)
         if h is None:
             raise SialSyntaxError(f"block {name}{list(labs)} read before it was written")
@@ -232,6 +284,15 @@ class Walker:
     def run(self):
         self._block(self.p.body)
         return self.scalars
+
+    def run_proc(self, name):
+        self._x_call(name)
+        return self.scalars
+
+    def _x_call(self, name):
+        if name not in self.p.procs:
+            raise SialSyntaxError(f"call of undefined proc {name}")
+        self._block(self.p.procs[name])
 
     def _block(self, stmts):
         for st in stmts:
@@ -276,7 +337,7 @@ class Walker:
         del self.idx[lab]
 
     def _x_request(self, name, labs):
-        self.be.request(name, self._segs_of(labs), self._shape(labs))
+        self.be.request(name, self._array_segs(name, labs), self._shape(labs))
 
     def _x_fill(self, name, labs, v):
         self.be.fill(self._write(name, labs), v)
@@ -290,7 +351,7 @@ class Walker:
         self.be.scale(self._write(name, labs), self.be.value(self.scalars[scalar]))
 
     def _x_put_init(self, arr, alabs, v):
-        self.be.put_initialize(arr, self._segs_of(alabs), self._shape(alabs), v)
+        self.be.put_initialize(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
 
     def _x_assign(self, name, labs, src, slabs, _sign):
         s, sl = self._read(src, slabs)
@@ -316,12 +377,13 @@ class Walker:
         s, sl = self._read(src, slabs)
         if tuple(sl) != tuple(alabs):
             raise SialSyntaxError("put/prepare needs matching labels on both sides")
-        (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._segs_of(alabs), s)
+        (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._array_segs(arr, alabs), s)
 
     def _x_execute(self, fname, args, bare):
         blocks = [self._read(n, labs)[0] if self._is_remote(n) else self._write(n, labs) for n, labs in args]
-        segs = [self._segs_of(labs) for _, labs in args]
         kinds = [[self._kind(x) for x in labs] for _, labs in args]
+        segs = [tuple(self.idx[x] + self.index_base.get(k, 0) for x, k in zip(labs, ks))
+                for (_, labs), ks in zip(args, kinds)]
         self.be.execute(fname, blocks, segs, kinds, bare)
 
     def _x_sdot(self, name, lname, llabs, rname, rlabs):

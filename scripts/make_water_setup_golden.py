@@ -1,0 +1,28 @@
+"""Decode the geometry / basis / segment tables of the reference's LCCD setup files (test/lccd_frozencore_test.dat,
+test/lccd_test.dat: water, 3-21G) and the energy goldens of the reference's tests for them (test/test_qm.cpp:371-468)
+into tests/golden/water_321g_setup.json.  Run in the build container (needs /root/reference); the GPU box only sees the
+committed JSON.  floats are written with repr() precision (json round-trips doubles exactly)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aces4_b200.setup_reader import read_setup  # noqa: E402
+
+GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_test) and :447-448, 459-462 (lccd_frozencore_test)
+    "scf_energy": -75.58432674274046, "lccd_correlation": -0.12610179886435, "lccd_energy": -75.71042854160481,
+    "tolerance": 1e-10}
+out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
+for name in ("lccd_frozencore_test.dat", "lccd_test.dat"):
+    s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
+    assert s["trailing_bytes"] == 0
+    keep_f = ("alphas", "charge", "coords", "pcoeffs")
+    keep_i = ("atom", "ivangmom", "ncfps", "npfps", "ixalphas", "ixpcoeffs", "ccbeg", "ccend", "end_nfps",
+              "moa_seg_ranges", "ao_seg_ranges")
+    out["setups"][name] = {
+        "programs": s["programs"], "ints": s["ints"], "scalars": s["scalars"], "segments": s["segments"],
+        "arrays": {k: s["arrays"][k] for k in keep_f}, "int_arrays": {k: s["int_arrays"][k] for k in keep_i}}
+path = os.path.join(ROOT, "tests", "golden", "water_321g_setup.json")
+json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+print("wrote", path, os.path.getsize(path), "bytes")

@@ -1,0 +1,70 @@
+"""Shared driver of the LCCD energy tests (water / 3-21G / frozen core, the reference's lccd_frozencore_test): inputs from
+the decoded `.dat` (tests/golden/water_321g_setup.json) through oracle/qm_inputs.py (numpy integrals + RHF, test
+infrastructure), then the reference's LCCD amplitude equations (tests/golden/lccd_program.sialx) walked block by block
+by aces4_b200/sial_frontend.py on a backend -- the CPU oracle here, libsipgpu in tests/test_gpu_lccd_water_energy.py --
+and the converged energy compared with the reference's golden values (test/test_qm.cpp:447-462)."""
+import functools
+import json
+import os
+
+import numpy as np
+
+from oracle import qm_inputs as qm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PROGRAM = open(os.path.join(HERE, "golden", "lccd_program.sialx")).read()
+FIXTURE = json.load(open(os.path.join(HERE, "golden", "water_321g_setup.json")))
+GOLDEN = FIXTURE["golden"]
+# array name -> index kinds of its declared dimensions
+KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"), "viaai": ("o", "v", "v", "o"),
+         "vaaii": ("v", "v", "o", "o"), "t2old_ab": ("v", "o", "v", "o"), "t2new_ab": ("v", "o", "v", "o"),
+         "tao_ab": ("ao", "o", "ao", "o"), "t2ao_ab": ("ao", "o", "ao", "o"), "tdaixj": ("v", "o", "ao", "o")}
+# segmentations: the .dat's own (moa [1 | 4 | 8], ao [11, 2]) and a finer one of the same orbitals
+SEGMENTATIONS = {"dat": None, "fine": {"moa": [1, 2, 2, 3, 5], "occ": (2, 3), "virt": (4, 5), "ao": [6, 5, 2]}}
+
+
+@functools.lru_cache(maxsize=None)
+def scf():
+    """integrals + RHF of the frozen-core setup; (setup, S, eri, e_scf, eps, C)"""
+    setup = FIXTURE["setups"]["lccd_frozencore_test.dat"]
+    basis = qm.basis_from_setup(setup)
+    S, T, V, eri = qm.ao_integrals(basis)
+    e_nuc = qm.nuclear_repulsion(basis)
+    e_scf, eps, C, _ = qm.rhf(S, T + V, eri, setup["ints"]["naocc"], e_nuc)
+    return setup, basis, S, eri, e_nuc, e_scf, eps, C
+
+
+def inputs(segmentation):
+    """-> dict(segs, index_base, moa_seg_ranges, fock, arrays {name: {segment tuple: block}}, e_scf)"""
+    setup, _, _, eri, _, e_scf, eps, C = scf()
+    sg = SEGMENTATIONS[segmentation]
+    if sg is None:
+        it = setup["ints"]
+        sg = {"moa": setup["segments"]["moa"], "occ": (it["baocc"], it["eaocc"]), "virt": (it["bavirt"], it["eavirt"]),
+              "ao": setup["segments"]["ao"]}
+    moa = sg["moa"]
+    off = np.concatenate([[0], np.cumsum(moa)])
+    occ = slice(off[sg["occ"][0] - 1], off[sg["occ"][1]])
+    virt = slice(off[sg["virt"][0] - 1], off[sg["virt"][1]])
+    segs = {"o": moa[sg["occ"][0] - 1: sg["occ"][1]], "v": moa[sg["virt"][0] - 1: sg["virt"][1]], "ao": sg["ao"]}
+    segs["p"] = segs["o"] + segs["v"]
+    dense = qm.mo_classes(eri, C, occ, virt)
+    dense["aoint"] = eri
+    dense["ca"] = np.hstack([C[:, occ], C[:, virt]])
+    arrays = {name: qm.split_blocks(dense[name], [segs[k] for k in KINDS[name]]) for name in dense}
+    for name in ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj"):
+        arrays[name] = {}
+    return {"segs": segs, "index_base": {"o": sg["occ"][0] - 1, "v": sg["virt"][0] - 1}, "moa_seg_ranges": list(moa),
+            "fock": np.asfortranarray(np.diag(eps)), "arrays": arrays, "e_scf": e_scf}
+
+
+def converge(walker, value, tol=1e-12, max_iter=80):
+    """main program (starting guess + second-order energy), then `proc iteration` until the energy is stationary;
+    `value` turns a walker scalar into a float.  -> (mp2 energy, [energy per iteration])"""
+    e_mp2 = value(walker.run()["ecorrab"])
+    hist = []
+    for _ in range(max_iter):
+        hist.append(value(walker.run_proc("iteration")["ecorrab"]))
+        if len(hist) > 1 and abs(hist[-1] - hist[-2]) < tol:
+            return e_mp2, hist
+    raise AssertionError(f"LCCD iterations did not converge: {hist[-3:]}")

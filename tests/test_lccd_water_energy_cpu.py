@@ -1,0 +1,106 @@
+"""Energy-level parity on the CPU side (no GPU): the reference's golden energies of lccd_frozencore_test
+(test/test_qm.cpp:431-468: water, 3-21G, drop_mo=1-1) reproduced by (1) the numpy input stage of oracle/qm_inputs.py
+(SCF energy: pins the integrals, i.e. the INPUTS of the hot path) and (2) the reference's LCCD amplitude equations
+(tests/golden/lccd_program.sialx) walked by the SIAL front-end on the ORACLE backend (correlation energy: pins the
+front-end's call stream and the oracle's block arithmetic at the energy level).  The same program on libsipgpu:
+tests/test_gpu_lccd_water_energy.py."""
+import numpy as np
+import pytest
+
+import lccd_water as lw
+from aces4_b200.sial_frontend import Program, Walker
+from oracle import qm_inputs as qm
+from sial_oracle_backend import OracleBackend
+
+
+def test_boys_function_against_quadrature():
+    T = np.array([0.0, 1e-9, 1e-3, 0.5, 3.0, 12.0, 34.9, 35.0, 36.0, 120.0, 900.0])
+    x, w = np.polynomial.legendre.leggauss(400)
+    t = 0.5 * (x + 1.0)
+    F = qm.boys(4, T)
+    for n in range(5):
+        want = np.array([0.5 * np.sum(w * t ** (2 * n) * np.exp(-Ti * t * t)) for Ti in T])
+        assert np.max(np.abs(F[n] - want) / want) < 5e-13, n
+
+
+def test_inputs_reproduce_the_reference_scf_energy():
+    setup, basis, S, eri, e_nuc, e_scf, eps, C = lw.scf()
+    assert abs(e_nuc - setup["scalars"]["nn_repulsion"]) < 1e-12          # geometry decoded as the reference reads it
+    assert np.allclose(C.T @ S @ C, np.eye(13), atol=1e-10)
+    for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)]:
+        assert np.max(np.abs(eri - eri.transpose(perm))) < 1e-13
+    assert abs(e_scf - lw.GOLDEN["scf_energy"]) < lw.GOLDEN["tolerance"]  # -75.58432674274046 @ 1e-10
+
+
+def dense_lccd(inp, tol=1e-13):
+    """the same equations as dense einsums (independent of the walker and of the block arithmetic)"""
+    segs, A = inp["segs"], inp["arrays"]
+    j = lambda n: qm.join_blocks(A[n], [segs[k] for k in lw.KINDS[n]])  # noqa: E731
+    Vp, Via, Vaa, ca, ao = j("vpiqj"), j("viaai"), j("vaaii"), j("ca"), j("aoint")
+    no = sum(segs["o"])
+    V, Vo, cv = Vp[no:, :, no:, :], Vp[:no, :, :no, :], ca[:, no:]
+    eps = np.diag(inp["fock"])
+    lo = sum(inp["moa_seg_ranges"][: inp["index_base"]["o"]])
+    eo, ev = eps[lo: lo + no], eps[lo + no:]
+    D = eo[None, :, None, None] + eo[None, None, None, :] - ev[:, None, None, None] - ev[None, None, :, None]
+    sym = lambda X: X + X.transpose(2, 3, 0, 1)  # noqa: E731
+    en = lambda T: np.einsum("aibj,aibj->", T, 2.0 * V - V.transpose(0, 3, 2, 1))  # noqa: E731
+    T = 0.5 * sym(V) / D
+    e_mp2, e_old = en(T), 0.0
+    for _ in range(100):
+        new = sym(0.5 * V) + np.einsum("akbl,ikjl->aibj", T, Vo)
+        TY = np.einsum("iack->aick", Via) - np.einsum("caik->aick", Vaa)
+        new += sym(np.einsum("aick,ckbj->aibj", TY, T))
+        W = np.einsum("ckai->ckia", T) - np.einsum("ciak->ckia", T)
+        new += sym(np.einsum("ckia,iabj->ckbj", W, Via))
+        new += sym(-np.einsum("akcj,bcki->aibj", T, Vaa))
+        tao = np.einsum("aibj,ma,nb->minj", T, cv, cv)
+        new += np.einsum("minj,ma,nb->aibj", np.einsum("lmsn,lisj->minj", ao, tao), cv, cv)
+        T = 0.5 * sym(new) / D
+        e = en(T)
+        if abs(e - e_old) < tol:
+            return e_mp2, e
+        e_old = e
+    raise AssertionError("dense LCCD did not converge")
+
+
+@pytest.mark.parametrize("segmentation", ["dat", "fine"])
+def test_lccd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, segmentation):
+    inp = lw.inputs(segmentation)
+    e_mp2_dense, e_dense = dense_lccd(inp)
+    assert abs(e_dense - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM), be, inp["segs"], index_base=inp["index_base"])
+    e_mp2, hist = lw.converge(w, be.value)
+    assert abs(e_mp2 - e_mp2_dense) < 1e-12
+    e_corr = hist[-1]
+    assert abs(e_corr - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]          # -0.12610179886435 @ 1e-10
+    assert abs(e_corr + inp["e_scf"] - lw.GOLDEN["lccd_energy"]) < lw.GOLDEN["tolerance"]  # -75.71042854160481 @ 1e-10
+    assert abs(e_corr - e_dense) < 1e-11
+    assert be.calls > 1000 * len(hist) or segmentation == "dat"   # the fine segmentation really is block-wise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_lccd_iteration_partitions_over_workers(oracle, world):
+    """every worker walks the program and executes its share of the pardo iterations (loop_manager.cpp:468-499);
+    accumulating into shared arrays, one residual evaluation by `world` workers equals the single-worker one"""
+    inpw = lw.inputs("fine")
+    prog = Program(lw.PROGRAM)
+    bes = [OracleBackend(oracle, inpw["arrays"], fock=inpw["fock"], moa_seg_ranges=inpw["moa_seg_ranges"])
+           for _ in range(world)]
+    ws = [Walker(prog, bes[r], inpw["segs"], rank=r, world=world, index_base=inpw["index_base"]) for r in range(world)]
+    # barrier-synchronous execution: every worker finishes a procedure before any starts the next one
+    for name in ("iguess", "t2new_zero", "t2newab", "hhladder_ab", "phladder_ab"):
+        for w in ws:
+            w.run_proc(name)
+    # reference state after the same procedures on one worker
+    inp2 = lw.inputs("fine")
+    be2 = OracleBackend(oracle, inp2["arrays"], fock=inp2["fock"], moa_seg_ranges=inp2["moa_seg_ranges"])
+    w2 = Walker(prog, be2, inp2["segs"], index_base=inp2["index_base"])
+    for name in ("iguess", "t2new_zero", "t2newab", "hhladder_ab", "phladder_ab"):
+        w2.run_proc(name)
+    for idx, b in inp2["arrays"]["t2old_ab"].items():
+        assert np.array_equal(inpw["arrays"]["t2old_ab"][idx], b)
+    for idx, b in inp2["arrays"]["t2new_ab"].items():
+        assert np.max(np.abs(inpw["arrays"]["t2new_ab"][idx] - b)) <= 1e-13
+    assert min(be.calls for be in bes) > 0
