@@ -12,9 +12,12 @@ from aces4_b200.setup_reader import read_setup  # noqa: E402
 
 GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_test) and :447-448, 459-462 (lccd_frozencore_test)
     "scf_energy": -75.58432674274046, "lccd_correlation": -0.12610179886435, "lccd_energy": -75.71042854160481,
-    "tolerance": 1e-10}
+    "tolerance": 1e-10,
+    # all-electron runs of the same molecule: test/test_qm.cpp:651-652, 677-678 (DISABLED_eom_lccd_test: rlccd_rhf.siox
+    # without drop_mo) and :732-733, 758-759 (DISABLED_eom_mp2_test: mp2_rhf_disc.siox)
+    "all_electron": {"scf_energy": -75.58432674274034, "lccd_energy": -75.71210049055006, "mp2_energy": -75.70540831822183}}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
-for name in ("lccd_frozencore_test.dat", "lccd_test.dat"):
+for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

@@ -19,14 +19,25 @@ GOLDEN = FIXTURE["golden"]
 KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"), "viaai": ("o", "v", "v", "o"),
          "vaaii": ("v", "v", "o", "o"), "t2old_ab": ("v", "o", "v", "o"), "t2new_ab": ("v", "o", "v", "o"),
          "tao_ab": ("ao", "o", "ao", "o"), "t2ao_ab": ("ao", "o", "ao", "o"), "tdaixj": ("v", "o", "ao", "o")}
-# segmentations: the .dat's own (moa [1 | 4 | 8], ao [11, 2]) and a finer one of the same orbitals
-SEGMENTATIONS = {"dat": None, "fine": {"moa": [1, 2, 2, 3, 5], "occ": (2, 3), "virt": (4, 5), "ao": [6, 5, 2]}}
+# cases: (setup file, segmentation).  Segmentations: the .dat's own (frozen core: moa [1 | 4 | 8], ao [11, 2]; all
+# electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
+FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"
+CASES = {"dat": (FROZEN, None), "fine": (FROZEN, {"moa": [1, 2, 2, 3, 5], "occ": (2, 3), "virt": (4, 5), "ao": [6, 5, 2]}),
+         "all_dat": (ALL, None), "all_fine": (ALL, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]})}
+
+
+def golden(case):
+    """(lccd_correlation or None, lccd_energy, mp2_energy or None) the reference's tests assert for this case"""
+    if CASES[case][0] == FROZEN:
+        return GOLDEN["lccd_correlation"], GOLDEN["lccd_energy"], None
+    g = GOLDEN["all_electron"]
+    return None, g["lccd_energy"], g["mp2_energy"]
 
 
 @functools.lru_cache(maxsize=None)
-def scf():
-    """integrals + RHF of the frozen-core setup; (setup, S, eri, e_scf, eps, C)"""
-    setup = FIXTURE["setups"]["lccd_frozencore_test.dat"]
+def scf(setup_name=FROZEN):
+    """integrals + RHF of one setup; (setup, basis, S, eri, e_nuc, e_scf, eps, C)"""
+    setup = FIXTURE["setups"][setup_name]
     basis = qm.basis_from_setup(setup)
     S, T, V, eri = qm.ao_integrals(basis)
     e_nuc = qm.nuclear_repulsion(basis)
@@ -34,10 +45,10 @@ def scf():
     return setup, basis, S, eri, e_nuc, e_scf, eps, C
 
 
-def inputs(segmentation):
+def inputs(case):
     """-> dict(segs, index_base, moa_seg_ranges, fock, arrays {name: {segment tuple: block}}, e_scf)"""
-    setup, _, _, eri, _, e_scf, eps, C = scf()
-    sg = SEGMENTATIONS[segmentation]
+    setup_name, sg = CASES[case]
+    setup, _, _, eri, _, e_scf, eps, C = scf(setup_name)
     if sg is None:
         it = setup["ints"]
         sg = {"moa": setup["segments"]["moa"], "occ": (it["baocc"], it["eaocc"]), "virt": (it["bavirt"], it["eavirt"]),

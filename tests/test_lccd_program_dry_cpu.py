@@ -50,7 +50,7 @@ class DryBackend(DeviceBackend):
         self.cache.clear()
 
 
-@pytest.mark.parametrize("segmentation", ["dat", "fine"])
+@pytest.mark.parametrize("segmentation", ["dat", "fine", "all_dat", "all_fine"])
 def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation):
     inp = lw.inputs(segmentation)
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])

@@ -1,5 +1,6 @@
 """Energy-level parity on the CPU side (no GPU): the reference's golden energies of lccd_frozencore_test
-(test/test_qm.cpp:431-468: water, 3-21G, drop_mo=1-1) reproduced by (1) the numpy input stage of oracle/qm_inputs.py
+(test/test_qm.cpp:431-468: water, 3-21G, drop_mo=1-1) and of the all-electron runs of the same molecule (:639-678 LCCD,
+:720-759 MP2) reproduced by (1) the numpy input stage of oracle/qm_inputs.py
 (SCF energy: pins the integrals, i.e. the INPUTS of the hot path) and (2) the reference's LCCD amplitude equations
 (tests/golden/lccd_program.sialx) walked by the SIAL front-end on the ORACLE backend (correlation energy: pins the
 front-end's call stream and the oracle's block arithmetic at the energy level).  The same program on libsipgpu:
@@ -23,13 +24,15 @@ def test_boys_function_against_quadrature():
         assert np.max(np.abs(F[n] - want) / want) < 5e-13, n
 
 
-def test_inputs_reproduce_the_reference_scf_energy():
-    setup, basis, S, eri, e_nuc, e_scf, eps, C = lw.scf()
+@pytest.mark.parametrize("setup_name", [lw.FROZEN, lw.ALL])
+def test_inputs_reproduce_the_reference_scf_energy(setup_name):
+    setup, basis, S, eri, e_nuc, e_scf, eps, C = lw.scf(setup_name)
     assert abs(e_nuc - setup["scalars"]["nn_repulsion"]) < 1e-12          # geometry decoded as the reference reads it
     assert np.allclose(C.T @ S @ C, np.eye(13), atol=1e-10)
     for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)]:
         assert np.max(np.abs(eri - eri.transpose(perm))) < 1e-13
     assert abs(e_scf - lw.GOLDEN["scf_energy"]) < lw.GOLDEN["tolerance"]  # -75.58432674274046 @ 1e-10
+    assert abs(e_scf - lw.GOLDEN["all_electron"]["scf_energy"]) < lw.GOLDEN["tolerance"]   # the other tests' rounding of it
 
 
 def dense_lccd(inp, tol=1e-13):
@@ -64,20 +67,25 @@ def dense_lccd(inp, tol=1e-13):
     raise AssertionError("dense LCCD did not converge")
 
 
-@pytest.mark.parametrize("segmentation", ["dat", "fine"])
-def test_lccd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, segmentation):
-    inp = lw.inputs(segmentation)
+@pytest.mark.parametrize("case", ["dat", "fine", "all_dat", "all_fine"])
+def test_lccd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, case):
+    inp = lw.inputs(case)
+    g_corr, g_total, g_mp2 = lw.golden(case)
+    tol = lw.GOLDEN["tolerance"]
     e_mp2_dense, e_dense = dense_lccd(inp)
-    assert abs(e_dense - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]
+    assert abs(e_dense + inp["e_scf"] - g_total) < tol
     be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
     w = Walker(Program(lw.PROGRAM), be, inp["segs"], index_base=inp["index_base"])
     e_mp2, hist = lw.converge(w, be.value)
     assert abs(e_mp2 - e_mp2_dense) < 1e-12
     e_corr = hist[-1]
-    assert abs(e_corr - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]          # -0.12610179886435 @ 1e-10
-    assert abs(e_corr + inp["e_scf"] - lw.GOLDEN["lccd_energy"]) < lw.GOLDEN["tolerance"]  # -75.71042854160481 @ 1e-10
+    if g_corr is not None:
+        assert abs(e_corr - g_corr) < tol                     # frozen core: lccd_correlation -0.12610179886435 @ 1e-10
+    assert abs(e_corr + inp["e_scf"] - g_total) < tol         # lccd_energy -75.71042854160481 / -75.71210049055006 @ 1e-10
+    if g_mp2 is not None:
+        assert abs(e_mp2 + inp["e_scf"] - g_mp2) < tol        # all electron: mp2_energy -75.70540831822183 @ 1e-10
     assert abs(e_corr - e_dense) < 1e-11
-    assert be.calls > 1000 * len(hist) or segmentation == "dat"   # the fine segmentation really is block-wise
+    assert be.calls > 1000 * len(hist) or case.endswith("dat")   # the fine segmentations really are block-wise
 
 
 @pytest.mark.parametrize("world", [2, 3])
