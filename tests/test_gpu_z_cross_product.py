@@ -23,6 +23,7 @@ def sip():
     return s.api
 
 
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
 def test_full_cross_product_s16_against_the_oracle(sip, oracle):
     s = 16
     rng = np.random.default_rng(16)
@@ -44,6 +45,7 @@ def test_full_cross_product_s16_against_the_oracle(sip, oracle):
     print(f"\n1728 patterns at s=16: worst relative error {worst:.2e}")
 
 
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
 def test_full_cross_product_s32_equivariance(sip, oracle):
     s = 32
     rng = np.random.default_rng(32)

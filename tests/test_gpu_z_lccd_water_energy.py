@@ -40,6 +40,7 @@ def device_arrays(sip, inp):
     return out
 
 
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
 @pytest.mark.parametrize("case,record", [("fine", True), ("dat", True), ("fine", False), ("all_fine", True),
                                          ("all_dat", True)])
 def test_lccd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
