@@ -22,7 +22,7 @@ Supported statements (case-insensitive keywords, `#` comments):
     T[...] = X[...] ^ Y[...] (outer product: the same opcode)               T[...] *= number     T[...] *= s
     s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
     execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
-    proc NAME ... endproc NAME        call NAME
+    proc NAME ... endproc NAME        call NAME        allocate L[a,*,b,j] / deallocate L[a,*,b,j]
 Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `moaindex p = baocc: eavirt` /
 `aoindex mu = 1: norb`; arrays `served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else
 raises SialSyntaxError.
@@ -31,6 +31,10 @@ An array declared over a `p` index (occupied followed by virtual, e.g. `served V
 addressed with occupied or virtual labels as in the reference (`Vpiqj[a,i,b,j]`, `Vpiqj[i,i1,j,j1]`, `ca[mu,b]`): the
 segment number of a virtual label is shifted by the number of occupied segments.  `static` arrays are read block-wise
 through the backend (`array_block`), i.e. as slices of a resident array (contiguous_array_manager.cpp:162-230).
+
+`allocate` creates the blocks of a `local` array for every segment of the `*` dimensions, zero-filled, and they live
+until `deallocate` (not until the end of the loop iteration like temps; block_manager.cpp allocate_local /
+deallocate_local) -- here a block is created, zero-filled, when it is first touched.
 
 Procedures: statements between `proc NAME` and `endproc` form a procedure; `call NAME` runs it; `Walker.run()` runs
 the main program (the statements outside procedures) and `Walker.run_proc(NAME)` one procedure (the test drivers use
@@ -160,6 +164,11 @@ class Program:
             args = [(m.group(1).lower(), _labels(m.group(2))) for m in re.finditer(_REF, line)]
             bare = [t for t in re.sub(_REF, " ", line).split()[2:]]
             return ("execute", tok[1], args, [b.lower() for b in bare])
+        if kw in ("allocate", "deallocate"):
+            m = re.match(r"\w+\s+([A-Za-z_]\w*)\s*\[([^\]]*)\]\s*$", line)
+            if not m:
+                raise SialSyntaxError("bad " + kw)
+            return (kw, m.group(1).lower(), _labels(m.group(2)))
         if kw in ("sip_barrier", "server_barrier"):
             return ("barrier",)
         if kw == "collective":
@@ -214,6 +223,7 @@ class Walker:
             self.segs["p"] = list(self.segs["o"]) + list(self.segs["v"])
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
+        self.locals = {}         # allocated local arrays: name -> {segs: handle}
         self.iteration = 0       # pardo iteration counter of the current barrier section
         self.scalars = {s: 0.0 for s in program.scalars}
 
@@ -253,6 +263,12 @@ class Walker:
 
     def _find(self, name, labs):
         key = (name, self._segs_of(labs))
+        if name in self.locals:            # allocated local array: zero-filled blocks that outlive the loop scopes
+            blocks = self.locals[name]
+            if key[1] not in blocks:
+                blocks[key[1]] = self.be.new_block(self._shape(labs))
+                self.be.fill(blocks[key[1]], 0.0)
+            return blocks[key[1]]
         for sc in reversed(self.scopes):
             if key in sc:
                 return sc[key]
@@ -335,6 +351,17 @@ class Walker:
             if ok is False:
                 continue
         del self.idx[lab]
+
+    def _x_allocate(self, name, labs):
+        if self.p.arrays.get(name, ("",))[0] != "local" or name in self.locals:
+            raise SialSyntaxError(f"allocate of {name}: not a (free) local array")
+        self.locals[name] = {}
+
+    def _x_deallocate(self, name, labs):
+        if name not in self.locals:
+            raise SialSyntaxError(f"deallocate of {name}: not allocated")
+        for h in self.locals.pop(name).values():
+            self.be.free(h)
 
     def _x_request(self, name, labs):
         self.be.request(name, self._array_segs(name, labs), self._shape(labs))

@@ -13,7 +13,8 @@ reference's golden energies:
     electron repulsion), Boys function by series / asymptotic expansion + recursion;
   * closed-shell RHF with DIIS from the core-Hamiltonian guess (what scf_rhf_coreh.sialx converges to);
   * the Mulliken-ordered MO integral classes of src/sialx/qm/utility/tran_rhf_no4v.sialx:494-523
-    (Vpiqj[p,i,q,j] = (pi|qj), Vaaii[a,a1,i,i1] = (a a1|i i1), Viaai[i,a,a1,i1] = (ia|a1 i1)).
+    (Vpiqj[p,i,q,j] = (pi|qj), VSpipi = Vpiqj - its i<->j exchange, Vaaii[a,a1,i,i1] = (a a1|i i1),
+    Viaai[i,a,a1,i1] = (ia|a1 i1), Vaaai[a,a1,a2,i] = (a a1|a2 i)).
 
 Pinned by: nn_repulsion of the .dat (9.361611480180377) and the reference's scf_energy golden to 1e-10
 (tests/test_lccd_water_energy_cpu.py).  Nothing in aces4_b200/ imports this module.
@@ -277,9 +278,12 @@ def mo_classes(eri, C, occ, virt):
     Co, Cv = C[:, occ], C[:, virt]
     Cp = np.hstack([Co, Cv])
     tr = lambda c1, c2, c3, c4: np.einsum("mnls,mw,nx,ly,sz->wxyz", eri, c1, c2, c3, c4, optimize=True)  # noqa: E731
-    return {"vpiqj": tr(Cp, Co, Cp, Co),     # (p i|q j)      tran_rhf_no4v.sialx:494
-            "vaaii": tr(Cv, Cv, Co, Co),     # (a a1|i i1)    :516
-            "viaai": tr(Co, Cv, Cv, Co)}     # (i a|a1 i1)    :523
+    vpiqj = tr(Cp, Co, Cp, Co)
+    return {"vpiqj": vpiqj,                              # (p i|q j)              tran_rhf_no4v.sialx:494
+            "vspipi": vpiqj - vpiqj.transpose(0, 3, 2, 1),   # (p i|q j) - (p j|q i)  :482-501
+            "vaaii": tr(Cv, Cv, Co, Co),                 # (a a1|i i1)            :516
+            "viaai": tr(Co, Cv, Cv, Co),                 # (i a|a1 i1)            :523
+            "vaaai": tr(Cv, Cv, Cv, Co)}                 # (a a1|a2 i)            :444-470 + the last quarter transformation
 
 
 def split_blocks(dense, seg_lists):

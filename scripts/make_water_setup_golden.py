@@ -15,9 +15,11 @@ GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_te
     "tolerance": 1e-10,
     # all-electron runs of the same molecule: test/test_qm.cpp:651-652, 677-678 (DISABLED_eom_lccd_test: rlccd_rhf.siox
     # without drop_mo) and :732-733, 758-759 (DISABLED_eom_mp2_test: mp2_rhf_disc.siox)
-    "all_electron": {"scf_energy": -75.58432674274034, "lccd_energy": -75.71210049055006, "mp2_energy": -75.70540831822183}}
+    "all_electron": {"scf_energy": -75.58432674274034, "lccd_energy": -75.71210049055006, "mp2_energy": -75.70540831822183,
+                     # test/test_qm.cpp:526-529 (DISABLED_lccsd_test: rlccsd_rhf.siox, all electron)
+                     "lccsd_correlation": -0.12865706498547, "lccsd_energy": -75.71298380772593}}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
-for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat"):
+for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

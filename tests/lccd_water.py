@@ -13,12 +13,17 @@ from oracle import qm_inputs as qm
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PROGRAM = open(os.path.join(HERE, "golden", "lccd_program.sialx")).read()
+PROGRAM_LCCSD = open(os.path.join(HERE, "golden", "lccsd_program.sialx")).read()
 FIXTURE = json.load(open(os.path.join(HERE, "golden", "water_321g_setup.json")))
 GOLDEN = FIXTURE["golden"]
 # array name -> index kinds of its declared dimensions
 KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"), "viaai": ("o", "v", "v", "o"),
          "vaaii": ("v", "v", "o", "o"), "t2old_ab": ("v", "o", "v", "o"), "t2new_ab": ("v", "o", "v", "o"),
-         "tao_ab": ("ao", "o", "ao", "o"), "t2ao_ab": ("ao", "o", "ao", "o"), "tdaixj": ("v", "o", "ao", "o")}
+         "tao_ab": ("ao", "o", "ao", "o"), "t2ao_ab": ("ao", "o", "ao", "o"), "tdaixj": ("v", "o", "ao", "o"),
+         # LCCSD only (tests/golden/lccsd_program.sialx)
+         "vspipi": ("p", "o", "p", "o"), "vaaai": ("v", "v", "v", "o"), "t2old_aa": ("v", "o", "v", "o"),
+         "t1a_old": ("v", "o"), "t1a_new": ("v", "o")}
+EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a_old", "t1a_new")
 # cases: (setup file, segmentation).  Segmentations: the .dat's own (frozen core: moa [1 | 4 | 8], ao [11, 2]; all
 # electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
 FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"
@@ -32,6 +37,12 @@ def golden(case):
         return GOLDEN["lccd_correlation"], GOLDEN["lccd_energy"], None
     g = GOLDEN["all_electron"]
     return None, g["lccd_energy"], g["mp2_energy"]
+
+
+def golden_lccsd():
+    """(lccsd_correlation, lccsd_energy) of the reference's lccsd_test (all electron: cases all_dat / all_fine)"""
+    g = GOLDEN["all_electron"]
+    return g["lccsd_correlation"], g["lccsd_energy"]
 
 
 @functools.lru_cache(maxsize=None)
@@ -63,7 +74,7 @@ def inputs(case):
     dense["aoint"] = eri
     dense["ca"] = np.hstack([C[:, occ], C[:, virt]])
     arrays = {name: qm.split_blocks(dense[name], [segs[k] for k in KINDS[name]]) for name in dense}
-    for name in ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj"):
+    for name in EMPTY:
         arrays[name] = {}
     return {"segs": segs, "index_base": {"o": sg["occ"][0] - 1, "v": sg["virt"][0] - 1}, "moa_seg_ranges": list(moa),
             "fock": np.asfortranarray(np.diag(eps)), "arrays": arrays, "e_scf": e_scf}

@@ -73,3 +73,33 @@ def test_lccd_energy_on_the_device_matches_the_reference_golden(sip, case, recor
         assert np.max(np.abs(blk - t2[b, j, a, i].transpose(2, 3, 0, 1))) < 1e-13
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
+@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", True), ("all_fine", False)])
+def test_lccsd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
+    """tests/golden/lccsd_program.sialx = src/sialx/qm/cc/rlccsd_rhf.sialx (singles + doubles, rank-2 distributed arrays,
+    allocated local arrays) against test/test_qm.cpp:526-529: lccsd_correlation -0.12865706498547, lccsd_energy
+    -75.71298380772593"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs(case)
+    g_corr, g_total = lw.golden_lccsd()
+    tol = lw.GOLDEN["tolerance"]
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=record)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    w = Walker(Program(lw.PROGRAM_LCCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=120)
+    e_corr = hist[-1]
+    print(f"\nLCCSD water/3-21G on the device ({case}, record={record}): lccsd_correlation {e_corr:.14f} after "
+          f"{len(hist)} iterations, lccsd_energy {e_corr + inp['e_scf']:.14f}")
+    assert abs(e_corr - g_corr) < tol
+    assert abs(e_corr + inp["e_scf"] - g_total) < tol
+    t1 = np.concatenate([np.concatenate([arrays["t1a_old"].get((a, i)).to_numpy() for i in range(1, len(inp["segs"]["o"]) + 1)],
+                                        axis=1) for a in range(1, len(inp["segs"]["v"]) + 1)], axis=0)
+    assert t1.shape == (sum(inp["segs"]["v"]), sum(inp["segs"]["o"])) and np.max(np.abs(t1)) > 1e-4
+    assert not w.locals
+    for A in arrays.values():
+        A.destroy()

@@ -1,4 +1,4 @@
-"""The full LCCD program (tests/golden/lccd_program.sialx) walked on the DEVICE backend without a GPU: the deferred op
+"""The full LCCD and LCCSD programs (tests/golden/lccd_program.sialx, lccsd_program.sialx) walked on the DEVICE backend without a GPU: the deferred op
 stream in DRY mode (fake device addresses, nothing executes) takes every C-ABI call the GPU energy test
 (tests/test_gpu_z_lccd_water_energy.py) will make -- label validation, pattern analysis, the recorder and the
 scheduler all run on the host.  Checks that the program is accepted end to end, that the schedule honours the hazards
@@ -38,6 +38,9 @@ class DryArray:
     def put_accumulate(self, idx, blk):
         self.block_view(idx).accumulate(blk)
 
+    def put_initialize(self, idx, v):
+        self.block_view(idx).fill(v)
+
 
 class DryBackend(DeviceBackend):
     """DeviceBackend with its two device-touching calls (scalar read-back, device sync) stubbed"""
@@ -50,11 +53,12 @@ class DryBackend(DeviceBackend):
         self.cache.clear()
 
 
-@pytest.mark.parametrize("segmentation", ["dat", "fine", "all_dat", "all_fine"])
-def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation):
+@pytest.mark.parametrize("segmentation,program", [("dat", "lccd"), ("fine", "lccd"), ("all_dat", "lccd"),
+                                                  ("all_fine", "lccd"), ("all_dat", "lccsd"), ("all_fine", "lccsd")])
+def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation, program):
     inp = lw.inputs(segmentation)
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
-    prog = Program(lw.PROGRAM)
+    prog = Program(lw.PROGRAM if program == "lccd" else lw.PROGRAM_LCCSD)
     with sip.recording(dry=True):
         arrays = {name: DryArray(sip, [inp["segs"][k] for k in kinds]) for name, kinds in lw.KINDS.items()}
         be = DryBackend(sip, arrays, record=False)       # one recording around everything (ended by the with block)
@@ -70,3 +74,4 @@ def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentat
     assert st["scheduled"] < st["recorded"]
     assert st["fused_accumulates"] > 0 and st["temps_elided"] > 0
     assert len(level) == len(unit) > 0 and min(level) >= 1
+    assert not w.locals

@@ -112,3 +112,64 @@ def test_lccd_iteration_partitions_over_workers(oracle, world):
     for idx, b in inp2["arrays"]["t2new_ab"].items():
         assert np.max(np.abs(inpw["arrays"]["t2new_ab"][idx] - b)) <= 1e-13
     assert min(be.calls for be in bes) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LCCSD (tests/golden/lccsd_program.sialx = src/sialx/qm/cc/rlccsd_rhf.sialx): singles + doubles, local arrays
+# ---------------------------------------------------------------------------------------------------------------------
+def dense_lccsd(inp, tol=1e-13):
+    """the LCCSD equations of rlccsd_rhf.sialx as dense einsums (independent of the walker / block arithmetic)"""
+    segs, A = inp["segs"], inp["arrays"]
+    j = lambda n: qm.join_blocks(A[n], [segs[k] for k in lw.KINDS[n]])  # noqa: E731
+    Vp, VSp, Via, Vaa, Vaaai, ca, ao = j("vpiqj"), j("vspipi"), j("viaai"), j("vaaii"), j("vaaai"), j("ca"), j("aoint")
+    no = sum(segs["o"])
+    V, Vo, Voovo, VS, cv = Vp[no:, :, no:, :], Vp[:no, :, :no, :], Vp[:no, :, no:, :], VSp[no:, :, :no, :], ca[:, no:]
+    eps = np.diag(inp["fock"])
+    lo = sum(inp["moa_seg_ranges"][: inp["index_base"]["o"]])
+    eo, ev = eps[lo: lo + no], eps[lo + no:]
+    D2 = eo[None, :, None, None] + eo[None, None, None, :] - ev[:, None, None, None] - ev[None, None, :, None]
+    D1 = eo[None, :] - ev[:, None]
+    sym = lambda X: X + X.transpose(2, 3, 0, 1)  # noqa: E731
+    en = lambda T: np.einsum("aibj,aibj->", T, 2.0 * V - V.transpose(0, 3, 2, 1))  # noqa: E731
+    T2, t1 = 0.5 * sym(V) / D2, np.zeros((len(ev), no))
+    e_old = 0.0
+    for _ in range(200):
+        Taa = T2 - T2.transpose(0, 3, 2, 1)
+        n1 = np.einsum("iabj,bj->ai", Via, t1) - np.einsum("acki,ck->ai", Vaa, t1) + np.einsum("kcai,ck->ai", Via, t1)
+        n1 += -0.5 * np.einsum("dack,cidk->ai", Vaaai - Vaaai.transpose(2, 1, 0, 3), Taa)
+        n1 += -0.5 * np.einsum("clik,akcl->ai", VS, Taa)
+        n1 += np.einsum("cabj,cibj->ai", Vaaai, T2) - np.einsum("ikbj,akbj->ai", Voovo, T2)
+        new = sym(0.5 * V - np.einsum("kibj,ak->aibj", Voovo, t1) + np.einsum("acbj,ci->aibj", Vaaai, t1))
+        new += np.einsum("akbl,kilj->aibj", T2, Vo)
+        TY = np.einsum("iack->aick", Via) - np.einsum("caik->aick", Vaa)
+        new += sym(np.einsum("aick,ckbj->aibj", TY, T2))
+        W = np.einsum("ckai->ckia", T2) - np.einsum("ciak->ckia", T2)
+        new += sym(np.einsum("ckia,iabj->ckbj", W, Via))
+        new += sym(-np.einsum("akcj,bcki->aibj", T2, Vaa))
+        tao = np.einsum("aibj,ma,nb->minj", T2, cv, cv)
+        new += np.einsum("minj,ma,nb->aibj", np.einsum("lmsn,lisj->minj", ao, tao), cv, cv)
+        t1, T2 = n1 / D1, 0.5 * sym(new) / D2
+        e = en(T2)
+        if abs(e - e_old) < tol:
+            return e, t1
+        e_old = e
+    raise AssertionError("dense LCCSD did not converge")
+
+
+@pytest.mark.parametrize("case", ["all_dat", "all_fine"])
+def test_lccsd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, case):
+    inp = lw.inputs(case)
+    g_corr, g_total = lw.golden_lccsd()
+    tol = lw.GOLDEN["tolerance"]
+    e_dense, t1_dense = dense_lccsd(inp)
+    assert abs(e_dense - g_corr) < tol
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM_LCCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=120)
+    e_corr = hist[-1]
+    assert abs(e_corr - g_corr) < tol                      # lccsd_correlation -0.12865706498547 @ 1e-10
+    assert abs(e_corr + inp["e_scf"] - g_total) < tol      # lccsd_energy -75.71298380772593 @ 1e-10
+    assert abs(e_corr - e_dense) < 1e-11
+    t1 = qm.join_blocks(inp["arrays"]["t1a_old"], [inp["segs"]["v"], inp["segs"]["o"]])
+    assert np.max(np.abs(t1 - t1_dense)) < 1e-9 and np.max(np.abs(t1_dense)) > 1e-4    # the singles really are non-zero
+    assert not w.locals                                    # every allocated local array was deallocated
