@@ -1,0 +1,169 @@
+"""A numpy stand-in for the PYTHON surface of aces4_b200.api that the SIAL front-end's DeviceBackend and the device
+energy tests touch -- blocks as Fortran-ordered numpy arrays, the arithmetic done by the CPU oracle.  TEST
+INFRASTRUCTURE: it exists so that the host-side logic of tests that have not yet seen a GPU (DeviceBackend's scalar
+handling across iterations, local arrays, the test bodies themselves) can be executed here, numerically, on the CPU
+(tests/test_device_tests_on_fake_api_cpu.py).  It says nothing about libsipgpu itself; nothing in aces4_b200/ imports it."""
+import itertools
+
+import numpy as np
+
+
+class _Lib:
+    def __init__(self, api):
+        self.api = api
+
+    def sipgpu_h2d(self, ptr, host, n):
+        blk = self.api._by_ptr[ptr]
+        blk.a[...] = np.asarray(host).reshape(blk.a.shape, order="F")
+        return 0
+
+    def sipgpu_block_dot_accumulate(self, lptr, rptr, n, accptr):
+        L, R, acc = (self.api._by_ptr[p] for p in (lptr, rptr, accptr))
+        acc.a[...] += float(np.sum(L.a * R.a))
+        self.api._launches += 1
+        return 0
+
+
+class FakeApi:
+    def __init__(self, oracle):
+        self.o = oracle
+        self._by_ptr = {}
+        self._ptr = itertools.count(0x1000, 0x1000)
+        self._launches = 0
+        self._moa = None
+        self._lib = _Lib(self)
+        api = self
+
+        class DeviceBlock:
+            def __init__(self, shape, zero=False, a=None):
+                self.shape = tuple(int(x) for x in shape)
+                self.a = a if a is not None else np.full(self.shape, 0.0 if zero else np.nan, order="F")
+                self.size, self.rank = int(self.a.size), len(self.shape)
+                self.ptr = next(api._ptr)
+                api._by_ptr[self.ptr] = self
+
+            @classmethod
+            def from_numpy(cls, a):
+                return cls(a.shape, a=np.array(a, order="F", dtype=float))
+
+            def to_numpy(self):
+                return np.array(self.a, order="F")
+
+            def free(self):
+                api._by_ptr.pop(self.ptr, None)
+                self.a = None
+
+            def _op(self):
+                api._launches += 1
+                return self
+
+            def fill(self, v):
+                self.a[...] = v
+                return self._op()
+
+            def scale(self, f):
+                self.a *= f
+                return self._op()
+
+            def increment(self, d):
+                self.a += d
+                return self._op()
+
+            def axpy(self, other, f):
+                self.a[...] = api.o.block_add(self.a, other.a, f)[0]
+                return self._op()
+
+            def accumulate(self, other):
+                return self.axpy(other, 1.0)
+
+            def scale_and_copy(self, other, f):
+                self.a[...] = f * other.a
+                return self._op()
+
+        class DistArray:
+            def __init__(self, seg_ext_per_index, my_rank=0, world=1, exchange=None, devices=None):
+                assert world == 1
+                self.seg_ext = [list(map(int, s)) for s in seg_ext_per_index]
+                self.blocks = {}
+
+            def block_shape(self, idx):
+                return tuple(self.seg_ext[d][i - 1] for d, i in enumerate(idx))
+
+            def owner(self, idx):
+                return 0
+
+            def block_view(self, idx):
+                idx = tuple(int(i) for i in idx)
+                if idx not in self.blocks:
+                    self.blocks[idx] = DeviceBlock(self.block_shape(idx), zero=True)
+                return self.blocks[idx]
+
+            def get(self, idx, out=None):
+                return DeviceBlock.from_numpy(self.block_view(idx).a)
+
+            def put(self, idx, blk):
+                self.block_view(idx).scale_and_copy(blk, 1.0)
+
+            def put_accumulate(self, idx, blk):
+                self.block_view(idx).accumulate(blk)
+
+            def put_initialize(self, idx, v):
+                self.block_view(idx).fill(v)
+
+            def fill_local(self, v):
+                for b in self.blocks.values():
+                    b.fill(v)
+
+            def destroy(self):
+                self.blocks = None
+
+        self.DeviceBlock, self.DistArray = DeviceBlock, DistArray
+
+    # ---- module-level functions of aces4_b200.api ----
+    def lib(self):
+        return self._lib
+
+    @staticmethod
+    def _check(rc, what=""):
+        assert rc == 0, what
+
+    @staticmethod
+    def _hp(a):
+        return a
+
+    def sync(self):
+        pass
+
+    def kernel_launches(self):
+        return self._launches
+
+    def wl_begin(self, dry=False):
+        pass
+
+    def wl_end(self):
+        return {}
+
+    def set_predefined_int_array(self, name, values):
+        assert name == "moa_seg_ranges"
+        self._moa = list(values)
+
+    def permute_labels(self, lhs_labels, rhs_labels, rhs, out=None):
+        res = self.o.permute_labels(list(lhs_labels), list(rhs_labels), rhs.a)
+        if out is None:
+            return self.DeviceBlock.from_numpy(res)
+        out.a[...] = res
+        self._launches += 1
+        return out
+
+    def contract_labels(self, dlab, dext, llab, L, rlab, R, out=None, alpha=1.0, beta=0.0):
+        res, ierr = self.o.contract_labels(list(dlab), list(dext), list(llab), L.a, list(rlab), R.a)
+        assert ierr == 0
+        if out is None:
+            out = self.DeviceBlock(tuple(dext), zero=True)
+        out.a[...] = alpha * res.reshape(out.a.shape, order="F") + (beta * out.a if beta != 0.0 else 0.0)
+        self._launches += 1
+        return out
+
+    def si_energy_denominator_rhf(self, block, index_values, fock):
+        self._launches += 1
+        return self.o.si_energy_denominator_rhf(block.a, list(index_values), fock.a, self._moa)

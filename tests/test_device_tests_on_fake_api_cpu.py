@@ -1,0 +1,27 @@
+"""The bodies of the device energy tests (tests/test_gpu_z_lccd_water_energy.py), executed on the CPU against a numpy
+stand-in for the Python API of libsipgpu (tests/fake_device_api.py).  Those GPU tests were written after the round's
+GPU minutes were spent; this runs everything in them that is not the CUDA library -- the front-end's DeviceBackend
+(device-resident scalars across iterations, block views, put / get traffic, local arrays) and the assertions of the
+tests themselves -- so that what remains unexercised until the first B200 run is libsipgpu's arithmetic alone, which the
+rest of the GPU suite has already covered op by op."""
+import pytest
+
+import test_gpu_z_cross_product as xp
+import test_gpu_z_lccd_water_energy as dev
+from fake_device_api import FakeApi
+
+
+@pytest.mark.parametrize("case,record", [("fine", True), ("dat", False), ("all_fine", True)])
+def test_lccd_device_test_body_on_the_fake_api(oracle, case, record):
+    dev.test_lccd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), case, record)
+
+
+@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", False)])
+def test_lccsd_device_test_body_on_the_fake_api(oracle, case, record):
+    dev.test_lccsd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), case, record)
+
+
+def test_cross_product_test_bodies_on_the_fake_api(oracle):
+    """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
+    xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)
+    xp.test_full_cross_product_s32_equivariance(FakeApi(oracle), oracle, s=3)

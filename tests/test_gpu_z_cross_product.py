@@ -24,8 +24,7 @@ def sip():
 
 
 @pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
-def test_full_cross_product_s16_against_the_oracle(sip, oracle):
-    s = 16
+def test_full_cross_product_s16_against_the_oracle(sip, oracle, s=16):
     rng = np.random.default_rng(16)
     L0, R0 = rand_block(rng, (s,) * 4), rand_block(rng, (s,) * 4)
     dL, dR = sip.DeviceBlock.from_numpy(L0), sip.DeviceBlock.from_numpy(R0)
@@ -42,12 +41,11 @@ def test_full_cross_product_s16_against_the_oracle(sip, oracle):
             worst = max(worst, e)
     finally:
         oracle.use_naive_gemm()
-    print(f"\n1728 patterns at s=16: worst relative error {worst:.2e}")
+    print(f"\n1728 patterns at s={s}: worst relative error {worst:.2e}")
 
 
 @pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
-def test_full_cross_product_s32_equivariance(sip, oracle):
-    s = 32
+def test_full_cross_product_s32_equivariance(sip, oracle, s=32):
     rng = np.random.default_rng(32)
     L0, R0 = rand_block(rng, (s,) * 4), rand_block(rng, (s,) * 4)
     dL, dR = sip.DeviceBlock.from_numpy(L0), sip.DeviceBlock.from_numpy(R0)
@@ -79,4 +77,4 @@ def test_full_cross_product_s32_equivariance(sip, oracle):
                 oracle.use_naive_gemm()
             assert oerr == 0 and relerr(ref.reshape(want.shape), want) <= TOL
     assert len(checked_canonical) == 6
-    print(f"\n1728 patterns at s=32: worst relative difference to the canonical-order product {worst:.2e}")
+    print(f"\n1728 patterns at s={s}: worst relative difference to the canonical-order product {worst:.2e}")
