@@ -205,3 +205,112 @@ def test_ccsd_fragment_on_the_oracle_backend_matches_dense_einsum(oracle, world)
     assert np.allclose(dense(arrays["t1a_new"], "vo", segs), 0.5 * np.einsum("aibj,bj->ai", tau, F), rtol=1e-12, atol=1e-15)
     e_ref = np.einsum("aibj,aibj->", 2.0 * V - np.transpose(V, (0, 3, 2, 1)), tau)
     assert abs(esum - e_ref) <= 1e-12 * abs(e_ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# procedures, local arrays, p-index arrays, static arrays, absolute index values (used by tests/golden/lcc*_program.sialx)
+# ---------------------------------------------------------------------------------------------------------------------
+DECL = """
+moaindex i = baocc: eaocc
+moaindex j = baocc: eaocc
+moaindex a = bavirt: eavirt
+moaindex p = baocc: eavirt
+moaindex q = baocc: eavirt
+aoindex mu = 1: norb
+served F[p,q]
+static ca[mu,p]
+served OUT[a,i]
+served S[i,j]
+temp T[a,i]
+temp U[a,i]
+local L[a,i]
+scalar x
+"""
+
+
+def test_procedures_run_only_when_called_and_fragments_run_in_order(oracle):
+    text = DECL + """
+    proc one
+    x += 1.0
+    endproc one
+    proc ten
+    x += 10.0
+    call one
+    endproc ten
+    """
+    frag = Program(text)                       # procedures only: a fragment, textual order (1 + 10 + 1)
+    assert list(frag.procs) == ["one", "ten"]
+    assert Walker(frag, OracleBackend(oracle, {}), {"o": [1], "v": [1]}).run()["x"] == 12.0
+    main = Program(text + "call ten\ncall ten\n")   # with a main program only the calls run
+    w = Walker(main, OracleBackend(oracle, {}), {"o": [1], "v": [1]})
+    assert w.run()["x"] == 22.0
+    assert w.run_proc("one")["x"] == 23.0
+    with pytest.raises(SialSyntaxError):
+        w.run_proc("nope")
+
+
+@pytest.mark.parametrize("bad", ["proc a\nproc b\nendproc b\nendproc a\n", "endproc a\n", "proc a\n", "proc a\nendproc a\nproc a\nendproc a\n",
+                                 "pardo i\nproc a\nendproc a\nendpardo i\n", "call\n", "allocate L\n"])
+def test_parser_rejects_malformed_procedures(bad):
+    with pytest.raises(SialSyntaxError):
+        Program("moaindex i = baocc: eaocc\n" + bad)
+
+
+def test_p_index_arrays_static_arrays_and_local_arrays(oracle):
+    """F[p,q] addressed with occupied and virtual labels (segment number of a virtual label shifted by the number of
+    occupied segments), ca[mu,a] read as a slice of a static array, a local array that outlives `do` scopes and is
+    zero-filled on allocation"""
+    segs = {"o": [2, 1], "v": [3, 2], "ao": [4]}
+    rng = np.random.default_rng(5)
+    n = 8
+    Fd = rng.uniform(-1, 1, (n, n))
+    cad = rng.uniform(-1, 1, (4, n))
+    from oracle import qm_inputs as qm
+    pseg = segs["o"] + segs["v"]
+    arrays = {"f": qm.split_blocks(Fd, [pseg, pseg]), "ca": qm.split_blocks(cad, [segs["ao"], pseg]), "out": {}, "s": {}}
+    text = DECL + """
+    pardo a, i
+        request F[a,i]
+        allocate L[a,*]
+        do j
+            request F[a,j]
+            T[a,j] = F[a,j]
+            L[a,j] += T[a,j]
+            L[a,j] += T[a,j]
+        enddo j
+        T[a,i]  = L[a,i]
+        U[a,i]  = F[a,i]
+        T[a,i] -= U[a,i]
+        prepare OUT[a,i] = T[a,i]
+        deallocate L[a,*]
+    endpardo a, i
+    pardo i, j
+        request F[i,j]
+        prepare S[i,j] = F[i,j]
+    endpardo i, j
+    """
+    w = Walker(Program(text), OracleBackend(oracle, arrays), segs)
+    w.run()
+    assert not w.locals
+    got = qm.join_blocks(arrays["out"], [segs["v"], segs["o"]])
+    assert np.max(np.abs(got - Fd[3:, :3])) < 1e-15   # 2F - F
+    assert np.array_equal(qm.join_blocks(arrays["s"], [segs["o"], segs["o"]]), Fd[:3, :3])
+    # an ao label cannot address a p dimension, and a local array must be declared `local`
+    with pytest.raises(SialSyntaxError):
+        Walker(Program(DECL + "pardo mu, i\nrequest F[mu,i]\nendpardo mu, i\n"), OracleBackend(oracle, arrays), segs).run()
+    with pytest.raises(SialSyntaxError):
+        Walker(Program(DECL + "pardo a\nallocate T[a,*]\nendpardo a\n"), OracleBackend(oracle, arrays), segs).run()
+
+
+def test_super_instructions_receive_absolute_index_values(oracle):
+    """moa segments [1 | 2 2 | 3 5] with occ = segments 2..3 and virt = 4..5: energy_denominator_rhf must see 2..5"""
+    seen = []
+
+    class Spy(OracleBackend):
+        def execute(self, fname, blocks, segs, kinds, bare):
+            seen.append((fname, segs[0], tuple(kinds[0]), tuple(bare)))
+
+    text = DECL + "pardo a, i\nT[a,i] = 1.0\nexecute energy_denominator_rhf T[a,i] fock_a\nendpardo a, i\n"
+    Walker(Program(text), Spy(oracle, {}), {"o": [2, 2], "v": [3, 5]}, index_base={"o": 1, "v": 3}).run()
+    assert sorted(s[1] for s in seen) == [(4, 2), (4, 3), (5, 2), (5, 3)]
+    assert seen[0][0] == "energy_denominator_rhf" and seen[0][2] == ("v", "o") and seen[0][3] == ("fock_a",)
