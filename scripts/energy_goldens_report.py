@@ -1,0 +1,49 @@
+"""Energy-level parity report (CPU, oracle backend): the reference's golden energies of test/test_qm.cpp for water /
+3-21G next to the values obtained by walking tests/golden/lccd_program.sialx and lccsd_program.sialx block by block with
+the SIAL front-end on the CPU oracle.  python scripts/energy_goldens_report.py > profiles/r01_energy_goldens_oracle_backend.txt
+(the device rows come from `pytest -m gpu -s tests/test_gpu_z_lccd_water_energy.py`)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import lccd_water as lw  # noqa: E402
+from aces4_b200.sial_frontend import Program, Walker  # noqa: E402
+from oracle import oracle  # noqa: E402
+from sial_oracle_backend import OracleBackend  # noqa: E402
+
+oracle.lib()
+rows = []
+for name in (lw.FROZEN, lw.ALL):
+    e = lw.scf(name)[5]
+    g = lw.GOLDEN["scf_energy"]
+    rows.append((f"scf_energy ({name})", g, e, "numpy input stage (oracle/qm_inputs.py)", "-", "-"))
+for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "all_fine")),
+                             ("lccsd", lw.PROGRAM_LCCSD, ("all_dat", "all_fine"))):
+    for case in cases:
+        inp = lw.inputs(case)
+        be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+        w = Walker(Program(text), be, inp["segs"], index_base=inp["index_base"])
+        t0 = time.time()
+        e_mp2, hist = lw.converge(w, be.value, max_iter=120)
+        dt = time.time() - t0
+        seg = f"occ {inp['segs']['o']} virt {inp['segs']['v']} ao {inp['segs']['ao']}"
+        how = f"{program} program, {seg}"
+        if program == "lccd":
+            g_corr, g_tot, g_mp2 = lw.golden(case)
+            if g_corr is not None:
+                rows.append(("lccd_correlation (frozen core)", g_corr, hist[-1], how, len(hist), be.calls))
+            rows.append((f"lccd_energy ({'frozen core' if g_corr is not None else 'all electron'})", g_tot,
+                         hist[-1] + inp["e_scf"], how, len(hist), be.calls))
+            if g_mp2 is not None:
+                rows.append(("mp2_energy (all electron)", g_mp2, e_mp2 + inp["e_scf"], how, 0, "-"))
+        else:
+            g_corr, g_tot = lw.golden_lccsd()
+            rows.append(("lccsd_correlation (all electron)", g_corr, hist[-1], how, len(hist), be.calls))
+            rows.append(("lccsd_energy (all electron)", g_tot, hist[-1] + inp["e_scf"], how, len(hist), be.calls))
+print("reference goldens: test/test_qm.cpp (ASSERT_NEAR 1e-10); north_star tolerance 1e-9 Hartree")
+print(f"{'quantity':38s} {'reference golden':>20s} {'reproduced':>20s} {'diff':>9s}  iters  block ops  how")
+for q, g, v, how, it, ops in rows:
+    print(f"{q:38s} {g:20.14f} {v:20.14f} {v - g:9.1e}  {it!s:>5s}  {ops!s:>9s}  {how}")
