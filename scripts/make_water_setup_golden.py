@@ -17,7 +17,10 @@ GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_te
     # without drop_mo) and :732-733, 758-759 (DISABLED_eom_mp2_test: mp2_rhf_disc.siox)
     "all_electron": {"scf_energy": -75.58432674274034, "lccd_energy": -75.71210049055006, "mp2_energy": -75.70540831822183,
                      # test/test_qm.cpp:526-529 (DISABLED_lccsd_test: rlccsd_rhf.siox, all electron)
-                     "lccsd_correlation": -0.12865706498547, "lccsd_energy": -75.71298380772593}}
+                     "lccsd_correlation": -0.12865706498547, "lccsd_energy": -75.71298380772593,
+                     # test/test_qm.cpp:252-253 (DISABLED_eom_test: rccsd_rhf.siox, cc_conv 1e-12) and :907-908 / :990-991
+                     # (eom_ccsd_water_right_test / eom_ccsd_water_test = BASELINE config 3: the same run stopped at cc_conv 1e-10)
+                     "ccsd_energy": -75.71251002928709, "ccsd_energy_cc_conv_1e-10": -75.71251002936883}}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())

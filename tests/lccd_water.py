@@ -14,6 +14,7 @@ from oracle import qm_inputs as qm
 HERE = os.path.dirname(os.path.abspath(__file__))
 PROGRAM = open(os.path.join(HERE, "golden", "lccd_program.sialx")).read()
 PROGRAM_LCCSD = open(os.path.join(HERE, "golden", "lccsd_program.sialx")).read()
+PROGRAM_CCSD = open(os.path.join(HERE, "golden", "ccsd_program.sialx")).read()
 FIXTURE = json.load(open(os.path.join(HERE, "golden", "water_321g_setup.json")))
 GOLDEN = FIXTURE["golden"]
 # array name -> index kinds of its declared dimensions
@@ -22,8 +23,14 @@ KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"),
          "tao_ab": ("ao", "o", "ao", "o"), "t2ao_ab": ("ao", "o", "ao", "o"), "tdaixj": ("v", "o", "ao", "o"),
          # LCCSD only (tests/golden/lccsd_program.sialx)
          "vspipi": ("p", "o", "p", "o"), "vaaai": ("v", "v", "v", "o"), "t2old_aa": ("v", "o", "v", "o"),
-         "t1a_old": ("v", "o"), "t1a_new": ("v", "o")}
-EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a_old", "t1a_new")
+         "t1a_old": ("v", "o"), "t1a_new": ("v", "o"),
+         # CCSD only (tests/golden/ccsd_program.sialx)
+         "tau_ab": ("v", "o", "v", "o"), "taup_ab": ("v", "o", "v", "o"), "taup_aa": ("v", "o", "v", "o"),
+         "e5aiai": ("v", "o", "v", "o"), "e5aibj": ("v", "o", "v", "o"), "e6aibj": ("v", "o", "v", "o"),
+         "wiibb": ("o", "o", "v", "v"), "t1a_ax": ("v", "ao"), "fae_a": ("v", "v"), "fme_a": ("o", "v"),
+         "fmi_a": ("o", "o"), "wminj_ab": ("o", "o", "o", "o")}
+EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a_old", "t1a_new", "tau_ab", "taup_ab",
+         "taup_aa", "e5aiai", "e5aibj", "e6aibj", "wiibb", "t1a_ax", "fae_a", "fme_a", "fmi_a", "wminj_ab")
 # cases: (setup file, segmentation).  Segmentations: the .dat's own (frozen core: moa [1 | 4 | 8], ao [11, 2]; all
 # electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
 FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"
@@ -37,6 +44,12 @@ def golden(case):
         return GOLDEN["lccd_correlation"], GOLDEN["lccd_energy"], None
     g = GOLDEN["all_electron"]
     return None, g["lccd_energy"], g["mp2_energy"]
+
+
+def golden_ccsd():
+    """(ccsd_energy converged to 1e-12, the same run stopped at 1e-10) of the reference's eom_test / eom_ccsd_water_test"""
+    g = GOLDEN["all_electron"]
+    return g["ccsd_energy"], g["ccsd_energy_cc_conv_1e-10"]
 
 
 def golden_lccsd():

@@ -103,3 +103,29 @@ def test_lccsd_energy_on_the_device_matches_the_reference_golden(sip, case, reco
     assert not w.locals
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
+@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", True), ("all_dat", False)])
+def test_ccsd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
+    """tests/golden/ccsd_program.sialx = src/sialx/qm/cc/rccsd_rhf.sialx (22 procedures) against the ground-state energy
+    of BASELINE config 3: ccsd_energy -75.71251002928709 (eom_test, cc_conv 1e-12, test/test_qm.cpp:252-253) and
+    -75.71251002936883 (eom_ccsd_water_test, the same run stopped at cc_conv 1e-10, :990-991)"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs(case)
+    g_tight, g_loose = lw.golden_ccsd()
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=record)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    e_total = hist[-1] + inp["e_scf"]
+    print(f"\nCCSD water/3-21G on the device ({case}, record={record}): ccsd_energy {e_total:.14f} after {len(hist)} "
+          f"iterations (golden {g_tight:.14f})")
+    assert abs(e_total - g_tight) < 1e-10          # north_star: 1e-9 Hartree
+    assert abs(e_total - g_loose) < lw.GOLDEN["tolerance"]
+    assert not w.locals
+    for A in arrays.values():
+        A.destroy()

@@ -1,4 +1,4 @@
-"""The full LCCD and LCCSD programs (tests/golden/lccd_program.sialx, lccsd_program.sialx) walked on the DEVICE backend without a GPU: the deferred op
+"""The full LCCD, LCCSD and CCSD programs (tests/golden/lccd_program.sialx, lccsd_program.sialx, ccsd_program.sialx) walked on the DEVICE backend without a GPU: the deferred op
 stream in DRY mode (fake device addresses, nothing executes) takes every C-ABI call the GPU energy test
 (tests/test_gpu_z_lccd_water_energy.py) will make -- label validation, pattern analysis, the recorder and the
 scheduler all run on the host.  Checks that the program is accepted end to end, that the schedule honours the hazards
@@ -54,11 +54,12 @@ class DryBackend(DeviceBackend):
 
 
 @pytest.mark.parametrize("segmentation,program", [("dat", "lccd"), ("fine", "lccd"), ("all_dat", "lccd"),
-                                                  ("all_fine", "lccd"), ("all_dat", "lccsd"), ("all_fine", "lccsd")])
+                                                  ("all_fine", "lccd"), ("all_dat", "lccsd"), ("all_fine", "lccsd"),
+                                                  ("all_dat", "ccsd"), ("all_fine", "ccsd")])
 def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation, program):
     inp = lw.inputs(segmentation)
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
-    prog = Program(lw.PROGRAM if program == "lccd" else lw.PROGRAM_LCCSD)
+    prog = Program({"lccd": lw.PROGRAM, "lccsd": lw.PROGRAM_LCCSD, "ccsd": lw.PROGRAM_CCSD}[program])
     with sip.recording(dry=True):
         arrays = {name: DryArray(sip, [inp["segs"][k] for k in kinds]) for name, kinds in lw.KINDS.items()}
         be = DryBackend(sip, arrays, record=False)       # one recording around everything (ended by the with block)

@@ -173,3 +173,25 @@ def test_lccsd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle,
     t1 = qm.join_blocks(inp["arrays"]["t1a_old"], [inp["segs"]["v"], inp["segs"]["o"]])
     assert np.max(np.abs(t1 - t1_dense)) < 1e-9 and np.max(np.abs(t1_dense)) > 1e-4    # the singles really are non-zero
     assert not w.locals                                    # every allocated local array was deallocated
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CCSD (tests/golden/ccsd_program.sialx = src/sialx/qm/cc/rccsd_rhf.sialx): BASELINE config 3's ground-state energy
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["all_dat", "all_fine"])
+def test_ccsd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, case):
+    """the reference's CCSD program (22 procedures: tau, Fae / Fmi / Fme, T1, Wminj, the t1-dressed AO ladder, Wmebj /
+    Wmjbe ring terms, ...) against ccsd_energy of eom_test (-75.71251002928709, cc_conv 1e-12; test_qm.cpp:252-253) and
+    of eom_ccsd_water_test (-75.71251002936883: the same run stopped at cc_conv 1e-10; :990-991)"""
+    inp = lw.inputs(case)
+    g_tight, g_loose = lw.golden_ccsd()
+    tol = lw.GOLDEN["tolerance"]
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    e_mp2, hist = lw.converge(w, be.value, max_iter=150)
+    e_total = hist[-1] + inp["e_scf"]
+    assert abs(e_mp2 + inp["e_scf"] - lw.GOLDEN["all_electron"]["mp2_energy"]) < tol
+    assert abs(e_total - g_tight) < 1e-11          # measured: 6.3e-13
+    assert abs(e_total - g_loose) < tol            # the reference's own 1e-10 around its loosely converged value
+    t1 = qm.join_blocks(inp["arrays"]["t1a_old"], [inp["segs"]["v"], inp["segs"]["o"]])
+    assert np.max(np.abs(t1)) > 1e-3 and not w.locals
