@@ -1,5 +1,6 @@
 """Energy-level parity report (CPU, oracle backend): the reference's golden energies of test/test_qm.cpp for water /
-3-21G next to the values obtained by walking tests/golden/lccd_program.sialx and lccsd_program.sialx block by block with
+3-21G (and hydrogen fluoride) next to the values obtained by walking tests/golden/lccd_program.sialx, lccsd_program.sialx
+and ccsd_program.sialx block by block with
 the SIAL front-end on the CPU oracle.  python scripts/energy_goldens_report.py > profiles/r01_energy_goldens_oracle_backend.txt
 (the device rows come from `pytest -m gpu -s tests/test_gpu_z_lccd_water_energy.py`)."""
 import os
@@ -16,18 +17,19 @@ from sial_oracle_backend import OracleBackend  # noqa: E402
 
 oracle.lib()
 rows = []
-for name in (lw.FROZEN, lw.ALL):
+for name, g in ((lw.FROZEN, lw.GOLDEN["scf_energy"]), (lw.ALL, lw.GOLDEN["scf_energy"]),
+                ("second_ccsdpt_test.dat", lw.GOLDEN["hf"]["scf_energy"])):
     e = lw.scf(name)[5]
-    g = lw.GOLDEN["scf_energy"]
     rows.append((f"scf_energy ({name})", g, e, "numpy input stage (oracle/qm_inputs.py)", "-", "-"))
 for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "all_fine")),
-                             ("lccsd", lw.PROGRAM_LCCSD, ("all_dat", "all_fine"))):
+                             ("lccsd", lw.PROGRAM_LCCSD, ("all_dat", "all_fine")),
+                             ("ccsd", lw.PROGRAM_CCSD, ("all_dat", "all_fine", "hf_dat", "hf_fc_dat", "hf_fc_fine"))):
     for case in cases:
         inp = lw.inputs(case)
         be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
         w = Walker(Program(text), be, inp["segs"], index_base=inp["index_base"])
         t0 = time.time()
-        e_mp2, hist = lw.converge(w, be.value, max_iter=120)
+        e_mp2, hist = lw.converge(w, be.value, max_iter=150)
         dt = time.time() - t0
         seg = f"occ {inp['segs']['o']} virt {inp['segs']['v']} ao {inp['segs']['ao']}"
         how = f"{program} program, {seg}"
@@ -39,6 +41,17 @@ for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "al
                          hist[-1] + inp["e_scf"], how, len(hist), be.calls))
             if g_mp2 is not None:
                 rows.append(("mp2_energy (all electron)", g_mp2, e_mp2 + inp["e_scf"], how, 0, "-"))
+        elif program == "ccsd":
+            e_tot = hist[-1] + inp["e_scf"]
+            if case.startswith("all"):
+                g_tight, g_loose = lw.golden_ccsd()
+                rows.append(("ccsd_energy water (cc_conv 1e-12)", g_tight, e_tot, how, len(hist), be.calls))
+                rows.append(("ccsd_energy water (cc_conv 1e-10)", g_loose, e_tot, how, len(hist), be.calls))
+            elif case == "hf_dat":
+                rows.append(("ccsd_correlation HF (cc_conv 1e-10)", lw.GOLDEN["hf"]["ccsd_correlation"], hist[-1], how, len(hist), be.calls))
+                rows.append(("ccsd_energy HF (cc_conv 1e-10)", lw.GOLDEN["hf"]["ccsd_energy"], e_tot, how, len(hist), be.calls))
+            else:
+                rows.append(("ccsd_energy HF frozen core (1e-12)", lw.GOLDEN["hf"]["frozen_core_ccsd_energy"], e_tot, how, len(hist), be.calls))
         else:
             g_corr, g_tot = lw.golden_lccsd()
             rows.append(("lccsd_correlation (all electron)", g_corr, hist[-1], how, len(hist), be.calls))

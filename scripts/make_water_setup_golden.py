@@ -21,8 +21,13 @@ GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_te
                      # test/test_qm.cpp:252-253 (DISABLED_eom_test: rccsd_rhf.siox, cc_conv 1e-12) and :907-908 / :990-991
                      # (eom_ccsd_water_right_test / eom_ccsd_water_test = BASELINE config 3: the same run stopped at cc_conv 1e-10)
                      "ccsd_energy": -75.71251002928709, "ccsd_energy_cc_conv_1e-10": -75.71251002936883}}
+# hydrogen fluoride / 3-21G: test/test_qm.cpp:86-102 (second_ccsdpt_test, the CCSD stage of the reference's enabled CCSD(T) test;
+# cc_conv 1e-10) and :810-824 (lamccsdpt_test: drop_mo=1-1, cc_conv 1e-12)
+GOLDEN["hf"] = {"scf_energy": -99.45975176375698, "ccsd_correlation": -0.12588695910754, "ccsd_energy": -99.58563872286452,
+                "frozen_core_ccsd_energy": -99.583972376431}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
-for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat"):
+for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
+             "lamccsdpt_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

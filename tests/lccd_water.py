@@ -1,4 +1,5 @@
-"""Shared driver of the LCCD energy tests (water / 3-21G / frozen core, the reference's lccd_frozencore_test): inputs from
+"""Shared driver of the energy tests (water / 3-21G: the reference's lccd_frozencore_test, eom_lccd_test, eom_mp2_test,
+lccsd_test, eom_test / eom_ccsd_water_test; hydrogen fluoride / 3-21G: second_ccsdpt_test, lamccsdpt_test): inputs from
 the decoded `.dat` (tests/golden/water_321g_setup.json) through oracle/qm_inputs.py (numpy integrals + RHF, test
 infrastructure), then the reference's LCCD amplitude equations (tests/golden/lccd_program.sialx) walked block by block
 by aces4_b200/sial_frontend.py on a backend -- the CPU oracle here, libsipgpu in tests/test_gpu_lccd_water_energy.py --
@@ -35,7 +36,10 @@ EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a
 # electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
 FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"
 CASES = {"dat": (FROZEN, None), "fine": (FROZEN, {"moa": [1, 2, 2, 3, 5], "occ": (2, 3), "virt": (4, 5), "ao": [6, 5, 2]}),
-         "all_dat": (ALL, None), "all_fine": (ALL, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]})}
+         "all_dat": (ALL, None), "all_fine": (ALL, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]}),
+         # hydrogen fluoride / 3-21G (the reference's second_ccsdpt_test and lamccsdpt_test): all electron, frozen core
+         "hf_dat": ("second_ccsdpt_test.dat", None), "hf_fc_dat": ("lamccsdpt_test.dat", None),
+         "hf_fc_fine": ("lamccsdpt_test.dat", {"moa": [1, 3, 1, 2, 4], "occ": (2, 3), "virt": (4, 5), "ao": [3, 6, 2]})}
 
 
 def golden(case):

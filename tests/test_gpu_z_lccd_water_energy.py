@@ -129,3 +129,23 @@ def test_ccsd_energy_on_the_device_matches_the_reference_golden(sip, case, recor
     assert not w.locals
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
+def test_ccsd_energy_of_hydrogen_fluoride_on_the_device(sip):
+    """second molecule, frozen core, block-wise segmentation: ccsd_energy -99.583972376431 of the reference's
+    lamccsdpt_test (test/test_qm.cpp:823-824)"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs("hf_fc_fine")
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=True)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    e_total = hist[-1] + inp["e_scf"]
+    print(f"\nCCSD HF/3-21G frozen core on the device: ccsd_energy {e_total:.14f} after {len(hist)} iterations")
+    assert abs(e_total - lw.GOLDEN["hf"]["frozen_core_ccsd_energy"]) < lw.GOLDEN["tolerance"]
+    for A in arrays.values():
+        A.destroy()

@@ -28,7 +28,7 @@ def test_boys_function_against_quadrature():
 def test_inputs_reproduce_the_reference_scf_energy(setup_name):
     setup, basis, S, eri, e_nuc, e_scf, eps, C = lw.scf(setup_name)
     assert abs(e_nuc - setup["scalars"]["nn_repulsion"]) < 1e-12          # geometry decoded as the reference reads it
-    assert np.allclose(C.T @ S @ C, np.eye(13), atol=1e-10)
+    assert np.allclose(C.T @ S @ C, np.eye(len(S)), atol=1e-10)
     for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)]:
         assert np.max(np.abs(eri - eri.transpose(perm))) < 1e-13
     assert abs(e_scf - lw.GOLDEN["scf_energy"]) < lw.GOLDEN["tolerance"]  # -75.58432674274046 @ 1e-10
@@ -195,3 +195,22 @@ def test_ccsd_energy_on_the_oracle_backend_matches_the_reference_golden(oracle, 
     assert abs(e_total - g_loose) < tol            # the reference's own 1e-10 around its loosely converged value
     t1 = qm.join_blocks(inp["arrays"]["t1a_old"], [inp["segs"]["v"], inp["segs"]["o"]])
     assert np.max(np.abs(t1)) > 1e-3 and not w.locals
+
+
+@pytest.mark.parametrize("case", ["hf_dat", "hf_fc_dat", "hf_fc_fine"])
+def test_ccsd_energy_of_hydrogen_fluoride_matches_the_reference_golden(oracle, case):
+    """a second molecule: the CCSD stage of the reference's enabled CCSD(T) test (second_ccsdpt_test: ccsd_correlation
+    -0.12588695910754, ccsd_energy -99.58563872286452, cc_conv 1e-10; test_qm.cpp:86-102) and of lamccsdpt_test (frozen
+    core, ccsd_energy -99.583972376431, cc_conv 1e-12; :810-824)"""
+    inp = lw.inputs(case)
+    g, tol = lw.GOLDEN["hf"], lw.GOLDEN["tolerance"]
+    assert abs(inp["e_scf"] - g["scf_energy"]) < tol          # -99.45975176375698: pins the inputs of this molecule
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    if case == "hf_dat":
+        assert abs(hist[-1] - g["ccsd_correlation"]) < tol                       # measured 9.1e-12
+        assert abs(hist[-1] + inp["e_scf"] - g["ccsd_energy"]) < tol
+    else:
+        assert abs(hist[-1] + inp["e_scf"] - g["frozen_core_ccsd_energy"]) < tol   # measured 1.7e-12
+    assert not w.locals
