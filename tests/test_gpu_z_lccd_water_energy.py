@@ -106,7 +106,7 @@ def test_lccsd_energy_on_the_device_matches_the_reference_golden(sip, case, reco
 
 
 @pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
-@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", True), ("all_dat", False)])
+@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", False)])
 def test_ccsd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
     """tests/golden/ccsd_program.sialx = src/sialx/qm/cc/rccsd_rhf.sialx (22 procedures) against the ground-state energy
     of BASELINE config 3: ccsd_energy -75.71251002928709 (eom_test, cc_conv 1e-12, test/test_qm.cpp:252-253) and

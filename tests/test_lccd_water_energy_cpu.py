@@ -214,3 +214,102 @@ def test_ccsd_energy_of_hydrogen_fluoride_matches_the_reference_golden(oracle, c
     else:
         assert abs(hist[-1] + inp["e_scf"] - g["frozen_core_ccsd_energy"]) < tol   # measured 1.7e-12
     assert not w.locals
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# several workers: the pardo work distribution, barriers, many-writer accumulates and the collective of the real programs
+# ---------------------------------------------------------------------------------------------------------------------
+class SharedOracleBackend(OracleBackend):
+    """OracleBackend for `world` walkers running as threads on ONE set of arrays: a barrier is a real barrier, put /
+    put += are atomic at the owner (the reference serialises them in the server loop, sip_server.cpp:172-334), the
+    collective is an all-reduce.  Blocks fetched with get/request are private copies until the next barrier, as in the
+    worker-side cache (sial_ops_parallel.cpp:41-47)."""
+
+    def __init__(self, oracle, arrays, shared, **kw):
+        super().__init__(oracle, arrays, **kw)
+        self.sh, self.cache = shared, {}
+
+    def array_block(self, name, segs, shape):
+        key = (name, segs)
+        if key not in self.cache:
+            with self.sh["lock"]:
+                self.cache[key] = HostBlockCopy(super().array_block(name, segs, shape).a)
+        return self.cache[key]
+
+    def put(self, arr, segs, b):
+        with self.sh["lock"]:
+            super().put(arr, segs, b)
+
+    def put_accumulate(self, arr, segs, b):
+        with self.sh["lock"]:
+            super().put_accumulate(arr, segs, b)
+
+    def put_initialize(self, arr, segs, shape, v):
+        with self.sh["lock"]:
+            super().put_initialize(arr, segs, shape, v)
+
+    def barrier(self):
+        self.sh["barrier"].wait()
+        self.cache.clear()
+
+    def collective_sum(self, a, b):
+        with self.sh["lock"]:
+            self.sh["sum"].append(b)
+        self.sh["barrier"].wait()
+        total = sum(self.sh["sum"])
+        self.sh["barrier"].wait()
+        with self.sh["lock"]:
+            self.sh["sum"].clear()
+        self.sh["barrier"].wait()
+        return a + total
+
+
+def HostBlockCopy(a):
+    from sial_oracle_backend import HostBlock
+    return HostBlock(np.array(a, order="F"))
+
+
+@pytest.mark.parametrize("program,world", [("lccd", 3), ("lccsd", 2), ("ccsd", 3)])
+def test_programs_on_several_workers_reproduce_the_goldens(oracle, program, world):
+    """`world` walkers (threads) share the arrays; every walker runs the whole program and executes the pardo
+    iterations k with (k - 1) mod world == rank (loop_manager.cpp:468-499).  The converged energy must be the
+    single-worker one -- which it only is if every read of an array another worker writes is separated from the
+    write by a barrier in the program text, i.e. if the transcribed programs kept the reference's barrier structure."""
+    import threading
+
+    text = {"lccd": lw.PROGRAM, "lccsd": lw.PROGRAM_LCCSD, "ccsd": lw.PROGRAM_CCSD}[program]
+    inp = lw.inputs("all_fine")
+    g = lw.GOLDEN["all_electron"]
+    want = {"lccd": g["lccd_energy"], "lccsd": g["lccsd_energy"], "ccsd": g["ccsd_energy"]}[program]
+    shared = {"lock": threading.Lock(), "barrier": threading.Barrier(world), "sum": []}
+    prog = Program(text)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            be = SharedOracleBackend(oracle, inp["arrays"], shared, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+            w = Walker(prog, be, inp["segs"], rank=rank, world=world, index_base=inp["index_base"])
+            w.run()
+            e = None
+            for _ in range(12):                      # a fixed number of iterations on every worker: no divergence
+                e = be.value(w.run_proc("iteration")["ecorrab"])
+            out[rank] = (e, be.calls)
+        except BaseException as ex:                  # noqa: BLE001 -- release the others, then report
+            errs.append(ex)
+            shared["barrier"].abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    # single worker, same number of iterations
+    inp1 = lw.inputs("all_fine")
+    be1 = OracleBackend(oracle, inp1["arrays"], fock=inp1["fock"], moa_seg_ranges=inp1["moa_seg_ranges"])
+    w1 = Walker(prog, be1, inp1["segs"], index_base=inp1["index_base"])
+    w1.run()
+    for _ in range(12):
+        e1 = be1.value(w1.run_proc("iteration")["ecorrab"])
+    assert all(abs(o[0] - e1) < 1e-12 for o in out), (out, e1)
+    assert abs(e1 + inp1["e_scf"] - want) < 1e-5          # 12 plain iterations: converging to the golden
+    calls = [o[1] for o in out]
+    assert min(calls) > 0.5 * max(calls)                   # the work really is shared
