@@ -23,7 +23,7 @@ for name, g in ((lw.FROZEN, lw.GOLDEN["scf_energy"]), (lw.ALL, lw.GOLDEN["scf_en
     rows.append((f"scf_energy ({name})", g, e, "numpy input stage (oracle/qm_inputs.py)", "-", "-"))
 for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "all_fine")),
                              ("lccsd", lw.PROGRAM_LCCSD, ("all_dat", "all_fine")),
-                             ("ccsd", lw.PROGRAM_CCSD, ("all_dat", "all_fine", "hf_dat", "hf_fc_dat", "hf_fc_fine"))):
+                             ("ccsd", lw.PROGRAM_CCSD, ("all_dat", "all_fine", "hf_dat", "hf_fine", "hf_fc_dat", "hf_fc_fine"))):
     for case in cases:
         inp = lw.inputs(case)
         be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
@@ -47,9 +47,15 @@ for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "al
                 g_tight, g_loose = lw.golden_ccsd()
                 rows.append(("ccsd_energy water (cc_conv 1e-12)", g_tight, e_tot, how, len(hist), be.calls))
                 rows.append(("ccsd_energy water (cc_conv 1e-10)", g_loose, e_tot, how, len(hist), be.calls))
-            elif case == "hf_dat":
-                rows.append(("ccsd_correlation HF (cc_conv 1e-10)", lw.GOLDEN["hf"]["ccsd_correlation"], hist[-1], how, len(hist), be.calls))
-                rows.append(("ccsd_energy HF (cc_conv 1e-10)", lw.GOLDEN["hf"]["ccsd_energy"], e_tot, how, len(hist), be.calls))
+            elif case in ("hf_dat", "hf_fine"):
+                gh = lw.GOLDEN["hf"]
+                rows.append(("ccsd_correlation HF (cc_conv 1e-10)", gh["ccsd_correlation"], hist[-1], how, len(hist), be.calls))
+                rows.append(("ccsd_energy HF (cc_conv 1e-10)", gh["ccsd_energy"], e_tot, how, len(hist), be.calls))
+                c0 = be.calls
+                e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+                how_t = how.replace("ccsd program", "ccsd program + restated (T), rank-6 blocks")
+                rows.append(("E(T) HF = eaaa+esaaa+eaab+esaab", gh["ccsdpt_energy"] - gh["ccsd_energy"], e_t, how_t, "-", be.calls - c0))
+                rows.append(("ccsdpt_energy HF (cc_conv 1e-10)", gh["ccsdpt_energy"], e_tot + e_t, how_t, len(hist), be.calls))
             else:
                 rows.append(("ccsd_energy HF frozen core (1e-12)", lw.GOLDEN["hf"]["frozen_core_ccsd_energy"], e_tot, how, len(hist), be.calls))
         else:

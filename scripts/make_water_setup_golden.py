@@ -24,7 +24,10 @@ GOLDEN = {  # test/test_qm.cpp:396-397, 412-415 (DISABLED_lccd_dropcoreinsial_te
 # hydrogen fluoride / 3-21G: test/test_qm.cpp:86-102 (second_ccsdpt_test, the CCSD stage of the reference's enabled CCSD(T) test;
 # cc_conv 1e-10) and :810-824 (lamccsdpt_test: drop_mo=1-1, cc_conv 1e-12)
 GOLDEN["hf"] = {"scf_energy": -99.45975176375698, "ccsd_correlation": -0.12588695910754, "ccsd_energy": -99.58563872286452,
-                "frozen_core_ccsd_energy": -99.583972376431}
+                "frozen_core_ccsd_energy": -99.583972376431,
+                # :110-126 (second_ccsdpt_test): ccsdpt_energy = ccsd_energy + eaaa + esaaa + eaab + esaab
+                "eaaa": -0.00001091437340, "esaaa": 0.00000240120432, "eaab": -0.00058787722879, "esaab": 0.00003533079603,
+                "ccsdpt_energy": -99.58619978246637}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
              "lamccsdpt_test.dat"):

@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PROGRAM = open(os.path.join(HERE, "golden", "lccd_program.sialx")).read()
 PROGRAM_LCCSD = open(os.path.join(HERE, "golden", "lccsd_program.sialx")).read()
 PROGRAM_CCSD = open(os.path.join(HERE, "golden", "ccsd_program.sialx")).read()
+PROGRAM_PT = open(os.path.join(HERE, "golden", "ccsd_t_restated.sialx")).read()
 FIXTURE = json.load(open(os.path.join(HERE, "golden", "water_321g_setup.json")))
 GOLDEN = FIXTURE["golden"]
 # array name -> index kinds of its declared dimensions
@@ -29,9 +30,11 @@ KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"),
          "tau_ab": ("v", "o", "v", "o"), "taup_ab": ("v", "o", "v", "o"), "taup_aa": ("v", "o", "v", "o"),
          "e5aiai": ("v", "o", "v", "o"), "e5aibj": ("v", "o", "v", "o"), "e6aibj": ("v", "o", "v", "o"),
          "wiibb": ("o", "o", "v", "v"), "t1a_ax": ("v", "ao"), "fae_a": ("v", "v"), "fme_a": ("o", "v"),
-         "fmi_a": ("o", "o"), "wminj_ab": ("o", "o", "o", "o")}
+         "fmi_a": ("o", "o"), "wminj_ab": ("o", "o", "o", "o"),
+         # (T) only (tests/golden/ccsd_t_restated.sialx): rank-6 arrays
+         "x3": ("v", "o") * 3, "w3": ("v", "o") * 3, "v3": ("v", "o") * 3}
 EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a_old", "t1a_new", "tau_ab", "taup_ab",
-         "taup_aa", "e5aiai", "e5aibj", "e6aibj", "wiibb", "t1a_ax", "fae_a", "fme_a", "fmi_a", "wminj_ab")
+         "taup_aa", "e5aiai", "e5aibj", "e6aibj", "wiibb", "t1a_ax", "fae_a", "fme_a", "fmi_a", "wminj_ab", "x3", "w3", "v3")
 # cases: (setup file, segmentation).  Segmentations: the .dat's own (frozen core: moa [1 | 4 | 8], ao [11, 2]; all
 # electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
 FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"
@@ -39,6 +42,7 @@ CASES = {"dat": (FROZEN, None), "fine": (FROZEN, {"moa": [1, 2, 2, 3, 5], "occ":
          "all_dat": (ALL, None), "all_fine": (ALL, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]}),
          # hydrogen fluoride / 3-21G (the reference's second_ccsdpt_test and lamccsdpt_test): all electron, frozen core
          "hf_dat": ("second_ccsdpt_test.dat", None), "hf_fc_dat": ("lamccsdpt_test.dat", None),
+         "hf_fine": ("second_ccsdpt_test.dat", {"moa": [2, 3, 2, 4], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 2]}),
          "hf_fc_fine": ("lamccsdpt_test.dat", {"moa": [1, 3, 1, 2, 4], "occ": (2, 3), "virt": (4, 5), "ao": [3, 6, 2]})}
 
 

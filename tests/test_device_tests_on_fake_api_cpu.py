@@ -25,6 +25,11 @@ def test_ccsd_device_test_body_on_the_fake_api(oracle):
     dev.test_ccsd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), "all_dat", True)
 
 
+def test_ccsd_t_device_test_body_on_the_fake_api(oracle):
+    dev.test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(FakeApi(oracle), "hf_dat", True)
+    dev.test_ccsd_energy_of_hydrogen_fluoride_on_the_device(FakeApi(oracle))
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

@@ -149,3 +149,29 @@ def test_ccsd_energy_of_hydrogen_fluoride_on_the_device(sip):
     assert abs(e_total - lw.GOLDEN["hf"]["frozen_core_ccsd_energy"]) < lw.GOLDEN["tolerance"]
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
+@pytest.mark.parametrize("case,record", [("hf_fine", True), ("hf_dat", False)])
+def test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(sip, case, record):
+    """the reference's enabled CCSD(T) test (second_ccsdpt_test, test/test_qm.cpp:86-126): ccsdpt_energy
+    -99.58619978246637 -- CCSD by the reference's program, (T) by the closed-shell restatement of
+    tests/golden/ccsd_t_restated.sialx (rank-6 blocks: contractions, outer products, permutes, denominator, dots)"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs(case)
+    g = lw.GOLDEN["hf"]
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=record)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+    e_total = hist[-1] + inp["e_scf"] + e_t
+    print(f"\nCCSD(T) HF/3-21G on the device ({case}, record={record}): E(T) {e_t:.14f}, ccsdpt_energy {e_total:.14f} "
+          f"(golden {g['ccsdpt_energy']:.14f})")
+    assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11
+    assert abs(e_total - g["ccsdpt_energy"]) < lw.GOLDEN["tolerance"]
+    for A in arrays.values():
+        A.destroy()

@@ -55,11 +55,11 @@ class DryBackend(DeviceBackend):
 
 @pytest.mark.parametrize("segmentation,program", [("dat", "lccd"), ("fine", "lccd"), ("all_dat", "lccd"),
                                                   ("all_fine", "lccd"), ("all_dat", "lccsd"), ("all_fine", "lccsd"),
-                                                  ("all_dat", "ccsd"), ("all_fine", "ccsd")])
+                                                  ("all_dat", "ccsd"), ("all_fine", "ccsd"), ("hf_fine", "ccsd+t")])
 def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation, program):
     inp = lw.inputs(segmentation)
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
-    prog = Program({"lccd": lw.PROGRAM, "lccsd": lw.PROGRAM_LCCSD, "ccsd": lw.PROGRAM_CCSD}[program])
+    prog = Program({"lccd": lw.PROGRAM, "lccsd": lw.PROGRAM_LCCSD, "ccsd": lw.PROGRAM_CCSD, "ccsd+t": lw.PROGRAM_CCSD}[program])
     with sip.recording(dry=True):
         arrays = {name: DryArray(sip, [inp["segs"][k] for k in kinds]) for name, kinds in lw.KINDS.items()}
         be = DryBackend(sip, arrays, record=False)       # one recording around everything (ended by the with block)
@@ -69,6 +69,9 @@ def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentat
         sip.wl_flush()
         w.run_proc("iteration")
         sip.wl_flush()
+        if program == "ccsd+t":      # the rank-6 stream of tests/golden/ccsd_t_restated.sialx
+            Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+            sip.wl_flush()
         st = sip.wl_stats()
         level, unit = sip.wl_last_plan()
     assert st["recorded"] > (2000 if segmentation == "fine" else 60)

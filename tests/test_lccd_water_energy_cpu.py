@@ -313,3 +313,20 @@ def test_programs_on_several_workers_reproduce_the_goldens(oracle, program, worl
     assert abs(e1 + inp1["e_scf"] - want) < 1e-5          # 12 plain iterations: converging to the golden
     calls = [o[1] for o in out]
     assert min(calls) > 0.5 * max(calls)                   # the work really is shared
+
+
+@pytest.mark.parametrize("case", ["hf_dat", "hf_fine"])
+def test_ccsd_t_energy_of_hydrogen_fluoride_matches_the_reference_golden(oracle, case):
+    """the reference's enabled CCSD(T) test (second_ccsdpt_test, test_qm.cpp:86-126): ccsdpt_energy -99.58619978246637.
+    CCSD by the reference's program (ccsd_program.sialx); the (T) correction by a closed-shell restatement in the same
+    statement subset (ccsd_t_restated.sialx -- NOT the reference's triples programs, see its header) whose rank-6
+    contractions, outer products, permutes, denominator and scalar contractions all go through the block backend"""
+    inp = lw.inputs(case)
+    g, tol = lw.GOLDEN["hf"], lw.GOLDEN["tolerance"]
+    assert abs(g["ccsd_energy"] + g["eaaa"] + g["esaaa"] + g["eaab"] + g["esaab"] - g["ccsdpt_energy"]) < 1e-13
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+    assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11          # E(T) itself: measured 1.3e-13
+    assert abs(hist[-1] + inp["e_scf"] + e_t - g["ccsdpt_energy"]) < tol       # measured 9.5e-12 (reference cc_conv 1e-10)
