@@ -2,8 +2,8 @@
 
 The reference compiles SIAL to `.siox` bytecode with a Java compiler (not available here) and interprets it one
 opcode at a time (src/sip/worker/interpreter.cpp:98-910).  This module is NOT that interpreter: it understands just the
-statement subset that the pardo bodies of the CC doubles equations use (src/sialx/qm/cc/rlccd_rhf.sialx:255-603) and
-turns them into the per-block calls the interpreter would issue -- in the same order, with the same temp-block
+statement subset that the amplitude equations of the coupled-cluster programs use (src/sialx/qm/cc/rlccd_rhf.sialx,
+rlccsd_rhf.sialx, rccsd_rhf.sialx: every procedure of an iteration except DIIS; tests/golden/*_program.sialx) and turns them into the per-block calls the interpreter would issue -- in the same order, with the same temp-block
 lifetimes (temps die at the end of the loop iteration that created them, BlockManager::leave_scope) and the same
 pardo work distribution (iteration k of the where-true iterations of a barrier section runs on worker k mod nworkers,
 BalancedTaskAllocParallelPardoLoop::do_update, loop_manager.cpp:468-499; first index fastest, :434-452).
