@@ -13,3 +13,6 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 python -c "import json; d=json.load(open('gpurun_out/bench_ref_r2.json')); print('cpu arm', d['value'], 'TFLOP/s on', d['cpu_baseline']['cores'], 'cores')"
 # 3. the default bench line
 timeout 900 python bench.py > gpurun_out/bench_n1_r2.json 2> gpurun_out/bench_n1_r2.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_n1_r2.json
+# 4. the energy tests with their printed energies, and the real CC programs op-at-a-time vs recorded (tiny molecules: launch / host bound)
+timeout 600 python -m pytest tests/test_gpu_z_lccd_water_energy.py tests/test_gpu_z_cross_product.py -m gpu -q -s > gpurun_out/pytest_gpu_energy_r2.log 2>&1; echo "energy tests rc=$?"; grep -a "on the device\|patterns at\|passed\|failed" gpurun_out/pytest_gpu_energy_r2.log | tail -20
+timeout 600 python scripts/cc_programs_bench.py > gpurun_out/cc_programs_bench.jsonl 2> gpurun_out/cc_programs_bench.err; echo "cc bench rc=$?"; cut -c1-200 gpurun_out/cc_programs_bench.jsonl
