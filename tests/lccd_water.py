@@ -17,6 +17,7 @@ PROGRAM = open(os.path.join(HERE, "golden", "lccd_program.sialx")).read()
 PROGRAM_LCCSD = open(os.path.join(HERE, "golden", "lccsd_program.sialx")).read()
 PROGRAM_CCSD = open(os.path.join(HERE, "golden", "ccsd_program.sialx")).read()
 PROGRAM_PT = open(os.path.join(HERE, "golden", "ccsd_t_restated.sialx")).read()
+PROGRAM_TRAN = open(os.path.join(HERE, "golden", "tran_program.sialx")).read()
 FIXTURE = json.load(open(os.path.join(HERE, "golden", "water_321g_setup.json")))
 GOLDEN = FIXTURE["golden"]
 # array name -> index kinds of its declared dimensions
@@ -32,9 +33,16 @@ KINDS = {"ca": ("ao", "p"), "aoint": ("ao",) * 4, "vpiqj": ("p", "o", "p", "o"),
          "wiibb": ("o", "o", "v", "v"), "t1a_ax": ("v", "ao"), "fae_a": ("v", "v"), "fme_a": ("o", "v"),
          "fmi_a": ("o", "o"), "wminj_ab": ("o", "o", "o", "o"),
          # (T) only (tests/golden/ccsd_t_restated.sialx): rank-6 arrays
-         "x3": ("v", "o") * 3, "w3": ("v", "o") * 3, "v3": ("v", "o") * 3}
+         "x3": ("v", "o") * 3, "w3": ("v", "o") * 3, "v3": ("v", "o") * 3,
+         # integral transformation only (tests/golden/tran_program.sialx): partially transformed classes
+         "vxxxi": ("ao", "ao", "ao", "o"), "vxxii": ("ao", "ao", "o", "o"), "vxixi": ("ao", "o", "ao", "o"),
+         "vixxi": ("o", "ao", "ao", "o"), "vxxai": ("ao", "ao", "v", "o"), "vxipi": ("ao", "o", "p", "o"),
+         "vxaii": ("ao", "v", "o", "o"), "vixai": ("o", "ao", "v", "o"), "vxaai": ("ao", "v", "v", "o"),
+         "vsaaai": ("v", "v", "v", "o")}
+MO_CLASSES = ("vpiqj", "vspipi", "vaaii", "viaai", "vaaai")      # what tran_program.sialx produces for the CC programs
 EMPTY = ("t2old_ab", "t2new_ab", "tao_ab", "t2ao_ab", "tdaixj", "t2old_aa", "t1a_old", "t1a_new", "tau_ab", "taup_ab",
-         "taup_aa", "e5aiai", "e5aibj", "e6aibj", "wiibb", "t1a_ax", "fae_a", "fme_a", "fmi_a", "wminj_ab", "x3", "w3", "v3")
+         "taup_aa", "e5aiai", "e5aibj", "e6aibj", "wiibb", "t1a_ax", "fae_a", "fme_a", "fmi_a", "wminj_ab", "x3", "w3", "v3",
+         "vxxxi", "vxxii", "vxixi", "vixxi", "vxxai", "vxipi", "vxaii", "vixai", "vxaai", "vsaaai")
 # cases: (setup file, segmentation).  Segmentations: the .dat's own (frozen core: moa [1 | 4 | 8], ao [11, 2]; all
 # electron: moa [5 | 8], ao [13]) and a finer one of the same orbitals
 FROZEN, ALL = "lccd_frozencore_test.dat", "eom_lccd_test.dat"

@@ -175,3 +175,34 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(sip, case, record):
     assert abs(e_total - g["ccsdpt_energy"]) < lw.GOLDEN["tolerance"]
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
+@pytest.mark.parametrize("case,program", [("fine", "lccd"), ("all_fine", "ccsd")])
+def test_transformation_then_cc_program_on_the_device(sip, case, program):
+    """the whole post-SCF pipeline on the device: AO integrals + MO coefficients -> tests/golden/tran_program.sialx
+    (= src/sialx/qm/utility/tran_rhf_no4v.sialx) -> MO classes -> LCCD / CCSD program -> the reference's golden energy"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs(case)
+    want = {n: inp["arrays"][n] for n in lw.MO_CLASSES}
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}            # not uploaded: the transformation program has to produce them
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=True)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    Walker(Program(lw.PROGRAM_TRAN), be, inp["segs"], index_base=inp["index_base"]).run()
+    worst = 0.0
+    for n in lw.MO_CLASSES:
+        for idx, b in want[n].items():
+            worst = max(worst, float(np.max(np.abs(arrays[n].get(idx).to_numpy() - b))))
+    assert worst < 1e-12, worst
+    text = {"lccd": lw.PROGRAM, "ccsd": lw.PROGRAM_CCSD}[program]
+    _, hist = lw.converge(Walker(Program(text), be, inp["segs"], index_base=inp["index_base"]), be.value, max_iter=150)
+    g = lw.golden(case)[1] if program == "lccd" else lw.golden_ccsd()[0]
+    print(f"\ntransformation + {program} on the device ({case}): classes within {worst:.1e} of the dense transformation, "
+          f"energy {hist[-1] + inp['e_scf']:.14f} (golden {g:.14f})")
+    assert abs(hist[-1] + inp["e_scf"] - g) < lw.GOLDEN["tolerance"]
+    for A in arrays.values():
+        A.destroy()

@@ -64,6 +64,9 @@ def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentat
         arrays = {name: DryArray(sip, [inp["segs"][k] for k in kinds]) for name, kinds in lw.KINDS.items()}
         be = DryBackend(sip, arrays, record=False)       # one recording around everything (ended by the with block)
         be.fock = sip.DeviceBlock(inp["fock"].shape)
+        if program == "ccsd+t":      # ... with the integral transformation program in front
+            Walker(Program(lw.PROGRAM_TRAN), be, inp["segs"], index_base=inp["index_base"]).run()
+            sip.wl_flush()
         w = Walker(prog, be, inp["segs"], index_base=inp["index_base"])
         w.run()
         sip.wl_flush()

@@ -330,3 +330,29 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_matches_the_reference_golden(oracle,
     e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
     assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11          # E(T) itself: measured 1.3e-13
     assert abs(hist[-1] + inp["e_scf"] + e_t - g["ccsdpt_energy"]) < tol       # measured 9.5e-12 (reference cc_conv 1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the integral transformation (tests/golden/tran_program.sialx = src/sialx/qm/utility/tran_rhf_no4v.sialx) in front of it
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,program", [("fine", "lccd"), ("all_fine", "ccsd")])
+def test_transformation_program_then_cc_program_reproduce_the_goldens(oracle, case, program):
+    """AO integrals + MO coefficients -> [the reference's transformation program] -> MO classes -> [the reference's CC
+    program] -> golden energy, every block operation of both programs on the backend.  The classes must equal the
+    dense numpy transformation of oracle/qm_inputs.py (which the other tests feed in directly)."""
+    inp = lw.inputs(case)
+    want = {n: inp["arrays"][n] for n in lw.MO_CLASSES}
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    wt = Walker(Program(lw.PROGRAM_TRAN), be, inp["segs"], index_base=inp["index_base"])
+    wt.run()
+    assert not wt.locals
+    for n in lw.MO_CLASSES:
+        assert set(inp["arrays"][n]) == set(want[n]), n
+        for idx, b in want[n].items():
+            assert np.max(np.abs(inp["arrays"][n][idx] - b)) < 1e-13, (n, idx)
+    text = {"lccd": lw.PROGRAM, "ccsd": lw.PROGRAM_CCSD}[program]
+    _, hist = lw.converge(Walker(Program(text), be, inp["segs"], index_base=inp["index_base"]), be.value, max_iter=150)
+    g = lw.golden(case)[1] if program == "lccd" else lw.golden_ccsd()[0]
+    assert abs(hist[-1] + inp["e_scf"] - g) < lw.GOLDEN["tolerance"]
