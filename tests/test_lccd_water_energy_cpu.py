@@ -356,3 +356,36 @@ def test_transformation_program_then_cc_program_reproduce_the_goldens(oracle, ca
     _, hist = lw.converge(Walker(Program(text), be, inp["segs"], index_base=inp["index_base"]), be.value, max_iter=150)
     g = lw.golden(case)[1] if program == "lccd" else lw.golden_ccsd()[0]
     assert abs(hist[-1] + inp["e_scf"] - g) < lw.GOLDEN["tolerance"]
+
+
+def test_transformation_program_on_several_workers(oracle):
+    """the transformation program shared by three workers (threads, real barriers, atomic prepare +=): same classes"""
+    import threading
+
+    world = 3
+    inp = lw.inputs("all_fine")
+    want = {n: inp["arrays"][n] for n in lw.MO_CLASSES}
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}
+    shared = {"lock": threading.Lock(), "barrier": threading.Barrier(world), "sum": []}
+    prog, errs, calls = Program(lw.PROGRAM_TRAN), [], [0] * world
+
+    def run(rank):
+        try:
+            be = SharedOracleBackend(oracle, inp["arrays"], shared, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+            Walker(prog, be, inp["segs"], rank=rank, world=world, index_base=inp["index_base"]).run()
+            calls[rank] = be.calls
+        except BaseException as ex:                  # noqa: BLE001
+            errs.append(ex)
+            shared["barrier"].abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for n in lw.MO_CLASSES:
+        for idx, b in want[n].items():
+            assert np.max(np.abs(inp["arrays"][n][idx] - b)) < 1e-13, (n, idx)
+    assert min(calls) > 0.5 * max(calls)
