@@ -1,5 +1,5 @@
 """Deferred op stream on the REAL coupled-cluster programs, without a GPU: one iteration of tests/golden/lccd_program.sialx,
-lccsd_program.sialx, ccsd_program.sialx (+ the rank-6 (T) stream) walked on the device backend with the library in dry
+lccsd_program.sialx, ccsd_program.sialx (+ the integral transformation program and the rank-6 (T) stream) walked on the device backend with the library in dry
 mode (fake device addresses; the recorder, the hazard analysis, the fusion passes and the level scheduler run on the
 host).  Prints per program: ops recorded -> units scheduled, accumulates fused into their contraction, temporaries elided,
 chains (several pairs accumulated into one destination tile walk), levels, and the host time of record + schedule.
@@ -20,7 +20,7 @@ sip = aces4_b200.api
 print("one iteration per program, pardo by pardo (every pardo is one recording, as in DeviceBackend(record=True))")
 print(f"{'program':8s} {'case':9s} {'recorded':>9s} {'scheduled':>9s} {'fused +=':>9s} {'temps elided':>12s} {'chains':>7s} "
       f"{'chain pairs':>11s} {'levels':>7s} {'pardos':>7s} {'host ms (walker+record+schedule)':>33s}")
-for program, text, case in (("lccd", lw.PROGRAM, "fine"), ("lccsd", lw.PROGRAM_LCCSD, "all_fine"),
+for program, text, case in (("tran", lw.PROGRAM_TRAN, "all_fine"), ("lccd", lw.PROGRAM, "fine"), ("lccsd", lw.PROGRAM_LCCSD, "all_fine"),
                             ("ccsd", lw.PROGRAM_CCSD, "all_fine"), ("ccsd", lw.PROGRAM_CCSD, "hf_fine"),
                             ("(T)", lw.PROGRAM_PT, "hf_fine")):
     inp = lw.inputs(case)
@@ -39,13 +39,13 @@ for program, text, case in (("lccd", lw.PROGRAM, "fine"), ("lccsd", lw.PROGRAM_L
 
         be.end_pardo = flush_and_count
         w = Walker(Program(text), be, inp["segs"], index_base=inp["index_base"])
-        if program != "(T)":
+        if program not in ("(T)", "tran"):
             w.run()
             sip.wl_flush()
         st0 = dict(sip.wl_stats())
         npardo[0] = 0
         t0 = time.perf_counter()
-        if program == "(T)":
+        if program in ("(T)", "tran"):
             w.run()
         else:
             w.run_proc("iteration")
