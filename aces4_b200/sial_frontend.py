@@ -224,6 +224,7 @@ class Walker:
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
         self.locals = {}         # allocated local arrays: name -> {segs: handle}
+        self._aseg_plan, self._ext_of = {}, {}   # memoised label resolution (per distinct reference in the text)
         self.iteration = 0       # pardo iteration counter of the current barrier section
         self.scalars = {s: 0.0 for s in program.scalars}
 
@@ -238,28 +239,38 @@ class Walker:
         return len(self.segs[self._kind(lab)])
 
     def _segs_of(self, labs):
-        return tuple(self.idx[lab] for lab in labs)
+        idx = self.idx
+        return tuple(idx[lab] for lab in labs)
 
     def _shape(self, labs):
-        return tuple(self.segs[self._kind(lab)][self.idx[lab] - 1] for lab in labs)
+        ext = self._ext_of.get(labs)
+        if ext is None:         # the extent table of each label's index type, resolved once per label tuple
+            ext = self._ext_of[labs] = [(lab, self.segs[self._kind(lab)]) for lab in labs]
+        idx = self.idx
+        return tuple(e[idx[lab] - 1] for lab, e in ext)
 
     def _is_remote(self, name):
         return self.p.arrays.get(name, ("temp",))[0] in ("served", "distributed", "static")
 
     def _array_segs(self, name, labs):
         """block coordinates of `name[labs]` in the segment numbering of the array's DECLARED indices"""
-        decl = self.p.arrays[name][1]
-        if len(decl) != len(labs):
-            raise SialSyntaxError(f"{name} has rank {len(decl)}")
-        out = []
-        for d, lab in zip(decl, labs):
-            dk, k, v = self._kind(d), self._kind(lab), self.idx[lab]
-            if dk == "p" and k == "v":
-                v += len(self.segs["o"])
-            elif dk != k and not (dk == "p" and k == "o"):
-                raise SialSyntaxError(f"index {lab} ({k}) cannot address dimension {d} ({dk}) of {name}")
-            out.append(v)
-        return tuple(out)
+        plan = self._aseg_plan.get((name, labs))
+        if plan is None:        # (label, shift) per dimension, resolved once per distinct reference in the program text
+            decl = self.p.arrays[name][1]
+            if len(decl) != len(labs):
+                raise SialSyntaxError(f"{name} has rank {len(decl)}")
+            plan = []
+            for d, lab in zip(decl, labs):
+                dk, k = self._kind(d), self._kind(lab)
+                if dk == "p" and k == "v":
+                    plan.append((lab, len(self.segs["o"])))
+                elif dk == k or (dk == "p" and k == "o"):
+                    plan.append((lab, 0))
+                else:
+                    raise SialSyntaxError(f"index {lab} ({k}) cannot address dimension {d} ({dk}) of {name}")
+            self._aseg_plan[name, labs] = plan
+        idx = self.idx
+        return tuple(idx[lab] + shift for lab, shift in plan)
 
     def _find(self, name, labs):
         key = (name, self._segs_of(labs))
@@ -441,13 +452,21 @@ class Walker:
         self.scalars[a] = self.be.collective_sum(self.scalars[a], self.scalars[b])
 
 
+_LABEL_NUMBERS = {}
+
+
 def label_numbers(*label_lists):
-    """labels -> small ints shared across the operands (the index-table slots the interpreter passes)"""
-    num = {}
-    for labs in label_lists:
-        for x in labs:
-            num.setdefault(x, len(num) + 1)
-    return [[num[x] for x in labs] for labs in label_lists]
+    """labels -> small ints shared across the operands (the index-table slots the interpreter passes); memoised per
+    distinct label pattern (a program has a few hundred at most), callers must not modify the result"""
+    key = tuple(tuple(labs) for labs in label_lists)
+    out = _LABEL_NUMBERS.get(key)
+    if out is None:
+        num = {}
+        for labs in key:
+            for x in labs:
+                num.setdefault(x, len(num) + 1)
+        out = _LABEL_NUMBERS[key] = [[num[x] for x in labs] for labs in key]
+    return out
 
 
 class DeviceBackend:
