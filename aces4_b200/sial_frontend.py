@@ -23,6 +23,7 @@ Supported statements (case-insensitive keywords, `#` comments):
     s = X[...] * Y[...]   s = number    s += t    s -= t    s *= number
     execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
     proc NAME ... endproc NAME        call NAME        allocate L[a,*,b,j] / deallocate L[a,*,b,j]
+    set_persistent A "label"          restore_persistent A "label"       (arrays and scalars)
 Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `moaindex p = baocc: eavirt` /
 `aoindex mu = 1: norb`; arrays `served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else
 raises SialSyntaxError.
@@ -35,6 +36,11 @@ through the backend (`array_block`), i.e. as slices of a resident array (contigu
 `allocate` creates the blocks of a `local` array for every segment of the `*` dimensions, zero-filled, and they live
 until `deallocate` (not until the end of the loop iteration like temps; block_manager.cpp allocate_local /
 deallocate_local) -- here a block is created, zero-filled, when it is first touched.
+
+`set_persistent` hands an array (or scalar) over to the backend's label registry and `restore_persistent` adopts it into
+the array of that name declared by the program that follows -- how the reference chains its programs (scf -> tran -> cc,
+worker_persistent_array_manager.cpp:34-155).  The hand-over happens when the statement executes (the reference defers
+it to the end of the program), so the statements belong at the end / start of a program, where the reference's have them.
 
 Procedures: statements between `proc NAME` and `endproc` form a procedure; `call NAME` runs it; `Walker.run()` runs
 the main program (the statements outside procedures) and `Walker.run_proc(NAME)` one procedure (the test drivers use
@@ -164,6 +170,11 @@ class Program:
             args = [(m.group(1).lower(), _labels(m.group(2))) for m in re.finditer(_REF, line)]
             bare = [t for t in re.sub(_REF, " ", line).split()[2:]]
             return ("execute", tok[1], args, [b.lower() for b in bare])
+        if kw in ("set_persistent", "restore_persistent"):
+            m = re.match(r'\w+\s+([A-Za-z_]\w*)\s+"([^"]+)"\s*$', line)
+            if not m:
+                raise SialSyntaxError("bad " + kw)
+            return (kw, m.group(1).lower(), m.group(2))
         if kw in ("allocate", "deallocate"):
             m = re.match(r"\w+\s+([A-Za-z_]\w*)\s*\[([^\]]*)\]\s*$", line)
             if not m:
@@ -374,6 +385,22 @@ class Walker:
         for h in self.locals.pop(name).values():
             self.be.free(h)
 
+    def _x_set_persistent(self, name, label):
+        if name in self.p.scalars:
+            self.be.persist_scalar(label, self.be.value(self.scalars[name]))
+        elif self._is_remote(name):
+            self.be.set_persistent(name, label)
+        else:
+            raise SialSyntaxError(f"set_persistent of {name}: not a scalar, served, distributed or static array")
+
+    def _x_restore_persistent(self, name, label):
+        if name in self.p.scalars:
+            self.scalars[name] = self.be.restore_scalar(label)
+        elif self._is_remote(name):
+            self.be.restore_persistent(name, label)
+        else:
+            raise SialSyntaxError(f"restore_persistent of {name}: not a scalar, served, distributed or static array")
+
     def _x_request(self, name, labs):
         self.be.request(name, self._array_segs(name, labs), self._shape(labs))
 
@@ -536,6 +563,20 @@ class DeviceBackend:
 
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr].put_initialize(segs, v)
+
+    # persistence: the array object (with its HBM slab) moves to the library's label registry and back -- no copy
+    def set_persistent(self, name, label):
+        self.cache.clear()
+        self.arrays[name].persist(label)
+
+    def restore_persistent(self, name, label):
+        self.arrays[name].restore(label)
+
+    def persist_scalar(self, label, value):
+        self.api.persist_scalar(label, value)
+
+    def restore_scalar(self, label):
+        return self.api.restore_scalar(label)
 
     def execute(self, fname, blocks, segs, kinds, bare):
         if fname == "energy_denominator_rhf":

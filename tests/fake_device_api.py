@@ -31,6 +31,7 @@ class FakeApi:
         self._ptr = itertools.count(0x1000, 0x1000)
         self._launches = 0
         self._moa = None
+        self._registry = {}
         self._lib = _Lib(self)
         api = self
 
@@ -117,6 +118,15 @@ class FakeApi:
             def destroy(self):
                 self.blocks = None
 
+            def persist(self, label):
+                api._registry[label] = (self.seg_ext, self.blocks)
+                self.blocks = None
+
+            def restore(self, label):
+                seg_ext, blocks = api._registry.pop(label)
+                assert seg_ext == self.seg_ext, "restore_persistent into an array of another layout"
+                self.blocks = blocks
+
         self.DeviceBlock, self.DistArray = DeviceBlock, DistArray
 
     # ---- module-level functions of aces4_b200.api ----
@@ -142,6 +152,12 @@ class FakeApi:
 
     def wl_end(self):
         return {}
+
+    def persist_scalar(self, label, value):
+        self._registry[label] = float(value)
+
+    def restore_scalar(self, label):
+        return self._registry.pop(label)
 
     def set_predefined_int_array(self, name, values):
         assert name == "moa_seg_ranges"

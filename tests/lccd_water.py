@@ -7,6 +7,7 @@ and the converged energy compared with the reference's golden values (test/test_
 import functools
 import json
 import os
+import re
 
 import numpy as np
 
@@ -119,3 +120,22 @@ def converge(walker, value, tol=1e-12, max_iter=80):
         if len(hist) > 1 and abs(hist[-1] - hist[-2]) < tol:
             return e_mp2, hist
     raise AssertionError(f"LCCD iterations did not converge: {hist[-3:]}")
+
+
+PERSISTED = ("VSpipi", "Vaaii", "Viaai", "Vaaai", "Vpiqj")
+
+
+def chained_through_persistence(tran_text, cc_text):
+    """the two programs chained the way the reference chains them (tran_rhf_no4v.sialx:632-637 `set_persistent X "X"` at
+    the end of the transformation; rlccd_rhf.sialx:243-251 / rccsd_rhf.sialx:225-244 `PROC READ_2EL` with
+    `restore_persistent X "X"` at the start of the CC program): -> (transformation text, CC text)"""
+    tail = "".join(f'set_persistent {x} "{x}"\n' for x in PERSISTED)
+    tran = tran_text.replace("endsial tran_program", tail + "endsial tran_program")
+    assert tran != tran_text
+    declared = [x for x in PERSISTED if re.search(rf"^served {x}\[", cc_text, re.M)]     # LCCD reads four of the five
+    head = "proc read_2el\n" + "".join(f'restore_persistent {x} "{x}"\n' for x in declared) + "server_barrier\nendproc read_2el\n\n"
+    i = cc_text.index("proc iguess")
+    cc = cc_text[:i] + head + cc_text[i:]
+    j = cc.index("call iguess")
+    cc = cc[:j] + "call read_2el\n" + cc[j:]
+    return tran, cc

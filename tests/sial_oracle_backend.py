@@ -80,6 +80,21 @@ class OracleBackend:
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr][segs] = np.full(shape, float(v), order="F")
 
+    # persistence: a label registry shared by the backends of consecutive programs (class attribute)
+    registry = {}
+
+    def set_persistent(self, name, label):
+        self.registry[label] = self.arrays.pop(name)
+
+    def restore_persistent(self, name, label):
+        self.arrays[name] = self.registry.pop(label)
+
+    def persist_scalar(self, label, value):
+        self.registry[label] = float(value)
+
+    def restore_scalar(self, label):
+        return self.registry.pop(label)
+
     def execute(self, fname, blocks, segs, kinds, bare):
         assert fname == "energy_denominator_rhf"
         assert self.o.si_energy_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, self.ranges) == 0

@@ -206,3 +206,35 @@ def test_transformation_then_cc_program_on_the_device(sip, case, program):
     assert abs(hist[-1] + inp["e_scf"] - g) < lw.GOLDEN["tolerance"]
     for A in arrays.values():
         A.destroy()
+
+
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
+def test_programs_chained_through_persistent_arrays_on_the_device(sip):
+    """transformation program -> `set_persistent` (the DistArray and its HBM slab move to the library's label registry,
+    persist.cu) -> freshly declared arrays -> `restore_persistent` in the CC program's READ_2EL -> LCCSD golden"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    tran_text, cc_text = lw.chained_through_persistence(lw.PROGRAM_TRAN, lw.PROGRAM_LCCSD)
+    inp = lw.inputs("all_fine")
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays1 = device_arrays(sip, inp)
+    be1 = DeviceBackend(sip, arrays1, record=True)
+    Walker(Program(tran_text), be1, inp["segs"], index_base=inp["index_base"]).run()
+    # the next program: its own arrays (only the SCF results are uploaded), the classes come back through the registry
+    for n in lw.KINDS:
+        if n not in ("ca", "aoint"):
+            inp["arrays"][n] = {}
+    arrays2 = device_arrays(sip, inp)
+    be2 = DeviceBackend(sip, arrays2, record=True)
+    be2.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    _, hist = lw.converge(Walker(Program(cc_text), be2, inp["segs"], index_base=inp["index_base"]), be2.value, max_iter=120)
+    g_corr, g_total = lw.golden_lccsd()
+    print(f"\ntransformation -> persistence -> LCCSD on the device: lccsd_correlation {hist[-1]:.14f} (golden {g_corr:.14f})")
+    assert abs(hist[-1] - g_corr) < lw.GOLDEN["tolerance"]
+    for name, A in arrays1.items():
+        if name.lower() not in [x.lower() for x in lw.PERSISTED]:
+            A.destroy()
+    for A in arrays2.values():
+        A.destroy()

@@ -389,3 +389,25 @@ def test_transformation_program_on_several_workers(oracle):
         for idx, b in want[n].items():
             assert np.max(np.abs(inp["arrays"][n][idx] - b)) < 1e-13, (n, idx)
     assert min(calls) > 0.5 * max(calls)
+
+
+def test_programs_chained_through_persistent_arrays(oracle):
+    """transformation program -> `set_persistent` -> a NEW backend with freshly declared arrays -> `restore_persistent` in
+    the CC program's READ_2EL -> LCCD golden: the hand-over the reference uses between its programs"""
+    tran_text, cc_text = lw.chained_through_persistence(lw.PROGRAM_TRAN, lw.PROGRAM)
+    inp = lw.inputs("fine")
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}
+    OracleBackend.registry.clear()
+    be1 = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    Walker(Program(tran_text), be1, inp["segs"], index_base=inp["index_base"]).run()
+    assert sorted(OracleBackend.registry) == sorted(lw.PERSISTED)
+    assert not any(x.lower() in inp["arrays"] for x in lw.PERSISTED)        # handed over, not copied
+    arrays2 = {n: {} for n in lw.KINDS}                                      # the next program's own declarations
+    arrays2["ca"], arrays2["aoint"] = inp["arrays"]["ca"], inp["arrays"]["aoint"]
+    be2 = OracleBackend(oracle, arrays2, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    _, hist = lw.converge(Walker(Program(cc_text), be2, inp["segs"], index_base=inp["index_base"]), be2.value)
+    assert sorted(OracleBackend.registry) == ["VSpipi", "Vaaai"]            # persisted for other programs (LCCSD, CCSD)
+    assert abs(hist[-1] - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]
+    with pytest.raises(KeyError):                                            # nothing left to restore a second time
+        Walker(Program(cc_text), be2, inp["segs"], index_base=inp["index_base"]).run()

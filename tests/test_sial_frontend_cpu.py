@@ -314,3 +314,18 @@ def test_super_instructions_receive_absolute_index_values(oracle):
     Walker(Program(text), Spy(oracle, {}), {"o": [2, 2], "v": [3, 5]}, index_base={"o": 1, "v": 3}).run()
     assert sorted(s[1] for s in seen) == [(4, 2), (4, 3), (5, 2), (5, 3)]
     assert seen[0][0] == "energy_denominator_rhf" and seen[0][2] == ("v", "o") and seen[0][3] == ("fock_a",)
+
+
+def test_persistence_statements(oracle):
+    text = DECL + 'x = 2.5\nset_persistent x "ex"\nset_persistent S "Sij"\n'
+    arrays = {"s": {(1, 1): np.ones((2, 2), order="F")}, "f": {}, "ca": {}, "out": {}}
+    OracleBackend.registry.clear()
+    Walker(Program(text), OracleBackend(oracle, arrays), {"o": [2], "v": [1], "ao": [1]}).run()
+    assert "s" not in arrays and OracleBackend.registry["ex"] == 2.5
+    arrays2 = {"s": {}, "f": {}, "ca": {}, "out": {}}
+    w = Walker(Program(DECL + 'restore_persistent S "Sij"\nrestore_persistent x "ex"\n'), OracleBackend(oracle, arrays2),
+               {"o": [2], "v": [1], "ao": [1]})
+    assert w.run()["x"] == 2.5 and np.array_equal(arrays2["s"][1, 1], np.ones((2, 2)))
+    for bad in ('set_persistent S\n', 'set_persistent T "t"\n', 'restore_persistent "x"\n'):
+        with pytest.raises(SialSyntaxError):
+            Walker(Program(DECL + bad), OracleBackend(oracle, dict(arrays2)), {"o": [2], "v": [1], "ao": [1]}).run()
