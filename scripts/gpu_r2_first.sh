@@ -16,3 +16,5 @@ timeout 900 python bench.py > gpurun_out/bench_n1_r2.json 2> gpurun_out/bench_n1
 # 4. the energy tests with their printed energies, and the real CC programs op-at-a-time vs recorded (tiny molecules: launch / host bound)
 timeout 600 python -m pytest tests/test_gpu_z_lccd_water_energy.py tests/test_gpu_z_cross_product.py -m gpu -q -s > gpurun_out/pytest_gpu_energy_r2.log 2>&1; echo "energy tests rc=$?"; grep -a "on the device\|patterns at\|passed\|failed" gpurun_out/pytest_gpu_energy_r2.log | tail -20
 timeout 600 python scripts/cc_programs_bench.py > gpurun_out/cc_programs_bench.jsonl 2> gpurun_out/cc_programs_bench.err; echo "cc bench rc=$?"; cut -c1-200 gpurun_out/cc_programs_bench.jsonl
+# 5. (with `gpurun --gpus 2`) the energy goldens on 2 GPUs:
+#    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/gpu_n_energy.py
