@@ -11,12 +11,12 @@ import test_gpu_z_lccd_water_energy as dev
 from fake_device_api import FakeApi
 
 
-@pytest.mark.parametrize("case,record", [("fine", True), ("dat", False), ("all_fine", True)])
+@pytest.mark.parametrize("case,record", [("fine", True), ("all_dat", True)])
 def test_lccd_device_test_body_on_the_fake_api(oracle, case, record):
     dev.test_lccd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), case, record)
 
 
-@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", False)])
+@pytest.mark.parametrize("case,record", [("all_dat", False)])
 def test_lccsd_device_test_body_on_the_fake_api(oracle, case, record):
     dev.test_lccsd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), case, record)
 

@@ -41,8 +41,7 @@ def device_arrays(sip, inp):
 
 
 @pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
-@pytest.mark.parametrize("case,record", [("fine", True), ("dat", True), ("fine", False), ("all_fine", True),
-                                         ("all_dat", True)])
+@pytest.mark.parametrize("case,record", [("fine", True), ("fine", False), ("all_dat", True)])
 def test_lccd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
@@ -76,7 +75,7 @@ def test_lccd_energy_on_the_device_matches_the_reference_golden(sip, case, recor
 
 
 @pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
-@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", True), ("all_fine", False)])
+@pytest.mark.parametrize("case,record", [("all_fine", True), ("all_dat", False)])
 def test_lccsd_energy_on_the_device_matches_the_reference_golden(sip, case, record):
     """tests/golden/lccsd_program.sialx = src/sialx/qm/cc/rlccsd_rhf.sialx (singles + doubles, rank-2 distributed arrays,
     allocated local arrays) against test/test_qm.cpp:526-529: lccsd_correlation -0.12865706498547, lccsd_energy
@@ -178,7 +177,7 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(sip, case, record):
 
 
 @pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
-@pytest.mark.parametrize("case,program", [("fine", "lccd"), ("all_fine", "ccsd")])
+@pytest.mark.parametrize("case,program", [("fine", "lccd"), ("all_dat", "ccsd")])
 def test_transformation_then_cc_program_on_the_device(sip, case, program):
     """the whole post-SCF pipeline on the device: AO integrals + MO coefficients -> tests/golden/tran_program.sialx
     (= src/sialx/qm/utility/tran_rhf_no4v.sialx) -> MO classes -> LCCD / CCSD program -> the reference's golden energy"""
@@ -215,7 +214,7 @@ def test_programs_chained_through_persistent_arrays_on_the_device(sip):
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
     tran_text, cc_text = lw.chained_through_persistence(lw.PROGRAM_TRAN, lw.PROGRAM_LCCSD)
-    inp = lw.inputs("all_fine")
+    inp = lw.inputs("all_dat")
     for n in lw.MO_CLASSES:
         inp["arrays"][n] = {}
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
