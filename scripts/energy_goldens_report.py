@@ -52,8 +52,11 @@ for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "al
                 rows.append(("ccsd_correlation HF (cc_conv 1e-10)", gh["ccsd_correlation"], hist[-1], how, len(hist), be.calls))
                 rows.append(("ccsd_energy HF (cc_conv 1e-10)", gh["ccsd_energy"], e_tot, how, len(hist), be.calls))
                 c0 = be.calls
-                e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+                sc = Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+                e_t = be.value(sc["et"])
                 how_t = how.replace("ccsd program", "ccsd program + restated (T), rank-6 blocks")
+                for comp in ("eaaa", "esaaa", "eaab", "esaab"):
+                    rows.append((f"{comp} HF", gh[comp], be.value(sc[comp]), how_t, "-", "-"))
                 rows.append(("E(T) HF = eaaa+esaaa+eaab+esaab", gh["ccsdpt_energy"] - gh["ccsd_energy"], e_t, how_t, "-", be.calls - c0))
                 rows.append(("ccsdpt_energy HF (cc_conv 1e-10)", gh["ccsdpt_energy"], e_tot + e_t, how_t, len(hist), be.calls))
             else:

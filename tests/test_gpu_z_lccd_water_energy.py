@@ -166,7 +166,10 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(sip, case, record):
     be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
     w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
     _, hist = lw.converge(w, be.value, max_iter=150)
-    e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+    sc = Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+    e_t = be.value(sc["et"])
+    for name in ("eaaa", "esaaa", "eaab", "esaab"):          # the reference's four spin components (test_qm.cpp:110-124)
+        assert abs(be.value(sc[name]) - g[name]) < lw.GOLDEN["tolerance"], name
     e_total = hist[-1] + inp["e_scf"] + e_t
     print(f"\nCCSD(T) HF/3-21G on the device ({case}, record={record}): E(T) {e_t:.14f}, ccsdpt_energy {e_total:.14f} "
           f"(golden {g['ccsdpt_energy']:.14f})")

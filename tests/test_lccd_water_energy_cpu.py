@@ -327,8 +327,11 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_matches_the_reference_golden(oracle,
     be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
     w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
     _, hist = lw.converge(w, be.value, max_iter=150)
-    e_t = be.value(Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()["et"])
+    sc = Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+    e_t = be.value(sc["et"])
     assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11          # E(T) itself: measured 1.3e-13
+    for name in ("eaaa", "esaaa", "eaab", "esaab"):                             # the four numbers the reference asserts:
+        assert abs(be.value(sc[name]) - g[name]) < 1e-11, name                  # measured 6e-15, 7e-15, 2.6e-13, 1.1e-13
     assert abs(hist[-1] + inp["e_scf"] + e_t - g["ccsdpt_energy"]) < tol       # measured 9.5e-12 (reference cc_conv 1e-10)
 
 
