@@ -13,7 +13,9 @@
  *
  * PARITY PINNING: the reference has no known-answer test for these routines other than
  * return_sval_test.sialx (test_basic_sial.cpp); the restatement is checked against closed-form numpy
- * statements in tests/test_super_instr_cpu.py -> "parity unpinned" at the reference level for this file.
+ * statements in tests/test_super_instr_cpu.py -> "parity unpinned" at the reference level for this file,
+ * except energy_denominator_rhf, which is pinned through the reference's energy goldens
+ * (tests/test_lccd_water_energy_cpu.py: rank 4 by LCCD, rank 2 by the LCCSD / CCSD singles update, rank 6 by (T)).
  */
 #include <string.h>
 

@@ -1,7 +1,8 @@
 """Shared driver of the energy tests (water / 3-21G: the reference's lccd_frozencore_test, eom_lccd_test, eom_mp2_test,
 lccsd_test, eom_test / eom_ccsd_water_test; hydrogen fluoride / 3-21G: second_ccsdpt_test, lamccsdpt_test): inputs from
 the decoded `.dat` (tests/golden/water_321g_setup.json) through oracle/qm_inputs.py (numpy integrals + RHF, test
-infrastructure), then the reference's LCCD amplitude equations (tests/golden/lccd_program.sialx) walked block by block
+infrastructure), then the reference's programs (tests/golden/tran_program.sialx, lccd_program.sialx, lccsd_program.sialx,
+ccsd_program.sialx, and the restated ccsd_t_restated.sialx) walked block by block
 by aces4_b200/sial_frontend.py on a backend -- the CPU oracle here, libsipgpu in tests/test_gpu_lccd_water_energy.py --
 and the converged energy compared with the reference's golden values (test/test_qm.cpp:447-462)."""
 import functools
