@@ -299,7 +299,8 @@ class Walker:
     def _read(self, name, labs):
         """(handle, labels it is stored with) of an operand block"""
         if self._is_remote(name):
-            return self.be.array_block(name, self._array_segs(name, labs), self._shape(labs)), labs
+            fetch = self.be.static_block if self.p.arrays[name][0] == "static" else self.be.array_block
+            return fetch(name, self._array_segs(name, labs), self._shape(labs)), labs
         h = self._find(name, labs)
         if h is None:
             raise SialSyntaxError(f"block {name}{list(labs)} read before it was written")
@@ -496,12 +497,24 @@ def label_numbers(*label_lists):
     return out
 
 
+class StaticSlice:
+    """A block of a static (contiguous) array that stays where it is: parent device block + 0-based first element +
+    extents.  Only contractions take it (sipgpu_block_contract_sliced reads the parent through its strides), which is
+    all the CC programs do with `ca[mu,p]`; the reference extracts a copy per use (contiguous_array_manager.cpp:202-230)."""
+
+    def __init__(self, parent, beg, shape):
+        self.parent, self.beg, self.shape = parent, tuple(beg), tuple(shape)
+
+
 class DeviceBackend:
     """The per-block calls of the walker on libsipgpu (C ABI).  Holds no arithmetic."""
 
-    def __init__(self, api, arrays, record=True, rank=0, world=1, barrier=None, allreduce=None):
-        """arrays: name -> api.DistArray (served/distributed arrays, created by the caller)"""
+    def __init__(self, api, arrays, record=True, rank=0, world=1, barrier=None, allreduce=None, static_in_place=None):
+        """arrays: name -> api.DistArray (served/distributed arrays, created by the caller).
+        static_in_place: name -> (resident api.DeviceBlock holding the WHOLE static array, [segment extents per
+        dimension]): blocks of these arrays are read in place by the contraction kernel instead of through `arrays`."""
         self.api, self.arrays, self.record = api, arrays, record
+        self.static = dict(static_in_place or {})
         self.rank, self.world = rank, world
         self._barrier, self._allreduce = barrier, allreduce
         self.fock = None    # resident Fock diagonal block for `execute energy_denominator_rhf` (set by the caller)
@@ -535,6 +548,13 @@ class DeviceBackend:
             self.cache[key] = A.get(segs)      # peer read over NVLink into the worker-side cache
         return self.cache[key]
 
+    def static_block(self, name, segs, shape):
+        if name not in self.static:
+            return self.array_block(name, segs, shape)
+        parent, seg_ext = self.static[name]
+        beg = [sum(ext[: s - 1]) for ext, s in zip(seg_ext, segs)]
+        return StaticSlice(parent, beg, shape)
+
     def fill(self, b, v):
         b.fill(v)
 
@@ -553,7 +573,15 @@ class DeviceBackend:
 
     def contract(self, d, dlabs, L, llabs, R, rlabs):
         dn, ln, rn = label_numbers(dlabs, llabs, rlabs)
-        self.api.contract_labels(dn, d.shape, ln, L, rn, R, out=d)
+        if isinstance(L, StaticSlice) or isinstance(R, StaticSlice):
+            ptrn, ierr = self.api.get_contraction_ptrn(dn, ln, rn)
+            if ierr:
+                raise SialSyntaxError(f"illegal contraction pattern {dlabs} = {llabs} * {rlabs} (ierr {ierr})")
+            lb, Lb = (L.beg, L.parent) if isinstance(L, StaticSlice) else (None, L)
+            rb, Rb = (R.beg, R.parent) if isinstance(R, StaticSlice) else (None, R)
+            self.api.contract_sliced(ptrn, Lb, L.shape, lb, Rb, R.shape, rb, d.shape, out=d)
+        else:
+            self.api.contract_labels(dn, d.shape, ln, L, rn, R, out=d)
 
     def put(self, arr, segs, b):
         self.arrays[arr].put(segs, b)

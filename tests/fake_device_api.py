@@ -180,6 +180,23 @@ class FakeApi:
         self._launches += 1
         return out
 
+    def get_contraction_ptrn(self, dlab, llab, rlab):
+        return self.o.get_contraction_ptrn(list(dlab), list(llab), list(rlab))
+
+    def contract_sliced(self, ptrn, L, lext, lbeg, R, rext, rbeg, dext, out=None, dbeg=None, alpha=1.0, beta=0.0):
+        assert dbeg is None and alpha == 1.0 and beta == 0.0
+
+        def operand(blk, ext, beg):
+            if beg is None:
+                return blk.a
+            return np.asfortranarray(blk.a[tuple(slice(b, b + e) for b, e in zip(beg, ext))])
+
+        res, ierr = self.o.block_contract(list(ptrn), operand(L, lext, lbeg), operand(R, rext, rbeg), tuple(dext))
+        assert ierr == 0
+        out.a[...] = res.reshape(out.a.shape, order="F")
+        self._launches += 1
+        return out
+
     def si_energy_denominator_rhf(self, block, index_values, fock):
         self._launches += 1
         return self.o.si_energy_denominator_rhf(block.a, list(index_values), fock.a, self._moa)

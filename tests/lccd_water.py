@@ -140,3 +140,9 @@ def chained_through_persistence(tran_text, cc_text):
     j = cc.index("call iguess")
     cc = cc[:j] + "call read_2el\n" + cc[j:]
     return tran, cc
+
+
+def dense_ca(inp):
+    """the whole static array ca[mu,p] (norb x active MOs) and the segment extents of its two dimensions"""
+    seg = [inp["segs"]["ao"], inp["segs"]["p"]]
+    return qm.join_blocks(inp["arrays"]["ca"], seg), seg

@@ -39,6 +39,9 @@ class OracleBackend:
             A[segs] = np.zeros(shape, order="F")
         return HostBlock(A[segs])
 
+    def static_block(self, name, segs, shape):
+        return self.array_block(name, segs, shape)
+
     def fill(self, b, v):
         b.a[...] = v
         self.calls += 1

@@ -38,6 +38,10 @@ def test_persistence_chain_device_test_body_on_the_fake_api(oracle):
     dev.test_programs_chained_through_persistent_arrays_on_the_device(FakeApi(oracle))
 
 
+def test_static_in_place_device_test_body_on_the_fake_api(oracle):
+    dev.test_static_array_blocks_read_in_place_through_the_programs(FakeApi(oracle))
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

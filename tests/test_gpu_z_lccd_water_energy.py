@@ -240,3 +240,27 @@ def test_programs_chained_through_persistent_arrays_on_the_device(sip):
             A.destroy()
     for A in arrays2.values():
         A.destroy()
+
+
+@pytest.mark.timeout(600, method="thread")   # first GPU run pending: never hang the box
+def test_static_array_blocks_read_in_place_through_the_programs(sip):
+    """SURVEY 8f row 2 inside real programs: `ca` is ONE resident (norb x nmo) array and every `...*ca[mu,p]` of the
+    transformation program and of the LCCD AO ladder reads its block in place (sipgpu_block_contract_sliced) instead of
+    through an extracted copy -- transformation -> LCCD golden with the in-place path"""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs("fine")
+    ca, ca_segs = lw.dense_ca(inp)
+    for n in lw.MO_CLASSES:
+        inp["arrays"][n] = {}
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    in_place = {"ca": (sip.DeviceBlock.from_numpy(ca), ca_segs)}
+    be = DeviceBackend(sip, arrays, record=True, static_in_place=in_place)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    Walker(Program(lw.PROGRAM_TRAN), be, inp["segs"], index_base=inp["index_base"]).run()
+    _, hist = lw.converge(Walker(Program(lw.PROGRAM), be, inp["segs"], index_base=inp["index_base"]), be.value)
+    print(f"\ntransformation + LCCD with ca read in place: lccd_correlation {hist[-1]:.14f}")
+    assert abs(hist[-1] - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]
+    for A in arrays.values():
+        A.destroy()

@@ -82,3 +82,24 @@ def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentat
     assert st["fused_accumulates"] > 0 and st["temps_elided"] > 0
     assert len(level) == len(unit) > 0 and min(level) >= 1
     assert not w.locals
+
+
+def test_static_array_slices_in_place_record_through_the_c_abi(sip):
+    """the in-place path of DeviceBackend (`static_in_place`): every contraction with a block of `ca` goes through
+    sipgpu_block_contract_sliced -- dry mode checks that the library accepts the whole transformation program and an
+    LCCD iteration that way (pattern, slice bounds against the parent extents)"""
+    inp = lw.inputs("fine")
+    ca, ca_segs = lw.dense_ca(inp)
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    with sip.recording(dry=True):
+        arrays = {name: DryArray(sip, [inp["segs"][k] for k in kinds]) for name, kinds in lw.KINDS.items()}
+        be = DryBackend(sip, arrays, record=False, static_in_place={"ca": (sip.DeviceBlock(ca.shape), ca_segs)})
+        be.fock = sip.DeviceBlock(inp["fock"].shape)
+        Walker(Program(lw.PROGRAM_TRAN), be, inp["segs"], index_base=inp["index_base"]).run()
+        sip.wl_flush()
+        w = Walker(Program(lw.PROGRAM), be, inp["segs"], index_base=inp["index_base"])
+        w.run()
+        w.run_proc("iteration")
+        sip.wl_flush()
+        st = sip.wl_stats()
+    assert st["recorded"] > 5000 and not arrays["ca"].blocks       # no block of ca was ever materialised
