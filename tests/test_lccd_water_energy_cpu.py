@@ -414,3 +414,78 @@ def test_programs_chained_through_persistent_arrays(oracle):
     assert abs(hist[-1] - lw.GOLDEN["lccd_correlation"]) < lw.GOLDEN["tolerance"]
     with pytest.raises(KeyError):                                            # nothing left to restore a second time
         Walker(Program(cc_text), be2, inp["segs"], index_base=inp["index_base"]).run()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's race rules (distributed_block_consistency.cpp:25-175) applied to the transcribed programs
+# ---------------------------------------------------------------------------------------------------------------------
+class AccessLoggingBackend(OracleBackend):
+    """logs (section, worker, GET/PUT/PUT_ACCUMULATE) of every block of a served / distributed array"""
+    GET, PUT, ACC = 0, 1, 2
+
+    def __init__(self, *a, log, rank, **kw):
+        super().__init__(*a, **kw)
+        self.log, self.rank, self.section = log, rank, 1
+
+    def array_block(self, name, segs, shape):
+        self.log[name, segs].append((self.section, self.rank, self.GET))
+        return super().array_block(name, segs, shape)
+
+    def static_block(self, name, segs, shape):          # static arrays are replicated, not served: no rule applies
+        return OracleBackend.array_block(self, name, segs, shape)
+
+    def put(self, arr, segs, b):
+        self.log[arr, segs].append((self.section, self.rank, self.PUT))
+        super().put(arr, segs, b)
+
+    def put_accumulate(self, arr, segs, b):
+        self.log[arr, segs].append((self.section, self.rank, self.ACC))
+        super().put_accumulate(arr, segs, b)
+
+    def put_initialize(self, arr, segs, shape, v):
+        self.log[arr, segs].append((self.section, self.rank, self.PUT))
+        super().put_initialize(arr, segs, shape, v)
+
+    def barrier(self):
+        self.section += 1
+
+
+def illegal_accesses(oracle, text, case, world=3):
+    import collections
+
+    log = collections.defaultdict(list)
+    for r in range(world):          # the access pattern does not depend on the data: the workers can run one after another
+        inp = lw.inputs(case)
+        be = AccessLoggingBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"], log=log, rank=r)
+        w = Walker(Program(text), be, inp["segs"], rank=r, world=world, index_base=inp["index_base"])
+        w.run()
+        if "iteration" in w.p.procs:
+            w.run_proc("iteration")
+    bad = []
+    for key, acc in log.items():
+        acc.sort(key=lambda t: (t[0], t[1]))
+        k = oracle.block_consistency([a[2] for a in acc], [a[1] for a in acc], [a[0] for a in acc])
+        if k != -1:
+            bad.append((key, acc[k]))
+    return bad, sum(len(v) for v in log.values())
+
+
+@pytest.mark.parametrize("program,case", [("tran", "all_fine"), ("lccd", "fine"), ("lccsd", "all_fine"), ("ccsd", "all_fine"),
+                                          ("(T)", "hf_fine")])
+def test_transcribed_programs_obey_the_reference_race_rules(oracle, program, case):
+    """every access of three workers to every block of every served / distributed array, section by section, through
+    the oracle's restatement of DistributedBlockConsistency::update_and_check_consistency: no illegal access, i.e. the
+    transcriptions kept the barrier structure that makes the reference's programs race-free"""
+    text = {"tran": lw.PROGRAM_TRAN, "lccd": lw.PROGRAM, "lccsd": lw.PROGRAM_LCCSD, "ccsd": lw.PROGRAM_CCSD,
+            "(T)": lw.PROGRAM_PT}[program]
+    bad, n = illegal_accesses(oracle, text, case)
+    assert n > 2000 and not bad, bad[:5]
+
+
+def test_race_rule_check_detects_a_missing_barrier(oracle):
+    """negative control: without the barrier between the first and second quarter transformation, Vxxxi is written by
+    one worker and read by another in the same section"""
+    text = lw.PROGRAM_TRAN.replace("endpardo mu, nu, lambda\nserver_barrier\n", "endpardo mu, nu, lambda\n", 1)
+    assert text != lw.PROGRAM_TRAN
+    bad, _ = illegal_accesses(oracle, text, "all_fine")
+    assert bad and all(key[0] == "vxxxi" for key, _ in bad)
