@@ -9,7 +9,8 @@ tests/golden/water_321g_setup.json by scripts/make_water_setup_golden.py), so th
 driven with the real amplitudes equations of src/sialx/qm/cc/rlccd_rhf.sialx and its result compared with the
 reference's golden energies:
 
-  * McMurchie-Davidson integrals over contracted cartesian s/p Gaussians (overlap, kinetic, nuclear attraction,
+  * McMurchie-Davidson integrals over contracted s/p/d Gaussians (cartesian, or real solid harmonics for the d shells of a
+    setup with intspherical = 1 -- test/ccsdpt_test.dat; overlap, kinetic, nuclear attraction,
     electron repulsion), Boys function by series / asymptotic expansion + recursion;
   * closed-shell RHF with DIIS from the core-Hamiltonian guess (what scf_rhf_coreh.sialx converges to);
   * the Mulliken-ordered MO integral classes of src/sialx/qm/utility/tran_rhf_no4v.sialx:494-523
@@ -28,36 +29,49 @@ import numpy as np
 # ------------------------------------------------------------------------------------------------------------------
 # basis: the shell tables of a .dat (setup_reader.cpp:486-612 names) -> primitive cartesian functions + contraction
 # ------------------------------------------------------------------------------------------------------------------
+_CARTESIAN = {0: [(0, 0, 0)], 1: [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
+              2: [(2, 0, 0), (1, 1, 0), (1, 0, 1), (0, 2, 0), (0, 1, 1), (0, 0, 2)]}
+_SOLID_D = [{(1, 1, 0): 1.0}, {(0, 1, 1): 1.0}, {(1, 0, 1): 1.0}, {(2, 0, 0): 1.0, (0, 2, 0): -1.0},
+            {(0, 0, 2): 2.0, (2, 0, 0): -1.0, (0, 2, 0): -1.0}]
+
+
 def basis_from_setup(setup):
     """-> dict(center[nprim,3], alpha[nprim], lmn[nprim,3], W[nprim, nao]): AO = sum_p W[p, ao] * g_p, the g_p being
     UNNORMALISED cartesian Gaussians x^l y^m z^n exp(-alpha r^2); W carries coefficient x primitive norm, and every
     contracted function is scaled to unit self-overlap afterwards (the energies do not depend on that scale)."""
     ia, fa = setup["int_arrays"], setup["arrays"]
+    spherical = bool(setup["ints"].get("intspherical", 0))
     coords = np.array(fa["coords"][1]).reshape(-1, 3)          # coords(xyz, atom), column-major
     alphas, pcoeffs = np.array(fa["alphas"][1]), np.array(fa["pcoeffs"][1])
     nshells = len(ia["ivangmom"][1])
+    if "atom" not in ia and len(coords) != 1:
+        raise ValueError("setup without a shell -> atom table and more than one centre")
     prim, cols = [], []                                        # prim: (center, alpha, (l,m,n)); cols: list of {prim index: w}
     for s in range(nshells):
         L, ncf, npf = ia["ivangmom"][1][s], ia["ncfps"][1][s], ia["npfps"][1][s]
-        if L > 1:
-            raise ValueError("only s and p shells are implemented")
-        A = coords[ia["atom"][1][s] - 1]
+        if L > 2:
+            raise ValueError("only s, p and d shells are implemented")
+        A = coords[ia["atom"][1][s] - 1] if "atom" in ia else coords[0]      # older setups of one atom carry no table
         a0, c0 = ia["ixalphas"][1][s] - 1, ia["ixpcoeffs"][1][s] - 1
-        comps = [(0, 0, 0)] if L == 0 else [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+        comps = _CARTESIAN[L]
+        # functions of the shell as combinations of its cartesian components: the components themselves, or (d shells of a
+        # setup with intspherical = 1) the five real solid harmonics.  Only the SPAN matters for the energies.
+        funcs = _SOLID_D if (L == 2 and spherical) else [{lmn: 1.0} for lmn in comps]
         base = {}
         for p in range(npf):
             for lmn in comps:
                 base[p, lmn] = len(prim)
                 prim.append((A, alphas[a0 + p], lmn))
         for c in range(ncf):
-            for lmn in comps:
+            for f in funcs:
                 col = {}
                 for p in range(npf):
                     coef = pcoeffs[c0 + c * npf + p]           # pcoeffs(prim, contracted) per shell, column-major
                     if coef != 0.0:
                         al = alphas[a0 + p]
                         norm = (2.0 * al / math.pi) ** 0.75 * (2.0 * math.sqrt(al)) ** L
-                        col[base[p, lmn]] = coef * norm
+                        for lmn, w in f.items():
+                            col[base[p, lmn]] = coef * norm * w
                 cols.append(col)
     W = np.zeros((len(prim), len(cols)))
     for j, col in enumerate(cols):
@@ -133,8 +147,8 @@ def _hermite_E(imax, jmax, a, b, XAB):
 def _select(E, li, lj, dj, tmax):
     """per-pair selection: out[t][i, j] = E[li[i], lj[j] + dj][t][i, j] (zero where t exceeds the order or lj+dj < 0)"""
     out = [np.zeros_like(E[0, 0][0]) for _ in range(tmax + 1)]
-    for i in (0, 1):
-        for j in (0, 1):
+    for i in range(int(li.max()) + 1):
+        for j in range(int(lj.max()) + 1):
             if j + dj < 0:
                 continue
             mask = (li[:, None] == i) & (lj[None, :] == j)
@@ -178,31 +192,33 @@ def ao_integrals(basis):
     a, b = al[:, None] * np.ones((1, n)), np.ones((n, 1)) * al[None, :]
     p = a + b
     P = (a[..., None] * A[:, None, :] + b[..., None] * A[None, :, :]) / p[..., None]
-    E1 = [_hermite_E(1, 3, a, b, A[:, None, d] - A[None, :, d]) for d in range(3)]
-    Es = [_select(E1[d], lmn[:, d], lmn[:, d], 0, 2) for d in range(3)]          # [dir][t] -> (n, n)
+    lmax = int(lmn.max())                                                         # 1 for s/p sets, 2 with d shells
+    E1 = [_hermite_E(lmax, lmax + 2, a, b, A[:, None, d] - A[None, :, d]) for d in range(3)]
+    Es = [_select(E1[d], lmn[:, d], lmn[:, d], 0, 2 * lmax) for d in range(3)]    # [dir][t] -> (n, n)
     # ---- overlap and kinetic energy (1-D factors) ----
     s1 = [Es[d][0] * np.sqrt(math.pi / p) for d in range(3)]
     k1 = []
     for d in range(3):
         lj = lmn[:, d][None, :] * np.ones((n, 1))
         up = _select(E1[d], lmn[:, d], lmn[:, d], 2, 0)[0] * np.sqrt(math.pi / p)
-        dn = _select(E1[d], lmn[:, d], lmn[:, d], -2, 0)[0] * np.sqrt(math.pi / p)   # zero for l <= 1
+        dn = _select(E1[d], lmn[:, d], lmn[:, d], -2, 0)[0] * np.sqrt(math.pi / p)   # zero where l <= 1
         k1.append(-0.5 * (lj * (lj - 1) * dn - 2.0 * b * (2 * lj + 1) * s1[d] + 4.0 * b * b * up))
     S = s1[0] * s1[1] * s1[2]
     T = k1[0] * s1[1] * s1[2] + s1[0] * k1[1] * s1[2] + s1[0] * s1[1] * k1[2]
     # ---- nuclear attraction ----
-    tuv = [(t, u, v) for t in range(3) for u in range(3 - t) for v in range(3 - t - u)]
+    o = 2 * lmax                                                                  # Hermite order of a primitive pair
+    tuv = [(t, u, v) for t in range(o + 1) for u in range(o + 1 - t) for v in range(o + 1 - t - u)]
     Epair = {k: Es[0][k[0]] * Es[1][k[1]] * Es[2][k[2]] for k in tuv}
     V = np.zeros((n, n))
     for Z, C in zip(basis["charge"], basis["coords"]):
-        R = _hermite_R(2, p, P[..., 0] - C[0], P[..., 1] - C[1], P[..., 2] - C[2])
+        R = _hermite_R(o, p, P[..., 0] - C[0], P[..., 1] - C[1], P[..., 2] - C[2])
         V -= Z * 2.0 * math.pi / p * sum(Epair[k] * R[k] for k in tuv)
     # ---- electron repulsion on the (pair, pair) grid ----
     pf, Pf = p.ravel(), P.reshape(-1, 3)
     Ef = {k: Epair[k].ravel() for k in tuv}
     pp, qq = pf[:, None], pf[None, :]
     alpha = pp * qq / (pp + qq)
-    R = _hermite_R(4, alpha, Pf[:, None, 0] - Pf[None, :, 0], Pf[:, None, 1] - Pf[None, :, 1],
+    R = _hermite_R(2 * o, alpha, Pf[:, None, 0] - Pf[None, :, 0], Pf[:, None, 1] - Pf[None, :, 1],
                    Pf[:, None, 2] - Pf[None, :, 2])
     G = np.zeros((n * n, n * n))
     for k1_ in tuv:

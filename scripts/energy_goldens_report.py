@@ -23,7 +23,8 @@ for name, g in ((lw.FROZEN, lw.GOLDEN["scf_energy"]), (lw.ALL, lw.GOLDEN["scf_en
     rows.append((f"scf_energy ({name})", g, e, "numpy input stage (oracle/qm_inputs.py)", "-", "-"))
 for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "all_fine")),
                              ("lccsd", lw.PROGRAM_LCCSD, ("all_dat", "all_fine")),
-                             ("ccsd", lw.PROGRAM_CCSD, ("all_dat", "all_fine", "hf_dat", "hf_fine", "hf_fc_dat", "hf_fc_fine"))):
+                             ("ccsd", lw.PROGRAM_CCSD, ("all_dat", "all_fine", "hf_dat", "hf_fine", "hf_fc_dat", "hf_fc_fine",
+                                                               "ne_dat", "ne_fine"))):
     for case in cases:
         inp = lw.inputs(case)
         be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
@@ -59,6 +60,16 @@ for program, text, cases in (("lccd", lw.PROGRAM, ("dat", "fine", "all_dat", "al
                     rows.append((f"{comp} HF", gh[comp], be.value(sc[comp]), how_t, "-", "-"))
                 rows.append(("E(T) HF = eaaa+esaaa+eaab+esaab", gh["ccsdpt_energy"] - gh["ccsd_energy"], e_t, how_t, "-", be.calls - c0))
                 rows.append(("ccsdpt_energy HF (cc_conv 1e-10)", gh["ccsdpt_energy"], e_tot + e_t, how_t, len(hist), be.calls))
+            elif case.startswith("ne"):
+                # BASELINE config 2: test/ccsdpt_test.dat (DISABLED_ccsdpt_test, test_qm.cpp:22-52); goldens of a run stopped at
+                # the setup's cc_conv 1e-7
+                gn = lw.GOLDEN["ne_ccsdpt_test"]
+                c0 = be.calls
+                sc = Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+                how_t = how.replace("ccsd program", "ccsd program + restated (T), rank-6 blocks")
+                for comp in ("eaab", "esaab"):
+                    rows.append((f"{comp} Ne ccsdpt_test.dat (cc_conv 1e-7)", gn[comp], be.value(sc[comp]), how_t, len(hist),
+                                 be.calls - c0))
             else:
                 rows.append(("ccsd_energy HF frozen core (1e-12)", lw.GOLDEN["hf"]["frozen_core_ccsd_energy"], e_tot, how, len(hist), be.calls))
         else:

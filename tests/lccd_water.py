@@ -53,7 +53,10 @@ CASES = {"dat": (FROZEN, None), "fine": (FROZEN, {"moa": [1, 2, 2, 3, 5], "occ":
          # hydrogen fluoride / 3-21G (the reference's second_ccsdpt_test and lamccsdpt_test): all electron, frozen core
          "hf_dat": ("second_ccsdpt_test.dat", None), "hf_fc_dat": ("lamccsdpt_test.dat", None),
          "hf_fine": ("second_ccsdpt_test.dat", {"moa": [2, 3, 2, 4], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 2]}),
-         "hf_fc_fine": ("lamccsdpt_test.dat", {"moa": [1, 3, 1, 2, 4], "occ": (2, 3), "virt": (4, 5), "ao": [3, 6, 2]})}
+         "hf_fc_fine": ("lamccsdpt_test.dat", {"moa": [1, 3, 1, 2, 4], "occ": (2, 3), "virt": (4, 5), "ao": [3, 6, 2]}),
+         # neon / cc-pVDZ with spherical d functions (the reference's DISABLED_ccsdpt_test = BASELINE config 2, ccsdpt_test.dat)
+         "ne_dat": ("ccsdpt_test.dat", None),
+         "ne_fine": ("ccsdpt_test.dat", {"moa": [2, 3, 4, 5], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 5]})}
 
 
 def golden(case):

@@ -30,6 +30,11 @@ def test_ccsd_t_device_test_body_on_the_fake_api(oracle):
     dev.test_ccsd_energy_of_hydrogen_fluoride_on_the_device(FakeApi(oracle))
 
 
+@pytest.mark.parametrize("case,record", [("ne_dat", True), ("ne_dat", False)])
+def test_neon_ccsd_t_device_test_body_on_the_fake_api(oracle, case, record):
+    dev.test_ccsd_t_of_neon_on_the_device_matches_the_goldens_of_ccsdpt_test(FakeApi(oracle), case, record)
+
+
 def test_transformation_pipeline_device_test_body_on_the_fake_api(oracle):
     dev.test_transformation_then_cc_program_on_the_device(FakeApi(oracle), "fine", "lccd")
 

@@ -180,6 +180,34 @@ def test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(sip, case, record):
 
 
 @pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
+@pytest.mark.parametrize("case,record", [("ne_fine", True), ("ne_dat", False)])
+def test_ccsd_t_of_neon_on_the_device_matches_the_goldens_of_ccsdpt_test(sip, case, record):
+    """BASELINE config 2 at file level (test/ccsdpt_test.dat, DISABLED_ccsdpt_test, test/test_qm.cpp:22-52: eaab
+    -0.0010909774775509193, esaab 8.5547845910409156e-05; neon, [3s2p1d] with spherical d).  The goldens carry the setup's own
+    cc_conv 1e-7; the converged run is 1.5e-10 / 2.2e-10 from them on the CPU oracle backend -- asserted at north_star's 1e-9,
+    and against the oracle-backend value at 1e-12."""
+    from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
+
+    inp = lw.inputs(case)
+    g = lw.GOLDEN["ne_ccsdpt_test"]
+    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
+    arrays = device_arrays(sip, inp)
+    be = DeviceBackend(sip, arrays, record=record)
+    be.fock = sip.DeviceBlock.from_numpy(inp["fock"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    sc = Walker(Program(lw.PROGRAM_PT), be, inp["segs"], index_base=inp["index_base"]).run()
+    eaab, esaab = be.value(sc["eaab"]), be.value(sc["esaab"])
+    print(f"\nCCSD(T) Ne / ccsdpt_test.dat on the device ({case}, record={record}): ccsd_correlation {hist[-1]:.14f}, "
+          f"eaab {eaab:.16f} (golden {g['eaab']:.16f}), esaab {esaab:.16e} (golden {g['esaab']:.16e})")
+    assert abs(eaab - g["eaab"]) < 1e-9 and abs(esaab - g["esaab"]) < 1e-9
+    assert abs(eaab - (-0.0010909776279972)) < 1e-12 and abs(esaab - 8.554806688752e-05) < 1e-12
+    assert abs(hist[-1] - (-0.190861375509551)) < 1e-10
+    for A in arrays.values():
+        A.destroy()
+
+
+@pytest.mark.timeout(900, method="thread")   # first GPU run pending: never hang the box
 @pytest.mark.parametrize("case,program", [("fine", "lccd"), ("all_dat", "ccsd")])
 def test_transformation_then_cc_program_on_the_device(sip, case, program):
     """the whole post-SCF pipeline on the device: AO integrals + MO coefficients -> tests/golden/tran_program.sialx

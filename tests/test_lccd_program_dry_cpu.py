@@ -55,7 +55,8 @@ class DryBackend(DeviceBackend):
 
 @pytest.mark.parametrize("segmentation,program", [("dat", "lccd"), ("fine", "lccd"), ("all_dat", "lccd"),
                                                   ("all_fine", "lccd"), ("all_dat", "lccsd"), ("all_fine", "lccsd"),
-                                                  ("all_dat", "ccsd"), ("all_fine", "ccsd"), ("hf_fine", "ccsd+t")])
+                                                  ("all_dat", "ccsd"), ("all_fine", "ccsd"), ("hf_fine", "ccsd+t"),
+                                                  ("ne_fine", "ccsd+t"), ("ne_dat", "ccsd+t")])
 def test_lccd_program_records_and_schedules_on_the_device_backend(sip, segmentation, program):
     inp = lw.inputs(segmentation)
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
