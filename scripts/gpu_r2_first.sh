@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 # 1. the whole GPU suite (includes tests/test_gpu_z_lccd_water_energy.py = the reference's LCCD energy golden on the device,
 #    never run on a GPU yet; it sorts last and prints the energies with -s; also the level-1 composition of tests/test_gpu_ref_block_on_sipgpu.py, never run on a GPU yet,
 #    and everything behind the export map / SIPGPU_NO_TENSORDIL_PROTOTYPES changes)
-timeout 300 python -m pytest tests -m gpu -q -rs > gpurun_out/pytest_gpu_r2_first.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu_r2_first.log
+timeout 900 python -m pytest tests -m gpu -q -rs > gpurun_out/pytest_gpu_r2_first.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu_r2_first.log
 # 2. smoke + the CPU arm with the fair thread policy (expected near 0.19 TFLOP/s on 16 cores, was 0.119)
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_r2.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_r2.log
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err; echo "ref arm rc=$?"
