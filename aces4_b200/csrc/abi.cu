@@ -369,7 +369,7 @@ namespace {
 
 int labels_to_ptrn(int drank, const int* dlab, int lrank, const int* llab, int rrank, const int* rlab, int* ptrn) {
     int aces[3 + 96], k = 3;
-    if (drank < 0 || lrank < 0 || rrank < 0 || drank + lrank + rrank > 96) return SIPGPU_E_ARG;
+    if (drank < 0 || lrank < 0 || rrank < 0 || drank > 32 || lrank > 32 || rrank > 32) return SIPGPU_E_ARG;
     aces[0] = drank; aces[1] = lrank; aces[2] = rrank;
     for (int i = 0; i < drank; ++i) aces[k++] = dlab[i];
     for (int i = 0; i < lrank; ++i) aces[k++] = llab[i];
@@ -721,7 +721,12 @@ int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int
 int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, double* D, int lrank, const int* lext,
                                  const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
                                  const double* R, double alpha, double beta) {
-    int ptrn[64];
+    // ranks are validated BEFORE the label conversion writes lrank + rrank pattern entries
+    if (drank < 0 || lrank < 0 || rrank < 0 || drank > kMaxRank || lrank > kMaxRank || rrank > kMaxRank) {
+        set_error("contract: ranks (%d, %d, %d) outside 0..%d", drank, lrank, rrank, kMaxRank);
+        return SIPGPU_E_ARG;
+    }
+    int ptrn[2 * kMaxRank];
     SIP_TRY(labels_to_ptrn(drank, dlab, lrank, llab, rrank, rlab, ptrn));
     return sipgpu_block_contract(ptrn, L, lrank, lext, R, rrank, rext, D, drank, dext, alpha, beta);
 }

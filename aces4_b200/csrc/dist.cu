@@ -110,6 +110,10 @@ int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_ra
     }
     a->base[my_rank] = (double*)p;
     SIP_CUDA(cudaMemsetAsync(p, 0, bytes, ctx().stream));  // new server blocks are zero (disk_backed_block_map.cpp:150-183)
+    // With peers the zero fill must have landed before the slab can be exported: a peer's first put / put += may arrive
+    // while this rank's stream is still busy with earlier work and would otherwise be wiped by the late memset (the
+    // reference needs no barrier between create and the first put either).
+    if (world > 1) SIP_CUDA(cudaStreamSynchronize(ctx().stream));
     *out = a;
     return SIPGPU_OK;
 }
@@ -217,6 +221,11 @@ int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta) {
     if (!dst) return SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT_ACCUMULATE;
     const long long n = sipgpu_array_block_size(a, idx);
+    // With several ranks put_increment shares a block with other workers' put_increment / put += inside one barrier
+    // section (it counts as PUT_ACCUMULATE for the race rules, distributed_block_consistency.cpp:60); the reference
+    // serialises them at the server.  A plain read-modify-write would lose updates, so the increment is atomic too.
+    if (a->world > 1)
+        return wl_active() ? wl_rec_ew(WL_REDINCR, dst, nullptr, nullptr, n, delta) : ew_red_increment(dst, n, delta);
     return wl_active() ? wl_rec_ew(WL_INCR, dst, nullptr, nullptr, n, delta) : ew_increment(dst, n, delta);
 }
 int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor) {

@@ -230,6 +230,21 @@ int ew_red_add(double* d, const double* s, long long n) {
     return SIPGPU_OK;
 }
 
+// d[i] += delta with red.global.add.f64: put_increment on a block other ranks may increment / accumulate concurrently.
+__global__ void __launch_bounds__(kThreads) red_incr_kernel(double* __restrict__ d, long long n, double delta) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(delta) : "memory");
+}
+int ew_red_increment(double* d, long long n, double delta) {
+    if (n < 0 || !d) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    SIP_TRY(ensure_init());
+    red_incr_kernel<<<grid_for(n), kThreads, 0, ctx().stream>>>(d, n, delta);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
 // Seeded synthetic fill: d[i] = scale * uniform(-1,1) from splitmix64((seed ^ tag) + (i+1)*golden).  Pure integer
 // arithmetic + exact conversions, so the CPU oracle's restatement (oracle_fill_hash) is bit-identical.
 __global__ void __launch_bounds__(kThreads) fill_hash_kernel(double* __restrict__ d, long long n, unsigned long long key,

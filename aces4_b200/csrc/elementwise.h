@@ -16,6 +16,7 @@ int ew_dot_device(const double* a, const double* b, long long n, double* d_out, 
 int ew_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg);
 int ew_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg);
 int ew_red_add(double* d, const double* s, long long n);
+int ew_red_increment(double* d, long long n, double delta);  // d[i] += delta, atomically (many-writer put_increment)
 int ew_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale);
 int ew_copy_probe(double* d, const double* s, long long n);
 // worklist.cu: d_i = beta * d_i for n blocks in ONE launch (beta = 0: zero fill)

@@ -13,6 +13,7 @@
 // replaces the block by a fresh one, :360-363, :411-414).  The transition itself is a pure function
 // (sipgpu_mirror_transition) so that it is covered without a device; sipgpu_mirror_* applies it to real buffers.
 #include "common.h"
+#include "worklist.h"
 
 namespace sipgpu {
 enum { ON_HOST = 1, ON_GPU = 2, DIRTY_HOST = 4, DIRTY_GPU = 8 };
@@ -73,7 +74,9 @@ int sipgpu_mirror_create(double* host_or_null, long long n, sipgpu_mirror** out)
 }
 int sipgpu_mirror_destroy(sipgpu_mirror* m) {
     if (!m) return SIPGPU_OK;
-    if (m->dev) pool_free(m->dev);
+    // inside a recording the ops that touch the device side have not run yet: defer the free like sipgpu_block_free
+    if (m->dev) { if (wl_active()) wl_free(m->dev); else pool_free(m->dev); }
+    if (m->own_host && m->host) wl_flush();  // recorded ops may still name the pinned host side (h2d / d2h)
     if (m->own_host && m->host) cudaFreeHost(m->host);
     delete m;
     return SIPGPU_OK;
@@ -87,6 +90,9 @@ double* sipgpu_mirror_access(sipgpu_mirror* m, int op) {
     if (!m) return nullptr;
     int nb = 0, act = 0;
     if (sipgpu_mirror_transition(m->bits, op, &nb, &act) != SIPGPU_OK) return nullptr;
+    // sipgpu.h promises that blocking calls flush an open recording: a host access must see what the recorded writers
+    // of the device side produce, and a copy towards the device must not overtake recorded readers of the old contents
+    if ((act != ACT_NONE || op >= OP_READ_HOST) && wl_flush() != SIPGPU_OK) return nullptr;
     if (ensure_init() != SIPGPU_OK) return nullptr;
     const size_t bytes = sizeof(double) * (size_t)(m->n > 0 ? m->n : 1);
     if ((act == ACT_ALLOC_DEV_H2D || act == ACT_NEW_DEV) && !m->dev) {

@@ -179,7 +179,7 @@ void ranges_of(const Op& o, std::vector<WlRange>& out) {
             const bool rd = o.ewop == WL_SCALE || o.ewop == WL_INCR || o.ewop == WL_AXPY;
             if (o.a) out.push_back({o.a, nb, WL_R});
             if (o.b) out.push_back({o.b, nb, WL_R});
-            out.push_back({o.D, nb, o.ewop == WL_REDADD ? WL_ATOMIC : (rd ? WL_RW : WL_W)});
+            out.push_back({o.D, nb, (o.ewop == WL_REDADD || o.ewop == WL_REDINCR) ? WL_ATOMIC : (rd ? WL_RW : WL_W)});
             break;
         }
         default:
@@ -238,9 +238,26 @@ __global__ void __launch_bounds__(kEwThreads) ew_batched_kernel(const EwDesc* __
         const double* a = e.a ? e.a + base : nullptr;
         const double* b = e.b ? e.b + base : nullptr;
         const int op = e.op;
-        if (op == WL_REDADD) {
+        if (op == WL_REDADD) {   // many-writer put +=: all loads of a pass in flight, then the fire-and-forget adds
+            constexpr int U = 8;
+            for (int i0 = threadIdx.x; i0 < cnt; i0 += U * kEwThreads) {
+                double x[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * kEwThreads;
+                    x[u] = i < cnt ? __ldg(a + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * kEwThreads;
+                    if (i < cnt) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(x[u]) : "memory");
+                }
+            }
+            continue;
+        }
+        if (op == WL_REDINCR) {  // many-writer put_increment
             for (int i = threadIdx.x; i < cnt; i += kEwThreads)
-                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(a[i]) : "memory");
+                asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(d + i), "d"(e.f) : "memory");
             continue;
         }
         const bool rd = op == WL_SCALE || op == WL_INCR || op == WL_AXPY;

@@ -16,7 +16,7 @@ struct WlRange {
 };
 
 // elementwise op codes of the batched kernel (same arithmetic as elementwise.cu)
-enum WlEwOp { WL_FILL = 0, WL_SCALE, WL_SCALE_COPY, WL_INCR, WL_AXPY, WL_ADDSUB, WL_REDADD };
+enum WlEwOp { WL_FILL = 0, WL_SCALE, WL_SCALE_COPY, WL_INCR, WL_AXPY, WL_ADDSUB, WL_REDADD, WL_REDINCR };
 
 bool wl_active();  // recording (entry points divert into the wl_rec_* functions)
 bool wl_dry();     // recording without a device (host-only planning, CPU tests)

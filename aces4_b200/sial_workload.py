@@ -175,47 +175,55 @@ class SyntheticCCSD:
         A = self.arr[name]
         return A.block_ptr(idx), A.block_shape(idx)
 
+    def _term_worklist(self, t, dests, dest_ptr, dest_shape, count=True):
+        """The destination-stationary work-list of term `t` over the destination blocks `dests`: one chain of operand
+        pairs per destination (all contracted segment combinations whose operands exist).  Returns (BatchedContraction
+        or None, destinations whose whole chain is absent)."""
+        dlab, llab, rlab = t["dlab"], t["llab"], t["rlab"]
+        labs = sorted(set(dlab + llab + rlab))
+        num = {c: n + 1 for n, c in enumerate(labs)}
+        ptrn, ierr = api.get_contraction_ptrn([num[c] for c in dlab], [num[c] for c in llab], [num[c] for c in rlab])
+        assert ierr == 0, (t["name"], ierr)
+        contracted = [c for c in llab if c in rlab]
+        cranges = [range(1, (self.nv if _is_virtual(c) else self.no) + 1) for c in contracted]
+        lsh, rsh, dsh, lp, rp, dp, chain = [], [], [], [], [], [], [0]
+        empty = []   # destinations whose whole chain is absent (block sparsity)
+        for blk in dests:
+            segs = dict(zip(dlab, blk))
+            first = True
+            for cseg in np.ndindex(*[len(r) for r in cranges]):
+                for c, s in zip(contracted, cseg):
+                    segs[c] = s + 1
+                if not (self._operand_present(t["L"], tuple(segs[c] for c in llab)) and
+                        self._operand_present(t["R"], tuple(segs[c] for c in rlab))):
+                    continue   # an absent amplitude block contributes nothing: the pair never reaches the device
+                pl, shl = self._operand(t["L"], llab, segs)
+                pr, shr = self._operand(t["R"], rlab, segs)
+                lp.append(pl), rp.append(pr)
+                if count:
+                    f = 2.0 * float(np.prod(dest_shape(blk))) * float(np.prod([self._seg_ext(c, segs[c]) for c in contracted]))
+                    self.flops += f
+                    self.term_flops_rank[t["name"]] = self.term_flops_rank.get(t["name"], 0.0) + f
+                if first:
+                    lsh.append(shl), rsh.append(shr)
+                    first = False
+                else:
+                    # a chain shares ONE shape: with non-uniform contracted segments the chain is split below
+                    assert shl == lsh[-1] and shr == rsh[-1], "non-uniform contracted segments: split the chain"
+            if first:
+                empty.append(blk)
+                continue
+            chain.append(len(lp))
+            dsh.append(dest_shape(blk))
+            dp.append(dest_ptr(blk))
+        bc = api.BatchedContraction(ptrn, lsh, rsh, dsh, lp, rp, dp, chain_start=chain) if dp else None
+        return bc, empty
+
     def _build_worklists(self):
         self.worklists = []
         for t in self.terms:
-            dlab, llab, rlab = t["dlab"], t["llab"], t["rlab"]
-            labs = sorted(set(dlab + llab + rlab))
-            num = {c: n + 1 for n, c in enumerate(labs)}
-            ptrn, ierr = api.get_contraction_ptrn([num[c] for c in dlab], [num[c] for c in llab], [num[c] for c in rlab])
-            assert ierr == 0, (t["name"], ierr)
-            contracted = [c for c in llab if c in rlab]
-            cranges = [range(1, (self.nv if _is_virtual(c) else self.no) + 1) for c in contracted]
             dest = self.Xs if t["sym"] else self.T2new
-            lsh, rsh, dsh, lp, rp, dp, chain = [], [], [], [], [], [], [0]
-            empty = []   # destinations whose whole chain is absent (block sparsity)
-            for blk in self.mine:
-                segs = dict(zip(dlab, blk))
-                first = True
-                for cseg in np.ndindex(*[len(r) for r in cranges]):
-                    for c, s in zip(contracted, cseg):
-                        segs[c] = s + 1
-                    if not (self._operand_present(t["L"], tuple(segs[c] for c in llab)) and
-                            self._operand_present(t["R"], tuple(segs[c] for c in rlab))):
-                        continue   # an absent amplitude block contributes nothing: the pair never reaches the device
-                    pl, shl = self._operand(t["L"], llab, segs)
-                    pr, shr = self._operand(t["R"], rlab, segs)
-                    lp.append(pl), rp.append(pr)
-                    f = 2.0 * float(np.prod(dest.block_shape(blk))) * float(np.prod([self._seg_ext(c, segs[c]) for c in contracted]))
-                    self.flops += f
-                    self.term_flops_rank[t["name"]] = self.term_flops_rank.get(t["name"], 0.0) + f
-                    if first:
-                        lsh.append(shl), rsh.append(shr)
-                        first = False
-                    else:
-                        # a chain shares ONE shape: with non-uniform contracted segments the chain is split below
-                        assert shl == lsh[-1] and shr == rsh[-1], "non-uniform contracted segments: split the chain"
-                if first:
-                    empty.append(blk)
-                    continue
-                chain.append(len(lp))
-                dsh.append(dest.block_shape(blk))
-                dp.append(dest.block_ptr(blk))
-            bc = api.BatchedContraction(ptrn, lsh, rsh, dsh, lp, rp, dp, chain_start=chain) if dp else None
+            bc, empty = self._term_worklist(t, self.mine, dest.block_ptr, dest.block_shape)
             self.worklists.append((t, bc, empty))
 
     # ------------------------------------------------------------------------------------------------
@@ -234,12 +242,16 @@ class SyntheticCCSD:
 
     def iterate(self):
         """One iteration; returns the (global) energy-like scalar.  All device work is asynchronous on the library's
-        compute stream until the final scalar read-back."""
+        compute stream until the final scalar read-back.  The per-block traffic of a barrier section (get, put +=, the
+        block-wise scale / accumulate statements) is issued inside a recording (sipgpu_wl_begin / _end), so every section
+        reaches the device as a few descriptor-driven launches instead of one copy / kernel per block."""
         L = api.lib()
-        # (0) request T2old: fetch every block into the per-GPU replica (peer reads over NVLink when remote)
+        # (0) request T2old: fetch every block into the per-GPU replica (peer reads over NVLink when remote) -- one
+        # gather launch for the whole section
         rep = self.arr["T2old"]
-        for blk in self.blocks:
-            self.T2old.get(blk, out=rep.block_view(blk))
+        with api.recording():
+            for blk in self.blocks:
+                self.T2old.get(blk, out=rep.block_view(blk))
         # (1) W[c,k,a,i] = T2old[c,k,a,i] - T2old[c,i,a,k]   (rlccd_rhf.sialx:517-522): one slab copy, then one fused
         # permute-accumulate launch per block-shape class (W += -1 * T2old[c,i,a,k] permuted)
         W = self.arr["W"]
@@ -247,8 +259,9 @@ class SyntheticCCSD:
         for srcs, dsts in self._w_groups.values():
             api.permute_batched(srcs, [1, 1, 4, 3, 2], dsts, alpha=-1.0, beta=1.0)
         # (2) Xs = 0.5 * Vvovo on the owned destinations (T2newab, :327-340); T2new = direct terms; Xs += ring terms
-        for blk in self.mine:
-            self.Xs.block_view(blk).scale_and_copy(self.arr["Vvovo"].block_view(blk), 0.5)
+        with api.recording():
+            for blk in self.mine:
+                self.Xs.block_view(blk).scale_and_copy(self.arr["Vvovo"].block_view(blk), 0.5)
         first_direct = True
         for t, bc, empty in self.worklists:
             if not t["sym"] and first_direct:
@@ -271,16 +284,20 @@ class SyntheticCCSD:
             for blk in self.mine:
                 self.T2new.block_view(blk).fill(0.0)
         # (3) T2new[a,i,b,j] += Xs[a,i,b,j] locally, then section barrier before the many-writer phase
-        for blk in self.mine:
-            self.T2new.block_view(blk).accumulate(self.Xs.block_view(blk))
+        with api.recording():
+            for blk in self.mine:
+                self.T2new.block_view(blk).accumulate(self.Xs.block_view(blk))
         api.sync()
         self.barrier()
-        # (4) PREPARE T2new[b,j,a,i] += R[b,j,a,i]: permute locally, accumulate at the owner (red.add over NVLink)
-        for blk in self.mine:
-            a, i, b, j = blk
-            tmp = self._temp(self.T2new.block_shape((b, j, a, i)), 1)
-            api.permute_labels([3, 4, 1, 2], [1, 2, 3, 4], self.Xs.block_view(blk), out=tmp)
-            self.T2new.put_accumulate((b, j, a, i), tmp)
+        # (4) PREPARE T2new[b,j,a,i] += R[b,j,a,i]: permute, accumulate at the owner (red.add over NVLink).  Recorded:
+        # the temp of every block is forwarded, so the section is one fused permute + red.add launch per shape class
+        with api.recording():
+            for blk in self.mine:
+                a, i, b, j = blk
+                tmp = api.DeviceBlock(self.T2new.block_shape((b, j, a, i)))
+                api.permute_labels([3, 4, 1, 2], [1, 2, 3, 4], self.Xs.block_view(blk), out=tmp)
+                self.T2new.put_accumulate((b, j, a, i), tmp)
+                tmp.free()
         api.sync()
         self.barrier()
         # (5) energy (PROC energy, :272-300): e = sum T2new[a,i,b,j] * (2 V[a,i,b,j] - V[a,j,b,i])
@@ -298,6 +315,52 @@ class SyntheticCCSD:
         if self.allreduce is not None:
             e = self.allreduce(e)  # collective_sum (sial_ops_parallel.cpp:549-565)
         return e
+
+    # ------------------------------------------------------------------------------------------------
+    def recompute_t2new_block(self, blk):
+        """T2new[blk] recomputed on THIS rank from the replicated inputs alone (no distributed-array traffic): the direct
+        terms of blk, its ring-term block Xs[blk] and the transposed ring-term block Xs[(b,j,a,i)].  Parity check of the
+        cross-GPU path (put += into peer HBM, peer get): bench.py compares it with the block the owner holds."""
+        a, i, b, j = blk
+        tb = (b, j, a, i)
+        V = self.arr["Vvovo"]
+        shp = V.block_shape
+        out = api.DeviceBlock(shp(blk))
+        x1 = api.DeviceBlock(shp(blk)).scale_and_copy(V.block_view(blk), 0.5)
+        x2 = api.DeviceBlock(shp(tb)).scale_and_copy(V.block_view(tb), 0.5)
+        first = True
+        for t in self.terms:
+            if t["sym"]:
+                for dst, d in ((x1, blk), (x2, tb)):
+                    bc, _ = self._term_worklist(t, [d], lambda _b, p=dst.ptr: p, shp, count=False)
+                    if bc is not None:
+                        bc.launch(alpha=t["alpha"], beta=1.0)
+            else:
+                bc, _ = self._term_worklist(t, [blk], lambda _b, p=out.ptr: p, shp, count=False)
+                if bc is not None:
+                    bc.launch(alpha=t["alpha"], beta=0.0 if first else 1.0)
+                    first = False
+        if first:
+            out.fill(0.0)
+        out.accumulate(x1)
+        x2t = api.permute_labels([3, 4, 1, 2], [1, 2, 3, 4], x2)   # lhs[b',j',a',i'] = x2[a',i',b',j'] with blk' = (b,j,a,i)
+        out.accumulate(x2t)
+        return out
+
+    def verify_blocks(self, nsample=64, offset=0):
+        """Largest relative deviation, over `nsample` destination blocks spread over all owners, between the T2new block
+        held by its owner (fetched with `get`: a peer read when remote) and the block recomputed locally."""
+        n = len(self.blocks)
+        step = max(1, n // max(1, nsample))
+        worst = 0.0
+        for k in range(min(nsample, n)):
+            blk = self.blocks[(offset + k * step + (k % max(1, self.world))) % n]
+            want = self.recompute_t2new_block(blk)
+            got = self.T2new.get(blk)
+            diff = api.DeviceBlock(got.shape).set_add_sub(got, want, -1.0)
+            denom = max(got.norm2(), 1e-300)   # norm2 = sum of squares (tensor_block_norm2_, F90:213-240)
+            worst = max(worst, (diff.norm2() / denom) ** 0.5)
+        return worst
 
     def t2new_checksum(self):
         """(sum of squares, weighted checksum) over the owned T2new blocks -- for parity checks."""

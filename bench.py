@@ -55,7 +55,28 @@ def parse_args():
                     help="block density of the amplitude array (SURVEY 8d item 3 asks for 1.0 and 0.5); the headline is 1.0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--wall-budget", type=float, default=None,
+                    help="seconds this process may take in total (default 600, reference arm 150): a full-size iteration is "
+                         "36 s on one B200, so --steps/--warmup are capped to what fits (never below 3 warm-ups / 2 timed "
+                         "steps unless fewer were asked for); the line reports the ACTUAL steps/warmup and *_requested")
+    ap.add_argument("--verify-blocks", type=int, default=None,
+                    help="destination blocks per rank recomputed locally and compared with the owner's copy (default: 64 at "
+                         "N > 1, 8 at N = 1)")
     return ap.parse_args()
+
+
+T_START = time.monotonic()   # the wall budget counts from process start (imports included)
+# energy functional of the default workload (o = 3x20, v = 12x50, density 1, seed 0xACE54) from the N = 1 run of record
+# (BENCH_r01.json): every N must reproduce it -- the iteration's result does not depend on the partition
+ENERGY_N1 = 4286482.921305567
+
+
+def config_of(o_segs, v_segs, density, world):
+    """`config` is the same object in both arms (the driver compares them)."""
+    return {"workload": workload_name(o_segs, v_segs, density),
+            "flops_per_step": None,   # filled by the caller: algorithmic flops of one whole iteration
+            "parallelism": f"destination blocks block-cyclic over {world} rank(s), owner computes",
+            "l2": "operand arrays (>= 10 GB each at full size) exceed the 126 MB L2; no flush needed"}
 
 
 def workload_name(o_segs, v_segs, density=1.0):
@@ -80,6 +101,7 @@ class CpuSample:
         self.oracle, self.TERMS = oracle, TERMS
         os.environ["OMP_NUM_THREADS"] = str(threads)
         self.blas = oracle.use_openblas(threads)
+        self.threads = threads
         self.o_segs, self.v_segs = o_segs, v_segs
         # block generator only (no dense assembly at full size)
         self.ref = RefWorkload.__new__(RefWorkload)
@@ -133,6 +155,27 @@ class CpuSample:
                 self.cache[key] = self.ref.block(name, idx)
         return self.cache[key]
 
+    def set_threads(self, n):
+        """Both thread pools of the CPU arm: OpenBLAS (dgemm) and libgomp (the oracle's permute loops)."""
+        import ctypes
+        self.oracle.use_openblas._keep.scipy_openblas_set_num_threads(int(n))
+        try:
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+        except OSError:
+            pass
+        self.threads = int(n)
+
+    def pick_threads(self, cores):
+        """More threads are not always faster here (SCALE_r01: 32 cores slower than 16 -- NUMA / oversubscription of the
+        memory-bound permutes): time one pass at 8 (the reference's own OpenMP cap, src/sip/core/sip.cpp:113), 16 and all
+        cores, keep the fastest.  Returns {threads: seconds}."""
+        seen = {}
+        for n in sorted({min(8, cores), min(16, cores), cores}):
+            self.set_threads(n)
+            seen[n] = self.run_once()[0]
+        self.set_threads(min(seen, key=seen.get))
+        return seen
+
     def run_once(self):
         import numpy as np
         t0 = time.perf_counter()
@@ -158,20 +201,34 @@ def run_reference(args, o_segs, v_segs):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from aces4_b200.sial_workload import iteration_flops
+    budget = args.wall_budget if args.wall_budget is not None else 150.0
     cores = host_cores()
     s = CpuSample(o_segs, v_segs, args.cpu_dests, cores)
-    for _ in range(args.warmup):
+    s.run_once()                       # first touch of every operand block (page faults), not a measurement
+    seen = s.pick_threads(cores)       # counts as the warm-up passes
+    per = seen[s.threads]
+    left = budget - (time.monotonic() - T_START) - 5.0
+    warm = max(0, min(args.warmup - len(seen), int(left / per) - min(args.steps, 3)))
+    for _ in range(warm):
         s.run_once()
-    times = [s.run_once()[0] for _ in range(args.steps)]
+    left = budget - (time.monotonic() - T_START) - 5.0
+    steps = max(1, min(args.steps, max(min(args.steps, 3), int(left / per))))
+    times = [s.run_once()[0] for _ in range(steps)]
     sec = sum(times) / len(times)
     tf = s.flops / sec / 1e12
     sample = (f"{len(s.dests)} of {len(v_segs) ** 2 * len(o_segs) ** 2} destination blocks x all 5 terms "
-              f"({s.flops / 1e9:.0f} GFLOP per step), oracle permute->dgemm->permute + accumulate, {s.blas.split()[0]} dgemm")
-    line = {"metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+              f"({s.flops / 1e9:.0f} GFLOP per step), oracle permute->dgemm->permute + accumulate, {s.blas.split()[0]} dgemm, "
+              f"{s.threads} threads (fastest of " + ", ".join(f"{n}: {t:.1f} s" for n, t in sorted(seen.items())) + ")")
+    cfg = config_of(o_segs, v_segs, args.density, args.gpus)
+    cfg["flops_per_step"] = iteration_flops(o_segs, v_segs)
+    line = {"metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm + len(seen) + 1, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "wall_budget_s": budget, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(o_segs, v_segs), "sample": sample},
-            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": s.threads, "host_cores": cores, "kind": "port",
+                             "sample": sample, "threads_tried_s": {str(k): v for k, v in seen.items()}},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -274,20 +331,47 @@ def main():
             barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, body):
+    def timed(nsteps, body, label=None):
+        """(max-over-ranks ms of the whole region, last result).  One event pair brackets the region; when `label` is
+        given a provisional line goes to stderr after every step, so a run that is killed leaves its progress behind."""
         fence()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         res = None
-        for _ in range(nsteps):
+        for k in range(nsteps):
             res = body()
+            if label and rank == 0:
+                ek = torch.cuda.Event(enable_timing=True)
+                ek.record(stream)
+                ek.synchronize()   # body() ended with a blocking scalar read-back: nothing is pending
+                ms = e0.elapsed_time(ek) / (k + 1)
+                print(json.dumps({"provisional": label, "steps_done": k + 1, "ms_per_step": ms,
+                                  "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s"}), file=sys.stderr, flush=True)
         e1.record(stream)
         e1.synchronize()
         fence()
         return reduce_max(e0.elapsed_time(e1)), res
 
-    for _ in range(args.warmup):
+    # ---- warm-up and the step plan: everything has to fit the wall budget (a full-size step is 36 s at N = 1) ----
+    budget = args.wall_budget if args.wall_budget is not None else 600.0
+    t0 = time.monotonic()
+    energy = w.iterate()          # warm-up 1: also the measure of a step's wall time
+    sip.sync()
+    step_s = reduce_max(time.monotonic() - t0)
+    elapsed = reduce_max(time.monotonic() - T_START)
+    nverify = args.verify_blocks if args.verify_blocks is not None else (64 if world > 1 else 8)
+    reserve = 15.0 + (0.0 if args.no_e2e else 1.1 * step_s) + nverify * 0.05 * min(1.0, step_s)
+    if world == 1 and not args.no_cpu_baseline:
+        reserve += 45.0           # CPU leg: one first-touch pass + two passes at 8 threads and at all cores
+    n_avail = int(max(0.0, budget - elapsed - reserve) / step_s)
+    if (args.warmup - 1) + args.steps <= n_avail:
+        warm, steps = args.warmup, args.steps
+    else:
+        warm = min(args.warmup, 3)                                        # timing rule: W >= 3 whenever it was asked for
+        steps = min(args.steps, max(min(args.steps, 2), n_avail - (warm - 1)))
+    for _ in range(max(0, warm - 1)):
         energy = w.iterate()
+    warm = max(warm, 1)
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local) if rank == 0 else None
@@ -306,7 +390,7 @@ def main():
 
     w.before_launch, w.after_launch = before_launch, after_launch
     launches0 = sip.kernel_launches()
-    ms_total, energy = timed(args.steps, w.iterate)
+    ms_total, energy = timed(steps, w.iterate, label="resident")
     launches = reduce_sum(float(sip.kernel_launches() - launches0))
     clocks = sampler.stop() if sampler else None
     w.before_launch = w.after_launch = None
@@ -314,8 +398,30 @@ def main():
     k_flops = sum(f for f, _, _ in kev)
     k_tf = reduce_sum(k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0) / world   # per-GPU achieved, mean over ranks
     k_share = reduce_max(k_ms) / ms_total if ms_total else None
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = flops / (ms_step * 1e-3) / 1e12
+
+    # ---- parity of the distributed result: the energy functional against the N = 1 value of record, and sampled T2new
+    # blocks (fetched from their owners: peer reads) against the same blocks recomputed on this rank from the replicated
+    # inputs alone.  A wrong put += into peer HBM or a wrong peer get shows up here, in the bench line itself. ----
+    parity = None
+    if nverify > 0:
+        sip.sync()
+        if world > 1:
+            barrier()
+        worst = reduce_max(w.verify_blocks(nverify, offset=rank * 17))
+        parity = {"blocks_checked_per_rank": nverify, "t2new_max_rel_err": worst, "tolerance": 1e-10}
+        if o_segs == O_SEGS and v_segs == V_SEGS and args.density >= 1.0:
+            parity["energy"] = energy
+            parity["energy_n1"] = ENERGY_N1
+            parity["energy_rel_err"] = abs(energy - ENERGY_N1) / abs(ENERGY_N1)
+            parity["ok"] = bool(worst <= 1e-10 and parity["energy_rel_err"] <= 1e-12)
+        else:
+            parity["ok"] = bool(worst <= 1e-10)
+        if world > 1:
+            barrier()
+        if not parity["ok"]:
+            raise SystemExit(f"parity check failed: {json.dumps(parity)}")
 
     # ---- timed region 2: end to end through the public API with HOST buffers (pinned) ----
     e2e = None
@@ -331,10 +437,11 @@ def main():
             w.store_t2new_to_host(h_out)
             return e
 
-        # The kernels are warm from region 1 and the copies go through pinned buffers, so no extra untimed pass; at most
-        # two end-to-end steps are timed (36 s each at full size) so that a large --steps stays bounded.
-        e2e_steps = max(1, min(args.steps, 2))
-        ms_e2e, energy_e2e = timed(e2e_steps, e2e_step)
+        # The kernels are warm from region 1 and the copies go through pinned buffers, so no extra untimed pass; the
+        # number of end-to-end steps is what is left of the wall budget (at least 1, at most what region 1 timed).
+        left = budget - reduce_max(time.monotonic() - T_START) - (reserve - 1.1 * step_s)
+        e2e_steps = max(1, min(steps, int(left / (1.05 * step_s))))
+        ms_e2e, energy_e2e = timed(e2e_steps, e2e_step, label="e2e")
         assert abs(energy_e2e - energy) <= 1e-9 * max(1.0, abs(energy)), (energy_e2e, energy)
         e2e = {"value": flops / (ms_e2e / e2e_steps * 1e-3) / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(reduce_sum(float(nbytes))), "d2h_bytes_per_step": int(reduce_sum(float(nbytes + 8))),
@@ -350,36 +457,51 @@ def main():
         nbytes_blk = 8.0 * int(np.prod(w.T2old.block_shape(peer_blocks[0])))
         tmp_blocks = [api.DeviceBlock(w.T2old.block_shape(b)) for b in peer_blocks]
 
-        def do_get():
+        def do_get():        # one section's worth of gets: recorded, so ONE gather launch over the peer-mapped slabs
+            with api.recording():
+                for b, t in zip(peer_blocks, tmp_blocks):
+                    w.T2old.get(b, out=t)
+
+        def do_put_acc():    # ONE red.global.add.f64 launch into the neighbour's slab
+            with api.recording():
+                for b, t in zip(peer_blocks, tmp_blocks):
+                    w.Xs.put_accumulate(b, t)
+
+        def do_get_eager():
             for b, t in zip(peer_blocks, tmp_blocks):
                 w.T2old.get(b, out=t)
 
-        def do_put_acc():
-            for b, t in zip(peer_blocks, tmp_blocks):
-                w.Xs.put_accumulate(b, t)
-
         do_get()
         ms_get, _ = timed(1, do_get)
+        do_get_eager()
+        ms_get_eager, _ = timed(1, do_get_eager)
         for t in tmp_blocks:
             t.fill(0.0)          # adds zeros: Xs is scratch that the next iteration overwrites anyway
         do_put_acc()
         ms_put, _ = timed(1, do_put_acc)
         vol = len(peer_blocks) * nbytes_blk
         nvlink = {"get_GBps_per_gpu": vol / (ms_get * 1e-3) / 1e9, "put_accumulate_GBps_per_gpu": vol / (ms_put * 1e-3) / 1e9,
+                  "get_per_block_memcpy_GBps_per_gpu": vol / (ms_get_eager * 1e-3) / 1e9,
                   "blocks": len(peer_blocks), "block_bytes": nbytes_blk,
-                  "how": "peer reads (cudaMemcpyAsync from the owner's IPC-mapped slab) / red.global.add.f64 into the owner's "
-                         "slab, all ranks concurrently towards rank+1, max over ranks of the elapsed time"}
+                  "how": "one section of gets / put += towards rank+1 issued inside a recording: one descriptor-driven launch "
+                         "of 16-byte peer loads (get) / red.global.add.f64 into the owner's IPC-mapped slab (put +=); all "
+                         "ranks concurrently, max over ranks of the elapsed time; per_block_memcpy = the same gets as one "
+                         "cudaMemcpyAsync per block"}
         del tmp_blocks
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         s = CpuSample(o_segs, v_segs, args.cpu_dests, cores)
-        s.run_once()
-        sec, _ = s.run_once()
-        cpu = {"value": s.flops / sec / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+        s.run_once()                     # first touch
+        seen = s.pick_threads(cores)
+        sec = seen[s.threads]
+        cpu = {"value": s.flops / sec / 1e12, "unit": "TFLOP/s", "cores": s.threads, "host_cores": cores, "kind": "port",
                "sample": f"{len(s.dests)} destination blocks x all 5 terms ({s.flops / 1e9:.0f} GFLOP, {sec:.1f} s), oracle "
-                         f"permute->OpenBLAS dgemm->permute + accumulate"}
+                         f"permute->OpenBLAS dgemm->permute + accumulate; fastest of the thread counts tried",
+               "threads_tried_TFLOPs": {str(n): s.flops / t / 1e12 for n, t in sorted(seen.items())},
+               "omp8": {"value": s.flops / seen[min(8, cores)] / 1e12, "unit": "TFLOP/s",
+                        "note": "8 threads = the reference's own OpenMP cap (src/sip/core/sip.cpp:113)"}}
 
     # DRAM traffic of the dominant launch (the pp-ladder chain launch, ~76 % of the step) from the committed single-pass
     # ncu capture of this same command at full size; null for development sizes
@@ -393,14 +515,14 @@ def main():
             traffic = traffic_alg = None
 
     if rank == 0:
+        cfg = config_of(o_segs, v_segs, args.density, world)
+        cfg["flops_per_step"] = flops
         line = {
-            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": steps,
+            "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "wall_budget_s": budget,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(o_segs, v_segs, args.density), "flops_per_step": flops,
-                       "parallelism": f"owner-computes over {world} GPU(s), destination blocks block-cyclic",
-                       "l2": "operand arrays (>= 10 GB each) exceed the 126 MB L2; no flush needed",
-                       "energy": energy},
+            "config": cfg, "energy": energy, "parity_vs_n1": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "contract_kernel (FP64 DMMA, mma.sync.m8n8k4.f64)",
                          "achieved": k_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": k_tf / peak_tf if peak_tf else None,
@@ -411,6 +533,7 @@ def main():
                                            "launch, the pp-ladder chain; bytes per launch per GPU)" if traffic else None},
             "cpu_baseline": cpu,
             "nvlink": nvlink,
+            "wall_s": time.monotonic() - T_START,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -27,7 +27,11 @@ def test_reference_arm_prints_one_contract_line():
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["dtype"] == "f64" and d["higher_is_better"] is True
-    assert d["steps"] == 2 and d["warmup"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    # steps / warmup are the ACTUAL counts (a wall budget caps them at full size; the first-touch pass and the thread-count
+    # probes are warm-up passes); what was asked for is reported next to them
+    assert d["steps"] == 2 and d["steps_requested"] == 2 and d["warmup"] >= 1 and d["warmup_requested"] == 1
+    assert d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert set(d["config"]) == {"workload", "flops_per_step", "parallelism", "l2"}    # same keys as the GPU arm's config
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]

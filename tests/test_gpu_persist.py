@@ -149,6 +149,32 @@ def test_mirrored_block_coherence(sip):
     m2.destroy()
 
 
+def test_mirrored_block_inside_a_recording(sip):
+    """sipgpu.h: blocking calls flush an open recording.  A contraction RECORDED into a mirror's device side must be
+    visible to a host access made inside the same recording (the d2h may not overtake the recorded writer), a copy towards
+    the device may not overtake recorded readers of the old contents, and destroying the mirror defers the free."""
+    rng = np.random.default_rng(5)
+    L = np.asfortranarray(rng.uniform(-1, 1, (6, 5)))
+    R = np.asfortranarray(rng.uniform(-1, 1, (5, 7)))
+    dL, dR = sip.DeviceBlock.from_numpy(L), sip.DeviceBlock.from_numpy(R)
+    m = sip.MirroredBlock(np.zeros((6, 7), order="F"))
+    old = sip.MirroredBlock(np.full((6, 7), 3.0, order="F"))
+    snap = sip.DeviceBlock((6, 7))
+    with sip.recording():
+        d = m.on_device(sip.WRITE_ON_DEVICE)
+        sip.contract_labels([1, 3], [6, 7], [1, 2], dL, [2, 3], dR, out=d)          # recorded, not launched yet
+        h = m.on_host(sip.READ_ON_HOST)                                             # must flush, then d2h
+        assert np.max(np.abs(h - L @ R)) <= 1e-13
+        do = old.on_device(sip.READ_ON_DEVICE)
+        snap.scale_and_copy(do, 1.0)                                                # recorded reader of the OLD contents
+        old.on_host(sip.WRITE_ON_HOST)[...] = 9.0
+        do2 = old.on_device(sip.READ_ON_DEVICE)                                     # h2d of the new contents: after the reader
+        assert do2.ptr == do.ptr
+        old.destroy()                                                               # free deferred past the recorded ops
+    assert np.all(snap.to_numpy() == 3.0)
+    m.destroy()
+
+
 def test_put_initialize_increment_scale(sip):
     """the scalar block ops of SialOpsParallel (sial_ops_parallel.cpp:412-528) at the owner, eager and recorded"""
     A = sip.DistArray([[3, 4], [2, 5]])
