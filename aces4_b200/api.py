@@ -102,6 +102,7 @@ def lib():
                                               c_int_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.sipgpu_dgemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_double, C.c_void_p, C.c_int]
+        L.sipgpu_set_tuning.argtypes = [C.c_char_p, C.c_double]
         L.sipgpu_dmma_peak_probe.argtypes = [C.c_int, c_dbl_p]
         L.sipgpu_copy_bw_probe.argtypes = [C.c_size_t, C.c_int, c_dbl_p]
         L._gpu_free.argtypes = [C.c_void_p]
@@ -575,6 +576,11 @@ class recording:
 def dgemm_tn(m, n, k, A, lda, B, ldb, Cblk, ldc, alpha=1.0, beta=0.0):
     _check(lib().sipgpu_dgemm_tn(m, n, k, float(alpha), A.ptr, lda, B.ptr, ldb, float(beta), Cblk.ptr, ldc),
            "sipgpu_dgemm_tn")
+
+
+def set_tuning(key, value):
+    """launch-policy knob (sipgpu.h: sipgpu_set_tuning), e.g. set_tuning("lowint_max_intensity", -1) for the tile kernel only"""
+    _check(lib().sipgpu_set_tuning(key.encode(), float(value)), "sipgpu_set_tuning")
 
 
 def dmma_peak_probe(iters=20000):

@@ -147,6 +147,12 @@ int contract_device_sliced(const int* ptrn, const double* L, int lrank, const in
         return ew_dot_device(L + ol, R + orr, a.s0.K, D + od, beta);
     }
     if (a.s0.M < a.s0.N && a.s0.M <= 64) a.s0 = swap_operands(a.s0);  // the small free dimension goes to the n side
+    if (lowint_eligible(a.s0)) {  // bandwidth-shaped kernel (strided operands and a strided destination included: no split then)
+        std::vector<Pair> pairs(1, a.s0.swapped ? Pair{R + orr, L + ol} : Pair{L + ol, R + orr});
+        std::vector<int> chain = {0, 1};
+        double* Dp = D + od;
+        return lowint_launch(a.s0, 1, pairs, chain, &Dp, alpha, beta, dpar == nullptr);
+    }
     a.s0.tile = contract_pick_tile(a.s0.M, a.s0.N);
     if (contract_tile_count(a.s0.M, a.s0.N, a.s0.tile) < ctx().num_sms) a.s0.tile = kSmallTile;  // spread a small block
     // one small destination with a long contracted range: split-K through the work-list path (dense D only: the
@@ -221,6 +227,49 @@ int contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, co
 // variant.  shapes[pshape[i]] is the Shape of problem i (operand roles already swapped where Shape::swapped).
 int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& pshape, const int* chain_start,
                  const double* const* L, const double* const* R, double* const* D, double alpha, double beta) {
+    // ---- low arithmetic intensity shapes (rank-2 results of rank-4 blocks, one segment-sized free + contracted index,
+    // matrix-vector shapes, tiny matrices, dot products) go to the bandwidth-shaped kernel, one launch per shape ----
+    {
+        std::vector<char> low(shapes.size(), 0);
+        bool any = false, all = true;
+        for (size_t k = 0; k < shapes.size(); ++k) { low[k] = lowint_eligible(shapes[k]) ? 1 : 0; any = any || low[k]; }
+        if (any) {
+            for (int i = 0; i < n; ++i) all = all && low[pshape[i]];
+            std::vector<int> rest_idx;
+            for (size_t k = 0; k < shapes.size(); ++k) {
+                if (!low[k]) continue;
+                std::vector<Pair> pairs;
+                std::vector<int> chain(1, 0);
+                std::vector<double*> dd;
+                for (int i = 0; i < n; ++i) {
+                    if (pshape[i] != (int)k) continue;
+                    const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+                    if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+                    for (int c = c0; c < c1; ++c) {
+                        if (!L[c] || !R[c]) return SIPGPU_E_ARG;
+                        pairs.push_back(shapes[k].swapped ? Pair{R[c], L[c]} : Pair{L[c], R[c]});
+                    }
+                    chain.push_back((int)pairs.size());
+                    dd.push_back(D[i]);
+                }
+                if (!dd.empty()) SIP_TRY(lowint_launch(shapes[k], (int)dd.size(), pairs, chain, dd.data(), alpha, beta, true));
+            }
+            if (all) return SIPGPU_OK;
+            // the remaining problems run below: compact the work-list
+            std::vector<int> pshape2, chain2(1, 0);
+            std::vector<const double*> L2, R2;
+            std::vector<double*> D2;
+            for (int i = 0; i < n; ++i) {
+                if (low[pshape[i]]) continue;
+                const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
+                for (int c = c0; c < c1; ++c) { L2.push_back(L[c]); R2.push_back(R[c]); }
+                chain2.push_back((int)L2.size());
+                D2.push_back(D[i]);
+                pshape2.push_back(pshape[i]);
+            }
+            return run_worklist((int)D2.size(), shapes, pshape2, chain2.data(), L2.data(), R2.data(), D2.data(), alpha, beta);
+        }
+    }
     long long total = 0;
     for (int i = 0; i < n; ++i) total += contract_tile_count(shapes[pshape[i]].M, shapes[pshape[i]].N, shapes[pshape[i]].tile);
     if (total < ctx().num_sms) {  // a work-list that cannot fill the SMs with large tiles runs on 64x64 tiles (two CTAs per SM)
@@ -919,6 +968,12 @@ int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long 
     return sipgpu::permute_plan_debug(rank, ext, transp, meta, rtab, wtab, cap);
 }
 
+int sipgpu_set_tuning(const char* key, double value) {
+    if (!key) return SIPGPU_E_ARG;
+    if (!strcmp(key, "lowint_max_intensity")) { lowint_set_max_intensity(value); return SIPGPU_OK; }
+    set_error("sipgpu_set_tuning: unknown key '%s'", key);
+    return SIPGPU_E_ARG;
+}
 int sipgpu_dmma_peak_probe(int iters, double* tflops_out) {
     SIP_TRY(ensure_init());
     return dmma_probe(iters, tflops_out);

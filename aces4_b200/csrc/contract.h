@@ -1,5 +1,7 @@
 // contract.h -- launch interface of the fused DMMA contraction kernel (contract.cu).
 #pragma once
+#include <vector>
+
 #include "plan.h"
 
 namespace sipgpu {
@@ -36,5 +38,13 @@ constexpr int kSyncEvery = 32;   // ring stages (of 16 contracted elements) betw
 constexpr int kSyncWindow = 2;   // allowed lead, in lockstep points
 constexpr int kSmallTile = 2;  // 64x64, for launches that cannot fill the SMs with large tiles
 int dmma_probe(int iters, double* tflops);
+
+// lowint.cu: the bandwidth-shaped kernel for low arithmetic intensity contractions (N <= 64 after the launcher's operand
+// swap, flops per algorithmic byte below the roofline ridge)
+bool lowint_eligible(const Shape& s);
+int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const std::vector<int>& chain, double* const* D,
+                  double alpha, double beta, bool dense_d);
+void lowint_cache_clear();
+void lowint_set_max_intensity(double flops_per_byte);  // negative: the kernel is never chosen
 
 }  // namespace sipgpu

@@ -183,6 +183,7 @@ int pool_free(void* p) {
 }
 
 void permute_cache_clear();
+void lowint_cache_clear();
 
 static int finalize_all() {
     Ctx& c = g_ctx;
@@ -190,6 +191,7 @@ static int finalize_all() {
     cudaStreamSynchronize(c.stream);
     cudaStreamSynchronize(c.copy_stream);
     permute_cache_clear();
+    lowint_cache_clear();
     for (auto& a : g_pool.arenas) cudaFree(a.base);
     g_pool = Pool();
     cudaFreeHost(c.h_scratch);

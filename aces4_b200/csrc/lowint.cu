@@ -440,8 +440,8 @@ int launch_low(const LowArgs& a, int grid, size_t smem) {
 
 void lowint_cache_clear() { table_cache().clear(); }
 
-static double lowint_max_intensity() {
-    static const double v = [] {
+static double& lowint_max_intensity() {
+    static double v = [] {
         const char* on = getenv("SIPGPU_LOWINT");
         if (on && atoi(on) == 0) return -1.0;
         const char* e = getenv("SIPGPU_LOWINT_MAXI");
@@ -449,6 +449,7 @@ static double lowint_max_intensity() {
     }();
     return v;
 }
+void lowint_set_max_intensity(double v) { lowint_max_intensity() = v; }
 
 // Is this (launcher-oriented: the small free dimension already on the n side) contraction one for the bandwidth-shaped
 // kernel?  N fits one tile and the flops per algorithmic byte stay below the ridge of the roofline
@@ -542,7 +543,7 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
     auto even_strides = [](int nd, const int* st) { for (int i = 1; i < nd; ++i) if (st[i] & 1) return false; return true; };
     bool ka_even = true, kb_even = true;
     for (int i = 0; i < s.nk; ++i) { ka_even = ka_even && !(s.ksL[i] & 1); kb_even = kb_even && !(s.ksR[i] & 1); }
-    a.a_vec = !a.a_kfast && s.nm >= 1 && s.msL[0] == 1 && s.mext[0] % 2 == 0 && even_strides(s.nm, s.msL) && ka_even && (s.M >= kLBM ? true : true);
+    a.a_vec = !a.a_kfast && s.nm >= 1 && s.msL[0] == 1 && s.mext[0] % 2 == 0 && even_strides(s.nm, s.msL) && ka_even;
     a.b_vec = !a.b_kfast && s.nn >= 1 && s.nsR[0] == 1 && s.next[0] % 2 == 0 && even_strides(s.nn, s.nsR) && kb_even;
     if (a.a_vec || a.b_vec)
         for (const Pair& p : pairs) {
@@ -553,14 +554,15 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
     a.p0 = probs[0]; a.pair0 = pairs[0];
 
     const size_t smem = (size_t)kLStages * KC * perk;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (smem + 1024)));
+    // resident CTAs per SM: 3 by registers (~155 x 128 threads), fewer when the ring is large
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / (smem + 1024)));
     const long long slots = (long long)c.num_sms * per_sm;
     const long long nwork0 = (long long)n * t.ntile_m;
     long long ns = 1;
     if (nwork0 < slots && dense_d) {
-        // every slice streams at least ~128 KB of operands
+        // every slice streams at least ~256 KB of operands (a split costs a pre-scale launch and atomics)
         const long long chunk_bytes = (long long)KC * 8 * (std::min(s.M, kLBM) + s.N);
-        const long long min_chunks = std::max<long long>(1, (128 * 1024) / std::max<long long>(1, chunk_bytes));
+        const long long min_chunks = std::max<long long>(1, (256 * 1024) / std::max<long long>(1, chunk_bytes));
         const long long avg_chunks = std::max<long long>(1, total_pairs * a.cpp / n);
         ns = std::min<long long>((2 * slots + nwork0 - 1) / nwork0, std::max<long long>(1, avg_chunks / min_chunks));
     }

@@ -207,6 +207,11 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
 int sipgpu_dmma_peak_probe(int iters, double* tflops_out);
 /* device copy bandwidth probe (GB/s, read+write) over a buffer of `bytes` */
 int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out);
+/* Launch-policy knobs for A/B measurements and for tests that must reach a particular kernel (defaults are the product
+ * path).  "lowint_max_intensity": contractions with N <= 64 and at most this many flops per algorithmic byte run on the
+ * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).  Returns
+ * SIPGPU_E_ARG for an unknown key.  Host-only. */
+int sipgpu_set_tuning(const char* key, double value);
 
 /* host-only views of the planner (no device needed; used by the CPU tests of the host logic) */
 int sipgpu_debug_contract_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank,

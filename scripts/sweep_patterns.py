@@ -73,7 +73,7 @@ for d, l, r, kinds, where in sial_patterns():
     del Ls, Rs, Ds, bc
 out = {"dmma_peak_tflops": peak, "copy_gbs": bw, "extents": EXT, "patterns": rows}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sweep_patterns.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("SWEEP_OUT", "sweep_patterns.json")), "w"), indent=1)
 for cls in sorted(set(x["ranks"] for x in rows)):
     sel = [x for x in rows if x["ranks"] == cls]
     f = [x["roofline_frac"] for x in sel]

@@ -231,7 +231,16 @@ def check_contraction(sip, oracle, rng, dlab, llab, rlab, ext, alpha=1.0, beta=0
     return got
 
 
-def test_random_patterns(sip, oracle):
+@pytest.fixture(params=["lowint", "tiles"])
+def route(request, sip):
+    """small test blocks are all low-intensity: run them through the bandwidth-shaped kernel (the default route) AND forced
+    through the 128-wide tile kernel, so that both stay covered"""
+    sip.set_tuning("lowint_max_intensity", 7.0 if request.param == "lowint" else -1.0)
+    yield request.param
+    sip.set_tuning("lowint_max_intensity", 7.0)
+
+
+def test_random_patterns(sip, oracle, route):
     pyrng = random.Random(1234)
     rng = np.random.default_rng(1234)
     for trial in range(150):
@@ -239,7 +248,7 @@ def test_random_patterns(sip, oracle):
         check_contraction(sip, oracle, rng, dlab, llab, rlab, ext)
 
 
-def test_random_patterns_alpha_beta(sip, oracle):
+def test_random_patterns_alpha_beta(sip, oracle, route):
     pyrng = random.Random(99)
     rng = np.random.default_rng(99)
     for trial in range(40):
@@ -264,7 +273,7 @@ SIAL_PATTERNS = [
 
 
 @pytest.mark.parametrize("o,v", [(4, 6), (5, 9), (8, 16)])
-def test_sial_cc_patterns(sip, oracle, o, v):
+def test_sial_cc_patterns(sip, oracle, o, v, route):
     rng = np.random.default_rng(o * 100 + v)
     for dl, ll, rl in SIAL_PATTERNS:
         labs = sorted(set(dl + ll + rl))
@@ -274,7 +283,7 @@ def test_sial_cc_patterns(sip, oracle, o, v):
 
 
 @pytest.mark.parametrize("sizes", [dict(o=4, v=6, p=5, n=7, x=2, s=2), dict(o=20, v=24, p=9, n=13, x=1, s=3)])
-def test_all_sial_patterns_golden(sip, oracle, sizes):
+def test_all_sial_patterns_golden(sip, oracle, sizes, route):
     """All 170 distinct contraction patterns of the reference's CC / (T) / EOM SIAL programs (tests/golden/
     sial_contraction_patterns.txt) through the fused kernel, against the oracle, at 1e-10."""
     from conftest import sial_patterns
@@ -307,7 +316,7 @@ def test_sweep_rank4_full_cross_product_sample(sip, oracle, s):
         oracle.use_naive_gemm()
 
 
-def test_ragged_and_eom_shapes(sip, oracle):
+def test_ragged_and_eom_shapes(sip, oracle, route):
     rng = np.random.default_rng(5)
     # ragged extents 13,30,50,64 (config 4) and EOM-style rank-5 blocks with a leading extent-1 index (config 3)
     check_contraction(sip, oracle, rng, [1, 2, 3, 4], [1, 5, 2, 6], [6, 3, 5, 4], {1: 13, 2: 30, 3: 50, 4: 7, 5: 9, 6: 11})
@@ -401,9 +410,17 @@ def test_batched_heterogeneous(sip, oracle):
         Rs.append(sip.DeviceBlock.from_numpy(R))
         Ds.append(sip.DeviceBlock([e[x] for x in dlab]))
         refs.append(ref)
+    sip.set_tuning("lowint_max_intensity", -1.0)   # the tile kernel: heterogeneous extents share a launch
     before = sip.kernel_launches()
     sip.contract_batched(ptrn, Ls, Rs, Ds)
     assert sip.kernel_launches() - before <= 4  # one launch per kernel variant, not per block
+    sip.set_tuning("lowint_max_intensity", 7.0)    # the bandwidth-shaped kernel: one launch per distinct shape
+    Ds2 = [sip.DeviceBlock(d.shape) for d in Ds]
+    before = sip.kernel_launches()
+    sip.contract_batched(ptrn, Ls, Rs, Ds2)
+    assert sip.kernel_launches() - before <= len({(l.shape, r.shape) for l, r in zip(Ls, Rs)})
+    for d, ref in zip(Ds2, refs):
+        assert relerr(d.to_numpy(), ref) <= TOL
     for d, ref in zip(Ds, refs):
         assert relerr(d.to_numpy(), ref) <= TOL
     # fused accumulate over the same work-list: D = D + L*R
@@ -412,7 +429,7 @@ def test_batched_heterogeneous(sip, oracle):
         assert relerr(d.to_numpy(), 2.0 * ref) <= TOL
 
 
-def test_chained_block_sparse(sip, oracle):
+def test_chained_block_sparse(sip, oracle, route):
     # hh-ladder body (rlccd_rhf.sialx:342-355): T2new[a,i,b,j] += T2old[a,i1,b,j1] * V[i,i1,j,j1] summed over the
     # (i1,j1) SEGMENTS inside one launch; ragged segment extents per destination
     rng = np.random.default_rng(31)
@@ -562,7 +579,7 @@ def test_full_size_properties(sip):
 
 
 @pytest.mark.parametrize("case", ["single_windows", "single_ragged", "chain_pairs", "chain_windows"])
-def test_split_k_partial_sums(sip, oracle, case):
+def test_split_k_partial_sums(sip, oracle, case, route):
     """few small destinations with a long contracted range (D[a,b] = L[a,i,c,j]*R[b,i,c,j], the (2,4,4) SIAL patterns):
     the launcher cuts the chain / the k windows into partial problems that meet in D through red.add (abi.cu
     run_worklist); alpha and beta must come out exactly as in the unsplit op."""
