@@ -100,6 +100,10 @@ def lib():
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.sipgpu_contract_chained.argtypes = [C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
                                               c_int_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.sipgpu_plan_contract_chained.argtypes = [C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
+                                                   c_int_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.sipgpu_plan_launch.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.sipgpu_plan_destroy.argtypes = [C.c_void_p]
         L.sipgpu_dgemm_tn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_double, C.c_void_p, C.c_int]
         L.sipgpu_set_tuning.argtypes = [C.c_char_p, C.c_double]
@@ -506,8 +510,22 @@ class BatchedContraction:
         self.rext = np.ascontiguousarray(rshapes, dtype=np.int32)
         self.dext = np.ascontiguousarray(dshapes, dtype=np.int32)
         self.L, self.R, self.D = _ptr_array(lptrs), _ptr_array(rptrs), _ptr_array(dptrs)
+        self.plan = None
 
-    def launch(self, alpha=1.0, beta=0.0):
+    def launch(self, alpha=1.0, beta=0.0, prepared=True):
+        """prepared (default): the work-list is marshalled once into a resident plan (sipgpu_plan_*) and every later launch
+        replays it without host-side work; prepared=False goes through sipgpu_contract_chained / _batched every time."""
+        if prepared:
+            if self.plan is None:
+                h = C.c_void_p(0)
+                _check(lib().sipgpu_plan_contract_chained(self.n, self.ptrn, self.lrank, self.rrank, self.drank,
+                                                          self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
+                                                          self.dext.ctypes.data_as(c_int_p),
+                                                          self.chain.ctypes.data_as(c_int_p) if self.chain is not None else None,
+                                                          self.L, self.R, self.D, C.byref(h)), "sipgpu_plan_contract_chained")
+                self.plan = h
+            _check(lib().sipgpu_plan_launch(self.plan, float(alpha), float(beta)), "sipgpu_plan_launch")
+            return
         if self.chain is not None:
             _check(lib().sipgpu_contract_chained(self.n, self.ptrn, self.lrank, self.rrank, self.drank,
                                                  self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
@@ -519,6 +537,17 @@ class BatchedContraction:
                                              self.lext.ctypes.data_as(c_int_p), self.rext.ctypes.data_as(c_int_p),
                                              self.dext.ctypes.data_as(c_int_p), self.L, self.R, self.D, float(alpha),
                                              float(beta)), "sipgpu_contract_batched")
+
+    def destroy(self):
+        if self.plan is not None:
+            lib().sipgpu_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 # ----------------------------------------------------------------------------------------------------

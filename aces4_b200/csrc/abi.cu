@@ -232,9 +232,9 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
     {
         std::vector<char> low(shapes.size(), 0);
         bool any = false, all = true;
-        for (size_t k = 0; k < shapes.size(); ++k) { low[k] = lowint_eligible(shapes[k]) ? 1 : 0; any = any || low[k]; }
+        for (size_t k = 0; k < shapes.size(); ++k) low[k] = lowint_eligible(shapes[k]) ? 1 : 0;
+        for (int i = 0; i < n; ++i) { any = any || low[pshape[i]]; all = all && low[pshape[i]]; }  // over PROBLEMS, not shapes
         if (any) {
-            for (int i = 0; i < n; ++i) all = all && low[pshape[i]];
             std::vector<int> rest_idx;
             for (size_t k = 0; k < shapes.size(); ++k) {
                 if (!low[k]) continue;
@@ -285,6 +285,7 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
         if (!is_dot(s)) continue;
         const int c0 = chain_start ? chain_start[i] : i, c1 = chain_start ? chain_start[i + 1] : i + 1;
         if (!D[i] || c1 <= c0) return SIPGPU_E_ARG;
+        if (capture()) { capture()->failed = true; return SIPGPU_E_STATE; }  // not a capturable launch site
         for (int c = c0; c < c1; ++c) {
             if (!L[c] || !R[c]) return SIPGPU_E_ARG;
             SIP_TRY(ew_dot_device(L[c], R[c], s.K, D[i], c == c0 ? beta : 1.0));
@@ -320,7 +321,12 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
             cnt.push_back((long long)s.M * s.N);
         }
         // dense destinations only (a sliced destination never comes here: see contract_device_sliced)
-        if (beta != 1.0) SIP_TRY(ew_scale_many((int)dd.size(), dd.data(), cnt.data(), beta));
+        if (beta != 1.0) {
+            if (Capture* cap = capture())
+                cap->steps.push_back([dd, cnt, beta]() mutable { return ew_scale_many((int)dd.size(), dd.data(), cnt.data(), beta); });
+            else
+                SIP_TRY(ew_scale_many((int)dd.size(), dd.data(), cnt.data(), beta));
+        }
     }
     // kernel variant of every problem: (a_kc, b_kc, 16-byte loads, tile)
     std::vector<int> pvariant(n, -1);
@@ -378,12 +384,12 @@ int run_worklist(int n, std::vector<Shape>& shapes, const std::vector<int>& psha
                      b_shapes = sizeof(Shape) * shapes.size(), b_prefix = sizeof(int) * prefix.size();
         const size_t off_pairs = up(b_probs), off_shapes = off_pairs + up(b_pairs), off_prefix = off_shapes + up(b_shapes);
         void *h, *d;
-        SIP_TRY(scratch_reserve(off_prefix + b_prefix, &h, &d));
+        SIP_TRY(desc_alloc(off_prefix + b_prefix, &h, &d));
         memcpy(h, probs.data(), b_probs);
         memcpy((char*)h + off_pairs, pairs.data(), b_pairs);
         memcpy((char*)h + off_shapes, shapes.data(), b_shapes);
         memcpy((char*)h + off_prefix, prefix.data(), b_prefix);
-        SIP_CUDA(cudaMemcpyAsync(d, h, off_prefix + b_prefix, cudaMemcpyHostToDevice, ctx().stream));
+        SIP_TRY(desc_commit(h, d, off_prefix + b_prefix));
         ContractArgs a;
         memset(&a, 0, sizeof(a));
         a.probs = (const Problem*)d;
@@ -838,6 +844,88 @@ int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int dr
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
 }
 
+// ---- prepared work-lists: marshal once, launch many times ----
+// A CC iteration launches the same work-list every time (same blocks, same chains); sipgpu_contract_chained rebuilds
+// shapes, problems, tile prefix sums and uploads them on every call -- for thousands of small blocks that host work is
+// longer than the kernel.  A plan keeps the descriptors resident and replays the launches.
+}  // extern "C"
+struct sipgpu_plan {
+    int n = 0, lrank = 0, rrank = 0, drank = 0;
+    std::vector<int> ptrn, lext, rext, dext, chain;
+    std::vector<const double*> L, R;
+    std::vector<double*> D;
+    struct Built {
+        double alpha, beta;
+        sipgpu::Capture cap;
+    };
+    std::vector<Built*> built;  // one captured launch sequence per (alpha, beta) used so far
+    ~sipgpu_plan() {
+        for (Built* b : built) {
+            for (void* p : b->cap.device) sipgpu::pool_free(p);
+            delete b;
+        }
+    }
+};
+extern "C" {
+int sipgpu_plan_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                                 const int* dext, const int* chain_start, const double* const* L, const double* const* R,
+                                 double* const* D, sipgpu_plan** out) {
+    if (!out || n < 0 || !ptrn || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank ||
+        (n && (!lext || !rext || !dext || !L || !R || !D)))
+        return SIPGPU_E_ARG;
+    sipgpu_plan* p = new sipgpu_plan();
+    p->n = n; p->lrank = lrank; p->rrank = rrank; p->drank = drank;
+    p->ptrn.assign(ptrn, ptrn + lrank + rrank);
+    p->lext.assign(lext, lext + (size_t)n * lrank);
+    p->rext.assign(rext, rext + (size_t)n * rrank);
+    p->dext.assign(dext, dext + (size_t)n * drank);
+    const int npairs = chain_start ? chain_start[n] : n;
+    if (chain_start) p->chain.assign(chain_start, chain_start + n + 1);
+    p->L.assign(L, L + npairs);
+    p->R.assign(R, R + npairs);
+    p->D.assign(D, D + n);
+    *out = p;
+    return SIPGPU_OK;
+}
+int sipgpu_plan_launch(sipgpu_plan* p, double alpha, double beta) {
+    if (!p) return SIPGPU_E_ARG;
+    SIP_TRY(wl_flush());  // runs after whatever was recorded before it, like sipgpu_contract_chained
+    if (p->n == 0) return SIPGPU_OK;
+    SIP_TRY(ensure_init());
+    sipgpu_plan::Built* b = nullptr;
+    for (sipgpu_plan::Built* x : p->built)
+        if (x->alpha == alpha && x->beta == beta) b = x;
+    if (!b) {
+        b = new sipgpu_plan::Built{alpha, beta, {}};
+        capture() = &b->cap;
+        const int rc = contract_chained(p->n, p->ptrn.data(), p->lrank, p->rrank, p->drank, p->lext.data(), p->rext.data(),
+                                        p->dext.data(), p->chain.empty() ? nullptr : p->chain.data(), p->L.data(), p->R.data(),
+                                        p->D.data(), alpha, beta);
+        capture() = nullptr;
+        if (rc != SIPGPU_OK && !b->cap.failed) {
+            for (void* q : b->cap.device) pool_free(q);
+            delete b;
+            return rc == 1 ? SIPGPU_E_PATTERN : rc;
+        }
+        if (b->cap.failed) b->cap.steps.clear();
+        p->built.push_back(b);
+    }
+    if (b->cap.failed) {  // a launch site that cannot be replayed: the eager path, every time
+        const int rc = contract_chained(p->n, p->ptrn.data(), p->lrank, p->rrank, p->drank, p->lext.data(), p->rext.data(),
+                                        p->dext.data(), p->chain.empty() ? nullptr : p->chain.data(), p->L.data(), p->R.data(),
+                                        p->D.data(), alpha, beta);
+        return rc == 1 ? SIPGPU_E_PATTERN : rc;
+    }
+    for (auto& step : b->cap.steps) SIP_TRY(step());
+    return SIPGPU_OK;
+}
+int sipgpu_plan_destroy(sipgpu_plan* p) {
+    if (!p) return SIPGPU_OK;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);  // descriptors may still be read by queued launches
+    delete p;
+    return SIPGPU_OK;
+}
+
 // ---- boundary 3b: elementwise CC super-instructions (superinstr.cu), reference calling convention ----
 int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) { return si_set_int_array(name, n, values); }
 #define SI_RETURN(expr)                   \
@@ -971,6 +1059,7 @@ int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long 
 int sipgpu_set_tuning(const char* key, double value) {
     if (!key) return SIPGPU_E_ARG;
     if (!strcmp(key, "lowint_max_intensity")) { lowint_set_max_intensity(value); return SIPGPU_OK; }
+    if (!strcmp(key, "lowint_scope")) { lowint_set_scope((int)value); return SIPGPU_OK; }
     set_error("sipgpu_set_tuning: unknown key '%s'", key);
     return SIPGPU_E_ARG;
 }

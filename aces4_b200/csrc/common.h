@@ -1,6 +1,8 @@
 // common.h -- shared state, error handling and launch bookkeeping of libsipgpu (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <functional>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -50,6 +52,22 @@ int ensure_init();  // lazily initialises on device 0 (or SIPGPU_DEVICE / LOCAL_
 int scratch_reserve(size_t bytes, void** h, void** d);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// ---- prepared launches (sipgpu_plan_*): while a Capture is open, descriptor uploads go to device memory the capture owns
+// (not the ring, whose slots are recycled) and the kernel launch sites push a closure instead of launching; replaying the
+// closures re-issues exactly the same launches with no host-side marshalling.
+struct Capture {
+    std::vector<std::function<int()>> steps;
+    std::vector<void*> device;  // pool blocks holding descriptors, freed with the capture
+    bool failed = false;        // a launch site that cannot be captured was reached: the plan falls back to the eager path
+};
+Capture*& capture();
+// descriptor memory of one launch: ring slot (eager) or capture-owned (capturing); commit = the host->device copy
+int desc_alloc(size_t bytes, void** h, void** d);
+int desc_commit(void* h, void* d, size_t bytes);
+
+// bumped by every device allocation made OUTSIDE the pool (distributed-array slabs): cached free-memory figures are stale then
+long long& mem_epoch();
 
 // device pool (pool.cu)
 double* pool_alloc(size_t bytes);

@@ -513,7 +513,7 @@ contract_kernel(const __grid_constant__ ContractArgs args) {
 }
 
 template <class C>
-int launch_cfg(const ContractArgs& a, int max_ctas) {
+int launch_cfg_now(const ContractArgs& a, int max_ctas) {
     static bool attr_set = false;
     if (!attr_set) {
         SIP_CUDA(cudaFuncSetAttribute(contract_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -539,6 +539,14 @@ int launch_cfg(const ContractArgs& a, int max_ctas) {
     SIP_CUDA(cudaGetLastError());
     count_launch();
     return SIPGPU_OK;
+}
+template <class C>
+int launch_cfg(const ContractArgs& a, int max_ctas) {
+    if (Capture* cap = capture()) {  // prepared launch: replayed by sipgpu_plan_launch
+        cap->steps.push_back([a, max_ctas] { return launch_cfg_now<C>(a, max_ctas); });
+        return SIPGPU_OK;
+    }
+    return launch_cfg_now<C>(a, max_ctas);
 }
 
 }  // namespace

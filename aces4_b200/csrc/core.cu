@@ -141,6 +141,28 @@ int scratch_reserve(size_t bytes, void** h, void** d) {
     return SIPGPU_OK;
 }
 
+Capture*& capture() {
+    static Capture* c = nullptr;
+    return c;
+}
+int desc_alloc(size_t bytes, void** h, void** d) {
+    Capture* cap = capture();
+    if (!cap) return scratch_reserve(bytes, h, d);
+    *h = malloc(bytes ? bytes : 1);
+    *d = pool_alloc(bytes ? bytes : 1);
+    if (!*h || !*d) { free(*h); return SIPGPU_E_NOMEM; }
+    cap->device.push_back(*d);
+    return SIPGPU_OK;
+}
+int desc_commit(void* h, void* d, size_t bytes) {
+    SIP_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    if (capture()) {  // pageable staging: the copy has left the buffer when the call returns
+        SIP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        free(h);
+    }
+    return SIPGPU_OK;
+}
+
 double* pool_alloc(size_t bytes) {
     if (ensure_init() != SIPGPU_OK) return nullptr;
     const size_t sz = round_up(bytes ? bytes : 1);
@@ -246,6 +268,9 @@ double* sipgpu_block_alloc(long long n, int zero) {
     return p;
 }
 int sipgpu_block_free(double* p) { return wl_active() ? wl_free(p) : pool_free(p); }
+}  // extern C (reopened below)
+namespace sipgpu { long long& mem_epoch() { static long long e = 0; return e; } }
+extern "C" {
 int sipgpu_pool_stats(size_t* reserved, size_t* in_use, size_t* n_live) {
     if (reserved) *reserved = g_pool.reserved;
     if (in_use) *in_use = g_pool.in_use;

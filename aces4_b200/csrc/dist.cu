@@ -109,6 +109,7 @@ int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_ra
         return SIPGPU_E_NOMEM;
     }
     a->base[my_rank] = (double*)p;
+    ++mem_epoch();
     SIP_CUDA(cudaMemsetAsync(p, 0, bytes, ctx().stream));  // new server blocks are zero (disk_backed_block_map.cpp:150-183)
     // With peers the zero fill must have landed before the slab can be exported: a peer's first put / put += may arrive
     // while this rank's stream is still busy with earlier work and would otherwise be wiped by the late memset (the
@@ -124,7 +125,7 @@ int sipgpu_array_destroy(sipgpu_array* a) {
     for (int r = 0; r < a->world; ++r) {
         if (!a->base[r]) continue;
         if (a->opened[r]) cudaIpcCloseMemHandle(a->base[r]);
-        else if (r == a->my_rank) cudaFree(a->base[r]);
+        else if (r == a->my_rank) { cudaFree(a->base[r]); ++mem_epoch(); }
     }
     delete a;
     return SIPGPU_OK;

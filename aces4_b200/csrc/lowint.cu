@@ -26,6 +26,7 @@
 //   * math on the FP64 tensor pipe (DMMA m8n8k4) from 8x8 fragments -- M and N are padded to 8, not to a tile of 64/128,
 //     and the four warps split the fragment grid 2x2, 1x4 or 4x1, whichever balances (50 x 50 -> 7 x 7 fragments -> 1x4);
 //   * M = N = 1 (dot products) skip the tensor pipe: dotk_kernel streams both operands with grid-wide slices.
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -37,7 +38,7 @@ namespace sipgpu {
 namespace {
 
 constexpr int kLT = 128;      // threads per CTA (4 warps)
-constexpr int kLStages = 3;   // cp.async ring depth
+constexpr int kLStages = 4;   // cp.async ring depth
 constexpr int kLBM = 64;      // rows of an m tile (the whole M when M <= 64)
 
 struct LowProb {
@@ -53,13 +54,18 @@ struct LowArgs {
     const int2* ktab;  // [K]             {offset in L, offset in R}; nullptr: k * ksL1, k * ksR1
     int nprob, M, N, K;
     int ksL1, ksR1;
-    int BM, Np;      // rows of an m tile / N, both rounded up to 8
-    int lda, ldb;    // leading dimensions of the staged chunks ([k][m], [k][n]); = 4 (mod 8): conflict-free fragment loads
+    int BM;          // table rows per m tile (rows of a full tile rounded up to 8)
+    // staged chunk of an operand: element (k, x) at k * sk + x * sx.  An operand whose contiguous direction is a free
+    // index is laid out [k][x] (sx = 1, sk = ld), one whose contiguous direction is contracted [x][k] (sk = 1, sx = ld):
+    // consecutive lanes of a cp.async instruction then write consecutive shared-memory words, and with ld = 4 (mod 8)
+    // doubles the DMMA fragment loads are conflict-free in both layouts
+    int a_sk, a_sx, b_sk, b_sx;
+    int a_elems, stage_elems;
     int KC;          // contracted elements per chunk, multiple of 4
     int cpp;         // chunks per operand pair = ceil(K / KC)
     int ntile_m, nslice;
-    int a_kfast, b_kfast;  // the operand's contiguous direction is contracted: lanes walk k (else m / n)
-    int a_vec, b_vec;      // m-/n-contiguous operand fetched as 16-byte pairs
+    int a_kfast, b_kfast;  // lanes walk k (else m / n)
+    int a_vec, b_vec;      // 16-byte items along the walking direction
     int atomic;
     double alpha, beta;
     LowProb p0;
@@ -81,9 +87,10 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// position of a CTA in its sequence of chunks: work item w, chunks [c, c_end) of it still to go
+// position of a CTA in its sequence of chunks: work item w, chunks [c, c_end) of it still to go; (pair, kc) = c split
+// into operand pair and chunk inside the pair, kept incrementally (no division per chunk)
 struct Cursor {
-    int w, c, c_end, tile, pair_begin;
+    int w, c, c_end, tile, pair, kc;
     double* D;
 };
 __device__ __forceinline__ void cursor_load(Cursor& q, const LowArgs& a, int w, int nwork) {
@@ -103,105 +110,118 @@ __device__ __forceinline__ void cursor_load(Cursor& q, const LowArgs& a, int w, 
         const long long T = (long long)pr.pair_len * a.cpp;
         q.c = (int)(s * T / a.nslice);
         q.c_end = (int)((s + 1) * T / a.nslice);
-        q.pair_begin = pr.pair_begin;
+        const int pr0 = q.c / a.cpp;
+        q.kc = q.c - pr0 * a.cpp;
+        q.pair = pr.pair_begin + pr0;
         q.D = pr.D;
         if (q.c < q.c_end) return;
     }
 }
+__device__ __forceinline__ void cursor_next_chunk(Cursor& q, const LowArgs& a) {
+    ++q.c;
+    if (++q.kc == a.cpp) { q.kc = 0; ++q.pair; }
+}
+
+// how the 128 threads of a CTA cover one operand chunk: the walking direction (k or x) across `lanes` consecutive
+// threads, the other direction across the 128 / lanes groups; fixed for the whole kernel
+struct LaneMap {
+    int f, s0, lanes, step;
+};
+__device__ __forceinline__ LaneMap lane_map(int walk_extent, bool vec, int tid) {
+    const int items = vec ? (walk_extent + 1) >> 1 : walk_extent;
+    int sh = 2;
+    while ((1 << sh) < items && sh < 7) ++sh;
+    LaneMap m;
+    m.lanes = 1 << sh;
+    m.f = (tid & (m.lanes - 1)) * (vec ? 2 : 1);
+    m.s0 = tid >> sh;
+    m.step = kLT >> sh;
+    return m;
+}
 
 // One operand chunk global -> shared: element (k, x) of the chunk (x = row of the m tile / column n) goes to
-// dst[k * ld + x].  rows = x extent that exists (others are never read into a stored result), kcnt = contracted elements
-// that exist; the k tail up to the next multiple of 4 is zero-filled (a DMMA k-step reads 4).
-__device__ __forceinline__ void issue_operand(double* dst, int ld, const double* __restrict__ base, const int2* __restrict__ xtab,
-                                              int rows, const int2* __restrict__ ktab, int ksel, int kstride, int k0, int kcnt,
-                                              bool kfast, bool vec, int tid) {
+// dst[k * sk + x * sx].  rows = x extent that exists (other rows are never read into a stored result), kcnt = contracted
+// elements that exist; the k tail up to the next multiple of 4 is zero-filled (a DMMA k-step reads 4).
+// KFAST: consecutive lanes walk k (else x); VEC: 16-byte items (pairs along the walking direction); KTAB: k offsets from
+// the table (several contracted dimensions) instead of k * kstride.  The inner loops carry no branch on these.
+template <bool VEC>
+__device__ __forceinline__ void cpa(double* s, const double* g, bool valid) {
+    if constexpr (VEC) cpa16(s, g, valid); else cpa8(s, g, valid);
+}
+template <bool KFAST, bool VEC, bool KTAB>
+__device__ __forceinline__ void issue_loop(double* dst, int sk, int sx, const double* __restrict__ base, const int2* __restrict__ xtab,
+                                           int rows, const int* __restrict__ ktab, int kstride, int k0, int kcnt, const LaneMap& lm) {
     const int kcnt4 = (kcnt + 3) & ~3;
-    if (kfast) {  // consecutive lanes -> consecutive k
-        int lanes = 4;
-        while (lanes < kcnt4 && lanes < kLT) lanes <<= 1;
-        const int f = tid & (lanes - 1), s0 = tid / lanes, step = kLT / lanes;
-        for (int kk = f; kk < kcnt4; kk += lanes) {
+    const int adv = lm.lanes * (VEC ? 2 : 1);
+    if constexpr (KFAST) {
+        for (int kk = lm.f; kk < kcnt4; kk += adv) {
             const bool kv = kk < kcnt;
-            int ko = 0;
-            if (kv) ko = ktab ? (ksel ? __ldg(&ktab[k0 + kk].y) : __ldg(&ktab[k0 + kk].x)) : (k0 + kk) * kstride;
-            double* d = dst + kk * ld;
+            const int ko = !kv ? 0 : (KTAB ? __ldg(ktab + 2 * (k0 + kk)) : (k0 + kk) * kstride);
+            const double* g = base + ko;
+            double* d = dst + kk * sk + lm.s0 * sx;
+            const int2* xt = xtab + lm.s0;
+            const int dsx = lm.step * sx;
 #pragma unroll 4
-            for (int x = s0; x < rows; x += step) {
-                const int xo = __ldg(&xtab[x].x);
-                cpa8(d + x, base + (kv ? ko + xo : 0), kv);
-            }
+            for (int x = lm.s0; x < rows; x += lm.step, d += dsx, xt += lm.step) cpa<VEC>(d, g + (kv ? __ldg(&xt->x) : 0), kv);
         }
-    } else if (vec) {  // consecutive lanes -> consecutive PAIRS of x (16 bytes)
-        const int pairs = (rows + 1) >> 1;
-        int lanes = 4;
-        while (lanes < pairs && lanes < kLT) lanes <<= 1;
-        const int f = (tid & (lanes - 1)) * 2, s0 = tid / lanes, step = kLT / lanes;
-        for (int x = f; x < rows; x += 2 * lanes) {
-            const int xo = __ldg(&xtab[x].x);
+    } else {
+        for (int x = lm.f; x < rows; x += adv) {
+            const double* g = base + __ldg(&xtab[x].x);
+            double* d = dst + x * sx + lm.s0 * sk;
+            const int dsk = lm.step * sk;
+            int kk = lm.s0;
+            if constexpr (KTAB) {
+                const int* kt = ktab + 2 * (k0 + kk);
 #pragma unroll 4
-            for (int kk = s0; kk < kcnt4; kk += step) {
-                const bool kv = kk < kcnt;
-                int ko = 0;
-                if (kv) ko = ktab ? (ksel ? __ldg(&ktab[k0 + kk].y) : __ldg(&ktab[k0 + kk].x)) : (k0 + kk) * kstride;
-                cpa16(dst + kk * ld + x, base + (kv ? ko + xo : 0), kv);
-            }
-        }
-    } else {  // consecutive lanes -> consecutive x
-        int lanes = 4;
-        while (lanes < rows && lanes < kLT) lanes <<= 1;
-        const int f = tid & (lanes - 1), s0 = tid / lanes, step = kLT / lanes;
-        for (int x = f; x < rows; x += lanes) {
-            const int xo = __ldg(&xtab[x].x);
+                for (; kk < kcnt; kk += lm.step, d += dsk, kt += 2 * lm.step) cpa<VEC>(d, g + __ldg(kt), true);
+            } else {
+                int ko = (k0 + kk) * kstride;
+                const int dko = lm.step * kstride;
 #pragma unroll 4
-            for (int kk = s0; kk < kcnt4; kk += step) {
-                const bool kv = kk < kcnt;
-                int ko = 0;
-                if (kv) ko = ktab ? (ksel ? __ldg(&ktab[k0 + kk].y) : __ldg(&ktab[k0 + kk].x)) : (k0 + kk) * kstride;
-                cpa8(dst + kk * ld + x, base + (kv ? ko + xo : 0), kv);
+                for (; kk < kcnt; kk += lm.step, d += dsk, ko += dko) cpa<VEC>(d, g + ko, true);
             }
+            for (; kk < kcnt4; kk += lm.step, d += dsk) cpa<VEC>(d, g, false);  // zero fill of the k tail
         }
     }
 }
+// ktab points at the .x (L) or .y (R) component of the {offset in L, offset in R} table, stride 2 ints
+__device__ __forceinline__ void issue_operand(double* dst, int sk, int sx, const double* __restrict__ base,
+                                              const int2* __restrict__ xtab, int rows, const int* __restrict__ ktab, int kstride,
+                                              int k0, int kcnt, int mode, const LaneMap& lm) {
+    switch (mode) {  // (kfast << 2) | (vec << 1) | ktab -- uniform for the whole kernel
+        case 0: issue_loop<false, false, false>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 1: issue_loop<false, false, true>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 2: issue_loop<false, true, false>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 3: issue_loop<false, true, true>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 4: issue_loop<true, false, false>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 5: issue_loop<true, false, true>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        case 6: issue_loop<true, true, false>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+        default: issue_loop<true, true, true>(dst, sk, sx, base, xtab, rows, ktab, kstride, k0, kcnt, lm); break;
+    }
+}
 
-// MF x NF fragments of 8 x 8 per warp, the 4 warps arranged WR x (4 / WR) over the fragment grid of the tile.
+// Every warp owns exactly MF x NF fragments of 8 x 8 (compile time: the DMMA loop carries no guards); the 4 warps are
+// arranged WR x (4 / WR) over the tile.  A tile smaller than the warps' footprint leaves rows / columns of the staged chunk
+// unwritten: their products land in accumulators that are never stored.
 template <int MF, int NF, int WR>
-__global__ void __launch_bounds__(kLT) lowint_kernel(const __grid_constant__ LowArgs a) {
+__global__ void __launch_bounds__(kLT, (MF * NF <= 8) ? 4 : 3) lowint_kernel(const __grid_constant__ LowArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
     const int mrow0 = (warp % WR) * MF * 8, ncol0 = (warp / WR) * NF * 8;
-    const int stage_elems = a.KC * (a.lda + a.ldb);
     const int nwork = a.nprob * a.ntile_m * a.nslice;
-    // fragments of this warp that exist in the (padded) tile; uniform per warp
-    const int mf_n = max(0, min(MF, (a.BM - mrow0) >> 3)), nf_n = max(0, min(NF, (a.Np - ncol0) >> 3));
+    const LaneMap lma = lane_map(a.a_kfast ? a.KC : a.BM, a.a_vec, tid);
+    const LaneMap lmb = lane_map(a.b_kfast ? a.KC : a.N, a.b_vec, tid);
+    // fragment addressing: A(k, m) of the tile at As[k * a_sk + m * a_sx]; a lane reads (k = 4 ks + t4, m = mrow0 + 8 i + g)
+    const int a_thr = t4 * a.a_sk + (mrow0 + g) * a.a_sx, b_thr = a.a_elems + t4 * a.b_sk + (ncol0 + g) * a.b_sx;
+    const int a_i = 8 * a.a_sx, b_j = 8 * a.b_sx, a_ks = 4 * a.a_sk, b_ks = 4 * a.b_sk;
+
+    const int* ktab_i = reinterpret_cast<const int*>(a.ktab);
+    const int a_mode = (a.a_kfast << 2) | (a.a_vec << 1) | (a.ktab ? 1 : 0), b_mode = (a.b_kfast << 2) | (a.b_vec << 1) | (a.ktab ? 1 : 0);
 
     Cursor pf, cp;  // prefetch cursor (kLStages - 1 chunks ahead) and compute cursor walk the same sequence
     cursor_load(pf, a, blockIdx.x, nwork);
     cp = pf;
-
-    auto issue = [&](int stage) {
-        if (pf.w < nwork) {
-            const int pair = pf.c / a.cpp, kc = pf.c - pair * a.cpp;
-            const int k0 = kc * a.KC, kcnt = min(a.KC, a.K - k0);
-            Pair pq;
-            if (a.probs) {
-                const int4 raw = __ldg(reinterpret_cast<const int4*>(a.pairs + pf.pair_begin + pair));
-                memcpy(&pq, &raw, sizeof(pq));
-            } else {
-                pq = a.pair0;
-            }
-            double* As = sm + (size_t)stage * stage_elems;
-            double* Bs = As + a.KC * a.lda;
-            const int rows = min(a.BM, a.M - pf.tile * kLBM);
-            issue_operand(As, a.lda, pq.L, a.mtab + pf.tile * a.BM, rows, a.ktab, 0, a.ksL1, k0, kcnt, a.a_kfast, a.a_vec, tid);
-            issue_operand(Bs, a.ldb, pq.R, a.ntab, a.N, a.ktab, 1, a.ksR1, k0, kcnt, a.b_kfast, a.b_vec, tid);
-            if (++pf.c == pf.c_end) cursor_load(pf, a, pf.w + gridDim.x, nwork);
-        }
-        cp_commit();  // always: the group count stays in step with the iteration count
-    };
-
-#pragma unroll
-    for (int s = 0; s < kLStages - 1; ++s) issue(s);
 
     double acc[MF][NF][2];
 #pragma unroll
@@ -210,60 +230,81 @@ __global__ void __launch_bounds__(kLT) lowint_kernel(const __grid_constant__ Low
         for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const bool unit_alpha = a.alpha == 1.0;
-    for (int it = 0; cp.w < nwork; ++it) {
-        cp_wait<kLStages - 2>();
-        __syncthreads();  // chunk `it` has landed for every thread; everybody is done with the stage refilled next
-        issue((it + kLStages - 1) % kLStages);
-
-        const int kc = cp.c % a.cpp;
-        const int kcnt = min(a.KC, a.K - kc * a.KC);
-        const double* As = sm + (size_t)(it % kLStages) * stage_elems + t4 * a.lda + mrow0 + g;
-        const double* Bs = sm + (size_t)(it % kLStages) * stage_elems + a.KC * a.lda + t4 * a.ldb + ncol0 + g;
-        const int nks = (kcnt + 3) >> 2;
-        if (mf_n > 0 && nf_n > 0) {
-#pragma unroll 2
-            for (int ks = 0; ks < nks; ++ks) {
-                double af[MF], bf[NF];
-#pragma unroll
-                for (int i = 0; i < MF; ++i)
-                    if (i < mf_n) af[i] = As[ks * 4 * a.lda + i * 8];
-#pragma unroll
-                for (int j = 0; j < NF; ++j)
-                    if (j < nf_n) bf[j] = Bs[ks * 4 * a.ldb + j * 8];
-#pragma unroll
-                for (int i = 0; i < MF; ++i)
-#pragma unroll
-                    for (int j = 0; j < NF; ++j)
-                        if (i < mf_n && j < nf_n) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-            }
+    for (int it = -(kLStages - 1); cp.w < nwork; ++it) {
+        if (it >= 0) {
+            cp_wait<kLStages - 2>();
+            __syncthreads();  // chunk `it` has landed for every thread; everybody is done with the stage refilled next
         }
-        if (++cp.c == cp.c_end) {
+        {   // ---- prefetch: the chunk kLStages - 1 ahead (the ring runs across item boundaries) ----
+            if (pf.w < nwork) {
+                const int stage = (it + kLStages - 1) % kLStages;
+                const int k0 = pf.kc * a.KC, kcnt = min(a.KC, a.K - k0);
+                Pair pq;
+                if (a.probs) {
+                    const int4 raw = __ldg(reinterpret_cast<const int4*>(a.pairs + pf.pair));
+                    memcpy(&pq, &raw, sizeof(pq));
+                } else {
+                    pq = a.pair0;
+                }
+                double* As = sm + (size_t)stage * a.stage_elems;
+                const int rows = min(a.BM, a.M - pf.tile * kLBM);
+                issue_operand(As, a.a_sk, a.a_sx, pq.L, a.mtab + pf.tile * a.BM, rows, ktab_i, a.ksL1, k0, kcnt, a_mode, lma);
+                issue_operand(As + a.a_elems, a.b_sk, a.b_sx, pq.R, a.ntab, a.N, ktab_i ? ktab_i + 1 : nullptr, a.ksR1, k0, kcnt, b_mode, lmb);
+                cursor_next_chunk(pf, a);
+                if (pf.c == pf.c_end) cursor_load(pf, a, pf.w + gridDim.x, nwork);
+            }
+            cp_commit();  // always: the group count stays in step with the iteration count
+        }
+        if (it < 0) continue;
+
+        const int kcnt = min(a.KC, a.K - cp.kc * a.KC);
+        const double* st = sm + (size_t)(it % kLStages) * a.stage_elems;
+        const double* Ap = st + a_thr;
+        const double* Bp = st + b_thr;
+        const int nks = (kcnt + 3) >> 2;
+#pragma unroll 2
+        for (int ks = 0; ks < nks; ++ks) {
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) af[i] = Ap[i * a_i];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) bf[j] = Bp[j * b_j];
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            Ap += a_ks;
+            Bp += b_ks;
+        }
+        cursor_next_chunk(cp, a);
+        if (cp.c == cp.c_end) {
             // ---- epilogue of the item: D[perm(m, n)] (+)= alpha * acc, the output permute as a scatter ----
             const int2* mt = a.mtab + cp.tile * a.BM;
             const int rows = min(a.BM, a.M - cp.tile * kLBM);
             double* __restrict__ Dp = cp.D;
+            int no[NF][2];
+#pragma unroll
+            for (int j = 0; j < NF; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = ncol0 + j * 8 + 2 * t4 + c;
+                    no[j][c] = col < a.N ? __ldg(&a.ntab[col].y) : -1;
+                }
 #pragma unroll
             for (int i = 0; i < MF; ++i) {
                 const int row = mrow0 + i * 8 + g;
-                if (i < mf_n && row < rows) {
-                    const int mo = __ldg(&mt[row].y);
+                const int mo = row < rows ? __ldg(&mt[row].y) : -1;
 #pragma unroll
-                    for (int j = 0; j < NF; ++j) {
-                        if (j < nf_n) {
+                for (int j = 0; j < NF; ++j)
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const int col = ncol0 + j * 8 + 2 * t4 + c;
-                                if (col < a.N) {
-                                    double* dst = Dp + (size_t)(mo + __ldg(&a.ntab[col].y));
-                                    const double v = unit_alpha ? acc[i][j][c] : a.alpha * acc[i][j][c];
-                                    if (a.atomic) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
-                                    else if (a.beta == 0.0) *dst = v;
-                                    else *dst = v + a.beta * *dst;
-                                }
-                            }
+                    for (int c = 0; c < 2; ++c)
+                        if ((mo | no[j][c]) >= 0) {
+                            double* dst = Dp + (size_t)(mo + no[j][c]);
+                            const double v = unit_alpha ? acc[i][j][c] : a.alpha * acc[i][j][c];
+                            if (a.atomic) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+                            else if (a.beta == 0.0) *dst = v;
+                            else *dst = v + a.beta * *dst;
                         }
-                    }
-                }
             }
 #pragma unroll
             for (int i = 0; i < MF; ++i)
@@ -424,16 +465,41 @@ int get_tables(const Shape& s, Tables* out) {
 }
 
 template <int MF, int NF, int WR>
-int launch_low(const LowArgs& a, int grid, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SIP_CUDA(cudaFuncSetAttribute(lowint_kernel<MF, NF, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
+int launch_low(LowArgs& a, size_t smem, long long nwork0, bool may_split, long long total_chunks, long long chunk_bytes,
+               const std::function<int()>& prescale) {
+    static int per_sm = 0;
+    auto* kern = lowint_kernel<MF, NF, WR>;
+    if (!per_sm) {
+        SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        // several CTAs per SM: ask for the full shared-memory carve-out
+        SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        per_sm = -1;
     }
-    lowint_kernel<MF, NF, WR><<<grid, kLT, smem, ctx().stream>>>(a);
-    SIP_CUDA(cudaGetLastError());
-    count_launch();
-    return SIPGPU_OK;
+    int occ = 1;
+    SIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLT, smem));
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)ctx().num_sms * occ;
+    long long ns = 1;
+    if (nwork0 < slots && may_split) {
+        // every slice streams at least ~256 KB of operands (a split costs a pre-scale launch and atomics)
+        const long long min_chunks = std::max<long long>(1, (256 * 1024) / std::max<long long>(1, chunk_bytes));
+        const long long avg_chunks = std::max<long long>(1, total_chunks / std::max<long long>(1, a.nprob));
+        ns = std::min<long long>((2 * slots + nwork0 - 1) / nwork0, std::max<long long>(1, avg_chunks / min_chunks));
+    }
+    a.nslice = (int)ns;
+    a.atomic = ns > 1;
+    if (a.atomic) SIP_TRY(prescale());
+    const long long nwork = nwork0 * ns;
+    if (nwork >= (1LL << 31)) return SIPGPU_E_ARG;
+    const int grid = (int)std::min<long long>(nwork, slots);
+    auto go = [a, grid, smem, kern]() -> int {
+        kern<<<grid, kLT, smem, ctx().stream>>>(a);
+        SIP_CUDA(cudaGetLastError());
+        count_launch();
+        return SIPGPU_OK;
+    };
+    if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+    return go();
 }
 
 }  // namespace
@@ -449,16 +515,28 @@ static double& lowint_max_intensity() {
     }();
     return v;
 }
+static int& lowint_scope() {
+    static int v = [] { const char* e = getenv("SIPGPU_LOWINT_SCOPE"); return e ? atoi(e) : 1; }();
+    return v;
+}
 void lowint_set_max_intensity(double v) { lowint_max_intensity() = v; }
+void lowint_set_scope(int v) { lowint_scope() = v; }
 
 // Is this (launcher-oriented: the small free dimension already on the n side) contraction one for the bandwidth-shaped
-// kernel?  N fits one tile and the flops per algorithmic byte stay below the ridge of the roofline
-// (37 TFLOP/s / 6.5 TB/s = 5.7); everything denser belongs to the 128-wide tiles of contract.cu.
+// kernel?  Scope 1 (default) is where it beats the 128-wide tiles on the B200 (profiles/r02_lowint_vs_tiles.txt, all 170
+// SIAL patterns at o = 20, v = 50): dot products (M = N = 1: 5-7x), destinations that fit ONE tile with a short contracted
+// range (tiny matrices: 1.2-1.4x) or with at most 512 elements (rank-2 results of rank-4 blocks, 20 x 20 / 50 x 1:
+// 1.3-1.9x).  Matrix-vector shapes run level with the tiles and the M-tiled skinny shapes slower (one warp role issues the
+// loads AND the DMMAs), so they stay with contract.cu.  Scope 2 (tests, A/B runs) takes everything with N <= 64 below
+// `lowint_max_intensity` flops per algorithmic byte.
 bool lowint_eligible(const Shape& s) {
     const double maxi = lowint_max_intensity();
-    if (maxi < 0 || s.N > 64 || s.M < 1 || s.N < 1 || s.K < 1) return false;
+    const int scope = lowint_scope();
+    if (maxi < 0 || scope <= 0 || s.N > 64 || s.M < 1 || s.N < 1 || s.K < 1) return false;
     const double flops = 2.0 * s.M * s.N * s.K, bytes = 8.0 * ((double)s.M * s.K + (double)s.N * s.K + (double)s.M * s.N);
-    return flops / bytes <= maxi;
+    if (flops / bytes > maxi) return false;
+    if (scope >= 2) return true;
+    return s.M <= 64 && ((long long)s.M * s.N <= 512 || s.K <= 64);
 }
 
 // n destinations of ONE shape: destination i = alpha * sum over pairs [chain[i], chain[i+1]) + beta * D_i.
@@ -485,18 +563,23 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
     if (n > 1 || pairs.size() > 1) {
         const size_t b_probs = (sizeof(LowProb) * probs.size() + 255) & ~(size_t)255, b_pairs = sizeof(Pair) * pairs.size();
         void *h, *d;
-        SIP_TRY(scratch_reserve(b_probs + b_pairs, &h, &d));
+        SIP_TRY(desc_alloc(b_probs + b_pairs, &h, &d));
         memcpy(h, probs.data(), sizeof(LowProb) * probs.size());
         memcpy((char*)h + b_probs, pairs.data(), b_pairs);
-        SIP_CUDA(cudaMemcpyAsync(d, h, b_probs + b_pairs, cudaMemcpyHostToDevice, c.stream));
+        SIP_TRY(desc_commit(h, d, b_probs + b_pairs));
         d_probs = (const LowProb*)d;
         d_pairs = (const Pair*)((char*)d + b_probs);
     }
-    auto prescale = [&]() -> int {  // split partial sums meet through red.add: beta is applied once, up front
+    // split partial sums meet through red.add: beta is applied once, up front (a closure that owns its pointer list, so
+    // that a prepared launch can replay it)
+    std::function<int()> prescale = [dd = std::vector<double*>(D, D + n), mn = (long long)s.M * s.N, beta]() -> int {
         if (beta == 1.0) return SIPGPU_OK;
-        std::vector<double*> dd(D, D + n);
-        std::vector<long long> cnt((size_t)n, (long long)s.M * s.N);
-        return ew_scale_many(n, dd.data(), cnt.data(), beta);
+        std::vector<long long> cnt(dd.size(), mn);
+        return ew_scale_many((int)dd.size(), dd.data(), cnt.data(), beta);
+    };
+    auto run_prescale = [&]() -> int {
+        if (Capture* cap = capture()) { cap->steps.push_back(prescale); return SIPGPU_OK; }
+        return prescale();
     };
 
     if (is_dot) {
@@ -514,12 +597,16 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
         }
         a.nslice = (int)ns;
         a.atomic = ns > 1;
-        if (a.atomic) SIP_TRY(prescale());
-        const long long nwork = (long long)n * ns;
-        dotk_kernel<<<(int)std::min<long long>(nwork, slots), kDotT, 0, c.stream>>>(a);
-        SIP_CUDA(cudaGetLastError());
-        count_launch();
-        return SIPGPU_OK;
+        if (a.atomic) SIP_TRY(run_prescale());
+        const int grid = (int)std::min<long long>((long long)n * ns, slots);
+        auto go = [a, grid]() -> int {
+            dotk_kernel<<<grid, kDotT, 0, ctx().stream>>>(a);
+            SIP_CUDA(cudaGetLastError());
+            count_launch();
+            return SIPGPU_OK;
+        };
+        if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+        return go();
     }
 
     LowArgs a;
@@ -528,66 +615,66 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
     a.mtab = t.mtab; a.ntab = t.ntab; a.ktab = t.ktab;
     a.nprob = n; a.M = s.M; a.N = s.N; a.K = s.K;
     a.ksL1 = s.nk >= 1 ? s.ksL[0] : 0; a.ksR1 = s.nk >= 1 ? s.ksR[0] : 0;
-    a.BM = t.BM; a.Np = t.Np; a.ntile_m = t.ntile_m;
-    a.lda = a.BM + 4; a.ldb = a.Np + 4;
-    const int perk = 8 * (a.lda + a.ldb);       // staged bytes per contracted element
-    const int k4 = (s.K + 3) & ~3;
-    int KC = (24 * 1024 / perk) & ~3;           // <= 24 KB per stage ...
-    if ((long long)k4 * perk <= 32 * 1024) KC = k4;  // ... unless the whole contracted range fits 32 KB: one chunk per pair
-    KC = std::max(4, std::min(KC, std::min(k4, 512)));
-    a.KC = KC;
-    a.cpp = (s.K + KC - 1) / KC;
+    a.BM = t.BM; a.ntile_m = t.ntile_m;
+    a.alpha = alpha; a.beta = beta;
+    a.p0 = probs[0]; a.pair0 = pairs[0];
+    // ---- warp arrangement: fragments (8 x 8) the tile needs, rounded up to the menu {1, 2, 4, 8}; WR x WC warps with
+    // exactly MF x NF fragments each, the arrangement with the fewest DMMAs per warp ----
+    auto pow2 = [](int x) { int p = 1; while (p < x) p <<= 1; return p; };
+    const int R = pow2(t.BM / 8), Cc = pow2(t.Np / 8);
+    int best = 1 << 20, WR = 2, MF = 4, NF = 4;
+    for (int wr : {2, 4, 1}) {  // ties: the square arrangement first
+        const int wc = 4 / wr;
+        const int mf = std::max(1, R / wr), nf = std::max(1, Cc / wc);
+        if (mf * nf < best) { best = mf * nf; WR = wr; MF = mf; NF = nf; }
+    }
+    const int rows_p = WR * MF * 8, cols_p = (4 / WR) * NF * 8;  // footprint of the warps (>= BM, Np)
     a.a_kfast = s.nk >= 1 && s.ksL[0] == 1 && s.kext[0] > 1;
     a.b_kfast = s.nk >= 1 && s.ksR[0] == 1 && s.kext[0] > 1;
-    // 16-byte pairs along m / n: unit stride, even extent (pairs never straddle a dimension), every other stride even
-    auto even_strides = [](int nd, const int* st) { for (int i = 1; i < nd; ++i) if (st[i] & 1) return false; return true; };
-    bool ka_even = true, kb_even = true;
-    for (int i = 0; i < s.nk; ++i) { ka_even = ka_even && !(s.ksL[i] & 1); kb_even = kb_even && !(s.ksR[i] & 1); }
-    a.a_vec = !a.a_kfast && s.nm >= 1 && s.msL[0] == 1 && s.mext[0] % 2 == 0 && even_strides(s.nm, s.msL) && ka_even;
-    a.b_vec = !a.b_kfast && s.nn >= 1 && s.nsR[0] == 1 && s.next[0] % 2 == 0 && even_strides(s.nn, s.nsR) && kb_even;
+    // bytes staged per contracted element decide the chunk length: <= 14 KB per stage (4 stages, 3-4 CTAs per SM), unless
+    // the whole contracted range fits 20 KB (one chunk per operand pair)
+    const int perk = 8 * (rows_p + cols_p + 8);
+    const int k4 = (s.K + 3) & ~3;
+    int KC = (14 * 1024 / perk) & ~3;
+    if ((long long)k4 * perk <= 20 * 1024) KC = k4;
+    KC = std::max(4, std::min(KC, std::min(k4, 512)));
+    for (;; KC -= 4) {  // exact footprint of the ring (the [x][k] layout pads every row): at most 80 KB per CTA
+        a.KC = KC;
+        const int ldk = KC + (KC % 8 == 0 ? 4 : 8);  // = 4 (mod 8)
+        if (a.a_kfast) { a.a_sk = 1; a.a_sx = ldk; a.a_elems = rows_p * ldk; }
+        else { a.a_sx = 1; a.a_sk = rows_p + 4; a.a_elems = KC * (rows_p + 4); }
+        int b_elems;
+        if (a.b_kfast) { a.b_sk = 1; a.b_sx = ldk; b_elems = cols_p * ldk; }
+        else { a.b_sx = 1; a.b_sk = cols_p + 4; b_elems = KC * (cols_p + 4); }
+        a.stage_elems = a.a_elems + b_elems;
+        if ((size_t)kLStages * a.stage_elems * 8 <= 80 * 1024 || KC <= 4) break;
+    }
+    a.cpp = (s.K + KC - 1) / KC;
+    // 16-byte items along the walking direction: unit stride there, even extent of the leading dimension (pairs never
+    // straddle it), every other stride of the operand even, 16-byte aligned blocks; the staged layout keeps pairs adjacent
+    auto all_even = [](int nd, const int* st, int from) { for (int i = from; i < nd; ++i) if (st[i] & 1) return false; return true; };
+    if (a.a_kfast) a.a_vec = s.kext[0] % 2 == 0 && all_even(s.nk, s.ksL, 1) && all_even(s.nm, s.msL, 0) && KC % 2 == 0;
+    else a.a_vec = s.nm >= 1 && s.msL[0] == 1 && s.mext[0] % 2 == 0 && all_even(s.nm, s.msL, 1) && all_even(s.nk, s.ksL, 0);
+    if (a.b_kfast) a.b_vec = s.kext[0] % 2 == 0 && all_even(s.nk, s.ksR, 1) && all_even(s.nn, s.nsR, 0) && KC % 2 == 0;
+    else a.b_vec = s.nn >= 1 && s.nsR[0] == 1 && s.next[0] % 2 == 0 && all_even(s.nn, s.nsR, 1) && all_even(s.nk, s.ksR, 0);
     if (a.a_vec || a.b_vec)
         for (const Pair& p : pairs) {
             if (a.a_vec && ((uintptr_t)p.L & 15)) a.a_vec = 0;
             if (a.b_vec && ((uintptr_t)p.R & 15)) a.b_vec = 0;
         }
-    a.alpha = alpha; a.beta = beta;
-    a.p0 = probs[0]; a.pair0 = pairs[0];
-
-    const size_t smem = (size_t)kLStages * KC * perk;
-    // resident CTAs per SM: 3 by registers (~155 x 128 threads), fewer when the ring is large
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (200 * 1024) / (smem + 1024)));
-    const long long slots = (long long)c.num_sms * per_sm;
+    const size_t smem = (size_t)kLStages * a.stage_elems * 8;
     const long long nwork0 = (long long)n * t.ntile_m;
-    long long ns = 1;
-    if (nwork0 < slots && dense_d) {
-        // every slice streams at least ~256 KB of operands (a split costs a pre-scale launch and atomics)
-        const long long chunk_bytes = (long long)KC * 8 * (std::min(s.M, kLBM) + s.N);
-        const long long min_chunks = std::max<long long>(1, (256 * 1024) / std::max<long long>(1, chunk_bytes));
-        const long long avg_chunks = std::max<long long>(1, total_pairs * a.cpp / n);
-        ns = std::min<long long>((2 * slots + nwork0 - 1) / nwork0, std::max<long long>(1, avg_chunks / min_chunks));
-    }
-    a.nslice = (int)ns;
-    a.atomic = ns > 1;
-    if (a.atomic) SIP_TRY(prescale());
-    const long long nwork = nwork0 * ns;
-    if (nwork >= (1LL << 31)) return SIPGPU_E_ARG;
-    const int grid = (int)std::min<long long>(nwork, slots);
-    // warp arrangement over the fragment grid: the one with the fewest fragments on its busiest warp
-    const int fm = a.BM / 8, fn = a.Np / 8;
-    auto busiest = [&](int wr, int mf, int nf) {
-        const int wc = 4 / wr;
-        if (wr * mf < fm || wc * nf < fn) return 1 << 20;  // does not cover the tile
-        int worst = 0;
-        for (int w = 0; w < 4; ++w) {
-            const int r = std::max(0, std::min(mf, fm - (w % wr) * mf)), q = std::max(0, std::min(nf, fn - (w / wr) * nf));
-            worst = std::max(worst, r * q);
-        }
-        return worst;
-    };
-    const int c22 = busiest(2, 4, 4), c14 = busiest(1, 8, 2), c41 = busiest(4, 2, 8);
-    if (c14 < c22 && c14 <= c41) return launch_low<8, 2, 1>(a, grid, smem);
-    if (c41 < c22) return launch_low<2, 8, 4>(a, grid, smem);
-    return launch_low<4, 4, 2>(a, grid, smem);
+    const long long chunk_bytes = (long long)KC * 8 * (std::min(s.M, kLBM) + s.N);
+    const long long total_chunks = total_pairs * a.cpp;
+    const std::function<int()> pre = run_prescale;
+#define LOW_CASE(mf, nf, wr) \
+    if (MF == mf && NF == nf && WR == wr) return launch_low<mf, nf, wr>(a, smem, nwork0, dense_d, total_chunks, chunk_bytes, pre)
+    LOW_CASE(4, 4, 2); LOW_CASE(4, 2, 2); LOW_CASE(2, 4, 2); LOW_CASE(2, 2, 2); LOW_CASE(4, 1, 2); LOW_CASE(1, 4, 2);
+    LOW_CASE(2, 1, 2); LOW_CASE(1, 2, 2); LOW_CASE(1, 1, 2); LOW_CASE(2, 1, 4); LOW_CASE(1, 1, 4); LOW_CASE(1, 2, 1);
+    LOW_CASE(1, 1, 1);
+#undef LOW_CASE
+    set_error("lowint: no kernel for the warp arrangement %d x %d fragments on %d x %d warps", MF, NF, WR, 4 / WR);
+    return SIPGPU_E_ARG;
 }
 
 }  // namespace sipgpu

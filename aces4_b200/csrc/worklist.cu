@@ -864,15 +864,26 @@ int sipgpu_wl_begin(int flags) {
     g.dry = dry;
     if (cfg_max_ops) g.max_ops = cfg_max_ops;
     if (cfg_idle >= 0) g.idle_flush_ops = (size_t)cfg_idle;
-    if (!dry) {  // temps whose free is deferred may take up to 40 % of what is free now (capped at 64 GiB)
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t pool_res = 0, pool_use = 0;
-            sipgpu_pool_stats(&pool_res, &pool_use, nullptr);
-            const size_t avail = free_b + (pool_res - pool_use);
+    if (!dry) {  // temps whose free is deferred may take up to 40 % of what is free (capped at 64 GiB)
+        // cudaMemGetInfo costs milliseconds (measured: 4 ms per call on the B200 box -- half of a recorded CC iteration
+        // with 23 pardos went there), so the figure is refreshed only when the pool has grown or shrunk since it was taken
+        static size_t cached_limit = 0, cached_reserved = ~(size_t)0;
+        static long long cached_epoch = -1;
+        size_t pool_res = 0, pool_use = 0;
+        sipgpu_pool_stats(&pool_res, &pool_use, nullptr);
+        if (cached_limit == 0 || pool_res != cached_reserved || cached_epoch != mem_epoch()) {
+            cached_epoch = mem_epoch();
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                cached_limit = free_b + pool_res;   // what the pool could ever hand out: free now + already reserved
+                cached_reserved = pool_res;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (cached_limit) {
+            const size_t avail = cached_limit > pool_use ? cached_limit - pool_use : 0;
             g.max_deferred_bytes = std::min<size_t>((size_t)64 << 30, std::max<size_t>((size_t)1 << 30, avail / 10 * 4));
-        } else {
-            cudaGetLastError();
         }
     }
     if (cfg_max_deferred) g.max_deferred_bytes = cfg_max_deferred;

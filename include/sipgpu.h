@@ -198,6 +198,19 @@ int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int dr
                             const int* dext, const int* chain_start, const double* const* L, const double* const* R,
                             double* const* D, double alpha, double beta);
 
+/* Prepared work-list: the arguments of sipgpu_contract_chained (chain_start may be NULL: n independent blocks) marshalled
+ * ONCE -- shapes, problem and pair descriptors, tile prefix sums resident on the device -- and launched any number of
+ * times.  A CC iteration replays the same work-lists (same blocks, same chains; rlccd_rhf.sialx:342-556 every
+ * iteration), and for thousands of small blocks the per-call host marshalling is longer than the kernels.  The pointer
+ * arrays are copied; the blocks they name must stay alive.  A launch with a new (alpha, beta) pair prepares that variant
+ * on first use. */
+typedef struct sipgpu_plan sipgpu_plan;
+int sipgpu_plan_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
+                                 const int* dext, const int* chain_start, const double* const* L, const double* const* R,
+                                 double* const* D, sipgpu_plan** out);
+int sipgpu_plan_launch(sipgpu_plan* plan, double alpha, double beta);
+int sipgpu_plan_destroy(sipgpu_plan* plan);
+
 /* Raw strided-batched GEMM view of the contraction core, for micro-benchmarks of the DMMA kernel:
  * C(m x n, col-major, ldc) = alpha * A^T * B + beta*C with A = [k x m] (lda), B = [k x n] (ldb): exactly the
  * dgemm('T','N',...) of F90:762. */
@@ -209,8 +222,9 @@ int sipgpu_dmma_peak_probe(int iters, double* tflops_out);
 int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out);
 /* Launch-policy knobs for A/B measurements and for tests that must reach a particular kernel (defaults are the product
  * path).  "lowint_max_intensity": contractions with N <= 64 and at most this many flops per algorithmic byte run on the
- * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).  Returns
- * SIPGPU_E_ARG for an unknown key.  Host-only. */
+ * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).
+ * "lowint_scope": 0 never, 1 (default) dot products + single-tile destinations where that kernel measured faster than the
+ * 128-wide tiles, 2 every eligible shape (tests, A/B).  Returns SIPGPU_E_ARG for an unknown key.  Host-only. */
 int sipgpu_set_tuning(const char* key, double value);
 
 /* host-only views of the planner (no device needed; used by the CPU tests of the host logic) */

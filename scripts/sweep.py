@@ -16,8 +16,13 @@ import json
 import os
 import sys
 
-import numpy as np
-import torch
+# CPU column: the oracle's OpenMP loops and OpenBLAS's threads take turns; idle libgomp workers must not spin through the
+# dgemm (see bench.py) -- set before any OpenMP runtime is loaded
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -91,6 +96,54 @@ for s in sizes + ["ragged"]:
     print(f"contract s={s}: batched TF/s min/median/max {min(v):.1f}/{np.median(v):.1f}/{max(v):.1f}; one block "
           f"{min(v1):.2f}/{np.median(v1):.2f}/{max(v1):.2f}", flush=True)
 out["contract_444"] = con
+
+# ------------------------------------------------------------------------ CPU column of config 4 ("1 GPU vs CPU")
+# The reference's CPU path for the same block contraction -- permute L, permute R, dgemm('T','N'), permute D
+# (tensor_dil_omp.F90:662-796), restated by the oracle with OpenBLAS dgemm -- on this box's host cores: at 8 threads (the
+# reference caps OpenMP at 8, src/sip/core/sip.cpp:113) and at all cores; one block per call, as the interpreter issues them.
+if "--no-cpu" not in sys.argv:
+    import ctypes
+    import time
+
+    from oracle import oracle
+
+    cores = len(os.sched_getaffinity(0))
+    cpu = {}
+    for s_ in sizes + ["ragged"]:
+        per_threads = {}
+        for nthr in sorted({min(8, cores), cores}):
+            oracle.use_openblas(nthr)
+            try:
+                ctypes.CDLL("libgomp.so.1").omp_set_num_threads(nthr)
+            except OSError:
+                pass
+            tf = []
+            for d, l, r in pats444[:4]:
+                labs = sorted(set(d + l + r))
+                num = {c: i + 1 for i, c in enumerate(labs)}
+                exts = dict(zip(labs, itertools.cycle([13, 30, 50, 64, 30, 13]))) if s_ == "ragged" else {c: s_ for c in labs}
+                rng = np.random.default_rng(7)
+                Lh = np.asfortranarray(rng.uniform(-1, 1, [exts[c] for c in l]))
+                Rh = np.asfortranarray(rng.uniform(-1, 1, [exts[c] for c in r]))
+                dsh = [exts[c] for c in d]
+                flops = 2.0 * np.prod(dsh) * np.prod([exts[c] for c in l if c in r])
+                args_ = ([num[c] for c in d], dsh, [num[c] for c in l], Lh, [num[c] for c in r], Rh)
+                oracle.contract_labels(*args_)
+                reps = int(max(1, min(20, 2e9 // flops)))
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    oracle.contract_labels(*args_)
+                tf.append(flops * reps / (time.perf_counter() - t0) / 1e12)
+            per_threads[str(nthr)] = float(np.median(tf))
+        gpu_b = float(np.median([x["batch_tflops"] for x in con[str(s_)]]))
+        gpu_1 = float(np.median([x["one_block_tflops"] for x in con[str(s_)]]))
+        cpu[str(s_)] = {"cpu_tflops_by_threads": per_threads, "gpu_batched_tflops_median": gpu_b, "gpu_one_block_tflops_median": gpu_1,
+                        "gpu_batched_over_cpu_best": gpu_b / max(per_threads.values())}
+        print(f"config 4 s={s_}: CPU (oracle + OpenBLAS) " + ", ".join(f"{k} thr {v:.3f} TF/s" for k, v in per_threads.items()) +
+              f"; GPU batched {gpu_b:.1f} TF/s, one block {gpu_1:.2f} TF/s", flush=True)
+    oracle.use_naive_gemm()
+    out["config4_vs_cpu"] = {"host_cores": cores, "how": "oracle.contract_labels (permute -> OpenBLAS dgemm -> permute), one block per "
+                             "call, median over 4 label patterns", "by_segment_size": cpu}
 
 # ---------------------------------------------------------------------------------------------- permutes
 perm = {}

@@ -19,7 +19,7 @@ def sip():
 
     s.init()
     yield s.api
-    s.api.set_tuning("lowint_max_intensity", 7.0)
+    s.api.set_tuning("lowint_scope", 1)
 
 
 def relerr(a, b):
@@ -54,7 +54,7 @@ CASES = [
 @pytest.mark.parametrize("route", ["lowint", "tiles"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_single_blocks(sip, oracle, case, route):
-    sip.set_tuning("lowint_max_intensity", 7.0 if route == "lowint" else -1.0)
+    sip.set_tuning("lowint_scope", 2 if route == "lowint" else 0)
     name, d, l, r, ext = case
     labs = sorted(set(d + l + r))
     num = {c: i + 1 for i, c in enumerate(labs)}
@@ -78,7 +78,7 @@ def test_single_blocks(sip, oracle, case, route):
 @pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[3], CASES[8], CASES[10]], ids=lambda c: c[0])
 def test_work_lists_with_chains(sip, oracle, case, nblocks, chain_max):
     """few destinations (split along the chain and K), many destinations (one item each), chains of unequal length"""
-    sip.set_tuning("lowint_max_intensity", 7.0)
+    sip.set_tuning("lowint_scope", 2)
     name, d, l, r, ext = case
     if nblocks >= 40:
         ext = {c: max(1, min(e, 12)) for c, e in ext.items()}   # keep the oracle fast
@@ -125,7 +125,7 @@ def test_work_lists_with_chains(sip, oracle, case, nblocks, chain_max):
 def test_sliced_operands_in_place(sip, oracle):
     """`T[a,i,mu,j] = T2[a,i,b,j] * ca[mu,b]` with ca read in place from the static array (strided operand) and a strided
     destination: the bandwidth-shaped kernel takes strides from the parent arrays (no split of a strided destination)"""
-    sip.set_tuning("lowint_max_intensity", 7.0)
+    sip.set_tuning("lowint_scope", 2)
     rng = np.random.default_rng(77)
     T2 = rand_block(rng, (9, 4, 11, 5))
     ca = rand_block(rng, (30, 26))
@@ -142,3 +142,54 @@ def test_sliced_operands_in_place(sip, oracle):
     want = Dpar.copy(order="F")
     want[:, :, d0:d0 + 8, :] = ref
     assert relerr(dD.to_numpy(), want) <= TOL
+
+
+def test_prepared_plans_replay_the_launches(sip, oracle):
+    """sipgpu_plan_*: a work-list marshalled once (descriptors resident) gives the same results as the eager call, for every
+    kernel family a work-list can reach (tile kernel, split-K with its pre-scale, bandwidth-shaped kernel, dot kernel), with
+    different (alpha, beta) pairs on the same plan, launch after launch, and costs no more launches than the eager path."""
+    rng = np.random.default_rng(11)
+    for scope, (d, l, r, ext, nb) in ((0, ("aibj", "aick", "ckbj", dict(a=9, i=4, b=9, j=4, c=9, k=4), 6)),     # tiles
+                                      (0, ("ab", "aicj", "bicj", dict(a=10, b=12, i=6, c=40, j=20), 2)),      # tiles, split-K
+                                      (2, ("ab", "aicj", "bicj", dict(a=10, b=12, i=6, c=40, j=20), 2)),      # lowint, k slices
+                                      (1, ("ab", "ac", "cb", dict(a=20, b=20, c=50), 40)),                    # lowint, tiny
+                                      (1, ("ab", "cda", "cdb", dict(a=1, b=1, c=50, d=41), 5))):              # dot kernel
+        sip.set_tuning("lowint_scope", scope)
+        labs = sorted(set(d + l + r))
+        num = {c: i + 1 for i, c in enumerate(labs)}
+        dl_, ll_, rl_ = [num[c] for c in d], [num[c] for c in l], [num[c] for c in r]
+        ptrn, ierr = sip.get_contraction_ptrn(dl_, ll_, rl_)
+        assert ierr == 0
+        lsh, rsh, dsh = tuple(ext[c] for c in l), tuple(ext[c] for c in r), tuple(ext[c] for c in d)
+        Lh = [rand_block(rng, lsh) for _ in range(2 * nb)]
+        Rh = [rand_block(rng, rsh) for _ in range(2 * nb)]
+        Ld, Rd = [sip.DeviceBlock.from_numpy(x) for x in Lh], [sip.DeviceBlock.from_numpy(x) for x in Rh]
+        refs = []
+        for b in range(nb):
+            acc = 0.0
+            for c in (2 * b, 2 * b + 1):
+                t, e = oracle.contract_labels(dl_, list(dsh), ll_, Lh[c], rl_, Rh[c])
+                assert e == 0
+                acc = acc + t
+            refs.append(acc)
+        Ds = [sip.DeviceBlock(dsh) for _ in range(nb)]
+        bc = sip.BatchedContraction(ptrn, [lsh] * nb, [rsh] * nb, [dsh] * nb, [x.ptr for x in Ld], [x.ptr for x in Rd],
+                                    [x.ptr for x in Ds], chain_start=[2 * b for b in range(nb + 1)])
+        l0 = sip.kernel_launches()
+        bc.launch(prepared=False)
+        eager = sip.kernel_launches() - l0
+        for b in range(nb):
+            assert relerr(Ds[b].to_numpy().reshape(refs[b].shape), refs[b]) <= TOL
+            Ds[b].fill(0.0)
+        for rep in range(3):                       # beta = 0 replays
+            l0 = sip.kernel_launches()
+            bc.launch()
+            assert sip.kernel_launches() - l0 == eager
+            for b in range(nb):
+                assert relerr(Ds[b].to_numpy().reshape(refs[b].shape), refs[b]) <= TOL
+        bc.launch(alpha=-0.5, beta=1.0)            # a second (alpha, beta) variant of the same plan
+        bc.launch(alpha=-0.5, beta=1.0)
+        for b in range(nb):
+            assert np.max(np.abs(Ds[b].to_numpy().reshape(refs[b].shape))) <= 1e-9 * max(1.0, np.max(np.abs(refs[b])))
+        bc.destroy()
+    sip.set_tuning("lowint_scope", 1)

@@ -235,9 +235,9 @@ def check_contraction(sip, oracle, rng, dlab, llab, rlab, ext, alpha=1.0, beta=0
 def route(request, sip):
     """small test blocks are all low-intensity: run them through the bandwidth-shaped kernel (the default route) AND forced
     through the 128-wide tile kernel, so that both stay covered"""
-    sip.set_tuning("lowint_max_intensity", 7.0 if request.param == "lowint" else -1.0)
+    sip.set_tuning("lowint_scope", 2 if request.param == "lowint" else 0)
     yield request.param
-    sip.set_tuning("lowint_max_intensity", 7.0)
+    sip.set_tuning("lowint_scope", 1)
 
 
 def test_random_patterns(sip, oracle, route):
@@ -410,17 +410,18 @@ def test_batched_heterogeneous(sip, oracle):
         Rs.append(sip.DeviceBlock.from_numpy(R))
         Ds.append(sip.DeviceBlock([e[x] for x in dlab]))
         refs.append(ref)
-    sip.set_tuning("lowint_max_intensity", -1.0)   # the tile kernel: heterogeneous extents share a launch
+    sip.set_tuning("lowint_scope", 0)   # the tile kernel: heterogeneous extents share a launch
     before = sip.kernel_launches()
     sip.contract_batched(ptrn, Ls, Rs, Ds)
     assert sip.kernel_launches() - before <= 4  # one launch per kernel variant, not per block
-    sip.set_tuning("lowint_max_intensity", 7.0)    # the bandwidth-shaped kernel: one launch per distinct shape
+    sip.set_tuning("lowint_scope", 2)    # the bandwidth-shaped kernel: one launch per distinct shape
     Ds2 = [sip.DeviceBlock(d.shape) for d in Ds]
     before = sip.kernel_launches()
     sip.contract_batched(ptrn, Ls, Rs, Ds2)
     assert sip.kernel_launches() - before <= len({(l.shape, r.shape) for l, r in zip(Ls, Rs)})
     for d, ref in zip(Ds2, refs):
         assert relerr(d.to_numpy(), ref) <= TOL
+    sip.set_tuning("lowint_scope", 1)
     for d, ref in zip(Ds, refs):
         assert relerr(d.to_numpy(), ref) <= TOL
     # fused accumulate over the same work-list: D = D + L*R
