@@ -170,6 +170,7 @@ def lib():
         L.sipgpu_wl_set_idle_flush.argtypes = [C.c_longlong]
         L.sipgpu_wl_stats.argtypes = [C.POINTER(C.c_longlong)]
         L.sipgpu_wl_last_plan.argtypes = [C.c_int, c_int_p, c_int_p]
+        L.sipgpu_wl_replays.restype = C.c_longlong
         _LIB = L
     return _LIB
 
@@ -574,6 +575,11 @@ def wl_stats():
     out = (C.c_longlong * 9)()
     _check(lib().sipgpu_wl_stats(out), "sipgpu_wl_stats")
     return dict(zip(WL_STAT_NAMES, [int(x) for x in out]))
+
+
+def wl_replays():
+    """flushes of the open / last recording that replayed a captured stream instead of scheduling it"""
+    return int(lib().sipgpu_wl_replays())
 
 
 def wl_last_plan():

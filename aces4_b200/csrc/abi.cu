@@ -1058,8 +1058,8 @@ int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long 
 
 int sipgpu_set_tuning(const char* key, double value) {
     if (!key) return SIPGPU_E_ARG;
-    if (!strcmp(key, "lowint_max_intensity")) { lowint_set_max_intensity(value); return SIPGPU_OK; }
-    if (!strcmp(key, "lowint_scope")) { lowint_set_scope((int)value); return SIPGPU_OK; }
+    if (!strcmp(key, "lowint_max_intensity")) { lowint_set_max_intensity(value); wl_tuning_changed(); return SIPGPU_OK; }
+    if (!strcmp(key, "lowint_scope")) { lowint_set_scope((int)value); wl_tuning_changed(); return SIPGPU_OK; }
     set_error("sipgpu_set_tuning: unknown key '%s'", key);
     return SIPGPU_E_ARG;
 }

@@ -206,12 +206,14 @@ int pool_free(void* p) {
 
 void permute_cache_clear();
 void lowint_cache_clear();
+void wl_replay_cache_clear();
 
 static int finalize_all() {
     Ctx& c = g_ctx;
     if (!c.inited) return SIPGPU_OK;
     cudaStreamSynchronize(c.stream);
     cudaStreamSynchronize(c.copy_stream);
+    wl_replay_cache_clear();
     permute_cache_clear();
     lowint_cache_clear();
     for (auto& a : g_pool.arenas) cudaFree(a.base);

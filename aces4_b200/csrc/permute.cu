@@ -359,8 +359,16 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
     else SIP_TRY(build_perm_shape(rank, ext, transp, &ps));
     if (ps.rank <= 1) {  // identity after collapsing: straight copy (F90:478-491) or axpby
         for (int i = 0; i < n; ++i) {
-            if (!acc) SIP_CUDA(cudaMemcpyAsync(out[i], in[i], sizeof(double) * (size_t)ps.total, cudaMemcpyDeviceToDevice, c.stream));
-            else SIP_TRY(ew_axpby(out[i], in[i], ps.total, alpha, beta));
+            const double* src = in[i];
+            double* dst = out[i];
+            const long long cnt = ps.total;
+            auto go = [src, dst, cnt, acc, alpha, beta]() -> int {
+                if (!acc) SIP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToDevice, ctx().stream));
+                else SIP_TRY(ew_axpby(dst, src, cnt, alpha, beta));
+                return SIPGPU_OK;
+            };
+            if (Capture* cap = capture()) cap->steps.push_back(go);
+            else SIP_TRY(go());
         }
         return SIPGPU_OK;
     }
@@ -388,10 +396,10 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
         b.out0 = out[0];
     } else {
         void *h, *d;
-        SIP_TRY(scratch_reserve(sizeof(void*) * 2 * (size_t)n, &h, &d));
+        SIP_TRY(desc_alloc(sizeof(void*) * 2 * (size_t)n, &h, &d));
         memcpy(h, in, sizeof(void*) * n);
         memcpy((char*)h + sizeof(void*) * n, out, sizeof(void*) * n);
-        SIP_CUDA(cudaMemcpyAsync(d, h, sizeof(void*) * 2 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+        SIP_TRY(desc_commit(h, d, sizeof(void*) * 2 * (size_t)n));
         b.in = (const double* const*)d;
         b.out = (double* const*)((char*)d + sizeof(void*) * n);
     }
@@ -406,17 +414,22 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
     if (per_sm < 1) per_sm = 1;
     long long grid = a.ntiles * n;
     if (grid > c.num_sms * per_sm) grid = c.num_sms * per_sm;
-    switch (ept) {
-        case 4: SIP_TRY(launch_perm<4>(a, b, acc, (int)grid, smem, c.stream)); break;
-        case 6: SIP_TRY(launch_perm<6>(a, b, acc, (int)grid, smem, c.stream)); break;
-        case 8: SIP_TRY(launch_perm<8>(a, b, acc, (int)grid, smem, c.stream)); break;
-        case 10: SIP_TRY(launch_perm<10>(a, b, acc, (int)grid, smem, c.stream)); break;
-        case 12: SIP_TRY(launch_perm<12>(a, b, acc, (int)grid, smem, c.stream)); break;
-        default: SIP_TRY(launch_perm<16>(a, b, acc, (int)grid, smem, c.stream)); break;
-    }
-    SIP_CUDA(cudaGetLastError());
-    count_launch();
-    return SIPGPU_OK;
+    auto go = [a, b, acc, ept, grid, smem]() -> int {
+        cudaStream_t st = ctx().stream;
+        switch (ept) {
+            case 4: SIP_TRY(launch_perm<4>(a, b, acc, (int)grid, smem, st)); break;
+            case 6: SIP_TRY(launch_perm<6>(a, b, acc, (int)grid, smem, st)); break;
+            case 8: SIP_TRY(launch_perm<8>(a, b, acc, (int)grid, smem, st)); break;
+            case 10: SIP_TRY(launch_perm<10>(a, b, acc, (int)grid, smem, st)); break;
+            case 12: SIP_TRY(launch_perm<12>(a, b, acc, (int)grid, smem, st)); break;
+            default: SIP_TRY(launch_perm<16>(a, b, acc, (int)grid, smem, st)); break;
+        }
+        SIP_CUDA(cudaGetLastError());
+        count_launch();
+        return SIPGPU_OK;
+    };
+    if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+    return go();
 }
 
 int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out) {

@@ -22,6 +22,8 @@ bool wl_active();  // recording (entry points divert into the wl_rec_* functions
 bool wl_dry();     // recording without a device (host-only planning, CPU tests)
 // Schedule and launch everything recorded so far; recording stays on.  Blocking entry points call this first.
 int wl_flush();
+void wl_replay_cache_clear();  // drops every captured stream (finalize; descriptors live in pool memory)
+void wl_tuning_changed();       // launch policy changed: captured streams of the old policy must not be replayed
 
 // exclusive: a WL_REDADD whose destination no other process can reach (single-rank array) -- the scheduler may turn it
 // into the fused accumulate of the producing contraction

@@ -294,6 +294,12 @@ int sipgpu_wl_set_idle_flush(long long min_ops);
 int sipgpu_wl_stats(long long* out9);
 /* plan of the most recent flush, per recorded op in program order: the level it ran in and the index of the
  * op it was fused into (itself if not fused).  Returns the number of ops of that flush. */
+/* A stream that was seen before -- the same ops on the same blocks in the same order, which is what every iteration of a CC
+ * program records (interpreter.cpp:98-910 walks the same pardo bodies) -- is not scheduled again: its launches were captured
+ * (descriptors resident on the device) and are replayed.  Streams are recognised by a 128-bit content hash folded while
+ * recording; streams with opaque ops (super-instructions, slices) are always scheduled.  Returns the number of flushes of
+ * the open / last recording that were served by a replay.  SIPGPU_WL_REPLAY=0 in the environment disables the cache. */
+long long sipgpu_wl_replays(void);
 int sipgpu_wl_last_plan(int cap, int* level_of_op, int* unit_of_op);
 
 /* ---------------------------------------------------------------------------------------------

@@ -279,3 +279,51 @@ def test_sliced_contractions_inside_a_recording(sip, oracle):
         dbig.scale(2.0)
     assert rec.stats["recorded"] == 4 and rec.stats["levels"] == 4     # all four touch the same parent array: serial
     assert rel(dbig.to_numpy(), 2.0 * want) <= TOL
+
+
+def test_repeated_stream_is_replayed_not_rescheduled(sip, oracle):
+    """Every iteration of a CC program records the same pardo body on the same blocks.  The second recording of an
+    identical stream must be served from the captured launches (sipgpu_wl_replays), give the same result on NEW operand
+    values, and a stream that differs in one pointer must be scheduled afresh."""
+    v, o, n = 10, 6, 3
+    rng = np.random.default_rng(17)
+    dlab, llab, rlab = [1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6]
+    dT2 = [[sip.DeviceBlock((v, o, v, o)) for _ in range(n)] for _ in range(n)]
+    dV = [[sip.DeviceBlock((o, o, o, o)) for _ in range(n)] for _ in range(n)]
+    D = sip.DeviceBlock((v, o, v, o))
+    other = sip.DeviceBlock((v, o, v, o))
+
+    def body(dest):
+        dest.fill(0.0)
+        for i1 in range(n):
+            for j1 in range(n):
+                t = sip.DeviceBlock((v, o, v, o))
+                sip.contract_labels(dlab, (v, o, v, o), llab, dT2[i1][j1], rlab, dV[i1][j1], out=t)
+                dest.accumulate(t)
+                t.free()
+        p = sip.DeviceBlock((v, o, v, o))
+        sip.permute_labels([3, 2, 1, 4], [1, 2, 3, 4], dest, out=p)      # a permute and an elementwise op in the stream too
+        dest.axpy(p, 0.5)
+        p.free()
+
+    replays = []
+    for it in range(4):
+        T2 = [[rng.uniform(-1, 1, (v, o, v, o)) for _ in range(n)] for _ in range(n)]
+        V = [[rng.uniform(-1, 1, (o, o, o, o)) for _ in range(n)] for _ in range(n)]
+        want = np.zeros((v, o, v, o), order="F")
+        for i1 in range(n):
+            for j1 in range(n):
+                sip._check(sip.lib().sipgpu_h2d(dT2[i1][j1].ptr, sip._hp(np.asfortranarray(T2[i1][j1])), dT2[i1][j1].size))
+                sip._check(sip.lib().sipgpu_h2d(dV[i1][j1].ptr, sip._hp(np.asfortranarray(V[i1][j1])), dV[i1][j1].size))
+                t, ierr = oracle.contract_labels(dlab, [v, o, v, o], llab, np.asfortranarray(T2[i1][j1]), rlab, np.asfortranarray(V[i1][j1]))
+                assert ierr == 0
+                want += t
+        sip.sync()
+        want = want + 0.5 * np.transpose(want, (2, 1, 0, 3))
+        dest = other if it == 3 else D            # the last pass writes another destination: a different stream
+        with sip.recording() as rec:
+            body(dest)
+            sip.wl_flush()
+            replays.append(sip.wl_replays())
+        assert rel(dest.to_numpy(), want) <= TOL, it
+    assert replays[0] == 0 and replays[1] == 1 and replays[2] == 1 and replays[3] == 0, replays
