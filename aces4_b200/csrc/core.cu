@@ -15,6 +15,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <algorithm>
+#include <functional>
+
 #include "common.h"
 #include "worklist.h"
 
@@ -169,6 +172,10 @@ double* pool_alloc(size_t bytes) {
     auto fl = g_pool.free_lists.find(sz);
     void* p = nullptr;
     if (fl != g_pool.free_lists.end() && !fl->second.empty()) {
+        // lowest free address first (min-heap): the address a block gets depends only on WHICH blocks are live, not on
+        // the order earlier frees happened in -- so the same program point of every CC iteration sees the same addresses,
+        // which is what lets the deferred op stream recognise a repeated recording (worklist.cu replay cache)
+        std::pop_heap(fl->second.begin(), fl->second.end(), std::greater<void*>());
         p = fl->second.back();
         fl->second.pop_back();
     } else {
@@ -198,7 +205,9 @@ int pool_free(void* p) {
     }
     // Stream order makes recycling safe: every kernel that used the block was enqueued on the compute stream
     // before this call, and the next user is enqueued after it.
-    g_pool.free_lists[it->second].push_back(p);
+    auto& fl = g_pool.free_lists[it->second];
+    fl.push_back(p);
+    std::push_heap(fl.begin(), fl.end(), std::greater<void*>());
     g_pool.in_use -= it->second;
     g_pool.live.erase(it);
     return SIPGPU_OK;

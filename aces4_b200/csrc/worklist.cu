@@ -736,13 +736,18 @@ int push(Op&& o) {
     g.ops.push_back(std::move(o));
     g.st_recorded++;
     if (g.ops.size() >= g.max_ops || g.deferred_bytes >= g.max_deferred_bytes) return wl_flush();
-    // Overlap recording with execution: when the compute stream has drained, hand it what has been recorded so far
-    // instead of letting the device idle until the end of the pardo.  Batches therefore grow with the time the device
-    // needs for the previous one (large blocks -> large batches, small blocks -> frequent flushes).
-    if (!g.dry && g.idle_flush_ops && g.ops.size() >= g.idle_flush_ops && (g.ops.size() & 511) == 0) {
-        const cudaError_t q = cudaStreamQuery(ctx().stream);
-        if (q == cudaSuccess) return wl_flush();
-        if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+    // Overlap recording with execution: hand the device what has been recorded so far instead of letting it idle until
+    // the end of the pardo.  With the replay cache the cut points must not depend on timing (a stream is recognised only
+    // if it is cut at the same ops every iteration): a flush every 4 x idle_flush_ops recorded ops.  Without the cache:
+    // whenever the compute stream has drained and at least idle_flush_ops ops are pending.
+    if (!g.dry && g.idle_flush_ops) {
+        if (g_replay_enabled) {
+            if (g.ops.size() >= 4 * g.idle_flush_ops) return wl_flush();
+        } else if (g.ops.size() >= g.idle_flush_ops && (g.ops.size() & 511) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx().stream);
+            if (q == cudaSuccess) return wl_flush();
+            if (q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery", __FILE__, __LINE__);
+        }
     }
     return SIPGPU_OK;
 }

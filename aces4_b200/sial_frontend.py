@@ -24,6 +24,10 @@ Supported statements (case-insensitive keywords, `#` comments):
     execute energy_denominator_rhf T[...] fock      sip_barrier | server_barrier      collective s += t
     proc NAME ... endproc NAME        call NAME        allocate L[a,*,b,j] / deallocate L[a,*,b,j]
     set_persistent A "label"          restore_persistent A "label"       (arrays and scalars)
+    if X <op> Y ... endif (X, Y: ints, scalars, indices, numbers, `(int)` / `(scalar)` casts)      exit (leaves the innermost do)
+    int n      n = n + 1      x = (int)Xijk[NT,i7]      t = a/(scalar)n      (host arithmetic on ints / scalars)
+    index ii = 1: naocc (simple index: integer loop variable; a block dimension it labels has extent 1)
+    execute stripi X[..] Y[..]      execute set_ijk_aab Xijk      execute return_sval Xijk[Nt,i7] s      print / create: ignored
 Indices are declared `moaindex i = baocc: eaocc` / `moaindex a = bavirt: eavirt` / `moaindex p = baocc: eavirt` /
 `aoindex mu = 1: norb`; arrays `served|distributed|temp|local|static NAME[i,j,..]`, scalars `scalar s`.  Anything else
 raises SialSyntaxError.
@@ -65,11 +69,89 @@ def _labels(s):
     return tuple(x.strip() for x in s.split(",") if x.strip())
 
 
+_TOK = re.compile(r"\s*(?:(\d+\.?\d*(?:[ed][-+]?\d+)?|\.\d+)|([a-z_]\w*)|(\[[^\]]*\])|(.))", re.I)
+
+
+def parse_expr(text):
+    """int / scalar expression -> AST: ('num', v) | ('var', name) | ('elem', array, labels) | ('cast', 'int'|'scalar', e) |
+    ('neg', e) | (op, l, r) with op in + - * /   (SIAL casts are prefix: `(int)Xijk[NT,i7]`, `tcomb/(scalar)nsects`)"""
+    toks = []
+    for num, name, br, other in _TOK.findall(text.strip().lower()):
+        if num:
+            toks.append(("num", float(num.replace("d", "e"))))
+        elif name:
+            toks.append(("name", name))
+        elif br:
+            toks.append(("br", _labels(br[1:-1])))
+        elif other.strip():
+            toks.append(("op", other))
+    pos = [0]
+
+    def peek():
+        return toks[pos[0]] if pos[0] < len(toks) else (None, None)
+
+    def take():
+        pos[0] += 1
+        return toks[pos[0] - 1]
+
+    def primary():
+        k, v = take() if pos[0] < len(toks) else (None, None)
+        if k == "num":
+            return ("num", v)
+        if k == "name":
+            if peek()[0] == "br":
+                return ("elem", v, take()[1])
+            return ("var", v)
+        if (k, v) == ("op", "-"):
+            return ("neg", primary())
+        if (k, v) == ("op", "("):
+            if peek() in (("name", "int"), ("name", "scalar")) and pos[0] + 1 < len(toks) and toks[pos[0] + 1] == ("op", ")"):
+                kind = take()[1]
+                take()
+                return ("cast", kind, primary())
+            e = expr()
+            if take() != ("op", ")"):
+                raise SialSyntaxError("unbalanced parenthesis in expression")
+            return e
+        raise SialSyntaxError(f"bad expression {text!r}")
+
+    def term():
+        e = primary()
+        while peek() in (("op", "*"), ("op", "/")):
+            op = take()[1]
+            e = (op, e, primary())
+        return e
+
+    def expr():
+        e = term()
+        while peek() in (("op", "+"), ("op", "-")):
+            op = take()[1]
+            e = (op, e, term())
+        return e
+
+    out = expr()
+    if pos[0] != len(toks):
+        raise SialSyntaxError(f"trailing tokens in expression {text!r}")
+    return out
+
+
+class _Exit(Exception):
+    """`exit`: leaves the innermost do loop (interpreter.cpp handles it as a jump to the loop's end)"""
+
+
+class _Ones:
+    """segment extents of a simple index: every value labels a block dimension of extent 1"""
+
+    def __getitem__(self, i):
+        return 1
+
+
 class Program:
     """Parsed SIAL fragment: declarations + a statement tree."""
 
     def __init__(self, text):
         self.index_kind, self.arrays, self.scalars = {}, {}, set()
+        self.simple_range = {}    # simple index name -> (lo, hi) as written (numbers or predefined constants such as naocc)
         self.procs = {}           # name -> statement list (textual order kept: dicts are ordered)
         main = []
         stack = [main]
@@ -98,12 +180,12 @@ class Program:
                     raise SialSyntaxError(f"line {ln}: misplaced endproc")
                 in_proc = None
                 stack = [main]
-            elif st[0] in ("pardo", "do"):
+            elif st[0] in ("pardo", "do", "if"):
                 st = st + ([],)
                 stack[-1].append(st)
                 stack.append(st[-1])
                 opens.append(st[0])
-            elif st[0] in ("endpardo", "enddo"):
+            elif st[0] in ("endpardo", "enddo", "endif"):
                 if not opens or opens.pop() != st[0][3:]:
                     raise SialSyntaxError(f"line {ln}: unbalanced {st[0]}")
                 stack.pop()
@@ -116,8 +198,27 @@ class Program:
 
     def _parse(self, line, low, tok):
         kw = tok[0]
-        if kw in ("sial", "endsial", "import"):
+        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete"):
+            return None           # arrays exist (zero) from the start; nothing is printed
+        if kw == "index":
+            m = re.match(r"index\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line, re.I)
+            if not m:
+                raise SialSyntaxError("bad simple index declaration")
+            self.index_kind[m.group(1)] = "s"
+            self.simple_range[m.group(1)] = (m.group(2).lower(), m.group(3).lower())
             return None
+        if kw == "int":
+            self.scalars.add(tok[1])
+            return None
+        if kw == "if":
+            m = re.match(r"if\s+(.+?)\s*(<=|>=|==|!=|<|>)\s*(.+)$", low)
+            if not m:
+                raise SialSyntaxError("unsupported if condition")
+            return ("if", parse_expr(m.group(1)), m.group(2), parse_expr(m.group(3)))
+        if kw == "endif":
+            return ("endif",)
+        if kw == "exit":
+            return ("exit",)
         if kw in ("proc", "call"):
             if len(tok) != 2:
                 raise SialSyntaxError("bad " + kw)
@@ -216,13 +317,60 @@ class Program:
                         float(rhs) * (-1.0 if op == "-=" else 1.0))
             if re.match(r"\w+$", rhs) and op in ("+=", "-=", "="):
                 return ("sadd" if op != "=" else "scopy", name, rhs.lower(), -1.0 if op == "-=" else 1.0)
+        m = re.match(r"(\w+)\s*(\+=|-=|\*=|/=|=)\s*(.+)$", line)
+        if m:   # host arithmetic on ints / scalars: counters, casts, elements of index tables
+            return ("sexpr", m.group(1).lower(), m.group(2), parse_expr(m.group(3).lower()))
         raise SialSyntaxError("unsupported statement")
+
+
+def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5):
+    """The batch table of the reference's (T) programs (super_instructions/qm/qm-generic/set_ijk_aab.F:60-160): every
+    occupied segment is cut into pieces of at most `maxi` orbitals (maxi shrinks by one for every occupied segment that is
+    not longer than it, as in the Fortran), and row Nt = (segment i, first orbital, last orbital, segment j >= i, first,
+    last, segment k) for every pair of pieces and every k; the row after the last one is all -1.  Host-only control logic
+    (which loop iterations exist), not arithmetic.  Returns {(Nt, column): value}, 1-based."""
+    nseg = eaocc - baocc + 1
+    for i in range(1, nseg + 1):
+        if maxi >= moa_seg_ranges[baocc + i - 2]:
+            maxi -= 1
+    start, end = [0] * (nseg + 1), [0] * (nseg + 1)
+    start[1], end[1] = 1, moa_seg_ranges[0]
+    for i in range(2, baocc + 1):
+        start[1] = end[1] + 1
+        end[1] = start[1] + moa_seg_ranges[i - 1] - 1
+    for i in range(2, nseg + 1):
+        start[i] = end[i - 1] + 1
+        end[i] = start[i] + moa_seg_ranges[baocc + i - 2] - 1
+    pieces = {}
+    for i in range(1, nseg + 1):
+        n = end[i] - start[i] + 1
+        np_ = n // maxi + (1 if maxi * (n // maxi) < n else 0)
+        sizes = [n // np_] * (np_ - 1)
+        sizes.append(n - sum(sizes))
+        pieces[i] = sizes
+    table, nt = {}, 0
+    ie = start[1] - 1
+    for i in range(1, nseg + 1):
+        for ni in pieces[i]:
+            is_, ie = ie + 1, ie + ni
+            je = start[1] - 1
+            for j in range(1, nseg + 1):
+                for nj in pieces[j]:
+                    js, je = je + 1, je + nj
+                    if i <= j:
+                        for k in range(1, nseg + 1):
+                            nt += 1
+                            for col, v in enumerate((i, is_, ie, j, js, je, k), 1):
+                                table[(nt, col)] = float(v)
+    for col in range(1, 8):
+        table[(nt + 1, col)] = -1.0
+    return table
 
 
 class Walker:
     """Executes a Program against a backend: the per-block call stream of one worker."""
 
-    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None):
+    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None):
         """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v.
         index_base: {'o': baocc - 1, 'v': bavirt - 1, ...}: what to add to a loop's segment number to get the absolute
         segment number of its index type -- the index values a super-instruction receives (the reference's loops run
@@ -232,6 +380,9 @@ class Walker:
         self.segs = dict(segs)
         if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
             self.segs["p"] = list(self.segs["o"]) + list(self.segs["v"])
+        self.segs["s"] = _Ones()
+        self.constants = {k.lower(): int(v) for k, v in (constants or {}).items()}   # predefined ints: naocc, ...
+        self.tables = {}         # static arrays over simple indices only (index tables such as Xijk): {(i, j): value}
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
         self.locals = {}         # allocated local arrays: name -> {segs: handle}
@@ -248,6 +399,48 @@ class Walker:
 
     def _nseg(self, lab):
         return len(self.segs[self._kind(lab)])
+
+    def _range(self, lab):
+        """the values a loop over `lab` takes: segment numbers 1..nseg, or lo..hi of a simple index"""
+        if self._kind(lab) != "s":
+            return range(1, self._nseg(lab) + 1)
+        lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[lab])
+        return range(lo, hi + 1)
+
+    def _core(self, labs):
+        """labels without the simple indices (their dimensions have extent 1 and do not affect the layout)"""
+        kinds = self.p.index_kind
+        return tuple(lab for lab in labs if kinds.get(lab) != "s")
+
+    def _is_table(self, name):
+        a = self.p.arrays.get(name)
+        return a is not None and a[0] == "static" and all(self.p.index_kind.get(d) == "s" for d in a[1])
+
+    def _eval(self, e):
+        """host value of an int / scalar expression (parse_expr AST)"""
+        k = e[0]
+        if k == "num":
+            return e[1]
+        if k == "var":
+            n = e[1]
+            if n in self.idx:
+                return self.idx[n]
+            if n in self.scalars:
+                return self.be.value(self.scalars[n])
+            if n in self.constants:
+                return self.constants[n]
+            raise SialSyntaxError(f"undefined name {n} in expression")
+        if k == "elem":
+            if not self._is_table(e[1]):
+                raise SialSyntaxError(f"{e[1]}: only static arrays over simple indices can be read as numbers")
+            return self.tables.get(e[1], {}).get(tuple(self.idx[x] for x in e[2]), 0.0)
+        if k == "cast":
+            v = self._eval(e[2])
+            return float(int(v)) if e[1] == "int" else float(v)
+        if k == "neg":
+            return -self._eval(e[1])
+        a, b = self._eval(e[1]), self._eval(e[2])
+        return a + b if k == "+" else a - b if k == "-" else a * b if k == "*" else a / b
 
     def _segs_of(self, labs):
         idx = self.idx
@@ -275,6 +468,9 @@ class Walker:
                 dk, k = self._kind(d), self._kind(lab)
                 if dk == "p" and k == "v":
                     plan.append((lab, len(self.segs["o"])))
+                elif dk == "s" and k == "s":       # block coordinate = value - first value + 1
+                    lo = self.p.simple_range[d][0]
+                    plan.append((lab, 1 - (int(lo) if lo.isdigit() else self.constants[lo])))
                 elif dk == k or (dk == "p" and k == "o"):
                     plan.append((lab, 0))
                 else:
@@ -340,15 +536,15 @@ class Walker:
         return True
 
     def _x_where(self, a, op, b):
-        va = self.idx[a] if a in self.idx else int(a)
-        vb = self.idx[b] if b in self.idx else int(b)
+        va = self.idx[a] if a in self.idx else int(a) if a.isdigit() else self._eval(("var", a))
+        vb = self.idx[b] if b in self.idx else int(b) if b.isdigit() else self._eval(("var", b))
         return {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]
 
     def _x_pardo(self, labs, body):
         wheres = [s for s in body if s[0] == "where"]
         rest = [s for s in body if s[0] != "where"]
         self.be.begin_pardo()
-        ranges = [range(1, self._nseg(lab) + 1) for lab in reversed(labs)]   # first index fastest
+        ranges = [self._range(lab) for lab in reversed(labs)]   # first index fastest
         for combo in itertools.product(*ranges):
             for lab, v in zip(reversed(labs), combo):
                 self.idx[lab] = v
@@ -366,23 +562,50 @@ class Walker:
 
     def _x_do(self, labs, body):
         lab = labs[0]
-        for v in range(1, self._nseg(lab) + 1):
+        for v in self._range(lab):
             self.idx[lab] = v
             self.scopes.append({})
-            ok = self._block(body)
+            try:
+                self._block(body)      # a false `where` skips the rest of this iteration
+            except _Exit:
+                self._leave_scope()
+                break
             self._leave_scope()
-            if ok is False:
-                continue
         del self.idx[lab]
 
+    def _x_if(self, lhs, op, rhs, body):
+        va, vb = self._eval(lhs), self._eval(rhs)
+        if {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]:
+            return self._block(body)   # a false `where` inside propagates
+
+    def _x_exit(self):
+        raise _Exit()
+
+    def _x_sexpr(self, name, op, e):
+        v = self._eval(e)
+        if op != "=":
+            cur = self.be.value(self.scalars[name])
+            v = cur + v if op == "+=" else cur - v if op == "-=" else cur * v if op == "*=" else cur / v
+        self.scalars[name] = self.be.scalar_set(self.scalars.get(name), v)
+
     def _x_allocate(self, name, labs):
-        if self.p.arrays.get(name, ("",))[0] != "local" or name in self.locals:
-            raise SialSyntaxError(f"allocate of {name}: not a (free) local array")
+        if self.p.arrays.get(name, ("",))[0] != "local":
+            raise SialSyntaxError(f"allocate of {name}: not a local array")
+        if "*" not in labs:      # one block, named by the current index values (rccsdpt_aab.sialx:2447): created on first touch
+            self.locals.setdefault(name, {})
+            return
+        if name in self.locals:
+            raise SialSyntaxError(f"allocate of {name}: already allocated")
         self.locals[name] = {}
 
     def _x_deallocate(self, name, labs):
         if name not in self.locals:
             raise SialSyntaxError(f"deallocate of {name}: not allocated")
+        if "*" not in labs:
+            h = self.locals[name].pop(self._segs_of(labs), None)
+            if h is not None:
+                self.be.free(h)
+            return
         for h in self.locals.pop(name).values():
             self.be.free(h)
 
@@ -419,18 +642,28 @@ class Walker:
     def _x_put_init(self, arr, alabs, v):
         self.be.put_initialize(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
 
+    def _views(self, d, labs, s, slabs):
+        """Blocks whose labels differ only by simple indices (extent-1 dimensions, e.g. t1ppp[a2,i1,a] = tppps[a2,i1,a,jj])
+        are the same run of elements: compare / permute on the labels that carry data."""
+        cd, cs = self._core(labs), self._core(slabs)
+        if cd != tuple(labs) or cs != tuple(slabs):
+            d = self.be.reshaped(d, self._shape(cd))
+            s = self.be.reshaped(s, self._shape(cs))
+        return d, cd, s, cs
+
     def _x_assign(self, name, labs, src, slabs, _sign):
         s, sl = self._read(src, slabs)
-        self.be.copy(self._write(name, labs), labs, s, sl)
+        d, dl, s, sl = self._views(self._write(name, labs), labs, s, sl)
+        self.be.copy(d, dl, s, sl)
 
     def _x_add(self, name, labs, src, slabs, sign):
         s, sl = self._read(src, slabs)
-        d = self._write(name, labs)
-        if tuple(sl) == tuple(labs):
+        d, dl, s, sl = self._views(self._write(name, labs), labs, s, sl)
+        if tuple(sl) == tuple(dl):
             self.be.axpy(d, s, sign)
         else:   # handle_block_add: permute the rhs into a temp first (interpreter.cpp:1874-1997)
-            t = self.be.new_block(self._shape(labs))
-            self.be.copy(t, labs, s, sl)
+            t = self.be.new_block(self._shape(dl))
+            self.be.copy(t, dl, s, sl)
             self.be.axpy(d, t, sign)
             self.be.free(t)
 
@@ -446,6 +679,16 @@ class Walker:
         (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._array_segs(arr, alabs), s)
 
     def _x_execute(self, fname, args, bare):
+        if fname in ("compute_int_scratchmem", "print_block", "print_scalar"):
+            return                                   # integral-engine scratch sizing / output: nothing on this path
+        if fname == "set_ijk_aab":                   # occupied-triplet batches of the (T) programs: host logic
+            self.tables[bare[0]] = set_ijk_aab(self.be.moa_seg_ranges(), self.constants["baocc"], self.constants["eaocc"])
+            return
+        if fname == "return_sval" and args and self._is_table(args[0][0]):
+            name, labs = args[0]
+            v = self.tables.get(name, {}).get(tuple(self.idx[x] for x in labs), 0.0)
+            self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), v)
+            return
         blocks = [self._read(n, labs)[0] if self._is_remote(n) else self._write(n, labs) for n, labs in args]
         kinds = [[self._kind(x) for x in labs] for _, labs in args]
         segs = [tuple(self.idx[x] + self.index_base.get(k, 0) for x, k in zip(labs, ks))
@@ -518,6 +761,7 @@ class DeviceBackend:
         self.rank, self.world = rank, world
         self._barrier, self._allreduce = barrier, allreduce
         self.fock = None    # resident Fock diagonal block for `execute energy_denominator_rhf` (set by the caller)
+        self.seg_ranges = []  # predefined int array moa_seg_ranges (set by the caller next to sipgpu_set_predefined_int_array)
         self.cache = {}     # remote blocks fetched since the last barrier (sial_ops_parallel.cpp:41-47)
         self.stats = []     # work-list statistics per pardo
 
@@ -609,8 +853,18 @@ class DeviceBackend:
     def execute(self, fname, blocks, segs, kinds, bare):
         if fname == "energy_denominator_rhf":
             self.api.si_energy_denominator_rhf(blocks[0], segs[0], self.fock)
+        elif fname == "stripi":
+            if self.api.si_stripi(blocks[0], segs[0], blocks[1], segs[1]) != 0:
+                raise SialSyntaxError("stripi: " + self.api.lib().sipgpu_last_error().decode(errors="replace"))
         else:
             raise SialSyntaxError(f"super-instruction {fname} is not on the device path")
+
+    def reshaped(self, b, shape):
+        """the same elements under other extents (extent-1 dimensions of simple indices dropped or added)"""
+        return b if tuple(b.shape) == tuple(shape) else self.api.DeviceBlock(shape, ptr=b.ptr, owned=False)
+
+    def moa_seg_ranges(self):
+        return list(self.seg_ranges)
 
     def dot(self, L, llabs, R, rlabs, prev):
         acc = prev if isinstance(prev, self.api.DeviceBlock) else self.api.DeviceBlock((1,), zero=True)

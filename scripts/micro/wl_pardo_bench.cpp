@@ -193,6 +193,7 @@ int main(int argc, char** argv) {
     double best[2] = {1e30, 1e30}, sum[2] = {0, 0};
     long long launches[2] = {0, 0};
     long long st[9] = {0};
+    std::vector<long long> replays(reps + 1, 0);
     for (int mode = 0; mode < 2; ++mode)
         for (int r = 0; r < reps + 1; ++r) {
             CK(sipgpu_array_fill_local(T2new.h, 0.0));
@@ -208,6 +209,7 @@ int main(int argc, char** argv) {
                     long long s9[9];
                     CK(sipgpu_wl_stats(s9));
                     for (int k = 0; k < 9; ++k) acc[k] += s9[k];
+                    replays[r] += sipgpu_wl_replays();
                 }
             }
             CK(sipgpu_sync());
@@ -221,8 +223,8 @@ int main(int argc, char** argv) {
            "\"flops\": %.6e, \"op_at_a_time\": {\"seconds\": %.6f, \"tflops\": %.3f, \"kernel_launches\": %lld}, "
            "\"recorded\": {\"seconds\": %.6f, \"tflops\": %.3f, \"kernel_launches\": %lld, \"ops_recorded\": %lld, "
            "\"ops_scheduled\": %lld, \"levels\": %lld, \"fused_accumulates\": %lld, \"chains\": %lld, \"chain_pairs\": %lld, "
-           "\"temps_elided\": %lld, \"flushes\": %lld}, \"speedup\": %.3f, \"t2new_norm2_rel_diff\": %.3e}\n",
+           "\"temps_elided\": %lld, \"flushes\": %lld, \"flushes_replayed_last_rep\": %lld}, \"speedup\": %.3f, \"t2new_norm2_rel_diff\": %.3e}\n",
            no, so, nv, sv, flops, best[0], flops / best[0] / 1e12, launches[0], best[1], flops / best[1] / 1e12, launches[1],
-           st[0], st[1], st[2], st[4], st[5], st[6], st[7], st[8], best[0] / best[1], std::fabs(sum[1] - sum[0]) / sum[0]);
+           st[0], st[1], st[2], st[4], st[5], st[6], st[7], st[8], replays[reps], best[0] / best[1], std::fabs(sum[1] - sum[0]) / sum[0]);
     return 0;
 }

@@ -99,8 +99,20 @@ class OracleBackend:
         return self.registry.pop(label)
 
     def execute(self, fname, blocks, segs, kinds, bare):
+        if fname == "stripi":
+            y, ierr = self.o.si_stripi(np.asfortranarray(blocks[0].a), list(segs[0]), blocks[1].a.shape, list(segs[1]), self.ranges)
+            assert ierr == 0, ierr
+            blocks[1].a[...] = y
+            self.calls += 1
+            return
         assert fname == "energy_denominator_rhf"
         assert self.o.si_energy_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, self.ranges) == 0
+
+    def reshaped(self, b, shape):
+        return b if tuple(b.a.shape) == tuple(shape) else HostBlock(b.a.reshape(shape, order="F"))
+
+    def moa_seg_ranges(self):
+        return list(self.ranges)
 
     def dot(self, L, llabs, R, rlabs, prev):
         from aces4_b200.sial_frontend import label_numbers
