@@ -66,7 +66,7 @@ _NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?"
 
 
 def _labels(s):
-    return tuple(x.strip() for x in s.split(",") if x.strip())
+    return tuple(x.strip().lower() for x in s.split(",") if x.strip())   # SIAL names are case-insensitive
 
 
 _TOK = re.compile(r"\s*(?:(\d+\.?\d*(?:[ed][-+]?\d+)?|\.\d+)|([a-z_]\w*)|(\[[^\]]*\])|(.))", re.I)
@@ -204,8 +204,8 @@ class Program:
             m = re.match(r"index\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line, re.I)
             if not m:
                 raise SialSyntaxError("bad simple index declaration")
-            self.index_kind[m.group(1)] = "s"
-            self.simple_range[m.group(1)] = (m.group(2).lower(), m.group(3).lower())
+            self.index_kind[m.group(1).lower()] = "s"
+            self.simple_range[m.group(1).lower()] = (m.group(2).lower(), m.group(3).lower())
             return None
         if kw == "int":
             self.scalars.add(tok[1])
@@ -232,7 +232,7 @@ class Program:
             kind = _KIND_BY_RANGE.get((m.group(2).lower(), m.group(3).lower()))
             if kind is None:
                 raise SialSyntaxError("unsupported index range")
-            self.index_kind[m.group(1)] = kind
+            self.index_kind[m.group(1).lower()] = kind
             return None
         if kw in ("served", "distributed", "temp", "local", "static"):
             m = re.match(r"\w+\s+" + _REF, line)
@@ -323,12 +323,13 @@ class Program:
         raise SialSyntaxError("unsupported statement")
 
 
-def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5):
+def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5, ordered_k=False):
     """The batch table of the reference's (T) programs (super_instructions/qm/qm-generic/set_ijk_aab.F:60-160): every
     occupied segment is cut into pieces of at most `maxi` orbitals (maxi shrinks by one for every occupied segment that is
     not longer than it, as in the Fortran), and row Nt = (segment i, first orbital, last orbital, segment j >= i, first,
     last, segment k) for every pair of pieces and every k; the row after the last one is all -1.  Host-only control logic
-    (which loop iterations exist), not arithmetic.  Returns {(Nt, column): value}, 1-based."""
+    (which loop iterations exist), not arithmetic.  ordered_k: set_ijk_aaa.F, the same table restricted to j <= k.
+    Returns {(Nt, column): value}, 1-based."""
     nseg = eaocc - baocc + 1
     for i in range(1, nseg + 1):
         if maxi >= moa_seg_ranges[baocc + i - 2]:
@@ -359,6 +360,8 @@ def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5):
                     js, je = je + 1, je + nj
                     if i <= j:
                         for k in range(1, nseg + 1):
+                            if ordered_k and j > k:     # set_ijk_aaa.F:99: the AAA combination takes i <= j <= k only
+                                continue
                             nt += 1
                             for col, v in enumerate((i, is_, ie, j, js, je, k), 1):
                                 table[(nt, col)] = float(v)
@@ -386,7 +389,7 @@ class Walker:
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
         self.locals = {}         # allocated local arrays: name -> {segs: handle}
-        self._aseg_plan, self._ext_of = {}, {}   # memoised label resolution (per distinct reference in the text)
+        self._aseg_plan, self._ext_of, self._segkey_plan = {}, {}, {}   # memoised label resolution (per distinct reference in the text)
         self.iteration = 0       # pardo iteration counter of the current barrier section
         self.scalars = {s: 0.0 for s in program.scalars}
 
@@ -443,8 +446,15 @@ class Walker:
         return a + b if k == "+" else a - b if k == "-" else a * b if k == "*" else a / b
 
     def _segs_of(self, labs):
+        """identity of a temp / local block: ABSOLUTE segment numbers, as in the SIP (a block of `tpp[p,p2]` addressed as
+        tpp[a,a2] and as tpp[b,k1] must not be confused when the loop values coincide: a virtual segment number counts
+        on from the occupied ones; AO and simple indices live in ranges of their own)"""
+        plan = self._segkey_plan.get(labs)
+        if plan is None:
+            base = {"o": 0, "p": 0, "v": len(self.segs.get("o", ())), "ao": 1 << 20, "s": 1 << 21}
+            plan = self._segkey_plan[labs] = [(lab, base.get(self._kind(lab), 0)) for lab in labs]
         idx = self.idx
-        return tuple(idx[lab] for lab in labs)
+        return tuple(idx[lab] + b for lab, b in plan)
 
     def _shape(self, labs):
         ext = self._ext_of.get(labs)
@@ -681,8 +691,9 @@ class Walker:
     def _x_execute(self, fname, args, bare):
         if fname in ("compute_int_scratchmem", "print_block", "print_scalar"):
             return                                   # integral-engine scratch sizing / output: nothing on this path
-        if fname == "set_ijk_aab":                   # occupied-triplet batches of the (T) programs: host logic
-            self.tables[bare[0]] = set_ijk_aab(self.be.moa_seg_ranges(), self.constants["baocc"], self.constants["eaocc"])
+        if fname in ("set_ijk_aab", "set_ijk_aaa"):  # occupied-triplet batches of the (T) programs: host logic
+            self.tables[bare[0]] = set_ijk_aab(self.be.moa_seg_ranges(), self.constants["baocc"], self.constants["eaocc"],
+                                               ordered_k=fname == "set_ijk_aaa")
             return
         if fname == "return_sval" and args and self._is_table(args[0][0]):
             name, labs = args[0]

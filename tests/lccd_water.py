@@ -149,3 +149,49 @@ def dense_ca(inp):
     """the whole static array ca[mu,p] (norb x active MOs) and the segment extents of its two dimensions"""
     seg = [inp["segs"]["ao"], inp["segs"]["p"]]
     return qm.join_blocks(inp["arrays"]["ca"], seg), seg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own (T) programs (tests/golden/rccsdpt_aaa_program.sialx / rccsdpt_aab_program.sialx, generated from
+# src/sialx/qm/cc/rccsdpt_aaa.sialx / rccsdpt_aab.sialx by scripts/make_ccsdpt_aab_golden.py)
+PROGRAM_PT_AAA = open(os.path.join(HERE, "golden", "rccsdpt_aaa_program.sialx")).read()
+PROGRAM_PT_AAB = open(os.path.join(HERE, "golden", "rccsdpt_aab_program.sialx")).read()
+# VSaaai[a2,a,a1,i] = Vaaai[a2,a,a1,i] - Vaaai[a1,a,a2,i]: the last step of TRAN_TRAN4 (rccsdpt_aab.sialx:431-439), whose
+# transformation procedures the generated programs replace by restore_persistent of their results
+VSAAAI_FRAGMENT = """
+moaindex a = bavirt: eavirt
+moaindex a1 = bavirt: eavirt
+moaindex a2 = bavirt: eavirt
+moaindex i = baocc: eaocc
+served Vaaai[a,a1,a2,i]
+served VSaaai[a,a1,a2,i]
+temp t[a,a1,a2,i]
+temp t1[a,a1,a2,i]
+pardo a2, a, a1, i
+   request Vaaai[a2,a,a1,i]
+   request Vaaai[a1,a,a2,i]
+   t[a2,a,a1,i]  = Vaaai[a2,a,a1,i]
+   t1[a2,a,a1,i] = Vaaai[a1,a,a2,i]
+   t[a2,a,a1,i] -= t1[a2,a,a1,i]
+   prepare VSaaai[a2,a,a1,i] = t[a2,a,a1,i]
+endpardo a2, a, a1, i
+server_barrier
+"""
+# persistence labels the (T) programs restore -> array names of the CCSD / transformation programs that produce them
+PT_LABELS = {"t1a_old": "t1a_old", "T2old_aa": "t2old_aa", "T2old_ab": "t2old_ab", "Vpiqj": "vpiqj", "VSpipi": "vspipi",
+             "Vaaai": "vaaai", "VSaaai": "vsaaai"}
+# label -> name of the array that holds it inside the (T) programs (what to persist again for the program that follows)
+PT_HOLDERS = {"t1a_old": "t1a_old", "T2old_aa": "tsaiai", "T2old_ab": "t2aiai", "Vpiqj": "vpiqj", "VSpipi": "vspipi",
+              "Vaaai": "vaaai", "VSaaai": "vsaaai"}
+
+
+def pt_constants(inp):
+    """predefined ints the (T) programs read: naocc = number of occupied ORBITALS (the range of the simple indices ii, jj),
+    baocc / eaocc = first / last occupied segment of moa_seg_ranges"""
+    return {"naocc": sum(inp["segs"]["o"]), "baocc": inp["index_base"]["o"] + 1,
+            "eaocc": inp["index_base"]["o"] + len(inp["segs"]["o"])}
+
+
+def pt_array_kinds(program):
+    """index kinds of every served / distributed array a (T) program declares ('s' = simple index: blocks of extent 1)"""
+    return {n: tuple(program.index_kind[d] for d in decl) for n, (k, decl) in program.arrays.items() if k in ("served", "distributed")}

