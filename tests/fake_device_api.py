@@ -36,8 +36,10 @@ class FakeApi:
         api = self
 
         class DeviceBlock:
-            def __init__(self, shape, zero=False, a=None):
+            def __init__(self, shape, zero=False, a=None, ptr=None, owned=True):
                 self.shape = tuple(int(x) for x in shape)
+                if ptr is not None:      # a view of an existing block under other extents (same elements)
+                    a = api._by_ptr[ptr].a.reshape(self.shape, order="F")
                 self.a = a if a is not None else np.full(self.shape, 0.0 if zero else np.nan, order="F")
                 self.size, self.rank = int(self.a.size), len(self.shape)
                 self.ptr = next(api._ptr)
@@ -196,6 +198,13 @@ class FakeApi:
         out.a[...] = res.reshape(out.a.shape, order="F")
         self._launches += 1
         return out
+
+    def si_stripi(self, x, iv0, y, iv1):
+        self._launches += 1
+        out, ierr = self.o.si_stripi(np.asfortranarray(x.a), list(iv0), y.a.shape, list(iv1), self._moa)
+        if ierr == 0:
+            y.a[...] = out
+        return ierr
 
     def si_energy_denominator_rhf(self, block, index_values, fock):
         self._launches += 1

@@ -47,6 +47,11 @@ def test_static_in_place_device_test_body_on_the_fake_api(oracle):
     dev.test_static_array_blocks_read_in_place_through_the_programs(FakeApi(oracle))
 
 
+def test_reference_triples_programs_device_test_body_on_the_fake_api(oracle):
+    import test_gpu_z_ccsdpt_reference as pt
+    pt.test_reference_triples_programs_on_the_device(FakeApi(oracle), "hf_dat", True)
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

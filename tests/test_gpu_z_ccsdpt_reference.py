@@ -61,7 +61,7 @@ def run_pt_on_device(sip, case, which, record):
         sip.persist_scalar("totenerg", 0.0)
         sip.persist_scalar("ccsd_energy", 0.0)
         prog = Program(lw.PROGRAM_PT_AAA if name == "aaa" else lw.PROGRAM_PT_AAB)
-        used = {n.lower() for n in re.findall(r"(?i)\\b(?:request|get|put|prepare|restore_persistent)\\s+([a-z_]\\w*)",
+        used = {n.lower() for n in re.findall(r"(?i)\b(?:request|get|put|prepare|restore_persistent)\s+([a-z_]\w*)",
                                                            lw.PROGRAM_PT_AAA if name == "aaa" else lw.PROGRAM_PT_AAB)}
         parr = {n: sip.DistArray([seg_ext[k] for k in kinds]) for n, kinds in lw.pt_array_kinds(prog).items()
                 if n in used and all(k in seg_ext for k in kinds)}
