@@ -27,6 +27,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libaces4_ref_on_sipgpu.so")
 _SO_L1 = os.path.join(_HERE, "_ref", "libaces4_ref_l1_on_sipgpu.so")   # + HAVE_CUDA: the device half of sip::Block (level 1)
+_SO_L2 = os.path.join(_HERE, "_ref", "libaces4_ref_l2_on_sipgpu.so")   # + include/sial_ops_device_aces4.hpp behind the reference's SialOps signatures (level 2)
 REFERENCE_ROOT = os.environ.get("ACES4_REFERENCE", "/root/reference")
 
 
@@ -39,8 +40,8 @@ def build(force=False):
     product = os.path.join(_HERE, "..", "aces4_b200", "lib", "libsipgpu.so")
     shim = os.path.join(_HERE, "ref_shim", "aces4_ref_shim.cpp")
     if have_src and os.path.exists(product) and (force or not os.path.exists(_SO)
-                                                 or os.path.getmtime(_SO) < os.path.getmtime(shim)):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref_on_sipgpu", "ref_l1", f"REF={REFERENCE_ROOT}"])
+                                                 or os.path.getmtime(_SO) < os.path.getmtime(shim) or not os.path.exists(_SO_L2)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref_on_sipgpu", "ref_l1", "ref_l2", f"REF={REFERENCE_ROOT}"])
     return _SO if os.path.exists(_SO) and os.path.exists(_SO_L1) else None
 
 
@@ -49,6 +50,25 @@ def available():
         return build() is not None
     except Exception:
         return os.path.exists(_SO)
+
+
+def run_level2_selftest(nseg=3, seg=4, reps=5, timeout=120):
+    """INTEGRATION level 2 in a child process: SialOpsDeviceAces4 (reference signatures: BlockId&, Block::BlockPtr, pc) driven
+    with real sip::BlockId / sip::Block objects.  Returns (blocks checked, mismatching elements, collective_sum seen by the
+    scalar sink, read-back after put_replace / increment / scale) or raises WorkerFailed with the library's message."""
+    if build() is None or not os.path.exists(_SO_L2):
+        raise WorkerFailed("oracle/_ref/libaces4_ref_l2_on_sipgpu.so is not built and the reference checkout is absent")
+    code = ("import ctypes as C, sys\n"
+            f"L = C.CDLL({_SO_L2!r})\n"
+            "L.aces4ref_l2_last_error.restype = C.c_char_p\n"
+            "out = (C.c_double * 4)()\n"
+            f"rc = L.aces4ref_l2_selftest({int(nseg)}, {int(seg)}, {int(reps)}, out)\n"
+            "print('L2', rc, *list(out)) if rc == 0 else print('L2ERR', L.aces4ref_l2_last_error().decode())\n")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("L2")]
+    if p.returncode != 0 or not line or line[-1].startswith("L2ERR"):
+        raise WorkerFailed(f"exit {p.returncode}: {(line[-1] if line else p.stderr or p.stdout)[-600:]}")
+    return tuple(float(x) for x in line[-1].split()[2:])
 
 
 def seeded(shape, seed):

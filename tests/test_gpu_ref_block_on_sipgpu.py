@@ -79,3 +79,18 @@ def test_level1_reference_gpu_block_methods_run_on_the_cuda_library(rb):
         assert np.array_equal(y[0], np.zeros_like(y[0]))                       # _gpu_allocate hands out zero-filled blocks
         assert np.array_equal(y[1], np.full_like(y[1], c["fill"] * c["scale"]))
         assert np.array_equal(y[2], y[1])
+
+
+def test_level2_reference_signatures_put_get_closed_forms_on_the_device(rb):
+    """INTEGRATION.md level 2, executed: SialOpsDeviceAces4 (include/sial_ops_device_aces4.hpp: the reference's SialOpsParallel
+    method signatures -- BlockId&, Block::BlockPtr, pc) driven with real sip::BlockId and sip::Block objects (reference code,
+    device half on libsipgpu's `_gpu_*`) the way interpreter.cpp:611-655 drives `sial_ops_`: the closed forms of the
+    reference's Sial tests (test/test_sial.cpp: put_accumulate_stress :1072-1113 recorded as one pardo, put_replace / get
+    :282-318,583, put_initialize / increment / scale) read back exactly, collective_sum through the scalar sink."""
+    try:
+        blocks, bad, csum, readback = rb.run_level2_selftest(nseg=3, seg=4, reps=5)
+    except rb.WorkerFailed as e:
+        pytest.fail(f"level-2 adapter failed on libsipgpu.so: {e}")
+    assert blocks == 9 and bad == 0
+    assert csum == 1.25
+    assert readback == (1.0 + 0.5) * 4.0

@@ -74,3 +74,27 @@ def test_level1_interpreter_compiles_against_the_replacement_header(rb):
     inc += ["-I" + os.path.join(src, d) for d in ("core", "cuda", "dynamic_data", "mpi", "setup", "static_data",
                                                    "super_instructions", "tensor_algebra", "worker", ".")]
     subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-w", *inc, os.path.join(src, "worker", "interpreter.cpp")])
+
+
+def test_level2_sial_ops_adapter_compiles_and_links_against_the_reference(rb):
+    """INTEGRATION.md level 2 at link level: include/sial_ops_device_aces4.hpp -- SialOpsDevice behind the reference's
+    SialOpsParallel signatures (sial_ops_parallel.h:47-73: BlockId&, Block::BlockPtr, pc) -- compiles against the reference's
+    block_id.h / block.h (HAVE_CUDA) and links, --no-undefined, against the reference objects and libsipgpu.so."""
+    rb.build()
+    import os
+
+    assert os.path.exists(rb._SO_L2)
+    lib = C.CDLL(rb._SO_L2)
+    assert hasattr(lib, "aces4ref_l2_selftest")
+    needed = subprocess.run(["readelf", "-d", rb._SO_L2], capture_output=True, text=True, check=True).stdout
+    assert "libsipgpu.so" in needed and "liboracle" not in needed
+
+
+def test_level2_without_a_gpu_fails_loudly(rb):
+    import aces4_b200 as s
+
+    if s.api.lib().sipgpu_init(-1) == 0:
+        pytest.skip("a GPU is present: the success path is tests/test_gpu_ref_block_on_sipgpu.py")
+    with pytest.raises(rb.WorkerFailed) as e:
+        rb.run_level2_selftest()
+    assert "no CUDA device" in str(e.value)
