@@ -613,6 +613,20 @@ def dgemm_tn(m, n, k, A, lda, B, ldb, Cblk, ldc, alpha=1.0, beta=0.0):
            "sipgpu_dgemm_tn")
 
 
+def trace(on=True, reset=True):
+    """per-entry-point call counts / host time (sipgpu_trace_*), the counterpart of the reference's Tracer"""
+    lib().sipgpu_trace_enable(1 if on else 0)
+    if reset:
+        lib().sipgpu_trace_reset()
+
+
+def trace_report(cap=256):
+    """[(entry point, calls, host seconds)], most host time first"""
+    names, calls, secs = (C.c_char_p * cap)(), (C.c_longlong * cap)(), (C.c_double * cap)()
+    n = min(cap, lib().sipgpu_trace_report(cap, names, calls, secs))
+    return [(names[i].decode(), int(calls[i]), float(secs[i])) for i in range(n)]
+
+
 def set_tuning(key, value):
     """launch-policy knob (sipgpu.h: sipgpu_set_tuning), e.g. set_tuning("lowint_max_intensity", -1) for the tile kernel only"""
     _check(lib().sipgpu_set_tuning(key.encode(), float(value)), "sipgpu_set_tuning")

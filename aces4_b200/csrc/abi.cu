@@ -489,6 +489,7 @@ extern "C" {
 
 // ------------------------------------------------ boundary 1 ------------------------------------------------
 long long tensor_size_by_shape_(int* num_dim, int* dims, int* ierr) {
+    SIP_TRACE("tensor_size_by_shape_");
     long long sz = 1;
     *ierr = 0;
     if (*num_dim > 0) {
@@ -502,10 +503,12 @@ long long tensor_size_by_shape_(int* num_dim, int* dims, int* ierr) {
 }
 
 void get_contraction_ptrn_(int* drank, int* lrank, int* rrank, int* aces_ptrn, int* my_ptrn, int* ierr) {
+    SIP_TRACE("get_contraction_ptrn_");
     *ierr = get_contraction_ptrn(*drank, *lrank, *rrank, aces_ptrn, my_ptrn);
 }
 
 void tensor_block_init__(int* nthreads, double* tens, int* rank, int* ext, double* val, int* ierr) {
+    SIP_TRACE("tensor_block_init__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = -1; return; }
@@ -518,6 +521,7 @@ void tensor_block_init__(int* nthreads, double* tens, int* rank, int* ext, doubl
 }
 
 void tensor_block_scale__(int* nthreads, double* tens, int* rank, int* ext, double* fac, int* ierr) {
+    SIP_TRACE("tensor_block_scale__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = -1; return; }
@@ -530,6 +534,7 @@ void tensor_block_scale__(int* nthreads, double* tens, int* rank, int* ext, doub
 }
 
 double tensor_block_norm2__(int* nthreads, double* tens, int* rank, int* ext, int* ierr) {
+    SIP_TRACE("tensor_block_norm2__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = -1; return 0.0; }
@@ -544,6 +549,7 @@ double tensor_block_norm2__(int* nthreads, double* tens, int* rank, int* ext, in
 
 void tensor_block_slice__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice, int* slice_ext,
                           int* ext_beg, int* ierr) {
+    SIP_TRACE("tensor_block_slice__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = 1; return; }
@@ -557,6 +563,7 @@ void tensor_block_slice__(int* nthreads, int* rank, double* tens, int* tens_ext,
 
 void tensor_block_insert__(int* nthreads, int* rank, double* tens, int* tens_ext, double* slice, int* slice_ext,
                            int* ext_beg, int* ierr) {
+    SIP_TRACE("tensor_block_insert__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = 1; return; }
@@ -570,6 +577,7 @@ void tensor_block_insert__(int* nthreads, int* rank, double* tens, int* tens_ext
 
 void tensor_block_add__(const int* nthreads, const int* rank, int* ext, double* tens0, double* tens1, const double* fac,
                         int* ierr) {
+    SIP_TRACE("tensor_block_add__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = -1; return; }
@@ -584,6 +592,7 @@ void tensor_block_add__(const int* nthreads, const int* rank, int* ext, double* 
 
 void tensor_block_copy__(int* nthreads, int* rank, int* ext, int* dim_transp, double* tens_in, double* tens_out,
                          int* ierr) {
+    SIP_TRACE("tensor_block_copy__");
     (void)nthreads;
     *ierr = 0;
     if (*rank < 0) { *ierr = *rank; return; }
@@ -598,6 +607,7 @@ void tensor_block_copy__(int* nthreads, int* rank, int* ext, int* dim_transp, do
 
 void tensor_block_contract__(int* nthreads, int* contr_ptrn, double* ltens, int* lrank, int* lext, double* rtens,
                              int* rrank, int* rext, double* dtens, int* drank, int* dext, int* ierr) {
+    SIP_TRACE("tensor_block_contract__");
     (void)nthreads;
     *ierr = 0;
     if (*lrank < 0 || *rrank < 0 || *drank < 0 || *lrank > 32 || *rrank > 32 || *drank > 32) { *ierr = -1; return; }
@@ -613,6 +623,7 @@ void tensor_block_contract__(int* nthreads, int* contr_ptrn, double* ltens, int*
 
 // ------------------------------------------------ boundary 2 ------------------------------------------------
 int _init_gpu(int* devid, int* my_rank) {
+    SIP_TRACE("_init_gpu");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -624,76 +635,99 @@ int _init_gpu(int* devid, int* my_rank) {
     if (devid) *devid = dev;
     return SIPGPU_OK;
 }
-int _finalize_gpu(void) { return sipgpu_finalize(); }
-double* _gpu_allocate(const int n) { return sipgpu_block_alloc(n, 1); }
-int _gpu_free(double* g) { return sipgpu_block_free(g); }
-int _gpu_host_to_device(double* c_addr, double* g_addr, const int n) { return sipgpu_h2d(g_addr, c_addr, n); }
-int _gpu_device_to_host(double* c_addr, double* g_addr, const int n) { return sipgpu_d2h(c_addr, g_addr, n); }
+int _finalize_gpu(void) {
+    SIP_TRACE("_finalize_gpu"); return sipgpu_finalize(); }
+double* _gpu_allocate(const int n) {
+    SIP_TRACE("_gpu_allocate"); return sipgpu_block_alloc(n, 1); }
+int _gpu_free(double* g) {
+    SIP_TRACE("_gpu_free"); return sipgpu_block_free(g); }
+int _gpu_host_to_device(double* c_addr, double* g_addr, const int n) {
+    SIP_TRACE("_gpu_host_to_device"); return sipgpu_h2d(g_addr, c_addr, n); }
+int _gpu_device_to_host(double* c_addr, double* g_addr, const int n) {
+    SIP_TRACE("_gpu_device_to_host"); return sipgpu_d2h(c_addr, g_addr, n); }
 int _gpu_device_to_device(double* dst, double* src, const int n) {
+    SIP_TRACE("_gpu_device_to_device");
     if (n < 0) return SIPGPU_E_ARG;
     if (wl_active()) return wl_rec_ew(WL_SCALE_COPY, dst, src, nullptr, n, 1.0);
     SIP_TRY(ensure_init());
     SIP_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx().stream));
     return SIPGPU_OK;
 }
-int _gpu_double_memset(double* g, double value, const int n) { return sipgpu_block_fill(g, n, value); }
-int _gpu_selfmultiply(double* x, const double alpha, const int n) { return sipgpu_block_scale(x, n, alpha); }
-int _gpu_axpy(double* y, double* x, const double alpha, const int n) { return sipgpu_block_axpy(y, x, n, alpha); }
+int _gpu_double_memset(double* g, double value, const int n) {
+    SIP_TRACE("_gpu_double_memset"); return sipgpu_block_fill(g, n, value); }
+int _gpu_selfmultiply(double* x, const double alpha, const int n) {
+    SIP_TRACE("_gpu_selfmultiply"); return sipgpu_block_scale(x, n, alpha); }
+int _gpu_axpy(double* y, double* x, const double alpha, const int n) {
+    SIP_TRACE("_gpu_axpy"); return sipgpu_block_axpy(y, x, n, alpha); }
 int _gpu_permute(double* y, const int ny, const int* y_dims, const int* y_inds, double* x, const int nx, const int* x_dims,
                  const int* x_inds) {
+    SIP_TRACE("_gpu_permute");
     (void)y_dims;
     if (ny != nx) return SIPGPU_E_ARG;
     return sipgpu_block_permute_labels(nx, x_dims, y_inds, x_inds, x, y);
 }
 int _gpu_contract(double* y, const int ny, const int* y_dims, const int* y_inds, double* x1, const int n1, const int* x1_dims,
                   const int* x1_inds, double* x2, const int n2, const int* x2_dims, const int* x2_inds) {
+    SIP_TRACE("_gpu_contract");
     return sipgpu_block_contract_labels(ny, y_dims, y_inds, y, n1, x1_dims, x1_inds, x1, n2, x2_dims, x2_inds, x2, 1.0, 0.0);
 }
 
 // ------------------------------------------------ boundary 3 ------------------------------------------------
 // While a work-list recording is open (sipgpu_wl_begin) the asynchronous ops below are recorded instead of launched.
 int sipgpu_block_fill(double* d, long long n, double v) {
+    SIP_TRACE("sipgpu_block_fill");
     return wl_active() ? wl_rec_ew(WL_FILL, d, nullptr, nullptr, n, v) : ew_fill(d, n, v);
 }
 int sipgpu_block_scale(double* d, long long n, double f) {
+    SIP_TRACE("sipgpu_block_scale");
     return wl_active() ? wl_rec_ew(WL_SCALE, d, nullptr, nullptr, n, f) : ew_scale(d, n, f);
 }
 int sipgpu_block_scale_and_copy(double* d, const double* s, long long n, double f) {
+    SIP_TRACE("sipgpu_block_scale_and_copy");
     if (wl_active()) return s ? wl_rec_ew(WL_SCALE_COPY, d, s, nullptr, n, f) : SIPGPU_E_ARG;
     return ew_scale_copy(d, s, n, f);
 }
 int sipgpu_block_increment(double* d, long long n, double delta) {
+    SIP_TRACE("sipgpu_block_increment");
     return wl_active() ? wl_rec_ew(WL_INCR, d, nullptr, nullptr, n, delta) : ew_increment(d, n, delta);
 }
 int sipgpu_block_axpy(double* d, const double* s, long long n, double f) {
+    SIP_TRACE("sipgpu_block_axpy");
     if (wl_active()) return s ? wl_rec_ew(WL_AXPY, d, s, nullptr, n, f) : SIPGPU_E_ARG;
     return ew_axpy(d, s, n, f);
 }
-int sipgpu_block_accumulate(double* d, const double* s, long long n) { return sipgpu_block_axpy(d, s, n, 1.0); }
+int sipgpu_block_accumulate(double* d, const double* s, long long n) {
+    SIP_TRACE("sipgpu_block_accumulate"); return sipgpu_block_axpy(d, s, n, 1.0); }
 int sipgpu_block_add_sub(double* d, const double* l, const double* r, long long n, double sign) {
+    SIP_TRACE("sipgpu_block_add_sub");
     if (wl_active()) return (l && r) ? wl_rec_ew(WL_ADDSUB, d, l, r, n, sign) : SIPGPU_E_ARG;
     return ew_add_sub(d, l, r, n, sign);
 }
 int sipgpu_block_fill_hash(double* d, long long n, unsigned long long seed, unsigned long long tag, double scale) {
+    SIP_TRACE("sipgpu_block_fill_hash");
     if (wl_active())
         return wl_rec_opaque([=] { return ew_fill_hash(d, n, seed, tag, scale); }, {{d, sizeof(double) * (size_t)n, WL_W}});
     return ew_fill_hash(d, n, seed, tag, scale);
 }
 int sipgpu_block_dot_accumulate(const double* l, const double* r, long long n, double* d_scalar) {
+    SIP_TRACE("sipgpu_block_dot_accumulate");
     if (wl_active())
         return wl_rec_opaque([=] { return ew_dot_device(l, r, n, d_scalar, 1.0); },
                              {{l, sizeof(double) * (size_t)n, WL_R}, {r, sizeof(double) * (size_t)n, WL_R}, {d_scalar, 8, WL_RW}});
     return ew_dot_device(l, r, n, d_scalar, 1.0);
 }
 int sipgpu_block_norm2(const double* t, long long n, double* out) {
+    SIP_TRACE("sipgpu_block_norm2");
     SIP_TRY(wl_flush());
     return ew_dot(t, t, n, out);
 }
 int sipgpu_block_dot(const double* l, const double* r, long long n, double* out) {
+    SIP_TRACE("sipgpu_block_dot");
     SIP_TRY(wl_flush());
     return ew_dot(l, r, n, out);
 }
 int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, const int* s_ext, const int* beg) {
+    SIP_TRACE("sipgpu_block_slice");
     if (wl_active()) {
         if (rank < 0 || rank > kMaxRank || !t || !s || !t_ext || !s_ext || !beg) return SIPGPU_E_ARG;
         std::array<int, kMaxRank> te{}, se{}, bg{};
@@ -704,6 +738,7 @@ int sipgpu_block_slice(int rank, const double* t, const int* t_ext, double* s, c
     return ew_slice(rank, t, t_ext, s, s_ext, beg);
 }
 int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, const int* s_ext, const int* beg) {
+    SIP_TRACE("sipgpu_block_insert");
     if (wl_active()) {
         if (rank < 0 || rank > kMaxRank || !t || !s || !t_ext || !s_ext || !beg) return SIPGPU_E_ARG;
         std::array<int, kMaxRank> te{}, se{}, bg{};
@@ -714,12 +749,14 @@ int sipgpu_block_insert(int rank, double* t, const int* t_ext, const double* s, 
     return ew_insert(rank, t, t_ext, s, s_ext, beg);
 }
 int sipgpu_block_permute(int rank, const int* ext, const int* transp, const double* in, double* out) {
+    SIP_TRACE("sipgpu_block_permute");
     if (wl_active() && rank >= 1 && rank <= kMaxRank) return wl_rec_permute(rank, ext, transp, in, out, 1.0, 0.0);
     SIP_TRY(wl_flush());
     return permute_block(rank, ext, transp, in, out);
 }
 int sipgpu_permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in,
                            double* const* out, double alpha, double beta) {
+    SIP_TRACE("sipgpu_permute_batched");
     if (wl_active() && rank >= 1 && rank <= kMaxRank) {
         if (n < 0 || (n && (!in || !out))) return SIPGPU_E_ARG;
         for (int i = 0; i < n; ++i) SIP_TRY(wl_rec_permute(rank, ext, transp, in[i], out[i], alpha, beta));
@@ -730,6 +767,7 @@ int sipgpu_permute_batched(int n, int rank, const int* ext, const int* transp, c
 }
 int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_labels, const int* rhs_labels, const double* rhs,
                                 double* lhs) {
+    SIP_TRACE("sipgpu_block_permute_labels");
     if (rank < 0 || rank > 32) return SIPGPU_E_ARG;
     int transp[33];
     SIP_TRY(permutation_from_labels(rank, lhs_labels, rhs_labels, transp));
@@ -737,6 +775,7 @@ int sipgpu_block_permute_labels(int rank, const int* rhs_ext, const int* lhs_lab
 }
 int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int* lext, const double* R, int rrank,
                           const int* rext, double* D, int drank, const int* dext, double alpha, double beta) {
+    SIP_TRACE("sipgpu_block_contract");
     if (wl_active()) {
         int rc;
         if (lrank >= 1 && rrank >= 1 && drank >= 1 && lrank <= kMaxRank && rrank <= kMaxRank && drank <= kMaxRank) {
@@ -776,6 +815,7 @@ int sipgpu_block_contract(const int* ptrn, const double* L, int lrank, const int
 int sipgpu_block_contract_labels(int drank, const int* dext, const int* dlab, double* D, int lrank, const int* lext,
                                  const int* llab, const double* L, int rrank, const int* rext, const int* rlab,
                                  const double* R, double alpha, double beta) {
+    SIP_TRACE("sipgpu_block_contract_labels");
     // ranks are validated BEFORE the label conversion writes lrank + rrank pattern entries
     if (drank < 0 || lrank < 0 || rrank < 0 || drank > kMaxRank || lrank > kMaxRank || rrank > kMaxRank) {
         set_error("contract: ranks (%d, %d, %d) outside 0..%d", drank, lrank, rrank, kMaxRank);
@@ -789,6 +829,7 @@ int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, co
                                  const int* lbeg, const double* R, int rrank, const int* rext, const int* rparent_ext,
                                  const int* rbeg, double* D, int drank, const int* dext, const int* dparent_ext,
                                  const int* dbeg, double alpha, double beta) {
+    SIP_TRACE("sipgpu_block_contract_sliced");
     if (wl_active()) {
         if (!L || !R || !D || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank)
             return SIPGPU_E_ARG;
@@ -831,6 +872,7 @@ int sipgpu_block_contract_sliced(const int* ptrn, const double* L, int lrank, co
 int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                             const int* dext, const double* const* L, const double* const* R, double* const* D,
                             double alpha, double beta) {
+    SIP_TRACE("sipgpu_contract_batched");
     SIP_TRY(wl_flush());  // already a work-list: runs as it is, after whatever was recorded before it
     const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, nullptr, L, R, D, alpha, beta);
     return rc == 1 ? SIPGPU_E_PATTERN : rc;
@@ -838,6 +880,7 @@ int sipgpu_contract_batched(int n, const int* ptrn, int lrank, int rrank, int dr
 int sipgpu_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                             const int* dext, const int* chain_start, const double* const* L, const double* const* R,
                             double* const* D, double alpha, double beta) {
+    SIP_TRACE("sipgpu_contract_chained");
     if (!chain_start) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());
     const int rc = contract_chained(n, ptrn, lrank, rrank, drank, lext, rext, dext, chain_start, L, R, D, alpha, beta);
@@ -870,6 +913,7 @@ extern "C" {
 int sipgpu_plan_contract_chained(int n, const int* ptrn, int lrank, int rrank, int drank, const int* lext, const int* rext,
                                  const int* dext, const int* chain_start, const double* const* L, const double* const* R,
                                  double* const* D, sipgpu_plan** out) {
+    SIP_TRACE("sipgpu_plan_contract_chained");
     if (!out || n < 0 || !ptrn || lrank < 1 || rrank < 1 || drank < 1 || lrank > kMaxRank || rrank > kMaxRank || drank > kMaxRank ||
         (n && (!lext || !rext || !dext || !L || !R || !D)))
         return SIPGPU_E_ARG;
@@ -888,6 +932,7 @@ int sipgpu_plan_contract_chained(int n, const int* ptrn, int lrank, int rrank, i
     return SIPGPU_OK;
 }
 int sipgpu_plan_launch(sipgpu_plan* p, double alpha, double beta) {
+    SIP_TRACE("sipgpu_plan_launch");
     if (!p) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());  // runs after whatever was recorded before it, like sipgpu_contract_chained
     if (p->n == 0) return SIPGPU_OK;
@@ -920,6 +965,7 @@ int sipgpu_plan_launch(sipgpu_plan* p, double alpha, double beta) {
     return SIPGPU_OK;
 }
 int sipgpu_plan_destroy(sipgpu_plan* p) {
+    SIP_TRACE("sipgpu_plan_destroy");
     if (!p) return SIPGPU_OK;
     if (ctx().inited) cudaStreamSynchronize(ctx().stream);  // descriptors may still be read by queued launches
     delete p;
@@ -927,7 +973,8 @@ int sipgpu_plan_destroy(sipgpu_plan* p) {
 }
 
 // ---- boundary 3b: elementwise CC super-instructions (superinstr.cu), reference calling convention ----
-int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) { return si_set_int_array(name, n, values); }
+int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) {
+    SIP_TRACE("sipgpu_set_predefined_int_array"); return si_set_int_array(name, n, values); }
 #define SI_RETURN(expr)                   \
     do {                                  \
         const int rc__ = (expr);          \
@@ -936,6 +983,7 @@ int sipgpu_set_predefined_int_array(const char* name, int n, const int* values) 
     } while (0)
 int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                                      int*, int*, int* extents_1, double* data_1, int* ierr) {
+    SIP_TRACE("sipgpu_si_energy_denominator_rhf");
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {  // recorded with its read/write sets; runs at its scheduled position
         const int r0 = *rank_0, r1 = *rank_1;
@@ -952,6 +1000,7 @@ int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int
 }
 int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                      int* index_values_1, int*, int* extents_1, double* data_1, int* ierr) {
+    SIP_TRACE("sipgpu_si_stripi");
     if (!rank_0 || !rank_1 || *rank_0 != *rank_1) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {
         const int r = *rank_0;
@@ -966,6 +1015,7 @@ int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_
     SI_RETURN(si_stripi(*rank_0, index_values_0, extents_0, data_0, index_values_1, extents_1, data_1));
 }
 int sipgpu_si_anti_symm_o(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
+    SIP_TRACE("sipgpu_si_anti_symm_o");
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {
         const int r = *rank_0;
@@ -978,6 +1028,7 @@ int sipgpu_si_anti_symm_o(int*, int* rank_0, int* index_values_0, int*, int* ext
     SI_RETURN(si_anti_symm_o(*rank_0, index_values_0, extents_0, data_0));
 }
 int sipgpu_si_anti_symm_v(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int* ierr) {
+    SIP_TRACE("sipgpu_si_anti_symm_v");
     if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {
         const int r = *rank_0;
@@ -991,6 +1042,7 @@ int sipgpu_si_anti_symm_v(int*, int* rank_0, int* index_values_0, int*, int* ext
 }
 int sipgpu_si_return_sval(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                           double* data_1, int* ierr) {
+    SIP_TRACE("sipgpu_si_return_sval");
     if (!rank_0 || !rank_1 || *rank_1 != 0) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {
         const int r = *rank_0;
@@ -1004,6 +1056,7 @@ int sipgpu_si_return_sval(int*, int* rank_0, int*, int*, int* extents_0, double*
 }
 int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int*, int* rank_1, int*, int*, int*,
                               double* data_1, int* ierr) {
+    SIP_TRACE("sipgpu_si_invert_diagonal");
     if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
     if (wl_active()) {
         const int r0 = *rank_0, r1 = *rank_1;
@@ -1019,6 +1072,7 @@ int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, dou
 
 int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
                     double* C, int ldc) {
+    SIP_TRACE("sipgpu_dgemm_tn");
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (m < 1 || n < 1 || k < 1 || lda < k || ldb < k || ldc < m || !A || !B || !C) return SIPGPU_E_ARG;
@@ -1046,17 +1100,21 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
 // ---- host-only planner views (no device needed): used by the CPU tests of the host logic ----
 int sipgpu_debug_contract_shape(const int* ptrn, int lrank, const int* lext, int rrank, const int* rext, int drank,
                                 const int* dext, int* shape_ints /* sizeof(Shape)/4 */) {
+    SIP_TRACE("sipgpu_debug_contract_shape");
     Shape s;
     const int rc = build_shape(ptrn, lrank, lext, rrank, rext, drank, dext, &s);
     if (rc == 0) memcpy(shape_ints, &s, sizeof(s));
     return rc;
 }
-int sipgpu_debug_shape_ints(void) { return (int)(sizeof(Shape) / sizeof(int)); }
+int sipgpu_debug_shape_ints(void) {
+    SIP_TRACE("sipgpu_debug_shape_ints"); return (int)(sizeof(Shape) / sizeof(int)); }
 int sipgpu_debug_permute_plan(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab, int cap) {
+    SIP_TRACE("sipgpu_debug_permute_plan");
     return sipgpu::permute_plan_debug(rank, ext, transp, meta, rtab, wtab, cap);
 }
 
 int sipgpu_set_tuning(const char* key, double value) {
+    SIP_TRACE("sipgpu_set_tuning");
     if (!key) return SIPGPU_E_ARG;
     if (!strcmp(key, "lowint_max_intensity")) { lowint_set_max_intensity(value); wl_tuning_changed(); return SIPGPU_OK; }
     if (!strcmp(key, "lowint_scope")) { lowint_set_scope((int)value); wl_tuning_changed(); return SIPGPU_OK; }
@@ -1064,11 +1122,13 @@ int sipgpu_set_tuning(const char* key, double value) {
     return SIPGPU_E_ARG;
 }
 int sipgpu_dmma_peak_probe(int iters, double* tflops_out) {
+    SIP_TRACE("sipgpu_dmma_peak_probe");
     SIP_TRY(ensure_init());
     return dmma_probe(iters, tflops_out);
 }
 
 int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out) {
+    SIP_TRACE("sipgpu_copy_bw_probe");
     SIP_TRY(ensure_init());
     Ctx& c = ctx();
     const long long n = (long long)(bytes / 16) * 2;

@@ -66,6 +66,22 @@ Capture*& capture();
 int desc_alloc(size_t bytes, void** h, void** d);
 int desc_commit(void* h, void* d, size_t bytes);
 
+// ---- per-entry-point trace (sipgpu_trace_*): the counterpart of the reference's Tracer (src/sip/worker/tracer.h:41-50, per-pc
+// call counts and wall time of the interpreter loop): calls and host wall time per C-ABI entry point.  Off by default; one
+// predictable branch per call when off.
+extern bool g_trace_on;
+int trace_slot(const char* name);              // registers `name` once (call sites keep the slot in a static)
+void trace_add(int slot, double host_seconds);
+struct TraceScope {
+    int slot;
+    double t0;
+    explicit TraceScope(int s);
+    ~TraceScope();
+};
+#define SIP_TRACE(name)                                                   \
+    static const int sip_trace_slot__ = ::sipgpu::trace_slot(name);       \
+    ::sipgpu::TraceScope sip_trace_scope__(::sipgpu::g_trace_on ? sip_trace_slot__ : -1)
+
 // bumped by every device allocation made OUTSIDE the pool (distributed-array slabs): cached free-memory figures are stale then
 long long& mem_epoch();
 

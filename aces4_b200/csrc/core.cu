@@ -9,6 +9,7 @@
 // distinct block sizes, so a freed block is almost always reused by the next allocation of the same shape.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <map>
 #include <mutex>
@@ -144,6 +145,37 @@ int scratch_reserve(size_t bytes, void** h, void** d) {
     return SIPGPU_OK;
 }
 
+bool g_trace_on = false;
+namespace {
+struct TraceRow {
+    const char* name;
+    long long calls = 0;
+    double host_s = 0.0;
+};
+std::vector<TraceRow>& trace_rows() {
+    static std::vector<TraceRow> r;
+    return r;
+}
+double now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+}  // namespace
+int trace_slot(const char* name) {
+    trace_rows().push_back(TraceRow{name});
+    return (int)trace_rows().size() - 1;
+}
+void trace_add(int slot, double host_seconds) {
+    TraceRow& r = trace_rows()[(size_t)slot];
+    r.calls++;
+    r.host_s += host_seconds;
+}
+TraceScope::TraceScope(int s) : slot(s), t0(s >= 0 ? now_s() : 0.0) {}
+TraceScope::~TraceScope() {
+    if (slot >= 0) trace_add(slot, now_s() - t0);
+}
+
 Capture*& capture() {
     static Capture* c = nullptr;
     return c;
@@ -245,14 +277,17 @@ using namespace sipgpu;
 
 extern "C" {
 
-int sipgpu_init(int device) { return init_on(device); }
+int sipgpu_init(int device) {
+    SIP_TRACE("sipgpu_init"); return init_on(device); }
 int sipgpu_finalize(void) {
+    SIP_TRACE("sipgpu_finalize");
     if (sipgpu_wl_recording()) sipgpu_wl_end();
     return finalize_all();
 }
 int sipgpu_device(void) { return g_ctx.inited ? g_ctx.device : -1; }
 const char* sipgpu_last_error(void) { return g_err; }
 int sipgpu_sync(void) {
+    SIP_TRACE("sipgpu_sync");
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     SIP_CUDA(cudaStreamSynchronize(g_ctx.stream));
@@ -262,10 +297,12 @@ void* sipgpu_stream(void) { return ensure_init() == SIPGPU_OK ? (void*)g_ctx.str
 long long sipgpu_kernel_launches(void) { return g_ctx.launches; }
 
 int sipgpu_pool_reserve(size_t bytes) {
+    SIP_TRACE("sipgpu_pool_reserve");
     SIP_TRY(ensure_init());
     return add_arena(round_up(bytes));
 }
 double* sipgpu_block_alloc(long long n, int zero) {
+    SIP_TRACE("sipgpu_block_alloc");
     if (n < 0) return nullptr;
     if (wl_active()) return wl_alloc(n, zero);  // a temp of the recorded stream; zeroing becomes a recorded fill
     double* p = pool_alloc(sizeof(double) * (size_t)n);
@@ -278,7 +315,8 @@ double* sipgpu_block_alloc(long long n, int zero) {
     }
     return p;
 }
-int sipgpu_block_free(double* p) { return wl_active() ? wl_free(p) : pool_free(p); }
+int sipgpu_block_free(double* p) {
+    SIP_TRACE("sipgpu_block_free"); return wl_active() ? wl_free(p) : pool_free(p); }
 }  // extern C (reopened below)
 namespace sipgpu { long long& mem_epoch() { static long long e = 0; return e; } }
 extern "C" {
@@ -289,6 +327,7 @@ int sipgpu_pool_stats(size_t* reserved, size_t* in_use, size_t* n_live) {
     return SIPGPU_OK;
 }
 int sipgpu_h2d(double* g_dst, const double* h_src, long long n) {
+    SIP_TRACE("sipgpu_h2d");
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (n < 0 || (n && (!g_dst || !h_src))) return SIPGPU_E_ARG;
@@ -296,6 +335,7 @@ int sipgpu_h2d(double* g_dst, const double* h_src, long long n) {
     return SIPGPU_OK;
 }
 int sipgpu_d2h(double* h_dst, const double* g_src, long long n) {
+    SIP_TRACE("sipgpu_d2h");
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
     if (n < 0 || (n && (!h_dst || !g_src))) return SIPGPU_E_ARG;
@@ -313,8 +353,32 @@ void* sipgpu_host_alloc(size_t bytes) {
     return p;
 }
 int sipgpu_host_free(void* p) {
+    SIP_TRACE("sipgpu_host_free");
     if (p) SIP_CUDA(cudaFreeHost(p));
     return SIPGPU_OK;
+}
+
+// ---- per-entry-point trace ----
+int sipgpu_trace_enable(int on) {
+    g_trace_on = on != 0;
+    return SIPGPU_OK;
+}
+int sipgpu_trace_reset(void) {
+    for (auto& r : trace_rows()) { r.calls = 0; r.host_s = 0.0; }
+    return SIPGPU_OK;
+}
+// rows with at least one call since the last reset, most host time first; returns how many there are (may exceed cap)
+int sipgpu_trace_report(int cap, const char** names, long long* calls, double* host_seconds) {
+    std::vector<const TraceRow*> rows;
+    for (const auto& r : trace_rows())
+        if (r.calls > 0) rows.push_back(&r);
+    std::sort(rows.begin(), rows.end(), [](const TraceRow* a, const TraceRow* b) { return a->host_s > b->host_s; });
+    for (int i = 0; i < (int)rows.size() && i < cap; ++i) {
+        if (names) names[i] = rows[i]->name;
+        if (calls) calls[i] = rows[i]->calls;
+        if (host_seconds) host_seconds[i] = rows[i]->host_s;
+    }
+    return (int)rows.size();
 }
 
 }  // extern "C"

@@ -64,6 +64,7 @@ int sipgpu_layout_block_owner(long long block_number, int world) {
 }
 
 int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_rank, int world, sipgpu_array** out) {
+    SIP_TRACE("sipgpu_array_create");
     if (rank < 1 || rank > kMaxRank || !nseg || !seg_ext || !out || world < 1 || my_rank < 0 || my_rank >= world)
         return SIPGPU_E_ARG;
     SIP_TRY(ensure_init());
@@ -120,6 +121,7 @@ int sipgpu_array_create(int rank, const int* nseg, const int* seg_ext, int my_ra
 }
 
 int sipgpu_array_destroy(sipgpu_array* a) {
+    SIP_TRACE("sipgpu_array_destroy");
     if (!a) return SIPGPU_OK;
     cudaStreamSynchronize(ctx().stream);
     for (int r = 0; r < a->world; ++r) {
@@ -132,6 +134,7 @@ int sipgpu_array_destroy(sipgpu_array* a) {
 }
 
 int sipgpu_array_export(sipgpu_array* a, void* handle_bytes) {
+    SIP_TRACE("sipgpu_array_export");
     if (!a || !handle_bytes) return SIPGPU_E_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == SIPGPU_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;
@@ -141,6 +144,7 @@ int sipgpu_array_export(sipgpu_array* a, void* handle_bytes) {
 }
 
 int sipgpu_array_attach(sipgpu_array* a, int peer_rank, const void* handle_bytes, int peer_device) {
+    SIP_TRACE("sipgpu_array_attach");
     if (!a || peer_rank < 0 || peer_rank >= a->world || !handle_bytes) return SIPGPU_E_ARG;
     if (peer_rank == a->my_rank) return SIPGPU_OK;
     (void)peer_device;
@@ -181,6 +185,7 @@ double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx) {
 }
 
 int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
+    SIP_TRACE("sipgpu_array_get");
     double* src = sipgpu_array_block_ptr(a, idx);
     if (!src || !g_dst) return src ? SIPGPU_E_ARG : SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_GET;
@@ -191,6 +196,7 @@ int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst) {
     return SIPGPU_OK;
 }
 int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
+    SIP_TRACE("sipgpu_array_put");
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
@@ -200,6 +206,7 @@ int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src) {
     return SIPGPU_OK;
 }
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src) {
+    SIP_TRACE("sipgpu_array_put_accumulate");
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst || !g_src) return dst ? SIPGPU_E_ARG : SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT_ACCUMULATE;
@@ -211,6 +218,7 @@ int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g
 // runs on the caller's stream directly on the owner's (possibly peer-mapped) block.  For the race detector they count
 // as put, put_accumulate and put respectively (distributed_block_consistency.cpp:60).
 int sipgpu_array_put_initialize(sipgpu_array* a, const int* idx, double value) {
+    SIP_TRACE("sipgpu_array_put_initialize");
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst) return SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
@@ -218,6 +226,7 @@ int sipgpu_array_put_initialize(sipgpu_array* a, const int* idx, double value) {
     return wl_active() ? wl_rec_ew(WL_FILL, dst, nullptr, nullptr, n, value) : ew_fill(dst, n, value);
 }
 int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta) {
+    SIP_TRACE("sipgpu_array_put_increment");
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst) return SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT_ACCUMULATE;
@@ -230,6 +239,7 @@ int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta) {
     return wl_active() ? wl_rec_ew(WL_INCR, dst, nullptr, nullptr, n, delta) : ew_increment(dst, n, delta);
 }
 int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor) {
+    SIP_TRACE("sipgpu_array_put_scale");
     double* dst = sipgpu_array_block_ptr(a, idx);
     if (!dst) return SIPGPU_E_STATE;
     if (a->track) a->touched[sipgpu_array_block_number(a, idx)] |= SIPGPU_ACCESS_PUT;
@@ -237,6 +247,7 @@ int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor) {
     return wl_active() ? wl_rec_ew(WL_SCALE, dst, nullptr, nullptr, n, factor) : ew_scale(dst, n, factor);
 }
 int sipgpu_array_fill_local(sipgpu_array* a, double v) {
+    SIP_TRACE("sipgpu_array_fill_local");
     if (!a) return SIPGPU_E_ARG;
     if (wl_active()) return wl_rec_ew(WL_FILL, a->base[a->my_rank], nullptr, nullptr, a->slab_elems[a->my_rank], v);
     return ew_fill(a->base[a->my_rank], a->slab_elems[a->my_rank], v);
@@ -249,12 +260,14 @@ int sipgpu_array_fill_local(sipgpu_array* a, double v) {
 // (sipgpu_array_section_accesses), the summaries are exchanged by the caller's barrier, and each rank validates the
 // union with sipgpu_consistency_validate (host-only arithmetic).
 int sipgpu_array_track_accesses(sipgpu_array* a, int on) {
+    SIP_TRACE("sipgpu_array_track_accesses");
     if (!a) return SIPGPU_E_ARG;
     a->track = on != 0;
     a->touched.clear();
     return SIPGPU_OK;
 }
 long long sipgpu_array_section_accesses(sipgpu_array* a, long long cap, long long* block_numbers, int* access_bits) {
+    SIP_TRACE("sipgpu_array_section_accesses");
     if (!a) return -1;
     std::map<long long, int> sorted(a->touched.begin(), a->touched.end());
     long long k = 0;
@@ -265,12 +278,14 @@ long long sipgpu_array_section_accesses(sipgpu_array* a, long long cap, long lon
     return k;
 }
 int sipgpu_array_section_reset(sipgpu_array* a) {
+    SIP_TRACE("sipgpu_array_section_reset");
     if (!a) return SIPGPU_E_ARG;
     a->touched.clear();  // sip_barrier: DistributedBlockConsistency::reset_consistency_status
     return SIPGPU_OK;
 }
 int sipgpu_consistency_validate(long long n, const long long* block_numbers, const int* access_bits, const int* workers,
                                 long long* bad_block) {
+    SIP_TRACE("sipgpu_consistency_validate");
     if (n < 0 || (n && (!block_numbers || !access_bits || !workers))) return SIPGPU_E_ARG;
     struct Agg { int bits = 0, worker = -1; bool multiple = false; };
     std::map<long long, Agg> agg;
@@ -298,6 +313,7 @@ int sipgpu_consistency_validate(long long n, const long long* block_numbers, con
 // index file : <offset DENSE_INDEX = 77><offset nblocks><offset per block number>*        (offset_val_t = long long)
 //              offset = byte position of the block in THIS rank's data file, -1 (ABSENT_BLOCK_OFFSET) for blocks of peers
 int sipgpu_array_save(sipgpu_array* a, const char* data_path, const char* index_path) {
+    SIP_TRACE("sipgpu_array_save");
     if (!a || !data_path || !index_path) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());
@@ -339,6 +355,7 @@ int sipgpu_array_save(sipgpu_array* a, const char* data_path, const char* index_
     return SIPGPU_OK;
 }
 int sipgpu_array_load(sipgpu_array* a, const char* data_path, const char* index_path) {
+    SIP_TRACE("sipgpu_array_load");
     if (!a || !data_path || !index_path) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());
     SIP_TRY(ensure_init());

@@ -34,6 +34,7 @@ using namespace sipgpu;
 extern "C" {
 
 int sipgpu_mirror_transition(int bits, int op, int* new_bits, int* action) {
+    SIP_TRACE("sipgpu_mirror_transition");
     if (op < OP_READ_DEV || op > OP_UPDATE_HOST || bits < 0 || bits > 15) return SIPGPU_E_ARG;
     const bool to_dev = op <= OP_UPDATE_DEV;
     const int here = to_dev ? ON_GPU : ON_HOST;
@@ -64,6 +65,7 @@ int sipgpu_mirror_transition(int bits, int op, int* new_bits, int* action) {
 }
 
 int sipgpu_mirror_create(double* host_or_null, long long n, sipgpu_mirror** out) {
+    SIP_TRACE("sipgpu_mirror_create");
     if (n < 0 || !out) return SIPGPU_E_ARG;
     sipgpu_mirror* m = new sipgpu_mirror();
     m->host = host_or_null;
@@ -73,6 +75,7 @@ int sipgpu_mirror_create(double* host_or_null, long long n, sipgpu_mirror** out)
     return SIPGPU_OK;
 }
 int sipgpu_mirror_destroy(sipgpu_mirror* m) {
+    SIP_TRACE("sipgpu_mirror_destroy");
     if (!m) return SIPGPU_OK;
     // inside a recording the ops that touch the device side have not run yet: defer the free like sipgpu_block_free
     if (m->dev) { if (wl_active()) wl_free(m->dev); else pool_free(m->dev); }
@@ -87,6 +90,7 @@ double* sipgpu_mirror_device_ptr(sipgpu_mirror* m) { return m ? m->dev : nullptr
 
 // applies one lazy_gpu_* transition; returns the pointer of the side that may now be used, NULL on error
 double* sipgpu_mirror_access(sipgpu_mirror* m, int op) {
+    SIP_TRACE("sipgpu_mirror_access");
     if (!m) return nullptr;
     int nb = 0, act = 0;
     if (sipgpu_mirror_transition(m->bits, op, &nb, &act) != SIPGPU_OK) return nullptr;

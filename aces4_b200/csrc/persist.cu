@@ -115,11 +115,13 @@ extern "C" {
 
 // ---- label registry (hand-off between SIAL programs) ----
 int sipgpu_persist_scalar(const char* label, double value) {
+    SIP_TRACE("sipgpu_persist_scalar");
     if (!label) return SIPGPU_E_ARG;
     g_scalars[label] = value;  // a repeated label overwrites (worker_persistent_array_manager.cpp:124-130)
     return SIPGPU_OK;
 }
 int sipgpu_restore_scalar(const char* label, double* value) {
+    SIP_TRACE("sipgpu_restore_scalar");
     if (!label || !value) return SIPGPU_E_ARG;
     auto it = g_scalars.find(label);
     if (it == g_scalars.end()) {
@@ -131,6 +133,7 @@ int sipgpu_restore_scalar(const char* label, double* value) {
     return SIPGPU_OK;
 }
 int sipgpu_persist_contiguous(const char* label, double* dev_block, int rank, const int* ext) {
+    SIP_TRACE("sipgpu_persist_contiguous");
     if (!label || !dev_block || rank < 0 || rank > kMaxRank || (rank && !ext)) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());
     Contig c;
@@ -151,6 +154,7 @@ int sipgpu_persist_contiguous(const char* label, double* dev_block, int rank, co
     return SIPGPU_OK;
 }
 int sipgpu_restore_contiguous(const char* label, double** dev_block, int* rank, int* ext6) {
+    SIP_TRACE("sipgpu_restore_contiguous");
     if (!label || !dev_block) return SIPGPU_E_ARG;
     auto it = g_contig.find(label);
     if (it == g_contig.end()) {
@@ -164,6 +168,7 @@ int sipgpu_restore_contiguous(const char* label, double** dev_block, int* rank, 
     return SIPGPU_OK;
 }
 int sipgpu_persist_array(const char* label, sipgpu_array* a) {
+    SIP_TRACE("sipgpu_persist_array");
     if (!label || !a) return SIPGPU_E_ARG;
     SIP_TRY(wl_flush());
     auto it = g_arrays.find(label);
@@ -172,6 +177,7 @@ int sipgpu_persist_array(const char* label, sipgpu_array* a) {
     return SIPGPU_OK;
 }
 int sipgpu_restore_array(const char* label, sipgpu_array** a) {
+    SIP_TRACE("sipgpu_restore_array");
     if (!label || !a) return SIPGPU_E_ARG;
     auto it = g_arrays.find(label);
     if (it == g_arrays.end()) {
@@ -183,6 +189,7 @@ int sipgpu_restore_array(const char* label, sipgpu_array** a) {
     return SIPGPU_OK;
 }
 int sipgpu_persist_count(int* nscalars, int* ncontiguous, int* narrays) {
+    SIP_TRACE("sipgpu_persist_count");
     if (nscalars) *nscalars = (int)g_scalars.size();
     if (ncontiguous) *ncontiguous = (int)g_contig.size();
     if (narrays) *narrays = (int)g_arrays.size();
@@ -191,6 +198,7 @@ int sipgpu_persist_count(int* nscalars, int* ncontiguous, int* narrays) {
 
 // ---- checkpoint file of the scalars + contiguous arrays, reference byte format ----
 int sipgpu_persist_checkpoint(const char* filename) {
+    SIP_TRACE("sipgpu_persist_checkpoint");
     if (!filename) return SIPGPU_E_ARG;
     if (!g_contig.empty()) SIP_TRY(ensure_init());
     SIP_TRY(wl_flush());
@@ -227,6 +235,7 @@ int sipgpu_persist_checkpoint(const char* filename) {
     return rc;
 }
 int sipgpu_persist_init_from_checkpoint(const char* filename) {
+    SIP_TRACE("sipgpu_persist_init_from_checkpoint");
     if (!filename) return SIPGPU_E_ARG;
     if (!g_scalars.empty() || !g_contig.empty()) {  // CHECKs of init_from_checkpoint (:204-205)
         set_error("init_from_checkpoint: persistent maps are not empty");

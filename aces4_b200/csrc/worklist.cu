@@ -972,6 +972,7 @@ using namespace sipgpu;
 extern "C" {
 
 int sipgpu_wl_begin(int flags) {
+    SIP_TRACE("sipgpu_wl_begin");
     if (g.on) {
         set_error("sipgpu_wl_begin: a recording is already open");
         return SIPGPU_E_STATE;
@@ -1022,8 +1023,10 @@ int sipgpu_wl_begin(int flags) {
     if (cfg_max_deferred) g.max_deferred_bytes = cfg_max_deferred;
     return SIPGPU_OK;
 }
-int sipgpu_wl_flush(void) { return wl_flush(); }
+int sipgpu_wl_flush(void) {
+    SIP_TRACE("sipgpu_wl_flush"); return wl_flush(); }
 int sipgpu_wl_end(void) {
+    SIP_TRACE("sipgpu_wl_end");
     if (!g.on) return SIPGPU_E_STATE;
     const int rc = wl_flush();
     g.on = false;
@@ -1031,16 +1034,19 @@ int sipgpu_wl_end(void) {
 }
 int sipgpu_wl_recording(void) { return g.on ? (g.dry ? 2 : 1) : 0; }
 int sipgpu_wl_set_limits(long long max_ops, long long max_deferred_bytes) {
+    SIP_TRACE("sipgpu_wl_set_limits");
     if (max_ops > 0) (g.on ? g.max_ops : cfg_max_ops) = (size_t)max_ops;
     if (max_deferred_bytes > 0) (g.on ? g.max_deferred_bytes : cfg_max_deferred) = (size_t)max_deferred_bytes;
     return SIPGPU_OK;
 }
-int sipgpu_wl_set_idle_flush(long long min_ops) {  // 0 disables the flush-when-the-device-is-idle policy
+int sipgpu_wl_set_idle_flush(long long min_ops) {
+    SIP_TRACE("sipgpu_wl_set_idle_flush");  // 0 disables the flush-when-the-device-is-idle policy
     if (g.on) g.idle_flush_ops = min_ops > 0 ? (size_t)min_ops : 0;
     else cfg_idle = min_ops > 0 ? min_ops : 0;
     return SIPGPU_OK;
 }
 int sipgpu_wl_stats(long long* out9) {
+    SIP_TRACE("sipgpu_wl_stats");
     if (!out9) return SIPGPU_E_ARG;
     const long long v[9] = {g.st_recorded, g.st_scheduled, g.st_levels, g.st_launches, g.st_fused_acc,
                             g.st_chains,   g.st_chain_pairs, g.st_temps_elided, g.st_flushes};
@@ -1049,6 +1055,7 @@ int sipgpu_wl_stats(long long* out9) {
 }
 long long sipgpu_wl_replays(void) { return g.st_replays; }
 int sipgpu_wl_last_plan(int cap, int* level_of_op, int* unit_of_op) {
+    SIP_TRACE("sipgpu_wl_last_plan");
     const int n = (int)g.last_level.size();
     for (int i = 0; i < n && i < cap; ++i) {
         if (level_of_op) level_of_op[i] = g.last_level[i];

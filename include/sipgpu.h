@@ -220,6 +220,14 @@ int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda,
 int sipgpu_dmma_peak_probe(int iters, double* tflops_out);
 /* device copy bandwidth probe (GB/s, read+write) over a buffer of `bytes` */
 int sipgpu_copy_bw_probe(size_t bytes, int reps, double* gbs_out);
+/* Per-entry-point trace: calls and host wall time of every C-ABI entry point since the last reset -- the table the
+ * reference's Tracer keeps per interpreter opcode (src/sip/worker/tracer.h:41-50: pc_histogram_, opcode_timer_), so that
+ * the two can be laid side by side.  Host time only: the device work of an entry point is asynchronous (device time per
+ * kernel is what ncu / the CUDA-event brackets of bench.py measure).  Off by default.  sipgpu_trace_report fills up to `cap`
+ * rows, most host time first (names are static strings), and returns the number of rows that have calls. */
+int sipgpu_trace_enable(int on);
+int sipgpu_trace_reset(void);
+int sipgpu_trace_report(int cap, const char** names, long long* calls, double* host_seconds);
 /* Launch-policy knobs for A/B measurements and for tests that must reach a particular kernel (defaults are the product
  * path).  "lowint_max_intensity": contractions with N <= 64 and at most this many flops per algorithmic byte run on the
  * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).

@@ -50,6 +50,8 @@ def main():
             w.run()
             w.run_proc("iteration")          # warm-up
             sip.sync()
+            if not fake:
+                sip.trace(True)
             l0, t0 = sip.kernel_launches(), time.perf_counter()
             for _ in range(iters):
                 e = be.value(w.run_proc("iteration")["ecorrab"])
@@ -59,6 +61,12 @@ def main():
                               "mode": "recorded" if record else "op-at-a-time", "ms_per_iteration": round(dt * 1e3, 2),
                               "launches_per_iteration": (sip.kernel_launches() - l0) // iters, "energy": e,
                               "backend": "fake (CPU)" if fake else "libsipgpu"}), flush=True)
+            if not fake:     # per-entry-point table of the timed iterations (the reference's Tracer keeps the same per opcode)
+                top = sip.trace_report()[:8]
+                sip.trace(False)
+                print(json.dumps({"program": program, "mode": "recorded" if record else "op-at-a-time", "trace_top8":
+                                  [{"entry": n, "calls_per_iteration": c // iters, "host_ms_per_iteration": round(s * 1e3 / iters, 3)}
+                                   for n, c, s in top]}), flush=True)
             for A in arrays.values():
                 A.destroy()
 

@@ -145,3 +145,19 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(api, "_HERE", str(tmp_path))
     with pytest.raises(api.SipGpuError, match="no CPU fallback"):
         api.lib()
+
+
+def test_trace_table_counts_calls_per_entry_point(sip):
+    """sipgpu_trace_*: the per-entry-point table (reference: Tracer's per-opcode histogram and timer, tracer.h:41-50) --
+    host-only entry points are enough to see it count"""
+    api = sip.api if hasattr(sip, "api") else sip
+    api.trace(True)
+    for _ in range(5):
+        api.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    api.lib().sipgpu_set_tuning(b"lowint_scope", 1.0)
+    rows = {name: (calls, secs) for name, calls, secs in api.trace_report()}
+    api.trace(False, reset=False)
+    assert rows["get_contraction_ptrn_"][0] == 5 and rows["get_contraction_ptrn_"][1] >= 0.0
+    assert rows["sipgpu_set_tuning"][0] == 1
+    api.get_contraction_ptrn([1, 2], [1, 3], [3, 2])      # tracing off: not counted
+    assert dict((n, c) for n, c, _ in api.trace_report())["get_contraction_ptrn_"] == 5
