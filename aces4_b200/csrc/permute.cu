@@ -8,6 +8,9 @@
 // memory, and writes it in output order (coalesced).  The per-element index arithmetic (the div/mod chains
 // of the reference's index walk, F90:531-654) is hoisted into two small offset tables built once per
 // (shape, permutation) on the host, cached on the device and shared by every tile and every later call.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -16,6 +19,7 @@
 #include "plan.h"
 
 namespace sipgpu {
+bool permute_bulk_enabled();
 namespace {
 
 constexpr int kPT = 256;        // threads per CTA
@@ -158,6 +162,179 @@ __global__ void __launch_bounds__(kPT, (EPT <= 4 ? 4 : EPT <= 8 ? 3 : 2) - (RAG 
     }
 }
 
+// ---- TMA variant: tiles are fetched by bulk copies (cp.async.bulk, SASS UBLKCP) issued by one warp into a ring of kBulkStages
+// staged tiles guarded by full / empty mbarriers; the threads never load from global memory -- they wait for a tile, read it
+// from shared memory in OUTPUT order and store it (coalesced), while the copies of the next kBulkStages - 1 tiles are in
+// flight.  Registers hold only the output-side table entries.
+constexpr int kBulkStages = 4;
+struct BulkArgs {
+    const int2* runtab;
+    const int4* wtab;
+    int nruns, te0, rs, stage_elems;
+};
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n"
+        " bra WAIT_%=;\n"
+        "DONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int EPT, bool RAG, bool ACC>
+__global__ void __launch_bounds__(kPT, (EPT <= 6 && !(RAG && ACC)) ? 3 : 2) permute_bulk_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b,
+                                                              const __grid_constant__ BulkArgs k) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ unsigned long long full[kBulkStages], empty[kBulkStages];
+    __shared__ double* s_dst[kBulkStages];
+    __shared__ int s_lim[kBulkStages][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kBulkStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kPT / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    int w_off[EPT], w_pos[EPT], w_rag[RAG ? EPT : 1];
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+        const int e = tid + u * kPT;
+        w_off[u] = w_pos[u] = 0;
+        if (RAG) w_rag[u] = kInvalid;
+        if (e < a.V) {
+            const int4 w = __ldg(k.wtab + e);
+            w_off[u] = w.x;
+            w_pos[u] = w.y;
+            if (RAG) w_rag[u] = w.z;
+        }
+    }
+    auto w_ok = [&](int u, int lim0, int lim1) {
+        if constexpr (RAG) return (w_rag[u] & 0xffff) < lim0 && (w_rag[u] >> 16) < lim1;
+        else return tid + u * kPT < a.V;
+    };
+    __syncthreads();
+    const long long total = a.ntiles * b.n;
+    const unsigned ntiles32 = (unsigned)a.ntiles;
+    auto decode = [&](long long work, const double*& src, double*& dst, int& lim0, int& lim1) {
+        const int blk = total < (1LL << 31) ? (int)((unsigned)work / ntiles32) : (int)(work / a.ntiles);
+        unsigned t = (unsigned)(work - (long long)blk * a.ntiles);
+        int bin = 0, bout = 0;
+        lim0 = lim1 = kNoLimit;
+#pragma unroll 1
+        for (int d = 0; d < a.rank; ++d) {
+            const unsigned q = t / (unsigned)a.ntile[d];
+            const int c = (int)(t - q * (unsigned)a.ntile[d]);
+            t = q;
+            bin += c * a.tstep_in[d];
+            bout += c * a.tstep_out[d];
+            if (RAG) {
+                if (d == a.rag_dim[0]) lim0 = min(a.rag_te[0], a.rag_ext[0] - c * a.rag_te[0]);
+                if (d == a.rag_dim[1]) lim1 = min(a.rag_te[1], a.rag_ext[1] - c * a.rag_te[1]);
+            }
+        }
+        src = (b.in ? b.in[blk] : b.in0) + bin;
+        dst = (b.in ? b.out[blk] : b.out0) + bout;
+    };
+    // warp 0: fetch item number j of this CTA (work = blockIdx.x + j * gridDim.x) into stage j % kBulkStages
+    auto produce = [&](long long j) {
+        const long long work = blockIdx.x + j * (long long)gridDim.x;
+        if (work >= total) return;
+        const int s = (int)(j % kBulkStages);
+        mbar_wait(empty + s, (int)((j / kBulkStages) & 1) ^ 1);   // everybody has read what the stage held (first lap: at once)
+        const double* src;
+        double* dst;
+        int lim0, lim1;
+        decode(work, src, dst, lim0, lim1);
+        double* stage = sm + (size_t)s * k.stage_elems;
+        unsigned bytes = 0;
+        for (int rr = lane; rr < k.nruns; rr += 32) {
+            const int2 r = __ldg(k.runtab + rr);
+            int len = k.te0;
+            bool ok = true;
+            if (RAG) {   // a ragged dimension 0 shortens the run, any other one drops whole runs
+                if (a.rag_dim[0] == 0) len = min(len, lim0); else ok = ok && (r.y & 0xffff) < lim0;
+                if (a.rag_dim[1] == 0) len = min(len, lim1); else ok = ok && (r.y >> 16) < lim1;
+            }
+            if (ok && len > 0) {
+                bulk_g2s(stage + rr * k.rs, src + r.x, (unsigned)len * 8u, full + s);
+                bytes += (unsigned)len * 8u;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        if (lane == 0) {
+            s_dst[s] = dst;
+            s_lim[s][0] = lim0;
+            s_lim[s][1] = lim1;
+            mbar_arrive_expect_tx(full + s, bytes);   // the one pending arrival gates the phase until the byte count is known
+        }
+    };
+    if (warp == 0)
+        for (int j = 0; j < kBulkStages - 1; ++j) produce(j);
+    for (long long j = 0;; ++j) {
+        const long long work = blockIdx.x + j * (long long)gridDim.x;
+        if (work >= total) break;
+        if (warp == 0) produce(j + kBulkStages - 1);
+        const int s = (int)(j % kBulkStages);
+        mbar_wait(full + s, (int)((j / kBulkStages) & 1));
+        const double* stage = sm + (size_t)s * k.stage_elems;
+        double* __restrict__ cdst = s_dst[s];
+        const int lim0 = s_lim[s][0], lim1 = s_lim[s][1];
+        if (ACC) {
+            double o[EPT];
+#pragma unroll
+            for (int u = 0; u < EPT; ++u)
+                if (w_ok(u, lim0, lim1)) o[u] = cdst[w_off[u]];
+#pragma unroll
+            for (int u = 0; u < EPT; ++u)
+                if (w_ok(u, lim0, lim1)) cdst[w_off[u]] = b.alpha * stage[w_pos[u]] + b.beta * o[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < EPT; ++u)
+                if (w_ok(u, lim0, lim1)) cdst[w_off[u]] = stage[w_pos[u]];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+template <int EPT>
+int launch_perm_bulk(const PermArgs& a, const PermBatch& b, const BulkArgs& k, bool acc, int grid, size_t smem, cudaStream_t st) {
+    const bool rag = a.rag_dim[0] >= 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SIP_CUDA(cudaFuncSetAttribute(permute_bulk_kernel<EPT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_bulk_kernel<EPT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_bulk_kernel<EPT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_bulk_kernel<EPT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    if (rag) {
+        if (acc) permute_bulk_kernel<EPT, true, true><<<grid, kPT, smem, st>>>(a, b, k);
+        else permute_bulk_kernel<EPT, true, false><<<grid, kPT, smem, st>>>(a, b, k);
+    } else {
+        if (acc) permute_bulk_kernel<EPT, false, true><<<grid, kPT, smem, st>>>(a, b, k);
+        else permute_bulk_kernel<EPT, false, false><<<grid, kPT, smem, st>>>(a, b, k);
+    }
+    return SIPGPU_OK;
+}
+
 template <int EPT>
 int launch_perm(const PermArgs& a, const PermBatch& b, bool acc, int grid, size_t smem, cudaStream_t st) {
     const bool rag = a.rag_dim[0] >= 0;
@@ -179,15 +356,24 @@ int ew_axpby(double* d, const double* s, long long n, double alpha, double beta)
     return ew_axpy(d, s, n, alpha);
 }
 
+// TMA path (cp.async.bulk): a tile arrives as `nruns` bulk copies of `te0` contiguous input elements each, laid out run by run
+// in shared memory (run stride te0 + 2 doubles: 16-byte aligned, and consecutive runs start two banks apart)
+struct BulkPlan {
+    bool ok = false;
+    const int2* runtab = nullptr;   // [nruns] {input offset of the run inside the tile, ragged coordinates of the run}
+    const int4* wtab = nullptr;     // output order: {out offset, position in the staged tile, ragged coords, -}
+    int nruns = 0, te0 = 0, rs = 0;
+};
 struct PlanEntry {
     PermArgs args;
+    BulkPlan bulk;
 };
 std::unordered_map<std::string, PlanEntry>& cache() {
     static std::unordered_map<std::string, PlanEntry> c;
     return c;
 }
 
-int build_plan_host(const PermShape& ps, PermArgs* out, std::vector<int2>& rt, std::vector<int4>& wt) {
+int build_plan_host(const PermShape& ps, PermArgs* out, std::vector<int2>& rt, std::vector<int4>& wt, int* te_out = nullptr) {
     const int r = ps.rank;
     int oorder[kMaxRank];  // dims by ascending output stride
     for (int i = 0; i < r; ++i) oorder[i] = i;
@@ -293,6 +479,8 @@ int build_plan_host(const PermShape& ps, PermArgs* out, std::vector<int2>& rt, s
         }
         wt[e] = make_int4(off, sp, pack(idx), 0);
     }
+    if (te_out)
+        for (int d = 0; d < kMaxRank; ++d) te_out[d] = d < r ? te[d] : 1;
     *out = a;
     return SIPGPU_OK;
 }
@@ -301,8 +489,35 @@ int build_plan(const PermShape& ps, PlanEntry* out) {
     PermArgs a;
     std::vector<int2> rt;
     std::vector<int4> wt;
-    SIP_TRY(build_plan_host(ps, &a, rt, wt));
+    int te[kMaxRank];
+    SIP_TRY(build_plan_host(ps, &a, rt, wt, te));
     const int V = a.V;
+    // ---- TMA path: dimension 0 is the input's contiguous one; every run (te[0] elements) must be a whole number of
+    // 16-byte units at a 16-byte aligned address: even tile extent and even extent along it (then every other input stride,
+    // a product of extents that contains ext[0], is even as well) ----
+    BulkPlan bp;
+    if (ps.in_stride[0] == 1 && te[0] >= 4 && te[0] % 2 == 0 && ps.ext[0] % 2 == 0 && V % te[0] == 0 && V / te[0] <= 1024) {
+        bp.te0 = te[0];
+        bp.rs = te[0] + 2;
+        bp.nruns = V / te[0];
+        std::vector<int2> runs((size_t)bp.nruns);
+        for (int rr = 0; rr < bp.nruns; ++rr) runs[rr] = rt[(size_t)rr * te[0]];   // first element of the run: {offset, ragged coords}
+        std::vector<int4> wb(wt);
+        for (int e = 0; e < V; ++e) {   // staged position: input-order index sp -> run sp / te0, element sp % te0
+            const int sp = wt[e].y;
+            wb[e].y = (sp / te[0]) * bp.rs + sp % te[0];
+        }
+        int2* d_runs = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * runs.size()));
+        int4* d_wb = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * wb.size()));
+        if (!d_runs || !d_wb) return SIPGPU_E_NOMEM;
+        SIP_CUDA(cudaMemcpyAsync(d_runs, runs.data(), sizeof(int2) * runs.size(), cudaMemcpyHostToDevice, ctx().stream));
+        SIP_CUDA(cudaMemcpyAsync(d_wb, wb.data(), sizeof(int4) * wb.size(), cudaMemcpyHostToDevice, ctx().stream));
+        SIP_CUDA(cudaStreamSynchronize(ctx().stream));
+        bp.runtab = d_runs;
+        bp.wtab = d_wb;
+        bp.ok = true;
+    }
+    out->bulk = bp;
     int2* d_rt = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * V));
     int4* d_wt = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * V));
     if (!d_rt || !d_wt) return SIPGPU_E_NOMEM;
@@ -319,6 +534,13 @@ int build_plan(const PermShape& ps, PlanEntry* out) {
 }  // namespace
 
 void permute_cache_clear() { cache().clear(); }
+
+static int& permute_bulk_flag() {
+    static int v = [] { const char* e = getenv("SIPGPU_PERMUTE_BULK"); return e ? atoi(e) : 1; }();
+    return v;
+}
+bool permute_bulk_enabled() { return permute_bulk_flag() != 0; }
+void permute_set_bulk(int on) { permute_bulk_flag() = on; }
 
 // Host-only view of the plan for CPU tests of the tiling logic (no device needed).
 // meta = {rank, V, ntiles, rag_dim0, rag_te0, rag_ext0, rag_dim1, rag_te1, rag_ext1, ntile[6], tstep_in[6], tstep_out[6]}
@@ -406,6 +628,42 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
     int ept = 16;
     for (int cand : {4, 6, 8, 10, 12})
         if (a.V <= cand * kPT) { ept = cand; break; }
+    // ---- TMA path: bulk copies need 16-byte aligned runs, i.e. 16-byte aligned blocks on top of the plan's conditions ----
+    const BulkPlan& bp = it->second.bulk;
+    bool bulk = bp.ok && permute_bulk_enabled();
+    for (int i = 0; i < n && bulk; ++i) bulk = (((uintptr_t)in[i]) & 15) == 0;
+    if (bulk) {
+        BulkArgs k;
+        k.runtab = bp.runtab;
+        k.wtab = bp.wtab;
+        k.nruns = bp.nruns;
+        k.te0 = bp.te0;
+        k.rs = bp.rs;
+        k.stage_elems = bp.nruns * bp.rs;
+        const size_t smem = sizeof(double) * (size_t)kBulkStages * k.stage_elems;
+        if (smem <= 160 * 1024) {
+            const long long reg_cap = (ept <= 6 && !(acc && a.rag_dim[0] >= 0)) ? 3 : 2;
+            long long per_sm = std::max<long long>(1, std::min<long long>(reg_cap, (long long)(210 * 1024) / (long long)(smem + 2048)));
+            long long grid = a.ntiles * n;
+            if (grid > c.num_sms * per_sm) grid = c.num_sms * per_sm;
+            auto go = [a, b, k, acc, ept, grid, smem]() -> int {
+                cudaStream_t st = ctx().stream;
+                switch (ept) {
+                    case 4: SIP_TRY(launch_perm_bulk<4>(a, b, k, acc, (int)grid, smem, st)); break;
+                    case 6: SIP_TRY(launch_perm_bulk<6>(a, b, k, acc, (int)grid, smem, st)); break;
+                    case 8: SIP_TRY(launch_perm_bulk<8>(a, b, k, acc, (int)grid, smem, st)); break;
+                    case 10: SIP_TRY(launch_perm_bulk<10>(a, b, k, acc, (int)grid, smem, st)); break;
+                    case 12: SIP_TRY(launch_perm_bulk<12>(a, b, k, acc, (int)grid, smem, st)); break;
+                    default: SIP_TRY(launch_perm_bulk<16>(a, b, k, acc, (int)grid, smem, st)); break;
+                }
+                SIP_CUDA(cudaGetLastError());
+                count_launch();
+                return SIPGPU_OK;
+            };
+            if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+            return go();
+        }
+    }
     const size_t smem = sizeof(double) * (size_t)(skew_host(ept * kPT) + 1);  // every thread parks all its EPT slots
     // persistent CTAs: as many as fit per SM (registers: 4-6 of 256 threads; shared memory: 227 KB / tile)
     long long per_sm = (long long)(200 * 1024) / (long long)(smem + 1024);

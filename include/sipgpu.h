@@ -232,7 +232,9 @@ int sipgpu_trace_report(int cap, const char** names, long long* calls, double* h
  * path).  "lowint_max_intensity": contractions with N <= 64 and at most this many flops per algorithmic byte run on the
  * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).
  * "lowint_scope": 0 never, 1 (default) dot products + single-tile destinations where that kernel measured faster than the
- * 128-wide tiles, 2 every eligible shape (tests, A/B).  Returns SIPGPU_E_ARG for an unknown key.  Host-only. */
+ * 128-wide tiles, 2 every eligible shape (tests, A/B).  "permute_bulk": 1 (default) permutes whose input runs are 16-byte
+ * aligned fetch their tiles with TMA bulk copies (cp.async.bulk), 0 the register-staged kernel only.  Returns SIPGPU_E_ARG
+ * for an unknown key.  Host-only. */
 int sipgpu_set_tuning(const char* key, double value);
 
 /* host-only views of the planner (no device needed; used by the CPU tests of the host logic) */

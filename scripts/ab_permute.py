@@ -23,6 +23,7 @@ def time_ms(fn, reps=5, warm=2):
     return float(np.median(ts))
 
 
+api.set_tuning("permute_bulk", int(os.environ.get("PERMUTE_BULK", "1")))
 out = {}
 for shape, n in (((16,) * 4, 1024), ((32,) * 4, 128), ((64,) * 4, 8), ((50, 20, 50, 20), 128)):
     ins = [api.DeviceBlock(shape).fill(1.0) for _ in range(n)]
@@ -38,4 +39,4 @@ for shape, n in (((16,) * 4, 1024), ((32,) * 4, 128), ((64,) * 4, 8), ((50, 20, 
     out[str(shape)] = {"blocks": n, "min": round(min(res)), "median": round(float(np.median(res))), "max": round(max(res)),
                        "acc_median": round(float(np.median(acc)))}
     del ins, outs
-print(os.environ.get("SIPGPU_LIB", "default"), json.dumps(out), flush=True)
+print(json.dumps({"permute_bulk": int(os.environ.get("PERMUTE_BULK", "1")), "GBps": out}), flush=True)

@@ -125,8 +125,18 @@ def test_sum_op_and_scale(sip, oracle):
 # ---------------------------------------------------------------------------------------------------
 # permutes: every rank-4 pattern, ragged and tiny extents, ranks 2..6
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(16, 16, 16, 16), (13, 30, 50, 7), (5, 8, 9, 5), (32, 3, 1, 33), (64, 20, 2, 50)])
-def test_all_rank4_permutes(sip, oracle, shape):
+@pytest.fixture(params=["tma", "registers"])
+def permute_route(request, sip):
+    """permutes whose input runs are 16-byte aligned fetch their tiles with TMA bulk copies (cp.async.bulk) by default; the
+    same cases are also forced through the register-staged kernel, so that both stay covered"""
+    sip.set_tuning("permute_bulk", 1 if request.param == "tma" else 0)
+    yield request.param
+    sip.set_tuning("permute_bulk", 1)
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16, 16), (13, 30, 50, 7), (5, 8, 9, 5), (32, 3, 1, 33), (64, 20, 2, 50), (50, 20, 50, 20),
+                                   (18, 6, 34, 10), (40, 40, 40, 6)])
+def test_all_rank4_permutes(sip, oracle, shape, permute_route):
     rng = np.random.default_rng(7)
     a = rand_block(rng, shape)
     da = sip.DeviceBlock.from_numpy(a)
@@ -138,11 +148,11 @@ def test_all_rank4_permutes(sip, oracle, shape):
 
 
 @pytest.mark.parametrize("rank", [1, 2, 3, 5, 6])
-def test_permutes_other_ranks(sip, oracle, rank):
+def test_permutes_other_ranks(sip, oracle, rank, permute_route):
     rng = np.random.default_rng(rank)
     pyrng = random.Random(rank)
     for trial in range(12):
-        shape = tuple(pyrng.choice([1, 2, 3, 5, 8, 11, 16, 21]) for _ in range(rank))
+        shape = tuple(pyrng.choice([1, 2, 3, 5, 8, 11, 16, 21, 6, 12]) for _ in range(rank))
         perm = list(range(rank))
         pyrng.shuffle(perm)
         a = rand_block(rng, shape)
@@ -151,8 +161,8 @@ def test_permutes_other_ranks(sip, oracle, rank):
         assert np.array_equal(out, oracle.block_copy(a, transp)), (shape, perm)
 
 
-@pytest.mark.parametrize("shape", [(50, 20, 50, 20), (13, 30, 7, 9), (64, 64, 16, 3), (70, 70, 70)])
-def test_permute_batched_and_accumulate(sip, oracle, shape):
+@pytest.mark.parametrize("shape", [(50, 20, 50, 20), (13, 30, 7, 9), (64, 64, 16, 3), (70, 70, 70), (66, 10, 34), (16, 16, 16, 16)])
+def test_permute_batched_and_accumulate(sip, oracle, shape, permute_route):
     """n blocks per launch, plain and fused permute-accumulate (out = alpha * P(in) + beta * out), incl. tiles of
     every element-per-thread class and ragged tiles."""
     rng = np.random.default_rng(11)
