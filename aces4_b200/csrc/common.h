@@ -86,7 +86,7 @@ struct TraceScope {
 long long& mem_epoch();
 
 // device pool (pool.cu)
-double* pool_alloc(size_t bytes);
+double* pool_alloc(size_t bytes, bool fresh = false);   // fresh: never a recycled block (long-lived plan tables)
 int pool_free(void* p);
 
 }  // namespace sipgpu

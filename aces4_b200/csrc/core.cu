@@ -198,12 +198,15 @@ int desc_commit(void* h, void* d, size_t bytes) {
     return SIPGPU_OK;
 }
 
-double* pool_alloc(size_t bytes) {
+// fresh: carve new arena space even when a recycled block of the size is free -- for tables that live as long as the library
+// (plan caches).  Taking a freed temp's slot would shift the addresses the next identical recording gets and defeat the
+// replay cache for one round.
+double* pool_alloc(size_t bytes, bool fresh) {
     if (ensure_init() != SIPGPU_OK) return nullptr;
     const size_t sz = round_up(bytes ? bytes : 1);
     auto fl = g_pool.free_lists.find(sz);
     void* p = nullptr;
-    if (fl != g_pool.free_lists.end() && !fl->second.empty()) {
+    if (!fresh && fl != g_pool.free_lists.end() && !fl->second.empty()) {
         // lowest free address first (min-heap): the address a block gets depends only on WHICH blocks are live, not on
         // the order earlier frees happened in -- so the same program point of every CC iteration sees the same addresses,
         // which is what lets the deferred op stream recognise a repeated recording (worklist.cu replay cache)

@@ -26,7 +26,8 @@ int ew_scale_many(int n, double* const* d, const long long* cnt, double beta);
 int permute_block(int rank, const int* ext, const int* transp, const double* in, double* out);
 int permute_batched(int n, int rank, const int* ext, const int* transp, const double* const* in, double* const* out,
                     double alpha, double beta);
-void permute_set_bulk(int on);  // 1 (default): TMA bulk-copy variant where the plan allows it; 0: register-staged variant only
+void permute_set_bulk(int variant);  // permute kernel: 0 register-staged tiles, 1 TMA bulk copies where the plan allows it, 2 cp.async ring, 3 chosen per launch (default)
+void permute_set_vec(int on);        // ring variant: 16-byte cp.async / stores where the runs are even and aligned: 1 always, 0 never, -1 for big tiles (default)
 int permute_plan_debug(int rank, const int* ext, const int* transp, long long* meta, int* rtab, int* wtab, int cap);
 
 // superinstr.cu: elementwise CC super-instructions on device blocks

@@ -451,7 +451,7 @@ int get_tables(const Shape& s, Tables* out) {
             offsets_of(k, s.nk, s.kext, s.ksL, s.ksR, oL, oR);
             hk[k] = make_int2(oL, oR);
         }
-    int2* d = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * h.size()));
+    int2* d = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * h.size(), true));
     if (!d) return SIPGPU_E_NOMEM;
     // built once per shape; a blocking upload keeps the host vector simple (as permute.cu's plan tables)
     SIP_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(int2) * h.size(), cudaMemcpyHostToDevice, ctx().stream));

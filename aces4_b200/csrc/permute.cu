@@ -20,6 +20,8 @@
 
 namespace sipgpu {
 bool permute_bulk_enabled();
+int permute_variant();
+int permute_vec_mode();
 namespace {
 
 constexpr int kPT = 256;        // threads per CTA
@@ -314,6 +316,195 @@ __global__ void __launch_bounds__(kPT, (EPT <= 6 && !(RAG && ACC)) ? 3 : 2) perm
     }
 }
 
+// ---- cp.async ring variant: a tile is fetched straight into a ring of kRingStages staged tiles in shared memory (LDGSTS, no
+// registers in between), so every CTA keeps kRingStages - 1 whole tiles of loads in flight while it stores the tile that has
+// landed; ONE barrier per tile.  VLD: 16-byte cp.async when the input runs are even and 16-byte aligned; VST: 16-byte global
+// stores (two 8-byte shared-memory reads of output-adjacent elements) when the output runs are.  Registers hold table entries only.
+constexpr int kRingStages = 3;
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// The staged position of every tile element comes from the plan (ptab / wtab.y, .w): the host searches a padded layout per
+// (shape, permutation) that keeps the output-order reads of a warp off each other's banks (ring_layout below).
+
+constexpr int ring_min_ctas(int ept, bool heavy) { return (ept <= 4 ? 4 : ept <= 8 ? 3 : 2) - (heavy ? 1 : 0); }   // heavy: ragged tiles or fused accumulate (more registers)
+
+template <int EPT, bool RAG, bool ACC, bool VLD, bool VST>
+__global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_ring_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b, const int* __restrict__ ptab,
+                                                                               const int4* __restrict__ wtab, int stage_elems) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int NL = VLD ? EPT / 2 : EPT;   // load units per thread (elements or pairs)
+    constexpr int NS = VST ? EPT / 2 : EPT;   // store units per thread
+    const int tid = threadIdx.x;
+    int r_off[NL], r_pos[NL], r_rag[RAG ? NL : 1];
+    int w_off[NS], w_p0[NS], w_p1[VST ? NS : 1], w_rag[RAG ? NS : 1];
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+        const int e = (tid + u * kPT) * (VLD ? 2 : 1);
+        r_off[u] = r_pos[u] = 0;
+        if (RAG) r_rag[u] = kInvalid;
+        if (e < a.V) {
+            const int2 r = __ldg(a.rtab + e);
+            r_off[u] = r.x;
+            r_pos[u] = __ldg(ptab + e);
+            if (RAG) r_rag[u] = r.y;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        const int e = (tid + u * kPT) * (VST ? 2 : 1);
+        w_off[u] = w_p0[u] = 0;
+        if (VST) w_p1[u] = 0;
+        if (RAG) w_rag[u] = kInvalid;
+        if (e < a.V) {
+            const int4 w = __ldg(wtab + e);
+            w_off[u] = w.x;
+            w_p0[u] = w.y;
+            if (RAG) w_rag[u] = w.z;
+            if (VST) w_p1[u] = w.w;
+        }
+    }
+    auto r_ok = [&](int u, int lim0, int lim1) {
+        if constexpr (RAG) return (r_rag[u] & 0xffff) < lim0 && (r_rag[u] >> 16) < lim1;
+        else return (tid + u * kPT) * (VLD ? 2 : 1) < a.V;
+    };
+    auto w_ok = [&](int u, int lim0, int lim1) {
+        if constexpr (RAG) return (w_rag[u] & 0xffff) < lim0 && (w_rag[u] >> 16) < lim1;
+        else return (tid + u * kPT) * (VST ? 2 : 1) < a.V;
+    };
+    const long long total = a.ntiles * b.n;
+    const unsigned ntiles32 = (unsigned)a.ntiles;
+    auto decode = [&](long long work, const double*& src, double*& dst, int& lim0, int& lim1) {
+        const int blk = total < (1LL << 31) ? (int)((unsigned)work / ntiles32) : (int)(work / a.ntiles);
+        unsigned t = (unsigned)(work - (long long)blk * a.ntiles);
+        int bin = 0, bout = 0;
+        lim0 = lim1 = kNoLimit;
+#pragma unroll 1
+        for (int d = 0; d < a.rank; ++d) {
+            const unsigned q = t / (unsigned)a.ntile[d];
+            const int c = (int)(t - q * (unsigned)a.ntile[d]);
+            t = q;
+            bin += c * a.tstep_in[d];
+            bout += c * a.tstep_out[d];
+            if (RAG) {
+                if (d == a.rag_dim[0]) lim0 = min(a.rag_te[0], a.rag_ext[0] - c * a.rag_te[0]);
+                if (d == a.rag_dim[1]) lim1 = min(a.rag_te[1], a.rag_ext[1] - c * a.rag_te[1]);
+            }
+        }
+        src = (b.in ? b.in[blk] : b.in0) + bin;
+        dst = (b.in ? b.out[blk] : b.out0) + bout;
+    };
+    // destination and ragged limits of the tiles in flight: a register ring shifted once per tile (kRingStages == 3)
+    double *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+    int l00 = kNoLimit, l01 = kNoLimit, l10 = kNoLimit, l11 = kNoLimit, l20 = kNoLimit, l21 = kNoLimit;
+    auto issue = [&](long long work, int stage, double*& dst, int& lim0, int& lim1) {
+        if (work < total) {
+            const double* src;
+            decode(work, src, dst, lim0, lim1);
+            double* st = sm + (size_t)stage * stage_elems;
+#pragma unroll
+            for (int u = 0; u < NL; ++u)
+                if (r_ok(u, lim0, lim1)) {
+                    if (VLD) cp_async16(st + r_pos[u], src + r_off[u]);
+                    else cp_async8(st + r_pos[u], src + r_off[u]);
+                }
+        }
+        cp_async_commit();
+    };
+    const long long w0 = blockIdx.x, step = gridDim.x;
+    issue(w0, 0, d0, l00, l01);
+    issue(w0 + step, 1, d1, l10, l11);
+    int stage = 0;
+    for (long long work = w0; work < total; work += step) {
+        cp_async_wait<kRingStages - 2>();   // this thread's copies of the current tile have landed ...
+        __syncthreads();                     // ... everybody's have, and everybody is done reading the stage refilled next
+        int nstage = stage + 2;
+        if (nstage >= kRingStages) nstage -= kRingStages;
+        issue(work + 2 * step, nstage, d2, l20, l21);
+        const double* st = sm + (size_t)stage * stage_elems;
+        double* __restrict__ cdst = d0;
+        if constexpr (VST) {
+            if (ACC) {
+                double2 o[NS];
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) o[u] = *reinterpret_cast<const double2*>(cdst + w_off[u]);
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) {
+                        double2 v;
+                        v.x = b.alpha * st[w_p0[u]] + b.beta * o[u].x;
+                        v.y = b.alpha * st[w_p1[u]] + b.beta * o[u].y;
+                        *reinterpret_cast<double2*>(cdst + w_off[u]) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) {
+                        double2 v;
+                        v.x = st[w_p0[u]];
+                        v.y = st[w_p1[u]];
+                        *reinterpret_cast<double2*>(cdst + w_off[u]) = v;
+                    }
+            }
+        } else {
+            if (ACC) {
+                double o[NS];
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) o[u] = cdst[w_off[u]];
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = b.alpha * st[w_p0[u]] + b.beta * o[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < NS; ++u)
+                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = st[w_p0[u]];
+            }
+        }
+        d0 = d1; l00 = l10; l01 = l11;
+        d1 = d2; l10 = l20; l11 = l21;
+        if (++stage == kRingStages) stage = 0;
+    }
+    cp_async_wait<0>();
+}
+
+template <int EPT, bool VLD, bool VST>
+int launch_perm_ring2(const PermArgs& a, const PermBatch& b, const int* ptab, const int4* wtab, bool acc, int grid, size_t smem, int stage_elems,
+                      cudaStream_t st) {
+    const bool rag = a.rag_dim[0] >= 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SIP_CUDA(cudaFuncSetAttribute(permute_ring_kernel<EPT, true, true, VLD, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_ring_kernel<EPT, true, false, VLD, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_ring_kernel<EPT, false, true, VLD, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(permute_ring_kernel<EPT, false, false, VLD, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_set = true;
+    }
+    if (rag) {
+        if (acc) permute_ring_kernel<EPT, true, true, VLD, VST><<<grid, kPT, smem, st>>>(a, b, ptab, wtab, stage_elems);
+        else permute_ring_kernel<EPT, true, false, VLD, VST><<<grid, kPT, smem, st>>>(a, b, ptab, wtab, stage_elems);
+    } else {
+        if (acc) permute_ring_kernel<EPT, false, true, VLD, VST><<<grid, kPT, smem, st>>>(a, b, ptab, wtab, stage_elems);
+        else permute_ring_kernel<EPT, false, false, VLD, VST><<<grid, kPT, smem, st>>>(a, b, ptab, wtab, stage_elems);
+    }
+    return SIPGPU_OK;
+}
+template <int EPT>
+int launch_perm_ring(const PermArgs& a, const PermBatch& b, const int* ptab, const int4* wtab, bool acc, bool vld, bool vst, int grid, size_t smem,
+                     int stage_elems, cudaStream_t st) {
+    if (vld) return vst ? launch_perm_ring2<EPT, true, true>(a, b, ptab, wtab, acc, grid, smem, stage_elems, st)
+                        : launch_perm_ring2<EPT, true, false>(a, b, ptab, wtab, acc, grid, smem, stage_elems, st);
+    return vst ? launch_perm_ring2<EPT, false, true>(a, b, ptab, wtab, acc, grid, smem, stage_elems, st)
+               : launch_perm_ring2<EPT, false, false>(a, b, ptab, wtab, acc, grid, smem, stage_elems, st);
+}
+
 template <int EPT>
 int launch_perm_bulk(const PermArgs& a, const PermBatch& b, const BulkArgs& k, bool acc, int grid, size_t smem, cudaStream_t st) {
     const bool rag = a.rag_dim[0] >= 0;
@@ -367,7 +558,68 @@ struct BulkPlan {
 struct PlanEntry {
     PermArgs args;
     BulkPlan bulk;
+    bool vld_ok = false, vst_ok = false;   // ring variant: 16-byte loads / stores possible (given 16-byte aligned blocks)
+    const int* ring_ptab = nullptr;        // ring variant: staged position of tile element e (input order)
+    const int4* ring_wtab = nullptr;       //   output order: {out offset, staged position, ragged coords, staged position of the next element}
+    int ring_stage_elems = 0;
 };
+
+// Staged layout of a tile for the ring variant: p(e) = e + pad1 * (e / R1) + pad2 * (e / R2), R = the tile strides of the dimensions
+// (where a warp's output-order walk jumps), pads searched so that the 8-byte shared-memory reads of every half-warp spread over
+// the 16 bank pairs.  `even`: 16-byte staging keeps pairs aligned (even pads only; same-parity reads are then 2-way conflicted at best).
+// sp_of[e_out] = input-order index of output-order element e_out; pairs: the threads read elements (2q, 2q + 1).
+static long long ring_read_cost(const std::vector<int>& pos, const std::vector<int>& sp_of, bool pairs) {
+    const int V = (int)sp_of.size();
+    long long cost = 0;
+    const int unit = pairs ? 2 : 1;
+    for (int part = 0; part < unit; ++part)
+        for (int base = 0; base * unit < V; base += 16) {   // one half-warp: 16 consecutive units
+            int cnt[16] = {0};
+            int worst = 0;
+            for (int l = 0; l < 16; ++l) {
+                const int e = (base + l) * unit + part;
+                if (e >= V) break;
+                const int c = ++cnt[pos[sp_of[e]] & 15];
+                if (c > worst) worst = c;
+            }
+            cost += worst;
+        }
+    return cost;
+}
+static void ring_layout(int rank, const int* te, const std::vector<int>& sp_of, bool even, bool pairs, std::vector<int>& pos, int* stage_elems) {
+    const int V = (int)sp_of.size();
+    std::vector<int> strides;
+    { int s = 1; for (int d = 0; d < rank; ++d) { if (s > 1 && te[d] > 1) strides.push_back(s); s *= te[d]; } }
+    strides.push_back(32);
+    std::sort(strides.begin(), strides.end());
+    strides.erase(std::unique(strides.begin(), strides.end()), strides.end());
+    const int step = even ? 2 : 1;
+    auto fill = [&](int r1, int p1, int r2, int p2, std::vector<int>& out) {
+        out.resize(V);
+        for (int e = 0; e < V; ++e) out[e] = e + p1 * (e / r1) + (r2 ? p2 * (e / r2) : 0);
+    };
+    long long best = -1;
+    int b_r1 = 32, b_p1 = 0, b_r2 = 0, b_p2 = 0;
+    std::vector<int> cand;
+    auto consider = [&](int r1, int p1, int r2, int p2) {
+        if (even && ((r1 & 1) || (r2 & 1))) return;   // a pad may only fall between pairs
+        fill(r1, p1, r2, p2, cand);
+        if ((long long)cand[V - 1] + 2 > (long long)V + V / 4 + 64) return;   // bounded shared-memory overhead
+        const long long c = ring_read_cost(cand, sp_of, pairs);
+        if (best < 0 || c < best) { best = c; b_r1 = r1; b_p1 = p1; b_r2 = r2; b_p2 = p2; }
+    };
+    consider(32, 0, 0, 0);
+    for (int r1 : strides)
+        for (int p1 = step; p1 <= 8; p1 += step) consider(r1, p1, 0, 0);
+    const long long ideal = (V / (pairs ? 2 : 1) + 15) / 16 * (pairs ? 2 : 1) * ((even || pairs) ? 2 : 1);
+    if (best > ideal + ideal / 8)   // two levels of padding
+        for (size_t i = 0; i < strides.size(); ++i)
+            for (size_t j = i + 1; j < strides.size(); ++j)
+                for (int p1 = 0; p1 <= 8; p1 += step)
+                    for (int p2 = step; p2 <= 8; p2 += step) consider(strides[i], p1, strides[j], p2);
+    fill(b_r1, b_p1, b_r2, b_p2, pos);
+    *stage_elems = (pos[V - 1] + 2 + 1) & ~1;
+}
 std::unordered_map<std::string, PlanEntry>& cache() {
     static std::unordered_map<std::string, PlanEntry> c;
     return c;
@@ -507,8 +759,8 @@ int build_plan(const PermShape& ps, PlanEntry* out) {
             const int sp = wt[e].y;
             wb[e].y = (sp / te[0]) * bp.rs + sp % te[0];
         }
-        int2* d_runs = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * runs.size()));
-        int4* d_wb = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * wb.size()));
+        int2* d_runs = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * runs.size(), true));
+        int4* d_wb = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * wb.size(), true));
         if (!d_runs || !d_wb) return SIPGPU_E_NOMEM;
         SIP_CUDA(cudaMemcpyAsync(d_runs, runs.data(), sizeof(int2) * runs.size(), cudaMemcpyHostToDevice, ctx().stream));
         SIP_CUDA(cudaMemcpyAsync(d_wb, wb.data(), sizeof(int4) * wb.size(), cudaMemcpyHostToDevice, ctx().stream));
@@ -518,8 +770,32 @@ int build_plan(const PermShape& ps, PlanEntry* out) {
         bp.ok = true;
     }
     out->bulk = bp;
-    int2* d_rt = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * V));
-    int4* d_wt = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * V));
+    {   // 16-byte accesses of the ring variant: the tile extent and the block extent along the contiguous dimension must be even
+        // (then every other stride and every tile step on that side is even as well)
+        int o0 = 0;
+        for (int d = 0; d < ps.rank; ++d)
+            if (ps.out_stride[d] < ps.out_stride[o0]) o0 = d;
+        out->vld_ok = ps.in_stride[0] == 1 && te[0] % 2 == 0 && ps.ext[0] % 2 == 0;
+        out->vst_ok = ps.out_stride[o0] == 1 && te[o0] % 2 == 0 && ps.ext[o0] % 2 == 0;
+        std::vector<int> sp_of((size_t)V), pos;
+        for (int e = 0; e < V; ++e) sp_of[e] = wt[e].y;
+        ring_layout(ps.rank, te, sp_of, out->vld_ok, out->vst_ok, pos, &out->ring_stage_elems);
+        std::vector<int4> wr(wt);
+        for (int e = 0; e < V; ++e) {
+            wr[e].y = pos[wt[e].y];
+            wr[e].w = e + 1 < V ? pos[wt[e + 1].y] : 0;
+        }
+        int* d_pt = reinterpret_cast<int*>(pool_alloc(sizeof(int) * V, true));
+        int4* d_wr = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * V, true));
+        if (!d_pt || !d_wr) return SIPGPU_E_NOMEM;
+        SIP_CUDA(cudaMemcpyAsync(d_pt, pos.data(), sizeof(int) * V, cudaMemcpyHostToDevice, ctx().stream));
+        SIP_CUDA(cudaMemcpyAsync(d_wr, wr.data(), sizeof(int4) * V, cudaMemcpyHostToDevice, ctx().stream));
+        SIP_CUDA(cudaStreamSynchronize(ctx().stream));
+        out->ring_ptab = d_pt;
+        out->ring_wtab = d_wr;
+    }
+    int2* d_rt = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * V, true));
+    int4* d_wt = reinterpret_cast<int4*>(pool_alloc(sizeof(int4) * V, true));
     if (!d_rt || !d_wt) return SIPGPU_E_NOMEM;
     // plan tables are built once per (shape, permutation); a blocking upload keeps the host vectors simple
     SIP_CUDA(cudaMemcpyAsync(d_rt, rt.data(), sizeof(int2) * V, cudaMemcpyHostToDevice, ctx().stream));
@@ -536,10 +812,17 @@ int build_plan(const PermShape& ps, PlanEntry* out) {
 void permute_cache_clear() { cache().clear(); }
 
 static int& permute_bulk_flag() {
-    static int v = [] { const char* e = getenv("SIPGPU_PERMUTE_BULK"); return e ? atoi(e) : 1; }();
+    static int v = [] { const char* e = getenv("SIPGPU_PERMUTE_BULK"); return e ? atoi(e) : 3; }();
     return v;
 }
-bool permute_bulk_enabled() { return permute_bulk_flag() != 0; }
+bool permute_bulk_enabled() { return permute_bulk_flag() == 1; }
+int permute_variant() { return permute_bulk_flag(); }
+static int& permute_vec_flag() {
+    static int v = [] { const char* e = getenv("SIPGPU_PERMUTE_VEC"); return e ? atoi(e) : -1; }();
+    return v;
+}
+int permute_vec_mode() { return permute_vec_flag(); }   // ring variant, 16-byte cp.async / stores where eligible: 1 always, 0 never, -1 by tile size
+void permute_set_vec(int on) { permute_vec_flag() = on; }   // 0: register-staged tiles, 1: TMA bulk copies, 2: cp.async ring
 void permute_set_bulk(int on) { permute_bulk_flag() = on; }
 
 // Host-only view of the plan for CPU tests of the tiling logic (no device needed).
@@ -628,9 +911,48 @@ int permute_batched(int n, int rank, const int* ext, const int* transp, const do
     int ept = 16;
     for (int cand : {4, 6, 8, 10, 12})
         if (a.V <= cand * kPT) { ept = cand; break; }
+    // Kernel choice by evidence (profiles/r02_permute_variants.txt, all 23 rank-4 permutations at 16^4 .. 64^4 and 50x20x50x20):
+    // plain permutes run fastest through the cp.async ring with 8-byte staging (conflict-free searched layout); tiles of more
+    // than 2560 elements (EPT >= 12: long unmerged leading runs, e.g. 64-element first dimension) want the 16-byte loads / stores
+    // (+20 %: half the instructions and table registers); the fused accumulate is faster register-staged except on those big
+    // tiles; TMA bulk copies only win (+4 %) when the leading dimensions stay merged -- not selected automatically.
+    const int variant = permute_variant();
+    const bool big = ept >= 12;
+    const bool use_ring = variant == 2 || (variant == 3 && (!acc || big));
+    if (use_ring) {   // ---- cp.async ring ----
+        bool vld = it->second.vld_ok, vst = it->second.vst_ok;
+        for (int i = 0; i < n && (vld || vst); ++i) {
+            vld = vld && (((uintptr_t)in[i]) & 15) == 0;
+            vst = vst && (((uintptr_t)out[i]) & 15) == 0;
+        }
+        if (permute_vec_mode() == 0 || (permute_vec_mode() < 0 && !big)) vld = vst = false;
+        const int stage_elems = it->second.ring_stage_elems;
+        const int* ptab = it->second.ring_ptab;
+        const int4* wtab = it->second.ring_wtab;
+        const size_t smem = sizeof(double) * (size_t)kRingStages * stage_elems;
+        long long per_sm = std::max<long long>(1, std::min<long long>(ring_min_ctas(ept, acc || a.rag_dim[0] >= 0), (long long)(220 * 1024) / (long long)(smem + 1024)));
+        long long grid = a.ntiles * n;
+        if (grid > c.num_sms * per_sm) grid = c.num_sms * per_sm;
+        auto go = [a, b, ptab, wtab, acc, vld, vst, ept, grid, smem, stage_elems]() -> int {
+            cudaStream_t st = ctx().stream;
+            switch (ept) {
+                case 4: SIP_TRY(launch_perm_ring<4>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+                case 6: SIP_TRY(launch_perm_ring<6>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+                case 8: SIP_TRY(launch_perm_ring<8>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+                case 10: SIP_TRY(launch_perm_ring<10>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+                case 12: SIP_TRY(launch_perm_ring<12>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+                default: SIP_TRY(launch_perm_ring<16>(a, b, ptab, wtab, acc, vld, vst, (int)grid, smem, stage_elems, st)); break;
+            }
+            SIP_CUDA(cudaGetLastError());
+            count_launch();
+            return SIPGPU_OK;
+        };
+        if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+        return go();
+    }
     // ---- TMA path: bulk copies need 16-byte aligned runs, i.e. 16-byte aligned blocks on top of the plan's conditions ----
     const BulkPlan& bp = it->second.bulk;
-    bool bulk = bp.ok && permute_bulk_enabled();
+    bool bulk = bp.ok && variant == 1;
     for (int i = 0; i < n && bulk; ++i) bulk = (((uintptr_t)in[i]) & 15) == 0;
     if (bulk) {
         BulkArgs k;

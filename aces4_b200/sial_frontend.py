@@ -60,7 +60,9 @@ class SialSyntaxError(ValueError):
 
 
 _KIND_BY_RANGE = {("baocc", "eaocc"): "o", ("bavirt", "eavirt"): "v", ("baocc", "eavirt"): "p", ("1", "norb"): "ao",
-                  ("bocc", "eocc"): "o", ("bvirt", "evirt"): "v"}
+                  ("bocc", "eocc"): "o", ("bvirt", "evirt"): "v",
+                  # the defs files' own index of the static arrays ca / fock_a: ALL molecular orbital segments
+                  ("1", "eavirt"): "pa", ("1", "ebvirt"): "pa"}
 _REF = r"([A-Za-z_]\w*)\s*\[([^\]]*)\]"
 _NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?"
 
@@ -74,7 +76,7 @@ _TOK = re.compile(r"\s*(?:(\d+\.?\d*(?:[ed][-+]?\d+)?|\.\d+)|([a-z_]\w*)|(\[[^\]
 
 def parse_expr(text):
     """int / scalar expression -> AST: ('num', v) | ('var', name) | ('elem', array, labels) | ('cast', 'int'|'scalar', e) |
-    ('neg', e) | (op, l, r) with op in + - * /   (SIAL casts are prefix: `(int)Xijk[NT,i7]`, `tcomb/(scalar)nsects`)"""
+    ('neg', e) | (op, l, r) with op in + - * / **   (SIAL casts are prefix: `(int)Xijk[NT,i7]`, `tcomb/(scalar)nsects`)"""
     toks = []
     for num, name, br, other in _TOK.findall(text.strip().lower()):
         if num:
@@ -115,11 +117,19 @@ def parse_expr(text):
             return e
         raise SialSyntaxError(f"bad expression {text!r}")
 
-    def term():
+    def power():
         e = primary()
-        while peek() in (("op", "*"), ("op", "/")):
+        while peek() == ("op", "*") and pos[0] + 1 < len(toks) and toks[pos[0] + 1] == ("op", "*"):
+            take()
+            take()
+            e = ("**", e, primary())
+        return e
+
+    def term():
+        e = power()
+        while peek() in (("op", "*"), ("op", "/")) and not (peek() == ("op", "*") and pos[0] + 1 < len(toks) and toks[pos[0] + 1] == ("op", "*")):
             op = take()[1]
-            e = (op, e, primary())
+            e = (op, e, power())
         return e
 
     def expr():
@@ -153,6 +163,8 @@ class Program:
         self.index_kind, self.arrays, self.scalars = {}, {}, set()
         self.simple_range = {}    # simple index name -> (lo, hi) as written (numbers or predefined constants such as naocc)
         self.procs = {}           # name -> statement list (textual order kept: dicts are ordered)
+        self.predefined = set()   # `predefined int|scalar X`: the value comes with the job (the .dat file), Walker(constants=...)
+        self.contiguous = set()   # `contiguous local X[...]`: print bookkeeping arrays, statements on them are ignored
         main = []
         stack = [main]
         opens = []
@@ -198,8 +210,23 @@ class Program:
 
     def _parse(self, line, low, tok):
         kw = tok[0]
-        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete"):
-            return None           # arrays exist (zero) from the start; nothing is printed
+        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "special", "broadcast_from", "assert_same"):
+            return None           # arrays exist (zero) from the start; nothing is printed; super-instruction signatures are not
+                                  # needed; broadcast_from / assert_same: every worker computes the replicated statics itself
+        if kw == "predefined":
+            if len(tok) < 3 or tok[1] not in ("int", "scalar"):
+                raise SialSyntaxError("bad predefined declaration")
+            self.predefined.add(tok[2])
+            self.scalars.add(tok[2])
+            return None
+        if kw == "contiguous":
+            m = re.match(r"contiguous\s+local\s+([A-Za-z_]\w*)\s*\[", line, re.I)
+            if not m:
+                raise SialSyntaxError("bad contiguous declaration")
+            self.contiguous.add(m.group(1).lower())
+            return None
+        if kw == "allocate" and len(tok) > 1 and tok[1] == "contiguous":
+            return None
         if kw == "index":
             m = re.match(r"index\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line, re.I)
             if not m:
@@ -261,6 +288,9 @@ class Program:
             m = re.match(r"\w+\s+" + _REF + r"\s*=\s*(" + _NUM + r")\s*$", line)
             if m:
                 return ("put_init", m.group(1).lower(), _labels(m.group(2)), float(m.group(3).lower().replace("d", "e")))
+            m = re.match(r"\w+\s+" + _REF + r"\s*\*=\s*(.+)$", line)
+            if m:     # `prepare RB1_a[davidson,a,i] *= etemp`: the owner scales its block
+                return ("put_scale", m.group(1).lower(), _labels(m.group(2)), parse_expr(m.group(3)))
             m = re.match(r"\w+\s+" + _REF + r"\s*(\+?=)\s*" + _REF + r"\s*$", line)
             if not m:
                 raise SialSyntaxError("bad put/prepare")
@@ -279,6 +309,9 @@ class Program:
         if kw in ("allocate", "deallocate"):
             m = re.match(r"\w+\s+([A-Za-z_]\w*)\s*\[([^\]]*)\]\s*$", line)
             if not m:
+                m = re.match(r"deallocate\s+([A-Za-z_]\w*)\s*$", line, re.I)     # `deallocate LGmat`: the whole array
+                if m:
+                    return ("deallocate", m.group(1).lower(), ("*",))
                 raise SialSyntaxError("bad " + kw)
             return (kw, m.group(1).lower(), _labels(m.group(2)))
         if kw in ("sip_barrier", "server_barrier"):
@@ -290,6 +323,8 @@ class Program:
             return ("collective", m.group(1), m.group(2))
         # block statements
         m = re.match(_REF + r"\s*(\+=|-=|\*=|=)\s*(.+)$", line)
+        if m and ":" in m.group(2) and m.group(1).lower() in self.contiguous:
+            return None           # `FINAL_EOM_EE_Energy[kstate:kstate] = ...`: print bookkeeping
         if m:
             name, labs, op, rhs = m.group(1).lower(), _labels(m.group(2)), m.group(3), m.group(4).strip()
             mm = re.match(_REF + r"\s*[\*\^]\s*" + _REF + r"\s*$", rhs)   # `^` (outer product) is the same opcode
@@ -304,6 +339,10 @@ class Program:
                 return ("fill" if op == "=" else "scale", name, labs, float(rhs.lower().replace("d", "e")))
             if re.match(r"[A-Za-z_]\w*$", rhs) and op == "*=":
                 return ("scale_by", name, labs, rhs.lower())
+            if name in self.contiguous:
+                return None
+            if op in ("=", "*=") and "[" not in rhs:      # `T4kai[davidson,a,i] = omega`, `Tkai[kstate,a,i] *= (0.5)**(0.5)`
+                return ("fill_expr" if op == "=" else "scale_expr", name, labs, parse_expr(rhs))
             raise SialSyntaxError("unsupported block statement")
         # scalar statements
         m = re.match(r"(\w+)\s*(\+=|-=|\*=|=)\s*(.+)$", line)
@@ -370,8 +409,43 @@ def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5, ordered_k=False):
     return table
 
 
+def gen_eigen_calc(A):
+    """The reference's `execute gen_eigen_calc G L R E` (super_instructions/qm/utility/gen_eigen_calc.F:60-78 and its
+    dgeev_wrapper :80-230): LAPACK DGEEV('V','V') of the (zero-padded) subspace matrix, real parts of the eigenvalues,
+    eigenvalues below 1e-12 in magnitude (the padding) sorted to the END and reported as 0, left / right eigenvector columns
+    reordered with the ascending eigenvalues.  Host control logic of the Davidson solver (the matrix is at most 60 x 60), not
+    block arithmetic.  -> (VL, VR, eigenvalues)"""
+    import numpy as np
+    from scipy.linalg import eig
+
+    A = np.array(A, dtype=float, order="F")
+    n = A.shape[0]
+    w, vl, vr = eig(A, left=True, right=True)
+
+    def lapack_columns(v):       # DGEEV stores a complex pair as (real part, imaginary part) in consecutive columns
+        out = np.zeros((n, n))
+        j = 0
+        while j < n:
+            if abs(w[j].imag) > 0.0 and j + 1 < n:
+                out[:, j], out[:, j + 1] = v[:, j].real, v[:, j].imag
+                j += 2
+            else:
+                out[:, j] = v[:, j].real
+                j += 1
+        return out
+
+    L, R = lapack_columns(vl), lapack_columns(vr)
+    ev = w.real.copy()
+    ev[np.abs(ev) < 1e-12] = 999.0
+    order = np.argsort(ev, kind="stable")
+    ev = ev[order]
+    ev[np.abs(ev) == 999.0] = 0.0
+    return L[:, order], R[:, order], ev
+
+
 class Walker:
     """Executes a Program against a backend: the per-block call stream of one worker."""
+    host_registry = {}       # persistent host tables (label -> {index values: number}), shared by consecutive programs
 
     def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None):
         """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v.
@@ -383,8 +457,11 @@ class Walker:
         self.segs = dict(segs)
         if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
             self.segs["p"] = list(self.segs["o"]) + list(self.segs["v"])
+        if "pa" not in self.segs and "p" in self.segs and not self.index_base.get("o", 0):
+            self.segs["pa"] = list(self.segs["p"])       # all-electron job: every MO segment is active
         self.segs["s"] = _Ones()
-        self.constants = {k.lower(): int(v) for k, v in (constants or {}).items()}   # predefined ints: naocc, ...
+        # predefined ints (naocc, eom_roots, ...) and scalars (eom_tol, ...)
+        self.constants = {k.lower(): (int(v) if float(v).is_integer() else float(v)) for k, v in (constants or {}).items()}
         self.tables = {}         # static arrays over simple indices only (index tables such as Xijk): {(i, j): value}
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
@@ -392,6 +469,11 @@ class Walker:
         self._aseg_plan, self._ext_of, self._segkey_plan = {}, {}, {}   # memoised label resolution (per distinct reference in the text)
         self.iteration = 0       # pardo iteration counter of the current barrier section
         self.scalars = {s: 0.0 for s in program.scalars}
+        for name in program.predefined:
+            if name in self.constants:
+                self.scalars[name] = float(self.constants[name])
+        self._own_memo = {}
+        self.own_static = {}     # static arrays the program itself fills (St1a[a,i], SHDiag[a,i], ...): name -> {segs: handle}
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _kind(self, lab):
@@ -443,7 +525,7 @@ class Walker:
         if k == "neg":
             return -self._eval(e[1])
         a, b = self._eval(e[1]), self._eval(e[2])
-        return a + b if k == "+" else a - b if k == "-" else a * b if k == "*" else a / b
+        return a + b if k == "+" else a - b if k == "-" else a * b if k == "*" else a ** b if k == "**" else a / b
 
     def _segs_of(self, labs):
         """identity of a temp / local block: ABSOLUTE segment numbers, as in the SIP (a block of `tpp[p,p2]` addressed as
@@ -478,6 +560,9 @@ class Walker:
                 dk, k = self._kind(d), self._kind(lab)
                 if dk == "p" and k == "v":
                     plan.append((lab, len(self.segs["o"])))
+                elif dk == "pa" and k in ("o", "v", "p", "pa"):    # all MO segments: absolute segment numbers
+                    base = self.index_base.get("o", 0) if k in ("o", "p") else 0
+                    plan.append((lab, self.index_base.get("v", len(self.segs["o"])) if k == "v" else base))
                 elif dk == "s" and k == "s":       # block coordinate = value - first value + 1
                     lo = self.p.simple_range[d][0]
                     plan.append((lab, 1 - (int(lo) if lo.isdigit() else self.constants[lo])))
@@ -489,8 +574,23 @@ class Walker:
         idx = self.idx
         return tuple(idx[lab] + shift for lab, shift in plan)
 
+    def _own_static(self, name):
+        """a `static` array that is not handed in by the harness: the program fills it itself (zero until then)"""
+        own = self._own_memo.get(name)
+        if own is None:
+            a = self.p.arrays.get(name)
+            own = self._own_memo[name] = (a is not None and a[0] == "static" and not self._is_table(name)
+                                          and not self.be.has_array(name))
+        return own
+
     def _find(self, name, labs):
         key = (name, self._segs_of(labs))
+        if name in self.own_static or self._own_static(name):
+            blocks = self.own_static.setdefault(name, {})
+            if key[1] not in blocks:
+                blocks[key[1]] = self.be.new_block(self._shape(labs))
+                self.be.fill(blocks[key[1]], 0.0)
+            return blocks[key[1]]
         if name in self.locals:            # allocated local array: zero-filled blocks that outlive the loop scopes
             blocks = self.locals[name]
             if key[1] not in blocks:
@@ -504,7 +604,12 @@ class Walker:
 
     def _read(self, name, labs):
         """(handle, labels it is stored with) of an operand block"""
-        if self._is_remote(name):
+        if self._is_table(name):       # an element of a host table as a one-element block
+            h = self.be.new_block(self._shape(labs))
+            self.be.fill(h, self.tables.get(name, {}).get(tuple(self.idx[x] for x in labs), 0.0))
+            self.scopes[-1][("%table", name, len(self.scopes[-1]))] = h      # dies with the loop iteration
+            return h, labs
+        if self._is_remote(name) and not self._own_static(name):
             fetch = self.be.static_block if self.p.arrays[name][0] == "static" else self.be.array_block
             return fetch(name, self._array_segs(name, labs), self._shape(labs)), labs
         h = self._find(name, labs)
@@ -513,7 +618,7 @@ class Walker:
         return h, labs
 
     def _write(self, name, labs):
-        if self._is_remote(name):
+        if self._is_remote(name) and not self._own_static(name):
             raise SialSyntaxError(f"{name} is served/distributed: use put/prepare")
         h = self._find(name, labs)
         if h is None:
@@ -620,7 +725,9 @@ class Walker:
             self.be.free(h)
 
     def _x_set_persistent(self, name, label):
-        if name in self.p.scalars:
+        if self._is_table(name):           # a host table (e.g. the converged roots SEk0): handed over by value
+            self.host_registry[label] = dict(self.tables.get(name, {}))
+        elif name in self.p.scalars:
             self.be.persist_scalar(label, self.be.value(self.scalars[name]))
         elif self._is_remote(name):
             self.be.set_persistent(name, label)
@@ -628,7 +735,9 @@ class Walker:
             raise SialSyntaxError(f"set_persistent of {name}: not a scalar, served, distributed or static array")
 
     def _x_restore_persistent(self, name, label):
-        if name in self.p.scalars:
+        if self._is_table(name):
+            self.tables[name] = dict(self.host_registry.pop(label))
+        elif name in self.p.scalars:
             self.scalars[name] = self.be.restore_scalar(label)
         elif self._is_remote(name):
             self.be.restore_persistent(name, label)
@@ -639,6 +748,8 @@ class Walker:
         self.be.request(name, self._array_segs(name, labs), self._shape(labs))
 
     def _x_fill(self, name, labs, v):
+        if self._is_table(name):
+            return self._table_set(name, labs, v)
         self.be.fill(self._write(name, labs), v)
 
     def _x_scale(self, name, labs, f):
@@ -648,6 +759,22 @@ class Walker:
         if scalar not in self.scalars:
             raise SialSyntaxError(f"undeclared scalar {scalar}")
         self.be.scale(self._write(name, labs), self.be.value(self.scalars[scalar]))
+
+    def _table_set(self, name, labs, v):
+        self.tables.setdefault(name, {})[tuple(self.idx[x] for x in labs)] = float(v)
+
+    def _x_fill_expr(self, name, labs, e):
+        v = self._eval(e)
+        if self._is_table(name):
+            self._table_set(name, labs, v)
+        else:
+            self.be.fill(self._write(name, labs), v)
+
+    def _x_scale_expr(self, name, labs, e):
+        self.be.scale(self._write(name, labs), self._eval(e))
+
+    def _x_put_scale(self, arr, alabs, e):
+        self.be.put_scale(arr, self._array_segs(arr, alabs), self._shape(alabs), self._eval(e))
 
     def _x_put_init(self, arr, alabs, v):
         self.be.put_initialize(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
@@ -662,6 +789,12 @@ class Walker:
         return d, cd, s, cs
 
     def _x_assign(self, name, labs, src, slabs, _sign):
+        if self._is_table(name):       # `GSmat[ksub1,ksub] = Tkk[ksub1,ksub]`, `SEkold[kstate] = SEk0[kstate]`: one number
+            if self._is_table(src):
+                v = self.tables.get(src, {}).get(tuple(self.idx[x] for x in slabs), 0.0)
+            else:
+                v = self.be.block_value(self._read(src, slabs)[0])
+            return self._table_set(name, labs, v)
         s, sl = self._read(src, slabs)
         d, dl, s, sl = self._views(self._write(name, labs), labs, s, sl)
         self.be.copy(d, dl, s, sl)
@@ -695,12 +828,27 @@ class Walker:
             self.tables[bare[0]] = set_ijk_aab(self.be.moa_seg_ranges(), self.constants["baocc"], self.constants["eaocc"],
                                                ordered_k=fname == "set_ijk_aaa")
             return
+        if fname == "get_my_rank":
+            self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), float(self.rank))
+            return
+        if fname == "gen_eigen_calc":                # dgeev of the Davidson subspace matrix: host LAPACK, as in the reference
+            G, L, R, E = bare
+            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
+            n = hi - lo + 1
+            t = self.tables.get(G, {})
+            A = [[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)]
+            vl, vr, ev = gen_eigen_calc(A)
+            self.tables[L] = {(i + lo, j + lo): float(vl[i][j]) for i in range(n) for j in range(n)}
+            self.tables[R] = {(i + lo, j + lo): float(vr[i][j]) for i in range(n) for j in range(n)}
+            self.tables[E] = {(i + lo,): float(ev[i]) for i in range(n)}
+            self.tables[G] = {}                      # dgeev overwrites its input
+            return
         if fname == "return_sval" and args and self._is_table(args[0][0]):
             name, labs = args[0]
             v = self.tables.get(name, {}).get(tuple(self.idx[x] for x in labs), 0.0)
             self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), v)
             return
-        blocks = [self._read(n, labs)[0] if self._is_remote(n) else self._write(n, labs) for n, labs in args]
+        blocks = [self._read(n, labs)[0] if self._is_remote(n) and not self._own_static(n) else self._write(n, labs) for n, labs in args]
         kinds = [[self._kind(x) for x in labs] for _, labs in args]
         segs = [tuple(self.idx[x] + self.index_base.get(k, 0) for x, k in zip(labs, ks))
                 for (_, labs), ks in zip(args, kinds)]
@@ -721,9 +869,13 @@ class Walker:
         self.scalars[name] = self.be.scalar_scale(self.scalars[name], v)
 
     def _x_sadd(self, name, other, sign):
+        if other not in self.scalars:      # an index value or a predefined constant
+            return self._x_sinc(name, sign * self._eval(("var", other)))
         self.scalars[name] = self.be.scalar_axpy(self.scalars[name], sign, self.scalars[other])
 
     def _x_scopy(self, name, other, _sign):
+        if other not in self.scalars:      # `maxdav = davidson`: an index value or a predefined constant
+            return self._x_sset(name, self._eval(("var", other)))
         self.scalars[name] = self.be.scalar_set(self.scalars.get(name), self.scalars[other])
 
     def _x_barrier(self):
@@ -846,6 +998,24 @@ class DeviceBackend:
 
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr].put_initialize(segs, v)
+
+    def put_scale(self, arr, segs, shape, f):
+        """`prepare A[...] *= s`: the block is scaled where it lives (one writer per block and section, like `put`)"""
+        A = self.arrays[arr]
+        if A.owner(segs) == self.rank:
+            A.block_view(segs).scale(f)
+        else:
+            b = A.get(segs)
+            b.scale(f)
+            A.put(segs, b)
+            b.free()
+
+    def has_array(self, name):
+        return name in self.arrays or name in self.static
+
+    def block_value(self, b):
+        """the single element of a one-element block, on the host (Davidson control logic: subspace matrix elements)"""
+        return float(b.to_numpy().reshape(-1)[0])
 
     # persistence: the array object (with its HBM slab) moves to the library's label registry and back -- no copy
     def set_persistent(self, name, label):

@@ -246,6 +246,14 @@ def si_invert_diagonal(a1, a2):
     return lib().oracle_si_invert_diagonal(a1.ndim, a2.ndim, _ia(a1.shape), _dp(a1), _dp(a2))
 
 
+def si_invert_diagonal_asym(a1, index_values, a2, moa_seg_ranges):
+    return lib().oracle_si_invert_diagonal_asym(a1.ndim, a2.ndim, _ia(index_values), _ia(a1.shape), _dp(a1), _dp(a2), _ia(moa_seg_ranges))
+
+
+def si_return_diagonal_elements(block, index_values, moa_seg_ranges):
+    return lib().oracle_si_return_diagonal_elements(block.ndim, _ia(index_values), _ia(block.shape), _dp(block), _ia(moa_seg_ranges))
+
+
 def block_consistency(ops, workers, sections):
     """distributed_block_consistency.cpp:25-175 for ONE block: index of the first illegal operation, or -1."""
     n = len(ops)

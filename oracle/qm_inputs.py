@@ -302,6 +302,23 @@ def mo_classes(eri, C, occ, virt):
             "vaaai": tr(Cv, Cv, Cv, Co)}                 # (a a1|a2 i)            :444-470 + the last quarter transformation
 
 
+def cis_singlets(eps_occ, eps_virt, vpiqj_vovo, vaaii, nroots):
+    """Singlet CIS of a closed-shell reference (what the reference's rcis_rhf.sialx iterates to; its converged vectors C1_a are
+    the starting guesses of the EOM-CCSD program): A[ai,bj] = d_ab d_ij (e_a - e_i) + 2 (ai|bj) - (ab|ij), lowest `nroots`
+    eigenpairs.  vpiqj_vovo = (a i|b j) [a,i,b,j], vaaii = (a b|i j) [a,b,i,j].  -> (energies [nroots], vectors [nroots,a,i],
+    each normalised to 1 over (a, i))"""
+    nv, no = len(eps_virt), len(eps_occ)
+    A = 2.0 * vpiqj_vovo - vaaii.transpose(0, 2, 1, 3)
+    A = A.reshape(nv * no, nv * no).copy()
+    A[np.diag_indices(nv * no)] += (eps_virt[:, None] - eps_occ[None, :]).reshape(-1)
+    w, v = np.linalg.eigh(0.5 * (A + A.T))
+    vec = v[:, :nroots].T.reshape(nroots, nv, no)
+    for k in range(nroots):          # a definite sign: the largest component positive
+        if vec[k].reshape(-1)[np.argmax(np.abs(vec[k]))] < 0:
+            vec[k] = -vec[k]
+    return w[:nroots], vec
+
+
 def split_blocks(dense, seg_lists):
     """dense ndarray -> {1-based segment tuple: Fortran-ordered block}"""
     offs = [np.concatenate([[0], np.cumsum(s)]) for s in seg_lists]

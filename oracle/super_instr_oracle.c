@@ -5,7 +5,7 @@
  * Plain-C restatement of
  *   src/sip/super_instructions/qm/qm-generic/energy_denominator_rhf.F:15-460
  *   src/sip/super_instructions/qm/utility/stripi.F, anti_symm_o.F, anti_symm_v.F, return_sval.F,
- *   invert_diagonal.F
+ *   invert_diagonal.F, invert_diagonal_asym.F, return_diagonal_elements.F
  * with the reference's super-instruction calling convention reduced to what the arithmetic reads:
  * (rank, index_values, extents, data) per argument (special_instructions.h:27-97), the predefined int
  * array "moa_seg_ranges" passed explicitly instead of through the sip_interface upcall.
@@ -163,5 +163,53 @@ int oracle_si_invert_diagonal(int rank0, int rank1, const int* ext, double* a1, 
     for (int d = 0; d < rank0; ++d) n *= ext[d];
     for (long long i = 0; i < n; ++i)
         if (a2[i] != 0.0) a1[i] = a1[i] / a2[i];
+    return 0;
+}
+
+/* return_diagonal_elements.F ret_diag_tensor2 / ret_diag_tensor4: keep x(p,p) (rank 2) or x(p,p,r,r) (rank 4), zero the rest.
+ * The Fortran declares BOTH dimensions of a pair over the range of the FIRST one (tensor(n1:n2,n1:n2),
+ * tensor(a1:a2,a1:a2,b1:b2,b1:b2)), so "diagonal" compares positions inside the block, whatever segments the pair of
+ * indices carries; the block must be square per pair (abort otherwise: ierr 1). */
+int oracle_si_return_diagonal_elements(int rank, const int* iv, const int* ext, double* x, const int* moa_seg_ranges) {
+    (void)iv; (void)moa_seg_ranges;
+    if (rank == 2) {
+        if (ext[0] != ext[1]) return 1;
+        for (int q = 0; q < ext[1]; ++q)
+            for (int p = 0; p < ext[0]; ++p)
+                if (p != q) x[p + (long long)q * ext[0]] = 0.0;
+        return 0;
+    }
+    if (rank == 4) {
+        if (ext[0] != ext[1] || ext[2] != ext[3]) return 1;
+        const long long s1 = ext[0], s2 = s1 * ext[1], s3 = s2 * ext[2];
+        for (int s = 0; s < ext[3]; ++s)
+            for (int r = 0; r < ext[2]; ++r)
+                for (int q = 0; q < ext[1]; ++q)
+                    for (int p = 0; p < ext[0]; ++p)
+                        if (!(p == q && r == s)) x[p + q * s1 + r * s2 + s * s3] = 0.0;
+        return 0;
+    }
+    return 1;
+}
+
+/* invert_diagonal_asym.F do_return_inv5_as: rank 5 (a, b, c, d, e), b..e carry segment offsets: where global b != d and
+ * c != e, array1 /= array2 (skipped where array2 == 0); everywhere else array1 = 0. */
+int oracle_si_invert_diagonal_asym(int rank0, int rank1, const int* iv, const int* ext, double* a1, const double* a2,
+                                   const int* moa_seg_ranges) {
+    if (rank0 != rank1 || rank0 != 5) return 1;
+    int o[5] = {0, 0, 0, 0, 0};
+    for (int d = 1; d < 5; ++d) o[d] = seg_offset(moa_seg_ranges, iv[d]);
+    long long i = 0;
+    for (int e = 0; e < ext[4]; ++e)
+        for (int d = 0; d < ext[3]; ++d)
+            for (int c = 0; c < ext[2]; ++c)
+                for (int b = 0; b < ext[1]; ++b)
+                    for (int a = 0; a < ext[0]; ++a, ++i) {
+                        if (b + o[1] != d + o[3] && c + o[2] != e + o[4]) {
+                            if (a2[i] != 0.0) a1[i] = a1[i] / a2[i];
+                        } else {
+                            a1[i] = 0.0;
+                        }
+                    }
     return 0;
 }

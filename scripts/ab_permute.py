@@ -23,12 +23,13 @@ def time_ms(fn, reps=5, warm=2):
     return float(np.median(ts))
 
 
-api.set_tuning("permute_bulk", int(os.environ.get("PERMUTE_BULK", "1")))
+api.set_tuning("permute_bulk", int(os.environ.get("PERMUTE_BULK", "3")))
+api.set_tuning("permute_vec", int(os.environ.get("PERMUTE_VEC", "-1")))
 out = {}
 for shape, n in (((16,) * 4, 1024), ((32,) * 4, 128), ((64,) * 4, 8), ((50, 20, 50, 20), 128)):
     ins = [api.DeviceBlock(shape).fill(1.0) for _ in range(n)]
     outs = [api.DeviceBlock(shape) for _ in range(n)]
-    res, acc = [], []
+    res, acc, per = [], [], {}
     for p in itertools.permutations(range(4)):
         if p == (0, 1, 2, 3):
             continue
@@ -36,7 +37,8 @@ for shape, n in (((16,) * 4, 1024), ((32,) * 4, 128), ((64,) * 4, 8), ((50, 20, 
         bp = api.BatchedPermute(ins, transp, outs)   # pointer arrays marshalled once: time the library, not ctypes
         res.append(n * 16.0 * np.prod(shape) / time_ms(lambda: bp.launch()) / 1e6)
         acc.append(n * 24.0 * np.prod(shape) / time_ms(lambda: bp.launch(alpha=0.5, beta=1.0)) / 1e6)
+        per["".join(map(str, p))] = [round(res[-1]), round(acc[-1])]
     out[str(shape)] = {"blocks": n, "min": round(min(res)), "median": round(float(np.median(res))), "max": round(max(res)),
-                       "acc_median": round(float(np.median(acc)))}
+                       "acc_median": round(float(np.median(acc))), "per_perm": per}
     del ins, outs
-print(json.dumps({"permute_bulk": int(os.environ.get("PERMUTE_BULK", "1")), "GBps": out}), flush=True)
+print(json.dumps({"permute_bulk": int(os.environ.get("PERMUTE_BULK", "3")), "permute_vec": int(os.environ.get("PERMUTE_VEC", "-1")), "GBps": out}), flush=True)

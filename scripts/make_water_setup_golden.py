@@ -32,9 +32,16 @@ GOLDEN["hf"] = {"scf_energy": -99.45975176375698, "ccsd_correlation": -0.1258869
 # scf_rhf_coreh, tran_rhf_no4v, rccsd_rhf, rccsdpt_aaa, rccsdpt_aab).  The setup stops the SCF at 1e-8 and the CCSD at 1e-7, so
 # these two numbers carry that run's convergence error: they pin a tightly converged run only to about the .dat's own cc_conv.
 GOLDEN["ne_ccsdpt_test"] = {"eaab": -0.0010909774775509193, "esaab": 8.5547845910409156e-05, "cc_conv": 1e-07, "scf_conv": 1e-08}
+# water / 3-21G excited states: test/test_qm.cpp:1005-1031 (eom_ccsd_water_test = BASELINE config 3) and :921-933
+# (eom_ccsd_water_right_test): the four EOM-CCSD roots `sek0` of eom_ccsd_rhf_right.siox, asserted at 1e-8 (the setup's
+# eom_tol is 1e-6, cc_conv 1e-10); :265-272 (DISABLED_eom_test, eom_test.dat: cc_conv 1e-12): the two CIS roots of rcis_rhf.siox
+# at 1e-10 -- they pin the CIS starting vectors the harness hands to the EOM program -- and its two EOM roots at 1e-8
+GOLDEN["eom_ccsd_water_test"] = {"sek0": [0.32850657002707, 0.41193399006592, 0.42288344162832, 0.51159731180444],
+                                 "tolerance": 1e-8, "oscnorm": [0.00680956, 0.0, 0.09037060, 0.11312310]}
+GOLDEN["eom_test"] = {"cis_sek0": [0.36275490375537, 0.43493738840536], "eom_sek0": [0.32850656893104, 0.41193399028059]}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
-             "lamccsdpt_test.dat", "ccsdpt_test.dat"):
+             "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

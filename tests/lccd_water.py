@@ -195,3 +195,53 @@ def pt_constants(inp):
 def pt_array_kinds(program):
     """index kinds of every served / distributed array a (T) program declares ('s' = simple index: blocks of extent 1)"""
     return {n: tuple(program.index_kind[d] for d in decl) for n, (k, decl) in program.arrays.items() if k in ("served", "distributed")}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3: the reference's right-hand EOM-CCSD program (tests/golden/eom_ccsd_right_program.sialx, generated from
+# src/sialx/qm/eom/eom_ccsd_rhf_right.sialx + eom_rhf_hbar.sialx + eom_rhf_vars.sialx + eom_rhf_defs.sialx by
+# scripts/make_eom_golden.py) on water / 3-21G (test/eom_ccsd_water_test.dat)
+PROGRAM_EOM = open(os.path.join(HERE, "golden", "eom_ccsd_right_program.sialx")).read()
+EOM_SETUP = "eom_ccsd_water_test.dat"
+CASES["eom_dat"] = (EOM_SETUP, None)
+CASES["eom_fine"] = (EOM_SETUP, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]})
+# persistence labels READ_AMP restores (eom_ccsd_rhf_right.sialx:13-29) -> arrays of the CCSD / transformation programs
+EOM_LABELS = {"t1a_old": "t1a_old", "T2old_aa": "t2old_aa", "T2old_ab": "t2old_ab", "VSpipi": "vspipi", "Vaaii": "vaaii",
+              "Viaai": "viaai", "Vaaai": "vaaai", "VSaaai": "vsaaai", "Vpiqj": "vpiqj"}
+
+
+def eom_constants():
+    """the predefined ints / scalars of the setup file the EOM program reads: eom_roots, eom_tol, cc_iter (the range of the
+    subspace indices), baocc ..."""
+    setup = FIXTURE["setups"][EOM_SETUP]
+    return {**setup["ints"], **setup["scalars"]}
+
+
+def cis_guess(inp, dense):
+    """The starting vectors C1_a[kstate,a,i] of the EOM program = the converged singlet CIS vectors of rcis_rhf.sialx, which
+    runs right before it.  Here: dense diagonalisation of the CIS matrix (oracle/qm_inputs.py, test infrastructure) -- pinned
+    by the reference's CIS goldens of the same molecule (DISABLED_eom_test, test/test_qm.cpp:265-272).
+    dense: name -> dense MO integral class.  -> (CIS energies, {(kstate, virtual segment, occupied segment): block [1,a,i]})"""
+    eps = np.diag(inp["fock"])
+    no = sum(inp["segs"]["o"])
+    nroots = FIXTURE["setups"][EOM_SETUP]["ints"]["eom_roots"]
+    e, vec = qm.cis_singlets(eps[:no], eps[no:], dense["vpiqj"][no:, :, no:, :], dense["vaaii"], nroots)
+    blocks = {}
+    for k in range(nroots):
+        for (sa, si), b in qm.split_blocks(vec[k], [inp["segs"]["v"], inp["segs"]["o"]]).items():
+            blocks[(k + 1, sa, si)] = np.asfortranarray(b[None, :, :])
+    return e, blocks
+
+
+def eom_array_kinds(program):
+    """index kinds of every served / distributed array the EOM program declares ('s': simple index, blocks of extent 1)"""
+    return {n: tuple(program.index_kind[d] for d in decl) for n, (k, decl) in program.arrays.items() if k in ("served", "distributed")}
+
+
+def eom_simple_extents(program, constants):
+    """number of values of every simple index range that occurs as an array dimension: {declared label: count}"""
+    out = {}
+    for lab, (lo, hi) in program.simple_range.items():
+        lo, hi = (int(x) if x.isdigit() else int(constants[x]) for x in (lo, hi))
+        out[lab] = hi - lo + 1
+    return out

@@ -83,6 +83,18 @@ class OracleBackend:
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr][segs] = np.full(shape, float(v), order="F")
 
+    def put_scale(self, arr, segs, shape, f):
+        A = self.arrays[arr]
+        if segs not in A:
+            A[segs] = np.zeros(shape, order="F")
+        A[segs] = A[segs] * float(f)
+
+    def has_array(self, name):
+        return name in self.arrays
+
+    def block_value(self, b):
+        return float(np.asarray(b.a).reshape(-1)[0])
+
     # persistence: a label registry shared by the backends of consecutive programs (class attribute)
     registry = {}
 
@@ -105,7 +117,23 @@ class OracleBackend:
             blocks[1].a[...] = y
             self.calls += 1
             return
-        assert fname == "energy_denominator_rhf"
+        if fname in ("anti_symm_o", "anti_symm_v"):
+            assert getattr(self.o, "si_" + fname)(blocks[0].a, list(segs[0]), self.ranges) == 0
+            self.calls += 1
+            return
+        if fname == "invert_diagonal":
+            assert self.o.si_invert_diagonal(blocks[0].a, blocks[1].a) == 0
+            self.calls += 1
+            return
+        if fname == "invert_diagonal_asym":
+            assert self.o.si_invert_diagonal_asym(blocks[0].a, list(segs[0]), blocks[1].a, self.ranges) == 0
+            self.calls += 1
+            return
+        if fname == "return_diagonal_elements":
+            assert self.o.si_return_diagonal_elements(blocks[0].a, list(segs[0]), self.ranges) == 0
+            self.calls += 1
+            return
+        assert fname == "energy_denominator_rhf", fname
         assert self.o.si_energy_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, self.ranges) == 0
 
     def reshaped(self, b, shape):

@@ -125,13 +125,19 @@ def test_sum_op_and_scale(sip, oracle):
 # ---------------------------------------------------------------------------------------------------
 # permutes: every rank-4 pattern, ragged and tiny extents, ranks 2..6
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["tma", "registers"])
+PERMUTE_ROUTES = {"registers": (0, -1), "tma": (1, -1), "ring": (2, 0), "ring16": (2, 1), "auto": (3, -1)}
+
+
+@pytest.fixture(params=list(PERMUTE_ROUTES))
 def permute_route(request, sip):
-    """permutes whose input runs are 16-byte aligned fetch their tiles with TMA bulk copies (cp.async.bulk) by default; the
-    same cases are also forced through the register-staged kernel, so that both stay covered"""
-    sip.set_tuning("permute_bulk", 1 if request.param == "tma" else 0)
+    """the three permute kernels -- the cp.async ring (LDGSTS into a 3-stage ring of staged tiles; with 8-byte and with 16-byte
+    loads / stores where the runs are even and aligned), TMA bulk copies (cp.async.bulk) and the register-staged tiles -- and the
+    default per-launch choice all run the same cases, so that every one stays covered"""
+    sip.set_tuning("permute_bulk", PERMUTE_ROUTES[request.param][0])
+    sip.set_tuning("permute_vec", PERMUTE_ROUTES[request.param][1])
     yield request.param
-    sip.set_tuning("permute_bulk", 1)
+    sip.set_tuning("permute_bulk", PERMUTE_ROUTES["auto"][0])
+    sip.set_tuning("permute_vec", PERMUTE_ROUTES["auto"][1])
 
 
 @pytest.mark.parametrize("shape", [(16, 16, 16, 16), (13, 30, 50, 7), (5, 8, 9, 5), (32, 3, 1, 33), (64, 20, 2, 50), (50, 20, 50, 20),
@@ -187,6 +193,34 @@ def test_permute_batched_and_accumulate(sip, oracle, shape, permute_route):
         for x, o, d in zip(ins, outs0, d_out):
             ref = -0.5 * oracle.block_copy(x, transp) + 2.0 * o
             assert relerr(d.to_numpy(), ref) <= 1e-14, (shape, perm)
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16, 16), (50, 20, 50, 20), (18, 6, 34, 10), (13, 30, 8, 7)])
+def test_permute_of_blocks_that_are_not_16_byte_aligned(sip, oracle, shape, permute_route):
+    """the 16-byte paths (vector cp.async / stores, TMA) need 16-byte aligned blocks: views that start one element into an
+    allocation must take the 8-byte paths -- input only, output only, both; plain and accumulating"""
+    rng = np.random.default_rng(23)
+    pyrng = random.Random(9)
+    n = int(np.prod(shape))
+    for trial in range(4):
+        perm = list(range(4))
+        pyrng.shuffle(perm)
+        transp = [1] + [p + 1 for p in perm]
+        new_shape = [0] * 4
+        for i, p in enumerate(perm):
+            new_shape[p] = shape[i]
+        a, o = rand_block(rng, shape), rand_block(rng, new_shape)
+        for off_in, off_out in ((1, 0), (0, 1), (1, 1)):
+            big_in, big_out = sip.DeviceBlock((n + 2,)), sip.DeviceBlock((n + 2,))
+            vin = sip.DeviceBlock(shape, ptr=big_in.ptr + 8 * off_in, owned=False)
+            vout = sip.DeviceBlock(tuple(new_shape), ptr=big_out.ptr + 8 * off_out, owned=False)
+            vin.scale_and_copy(sip.DeviceBlock.from_numpy(a), 1.0)
+            vout.scale_and_copy(sip.DeviceBlock.from_numpy(o), 1.0)
+            sip.permute_batched([vin], transp, [vout])
+            assert np.array_equal(vout.to_numpy(), oracle.block_copy(a, transp)), (shape, perm, off_in, off_out)
+            sip.permute_batched([vin], transp, [vout], alpha=0.25, beta=-1.0)
+            ref = 0.25 * oracle.block_copy(a, transp) - oracle.block_copy(a, transp)
+            assert relerr(vout.to_numpy(), ref) <= 1e-14, (shape, perm, off_in, off_out)
 
 
 def test_permute_host_abi_and_large(sip, oracle):
