@@ -707,6 +707,14 @@ def si_invert_diagonal(a1, a2):
     return _si_call(lib().sipgpu_si_invert_diagonal, "invert_diagonal", (a1, None), (a2, None))
 
 
+def si_invert_diagonal_asym(a1, index_values, a2):
+    return _si_call(lib().sipgpu_si_invert_diagonal_asym, "invert_diagonal_asym", (a1, index_values), (a2, index_values))
+
+
+def si_return_diagonal_elements(block, index_values):
+    return _si_call(lib().sipgpu_si_return_diagonal_elements, "return_diagonal_elements", (block, index_values))
+
+
 # ----------------------------------------------------------------------------------------------------
 # Host/device coherence of one block (BlockManager::lazy_gpu_*, block_manager.cpp:340-441)
 # ----------------------------------------------------------------------------------------------------

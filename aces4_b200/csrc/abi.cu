@@ -1070,6 +1070,35 @@ int sipgpu_si_invert_diagonal(int*, int* rank_0, int*, int*, int* extents_0, dou
     SI_RETURN(si_invert_diagonal(*rank_0, *rank_1, extents_0, data_0, data_1));
 }
 
+int sipgpu_si_invert_diagonal_asym(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1, int*,
+                                   int*, int*, double* data_1, int* ierr) {
+    SIP_TRACE("sipgpu_si_invert_diagonal_asym");
+    if (!rank_0 || !rank_1) SI_RETURN(SIPGPU_E_ARG);
+    if (wl_active()) {
+        const int r0 = *rank_0, r1 = *rank_1;
+        if (r0 < 1 || r0 > kMaxRank || !index_values_0 || !extents_0 || !data_0 || !data_1) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv{}, e0{};
+        for (int i = 0; i < r0; ++i) iv[i] = index_values_0[i], e0[i] = extents_0[i];
+        const size_t nb = sizeof(double) * (size_t)volume(r0, extents_0);
+        SI_RETURN(wl_rec_opaque([=] { return si_invert_diagonal_asym(r0, r1, iv.data(), e0.data(), data_0, data_1); },
+                                {{data_0, nb, WL_RW}, {data_1, nb, WL_R}}));
+    }
+    SI_RETURN(si_invert_diagonal_asym(*rank_0, *rank_1, index_values_0, extents_0, data_0, data_1));
+}
+int sipgpu_si_return_diagonal_elements(int*, int* rank_0, int*, int*, int* extents_0, double* data_0, int* ierr) {
+    SIP_TRACE("sipgpu_si_return_diagonal_elements");
+    if (!rank_0) SI_RETURN(SIPGPU_E_ARG);
+    if (wl_active()) {
+        const int r = *rank_0;
+        if (r < 1 || r > kMaxRank || !extents_0 || !data_0) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> e0{};
+        for (int i = 0; i < r; ++i) e0[i] = extents_0[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_return_diagonal_elements(r, e0.data(), data_0); },
+                                {{data_0, sizeof(double) * (size_t)volume(r, extents_0), WL_RW}}));
+    }
+    SI_RETURN(si_return_diagonal_elements(*rank_0, extents_0, data_0));
+}
+
 int sipgpu_dgemm_tn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb, double beta,
                     double* C, int ldc) {
     SIP_TRACE("sipgpu_dgemm_tn");

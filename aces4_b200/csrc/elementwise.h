@@ -39,5 +39,7 @@ int si_anti_symm_o(int rank, const int* iv, const int* ext, double* x);
 int si_anti_symm_v(int rank, const int* iv, const int* ext, double* x);
 int si_return_sval(int rank, const int* ext, const double* data, double* d_scalar);
 int si_invert_diagonal(int rank0, int rank1, const int* ext, double* a1, const double* a2);
+int si_invert_diagonal_asym(int rank0, int rank1, const int* iv, const int* ext, double* a1, const double* a2);
+int si_return_diagonal_elements(int rank, const int* ext, double* x);
 
 }  // namespace sipgpu

@@ -104,6 +104,44 @@ __global__ void __launch_bounds__(kT) invert_diagonal_kernel(double* __restrict_
     }
 }
 
+// invert_diagonal_asym.F do_return_inv5_as: rank 5 (a, b, c, d, e): where global b != d and c != e, a1 /= a2 (skipped where a2 == 0);
+// everywhere else a1 = 0.  off[1..4] = segment offsets of b .. e.
+struct Inv5Args {
+    int ext[5], off[5];
+    long long n;
+};
+__global__ void __launch_bounds__(kT) invert_diagonal_asym_kernel(double* __restrict__ a1, const double* __restrict__ a2, const __grid_constant__ Inv5Args s) {
+    for (long long lin = (long long)blockIdx.x * kT + threadIdx.x; lin < s.n; lin += (long long)gridDim.x * kT) {
+        long long r = lin / s.ext[0];
+        const int b = (int)(r % s.ext[1]); r /= s.ext[1];
+        const int c = (int)(r % s.ext[2]); r /= s.ext[2];
+        const int d = (int)(r % s.ext[3]); r /= s.ext[3];
+        const int e = (int)r;
+        if (b + s.off[1] != d + s.off[3] && c + s.off[2] != e + s.off[4]) {
+            const double div = a2[lin];
+            if (div != 0.0) a1[lin] = a1[lin] / div;
+        } else {
+            a1[lin] = 0.0;
+        }
+    }
+}
+
+// return_diagonal_elements.F ret_diag_tensor2 / 4: keep x(p,p) / x(p,p,r,r), zero the rest (positions inside the block: the
+// Fortran declares both dimensions of a pair over the range of the first one)
+__global__ void __launch_bounds__(kT) return_diagonal_kernel(double* __restrict__ x, int e0, int e2, long long n) {
+    for (long long lin = (long long)blockIdx.x * kT + threadIdx.x; lin < n; lin += (long long)gridDim.x * kT) {
+        long long r = lin;
+        const int p = (int)(r % e0); r /= e0;
+        const int q = (int)(r % e0); r /= e0;
+        bool keep = p == q;
+        if (e2 > 0) {
+            const int rr = (int)(r % e2); r /= e2;
+            keep = keep && rr == (int)r;
+        }
+        if (!keep) x[lin] = 0.0;
+    }
+}
+
 int grid_for(long long n) {
     long long b = (n + kT - 1) / kT;
     const long long cap = (long long)ctx().num_sms * 8;
@@ -220,6 +258,37 @@ int si_invert_diagonal(int rank0, int rank1, const int* ext, double* a1, const d
     long long n = 1;
     for (int d = 0; d < rank0; ++d) n *= ext[d];
     invert_diagonal_kernel<<<grid_for(n), kT, 0, ctx().stream>>>(a1, a2, n);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+int si_invert_diagonal_asym(int rank0, int rank1, const int* iv, const int* ext, double* a1, const double* a2) {
+    SIP_TRY(ensure_init());
+    const std::vector<int>* seg = moa_segs();
+    if (!seg) { set_error("invert_diagonal_asym: predefined int array moa_seg_ranges is not registered"); return SIPGPU_E_STATE; }
+    if (rank0 != rank1 || rank0 != 5 || !iv || !ext || !a1 || !a2) return SIPGPU_E_ARG;
+    Inv5Args s;
+    s.n = 1;
+    s.off[0] = 0;
+    for (int d = 0; d < 5; ++d) {
+        s.ext[d] = ext[d];
+        if (d > 0) SIP_TRY(seg_offset(*seg, iv[d], &s.off[d]));
+        s.n *= ext[d];
+    }
+    invert_diagonal_asym_kernel<<<grid_for(s.n), kT, 0, ctx().stream>>>(a1, a2, s);
+    SIP_CUDA(cudaGetLastError());
+    count_launch();
+    return SIPGPU_OK;
+}
+
+int si_return_diagonal_elements(int rank, const int* ext, double* x) {
+    SIP_TRY(ensure_init());
+    if (!(rank == 2 || rank == 4) || !ext || !x) return SIPGPU_E_ARG;
+    if (ext[0] != ext[1] || (rank == 4 && ext[2] != ext[3])) { set_error("return_diagonal_elements: the block is not square"); return SIPGPU_E_ARG; }
+    long long n = 1;
+    for (int d = 0; d < rank; ++d) n *= ext[d];
+    return_diagonal_kernel<<<grid_for(n), kT, 0, ctx().stream>>>(x, ext[0], rank == 4 ? ext[2] : 0, n);
     SIP_CUDA(cudaGetLastError());
     count_launch();
     return SIPGPU_OK;

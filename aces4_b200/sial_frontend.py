@@ -1001,14 +1001,7 @@ class DeviceBackend:
 
     def put_scale(self, arr, segs, shape, f):
         """`prepare A[...] *= s`: the block is scaled where it lives (one writer per block and section, like `put`)"""
-        A = self.arrays[arr]
-        if A.owner(segs) == self.rank:
-            A.block_view(segs).scale(f)
-        else:
-            b = A.get(segs)
-            b.scale(f)
-            A.put(segs, b)
-            b.free()
+        self.arrays[arr].put_scale(segs, f)      # SialOpsParallel::put_scale, sial_ops_parallel.cpp:412-528
 
     def has_array(self, name):
         return name in self.arrays or name in self.static
@@ -1037,6 +1030,15 @@ class DeviceBackend:
         elif fname == "stripi":
             if self.api.si_stripi(blocks[0], segs[0], blocks[1], segs[1]) != 0:
                 raise SialSyntaxError("stripi: " + self.api.lib().sipgpu_last_error().decode(errors="replace"))
+        elif fname in ("anti_symm_o", "anti_symm_v", "return_diagonal_elements"):
+            if getattr(self.api, "si_" + fname)(blocks[0], segs[0]) != 0:
+                raise SialSyntaxError(fname + " failed")
+        elif fname == "invert_diagonal":
+            if self.api.si_invert_diagonal(blocks[0], blocks[1]) != 0:
+                raise SialSyntaxError("invert_diagonal failed")
+        elif fname == "invert_diagonal_asym":
+            if self.api.si_invert_diagonal_asym(blocks[0], segs[0], blocks[1]) != 0:
+                raise SialSyntaxError("invert_diagonal_asym failed")
         else:
             raise SialSyntaxError(f"super-instruction {fname} is not on the device path")
 

@@ -274,6 +274,15 @@ int sipgpu_si_return_sval(int* array_0, int* rank_0, int* index_values_0, int* s
 int sipgpu_si_invert_diagonal(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
                               int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
                               int* ierr);
+/* qm/utility/invert_diagonal_asym.F (special invert_diagonal_asym ur): rank-5 blocks [k,a,i,a1,i1]: array_0 /= array_1 where
+ * a != a1 and i != i1 (orbital numbers) and array_1 != 0, array_0 = 0 on the a == a1 or i == i1 planes */
+int sipgpu_si_invert_diagonal_asym(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                                   int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
+                                   int* ierr);
+/* qm/utility/return_diagonal_elements.F (special return_diagonal_elements u): keep x(p,p) (rank 2) / x(p,p,r,r) (rank 4) of a
+ * block that is square per index pair, zero everything else */
+int sipgpu_si_return_diagonal_elements(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                                       int* ierr);
 
 /* ---------------------------------------------------------------------------------------------
  * Boundary 3c -- deferred op stream: the batching front-end for pardo bodies.

@@ -110,6 +110,9 @@ class FakeApi:
             def put_accumulate(self, idx, blk):
                 self.block_view(idx).accumulate(blk)
 
+            def put_scale(self, idx, f):
+                self.block_view(idx).scale(f)
+
             def put_initialize(self, idx, v):
                 self.block_view(idx).fill(v)
 
@@ -205,6 +208,26 @@ class FakeApi:
         if ierr == 0:
             y.a[...] = out
         return ierr
+
+    def si_anti_symm_o(self, block, index_values):
+        self._launches += 1
+        return self.o.si_anti_symm_o(block.a, list(index_values), self._moa)
+
+    def si_anti_symm_v(self, block, index_values):
+        self._launches += 1
+        return self.o.si_anti_symm_v(block.a, list(index_values), self._moa)
+
+    def si_return_diagonal_elements(self, block, index_values):
+        self._launches += 1
+        return self.o.si_return_diagonal_elements(block.a, list(index_values), self._moa)
+
+    def si_invert_diagonal(self, a1, a2):
+        self._launches += 1
+        return self.o.si_invert_diagonal(a1.a, a2.a)
+
+    def si_invert_diagonal_asym(self, a1, index_values, a2):
+        self._launches += 1
+        return self.o.si_invert_diagonal_asym(a1.a, list(index_values), a2.a, self._moa)
 
     def si_energy_denominator_rhf(self, block, index_values, fock):
         self._launches += 1

@@ -52,6 +52,11 @@ def test_reference_triples_programs_device_test_body_on_the_fake_api(oracle):
     pt.test_reference_triples_programs_on_the_device(FakeApi(oracle), "hf_dat", True)
 
 
+def test_reference_eom_program_device_test_body_on_the_fake_api(oracle):
+    import test_gpu_z_eom_ccsd as eom
+    eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True)
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

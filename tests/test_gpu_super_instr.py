@@ -118,3 +118,22 @@ def test_return_sval_and_invert_diagonal(sip, oracle):
         assert oracle.si_invert_diagonal(a1, a2) == 0
         assert np.array_equal(d1.to_numpy(), a1)
     assert sip.si_invert_diagonal(sip.DeviceBlock((2, 2)), sip.DeviceBlock((2, 2))) != 0
+
+
+def test_return_diagonal_elements_and_invert_diagonal_asym(sip, oracle):
+    rng = np.random.default_rng(21)
+    for shape, iv in (((8, 8), (2, 2)), ((5, 5, 8, 8), (1, 1, 2, 2)), ((20, 20, 50, 50), (1, 1, 2, 2))):
+        x = fblock(rng, shape)
+        d = sip.DeviceBlock.from_numpy(x)
+        assert sip.si_return_diagonal_elements(d, iv) == 0
+        assert oracle.si_return_diagonal_elements(x, iv, SEGS) == 0
+        assert np.array_equal(d.to_numpy(), x)
+    assert sip.si_return_diagonal_elements(sip.DeviceBlock((2, 3)), (1, 1)) != 0
+    for shape, iv in (((1, 8, 5, 8, 5), (3, 2, 1, 2, 1)), ((1, 50, 20, 50, 20), (7, 2, 1, 2, 1)), ((2, 8, 5, 5, 8), (1, 2, 1, 1, 2))):
+        a1, a2 = fblock(rng, shape), fblock(rng, shape)
+        a2.ravel(order="F")[::9] = 0.0
+        d1 = sip.DeviceBlock.from_numpy(a1)
+        assert sip.si_invert_diagonal_asym(d1, iv, sip.DeviceBlock.from_numpy(a2)) == 0
+        assert oracle.si_invert_diagonal_asym(a1, iv, a2, SEGS) == 0
+        assert np.array_equal(d1.to_numpy(), a1), shape
+    assert sip.si_invert_diagonal_asym(sip.DeviceBlock((2, 2, 2)), (1, 1, 1), sip.DeviceBlock((2, 2, 2))) != 0

@@ -1,5 +1,6 @@
 """CPU tests of the super-instruction oracle (oracle/super_instr_oracle.c) against independent numpy statements of
-energy_denominator_rhf.F, stripi.F, anti_symm_o/v.F, return_sval.F and invert_diagonal.F."""
+energy_denominator_rhf.F, stripi.F, anti_symm_o/v.F, return_sval.F, invert_diagonal.F, invert_diagonal_asym.F and
+return_diagonal_elements.F."""
 import numpy as np
 import pytest
 
@@ -127,3 +128,40 @@ def test_return_sval_and_invert_diagonal(oracle):
         assert oracle.si_invert_diagonal(a1, a2) == 0
         assert np.array_equal(a1, ref)
     assert oracle.si_invert_diagonal(np.zeros((2, 2), order="F"), np.zeros((2, 2), order="F")) == 1
+
+
+def test_return_diagonal_elements_and_invert_diagonal_asym(oracle):
+    """return_diagonal_elements.F: x(p,p) / x(p,p,r,r) survive, by POSITION inside the block (both dimensions of a pair are
+    declared over the first one's range); invert_diagonal_asym.F: rank 5, a1 /= a2 where the orbital numbers b != d and
+    c != e (segment offsets count) and a2 != 0, a1 = 0 on the b == d or c == e planes"""
+    rng = np.random.default_rng(8)
+    segs = [2, 3, 3, 5]
+    x = np.asfortranarray(rng.uniform(-1, 1, (4, 4)))
+    ref = np.diag(np.diag(x))
+    assert oracle.si_return_diagonal_elements(x, (3, 4), segs) == 0 and np.array_equal(x, ref)
+    x = np.asfortranarray(rng.uniform(-1, 1, (3, 3, 5, 5)))
+    ref = np.zeros_like(x)
+    for p in range(3):
+        for r in range(5):
+            ref[p, p, r, r] = x[p, p, r, r]
+    assert oracle.si_return_diagonal_elements(x, (2, 3, 4, 4), segs) == 0 and np.array_equal(x, ref)
+    assert oracle.si_return_diagonal_elements(np.zeros((2, 3), order="F"), (1, 2), segs) == 1
+    assert oracle.si_return_diagonal_elements(np.zeros((2, 2, 2), order="F"), (1, 1, 1), segs) == 1
+    # blocks [k, a, i, a1, i1]: a in virtual segment 3 (orbitals 6..8), a1 in segment 4 (9..13) or 3; i, i1 in segments 1 / 2
+    off = np.concatenate([[0], np.cumsum(segs)])
+    for iv in ((1, 3, 1, 3, 1), (1, 3, 1, 4, 2), (2, 4, 2, 3, 2)):
+        shape = (1,) + tuple(segs[s - 1] for s in iv[1:])
+        a1 = np.asfortranarray(rng.uniform(-1, 1, shape))
+        a2 = np.asfortranarray(rng.uniform(-1, 1, shape))
+        a2.ravel(order="F")[::5] = 0.0
+        ref = a1.copy(order="F")
+        for idx in np.ndindex(*shape):
+            g = [idx[d] + off[iv[d] - 1] for d in range(1, 5)]
+            if g[0] != g[2] and g[1] != g[3]:
+                if a2[idx] != 0.0:
+                    ref[idx] = a1[idx] / a2[idx]
+            else:
+                ref[idx] = 0.0
+        assert oracle.si_invert_diagonal_asym(a1, iv, a2, segs) == 0
+        assert np.array_equal(a1, ref), iv
+    assert oracle.si_invert_diagonal_asym(np.zeros((2, 2, 2), order="F"), (1, 1, 1), np.zeros((2, 2, 2), order="F"), segs) == 1
