@@ -321,12 +321,6 @@ __global__ void __launch_bounds__(kPT, (EPT <= 6 && !(RAG && ACC)) ? 3 : 2) perm
 // landed; ONE barrier per tile.  VLD: 16-byte cp.async when the input runs are even and 16-byte aligned; VST: 16-byte global
 // stores (two 8-byte shared-memory reads of output-adjacent elements) when the output runs are.  Registers hold table entries only.
 constexpr int kRingStages = 3;
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -335,6 +329,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int ring_min_ctas(int ept, bool heavy) { return (ept <= 4 ? 4 : ept <= 8 ? 3 : 2) - (heavy ? 1 : 0); }   // heavy: ragged tiles or fused accumulate (more registers)
 
+__device__ __forceinline__ void cp_async8s(unsigned saddr, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16s(unsigned saddr, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ double lds_f64(unsigned saddr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
+// Instruction budget of the tile loop: every shared-memory address is a 32-bit byte address (stage base + the thread's byte
+// offset from the plan table), the validity of a thread's slots is one bit mask when the tile is not ragged -- about 10 warp
+// instructions per 32 elements moved (the first version spent 51 on 64-bit generic address arithmetic and parameter reloads).
 template <int EPT, bool RAG, bool ACC, bool VLD, bool VST>
 __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_ring_kernel(const __grid_constant__ PermArgs a, const __grid_constant__ PermBatch b, const int* __restrict__ ptab,
                                                                                const int4* __restrict__ wtab, int stage_elems) {
@@ -342,41 +351,50 @@ __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_r
     constexpr int NL = VLD ? EPT / 2 : EPT;   // load units per thread (elements or pairs)
     constexpr int NS = VST ? EPT / 2 : EPT;   // store units per thread
     const int tid = threadIdx.x;
-    int r_off[NL], r_pos[NL], r_rag[RAG ? NL : 1];
-    int w_off[NS], w_p0[NS], w_p1[VST ? NS : 1], w_rag[RAG ? NS : 1];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+    const unsigned stage_bytes = (unsigned)stage_elems * 8u;
+    int r_off[NL], r_rag[RAG ? NL : 1];
+    unsigned r_pb[NL];                          // staged position of the load unit, in bytes
+    int w_off[NS], w_rag[RAG ? NS : 1];
+    unsigned w_pb0[NS], w_pb1[VST ? NS : 1];    // staged position(s) of the store unit, in bytes
+    unsigned rmask = 0, wmask = 0;              // which slots of this thread are real elements of the tile
 #pragma unroll
     for (int u = 0; u < NL; ++u) {
         const int e = (tid + u * kPT) * (VLD ? 2 : 1);
-        r_off[u] = r_pos[u] = 0;
+        r_off[u] = 0;
+        r_pb[u] = 0;
         if (RAG) r_rag[u] = kInvalid;
         if (e < a.V) {
             const int2 r = __ldg(a.rtab + e);
             r_off[u] = r.x;
-            r_pos[u] = __ldg(ptab + e);
+            r_pb[u] = (unsigned)__ldg(ptab + e) * 8u;
             if (RAG) r_rag[u] = r.y;
+            rmask |= 1u << u;
         }
     }
 #pragma unroll
     for (int u = 0; u < NS; ++u) {
         const int e = (tid + u * kPT) * (VST ? 2 : 1);
-        w_off[u] = w_p0[u] = 0;
-        if (VST) w_p1[u] = 0;
+        w_off[u] = 0;
+        w_pb0[u] = 0;
+        if (VST) w_pb1[u] = 0;
         if (RAG) w_rag[u] = kInvalid;
         if (e < a.V) {
             const int4 w = __ldg(wtab + e);
             w_off[u] = w.x;
-            w_p0[u] = w.y;
+            w_pb0[u] = (unsigned)w.y * 8u;
             if (RAG) w_rag[u] = w.z;
-            if (VST) w_p1[u] = w.w;
+            if (VST) w_pb1[u] = (unsigned)w.w * 8u;
+            wmask |= 1u << u;
         }
     }
     auto r_ok = [&](int u, int lim0, int lim1) {
         if constexpr (RAG) return (r_rag[u] & 0xffff) < lim0 && (r_rag[u] >> 16) < lim1;
-        else return (tid + u * kPT) * (VLD ? 2 : 1) < a.V;
+        else return (rmask >> u) & 1u;
     };
     auto w_ok = [&](int u, int lim0, int lim1) {
         if constexpr (RAG) return (w_rag[u] & 0xffff) < lim0 && (w_rag[u] >> 16) < lim1;
-        else return (tid + u * kPT) * (VST ? 2 : 1) < a.V;
+        else return (wmask >> u) & 1u;
     };
     const long long total = a.ntiles * b.n;
     const unsigned ntiles32 = (unsigned)a.ntiles;
@@ -403,31 +421,31 @@ __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_r
     // destination and ragged limits of the tiles in flight: a register ring shifted once per tile (kRingStages == 3)
     double *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
     int l00 = kNoLimit, l01 = kNoLimit, l10 = kNoLimit, l11 = kNoLimit, l20 = kNoLimit, l21 = kNoLimit;
-    auto issue = [&](long long work, int stage, double*& dst, int& lim0, int& lim1) {
+    auto issue = [&](long long work, unsigned sstage, double*& dst, int& lim0, int& lim1) {
         if (work < total) {
             const double* src;
             decode(work, src, dst, lim0, lim1);
-            double* st = sm + (size_t)stage * stage_elems;
 #pragma unroll
             for (int u = 0; u < NL; ++u)
                 if (r_ok(u, lim0, lim1)) {
-                    if (VLD) cp_async16(st + r_pos[u], src + r_off[u]);
-                    else cp_async8(st + r_pos[u], src + r_off[u]);
+                    if (VLD) cp_async16s(sstage + r_pb[u], src + r_off[u]);
+                    else cp_async8s(sstage + r_pb[u], src + r_off[u]);
                 }
         }
         cp_async_commit();
     };
     const long long w0 = blockIdx.x, step = gridDim.x;
-    issue(w0, 0, d0, l00, l01);
-    issue(w0 + step, 1, d1, l10, l11);
+    issue(w0, sbase, d0, l00, l01);
+    issue(w0 + step, sbase + stage_bytes, d1, l10, l11);
     int stage = 0;
+    const double alpha = b.alpha, beta = b.beta;
     for (long long work = w0; work < total; work += step) {
         cp_async_wait<kRingStages - 2>();   // this thread's copies of the current tile have landed ...
         __syncthreads();                     // ... everybody's have, and everybody is done reading the stage refilled next
         int nstage = stage + 2;
         if (nstage >= kRingStages) nstage -= kRingStages;
-        issue(work + 2 * step, nstage, d2, l20, l21);
-        const double* st = sm + (size_t)stage * stage_elems;
+        issue(work + 2 * step, sbase + (unsigned)nstage * stage_bytes, d2, l20, l21);
+        const unsigned st = sbase + (unsigned)stage * stage_bytes;
         double* __restrict__ cdst = d0;
         if constexpr (VST) {
             if (ACC) {
@@ -439,8 +457,8 @@ __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_r
                 for (int u = 0; u < NS; ++u)
                     if (w_ok(u, l00, l01)) {
                         double2 v;
-                        v.x = b.alpha * st[w_p0[u]] + b.beta * o[u].x;
-                        v.y = b.alpha * st[w_p1[u]] + b.beta * o[u].y;
+                        v.x = alpha * lds_f64(st + w_pb0[u]) + beta * o[u].x;
+                        v.y = alpha * lds_f64(st + w_pb1[u]) + beta * o[u].y;
                         *reinterpret_cast<double2*>(cdst + w_off[u]) = v;
                     }
             } else {
@@ -448,8 +466,8 @@ __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_r
                 for (int u = 0; u < NS; ++u)
                     if (w_ok(u, l00, l01)) {
                         double2 v;
-                        v.x = st[w_p0[u]];
-                        v.y = st[w_p1[u]];
+                        v.x = lds_f64(st + w_pb0[u]);
+                        v.y = lds_f64(st + w_pb1[u]);
                         *reinterpret_cast<double2*>(cdst + w_off[u]) = v;
                     }
             }
@@ -461,11 +479,11 @@ __global__ void __launch_bounds__(kPT, ring_min_ctas(EPT, RAG || ACC)) permute_r
                     if (w_ok(u, l00, l01)) o[u] = cdst[w_off[u]];
 #pragma unroll
                 for (int u = 0; u < NS; ++u)
-                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = b.alpha * st[w_p0[u]] + b.beta * o[u];
+                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = alpha * lds_f64(st + w_pb0[u]) + beta * o[u];
             } else {
 #pragma unroll
                 for (int u = 0; u < NS; ++u)
-                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = st[w_p0[u]];
+                    if (w_ok(u, l00, l01)) cdst[w_off[u]] = lds_f64(st + w_pb0[u]);
             }
         }
         d0 = d1; l00 = l10; l01 = l11;
