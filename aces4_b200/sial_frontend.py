@@ -43,8 +43,8 @@ deallocate_local) -- here a block is created, zero-filled, when it is first touc
 
 `set_persistent` hands an array (or scalar) over to the backend's label registry and `restore_persistent` adopts it into
 the array of that name declared by the program that follows -- how the reference chains its programs (scf -> tran -> cc,
-worker_persistent_array_manager.cpp:34-155).  The hand-over happens when the statement executes (the reference defers
-it to the end of the program), so the statements belong at the end / start of a program, where the reference's have them.
+worker_persistent_array_manager.cpp:34-155).  As in the reference the hand-over happens when the program ENDS (Walker.run /
+run_proc return), so an array stays usable after its `set_persistent` statement.
 
 Procedures: statements between `proc NAME` and `endproc` form a procedure; `call NAME` runs it; `Walker.run()` runs
 the main program (the statements outside procedures) and `Walker.run_proc(NAME)` one procedure (the test drivers use
@@ -409,6 +409,28 @@ def set_ijk_aab(moa_seg_ranges, baocc, eaocc, maxi=5, ordered_k=False):
     return table
 
 
+def compute_diis(B):
+    """The reference's `execute compute_diis BB` (super_instructions/qm/utility/compute_diis.F -> form_R.F:8-110): the upper
+    triangle of the error-overlap matrix BB is symmetrised, its all-zero rows (history slots not filled yet) are dropped from
+    the end, the matrix is bordered with -1 / 0 and R c = (0, ..., 0, -1) is solved with LAPACK dgesv; the coefficients come back
+    on the DIAGONAL of BB (zero for the unused slots).  Host control logic of the CC iterations (order <= 30).  -> [c_1 .. c_n]"""
+    import numpy as np
+
+    B = np.array(B, dtype=float)
+    n = B.shape[0]
+    R = np.triu(B) + np.triu(B, 1).T
+    ndim = n - sum(1 for i in range(n) if not np.any(np.abs(R[i, :]) > 0.0))
+    M = np.zeros((ndim + 1, ndim + 1))
+    M[:ndim, :ndim] = R[:ndim, :ndim]
+    M[:ndim, ndim] = M[ndim, :ndim] = -1.0
+    v = np.zeros(ndim + 1)
+    v[ndim] = -1.0
+    c = np.linalg.solve(M, v)
+    out = np.zeros(n)
+    out[:ndim] = c[:ndim]
+    return out
+
+
 def gen_eigen_calc(A):
     """The reference's `execute gen_eigen_calc G L R E` (super_instructions/qm/utility/gen_eigen_calc.F:60-78 and its
     dgeev_wrapper :80-230): LAPACK DGEEV('V','V') of the (zero-padded) subspace matrix, real parts of the eigenvalues,
@@ -473,6 +495,7 @@ class Walker:
             if name in self.constants:
                 self.scalars[name] = float(self.constants[name])
         self._own_memo = {}
+        self._pending_persist = []   # (name, label) of the set_persistent statements executed so far: handed over at the end
         self.own_static = {}     # static arrays the program itself fills (St1a[a,i], SHDiag[a,i], ...): name -> {segs: handle}
 
     # ---- helpers -------------------------------------------------------------------------------------
@@ -633,11 +656,28 @@ class Walker:
     # ---- execution -----------------------------------------------------------------------------------
     def run(self):
         self._block(self.p.body)
+        self._hand_over()
         return self.scalars
 
     def run_proc(self, name):
         self._x_call(name)
+        self._hand_over()
         return self.scalars
+
+    def _hand_over(self):
+        """`set_persistent` takes effect when the program ends (worker_persistent_array_manager.cpp:34-88: the arrays are
+        moved to the persistent manager in `save_marked_arrays` after the last instruction), so `restore_persistent ca "ca"`
+        directly followed by `set_persistent ca "ca"` (rccsd_rhf.sialx:229-232) keeps the array usable in between"""
+        pending, self._pending_persist = self._pending_persist, []
+        for name, label in pending:
+            if self._is_table(name):           # a host table (e.g. the converged roots SEk0): handed over by value
+                self.host_registry[label] = dict(self.tables.get(name, {}))
+            elif name in self.own_static:
+                self.host_registry[label] = self.own_static.pop(name)
+            elif name in self.p.scalars:
+                self.be.persist_scalar(label, self.be.value(self.scalars[name]))
+            else:
+                self.be.set_persistent(name, label)
 
     def _x_call(self, name):
         if name not in self.p.procs:
@@ -725,14 +765,9 @@ class Walker:
             self.be.free(h)
 
     def _x_set_persistent(self, name, label):
-        if self._is_table(name):           # a host table (e.g. the converged roots SEk0): handed over by value
-            self.host_registry[label] = dict(self.tables.get(name, {}))
-        elif name in self.p.scalars:
-            self.be.persist_scalar(label, self.be.value(self.scalars[name]))
-        elif self._is_remote(name):
-            self.be.set_persistent(name, label)
-        else:
+        if not (self._is_table(name) or name in self.p.scalars or self._is_remote(name)):
             raise SialSyntaxError(f"set_persistent of {name}: not a scalar, served, distributed or static array")
+        self._pending_persist = [(n, lab) for n, lab in self._pending_persist if lab != label] + [(name, label)]
 
     def _x_restore_persistent(self, name, label):
         if self._is_table(name):
@@ -818,7 +853,9 @@ class Walker:
     def _x_put(self, arr, alabs, op, src, slabs):
         s, sl = self._read(src, slabs)
         if tuple(sl) != tuple(alabs):
-            raise SialSyntaxError("put/prepare needs matching labels on both sides")
+            if self._core(sl) != self._core(alabs):
+                raise SialSyntaxError("put/prepare needs matching labels on both sides")
+            s = self.be.reshaped(s, self._shape(alabs))     # `PREPARE Daibj[a,i,b,j,kiter] = Taibj[a,i,b,j]`: extent-1 dimensions
         (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._array_segs(arr, alabs), s)
 
     def _x_execute(self, fname, args, bare):
@@ -830,6 +867,15 @@ class Walker:
             return
         if fname == "get_my_rank":
             self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), float(self.rank))
+            return
+        if fname == "compute_diis":                  # the DIIS equations of the CC iterations: host LAPACK (dgesv), as in the reference
+            B = bare[0]
+            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[B][1][1]])
+            n = hi - lo + 1
+            t = self.tables.setdefault(B, {})
+            c = compute_diis([[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)])
+            for i in range(n):
+                t[(i + lo, i + lo)] = float(c[i])
             return
         if fname == "gen_eigen_calc":                # dgeev of the Davidson subspace matrix: host LAPACK, as in the reference
             G, L, R, E = bare

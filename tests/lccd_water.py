@@ -245,3 +245,35 @@ def eom_simple_extents(program, constants):
         lo, hi = (int(x) if x.isdigit() else int(constants[x]) for x in (lo, hi))
         out[lab] = hi - lo + 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CCSD program VERBATIM (tests/golden/rccsd_rhf_program.sialx = src/sialx/qm/cc/rccsd_rhf.sialx, generated by
+# scripts/make_rccsd_golden.py): the `DO KITER` loop with DIIS and the convergence test at the setup's cc_conv
+PROGRAM_RCCSD = open(os.path.join(HERE, "golden", "rccsd_rhf_program.sialx")).read()
+
+
+def program_array_kinds(program):
+    """index kinds of every served / distributed array a program declares ('s': simple index, blocks of extent 1)"""
+    return {n: tuple(program.index_kind[d] for d in decl) for n, (k, decl) in program.arrays.items() if k in ("served", "distributed")}
+
+
+def used_arrays(text):
+    """names of the arrays a program text moves blocks of (request / get / put / prepare / restore_persistent / set_persistent)"""
+    return {n.lower() for n in re.findall(r"(?im)^\s*(?:request|get|put|prepare|restore_persistent|set_persistent)\s+([a-z_]\w*)", text)}
+
+
+def device_program_arrays(sip, program, text, constants, segs, skip=()):
+    """one (zero-filled) api.DistArray per served / distributed array the program text touches; a simple-index dimension
+    becomes as many one-element segments as the index has values"""
+    seg_ext = dict(segs)
+    seg_ext["p"] = list(segs["o"]) + list(segs["v"])
+    simple = eom_simple_extents(program, constants)
+    used = used_arrays(text)
+    out = {}
+    for name, (kind, decl) in program.arrays.items():
+        if kind not in ("served", "distributed") or name not in used or name in skip:
+            continue
+        out[name] = sip.DistArray([[1] * simple[d] if program.index_kind[d] == "s" else seg_ext[program.index_kind[d]] for d in decl])
+        out[name].fill_local(0.0)
+    return out

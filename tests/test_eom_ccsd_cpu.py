@@ -18,44 +18,59 @@ from aces4_b200.sial_frontend import Program, Walker, gen_eigen_calc, parse_expr
 from sial_oracle_backend import OracleBackend
 
 
-def run_eom(oracle, case):
+def run_eom(oracle, case, tight):
+    """tight: ground state from the hand-transcribed CCSD equations iterated to 1e-12 (no DIIS); else the reference's chain:
+    rccsd_rhf.sialx verbatim (DIIS, stopped at the setup's cc_conv = 1e-10) -> persistent arrays -> the EOM program"""
     inp = lw.inputs(case)
-    be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
-    w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
-    _, hist = lw.converge(w, be.value, tol=1e-12, max_iter=150)
-    Walker(Program(lw.VSAAAI_FRAGMENT), be, inp["segs"], index_base=inp["index_base"]).run()
-    dense = {n: qm.join_blocks(be.arrays[n], [inp["segs"][k] for k in lw.KINDS[n]]) for n in ("vpiqj", "vaaii")}
-    e_cis, c1 = lw.cis_guess(inp, dense)
+    reg = OracleBackend.registry
+    if tight:
+        be = OracleBackend(oracle, inp["arrays"], fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+        w = Walker(Program(lw.PROGRAM_CCSD), be, inp["segs"], index_base=inp["index_base"])
+        _, hist = lw.converge(w, be.value, tol=1e-12, max_iter=150)
+        e_ccsd = inp["e_scf"] + hist[-1]
+        reg.clear()
+        reg.update({label: be.arrays[arr] for label, arr in lw.EOM_LABELS.items() if label != "VSaaai"})
+        reg.update(ca=be.arrays["ca"], fock_a=qm.split_blocks(inp["fock"], [inp["segs"]["p"], inp["segs"]["p"]]))
+    else:
+        from test_rccsd_reference_program_cpu import run_rccsd
+        e_ccsd = run_rccsd(oracle, case)[0]
+    # what rlambda / rcis leave behind for the EOM program: VSaaai (antisymmetrised Vaaai) and the CIS vectors
+    be_f = OracleBackend(oracle, {"vaaai": reg["Vaaai"], "vsaaai": {}}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    Walker(Program(lw.VSAAAI_FRAGMENT), be_f, inp["segs"], index_base=inp["index_base"]).run()
+    reg["VSaaai"] = be_f.arrays["vsaaai"]
+    dense = {n: qm.join_blocks(reg[lab], [inp["segs"][k] for k in lw.KINDS[n]]) for n, lab in (("vpiqj", "Vpiqj"), ("vaaii", "Vaaii"))}
+    e_cis, reg["C1_a"] = lw.cis_guess(inp, dense)
     prog = Program(lw.PROGRAM_EOM)
-    OracleBackend.registry.clear()
-    OracleBackend.registry.update({label: be.arrays[arr] for label, arr in lw.EOM_LABELS.items()})
-    OracleBackend.registry["C1_a"] = c1
     arrays = {n: {} for n in lw.eom_array_kinds(prog)}
-    arrays.update(aoint=be.arrays["aoint"], ca=be.arrays["ca"],
-                  fock_a=qm.split_blocks(inp["fock"], [inp["segs"]["p"], inp["segs"]["p"]]))
+    arrays.update(aoint=inp["arrays"]["aoint"], ca=reg["ca"], fock_a=reg["fock_a"])
     be2 = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
     w2 = Walker(prog, be2, inp["segs"], index_base=inp["index_base"], constants=lw.eom_constants())
     w2.run()
     roots = [w2.tables["sek0"][(k,)] for k in range(1, len(e_cis) + 1)]
-    return roots, e_cis, inp["e_scf"] + hist[-1], be2.calls, Walker.host_registry.get("reom_Ek")
+    return roots, e_cis, e_ccsd, be2.calls, Walker.host_registry.get("reom_Ek")
 
 
-@pytest.mark.parametrize("case", ["eom_dat", "eom_fine"])
-def test_reference_eom_program_reproduces_the_four_roots_of_eom_ccsd_water_test(oracle, case):
+@pytest.mark.parametrize("case,tight", [("eom_dat", False), ("eom_dat", True), ("eom_fine", True)])
+def test_reference_eom_program_reproduces_the_four_roots_of_eom_ccsd_water_test(oracle, case, tight):
     """eom_dat: the reference's own segmentation (one occupied, one virtual, one AO segment); eom_fine: occupied 2 + 3, virtual
-    3 + 5, AO 4 + 7 + 2 -- every pardo runs over several blocks, the `where a < a1` branches are taken.  Measured: both give
-    0.32850656893285, 0.41193398931800, 0.42288344176331, 0.51159731127927 (equal to 1e-15): 1.1e-9, 7.5e-10, 1.3e-10, 5.3e-10
-    from the goldens, which carry the reference run's cc_conv = 1e-10 (the ground state here is converged to 1e-12): the first
-    root is 1.8e-12 from the golden of the reference's tightly converged run of the same molecule (DISABLED_eom_test)."""
+    3 + 5, AO 4 + 7 + 2 -- every pardo runs over several blocks, the `where a < a1` branches are taken.
+    The reference's chain (tight = False: rccsd_rhf.sialx verbatim with DIIS, stopped at cc_conv = 1e-10 with the golden's
+    ccsd_energy to 3e-14, then the EOM program): roots 0.32850656917162, 0.41193398958067, 0.42288344248848, 0.51159731181814
+    = 8.6e-10, 4.9e-10, 8.6e-10, 1.4e-11 from the goldens (asserted at the reference's 1e-8; what is left is the Davidson
+    solver's own stopping rule -- `orb_conv < 10 eom_tol` five times in a row forces convergence -- on slightly different
+    CIS starting vectors).  Ground state converged to 1e-12 instead (tight): 0.32850656893285, 0.41193398931800,
+    0.42288344176331, 0.51159731127927 at both segmentations (equal to 1e-15); the first root is then 1.8e-12 from the golden
+    of the reference's own tightly converged run of the same molecule (DISABLED_eom_test, cc_conv 1e-12)."""
     g = lw.GOLDEN["eom_ccsd_water_test"]
-    roots, e_cis, e_ccsd, calls, persisted = run_eom(oracle, case)
-    assert abs(e_ccsd - lw.golden_ccsd()[0]) < 1e-10
+    roots, e_cis, e_ccsd, calls, persisted = run_eom(oracle, case, tight)
+    assert abs(e_ccsd - lw.golden_ccsd()[0 if tight else 1]) < (1e-10 if tight else 1e-12)
     for got, want in zip(e_cis, lw.GOLDEN["eom_test"]["cis_sek0"]):        # the starting vectors: the reference's CIS roots
         assert abs(got - want) < 1e-9, (got, want)
     for got, want in zip(roots, g["sek0"]):
         assert abs(got - want) < g["tolerance"], (roots, g["sek0"])
     assert max(abs(a - b) for a, b in zip(roots, g["sek0"])) < 2e-9
-    assert abs(roots[0] - lw.GOLDEN["eom_test"]["eom_sek0"][0]) < 1e-10      # cc_conv 1e-12 run of the reference
+    if tight:
+        assert abs(roots[0] - lw.GOLDEN["eom_test"]["eom_sek0"][0]) < 1e-10      # cc_conv 1e-12 run of the reference
     assert persisted is not None and abs(persisted[(1,)] - roots[0]) == 0.0  # set_persistent SEk0 "reom_Ek"
     assert calls > 100000
 
