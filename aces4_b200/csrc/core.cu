@@ -184,7 +184,7 @@ int desc_alloc(size_t bytes, void** h, void** d) {
     Capture* cap = capture();
     if (!cap) return scratch_reserve(bytes, h, d);
     *h = malloc(bytes ? bytes : 1);
-    *d = pool_alloc(bytes ? bytes : 1);
+    *d = pool_alloc(bytes ? bytes : 1, true);   // plan-owned, long-lived: fresh space (see pool_alloc), never a freed temp's slot
     if (!*h || !*d) { free(*h); return SIPGPU_E_NOMEM; }
     cap->device.push_back(*d);
     return SIPGPU_OK;

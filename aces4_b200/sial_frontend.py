@@ -343,6 +343,8 @@ class Program:
                 return None
             if op in ("=", "*=") and "[" not in rhs:      # `T4kai[davidson,a,i] = omega`, `Tkai[kstate,a,i] *= (0.5)**(0.5)`
                 return ("fill_expr" if op == "=" else "scale_expr", name, labs, parse_expr(rhs))
+            if op in ("+=", "-=") and "[" not in rhs:     # `dipole[ixyz] -= dsum`: every element incremented by a number
+                return ("incr_expr", name, labs, -1.0 if op == "-=" else 1.0, parse_expr(rhs))
             raise SialSyntaxError("unsupported block statement")
         # scalar statements
         m = re.match(r"(\w+)\s*(\+=|-=|\*=|=)\s*(.+)$", line)
@@ -805,6 +807,15 @@ class Walker:
         else:
             self.be.fill(self._write(name, labs), v)
 
+    def _x_incr_expr(self, name, labs, sign, e):
+        v = sign * self._eval(e)
+        if self._is_table(name):
+            key = tuple(self.idx[x] for x in labs)
+            t = self.tables.setdefault(name, {})
+            t[key] = t.get(key, 0.0) + v
+        else:
+            self.be.increment(self._write(name, labs), v)    # Block::increment_elements, block.cpp:258-268
+
     def _x_scale_expr(self, name, labs, e):
         self.be.scale(self._write(name, labs), self._eval(e))
 
@@ -1016,6 +1027,9 @@ class DeviceBackend:
 
     def axpy(self, d, s, f):
         d.axpy(s, f)
+
+    def increment(self, b, v):
+        b.increment(v)
 
     def copy(self, d, dlabs, s, slabs):
         if tuple(dlabs) == tuple(slabs):

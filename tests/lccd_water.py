@@ -249,8 +249,29 @@ def eom_simple_extents(program, constants):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the reference's CCSD program VERBATIM (tests/golden/rccsd_rhf_program.sialx = src/sialx/qm/cc/rccsd_rhf.sialx, generated by
-# scripts/make_rccsd_golden.py): the `DO KITER` loop with DIIS and the convergence test at the setup's cc_conv
+# scripts/make_cc_program_goldens.py): the `DO KITER` loop with DIIS and the convergence test at the setup's cc_conv
 PROGRAM_RCCSD = open(os.path.join(HERE, "golden", "rccsd_rhf_program.sialx")).read()
+PROGRAM_RLCCD = open(os.path.join(HERE, "golden", "rlccd_rhf_program.sialx")).read()
+PROGRAM_RLCCSD = open(os.path.join(HERE, "golden", "rlccsd_rhf_program.sialx")).read()
+
+
+def setup_constants(case):
+    """the predefined ints / scalars of the case's setup file (cc_conv, cc_iter, scf_hist, baocc ...)"""
+    setup = FIXTURE["setups"][CASES[case][0]]
+    return {**setup["ints"], **setup["scalars"]}
+
+
+def all_orbital_statics(case, inp):
+    """the static arrays of the defs files, declared over ALL molecular orbital segments (`moaindex aces_defs_pa = 1: eavirt`):
+    ca[mu,pa] with the frozen-core columns in place, fock_a[pa,pa] -> {label: {segment tuple: block}}"""
+    C = scf(CASES[case][0])[7]
+    moa = inp["moa_seg_ranges"]
+    return {"ca": qm.split_blocks(C, [inp["segs"]["ao"], moa]), "fock_a": qm.split_blocks(inp["fock"], [moa, moa])}
+
+
+def segs_with_all_orbitals(inp):
+    """segment extents per index kind, plus 'pa' = every molecular orbital segment of the setup (frozen core included)"""
+    return {**inp["segs"], "pa": list(inp["moa_seg_ranges"])}
 
 
 def program_array_kinds(program):

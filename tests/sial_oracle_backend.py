@@ -50,6 +50,10 @@ class OracleBackend:
         b.a *= f
         self.calls += 1
 
+    def increment(self, b, v):
+        b.a += v
+        self.calls += 1
+
     def axpy(self, d, s, f):
         d.a[...] = self.o.block_add(d.a, s.a, f)[0]
         self.calls += 1

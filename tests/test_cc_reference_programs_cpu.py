@@ -1,0 +1,94 @@
+"""The reference's coupled-cluster programs VERBATIM -- tests/golden/rlccd_rhf_program.sialx, rlccsd_rhf_program.sialx,
+rccsd_rhf_program.sialx = src/sialx/qm/cc/rlccd_rhf.sialx, rlccsd_rhf.sialx, rccsd_rhf.sialx with the documented edits of
+scripts/make_cc_program_goldens.py (the AO integral engine is a `request`; LCCD's response-dipole call left out) -- walked by the
+SIAL front-end: the main program with `DO KITER`, DIIS (MOVET1 / MOVET2 / DIISN: five-index history arrays
+Daibj[a,i,b,j,kdiis] / Eaibj[...], the scalar-valued contractions into DIST_BB[jdiis,j1diis], `execute compute_diis BB` = host
+dgesv), the convergence test `IF ediff < ecrit ... exit` at the setup's cc_conv and the deferred `set_persistent` hand-over.
+Goldens (test/test_qm.cpp): BASELINE config 1 -- lccd_frozencore_test's lccd_correlation / lccd_energy (:459-462, the enabled
+test; frozen core: `ca` / `fock_a` over ALL orbital segments, the active ranges start at segment 2), the all-electron LCCD
+energy (:677-678), lccsd_test (:526-529), and eom_ccsd_water_test's ccsd_energy -75.71251002936883 (:990-991), which is the
+value of a run STOPPED at cc_conv = 1e-10 (the converged energy is -75.71251002928709): reproducing it to 1e-12 means the
+iteration PATH -- DIIS extrapolation included -- is the reference's.  Oracle backend (CPU); device twins:
+tests/test_gpu_z_eom_ccsd.py, tests/test_gpu_z_lccd_water_energy.py."""
+import numpy as np
+import pytest
+
+import lccd_water as lw
+from oracle import qm_inputs as qm
+from aces4_b200.sial_frontend import Program, Walker, compute_diis
+from sial_oracle_backend import OracleBackend
+
+PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD}
+
+
+def run_cc_program(oracle, name, case):
+    """-> (walker scalars as floats, backend calls); leaves the program's persistent arrays in OracleBackend.registry"""
+    inp = lw.inputs(case)
+    prog = Program(PROGRAMS[name])
+    arrays = {n: {} for n in lw.program_array_kinds(prog)}
+    arrays["aoint"] = inp["arrays"]["aoint"]
+    OracleBackend.registry.clear()
+    OracleBackend.registry.update({lab: inp["arrays"][lab.lower()] for lab in lw.PERSISTED})      # the transformation program's
+    OracleBackend.registry.update(scf_energy=inp["e_scf"], **lw.all_orbital_statics(case, inp))
+    be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.setup_constants(case))
+    sc = w.run()
+    return {k: be.value(v) for k, v in sc.items()}, be.calls
+
+
+def run_rccsd(oracle, case):
+    sc, calls = run_cc_program(oracle, "rccsd_rhf", case)
+    return sc["ccsd_energy"], int(sc["niter"]), calls
+
+
+def test_reference_ccsd_program_with_diis_stops_where_the_reference_stops(oracle):
+    """measured: -75.71251002936886 after 15 iterations (golden -75.71251002936883: 3e-14)"""
+    e, niter, calls = run_rccsd(oracle, "eom_dat")
+    assert abs(e - lw.golden_ccsd()[1]) < 1e-12, e
+    assert niter == 15
+    reg = OracleBackend.registry
+    assert {"t1a_old", "T2old_aa", "T2old_ab", "VSpipi", "Vaaii", "Viaai", "Vaaai", "Vpiqj", "ca", "fock_a", "ccsd_energy"} <= set(reg)
+    assert abs(reg["ccsd_energy"] - e) == 0.0 and reg["has_singles"] == 1.0
+
+
+def test_reference_ccsd_program_at_a_finer_segmentation(oracle):
+    """occupied 2 + 3, virtual 3 + 5, AO 4 + 7 + 2: the same iteration path block by block"""
+    e, niter, calls = run_rccsd(oracle, "eom_fine")
+    assert abs(e - lw.golden_ccsd()[1]) < 1e-12 and niter == 15
+
+
+@pytest.mark.parametrize("case", ["dat", "fine"])
+def test_reference_lccd_program_reproduces_lccd_frozencore_test(oracle, case):
+    """BASELINE config 1 through the reference's own program text (frozen core: moa [1 | 4 | 8]; `fine`: [1 | 2 2 | 3 5]).
+    measured: lccd_correlation -0.12610179885837 (golden -0.12610179886435: 6.0e-12), lccd_energy -75.71042854159870 (6.1e-12),
+    15 iterations (the setup's cc_conv is 1e-12)"""
+    g_corr, g_e, _ = lw.golden(case)
+    sc, calls = run_cc_program(oracle, "rlccd_rhf", case)
+    assert abs(sc["lccd_correlation"] - g_corr) < lw.GOLDEN["tolerance"], sc["lccd_correlation"]
+    assert abs(sc["lccd_energy"] - g_e) < lw.GOLDEN["tolerance"], sc["lccd_energy"]
+    assert abs(sc["lccd_correlation"] - g_corr) < 2e-11 and int(sc["niter"]) == 15
+
+
+def test_reference_lccd_and_lccsd_programs_all_electron(oracle):
+    """eom_lccd_test / lccsd_test (test/test_qm.cpp:677-678, 526-529).  measured: lccd_energy 2.9e-12, lccsd_correlation
+    -0.12865706498546847 vs the golden -0.12865706498547 (1.5e-15), lccsd_energy 1.3e-13"""
+    sc, _ = run_cc_program(oracle, "rlccd_rhf", "all_dat")
+    assert abs(sc["lccd_energy"] - lw.golden("all_dat")[1]) < 2e-11
+    sc, _ = run_cc_program(oracle, "rlccsd_rhf", "all_dat")
+    g_corr, g_e = lw.golden_lccsd()
+    assert abs(sc["lccsd_correlation"] - g_corr) < 1e-12 and abs(sc["lccsd_energy"] - g_e) < 1e-11
+
+
+def test_compute_diis_follows_form_R():
+    """form_R.F: upper triangle symmetrised, trailing all-zero rows dropped, bordered system solved; the coefficients sum to 1"""
+    rng = np.random.default_rng(4)
+    n, m = 6, 3
+    E = rng.uniform(-1, 1, (m, 20))
+    B = np.zeros((n, n))
+    B[:m, :m] = np.triu(E @ E.T)          # only the upper triangle is read
+    c = compute_diis(B.tolist())
+    assert abs(sum(c) - 1.0) < 1e-12 and np.all(c[m:] == 0.0)
+    full = E @ E.T
+    M = np.block([[full, -np.ones((m, 1))], [-np.ones((1, m)), np.zeros((1, 1))]])
+    ref = np.linalg.solve(M, np.r_[np.zeros(m), -1.0])[:m]
+    assert np.allclose(c[:m], ref, atol=1e-13)

@@ -57,6 +57,12 @@ def test_reference_eom_program_device_test_body_on_the_fake_api(oracle):
     eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True)
 
 
+def test_reference_cc_programs_device_test_bodies_on_the_fake_api(oracle):
+    import test_gpu_z_cc_reference_programs as cc
+    cc.test_reference_lccd_program_on_the_device(FakeApi(oracle), "dat", True)
+    cc.test_reference_lccsd_and_ccsd_programs_on_the_device(FakeApi(oracle))
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

@@ -32,7 +32,7 @@ def run_eom(oracle, case, tight):
         reg.update({label: be.arrays[arr] for label, arr in lw.EOM_LABELS.items() if label != "VSaaai"})
         reg.update(ca=be.arrays["ca"], fock_a=qm.split_blocks(inp["fock"], [inp["segs"]["p"], inp["segs"]["p"]]))
     else:
-        from test_rccsd_reference_program_cpu import run_rccsd
+        from test_cc_reference_programs_cpu import run_rccsd
         e_ccsd = run_rccsd(oracle, case)[0]
     # what rlambda / rcis leave behind for the EOM program: VSaaai (antisymmetrised Vaaai) and the CIS vectors
     be_f = OracleBackend(oracle, {"vaaai": reg["Vaaai"], "vsaaai": {}}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])

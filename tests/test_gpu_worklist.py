@@ -282,9 +282,12 @@ def test_sliced_contractions_inside_a_recording(sip, oracle):
 
 
 def test_repeated_stream_is_replayed_not_rescheduled(sip, oracle):
-    """Every iteration of a CC program records the same pardo body on the same blocks.  The second recording of an
+    """Every iteration of a CC program records the same pardo body on the same blocks.  A repeated recording of an
     identical stream must be served from the captured launches (sipgpu_wl_replays), give the same result on NEW operand
-    values, and a stream that differs in one pointer must be scheduled afresh."""
+    values, and a stream that differs in one pointer must be scheduled afresh.  The temp addresses are a function of the
+    pool's free lists: the FIRST recording may have to carve new arena space for some of its temps, so the second one (which
+    finds all of them in the free list and takes them in address order) can still differ from it; from then on the stream
+    is stable -- the second pass may or may not replay, the third and fourth must."""
     v, o, n = 10, 6, 3
     rng = np.random.default_rng(17)
     dlab, llab, rlab = [1, 2, 3, 4], [1, 5, 3, 6], [2, 5, 4, 6]
@@ -307,7 +310,8 @@ def test_repeated_stream_is_replayed_not_rescheduled(sip, oracle):
         p.free()
 
     replays = []
-    for it in range(4):
+    last = 4
+    for it in range(last + 1):
         T2 = [[rng.uniform(-1, 1, (v, o, v, o)) for _ in range(n)] for _ in range(n)]
         V = [[rng.uniform(-1, 1, (o, o, o, o)) for _ in range(n)] for _ in range(n)]
         want = np.zeros((v, o, v, o), order="F")
@@ -320,10 +324,10 @@ def test_repeated_stream_is_replayed_not_rescheduled(sip, oracle):
                 want += t
         sip.sync()
         want = want + 0.5 * np.transpose(want, (2, 1, 0, 3))
-        dest = other if it == 3 else D            # the last pass writes another destination: a different stream
+        dest = other if it == last else D         # the last pass writes another destination: a different stream
         with sip.recording() as rec:
             body(dest)
             sip.wl_flush()
             replays.append(sip.wl_replays())
         assert rel(dest.to_numpy(), want) <= TOL, it
-    assert replays[0] == 0 and replays[1] == 1 and replays[2] == 1 and replays[3] == 0, replays
+    assert replays[0] == 0 and replays[2] == 1 and replays[3] == 1 and replays[last] == 0, replays

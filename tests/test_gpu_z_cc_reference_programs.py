@@ -1,0 +1,52 @@
+"""BASELINE config 1 ("test/lccd_test.dat LCCD water small basis", the enabled lccd_frozencore_test) and the LCCSD / CCSD jobs ON
+THE DEVICE through the reference's own program texts run VERBATIM: tests/golden/rlccd_rhf_program.sialx,
+rlccsd_rhf_program.sialx, rccsd_rhf_program.sialx (= src/sialx/qm/cc/*.sialx, scripts/make_cc_program_goldens.py) walked by the
+SIAL front-end on libsipgpu -- `DO KITER`, DIIS with its five-index history arrays and scalar-valued DIST_BB contractions,
+`energy_denominator_rhf`, the AO ladder over resident AO integrals, the convergence test at the setup's cc_conv -- against
+the energy goldens of test/test_qm.cpp.  CPU twin (oracle backend): tests/test_cc_reference_programs_cpu.py."""
+import pytest
+
+import device_chain as dc
+import lccd_water as lw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sip():
+    import aces4_b200 as s
+
+    s.init()
+    return s.api
+
+
+def run(sip, text, case, record):
+    inp = lw.inputs(case)
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp)
+    l0 = sip.kernel_launches()
+    _, _, sc = dc.run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, lw.setup_constants(case),
+                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    return sc, sip.kernel_launches() - l0
+
+
+@pytest.mark.timeout(900, method="thread")
+@pytest.mark.parametrize("case,record", [("dat", True), ("fine", False)])
+def test_reference_lccd_program_on_the_device(sip, case, record):
+    g_corr, g_e, _ = lw.golden(case)
+    sc, launches = run(sip, lw.PROGRAM_RLCCD, case, record)
+    print(f"\nrlccd_rhf.sialx verbatim on the device ({case}, record={record}): lccd_correlation {sc['lccd_correlation']:.14f} "
+          f"(golden {g_corr:.14f}), lccd_energy {sc['lccd_energy']:.14f} (golden {g_e:.14f}), {int(sc['niter'])} iterations, {launches} launches")
+    assert abs(sc["lccd_correlation"] - g_corr) < lw.GOLDEN["tolerance"] and abs(sc["lccd_energy"] - g_e) < lw.GOLDEN["tolerance"]
+    assert int(sc["niter"]) == 15 and launches > 0
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
+    sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
+    g_corr, g_e = lw.golden_lccsd()
+    print(f"\nrlccsd_rhf.sialx verbatim on the device: lccsd_correlation {sc['lccsd_correlation']:.14f} (golden {g_corr:.14f}), {launches} launches")
+    assert abs(sc["lccsd_correlation"] - g_corr) < 1e-11 and abs(sc["lccsd_energy"] - g_e) < 1e-10
+    sc, launches = run(sip, lw.PROGRAM_RCCSD, "eom_dat", True)
+    print(f"rccsd_rhf.sialx verbatim on the device: ccsd_energy {sc['ccsd_energy']:.14f} (golden at cc_conv 1e-10 {lw.golden_ccsd()[1]:.14f}), "
+          f"{int(sc['niter'])} iterations, {launches} launches")
+    assert abs(sc["ccsd_energy"] - lw.golden_ccsd()[1]) < 1e-11 and int(sc["niter"]) == 15

@@ -12,6 +12,7 @@ tests/test_eom_ccsd_cpu.py."""
 import numpy as np
 import pytest
 
+import device_chain as dc
 import lccd_water as lw
 from oracle import qm_inputs as qm
 
@@ -26,12 +27,6 @@ def sip():
     return s.api
 
 
-def upload(sip, A, blocks):
-    for idx, b in blocks.items():
-        view = A.block_view(idx)
-        sip._check(sip.lib().sipgpu_h2d(view.ptr, sip._hp(np.asfortranarray(b)), view.size), "h2d")
-
-
 def run_eom_on_device(sip, case, record):
     """the reference's chain on libsipgpu: rccsd_rhf.sialx verbatim (DIIS, stopped at the setup's cc_conv) -> persistent arrays
     (the library's label registry: the slabs never leave HBM) -> the EOM program"""
@@ -39,38 +34,12 @@ def run_eom_on_device(sip, case, record):
 
     inp = lw.inputs(case)
     consts = lw.eom_constants()
-    sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
-    seg_ext = dict(inp["segs"])
-    seg_ext["p"] = list(inp["segs"]["o"]) + list(inp["segs"]["v"])
-    fock = sip.DeviceBlock.from_numpy(inp["fock"])
-
-    def resident(name, kinds, blocks):
-        A = sip.DistArray([seg_ext[k] for k in kinds])
-        A.fill_local(0.0)
-        upload(sip, A, blocks)
-        return A
-
-    # what the SCF / transformation programs hand over
-    given = {lab: resident(lab, lw.KINDS[lab.lower()], inp["arrays"][lab.lower()]) for lab in lw.PERSISTED}
-    given["ca"] = resident("ca", lw.KINDS["ca"], inp["arrays"]["ca"])
-    given["fock_a"] = resident("fock_a", ("p", "p"), qm.split_blocks(inp["fock"], [seg_ext["p"], seg_ext["p"]]))
-    aoint = resident("aoint", lw.KINDS["aoint"], inp["arrays"]["aoint"])
-    sip.sync()
-    for label, A in given.items():
-        A.persist(label)
-    sip.persist_scalar("scf_energy", inp["e_scf"])
-
-    # ---- CCSD: the reference's program, verbatim ----
-    prog = Program(lw.PROGRAM_RCCSD)
-    arr = lw.device_program_arrays(sip, prog, lw.PROGRAM_RCCSD, consts, inp["segs"], skip=("aoint",))
-    arr["aoint"] = aoint
-    for name in ("ca", "fock_a"):
-        arr[name] = sip.DistArray([seg_ext[k] for k in (lw.KINDS["ca"] if name == "ca" else ("p", "p"))])
-    be = DeviceBackend(sip, arr, record=record)
-    be.fock, be.seg_ranges = fock, inp["moa_seg_ranges"]
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp)
     l0 = sip.kernel_launches()
-    sc = Walker(prog, be, inp["segs"], index_base=inp["index_base"], constants=consts).run()
-    e_ccsd, niter = be.value(sc["ccsd_energy"]), int(be.value(sc["niter"]))
+    # ---- CCSD: the reference's program, verbatim ----
+    _, _, sc = dc.run_program_on_device(sip, lw.PROGRAM_RCCSD, case, inp, seg_ext, aoint, fock, record, consts,
+                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    e_ccsd, niter = sc["ccsd_energy"], int(sc["niter"])
 
     # ---- what rlambda / rcis leave behind: VSaaai and the CIS vectors ----
     frag = {"vaaai": sip.DistArray([seg_ext[k] for k in lw.KINDS["vaaai"]]), "vsaaai": sip.DistArray([seg_ext[k] for k in lw.KINDS["vsaaai"]])}
@@ -91,18 +60,13 @@ def run_eom_on_device(sip, case, record):
 
     # ---- EOM-CCSD: the reference's right-hand program ----
     prog2 = Program(lw.PROGRAM_EOM)
-    parr = lw.device_program_arrays(sip, prog2, lw.PROGRAM_EOM, consts, inp["segs"], skip=("aoint",))
-    upload(sip, parr["c1_a"], c1)
+    c1_a = dc.resident(sip, [[1] * lw.eom_simple_extents(prog2, consts)["kstate"], seg_ext["v"], seg_ext["o"]], c1)
     sip.sync()
-    parr["c1_a"].persist("C1_a")
-    parr["aoint"] = aoint
-    for name in ("ca", "fock_a"):
-        parr[name] = sip.DistArray([seg_ext[k] for k in (lw.KINDS["ca"] if name == "ca" else ("p", "p"))])
-        parr[name].restore(name)
-    be2 = DeviceBackend(sip, parr, record=record)
-    be2.fock, be2.seg_ranges = fock, inp["moa_seg_ranges"]
-    w2 = Walker(prog2, be2, inp["segs"], index_base=inp["index_base"], constants=consts)
-    w2.run()
+    c1_a.persist("C1_a")
+    stat = dc.static_arrays(sip, seg_ext)
+    for name, A in stat.items():
+        A.restore(name)
+    w2, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
     roots = [w2.tables["sek0"][(k,)] for k in range(1, len(e_cis) + 1)]
     return roots, e_cis, e_ccsd, niter, sip.kernel_launches() - l0
 
