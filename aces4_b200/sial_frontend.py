@@ -210,7 +210,7 @@ class Program:
 
     def _parse(self, line, low, tok):
         kw = tok[0]
-        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "special", "broadcast_from", "assert_same"):
+        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "destroy", "special", "broadcast_from", "assert_same"):
             return None           # arrays exist (zero) from the start; nothing is printed; super-instruction signatures are not
                                   # needed; broadcast_from / assert_same: every worker computes the replicated statics itself
         if kw == "predefined":

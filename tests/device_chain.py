@@ -22,13 +22,15 @@ def resident(sip, seg_lists, blocks):
     return A
 
 
-def hand_over_scf_and_transformation(sip, case, inp):
-    """persist the MO integral classes, ca / fock_a (over ALL orbital segments) and scf_energy under the labels the CC programs
-    restore (rccsd_rhf.sialx:225-244, rlccd_rhf.sialx:243-251, :917-919).  -> (seg_ext per index kind, resident aoint, device Fock block)"""
+def hand_over_scf_and_transformation(sip, case, inp, transformed=True):
+    """persist the MO integral classes (transformed: from the dense numpy transformation; else the reference's transformation
+    program has to run first), ca / fock_a (over ALL orbital segments) and scf_energy under the labels the CC programs restore
+    (rccsd_rhf.sialx:225-244, rlccd_rhf.sialx:243-251, :917-919).  -> (seg_ext per index kind, resident aoint, device Fock block)"""
     sip.set_predefined_int_array("moa_seg_ranges", inp["moa_seg_ranges"])
     seg_ext = lw.segs_with_all_orbitals(inp)
     seg_ext["p"] = list(inp["segs"]["o"]) + list(inp["segs"]["v"])
-    given = {lab: resident(sip, [seg_ext[k] for k in lw.KINDS[lab.lower()]], inp["arrays"][lab.lower()]) for lab in lw.PERSISTED}
+    given = {lab: resident(sip, [seg_ext[k] for k in lw.KINDS[lab.lower()]], inp["arrays"][lab.lower()])
+             for lab in (lw.PERSISTED if transformed else ())}
     statics = lw.all_orbital_statics(case, inp)
     given["ca"] = resident(sip, [seg_ext["ao"], seg_ext["pa"]], statics["ca"])
     given["fock_a"] = resident(sip, [seg_ext["pa"], seg_ext["pa"]], statics["fock_a"])

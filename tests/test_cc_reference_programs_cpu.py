@@ -18,18 +18,23 @@ from oracle import qm_inputs as qm
 from aces4_b200.sial_frontend import Program, Walker, compute_diis
 from sial_oracle_backend import OracleBackend
 
-PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD}
+PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
+            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V}
 
 
-def run_cc_program(oracle, name, case):
-    """-> (walker scalars as floats, backend calls); leaves the program's persistent arrays in OracleBackend.registry"""
+def run_cc_program(oracle, name, case, chained=False):
+    """-> (walker scalars as floats, backend calls); leaves the program's persistent arrays in OracleBackend.registry.
+    chained: the registry already holds what the program before it handed over (else: the SCF results and the dense numpy
+    transformation of oracle/qm_inputs.py are put there)"""
     inp = lw.inputs(case)
     prog = Program(PROGRAMS[name])
     arrays = {n: {} for n in lw.program_array_kinds(prog)}
     arrays["aoint"] = inp["arrays"]["aoint"]
-    OracleBackend.registry.clear()
-    OracleBackend.registry.update({lab: inp["arrays"][lab.lower()] for lab in lw.PERSISTED})      # the transformation program's
-    OracleBackend.registry.update(scf_energy=inp["e_scf"], **lw.all_orbital_statics(case, inp))
+    if not chained:
+        OracleBackend.registry.clear()
+        if name != "tran_rhf_no4v":
+            OracleBackend.registry.update({lab: inp["arrays"][lab.lower()] for lab in lw.PERSISTED})      # the transformation program's
+        OracleBackend.registry.update(scf_energy=inp["e_scf"], **lw.all_orbital_statics(case, inp))
     be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
     w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.setup_constants(case))
     sc = w.run()
@@ -67,6 +72,24 @@ def test_reference_lccd_program_reproduces_lccd_frozencore_test(oracle, case):
     assert abs(sc["lccd_correlation"] - g_corr) < lw.GOLDEN["tolerance"], sc["lccd_correlation"]
     assert abs(sc["lccd_energy"] - g_e) < lw.GOLDEN["tolerance"], sc["lccd_energy"]
     assert abs(sc["lccd_correlation"] - g_corr) < 2e-11 and int(sc["niter"]) == 15
+
+
+@pytest.mark.parametrize("case", ["dat", "fine"])
+def test_config_1_from_ao_integrals_through_the_reference_texts(oracle, case):
+    """BASELINE config 1 end to end on the hot path: AO integrals + SCF orbitals -> tran_rhf_no4v.sialx VERBATIM (four quarter
+    transformations, the six MO classes handed over with set_persistent) -> rlccd_rhf.sialx VERBATIM -> the goldens of
+    lccd_frozencore_test.  The transformed classes equal the dense numpy transformation to 3e-15."""
+    inp = lw.inputs(case)
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    reg = OracleBackend.registry
+    assert {"VSpipi", "Vaaii", "Viaai", "Vaaai", "VSaaai", "Vpiqj", "ca"} <= set(reg)
+    for lab in lw.PERSISTED:
+        ref = inp["arrays"][lab.lower()]
+        assert set(reg[lab]) == set(ref)
+        assert max(float(np.max(np.abs(reg[lab][k] - ref[k]))) for k in ref) < 1e-13, lab
+    sc, _ = run_cc_program(oracle, "rlccd_rhf", case, chained=True)
+    g_corr, g_e, _ = lw.golden(case)
+    assert abs(sc["lccd_correlation"] - g_corr) < 2e-11 and abs(sc["lccd_energy"] - g_e) < 2e-11 and int(sc["niter"]) == 15
 
 
 def test_reference_lccd_and_lccsd_programs_all_electron(oracle):

@@ -20,7 +20,8 @@ from sial_oracle_backend import OracleBackend
 
 def run_eom(oracle, case, tight):
     """tight: ground state from the hand-transcribed CCSD equations iterated to 1e-12 (no DIIS); else the reference's chain:
-    rccsd_rhf.sialx verbatim (DIIS, stopped at the setup's cc_conv = 1e-10) -> persistent arrays -> the EOM program"""
+    tran_rhf_no4v.sialx -> rccsd_rhf.sialx verbatim (DIIS, stopped at the setup's cc_conv = 1e-10) -> persistent arrays -> the
+    EOM program"""
     inp = lw.inputs(case)
     reg = OracleBackend.registry
     if tight:
@@ -31,13 +32,14 @@ def run_eom(oracle, case, tight):
         reg.clear()
         reg.update({label: be.arrays[arr] for label, arr in lw.EOM_LABELS.items() if label != "VSaaai"})
         reg.update(ca=be.arrays["ca"], fock_a=qm.split_blocks(inp["fock"], [inp["segs"]["p"], inp["segs"]["p"]]))
-    else:
-        from test_cc_reference_programs_cpu import run_rccsd
-        e_ccsd = run_rccsd(oracle, case)[0]
-    # what rlambda / rcis leave behind for the EOM program: VSaaai (antisymmetrised Vaaai) and the CIS vectors
-    be_f = OracleBackend(oracle, {"vaaai": reg["Vaaai"], "vsaaai": {}}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
-    Walker(Program(lw.VSAAAI_FRAGMENT), be_f, inp["segs"], index_base=inp["index_base"]).run()
-    reg["VSaaai"] = be_f.arrays["vsaaai"]
+        be_f = OracleBackend(oracle, {"vaaai": reg["Vaaai"], "vsaaai": {}}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+        Walker(Program(lw.VSAAAI_FRAGMENT), be_f, inp["segs"], index_base=inp["index_base"]).run()
+        reg["VSaaai"] = be_f.arrays["vsaaai"]
+    else:     # tran_rhf_no4v.sialx -> rccsd_rhf.sialx, both verbatim (VSaaai is the transformation program's)
+        from test_cc_reference_programs_cpu import run_cc_program
+        run_cc_program(oracle, "tran_rhf_no4v", case)
+        e_ccsd = run_cc_program(oracle, "rccsd_rhf", case, chained=True)[0]["ccsd_energy"]
+    # what rcis leaves behind for the EOM program: the CIS vectors
     dense = {n: qm.join_blocks(reg[lab], [inp["segs"][k] for k in lw.KINDS[n]]) for n, lab in (("vpiqj", "Vpiqj"), ("vaaii", "Vaaii"))}
     e_cis, reg["C1_a"] = lw.cis_guess(inp, dense)
     prog = Program(lw.PROGRAM_EOM)

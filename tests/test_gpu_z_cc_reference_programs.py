@@ -41,6 +41,24 @@ def test_reference_lccd_program_on_the_device(sip, case, record):
 
 
 @pytest.mark.timeout(900, method="thread")
+def test_config_1_from_ao_integrals_on_the_device(sip):
+    """AO integrals + SCF orbitals resident -> tran_rhf_no4v.sialx VERBATIM -> (persistent-array registry: the MO classes never
+    leave HBM) -> rlccd_rhf.sialx VERBATIM -> the goldens of lccd_frozencore_test"""
+    case = "dat"
+    inp = lw.inputs(case)
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
+    consts = lw.setup_constants(case)
+    l0 = sip.kernel_launches()
+    dc.run_program_on_device(sip, lw.PROGRAM_TRAN_NO4V, case, inp, seg_ext, aoint, fock, True, consts, extra_arrays=dc.static_arrays(sip, seg_ext))
+    _, _, sc = dc.run_program_on_device(sip, lw.PROGRAM_RLCCD, case, inp, seg_ext, aoint, fock, True, consts,
+                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    g_corr, g_e, _ = lw.golden(case)
+    print(f"\ntran_rhf_no4v.sialx -> rlccd_rhf.sialx verbatim on the device: lccd_correlation {sc['lccd_correlation']:.14f} (golden {g_corr:.14f}), "
+          f"{sip.kernel_launches() - l0} launches")
+    assert abs(sc["lccd_correlation"] - g_corr) < lw.GOLDEN["tolerance"] and abs(sc["lccd_energy"] - g_e) < lw.GOLDEN["tolerance"]
+
+
+@pytest.mark.timeout(900, method="thread")
 def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
     sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
     g_corr, g_e = lw.golden_lccsd()
