@@ -68,7 +68,19 @@ _NUM = r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?"
 
 
 def _labels(s):
-    return tuple(x.strip().lower() for x in s.split(",") if x.strip())   # SIAL names are case-insensitive
+    """subscripts of an array reference, lower-cased (SIAL names are case-insensitive); the one-value range `x:x` that addresses
+    a contiguous array (`CLRB1_a[kstart:kstart,a:a,i:i]`) is the block `x`"""
+    out = []
+    for x in s.split(","):
+        x = x.strip().lower()
+        if not x:
+            continue
+        if ":" in x:
+            lo, hi = (y.strip() for y in x.split(":", 1))
+            if lo == hi:
+                x = lo
+        out.append(x)
+    return tuple(out)
 
 
 _TOK = re.compile(r"\s*(?:(\d+\.?\d*(?:[ed][-+]?\d+)?|\.\d+)|([a-z_]\w*)|(\[[^\]]*\])|(.))", re.I)
@@ -164,7 +176,8 @@ class Program:
         self.simple_range = {}    # simple index name -> (lo, hi) as written (numbers or predefined constants such as naocc)
         self.procs = {}           # name -> statement list (textual order kept: dicts are ordered)
         self.predefined = set()   # `predefined int|scalar X`: the value comes with the job (the .dat file), Walker(constants=...)
-        self.contiguous = set()   # `contiguous local X[...]`: print bookkeeping arrays, statements on them are ignored
+        self.contiguous = set()   # `contiguous local X[...]` arrays (held block-wise like `local` ones)
+        self.var_labels = set()   # int variables that occur as subscripts
         main = []
         stack = [main]
         opens = []
@@ -181,6 +194,19 @@ class Program:
                 raise SialSyntaxError(f"line {ln}: {e}: {raw.strip()!r}") from None
             if st is None:
                 continue
+            label_slots = {"assign": (2, 4), "add": (2, 4), "fill": (2,), "fill_expr": (2,), "scale": (2,), "scale_expr": (2,),
+                           "contract": (2, 4, 6), "put": (2, 5), "request": (2,)}.get(st[0])
+            if label_slots:
+                # an int VARIABLE used as a subscript (`CLRB1_a[kstart:kstart,a:a,i:i]`, kstart = kstate + roots): it labels a
+                # one-element dimension like a simple index, its value is read when the statement executes
+                var_labels = tuple(sorted({x for k in label_slots for x in st[k]
+                                           if x in self.scalars and (x not in self.index_kind or x in self.var_labels)}))
+                if var_labels:
+                    for x in var_labels:
+                        self.var_labels.add(x)
+                        self.index_kind[x] = "s"
+                        self.simple_range[x] = ("1", "1")
+                    st = ("with_vars", var_labels, st)
             if st[0] == "proc":
                 if in_proc is not None or opens or st[1] in self.procs:
                     raise SialSyntaxError(f"line {ln}: misplaced or duplicate proc {st[1]}")
@@ -219,14 +245,18 @@ class Program:
             self.predefined.add(tok[2])
             self.scalars.add(tok[2])
             return None
-        if kw == "contiguous":
-            m = re.match(r"contiguous\s+local\s+([A-Za-z_]\w*)\s*\[", line, re.I)
+        if kw == "contiguous":     # a dense local array addressed by ranges; the programs here address it block by block (`x:x`)
+            m = re.match(r"contiguous\s+local\s+" + _REF, line, re.I)
             if not m:
                 raise SialSyntaxError("bad contiguous declaration")
             self.contiguous.add(m.group(1).lower())
+            self.arrays[m.group(1).lower()] = ("local", _labels(m.group(2)))
             return None
-        if kw == "allocate" and len(tok) > 1 and tok[1] == "contiguous":
-            return None
+        if kw in ("allocate", "deallocate") and len(tok) > 1 and tok[1] == "contiguous":
+            m = re.match(r"\w+\s+contiguous\s+([A-Za-z_]\w*)\s*\[", line, re.I)
+            if not m:
+                raise SialSyntaxError("bad " + kw + " contiguous")
+            return (kw, m.group(1).lower(), ("*",))
         if kw == "index":
             m = re.match(r"index\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line, re.I)
             if not m:
@@ -323,8 +353,6 @@ class Program:
             return ("collective", m.group(1), m.group(2))
         # block statements
         m = re.match(_REF + r"\s*(\+=|-=|\*=|=)\s*(.+)$", line)
-        if m and ":" in m.group(2) and m.group(1).lower() in self.contiguous:
-            return None           # `FINAL_EOM_EE_Energy[kstate:kstate] = ...`: print bookkeeping
         if m:
             name, labs, op, rhs = m.group(1).lower(), _labels(m.group(2)), m.group(3), m.group(4).strip()
             mm = re.match(_REF + r"\s*[\*\^]\s*" + _REF + r"\s*$", rhs)   # `^` (outer product) is the same opcode
@@ -339,8 +367,6 @@ class Program:
                 return ("fill" if op == "=" else "scale", name, labs, float(rhs.lower().replace("d", "e")))
             if re.match(r"[A-Za-z_]\w*$", rhs) and op == "*=":
                 return ("scale_by", name, labs, rhs.lower())
-            if name in self.contiguous:
-                return None
             if op in ("=", "*=") and "[" not in rhs:      # `T4kai[davidson,a,i] = omega`, `Tkai[kstate,a,i] *= (0.5)**(0.5)`
                 return ("fill_expr" if op == "=" else "scale_expr", name, labs, parse_expr(rhs))
             if op in ("+=", "-=") and "[" not in rhs:     # `dipole[ixyz] -= dsum`: every element incremented by a number
@@ -431,6 +457,42 @@ def compute_diis(B):
     out = np.zeros(n)
     out[:ndim] = c[:ndim]
     return out
+
+
+def eigen_calc(A):
+    """The reference's `execute eigen_calc A V` (super_instructions/qm/utility/eigen_calc.F dsyev_wrapper): LAPACK DSYEV('V','L'),
+    each eigenvector's sign fixed so that its first component above 1e-5 in magnitude is positive, ascending eigenvalues; A comes
+    back as diag(eigenvalues), V holds the eigenvectors in its columns.  -> (A_out, V)"""
+    import numpy as np
+
+    A = np.array(A, dtype=float)
+    w, v = np.linalg.eigh(np.tril(A) + np.tril(A, -1).T, UPLO="L")
+    for j in range(v.shape[1]):
+        big = np.nonzero(np.abs(v[:, j]) > 1.0e-5)[0]
+        if big.size and v[big[0], j] < 0.0:
+            v[:, j] = -v[:, j]
+    order = np.argsort(w, kind="stable")
+    return np.diag(w[order]), v[:, order]
+
+
+def cis_unit_guess(hdiag, nsub):
+    """The reference's `execute cis_unit_guess C1_a SHDiag` (super_instructions/qm/excited/cis_unit_guess.F unitvecguess): unit
+    vectors on the `nsub` smallest elements of the Hamiltonian diagonal hdiag[a,i], smallest first; on ties the LAST element
+    in (i outer, a inner) order wins (`.le.`).  -> B[nsub, a, i]"""
+    import numpy as np
+
+    work = np.array(hdiag, dtype=float)
+    nv, no = work.shape
+    B = np.zeros((nsub, nv, no))
+    for k in range(nsub):
+        ee, sav = 1.0e8, None
+        for i in range(no):
+            for a in range(nv):
+                if work[a, i] <= ee:
+                    ee, sav = work[a, i], (a, i)
+        B[k, sav[0], sav[1]] = 1.0
+        work[sav] = 1.0e9
+    return B
 
 
 def gen_eigen_calc(A):
@@ -692,6 +754,15 @@ class Walker:
                 return False
         return True
 
+    def _x_with_vars(self, names, st):
+        for n in names:
+            self.idx[n] = int(self.be.value(self.scalars[n]))
+        try:
+            return getattr(self, "_x_" + st[0])(*st[1:])
+        finally:
+            for n in names:
+                self.idx.pop(n, None)
+
     def _x_where(self, a, op, b):
         va = self.idx[a] if a in self.idx else int(a) if a.isdigit() else self._eval(("var", a))
         vb = self.idx[b] if b in self.idx else int(b) if b.isdigit() else self._eval(("var", b))
@@ -752,11 +823,15 @@ class Walker:
             self.locals.setdefault(name, {})
             return
         if name in self.locals:
-            raise SialSyntaxError(f"allocate of {name}: already allocated")
+            if name not in self.p.contiguous:
+                raise SialSyntaxError(f"allocate of {name}: already allocated")
+            self._x_deallocate(name, labs)
         self.locals[name] = {}
 
     def _x_deallocate(self, name, labs):
         if name not in self.locals:
+            if name in self.p.contiguous:
+                return
             raise SialSyntaxError(f"deallocate of {name}: not allocated")
         if "*" not in labs:
             h = self.locals[name].pop(self._segs_of(labs), None)
@@ -796,6 +871,41 @@ class Walker:
         if scalar not in self.scalars:
             raise SialSyntaxError(f"undeclared scalar {scalar}")
         self.be.scale(self._write(name, labs), self.be.value(self.scalars[scalar]))
+
+    def _static_blocks(self, name):
+        """every block of a program-owned static array: [(per-dimension 0-based start, handle)], plus the dense extents"""
+        decl = self.p.arrays[name][1]
+        ranges, starts, dims = [], [], []
+        for d in decl:
+            vals = list(self._range(d))
+            ext = [self.segs[self._kind(d)][v - 1] for v in vals] if self._kind(d) != "s" else [1] * len(vals)
+            ranges.append(vals)
+            starts.append([sum(ext[:k]) for k in range(len(vals))])
+            dims.append(sum(ext))
+        saved = dict(self.idx)
+        out = []
+        for combo in itertools.product(*[range(len(r)) for r in ranges]):
+            for d, r, k in zip(decl, ranges, combo):
+                self.idx[d] = r[k]
+            out.append((tuple(st[k] for st, k in zip(starts, combo)), self._find(name, decl)))
+        self.idx = saved
+        return out, tuple(dims)
+
+    def _static_dense(self, name):
+        import numpy as np
+        blocks, dims = self._static_blocks(name)
+        full = np.zeros(dims, order="F")
+        for start, h in blocks:
+            a = self.be.host_array(h)
+            full[tuple(slice(s, s + e) for s, e in zip(start, a.shape))] = a
+        return full
+
+    def _static_scatter(self, name, full):
+        import numpy as np
+        blocks, _ = self._static_blocks(name)
+        for start, h in blocks:
+            shape = self.be.host_array(h).shape
+            self.be.set_from_host(h, np.asfortranarray(full[tuple(slice(s, s + e) for s, e in zip(start, shape))]))
 
     def _table_set(self, name, labs, v):
         self.tables.setdefault(name, {})[tuple(self.idx[x] for x in labs)] = float(v)
@@ -887,6 +997,21 @@ class Walker:
             c = compute_diis([[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)])
             for i in range(n):
                 t[(i + lo, i + lo)] = float(c[i])
+            return
+        if fname == "eigen_calc":                    # dsyev of the (symmetric) CIS subspace matrix: host LAPACK, as in the reference
+            G, V = bare
+            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
+            n = hi - lo + 1
+            t = self.tables.get(G, {})
+            a_out, vec = eigen_calc([[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)])
+            self.tables[G] = {(i + lo, j + lo): float(a_out[i][j]) for i in range(n) for j in range(n)}
+            self.tables[V] = {(i + lo, j + lo): float(vec[i][j]) for i in range(n) for j in range(n)}
+            return
+        if fname == "cis_unit_guess":                # unit starting vectors on the smallest Hamiltonian diagonal elements
+            B, H = bare
+            hd = self._static_dense(H)
+            nsub = len(list(self._range(self.p.arrays[B][1][0])))
+            self._static_scatter(B, cis_unit_guess(hd, nsub))
             return
         if fname == "gen_eigen_calc":                # dgeev of the Davidson subspace matrix: host LAPACK, as in the reference
             G, L, R, E = bare
@@ -1069,6 +1194,15 @@ class DeviceBackend:
     def block_value(self, b):
         """the single element of a one-element block, on the host (Davidson control logic: subspace matrix elements)"""
         return float(b.to_numpy().reshape(-1)[0])
+
+    def host_array(self, b):
+        return b.to_numpy()
+
+    def set_from_host(self, b, a):
+        import numpy as np
+        a = np.asfortranarray(a, dtype=np.float64)
+        self.api._check(self.api.lib().sipgpu_h2d(b.ptr, self.api._hp(a), b.size), "sipgpu_h2d")
+        self.api.sync()
 
     # persistence: the array object (with its HBM slab) moves to the library's label registry and back -- no copy
     def set_persistent(self, name, label):

@@ -253,6 +253,7 @@ def eom_simple_extents(program, constants):
 PROGRAM_RCCSD = open(os.path.join(HERE, "golden", "rccsd_rhf_program.sialx")).read()
 PROGRAM_RLCCD = open(os.path.join(HERE, "golden", "rlccd_rhf_program.sialx")).read()
 PROGRAM_RLCCSD = open(os.path.join(HERE, "golden", "rlccsd_rhf_program.sialx")).read()
+PROGRAM_RCIS = open(os.path.join(HERE, "golden", "rcis_rhf_program.sialx")).read()     # src/sialx/qm/eom/rcis_rhf.sialx
 PROGRAM_TRAN_NO4V = open(os.path.join(HERE, "golden", "tran_rhf_no4v_program.sialx")).read()    # src/sialx/qm/utility/tran_rhf_no4v.sialx
 
 

@@ -96,6 +96,12 @@ class OracleBackend:
     def has_array(self, name):
         return name in self.arrays
 
+    def host_array(self, b):
+        return b.a
+
+    def set_from_host(self, b, a):
+        b.a[...] = a
+
     def block_value(self, b):
         return float(np.asarray(b.a).reshape(-1)[0])
 

@@ -19,7 +19,7 @@ from aces4_b200.sial_frontend import Program, Walker, compute_diis
 from sial_oracle_backend import OracleBackend
 
 PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
-            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V}
+            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS}
 
 
 def run_cc_program(oracle, name, case, chained=False):
@@ -38,7 +38,9 @@ def run_cc_program(oracle, name, case, chained=False):
     be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
     w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.setup_constants(case))
     sc = w.run()
-    return {k: be.value(v) for k, v in sc.items()}, be.calls
+    out = {k: be.value(v) for k, v in sc.items()}
+    out["tables"] = w.tables
+    return out, be.calls
 
 
 def run_rccsd(oracle, case):
@@ -90,6 +92,27 @@ def test_config_1_from_ao_integrals_through_the_reference_texts(oracle, case):
     sc, _ = run_cc_program(oracle, "rlccd_rhf", case, chained=True)
     g_corr, g_e, _ = lw.golden(case)
     assert abs(sc["lccd_correlation"] - g_corr) < 2e-11 and abs(sc["lccd_energy"] - g_e) < 2e-11 and int(sc["niter"]) == 15
+
+
+def test_reference_cis_program_reproduces_the_cis_roots_of_eom_test(oracle):
+    """rcis_rhf.sialx VERBATIM (scripts/make_eom_golden.py: transition-dipole part left out): H-bar of CIS, `cis_unit_guess`,
+    the subspace-collapse Davidson with `eigen_calc` (host dsyev), `invert_diagonal`, `return_diagonal_elements`, contiguous
+    local arrays addressed block-wise through int variables -- against the two CIS roots the reference asserts for this molecule
+    (DISABLED_eom_test, test/test_qm.cpp:265-272, 1e-10).  measured: 4.3e-13, 2.7e-13; roots 3, 4 equal the dense
+    diagonalisation of oracle/qm_inputs.py::cis_singlets to 1e-11"""
+    case = "eom_dat"
+    inp = lw.inputs(case)
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    sc, calls = run_cc_program(oracle, "rcis_rhf", case, chained=True)
+    roots = [sc["tables"]["sek0"][(k,)] for k in range(1, 5)]
+    for got, want in zip(roots, lw.GOLDEN["eom_test"]["cis_sek0"]):
+        assert abs(got - want) < 1e-10, (got, want)
+    dense = {n: qm.join_blocks(inp["arrays"][n], [inp["segs"][k] for k in lw.KINDS[n]]) for n in ("vpiqj", "vaaii")}
+    e_dense, _ = lw.cis_guess(inp, dense)
+    assert max(abs(a - b) for a, b in zip(roots, e_dense)) < 1e-10
+    assert {"C1_a", "B1_a", "Vaaii", "Viaai", "ca", "fock_a"} <= set(OracleBackend.registry)
+    from aces4_b200.sial_frontend import Walker as W
+    assert abs(W.host_registry["CIS_E"][(1,)] - roots[0]) == 0.0
 
 
 def test_reference_lccd_and_lccsd_programs_all_electron(oracle):

@@ -59,6 +59,25 @@ def test_config_1_from_ao_integrals_on_the_device(sip):
 
 
 @pytest.mark.timeout(900, method="thread")
+def test_reference_cis_program_on_the_device(sip):
+    """tran_rhf_no4v.sialx -> rcis_rhf.sialx VERBATIM on libsipgpu: the CIS roots the reference asserts for this molecule
+    (DISABLED_eom_test, test/test_qm.cpp:265-272, 1e-10); `eigen_calc` / `cis_unit_guess` are the host routines they are in the
+    reference, everything else -- H-bar, H*B, B*HB matrix elements, residuals, Gram-Schmidt -- runs through the C ABI"""
+    case = "eom_dat"
+    inp = lw.inputs(case)
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
+    consts = lw.setup_constants(case)
+    dc.run_program_on_device(sip, lw.PROGRAM_TRAN_NO4V, case, inp, seg_ext, aoint, fock, True, consts, extra_arrays=dc.static_arrays(sip, seg_ext))
+    w, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_RCIS, case, inp, seg_ext, aoint, fock, True, consts,
+                                       extra_arrays=dc.static_arrays(sip, seg_ext))
+    roots = [w.tables["sek0"][(k,)] for k in range(1, 5)]
+    print(f"\nrcis_rhf.sialx verbatim on the device: CIS roots " + ", ".join(f"{r:.14f}" for r in roots) +
+          " (goldens " + ", ".join(f"{r:.14f}" for r in lw.GOLDEN["eom_test"]["cis_sek0"]) + ")")
+    for got, want in zip(roots, lw.GOLDEN["eom_test"]["cis_sek0"]):
+        assert abs(got - want) < 1e-10, (got, want)
+
+
+@pytest.mark.timeout(900, method="thread")
 def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
     sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
     g_corr, g_e = lw.golden_lccsd()
