@@ -706,7 +706,13 @@ class Walker:
 
     def _write(self, name, labs):
         if self._is_remote(name) and not self._own_static(name):
-            raise SialSyntaxError(f"{name} is served/distributed: use put/prepare")
+            # a block statement ON a distributed array (`Gmi_a[i1,i] = 0.0`, rlambda_rhf.sialx:1118): the interpreter writes the
+            # worker's cached copy of the block, which never reaches the owner and is dropped at the next barrier
+            # (sial_ops_parallel.cpp:41-47) -- here: a scratch block that dies with the loop iteration
+            key = ("%cache", name, self._array_segs(name, labs))
+            if key not in self.scopes[-1]:
+                self.scopes[-1][key] = self.be.new_block(self._shape(labs))
+            return self.scopes[-1][key]
         h = self._find(name, labs)
         if h is None:
             h = self.be.new_block(self._shape(labs))

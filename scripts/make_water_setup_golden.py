@@ -39,9 +39,12 @@ GOLDEN["ne_ccsdpt_test"] = {"eaab": -0.0010909774775509193, "esaab": 8.554784591
 GOLDEN["eom_ccsd_water_test"] = {"sek0": [0.32850657002707, 0.41193399006592, 0.42288344162832, 0.51159731180444],
                                  "tolerance": 1e-8, "oscnorm": [0.00680956, 0.0, 0.09037060, 0.11312310]}
 GOLDEN["eom_test"] = {"cis_sek0": [0.36275490375537, 0.43493738840536], "eom_sek0": [0.32850656893104, 0.41193399028059]}
+# hydrogen fluoride / 3-21G, the reference's enabled rlambda_test (test/test_qm.cpp:307-341: scf, tran, rccsd_rhf, rlambda_rhf;
+# scf_conv / cc_conv 1e-12): the lambda pseudo-energy at 1e-10
+GOLDEN["rlambda_test"] = {"lambda_pseudo": -0.12592115116563}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
-             "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat"):
+             "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat", "rlambda_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

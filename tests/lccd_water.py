@@ -253,6 +253,9 @@ def eom_simple_extents(program, constants):
 PROGRAM_RCCSD = open(os.path.join(HERE, "golden", "rccsd_rhf_program.sialx")).read()
 PROGRAM_RLCCD = open(os.path.join(HERE, "golden", "rlccd_rhf_program.sialx")).read()
 PROGRAM_RLCCSD = open(os.path.join(HERE, "golden", "rlccsd_rhf_program.sialx")).read()
+PROGRAM_RLAMBDA = open(os.path.join(HERE, "golden", "rlambda_rhf_program.sialx")).read()   # src/sialx/qm/cc/rlambda_rhf.sialx
+CASES["lam_dat"] = ("rlambda_test.dat", None)       # hydrogen fluoride / 3-21G, cc_conv 1e-12 (the reference's rlambda_test)
+CASES["lam_fine"] = ("rlambda_test.dat", {"moa": [2, 3, 2, 4], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 2]})
 PROGRAM_RCIS = open(os.path.join(HERE, "golden", "rcis_rhf_program.sialx")).read()     # src/sialx/qm/eom/rcis_rhf.sialx
 PROGRAM_TRAN_NO4V = open(os.path.join(HERE, "golden", "tran_rhf_no4v_program.sialx")).read()    # src/sialx/qm/utility/tran_rhf_no4v.sialx
 

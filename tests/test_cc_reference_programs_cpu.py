@@ -19,7 +19,7 @@ from aces4_b200.sial_frontend import Program, Walker, compute_diis
 from sial_oracle_backend import OracleBackend
 
 PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
-            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS}
+            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS, "rlambda_rhf": lw.PROGRAM_RLAMBDA}
 
 
 def run_cc_program(oracle, name, case, chained=False):
@@ -113,6 +113,21 @@ def test_reference_cis_program_reproduces_the_cis_roots_of_eom_test(oracle):
     assert {"C1_a", "B1_a", "Vaaii", "Viaai", "ca", "fock_a"} <= set(OracleBackend.registry)
     from aces4_b200.sial_frontend import Walker as W
     assert abs(W.host_registry["CIS_E"][(1,)] - roots[0]) == 0.0
+
+
+@pytest.mark.parametrize("case", ["lam_dat", "lam_fine"])
+def test_reference_lambda_program_reproduces_rlambda_test(oracle, case):
+    """The reference's ENABLED rlambda_test (test/test_qm.cpp:307-341; hydrogen fluoride / 3-21G): scf -> tran_rhf_no4v ->
+    rccsd_rhf -> rlambda_rhf, every program the reference's text (scripts/make_cc_program_goldens.py; lambda: the response-density
+    / dipole call left out): 26 intermediates (F1ae, F1mi, Gae, Gmi, W1minj, W2mebj, W1imen, W1eafm ...), the lambda ladder over
+    the AO integrals, DIIS, `lambda_pseudo` asserted at 1e-10.  measured: -0.12592115116562566 vs -0.12592115116563 (4e-15),
+    17 iterations"""
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    sc, _ = run_cc_program(oracle, "rccsd_rhf", case, chained=True)
+    assert abs(sc["ccsd_energy"] - lw.GOLDEN["hf"]["ccsd_energy"]) < 1e-10      # second_ccsdpt_test's CCSD energy: the same molecule
+    sc, calls = run_cc_program(oracle, "rlambda_rhf", case, chained=True)
+    assert abs(sc["lambda_pseudo"] - lw.GOLDEN["rlambda_test"]["lambda_pseudo"]) < 1e-12, sc["lambda_pseudo"]
+    assert {"l1a_old", "L2old_aa", "L2old_ab", "t1a_old", "T2old_ab"} <= set(OracleBackend.registry)
 
 
 def test_reference_lccd_and_lccsd_programs_all_electron(oracle):

@@ -78,6 +78,21 @@ def test_reference_cis_program_on_the_device(sip):
 
 
 @pytest.mark.timeout(900, method="thread")
+def test_reference_lambda_program_on_the_device(sip):
+    """the reference's enabled rlambda_test on libsipgpu: tran_rhf_no4v -> rccsd_rhf -> rlambda_rhf verbatim, lambda_pseudo at 1e-10"""
+    case = "lam_dat"
+    inp = lw.inputs(case)
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
+    consts = lw.setup_constants(case)
+    l0 = sip.kernel_launches()
+    for text in (lw.PROGRAM_TRAN_NO4V, lw.PROGRAM_RCCSD, lw.PROGRAM_RLAMBDA):
+        _, _, sc = dc.run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, True, consts, extra_arrays=dc.static_arrays(sip, seg_ext))
+    g = lw.GOLDEN["rlambda_test"]["lambda_pseudo"]
+    print(f"\ntran -> rccsd -> rlambda verbatim on the device: lambda_pseudo {sc['lambda_pseudo']:.14f} (golden {g:.14f}), {sip.kernel_launches() - l0} launches")
+    assert abs(sc["lambda_pseudo"] - g) < 1e-10
+
+
+@pytest.mark.timeout(900, method="thread")
 def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
     sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
     g_corr, g_e = lw.golden_lccsd()
