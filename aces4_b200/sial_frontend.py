@@ -829,7 +829,7 @@ class Walker:
             self.locals.setdefault(name, {})
             return
         if name in self.locals:
-            if name not in self.p.contiguous:
+            if self.locals[name] and name not in self.p.contiguous:     # (empty: only single blocks were allocated, all freed)
                 raise SialSyntaxError(f"allocate of {name}: already allocated")
             self._x_deallocate(name, labs)
         self.locals[name] = {}

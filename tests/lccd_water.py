@@ -202,6 +202,7 @@ def pt_array_kinds(program):
 # src/sialx/qm/eom/eom_ccsd_rhf_right.sialx + eom_rhf_hbar.sialx + eom_rhf_vars.sialx + eom_rhf_defs.sialx by
 # scripts/make_eom_golden.py) on water / 3-21G (test/eom_ccsd_water_test.dat)
 PROGRAM_EOM = open(os.path.join(HERE, "golden", "eom_ccsd_right_program.sialx")).read()
+PROGRAM_EOM_LEFT = open(os.path.join(HERE, "golden", "eom_ccsd_left_program.sialx")).read()
 EOM_SETUP = "eom_ccsd_water_test.dat"
 CASES["eom_dat"] = (EOM_SETUP, None)
 CASES["eom_fine"] = (EOM_SETUP, {"moa": [2, 3, 3, 5], "occ": (1, 2), "virt": (3, 4), "ao": [4, 7, 2]})
@@ -303,3 +304,11 @@ def device_program_arrays(sip, program, text, constants, segs, skip=()):
         out[name] = sip.DistArray([[1] * simple[d] if program.index_kind[d] == "s" else seg_ext[program.index_kind[d]] for d in decl])
         out[name].fill_local(0.0)
     return out
+
+
+def restored_labels(text):
+    """[(array name, label)] of the `restore_persistent` statements of a program text.  Served arrays persisted by an earlier
+    program live in the servers' files and outlive a restore (disk_backed_block_map.restore_persistent_array), so a later program
+    can restore a label again although the program in between did not `set_persistent` it: the harnesses hand the arrays a
+    program restored over again under the same labels before the next program runs."""
+    return [(n.lower(), lab) for n, lab in re.findall(r'(?im)^\s*restore_persistent\s+(\w+)\s+"(\w+)"', text)]

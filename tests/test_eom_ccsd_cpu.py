@@ -65,6 +65,7 @@ def run_eom(oracle, case, tight, cis_program=False):
     w2.run()
     roots = [w2.tables["sek0"][(k,)] for k in range(1, len(e_cis) + 1)]
     run_eom.state_converged = dict(w2.state_converged)
+    run_eom.backend = be2
     return roots, e_cis, e_ccsd, be2.calls, Walker.host_registry.get("reom_Ek")
 
 
@@ -91,6 +92,32 @@ def test_reference_eom_program_reproduces_the_four_roots_of_eom_ccsd_water_test(
         assert abs(roots[0] - lw.GOLDEN["eom_test"]["eom_sek0"][0]) < 1e-10      # cc_conv 1e-12 run of the reference
     assert persisted is not None and abs(persisted[(1,)] - roots[0]) == 0.0  # set_persistent SEk0 "reom_Ek"
     assert calls > 100000
+
+
+def test_reference_left_hand_program_finds_the_same_roots(oracle):
+    """eom_ccsd_water_test asserts `sek0` a second time after eom_ccsd_rhf_left.sialx (test/test_qm.cpp:1017-1024): the left-hand
+    program VERBATIM (tests/golden/eom_ccsd_left_program.sialx: L H-bar sigma vectors = left_factorize, l2ab_works, l2aa_works,
+    l1anew of eom_rhf_hbar.sialx; property part left out) started from the right-hand vectors the right-hand program persisted.
+    measured: left roots within 8e-12 of the right roots, 8.6e-10 / 4.9e-10 / 8.6e-10 / 5.8e-12 from the goldens"""
+    case = "eom_dat"
+    g = lw.GOLDEN["eom_ccsd_water_test"]
+    inp = lw.inputs(case)
+    right, _, _, _, _ = run_eom(oracle, case, False)
+    reg = OracleBackend.registry
+    for name, label in lw.restored_labels(lw.PROGRAM_EOM):          # the servers' files of persistent arrays outlive a restore
+        if label not in reg and name in run_eom.backend.arrays:
+            reg[label] = run_eom.backend.arrays[name]
+    prog = Program(lw.PROGRAM_EOM_LEFT)
+    arrays = {n: {} for n in lw.eom_array_kinds(prog)}
+    arrays.update(aoint=inp["arrays"]["aoint"], **lw.all_orbital_statics(case, inp))
+    be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+    w = Walker(prog, be, inp["segs"], index_base=inp["index_base"], constants=lw.eom_constants())
+    w.run()
+    left = [w.tables["sek0"][(k,)] for k in range(1, 5)]
+    for l, r, want in zip(left, right, g["sek0"]):
+        assert abs(l - want) < g["tolerance"] and abs(l - want) < 2e-9, (left, g["sek0"])
+        assert abs(l - r) < 1e-10, (left, right)
+    assert be.calls > 100000
 
 
 def test_reference_chain_with_the_cis_program_in_it(oracle):

@@ -66,9 +66,28 @@ def run_eom_on_device(sip, case, record):
     stat = dc.static_arrays(sip, seg_ext)
     for name, A in stat.items():
         A.restore(name)
-    w2, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
+    w2, be2, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
     roots = [w2.tables["sek0"][(k,)] for k in range(1, len(e_cis) + 1)]
+    run_eom_on_device.state = (inp, seg_ext, aoint, fock, consts, be2)
     return roots, e_cis, e_ccsd, niter, sip.kernel_launches() - l0
+
+
+def run_left_program_on_device(sip, case, record):
+    """after run_eom_on_device: the left-hand program on the arrays the right-hand one restored (handed over again under their
+    labels: the servers' files of persistent arrays outlive a restore) and the right-hand vectors it persisted"""
+    inp, seg_ext, aoint, fock, consts, be2 = run_eom_on_device.state
+    persisted_by_right = {lab for _, lab in __import__("re").findall(r'(?im)^\s*set_persistent\s+(\w+)\s+"(\w+)"', lw.PROGRAM_EOM)}
+    for name, label in lw.restored_labels(lw.PROGRAM_EOM):
+        if label not in persisted_by_right and name in be2.arrays:
+            be2.arrays[name].persist(label)
+    stat = dc.static_arrays(sip, seg_ext)          # ca / fock_a: not restored by the generated programs, handed in resident
+    stat_blocks = lw.all_orbital_statics(case, inp)
+    for name, A in stat.items():
+        A.fill_local(0.0)
+        dc.upload(sip, A, stat_blocks[name])
+    sip.sync()
+    w, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM_LEFT, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
+    return [w.tables["sek0"][(k,)] for k in range(1, 5)]
 
 
 @pytest.mark.timeout(1500, method="thread")
@@ -84,3 +103,8 @@ def test_reference_eom_program_on_the_device(sip, case, record):
         assert abs(got - want) < g["tolerance"], (roots, g["sek0"])
     assert max(abs(a - b) for a, b in zip(roots, g["sek0"])) < 2e-9
     assert launches > 0
+    if case == "eom_dat":        # ... and the left-hand program, whose roots the reference asserts as well (test_qm.cpp:1017-1024)
+        left = run_left_program_on_device(sip, case, record)
+        print("left-hand program on the device: roots " + ", ".join(f"{r:.14f}" for r in left))
+        for l, r, want in zip(left, roots, g["sek0"]):
+            assert abs(l - want) < g["tolerance"] and abs(l - r) < 1e-10, (left, roots)
