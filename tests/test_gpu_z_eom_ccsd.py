@@ -92,7 +92,7 @@ def run_left_program_on_device(sip, case, record):
 
 @pytest.mark.timeout(1500, method="thread")
 @pytest.mark.parametrize("case,record", [("eom_dat", True), ("eom_fine", False)])
-def test_reference_eom_program_on_the_device(sip, case, record):
+def test_reference_eom_program_on_the_device(sip, case, record, with_left=True):
     g = lw.GOLDEN["eom_ccsd_water_test"]
     roots, e_cis, e_ccsd, niter, launches = run_eom_on_device(sip, case, record)
     print(f"\nreference CCSD (DIIS, {niter} iterations: ccsd_energy {e_ccsd:.14f}, golden {lw.golden_ccsd()[1]:.14f}) + EOM-CCSD programs on "
@@ -103,7 +103,7 @@ def test_reference_eom_program_on_the_device(sip, case, record):
         assert abs(got - want) < g["tolerance"], (roots, g["sek0"])
     assert max(abs(a - b) for a, b in zip(roots, g["sek0"])) < 2e-9
     assert launches > 0
-    if case == "eom_dat":        # ... and the left-hand program, whose roots the reference asserts as well (test_qm.cpp:1017-1024)
+    if case == "eom_dat" and with_left:        # ... and the left-hand program, whose roots the reference asserts as well (test_qm.cpp:1017-1024)
         left = run_left_program_on_device(sip, case, record)
         print("left-hand program on the device: roots " + ", ".join(f"{r:.14f}" for r in left))
         for l, r, want in zip(left, roots, g["sek0"]):
