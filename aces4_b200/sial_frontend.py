@@ -533,12 +533,13 @@ class Walker:
     """Executes a Program against a backend: the per-block call stream of one worker."""
     host_registry = {}       # persistent host tables (label -> {index values: number}), shared by consecutive programs
 
-    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None):
+    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None, host_data=None):
         """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v.
         index_base: {'o': baocc - 1, 'v': bavirt - 1, ...}: what to add to a loop's segment number to get the absolute
         segment number of its index type -- the index values a super-instruction receives (the reference's loops run
         over baocc..eaocc / bavirt..eavirt directly, interpreter.cpp:1011-1208)."""
         self.p, self.be, self.rank, self.world = program, backend, rank, world
+        self.host_data = dict(host_data or {})     # tables an out-of-scope engine would compute (dipole integrals, ...)
         self.index_base = dict(index_base or {})
         self.segs = dict(segs)
         if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
@@ -994,6 +995,22 @@ class Walker:
             return
         if fname == "get_my_rank":
             self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), float(self.rank))
+            return
+        if fname == "compute_dipole_integrals":      # the dipole integral engine (OED package, out of scope): a resident table here
+            # `execute compute_dipole_integrals DAOINT[mu,nu] ncount1 ncount2`: block = <mu| r_c |nu>, c = (int)ncount2; ncount1 = the
+            # nuclear dipole component (compute_dipole_integrals.F: data_1(1) = dnuc).  Walker.host_data["dipole_integrals"] [3,nao,nao],
+            # ["nuclear_dipole"] [3] come with the job like the AO repulsion integrals do.
+            import numpy as np
+            (name, labs), (s1, s2) = args[0], bare
+            c = int(round(self.be.value(self.scalars[s2]))) - 1
+            D = self.host_data["dipole_integrals"][c]
+            sl = []
+            for lab in labs:
+                ext = self.segs[self._kind(lab)]
+                lo = sum(ext[: self.idx[lab] - 1])
+                sl.append(slice(lo, lo + ext[self.idx[lab] - 1]))
+            self.be.set_from_host(self._write(name, labs), np.asfortranarray(D[tuple(sl)]))
+            self.scalars[s1] = self.be.scalar_set(self.scalars.get(s1), float(self.host_data["nuclear_dipole"][c]))
             return
         if fname == "compute_diis":                  # the DIIS equations of the CC iterations: host LAPACK (dgesv), as in the reference
             B = bare[0]

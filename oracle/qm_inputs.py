@@ -238,6 +238,29 @@ def ao_integrals(basis):
     return S, T, V, eri
 
 
+def dipole_integrals(basis, origin=(0.0, 0.0, 0.0)):
+    """-> D[3, nao, nao]: <mu| r_d - origin_d |nu> over the contracted, normalised functions of ao_integrals (the reference's
+    `compute_dipole_integrals` super-instruction: OED package; used by the response / transition-moment parts of its programs).
+    McMurchie-Davidson: the 1-D moment factor is (E_1 + (P_d - C_d) E_0) sqrt(pi / p)."""
+    A, al, lmn, W = basis["center"], basis["alpha"], basis["lmn"], basis["W"]
+    n = len(al)
+    a, b = al[:, None] * np.ones((1, n)), np.ones((n, 1)) * al[None, :]
+    p = a + b
+    P = (a[..., None] * A[:, None, :] + b[..., None] * A[None, :, :]) / p[..., None]
+    lmax = int(lmn.max())
+    E1 = [_hermite_E(lmax, lmax, a, b, A[:, None, d] - A[None, :, d]) for d in range(3)]
+    Es = [_select(E1[d], lmn[:, d], lmn[:, d], 0, 1) for d in range(3)]
+    s1 = [Es[d][0] * np.sqrt(math.pi / p) for d in range(3)]
+    m1 = [(Es[d][1] + (P[..., d] - origin[d]) * Es[d][0]) * np.sqrt(math.pi / p) for d in range(3)]
+    S = W.T @ (s1[0] * s1[1] * s1[2]) @ W
+    dn = 1.0 / np.sqrt(np.diag(S))
+    out = []
+    for d in range(3):
+        f = [m1[k] if k == d else s1[k] for k in range(3)]
+        out.append((W.T @ (f[0] * f[1] * f[2]) @ W) * dn[:, None] * dn[None, :])
+    return np.array(out)
+
+
 def nuclear_repulsion(basis):
     Z, X = basis["charge"], basis["coords"]
     return sum(Z[i] * Z[j] / np.linalg.norm(X[i] - X[j]) for i, j in itertools.combinations(range(len(Z)), 2))

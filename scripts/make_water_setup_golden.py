@@ -41,7 +41,9 @@ GOLDEN["eom_ccsd_water_test"] = {"sek0": [0.32850657002707, 0.41193399006592, 0.
 GOLDEN["eom_test"] = {"cis_sek0": [0.36275490375537, 0.43493738840536], "eom_sek0": [0.32850656893104, 0.41193399028059]}
 # hydrogen fluoride / 3-21G, the reference's enabled rlambda_test (test/test_qm.cpp:307-341: scf, tran, rccsd_rhf, rlambda_rhf;
 # scf_conv / cc_conv 1e-12): the lambda pseudo-energy at 1e-10
-GOLDEN["rlambda_test"] = {"lambda_pseudo": -0.12592115116563}
+GOLDEN["rlambda_test"] = {"lambda_pseudo": -0.12592115116563,
+                          # :317, :337 the z components the test carries in its `expected` arrays (it asserts x and y only)
+                          "scf_dipole_z": 0.84792717246707, "ccsd_dipole_z": 0.80028992302928}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
              "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat", "rlambda_test.dat"):

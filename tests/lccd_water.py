@@ -312,3 +312,19 @@ def restored_labels(text):
     can restore a label again although the program in between did not `set_persistent` it: the harnesses hand the arrays a
     program restored over again under the same labels before the next program runs."""
     return [(n.lower(), lab) for n, lab in re.findall(r'(?im)^\s*restore_persistent\s+(\w+)\s+"(\w+)"', text)]
+
+
+@functools.lru_cache(maxsize=None)
+def dipole_data(setup_name):
+    """what the dipole integral engine (`compute_dipole_integrals`, OED package: out of scope) and the SCF program would supply:
+    {"dipole_integrals": <mu|r|nu> [3,nao,nao], "nuclear_dipole": [3]} for Walker(host_data=...) and the SCF dipole moment
+    (persistence label "scf_dipole"), from oracle/qm_inputs.py.  Pinned by the reference's SCF dipole of rlambda_test
+    (test/test_qm.cpp:317: 0.84792717246707)."""
+    setup, basis, _, _, _, _, _, C = scf(setup_name)
+    D = qm.dipole_integrals(basis)
+    Z, X = np.array(basis["charge"]), np.array(basis["coords"])
+    nuc = (Z[:, None] * X).sum(0)
+    nocc = setup["ints"]["naocc"]
+    P = 2.0 * C[:, :nocc] @ C[:, :nocc].T
+    scf_dipole = nuc - np.einsum("dmn,mn->d", D, P)
+    return {"dipole_integrals": D, "nuclear_dipole": nuc}, {(k + 1,): float(scf_dipole[k]) for k in range(3)}

@@ -16,6 +16,7 @@ import pytest
 import lccd_water as lw
 from oracle import qm_inputs as qm
 from aces4_b200.sial_frontend import Program, Walker, compute_diis
+from aces4_b200.sial_frontend import Walker as W
 from sial_oracle_backend import OracleBackend
 
 PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
@@ -36,7 +37,10 @@ def run_cc_program(oracle, name, case, chained=False):
             OracleBackend.registry.update({lab: inp["arrays"][lab.lower()] for lab in lw.PERSISTED})      # the transformation program's
         OracleBackend.registry.update(scf_energy=inp["e_scf"], **lw.all_orbital_statics(case, inp))
     be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
-    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.setup_constants(case))
+    host_data, scf_dipole = lw.dipole_data(lw.CASES[case][0])
+    Walker.host_registry.setdefault("scf_dipole", scf_dipole)
+    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.setup_constants(case),
+               host_data=host_data)
     sc = w.run()
     out = {k: be.value(v) for k, v in sc.items()}
     out["tables"] = w.tables
@@ -111,22 +115,30 @@ def test_reference_cis_program_reproduces_the_cis_roots_of_eom_test(oracle):
     e_dense, _ = lw.cis_guess(inp, dense)
     assert max(abs(a - b) for a, b in zip(roots, e_dense)) < 1e-10
     assert {"C1_a", "B1_a", "Vaaii", "Viaai", "ca", "fock_a"} <= set(OracleBackend.registry)
-    from aces4_b200.sial_frontend import Walker as W
     assert abs(W.host_registry["CIS_E"][(1,)] - roots[0]) == 0.0
 
 
 @pytest.mark.parametrize("case", ["lam_dat", "lam_fine"])
 def test_reference_lambda_program_reproduces_rlambda_test(oracle, case):
     """The reference's ENABLED rlambda_test (test/test_qm.cpp:307-341; hydrogen fluoride / 3-21G): scf -> tran_rhf_no4v ->
-    rccsd_rhf -> rlambda_rhf, every program the reference's text (scripts/make_cc_program_goldens.py; lambda: the response-density
-    / dipole call left out): 26 intermediates (F1ae, F1mi, Gae, Gmi, W1minj, W2mebj, W1imen, W1eafm ...), the lambda ladder over
+    rccsd_rhf -> rlambda_rhf, every program the reference's text (scripts/make_cc_program_goldens.py; `compute_dipole_integrals` served
+    from a resident table): 26 intermediates (F1ae, F1mi, Gae, Gmi, W1minj, W2mebj, W1imen, W1eafm ...), the lambda ladder over
     the AO integrals, DIIS, `lambda_pseudo` asserted at 1e-10.  measured: -0.12592115116562566 vs -0.12592115116563 (4e-15),
     17 iterations"""
     run_cc_program(oracle, "tran_rhf_no4v", case)
     sc, _ = run_cc_program(oracle, "rccsd_rhf", case, chained=True)
     assert abs(sc["ccsd_energy"] - lw.GOLDEN["hf"]["ccsd_energy"]) < 1e-10      # second_ccsdpt_test's CCSD energy: the same molecule
+    W.host_registry.clear()
     sc, calls = run_cc_program(oracle, "rlambda_rhf", case, chained=True)
-    assert abs(sc["lambda_pseudo"] - lw.GOLDEN["rlambda_test"]["lambda_pseudo"]) < 1e-12, sc["lambda_pseudo"]
+    g = lw.GOLDEN["rlambda_test"]
+    assert abs(sc["lambda_pseudo"] - g["lambda_pseudo"]) < 1e-12, sc["lambda_pseudo"]
+    # form_G1: the CCSD response density (DABA, DIJA, DIAA, DAIA: block contractions of lambda and T amplitudes), back-transformed
+    # and traced with the dipole integrals.  The reference asserts x = y = 0 at 1e-6 and carries z in its `expected` array
+    dip = sc["tables"]["dipole"]
+    assert abs(dip[(1,)]) < 1e-10 and abs(dip[(2,)]) < 1e-10
+    assert abs(dip[(3,)] - g["ccsd_dipole_z"]) < 1e-10, dip           # measured: 8e-15
+    assert abs(lw.dipole_data("rlambda_test.dat")[1][(3,)] - g["scf_dipole_z"]) < 1e-9
+    assert abs(W.host_registry["ccsd_dipole"][(3,)] - dip[(3,)]) == 0.0
     assert {"l1a_old", "L2old_aa", "L2old_ab", "t1a_old", "T2old_ab"} <= set(OracleBackend.registry)
 
 
