@@ -47,7 +47,7 @@ def static_arrays(sip, seg_ext):
     return {"ca": sip.DistArray([seg_ext["ao"], seg_ext["pa"]]), "fock_a": sip.DistArray([seg_ext["pa"], seg_ext["pa"]])}
 
 
-def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, constants, extra_arrays=None):
+def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, constants, extra_arrays=None, host_data=None):
     """-> (walker, backend, scalars as floats)"""
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
@@ -57,6 +57,6 @@ def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, co
     arr.update(extra_arrays or {})
     be = DeviceBackend(sip, arr, record=record)
     be.fock, be.seg_ranges = fock, inp["moa_seg_ranges"]
-    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=constants)
+    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=constants, host_data=host_data)
     sc = w.run()
     return w, be, {k: be.value(v) for k, v in sc.items()}

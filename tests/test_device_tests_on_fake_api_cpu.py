@@ -54,7 +54,7 @@ def test_reference_triples_programs_device_test_body_on_the_fake_api(oracle):
 
 def test_reference_eom_program_device_test_body_on_the_fake_api(oracle):
     import test_gpu_z_eom_ccsd as eom
-    eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True, with_left=False)   # (the left-hand program: CPU twin in test_eom_ccsd_cpu.py)
+    eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True)
 
 
 def test_reference_cc_programs_device_test_bodies_on_the_fake_api(oracle):

@@ -97,29 +97,56 @@ def test_reference_eom_program_reproduces_the_four_roots_of_eom_ccsd_water_test(
     assert calls > 100000
 
 
-def test_reference_left_hand_program_finds_the_same_roots(oracle):
-    """eom_ccsd_water_test asserts `sek0` a second time after eom_ccsd_rhf_left.sialx (test/test_qm.cpp:1017-1024): the left-hand
-    program VERBATIM (tests/golden/eom_ccsd_left_program.sialx: L H-bar sigma vectors = left_factorize, l2ab_works, l2aa_works,
-    l1anew of eom_rhf_hbar.sialx; property part left out) started from the right-hand vectors the right-hand program persisted.
-    measured: left roots within 8e-12 of the right roots, 8.6e-10 / 4.9e-10 / 8.6e-10 / 5.8e-12 from the goldens"""
+def test_eom_ccsd_water_test_in_full(oracle):
+    """Every assertion of the reference's eom_ccsd_water_test (test/test_qm.cpp:965-1031) through its own program texts:
+    tran_rhf_no4v -> rccsd_rhf (ccsd_energy of the cc_conv = 1e-10 run) -> rlambda_rhf -> eom_ccsd_rhf_right (roots `sek0`) ->
+    eom_ccsd_rhf_left VERBATIM, whole file (tests/golden/eom_ccsd_left_program.sialx: L H-bar sigma vectors started from the
+    right-hand vectors; biorthogonalisation, r0, the one-particle transition densities of COMPUTE_DENSITY -- 1 400 lines of block
+    contractions of R, L, T and Lambda amplitudes --, back-transformation, trace with the dipole integrals): the roots a second
+    time (:1017-1024, 1e-8) and the oscillator norms `oscnorm` (:1025-1030, 1e-4).
+    measured: oscnorm 0.00680962, 6e-14, 0.09037069, 0.11312273 vs 0.00680956, 0, 0.0903706, 0.1131231 (6e-8, 6e-14, 9e-8, 4e-7);
+    left roots within 5e-9 of the right ones."""
     case = "eom_dat"
     g = lw.GOLDEN["eom_ccsd_water_test"]
     inp = lw.inputs(case)
-    right, _, _, _, _ = run_eom(oracle, case, False)
     reg = OracleBackend.registry
+    from test_cc_reference_programs_cpu import run_cc_program
+    Walker.host_registry.clear()
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    e_ccsd = run_cc_program(oracle, "rccsd_rhf", case, chained=True)[0]["ccsd_energy"]
+    assert abs(e_ccsd - lw.golden_ccsd()[1]) < 1e-12
+    run_cc_program(oracle, "rlambda_rhf", case, chained=True)
+    assert {"l1a_old", "L2old_aa", "L2old_ab"} <= set(reg)
+    dense = {n: qm.join_blocks(reg[lab], [inp["segs"][k] for k in lw.KINDS[n]]) for n, lab in (("vpiqj", "Vpiqj"), ("vaaii", "Vaaii"))}
+    _, reg["C1_a"] = lw.cis_guess(inp, dense)
+    host_data, scf_dipole = lw.dipole_data(lw.EOM_SETUP)
+
+    def run(text, arrays_in):
+        prog = Program(text)
+        arrays = {n: {} for n in lw.eom_array_kinds(prog)}
+        arrays.update(aoint=inp["arrays"]["aoint"], **arrays_in)
+        be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
+        w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=lw.eom_constants(), host_data=host_data)
+        w.run()
+        return w, be
+
+    statics = {"ca": reg["ca"], "fock_a": reg["fock_a"]}
+    w, be = run(lw.PROGRAM_EOM, statics)                 # (the generated right-hand program takes ca / fock_a from the harness)
+    right = [w.tables["sek0"][(k,)] for k in range(1, 5)]
     for name, label in lw.restored_labels(lw.PROGRAM_EOM):          # the servers' files of persistent arrays outlive a restore
-        if label not in reg and name in run_eom.backend.arrays:
-            reg[label] = run_eom.backend.arrays[name]
-    prog = Program(lw.PROGRAM_EOM_LEFT)
-    arrays = {n: {} for n in lw.eom_array_kinds(prog)}
-    arrays.update(aoint=inp["arrays"]["aoint"], **lw.all_orbital_statics(case, inp))
-    be = OracleBackend(oracle, arrays, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
-    w = Walker(prog, be, inp["segs"], index_base=inp["index_base"], constants=lw.eom_constants())
-    w.run()
+        if label not in reg and name in be.arrays:
+            reg[label] = be.arrays[name]
+    reg.update(statics)
+    Walker.host_registry["scf_dipole"] = scf_dipole
+    Walker.host_registry["nuclear_dipole"] = {(k + 1,): float(host_data["nuclear_dipole"][k]) for k in range(3)}
+    w, be = run(lw.PROGRAM_EOM_LEFT, {})
     left = [w.tables["sek0"][(k,)] for k in range(1, 5)]
-    for l, r, want in zip(left, right, g["sek0"]):
-        assert abs(l - want) < g["tolerance"] and abs(l - want) < 2e-9, (left, g["sek0"])
-        assert abs(l - r) < 1e-10, (left, right)
+    osc = [w.tables["oscnorm"][(k,)] for k in range(1, 5)]
+    for r, l, want in zip(right, left, g["sek0"]):
+        assert abs(r - want) < g["tolerance"] and abs(l - want) < g["tolerance"], (right, left, g["sek0"])
+    for got, want in zip(osc, g["oscnorm"]):
+        assert abs(got - want) < 1e-4, (osc, g["oscnorm"])           # the reference's tolerance
+        assert abs(got - want) < 2e-6, (osc, g["oscnorm"])           # measured: <= 4e-7
     assert be.calls > 100000
 
 

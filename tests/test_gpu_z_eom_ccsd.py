@@ -28,28 +28,27 @@ def sip():
 
 
 def run_eom_on_device(sip, case, record):
-    """the reference's chain on libsipgpu: rccsd_rhf.sialx verbatim (DIIS, stopped at the setup's cc_conv) -> persistent arrays
-    (the library's label registry: the slabs never leave HBM) -> the EOM program"""
+    """the reference's job on libsipgpu, program by program: tran_rhf_no4v -> rccsd_rhf (DIIS, stopped at the setup's cc_conv) ->
+    rlambda_rhf -> eom_ccsd_rhf_right, chained through persistent arrays (the library's label registry: the slabs never leave HBM)"""
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
     inp = lw.inputs(case)
     consts = lw.eom_constants()
-    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp)
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
     l0 = sip.kernel_launches()
-    # ---- CCSD: the reference's program, verbatim ----
-    _, _, sc = dc.run_program_on_device(sip, lw.PROGRAM_RCCSD, case, inp, seg_ext, aoint, fock, record, consts,
-                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    host_data, scf_dipole = lw.dipole_data(lw.EOM_SETUP)
+    Walker.host_registry.clear()
+    Walker.host_registry["scf_dipole"] = scf_dipole
+    # ---- the reference's job, program by program, verbatim: transformation, CCSD (DIIS), lambda ----
+    sc = None
+    for text in (lw.PROGRAM_TRAN_NO4V, lw.PROGRAM_RCCSD, lw.PROGRAM_RLAMBDA):
+        _, _, out = dc.run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, consts,
+                                             extra_arrays=dc.static_arrays(sip, seg_ext), host_data=host_data)
+        sc = out if text is lw.PROGRAM_RCCSD else sc
     e_ccsd, niter = sc["ccsd_energy"], int(sc["niter"])
-
-    # ---- what rlambda / rcis leave behind: VSaaai and the CIS vectors ----
-    frag = {"vaaai": sip.DistArray([seg_ext[k] for k in lw.KINDS["vaaai"]]), "vsaaai": sip.DistArray([seg_ext[k] for k in lw.KINDS["vsaaai"]])}
-    frag["vaaai"].restore("Vaaai")
-    frag["vsaaai"].fill_local(0.0)
-    bf = DeviceBackend(sip, frag, record=record)
-    Walker(Program(lw.VSAAAI_FRAGMENT), bf, inp["segs"], index_base=inp["index_base"]).run()
     sip.sync()
-    frag["vaaai"].persist("Vaaai")
-    frag["vsaaai"].persist("VSaaai")
+
+    # ---- what rcis leaves behind: the CIS vectors (dense diagonalisation, see tests/test_eom_ccsd_cpu.py) ----
     dense = {}
     for n, lab in (("vpiqj", "Vpiqj"), ("vaaii", "Vaaii")):
         A = sip.DistArray([seg_ext[k] for k in lw.KINDS[n]])
@@ -73,21 +72,24 @@ def run_eom_on_device(sip, case, record):
 
 
 def run_left_program_on_device(sip, case, record):
-    """after run_eom_on_device: the left-hand program on the arrays the right-hand one restored (handed over again under their
-    labels: the servers' files of persistent arrays outlive a restore) and the right-hand vectors it persisted"""
+    """after run_eom_on_device: eom_ccsd_rhf_left.sialx VERBATIM (whole file, property part included) on the arrays the right-hand
+    program restored (handed over again under their labels: the servers' files of persistent arrays outlive a restore), the
+    right-hand vectors it persisted and the lambda amplitudes.  -> (roots, oscillator norms)"""
+    from aces4_b200.sial_frontend import Walker
+
     inp, seg_ext, aoint, fock, consts, be2 = run_eom_on_device.state
     persisted_by_right = {lab for _, lab in __import__("re").findall(r'(?im)^\s*set_persistent\s+(\w+)\s+"(\w+)"', lw.PROGRAM_EOM)}
     for name, label in lw.restored_labels(lw.PROGRAM_EOM):
         if label not in persisted_by_right and name in be2.arrays:
             be2.arrays[name].persist(label)
-    stat = dc.static_arrays(sip, seg_ext)          # ca / fock_a: not restored by the generated programs, handed in resident
-    stat_blocks = lw.all_orbital_statics(case, inp)
-    for name, A in stat.items():
-        A.fill_local(0.0)
-        dc.upload(sip, A, stat_blocks[name])
-    sip.sync()
-    w, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM_LEFT, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
-    return [w.tables["sek0"][(k,)] for k in range(1, 5)]
+    for name in ("ca", "fock_a"):               # the generated right-hand program took them from the harness: hand them back
+        be2.arrays[name].persist(name)
+    host_data, scf_dipole = lw.dipole_data(lw.EOM_SETUP)
+    Walker.host_registry["scf_dipole"] = scf_dipole
+    Walker.host_registry["nuclear_dipole"] = {(k + 1,): float(host_data["nuclear_dipole"][k]) for k in range(3)}
+    w, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM_LEFT, case, inp, seg_ext, aoint, fock, record, consts,
+                                       extra_arrays=dc.static_arrays(sip, seg_ext), host_data=host_data)
+    return [w.tables["sek0"][(k,)] for k in range(1, 5)], [w.tables["oscnorm"][(k,)] for k in range(1, 5)]
 
 
 @pytest.mark.timeout(1500, method="thread")
@@ -103,8 +105,11 @@ def test_reference_eom_program_on_the_device(sip, case, record, with_left=True):
         assert abs(got - want) < g["tolerance"], (roots, g["sek0"])
     assert max(abs(a - b) for a, b in zip(roots, g["sek0"])) < 2e-9
     assert launches > 0
-    if case == "eom_dat" and with_left:        # ... and the left-hand program, whose roots the reference asserts as well (test_qm.cpp:1017-1024)
-        left = run_left_program_on_device(sip, case, record)
-        print("left-hand program on the device: roots " + ", ".join(f"{r:.14f}" for r in left))
-        for l, r, want in zip(left, roots, g["sek0"]):
-            assert abs(l - want) < g["tolerance"] and abs(l - r) < 1e-10, (left, roots)
+    if case == "eom_dat" and with_left:        # ... and the left-hand program: roots again (test_qm.cpp:1017-1024) + oscillator norms (:1025-1030)
+        left, osc = run_left_program_on_device(sip, case, record)
+        print("left-hand program on the device: roots " + ", ".join(f"{r:.14f}" for r in left) + "; oscillator norms " +
+              ", ".join(f"{x:.8f}" for x in osc) + " (goldens " + ", ".join(f"{x:.8f}" for x in g["oscnorm"]) + ")")
+        for l, want in zip(left, g["sek0"]):
+            assert abs(l - want) < g["tolerance"], (left, g["sek0"])
+        for got, want in zip(osc, g["oscnorm"]):
+            assert abs(got - want) < 1e-4 and abs(got - want) < 2e-6, (osc, g["oscnorm"])
