@@ -779,20 +779,27 @@ class Walker:
         wheres = [s for s in body if s[0] == "where"]
         rest = [s for s in body if s[0] != "where"]
         self.be.begin_pardo()
-        ranges = [self._range(lab) for lab in reversed(labs)]   # first index fastest
-        for combo in itertools.product(*ranges):
-            for lab, v in zip(reversed(labs), combo):
-                self.idx[lab] = v
-            if not all(self._x_where(*w[1:]) for w in wheres):
-                continue
-            self.iteration += 1
-            if (self.iteration - 1) % self.world != self.rank:
-                continue
-            self.scopes.append({})
-            self._block(rest)
-            self._leave_scope()
-        for lab in labs:
-            del self.idx[lab]
+        try:
+            ranges = [self._range(lab) for lab in reversed(labs)]   # first index fastest
+            for combo in itertools.product(*ranges):
+                for lab, v in zip(reversed(labs), combo):
+                    self.idx[lab] = v
+                if not all(self._x_where(*w[1:]) for w in wheres):
+                    continue
+                self.iteration += 1
+                if (self.iteration - 1) % self.world != self.rank:
+                    continue
+                self.scopes.append({})
+                self._block(rest)
+                self._leave_scope()
+            for lab in labs:
+                del self.idx[lab]
+        except BaseException:
+            try:
+                self.be.end_pardo()      # do not leave a recording open behind a failing program
+            except Exception:
+                pass
+            raise
         self.be.end_pardo()
 
     def _x_do(self, labs, body):

@@ -44,6 +44,10 @@ GOLDEN["eom_test"] = {"cis_sek0": [0.36275490375537, 0.43493738840536], "eom_sek
 GOLDEN["rlambda_test"] = {"lambda_pseudo": -0.12592115116563,
                           # :317, :337 the z components the test carries in its `expected` arrays (it asserts x and y only)
                           "scf_dipole_z": 0.84792717246707, "ccsd_dipole_z": 0.80028992302928}
+# hydrogen fluoride / 3-21G, frozen core: the reference's enabled lamccsdpt_test (test/test_qm.cpp:798-869: scf, tran, rccsd_rhf,
+# rlambda_rhf, rlamccsdpt_aaa, rlamccsdpt_aab; cc_conv 1e-12), Lambda-CCSD(T): every number asserted at 1e-10
+GOLDEN["lamccsdpt_test"] = {"ccsd_energy": -99.583972376431, "eaaa": -0.00001109673867, "esaaa": 0.00000190144932,
+                            "eaab": -0.00057100058054, "esaab": 0.00002785417018, "ccsdpt_energy": -99.584524718131}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
              "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat", "rlambda_test.dat"):

@@ -47,7 +47,17 @@ def static_arrays(sip, seg_ext):
     return {"ca": sip.DistArray([seg_ext["ao"], seg_ext["pa"]]), "fock_a": sip.DistArray([seg_ext["pa"], seg_ext["pa"]])}
 
 
-def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, constants, extra_arrays=None, host_data=None):
+class TracingWalker:
+    """mixin: records, per excited state, whether the EOM program's own Davidson solver reported convergence (`converged = 1`)"""
+
+    def _x_call(self, name):
+        out = super()._x_call(name)
+        if name == "collapse_davidson":
+            self.__dict__.setdefault("state_converged", {})[self.idx["kstate"]] = self.be.value(self.scalars["converged"]) == 1.0
+        return out
+
+
+def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, constants, extra_arrays=None, host_data=None, trace=False):
     """-> (walker, backend, scalars as floats)"""
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
@@ -57,6 +67,10 @@ def run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, record, co
     arr.update(extra_arrays or {})
     be = DeviceBackend(sip, arr, record=record)
     be.fock, be.seg_ranges = fock, inp["moa_seg_ranges"]
-    w = Walker(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=constants, host_data=host_data)
+    if host_data is None:      # what the dipole integral engine and the SCF program would supply (lambda / EOM property parts)
+        host_data, scf_dipole = lw.dipole_data(lw.CASES[case][0])
+        Walker.host_registry.setdefault("scf_dipole", scf_dipole)
+    cls = type("TracedWalker", (TracingWalker, Walker), {}) if trace else Walker
+    w = cls(prog, be, lw.segs_with_all_orbitals(inp), index_base=inp["index_base"], constants=constants, host_data=host_data)
     sc = w.run()
     return w, be, {k: be.value(v) for k, v in sc.items()}

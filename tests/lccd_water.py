@@ -255,8 +255,11 @@ PROGRAM_RCCSD = open(os.path.join(HERE, "golden", "rccsd_rhf_program.sialx")).re
 PROGRAM_RLCCD = open(os.path.join(HERE, "golden", "rlccd_rhf_program.sialx")).read()
 PROGRAM_RLCCSD = open(os.path.join(HERE, "golden", "rlccsd_rhf_program.sialx")).read()
 PROGRAM_RLAMBDA = open(os.path.join(HERE, "golden", "rlambda_rhf_program.sialx")).read()   # src/sialx/qm/cc/rlambda_rhf.sialx
+CASES["hf_fc_virt_fine"] = ("lamccsdpt_test.dat", {"moa": [1, 4, 2, 4], "occ": (2, 2), "virt": (3, 4), "ao": [3, 6, 2]})
 CASES["lam_dat"] = ("rlambda_test.dat", None)       # hydrogen fluoride / 3-21G, cc_conv 1e-12 (the reference's rlambda_test)
 CASES["lam_fine"] = ("rlambda_test.dat", {"moa": [2, 3, 2, 4], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 2]})
+PROGRAM_RLAMPT_AAA = open(os.path.join(HERE, "golden", "rlamccsdpt_aaa_program.sialx")).read()   # src/sialx/qm/cc/rlamccsdpt_aaa.sialx
+PROGRAM_RLAMPT_AAB = open(os.path.join(HERE, "golden", "rlamccsdpt_aab_program.sialx")).read()   # src/sialx/qm/cc/rlamccsdpt_aab.sialx
 PROGRAM_RCIS = open(os.path.join(HERE, "golden", "rcis_rhf_program.sialx")).read()     # src/sialx/qm/eom/rcis_rhf.sialx
 PROGRAM_TRAN_NO4V = open(os.path.join(HERE, "golden", "tran_rhf_no4v_program.sialx")).read()    # src/sialx/qm/utility/tran_rhf_no4v.sialx
 
@@ -264,7 +267,11 @@ PROGRAM_TRAN_NO4V = open(os.path.join(HERE, "golden", "tran_rhf_no4v_program.sia
 def setup_constants(case):
     """the predefined ints / scalars of the case's setup file (cc_conv, cc_iter, scf_hist, baocc ...)"""
     setup = FIXTURE["setups"][CASES[case][0]]
-    return {**setup["ints"], **setup["scalars"]}
+    out = {**setup["ints"], **setup["scalars"]}
+    sg = CASES[case][1]
+    if sg is not None:          # a finer segmentation of the same orbitals: the segment ranges of the active spaces move with it
+        out.update(baocc=sg["occ"][0], eaocc=sg["occ"][1], bavirt=sg["virt"][0], eavirt=sg["virt"][1], norb=len(sg["ao"]))
+    return out
 
 
 def all_orbital_statics(case, inp):

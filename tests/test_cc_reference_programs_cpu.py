@@ -20,7 +20,8 @@ from aces4_b200.sial_frontend import Walker as W
 from sial_oracle_backend import OracleBackend
 
 PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
-            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS, "rlambda_rhf": lw.PROGRAM_RLAMBDA}
+            "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS, "rlambda_rhf": lw.PROGRAM_RLAMBDA,
+            "rlamccsdpt_aaa": lw.PROGRAM_RLAMPT_AAA, "rlamccsdpt_aab": lw.PROGRAM_RLAMPT_AAB}
 
 
 def run_cc_program(oracle, name, case, chained=False):
@@ -140,6 +141,31 @@ def test_reference_lambda_program_reproduces_rlambda_test(oracle, case):
     assert abs(lw.dipole_data("rlambda_test.dat")[1][(3,)] - g["scf_dipole_z"]) < 1e-9
     assert abs(W.host_registry["ccsd_dipole"][(3,)] - dip[(3,)]) == 0.0
     assert {"l1a_old", "L2old_aa", "L2old_ab", "t1a_old", "T2old_ab"} <= set(OracleBackend.registry)
+
+
+@pytest.mark.parametrize("case", ["hf_fc_dat", "hf_fc_virt_fine"])
+def test_reference_lambda_ccsdpt_programs_reproduce_lamccsdpt_test(oracle, case):
+    """The reference's ENABLED lamccsdpt_test (test/test_qm.cpp:798-869; hydrogen fluoride / 3-21G, frozen core): scf ->
+    tran_rhf_no4v -> rccsd_rhf -> rlambda_rhf -> rlamccsdpt_aaa -> rlamccsdpt_aab, every program the reference's text with the one
+    edit of scripts/make_cc_program_goldens.py (their own TRAN_UHF transformation procedures included): Lambda-CCSD(T) -- the
+    stripi / one-segment-contraction / rank-6 accumulate inner loops of the (T) programs with lambda amplitudes on the left.
+    Every number the test asserts (1e-10).  measured: ccsd_energy 7e-13, eaaa 5e-16, esaaa 1e-15, eaab 2e-15, esaab 1e-16,
+    ccsdpt_energy 1e-12.  hf_fc_virt_fine: the virtual space cut into 2 + 4 (AO 3 + 6 + 2), the occupied space in ONE segment like in
+    every setup the reference ships -- with two active occupied segments the AAA programs' batch logic (set_ijk_aaa pieces across
+    segment boundaries) gives eaaa 1e-7 off, as observed for rccsdpt_aaa in tests/test_ccsdpt_reference_programs_cpu.py; whether
+    that is the reference program's or this front-end's is open, the reference never runs such a segmentation."""
+    g = lw.GOLDEN["lamccsdpt_test"]
+    W.host_registry.clear()
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    sc, _ = run_cc_program(oracle, "rccsd_rhf", case, chained=True)
+    assert abs(sc["ccsd_energy"] - g["ccsd_energy"]) < 1e-10
+    run_cc_program(oracle, "rlambda_rhf", case, chained=True)
+    got, _ = run_cc_program(oracle, "rlamccsdpt_aaa", case, chained=True)
+    sc, calls = run_cc_program(oracle, "rlamccsdpt_aab", case, chained=True)
+    got = {"eaaa": got["eaaa"], "esaaa": got["esaaa"], "eaab": sc["eaab"], "esaab": sc["esaab"], "ccsdpt_energy": sc["ccsdpt_energy"]}
+    for k, v in got.items():
+        assert abs(v - g[k]) < 1e-10, (k, v, g[k])
+        assert abs(v - g[k]) < (1e-11 if k == "ccsdpt_energy" else 1e-13), (k, v, g[k])
 
 
 def test_reference_lccd_and_lccsd_programs_all_electron(oracle):

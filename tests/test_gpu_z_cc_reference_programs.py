@@ -93,6 +93,25 @@ def test_reference_lambda_program_on_the_device(sip):
 
 
 @pytest.mark.timeout(900, method="thread")
+def test_reference_lambda_ccsdpt_programs_on_the_device(sip):
+    """the reference's enabled lamccsdpt_test on libsipgpu (hydrogen fluoride / 3-21G, frozen core): tran_rhf_no4v -> rccsd_rhf ->
+    rlambda_rhf -> rlamccsdpt_aaa -> rlamccsdpt_aab verbatim; every number the test asserts, at its 1e-10"""
+    case = "hf_fc_dat"
+    inp = lw.inputs(case)
+    g = lw.GOLDEN["lamccsdpt_test"]
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
+    consts = lw.setup_constants(case)
+    l0 = sip.kernel_launches()
+    got = {}
+    for text in (lw.PROGRAM_TRAN_NO4V, lw.PROGRAM_RCCSD, lw.PROGRAM_RLAMBDA, lw.PROGRAM_RLAMPT_AAA, lw.PROGRAM_RLAMPT_AAB):
+        _, _, sc = dc.run_program_on_device(sip, text, case, inp, seg_ext, aoint, fock, True, consts, extra_arrays=dc.static_arrays(sip, seg_ext))
+        got.update({k: sc[k] for k in g if k in sc and sc[k] != 0.0})
+    print("\nlamccsdpt_test on the device: " + ", ".join(f"{k} {got[k]:.14e} (golden {g[k]:.10e})" for k in g) + f", {sip.kernel_launches() - l0} launches")
+    for k in g:
+        assert abs(got[k] - g[k]) < 1e-10, (k, got[k], g[k])
+
+
+@pytest.mark.timeout(900, method="thread")
 def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
     sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
     g_corr, g_e = lw.golden_lccsd()
