@@ -684,6 +684,11 @@ def si_energy_denominator_rhf(block, index_values, fock):
     return _si_call(lib().sipgpu_si_energy_denominator_rhf, "energy_denominator_rhf", (block, index_values), (fock, None))
 
 
+def si_energy_ty_denominator_rhf(block, index_values, fock, shift_block):
+    return _si_call(lib().sipgpu_si_energy_ty_denominator_rhf, "energy_ty_denominator_rhf", (block, index_values), (fock, None),
+                    (shift_block, None))
+
+
 def si_stripi(x, iv0, y, iv1):
     return _si_call(lib().sipgpu_si_stripi, "stripi", (x, iv0), (y, iv1))
 

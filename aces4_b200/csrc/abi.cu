@@ -998,6 +998,22 @@ int sipgpu_si_energy_denominator_rhf(int*, int* rank_0, int* index_values_0, int
     }
     SI_RETURN(si_energy_denominator_rhf(*rank_0, index_values_0, extents_0, data_0, *rank_1, extents_1, data_1));
 }
+int sipgpu_si_energy_ty_denominator_rhf(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
+                                        int*, int*, int* extents_1, double* data_1, int*, int*, int*, int*, int*, double* data_2, int* ierr) {
+    SIP_TRACE("sipgpu_si_energy_ty_denominator_rhf");
+    if (!rank_0 || !rank_1 || !data_2) SI_RETURN(SIPGPU_E_ARG);
+    if (wl_active()) {
+        const int r0 = *rank_0, r1 = *rank_1;
+        if (r0 != 4 || r1 != 2 || !index_values_0 || !extents_0 || !extents_1 || !data_0 || !data_1) SI_RETURN(SIPGPU_E_ARG);
+        std::array<int, kMaxRank> iv{}, e0{}, e1{};
+        for (int i = 0; i < r0; ++i) iv[i] = index_values_0[i], e0[i] = extents_0[i];
+        for (int i = 0; i < r1; ++i) e1[i] = extents_1[i];
+        SI_RETURN(wl_rec_opaque([=] { return si_energy_denominator_rhf(r0, iv.data(), e0.data(), data_0, r1, e1.data(), data_1, data_2); },
+                                {{data_0, sizeof(double) * (size_t)volume(r0, extents_0), WL_RW},
+                                 {data_1, sizeof(double) * (size_t)volume(r1, extents_1), WL_R}, {data_2, sizeof(double), WL_R}}));
+    }
+    SI_RETURN(si_energy_denominator_rhf(*rank_0, index_values_0, extents_0, data_0, *rank_1, extents_1, data_1, data_2));
+}
 int sipgpu_si_stripi(int*, int* rank_0, int* index_values_0, int*, int* extents_0, double* data_0, int*, int* rank_1,
                      int* index_values_1, int*, int* extents_1, double* data_1, int* ierr) {
     SIP_TRACE("sipgpu_si_stripi");

@@ -33,7 +33,7 @@ int permute_plan_debug(int rank, const int* ext, const int* transp, long long* m
 // superinstr.cu: elementwise CC super-instructions on device blocks
 int si_set_int_array(const char* name, int n, const int* values);
 int si_energy_denominator_rhf(int rank, const int* index_values, const int* ext, double* data, int fock_rank,
-                              const int* fock_ext, const double* fock);
+                              const int* fock_ext, const double* fock, const double* d_shift = nullptr);
 int si_stripi(int rank, const int* iv0, const int* ext0, const double* x, const int* iv1, const int* ext1, double* y);
 int si_anti_symm_o(int rank, const int* iv, const int* ext, double* x);
 int si_anti_symm_v(int rank, const int* iv, const int* ext, double* x);

@@ -37,6 +37,7 @@ struct DenArgs {
     int ext[6], off[6];
     int fock_ld;  // 0: rank-1 Fock array
     long long n;
+    const double* shift;  // energy_ty_denominator_rhf: a device scalar added to eps (nullptr: none)
 };
 
 __global__ void __launch_bounds__(kT) energy_denominator_kernel(double* __restrict__ d, const double* __restrict__ fock,
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kT) energy_denominator_kernel(double* __restri
         if (a.rank == 2) eps = e[1] - e[0];
         else if (a.rank == 4) eps = e[1] + e[3] - e[0] - e[2];
         else eps = e[1] + e[3] + e[5] - e[0] - e[2] - e[4];
+        if (a.shift) eps = eps + __ldg(a.shift);   // energy_ty_denominator_rhf.F: epsb + epsd - epsa - epsc + shift
         d[lin] = d[lin] / eps;
     }
 }
@@ -162,8 +164,9 @@ int si_set_int_array(const char* name, int n, const int* values) {
 }
 
 int si_energy_denominator_rhf(int rank, const int* index_values, const int* ext, double* data, int fock_rank,
-                              const int* fock_ext, const double* fock) {
+                              const int* fock_ext, const double* fock, const double* d_shift) {
     SIP_TRY(ensure_init());
+    if (d_shift && !(rank == 4 && fock_rank == 2)) return SIPGPU_E_ARG;   // the shifted form exists for rank-4 blocks only
     const std::vector<int>* seg = moa_segs();
     if (!seg) { set_error("energy_denominator_rhf: predefined int array moa_seg_ranges is not registered"); return SIPGPU_E_STATE; }
     if (!(rank == 2 || rank == 4 || rank == 6) || !(fock_rank == 1 || fock_rank == 2) || (rank == 6 && fock_rank != 2) ||
@@ -182,6 +185,7 @@ int si_energy_denominator_rhf(int rank, const int* index_values, const int* ext,
         a.n *= ext[d];
     }
     a.fock_ld = fock_rank == 2 ? fock_ext[0] : 0;
+    a.shift = d_shift;
     energy_denominator_kernel<<<grid_for(a.n), kT, 0, ctx().stream>>>(data, fock, a);
     SIP_CUDA(cudaGetLastError());
     count_launch();

@@ -1060,6 +1060,8 @@ class Walker:
             v = self.tables.get(name, {}).get(tuple(self.idx[x] for x in labs), 0.0)
             self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), v)
             return
+        if fname == "energy_ty_denominator_rhf":     # `execute energy_ty_denominator_rhf T[a,i,b,j] fock_a shift`: shift by value
+            bare = [bare[0], self.be.value(self.scalars[bare[1]])]
         blocks = [self._read(n, labs)[0] if self._is_remote(n) and not self._own_static(n) else self._write(n, labs) for n, labs in args]
         kinds = [[self._kind(x) for x in labs] for _, labs in args]
         segs = [tuple(self.idx[x] + self.index_base.get(k, 0) for x, k in zip(labs, ks))
@@ -1251,6 +1253,11 @@ class DeviceBackend:
     def execute(self, fname, blocks, segs, kinds, bare):
         if fname == "energy_denominator_rhf":
             self.api.si_energy_denominator_rhf(blocks[0], segs[0], self.fock)
+        elif fname == "energy_ty_denominator_rhf":      # bare = (fock_a, shift): the scalar travels as a one-element device block
+            shift = self.api.DeviceBlock((1,)).fill(float(bare[1]))
+            if self.api.si_energy_ty_denominator_rhf(blocks[0], segs[0], self.fock, shift) != 0:
+                raise SialSyntaxError("energy_ty_denominator_rhf failed")
+            shift.free()
         elif fname == "stripi":
             if self.api.si_stripi(blocks[0], segs[0], blocks[1], segs[1]) != 0:
                 raise SialSyntaxError("stripi: " + self.api.lib().sipgpu_last_error().decode(errors="replace"))

@@ -260,6 +260,12 @@ int sipgpu_set_predefined_int_array(const char* name, int n, const int* values);
 int sipgpu_si_energy_denominator_rhf(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
                                      int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
                                      int* ierr);
+/* qm-generic/energy_ty_denominator_rhf.F (special energy_ty_denominator_rhf urr): rank-4 array_0 /= eps + shift, array_1 = Fock
+ * matrix (rank 2, device), array_2 = the scalar `shift` as a one-element DEVICE block */
+int sipgpu_si_energy_ty_denominator_rhf(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,
+                                        int* array_1, int* rank_1, int* index_values_1, int* size_1, int* extents_1, double* data_1,
+                                        int* array_2, int* rank_2, int* index_values_2, int* size_2, int* extents_2, double* data_2,
+                                        int* ierr);
 /* qm/utility/stripi.F (special stripi ru): array_1 (one index thick in its stripped dimensions) = the matching
  * strip of array_0; ranks 2-4 */
 int sipgpu_si_stripi(int* array_0, int* rank_0, int* index_values_0, int* size_0, int* extents_0, double* data_0,

@@ -222,6 +222,12 @@ def si_energy_denominator_rhf(block, index_values, fock, moa_seg_ranges):
     return ierr
 
 
+def si_energy_ty_denominator_rhf(block, index_values, fock, shift, moa_seg_ranges):
+    fock = np.asfortranarray(fock, dtype=np.float64)
+    return lib().oracle_si_energy_ty_denominator_rhf(block.ndim, _ia(index_values), _ia(block.shape), _dp(block), fock.shape[0],
+                                                     _dp(fock), C.c_double(shift), _ia(moa_seg_ranges))
+
+
 def si_stripi(x, iv0, y_shape, iv1, moa_seg_ranges):
     y = np.zeros(y_shape, order="F")
     ierr = lib().oracle_si_stripi(x.ndim, _ia(iv0), _ia(x.shape), _dp(x), _ia(iv1), _ia(y_shape), _dp(y), _ia(moa_seg_ranges))

@@ -5,7 +5,7 @@
  * Plain-C restatement of
  *   src/sip/super_instructions/qm/qm-generic/energy_denominator_rhf.F:15-460
  *   src/sip/super_instructions/qm/utility/stripi.F, anti_symm_o.F, anti_symm_v.F, return_sval.F,
- *   invert_diagonal.F, invert_diagonal_asym.F, return_diagonal_elements.F
+ *   invert_diagonal.F, invert_diagonal_asym.F, return_diagonal_elements.F, qm-generic/energy_ty_denominator_rhf.F
  * with the reference's super-instruction calling convention reduced to what the arithmetic reads:
  * (rank, index_values, extents, data) per argument (special_instructions.h:27-97), the predefined int
  * array "moa_seg_ranges" passed explicitly instead of through the sip_interface upcall.
@@ -211,5 +211,25 @@ int oracle_si_invert_diagonal_asym(int rank0, int rank1, const int* iv, const in
                             a1[i] = 0.0;
                         }
                     }
+    return 0;
+}
+
+/* energy_ty_denominator_rhf.F do_rhfty_den4: rank 4 only, rank-2 Fock array: array(a,b,c,d) /= epsb + epsd - epsa - epsc + shift
+ * (the shifted denominator of the CIS(D) program, rcis_d_rhf.sialx:1175) */
+int oracle_si_energy_ty_denominator_rhf(int rank, const int* index_values, const int* ext, double* data, int fock_ld,
+                                        const double* fock, double shift, const int* moa_seg_ranges) {
+    if (rank != 4) return 1;
+    int off[4];
+    for (int d = 0; d < 4; ++d) off[d] = seg_offset(moa_seg_ranges, index_values[d]);
+    long long lin = 0;
+    for (int d = 0; d < ext[3]; ++d)
+        for (int c = 0; c < ext[2]; ++c)
+            for (int b = 0; b < ext[1]; ++b)
+                for (int a = 0; a < ext[0]; ++a, ++lin) {
+                    const double epsa = fock[(size_t)(a + off[0]) * fock_ld + a + off[0]], epsb = fock[(size_t)(b + off[1]) * fock_ld + b + off[1]];
+                    const double epsc = fock[(size_t)(c + off[2]) * fock_ld + c + off[2]], epsd = fock[(size_t)(d + off[3]) * fock_ld + d + off[3]];
+                    const double eps = epsb + epsd - epsa - epsc + shift;
+                    data[lin] = data[lin] / eps;
+                }
     return 0;
 }

@@ -38,6 +38,8 @@ GOLDEN["ne_ccsdpt_test"] = {"eaab": -0.0010909774775509193, "esaab": 8.554784591
 # at 1e-10 -- they pin the CIS starting vectors the harness hands to the EOM program -- and its two EOM roots at 1e-8
 GOLDEN["eom_ccsd_water_test"] = {"sek0": [0.32850657002707, 0.41193399006592, 0.42288344162832, 0.51159731180444],
                                  "tolerance": 1e-8, "oscnorm": [0.00680956, 0.0, 0.09037060, 0.11312310]}
+# eom_ccsd_water_right_test (:927-932): right-hand transition moments, the first two asserted at 1e-4
+GOLDEN["eom_ccsd_water_right_test"] = {"rdipmom": [0.17558771, 0.0, 0.56188382, 0.56905669]}
 GOLDEN["eom_test"] = {"cis_sek0": [0.36275490375537, 0.43493738840536], "eom_sek0": [0.32850656893104, 0.41193399028059]}
 # hydrogen fluoride / 3-21G, the reference's enabled rlambda_test (test/test_qm.cpp:307-341: scf, tran, rccsd_rhf, rlambda_rhf;
 # scf_conv / cc_conv 1e-12): the lambda pseudo-energy at 1e-10
@@ -48,9 +50,12 @@ GOLDEN["rlambda_test"] = {"lambda_pseudo": -0.12592115116563,
 # rlambda_rhf, rlamccsdpt_aaa, rlamccsdpt_aab; cc_conv 1e-12), Lambda-CCSD(T): every number asserted at 1e-10
 GOLDEN["lamccsdpt_test"] = {"ccsd_energy": -99.583972376431, "eaaa": -0.00001109673867, "esaaa": 0.00000190144932,
                             "eaab": -0.00057100058054, "esaab": 0.00002785417018, "ccsdpt_energy": -99.584524718131}
+# hydrogen fluoride / 3-21G: the reference's enabled cis_test (test/test_qm.cpp:153-202: scf, tran, rcis_rhf, rcis_d_rhf; two roots,
+# the degenerate 1-Pi pair): CIS roots `sek0` and the CIS(D) corrections `ekd`, all at 1e-10
+GOLDEN["cis_test"] = {"sek0": [0.43427913493064, 0.43427913493252], "ekd": [-0.03032115569246, -0.03032115569276]}
 out = {"golden": GOLDEN, "source": "UFParLab/aces4 test/*.dat decoded by aces4_b200/setup_reader.py", "setups": {}}
 for name in ("lccd_frozencore_test.dat", "lccd_test.dat", "eom_lccd_test.dat", "lccsd_test.dat", "second_ccsdpt_test.dat",
-             "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat", "rlambda_test.dat"):
+             "lamccsdpt_test.dat", "ccsdpt_test.dat", "eom_ccsd_water_test.dat", "eom_test.dat", "rlambda_test.dat", "cis_test.dat"):
     s = read_setup(open(os.path.join("/root/reference/test", name), "rb").read())
     assert s["trailing_bytes"] == 0
     keep_f = ("alphas", "charge", "coords", "pcoeffs")

@@ -229,6 +229,10 @@ class FakeApi:
         self._launches += 1
         return self.o.si_invert_diagonal_asym(a1.a, list(index_values), a2.a, self._moa)
 
+    def si_energy_ty_denominator_rhf(self, block, index_values, fock, shift_block):
+        self._launches += 1
+        return self.o.si_energy_ty_denominator_rhf(block.a, list(index_values), fock.a, float(shift_block.a.reshape(-1)[0]), self._moa)
+
     def si_energy_denominator_rhf(self, block, index_values, fock):
         self._launches += 1
         return self.o.si_energy_denominator_rhf(block.a, list(index_values), fock.a, self._moa)

@@ -202,6 +202,9 @@ def pt_array_kinds(program):
 # src/sialx/qm/eom/eom_ccsd_rhf_right.sialx + eom_rhf_hbar.sialx + eom_rhf_vars.sialx + eom_rhf_defs.sialx by
 # scripts/make_eom_golden.py) on water / 3-21G (test/eom_ccsd_water_test.dat)
 PROGRAM_EOM = open(os.path.join(HERE, "golden", "eom_ccsd_right_program.sialx")).read()
+PROGRAM_EOM_FULL = open(os.path.join(HERE, "golden", "eom_ccsd_right_full_program.sialx")).read()   # the same, whole file
+PROGRAM_RCIS_D = open(os.path.join(HERE, "golden", "rcis_d_rhf_program.sialx")).read()             # src/sialx/qm/eom/rcis_d_rhf.sialx
+CASES["cis_dat"] = ("cis_test.dat", None)           # hydrogen fluoride / 3-21G, two roots (the reference's cis_test)
 PROGRAM_EOM_LEFT = open(os.path.join(HERE, "golden", "eom_ccsd_left_program.sialx")).read()
 EOM_SETUP = "eom_ccsd_water_test.dat"
 CASES["eom_dat"] = (EOM_SETUP, None)

@@ -127,6 +127,10 @@ class OracleBackend:
             blocks[1].a[...] = y
             self.calls += 1
             return
+        if fname == "energy_ty_denominator_rhf":
+            assert self.o.si_energy_ty_denominator_rhf(blocks[0].a, list(segs[0]), self.fock, float(bare[1]), self.ranges) == 0
+            self.calls += 1
+            return
         if fname in ("anti_symm_o", "anti_symm_v"):
             assert getattr(self.o, "si_" + fname)(blocks[0].a, list(segs[0]), self.ranges) == 0
             self.calls += 1

@@ -21,7 +21,7 @@ from sial_oracle_backend import OracleBackend
 
 PROGRAMS = {"rccsd_rhf": lw.PROGRAM_RCCSD, "rlccd_rhf": lw.PROGRAM_RLCCD, "rlccsd_rhf": lw.PROGRAM_RLCCSD,
             "tran_rhf_no4v": lw.PROGRAM_TRAN_NO4V, "rcis_rhf": lw.PROGRAM_RCIS, "rlambda_rhf": lw.PROGRAM_RLAMBDA,
-            "rlamccsdpt_aaa": lw.PROGRAM_RLAMPT_AAA, "rlamccsdpt_aab": lw.PROGRAM_RLAMPT_AAB}
+            "rlamccsdpt_aaa": lw.PROGRAM_RLAMPT_AAA, "rlamccsdpt_aab": lw.PROGRAM_RLAMPT_AAB, "rcis_d_rhf": lw.PROGRAM_RCIS_D}
 
 
 def run_cc_program(oracle, name, case, chained=False):
@@ -166,6 +166,27 @@ def test_reference_lambda_ccsdpt_programs_reproduce_lamccsdpt_test(oracle, case)
     for k, v in got.items():
         assert abs(v - g[k]) < 1e-10, (k, v, g[k])
         assert abs(v - g[k]) < (1e-11 if k == "ccsdpt_energy" else 1e-13), (k, v, g[k])
+
+
+def test_reference_cis_and_cis_d_programs_reproduce_cis_test(oracle):
+    """The reference's ENABLED cis_test (test/test_qm.cpp:153-202; hydrogen fluoride / 3-21G, the degenerate 1-Pi pair): scf ->
+    tran -> rcis_rhf -> rcis_d_rhf verbatim: the CIS roots `sek0` and the CIS(D) corrections `ekd` (the doubles correction with the
+    shifted denominator `energy_ty_denominator_rhf`), all at 1e-10.  measured: sek0 2.7e-12 / 9e-13, ekd 1.3e-13 / 1.6e-13.
+    (The reference's job transforms with tran_rhf_no3v; tran_rhf_no4v produces the same classes the two programs restore.)"""
+    case = "cis_dat"
+    g = lw.GOLDEN["cis_test"]
+    W.host_registry.clear()
+    run_cc_program(oracle, "tran_rhf_no4v", case)
+    reg = OracleBackend.registry
+    kept = {lab: reg[lab] for lab in ("Vpiqj", "VSpipi")}        # (rcis_rhf does not touch them; rcis_d_rhf restores them)
+    sc, _ = run_cc_program(oracle, "rcis_rhf", case, chained=True)
+    for k in (1, 2):
+        assert abs(sc["tables"]["sek0"][(k,)] - g["sek0"][k - 1]) < 1e-10, sc["tables"]["sek0"]
+    reg.update({lab: a for lab, a in kept.items() if lab not in reg})
+    sc, _ = run_cc_program(oracle, "rcis_d_rhf", case, chained=True)
+    for k in (1, 2):
+        assert abs(sc["tables"]["ekd"][(k,)] - g["ekd"][k - 1]) < 1e-10, sc["tables"]["ekd"]
+        assert abs(sc["tables"]["ekd"][(k,)] - g["ekd"][k - 1]) < 1e-12
 
 
 def test_reference_lccd_and_lccsd_programs_all_electron(oracle):

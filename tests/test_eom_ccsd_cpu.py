@@ -98,8 +98,9 @@ def test_reference_eom_program_reproduces_the_four_roots_of_eom_ccsd_water_test(
 
 
 def test_eom_ccsd_water_test_in_full(oracle):
-    """Every assertion of the reference's eom_ccsd_water_test (test/test_qm.cpp:965-1031) through its own program texts:
-    tran_rhf_no4v -> rccsd_rhf (ccsd_energy of the cc_conv = 1e-10 run) -> rlambda_rhf -> eom_ccsd_rhf_right (roots `sek0`) ->
+    """Every assertion of the reference's eom_ccsd_water_test (test/test_qm.cpp:965-1031) and of eom_ccsd_water_right_test
+    (:882-934: the same job up to the right-hand program, plus its transition moments `Rdipmom`) through its own program texts:
+    tran_rhf_no4v -> rccsd_rhf (ccsd_energy of the cc_conv = 1e-10 run) -> rlambda_rhf -> eom_ccsd_rhf_right WHOLE (roots `sek0`) ->
     eom_ccsd_rhf_left VERBATIM, whole file (tests/golden/eom_ccsd_left_program.sialx: L H-bar sigma vectors started from the
     right-hand vectors; biorthogonalisation, r0, the one-particle transition densities of COMPUTE_DENSITY -- 1 400 lines of block
     contractions of R, L, T and Lambda amplitudes --, back-transformation, trace with the dipole integrals): the roots a second
@@ -130,15 +131,16 @@ def test_eom_ccsd_water_test_in_full(oracle):
         w.run()
         return w, be
 
-    statics = {"ca": reg["ca"], "fock_a": reg["fock_a"]}
-    w, be = run(lw.PROGRAM_EOM, statics)                 # (the generated right-hand program takes ca / fock_a from the harness)
-    right = [w.tables["sek0"][(k,)] for k in range(1, 5)]
-    for name, label in lw.restored_labels(lw.PROGRAM_EOM):          # the servers' files of persistent arrays outlive a restore
-        if label not in reg and name in be.arrays:
-            reg[label] = be.arrays[name]
-    reg.update(statics)
     Walker.host_registry["scf_dipole"] = scf_dipole
     Walker.host_registry["nuclear_dipole"] = {(k + 1,): float(host_data["nuclear_dipole"][k]) for k in range(3)}
+    w, be = run(lw.PROGRAM_EOM_FULL, {})                 # eom_ccsd_rhf_right.sialx, whole file
+    right = [w.tables["sek0"][(k,)] for k in range(1, 5)]
+    rdip = [w.tables["rdipmom"][(k,)] for k in range(1, 5)]
+    for got, want in zip(rdip[:2], lw.GOLDEN["eom_ccsd_water_right_test"]["rdipmom"][:2]):     # the two the reference asserts (1e-4)
+        assert abs(got - want) < 1e-4 and abs(got - want) < 1e-5, (rdip, want)                  # measured: 2.2e-6, 4.7e-7
+    for name, label in lw.restored_labels(lw.PROGRAM_EOM_FULL):     # the servers' files of persistent arrays outlive a restore
+        if label not in reg and label not in Walker.host_registry and name in be.arrays:
+            reg[label] = be.arrays[name]
     w, be = run(lw.PROGRAM_EOM_LEFT, {})
     left = [w.tables["sek0"][(k,)] for k in range(1, 5)]
     osc = [w.tables["oscnorm"][(k,)] for k in range(1, 5)]

@@ -137,3 +137,18 @@ def test_return_diagonal_elements_and_invert_diagonal_asym(sip, oracle):
         assert oracle.si_invert_diagonal_asym(a1, iv, a2, SEGS) == 0
         assert np.array_equal(d1.to_numpy(), a1), shape
     assert sip.si_invert_diagonal_asym(sip.DeviceBlock((2, 2, 2)), (1, 1, 1), sip.DeviceBlock((2, 2, 2))) != 0
+
+
+def test_energy_ty_denominator_rhf(sip, oracle):
+    rng = np.random.default_rng(33)
+    n = sum(SEGS)
+    fock = np.asfortranarray(np.diag(np.sort(rng.uniform(-3, 3, n))) + 0.01 * rng.uniform(-1, 1, (n, n)))
+    dfock = sip.DeviceBlock.from_numpy(fock)
+    for iv, shift in (((3, 1, 3, 1), 0.4342791), ((4, 2, 3, 1), -0.125), ((5, 1, 5, 2), 0.0)):
+        shape = tuple(SEGS[s - 1] for s in iv)
+        x = fblock(rng, shape)
+        d = sip.DeviceBlock.from_numpy(x)
+        assert sip.si_energy_ty_denominator_rhf(d, iv, dfock, sip.DeviceBlock((1,)).fill(shift)) == 0
+        assert oracle.si_energy_ty_denominator_rhf(x, iv, fock, shift, SEGS) == 0
+        assert np.array_equal(d.to_numpy(), x), iv
+    assert sip.si_energy_ty_denominator_rhf(sip.DeviceBlock((4, 4)), (1, 1), dfock, sip.DeviceBlock((1,)).fill(0.0)) != 0

@@ -112,6 +112,27 @@ def test_reference_lambda_ccsdpt_programs_on_the_device(sip):
 
 
 @pytest.mark.timeout(900, method="thread")
+def test_reference_cis_and_cis_d_programs_on_the_device(sip):
+    """the reference's enabled cis_test on libsipgpu (hydrogen fluoride / 3-21G): tran -> rcis_rhf -> rcis_d_rhf verbatim; CIS roots and
+    CIS(D) corrections at the test's 1e-10"""
+    case = "cis_dat"
+    inp = lw.inputs(case)
+    g = lw.GOLDEN["cis_test"]
+    seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
+    consts = lw.setup_constants(case)
+    dc.run_program_on_device(sip, lw.PROGRAM_TRAN_NO4V, case, inp, seg_ext, aoint, fock, True, consts, extra_arrays=dc.static_arrays(sip, seg_ext))
+    w1, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_RCIS, case, inp, seg_ext, aoint, fock, True, consts,
+                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    w2, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_RCIS_D, case, inp, seg_ext, aoint, fock, True, consts,
+                                        extra_arrays=dc.static_arrays(sip, seg_ext))
+    sek0 = [w1.tables["sek0"][(k,)] for k in (1, 2)]
+    ekd = [w2.tables["ekd"][(k,)] for k in (1, 2)]
+    print(f"\ncis_test on the device: sek0 {sek0} (goldens {g['sek0']}), ekd {ekd} (goldens {g['ekd']})")
+    for got, want in zip(sek0 + ekd, g["sek0"] + g["ekd"]):
+        assert abs(got - want) < 1e-10, (sek0, ekd)
+
+
+@pytest.mark.timeout(900, method="thread")
 def test_reference_lccsd_and_ccsd_programs_on_the_device(sip):
     sc, launches = run(sip, lw.PROGRAM_RLCCSD, "all_dat", True)
     g_corr, g_e = lw.golden_lccsd()

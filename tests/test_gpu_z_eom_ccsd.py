@@ -29,7 +29,7 @@ def sip():
 
 def run_eom_on_device(sip, case, record):
     """the reference's job on libsipgpu, program by program: tran_rhf_no4v -> rccsd_rhf (DIIS, stopped at the setup's cc_conv) ->
-    rlambda_rhf -> eom_ccsd_rhf_right, chained through persistent arrays (the library's label registry: the slabs never leave HBM)"""
+    rlambda_rhf -> eom_ccsd_rhf_right (whole file), chained through persistent arrays (the library's label registry: the slabs never leave HBM)"""
     from aces4_b200.sial_frontend import DeviceBackend, Program, Walker
 
     inp = lw.inputs(case)
@@ -62,11 +62,11 @@ def run_eom_on_device(sip, case, record):
     c1_a = dc.resident(sip, [[1] * lw.eom_simple_extents(prog2, consts)["kstate"], seg_ext["v"], seg_ext["o"]], c1)
     sip.sync()
     c1_a.persist("C1_a")
-    stat = dc.static_arrays(sip, seg_ext)
-    for name, A in stat.items():
-        A.restore(name)
-    w2, be2, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM, case, inp, seg_ext, aoint, fock, record, consts, extra_arrays=stat)
+    Walker.host_registry["nuclear_dipole"] = {(k + 1,): float(host_data["nuclear_dipole"][k]) for k in range(3)}
+    w2, be2, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM_FULL, case, inp, seg_ext, aoint, fock, record, consts,
+                                          extra_arrays=dc.static_arrays(sip, seg_ext), host_data=host_data)
     roots = [w2.tables["sek0"][(k,)] for k in range(1, len(e_cis) + 1)]
+    run_eom_on_device.rdipmom = [w2.tables["rdipmom"][(k,)] for k in range(1, len(e_cis) + 1)]
     run_eom_on_device.state = (inp, seg_ext, aoint, fock, consts, be2)
     return roots, e_cis, e_ccsd, niter, sip.kernel_launches() - l0
 
@@ -78,15 +78,11 @@ def run_left_program_on_device(sip, case, record):
     from aces4_b200.sial_frontend import Walker
 
     inp, seg_ext, aoint, fock, consts, be2 = run_eom_on_device.state
-    persisted_by_right = {lab for _, lab in __import__("re").findall(r'(?im)^\s*set_persistent\s+(\w+)\s+"(\w+)"', lw.PROGRAM_EOM)}
-    for name, label in lw.restored_labels(lw.PROGRAM_EOM):
+    persisted_by_right = {lab for _, lab in __import__("re").findall(r'(?im)^\s*set_persistent\s+(\w+)\s+"(\w+)"', lw.PROGRAM_EOM_FULL)}
+    for name, label in lw.restored_labels(lw.PROGRAM_EOM_FULL):
         if label not in persisted_by_right and name in be2.arrays:
             be2.arrays[name].persist(label)
-    for name in ("ca", "fock_a"):               # the generated right-hand program took them from the harness: hand them back
-        be2.arrays[name].persist(name)
-    host_data, scf_dipole = lw.dipole_data(lw.EOM_SETUP)
-    Walker.host_registry["scf_dipole"] = scf_dipole
-    Walker.host_registry["nuclear_dipole"] = {(k + 1,): float(host_data["nuclear_dipole"][k]) for k in range(3)}
+    host_data, _ = lw.dipole_data(lw.EOM_SETUP)
     w, _, _ = dc.run_program_on_device(sip, lw.PROGRAM_EOM_LEFT, case, inp, seg_ext, aoint, fock, record, consts,
                                        extra_arrays=dc.static_arrays(sip, seg_ext), host_data=host_data, trace=True)
     return [w.tables["sek0"][(k,)] for k in range(1, 5)], [w.tables["oscnorm"][(k,)] for k in range(1, 5)], dict(w.state_converged)
@@ -105,6 +101,9 @@ def test_reference_eom_program_on_the_device(sip, case, record, with_left=True):
         assert abs(got - want) < g["tolerance"], (roots, g["sek0"])
     assert max(abs(a - b) for a, b in zip(roots, g["sek0"])) < 2e-9
     assert launches > 0
+    rdip = run_eom_on_device.rdipmom            # eom_ccsd_water_right_test asserts the first two right-hand transition moments (1e-4)
+    for got, want in zip(rdip[:2], lw.GOLDEN["eom_ccsd_water_right_test"]["rdipmom"][:2]):
+        assert abs(got - want) < 1e-4, (rdip, want)
     if case == "eom_dat" and with_left:        # ... and the left-hand program: roots again (test_qm.cpp:1017-1024) + oscillator norms (:1025-1030)
         left, osc, flags = run_left_program_on_device(sip, case, record)
         print("left-hand program on the device: roots " + ", ".join(f"{r:.14f}" for r in left) + f" (solver's convergence flags {flags}); "

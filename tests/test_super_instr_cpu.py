@@ -165,3 +165,23 @@ def test_return_diagonal_elements_and_invert_diagonal_asym(oracle):
         assert oracle.si_invert_diagonal_asym(a1, iv, a2, segs) == 0
         assert np.array_equal(a1, ref), iv
     assert oracle.si_invert_diagonal_asym(np.zeros((2, 2, 2), order="F"), (1, 1, 1), np.zeros((2, 2, 2), order="F"), segs) == 1
+
+
+def test_energy_ty_denominator_rhf(oracle):
+    """energy_ty_denominator_rhf.F do_rhfty_den4: x(a,b,c,d) /= eps_b + eps_d - eps_a - eps_c + shift, orbital numbers from the
+    segment offsets"""
+    rng = np.random.default_rng(19)
+    segs = [2, 3, 3, 5]
+    off = np.concatenate([[0], np.cumsum(segs)])
+    eps = np.sort(rng.uniform(-2, 2, 13))
+    fock = np.asfortranarray(np.diag(eps) + 0.01 * rng.uniform(-1, 1, (13, 13)))
+    for iv, shift in (((3, 1, 4, 2), 0.375), ((4, 2, 4, 2), -0.2)):
+        shape = tuple(segs[s - 1] for s in iv)
+        x = np.asfortranarray(rng.uniform(-1, 1, shape))
+        ref = x.copy(order="F")
+        for a, b, c, d in np.ndindex(*shape):
+            e = [fock[i + off[s - 1], i + off[s - 1]] for i, s in zip((a, b, c, d), iv)]
+            ref[a, b, c, d] = x[a, b, c, d] / (e[1] + e[3] - e[0] - e[2] + shift)
+        assert oracle.si_energy_ty_denominator_rhf(x, iv, fock, shift, segs) == 0
+        assert np.array_equal(x, ref)
+    assert oracle.si_energy_ty_denominator_rhf(np.zeros((2, 2), order="F"), (1, 1), fock, 0.0, segs) == 1
