@@ -4,6 +4,7 @@ GPU minutes were spent; this runs everything in them that is not the CUDA librar
 (device-resident scalars across iterations, block views, put / get traffic, local arrays) and the assertions of the
 tests themselves -- so that what remains unexercised until the first B200 run is libsipgpu's arithmetic alone, which the
 rest of the GPU suite has already covered op by op."""
+import os
 import pytest
 
 import test_gpu_z_cross_product as xp
@@ -54,7 +55,8 @@ def test_reference_triples_programs_device_test_body_on_the_fake_api(oracle):
 
 def test_reference_eom_program_device_test_body_on_the_fake_api(oracle):
     import test_gpu_z_eom_ccsd as eom
-    eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True)
+    # (without the left-hand program, 25 s more: its CPU twin is tests/test_eom_ccsd_cpu.py::test_eom_ccsd_water_test_in_full)
+    eom.test_reference_eom_program_on_the_device(FakeApi(oracle), "eom_dat", True, with_left=bool(os.environ.get("SIPGPU_SLOW_TESTS")))
 
 
 def test_reference_cc_programs_device_test_bodies_on_the_fake_api(oracle):
