@@ -236,7 +236,8 @@ class Program:
 
     def _parse(self, line, low, tok):
         kw = tok[0]
-        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "destroy", "special", "broadcast_from", "assert_same"):
+        if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "destroy", "special", "broadcast_from", "assert_same",
+                  "gpu_on", "gpu_off"):
             return None           # arrays exist (zero) from the start; nothing is printed; super-instruction signatures are not
                                   # needed; broadcast_from / assert_same: every worker computes the replicated statics itself
         if kw == "predefined":
@@ -286,9 +287,10 @@ class Program:
             m = re.match(r"\w+\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line)
             if not m:
                 raise SialSyntaxError("bad index declaration")
-            kind = _KIND_BY_RANGE.get((m.group(2).lower(), m.group(3).lower()))
-            if kind is None:
-                raise SialSyntaxError("unsupported index range")
+            lo, hi = m.group(2).lower(), m.group(3).lower()
+            kind = _KIND_BY_RANGE.get((lo, hi))
+            if kind is None:     # any other segment range of the index type (`aoindex i = 1:1`, `moaindex j = 2: 3`): a kind of its own
+                kind = f"{'ao' if kw == 'aoindex' else 'mo'}:{lo}:{hi}"
             self.index_kind[m.group(1).lower()] = kind
             return None
         if kw in ("served", "distributed", "temp", "local", "static"):
@@ -305,10 +307,13 @@ class Program:
         if kw in ("endpardo", "enddo"):
             return (kw,)
         if kw == "where":
-            m = re.match(r"where\s+(\w+)\s*(<=|>=|==|!=|<|>)\s*(\w+)", low)
+            m = re.match(r"where\s+(\w+)\s*(<=|>=|==|!=|<|>)\s*(\w+)\s*$", low)
+            if m:
+                return ("where", m.group(1), m.group(2), m.group(3))
+            m = re.match(r"where\s+(.+?)\s*(<=|>=|==|!=|<|>)\s*(.+)$", low)     # `where k == ((i-1)*norb + (j-1)) + 1`
             if not m:
                 raise SialSyntaxError("unsupported where clause")
-            return ("where", m.group(1), m.group(2), m.group(3))
+            return ("where", parse_expr(m.group(1)), m.group(2), parse_expr(m.group(3)))
         if kw in ("request", "get"):
             m = re.match(r"\w+\s+" + _REF, line)
             if not m:
@@ -359,6 +364,10 @@ class Program:
             if mm and op == "=":
                 return ("contract", name, labs, mm.group(1).lower(), _labels(mm.group(2)), mm.group(3).lower(),
                         _labels(mm.group(4)))
+            mm = re.match(_REF + r"\s*([+-])\s*" + _REF + r"\s*$", rhs)
+            if mm and op == "=":     # `a[i,j] = b[i,j] + c[i,j]` (handle_block_add / subtract, interpreter.cpp:1874-1997)
+                return ("addsub", name, labs, mm.group(1).lower(), _labels(mm.group(2)), mm.group(4).lower(), _labels(mm.group(5)),
+                        1.0 if mm.group(3) == "+" else -1.0)
             mm = re.match(_REF + r"\s*$", rhs)
             if mm and op in ("=", "+=", "-="):
                 return ("assign" if op == "=" else "add", name, labs, mm.group(1).lower(), _labels(mm.group(2)),
@@ -533,13 +542,15 @@ class Walker:
     """Executes a Program against a backend: the per-block call stream of one worker."""
     host_registry = {}       # persistent host tables (label -> {index values: number}), shared by consecutive programs
 
-    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None, host_data=None):
+    def __init__(self, program, backend, segs, rank=0, world=1, index_base=None, constants=None, host_data=None, seg_tables=None,
+                 extra_si=None):
         """segs: {'o': [extents of the occupied segments], 'v': [...], 'ao': [...]}; 'p' = o followed by v.
         index_base: {'o': baocc - 1, 'v': bavirt - 1, ...}: what to add to a loop's segment number to get the absolute
         segment number of its index type -- the index values a super-instruction receives (the reference's loops run
         over baocc..eaocc / bavirt..eavirt directly, interpreter.cpp:1011-1208)."""
         self.p, self.be, self.rank, self.world = program, backend, rank, world
         self.host_data = dict(host_data or {})     # tables an out-of-scope engine would compute (dipole integrals, ...)
+        self.extra_si = dict(extra_si or {})       # further super-instructions by name: f(walker, args, bare) (the reference's test helpers)
         self.index_base = dict(index_base or {})
         self.segs = dict(segs)
         if "p" not in self.segs and "o" in self.segs and "v" in self.segs:
@@ -549,6 +560,19 @@ class Walker:
         self.segs["s"] = _Ones()
         # predefined ints (naocc, eom_roots, ...) and scalars (eom_tol, ...)
         self.constants = {k.lower(): (int(v) if float(v).is_integer() else float(v)) for k, v in (constants or {}).items()}
+        # index ranges outside the named ones: segments lo..hi of the index type's table (`seg_tables` = {'ao': [...], 'mo': [...]},
+        # default: segs['ao'] / segs['pa'])
+        tables = dict(seg_tables or {})
+        self._range_lo = {}
+        for kind in set(program.index_kind.values()):
+            if ":" in kind:
+                typ, lo, hi = kind.split(":")
+                lo, hi = (int(x) if x.isdigit() else int(self.constants[x]) for x in (lo, hi))
+                full = tables.get(typ, self.segs.get("ao" if typ == "ao" else "pa"))
+                if full is None or hi > len(full):
+                    raise SialSyntaxError(f"index range {kind}: no segment table of that length for index type {typ}")
+                self.segs[kind] = list(full[lo - 1: hi])
+                self._range_lo[kind] = lo
         self.tables = {}         # static arrays over simple indices only (index tables such as Xijk): {(i, j): value}
         self.idx = {}            # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
@@ -622,7 +646,13 @@ class Walker:
         plan = self._segkey_plan.get(labs)
         if plan is None:
             base = {"o": 0, "p": 0, "v": len(self.segs.get("o", ())), "ao": 1 << 20, "s": 1 << 21}
-            plan = self._segkey_plan[labs] = [(lab, base.get(self._kind(lab), 0)) for lab in labs]
+
+            def key_base(kind):
+                if ":" in kind:      # absolute segment number inside the index type's own range of keys
+                    return (1 << 20 if kind.startswith("ao:") else 0) + self._range_lo[kind] - 1
+                return base.get(kind, 0)
+
+            plan = self._segkey_plan[labs] = [(lab, key_base(self._kind(lab))) for lab in labs]
         idx = self.idx
         return tuple(idx[lab] + b for lab, b in plan)
 
@@ -656,11 +686,25 @@ class Walker:
                     plan.append((lab, 1 - (int(lo) if lo.isdigit() else self.constants[lo])))
                 elif dk == k or (dk == "p" and k == "o"):
                     plan.append((lab, 0))
+                elif (":" in dk or dk == "ao") and (":" in k or k == "ao") and dk.split(":")[0] == k.split(":")[0]:
+                    plan.append((lab, self._range_lo.get(k, 1) - self._range_lo.get(dk, 1)))    # same index type, other range
                 else:
                     raise SialSyntaxError(f"index {lab} ({k}) cannot address dimension {d} ({dk}) of {name}")
             self._aseg_plan[name, labs] = plan
         idx = self.idx
         return tuple(idx[lab] + shift for lab, shift in plan)
+
+    def block_of(self, name, values):
+        """handle of the block of a local / static array at the given values of its DECLARED indices (what the reference's test
+        controllers read with `local_block(name, indices)`), or None"""
+        decl = self.p.arrays[name][1]
+        saved = dict(self.idx)
+        self.idx.update(dict(zip(decl, values)))
+        try:
+            key = self._segs_of(decl)
+            return self.locals.get(name, {}).get(key) or self.own_static.get(name, {}).get(key)
+        finally:
+            self.idx = saved
 
     def _own_static(self, name):
         """a `static` array that is not handed in by the harness: the program fills it itself (zero until then)"""
@@ -679,6 +723,8 @@ class Walker:
                 blocks[key[1]] = self.be.new_block(self._shape(labs))
                 self.be.fill(blocks[key[1]], 0.0)
             return blocks[key[1]]
+        if name not in self.locals and self.p.arrays.get(name, ("",))[0] == "local" and name not in self.p.contiguous:
+            self.locals[name] = {}         # a local array written without `allocate` (put_test.sialx: `result[k] = x`): created on first touch
         if name in self.locals:            # allocated local array: zero-filled blocks that outlive the loop scopes
             blocks = self.locals[name]
             if key[1] not in blocks:
@@ -771,8 +817,11 @@ class Walker:
                 self.idx.pop(n, None)
 
     def _x_where(self, a, op, b):
-        va = self.idx[a] if a in self.idx else int(a) if a.isdigit() else self._eval(("var", a))
-        vb = self.idx[b] if b in self.idx else int(b) if b.isdigit() else self._eval(("var", b))
+        if isinstance(a, tuple):
+            va, vb = self._eval(a), self._eval(b)
+        else:
+            va = self.idx[a] if a in self.idx else int(a) if a.isdigit() else self._eval(("var", a))
+            vb = self.idx[b] if b in self.idx else int(b) if b.isdigit() else self._eval(("var", b))
         return {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]
 
     def _x_pardo(self, labs, body):
@@ -980,6 +1029,20 @@ class Walker:
             self.be.axpy(d, t, sign)
             self.be.free(t)
 
+    def _x_addsub(self, name, labs, lname, llabs, rname, rlabs, sign):
+        L, ll = self._read(lname, llabs)
+        R, rl = self._read(rname, rlabs)
+        if tuple(ll) != tuple(labs):
+            raise SialSyntaxError("block add: the first operand must carry the destination's labels")
+        d = self._write(name, labs)
+        if tuple(rl) != tuple(labs):     # the interpreter permutes the second operand into a temp first
+            t = self.be.new_block(self._shape(labs))
+            self.be.copy(t, labs, R, rl)
+            self.be.add_sub(d, L, t, sign)
+            self.be.free(t)
+        else:
+            self.be.add_sub(d, L, R, sign)
+
     def _x_contract(self, name, labs, lname, llabs, rname, rlabs):
         L, ll = self._read(lname, llabs)
         R, rl = self._read(rname, rlabs)
@@ -994,7 +1057,9 @@ class Walker:
         (self.be.put_accumulate if op == "+=" else self.be.put)(arr, self._array_segs(arr, alabs), s)
 
     def _x_execute(self, fname, args, bare):
-        if fname in ("compute_int_scratchmem", "print_block", "print_scalar"):
+        if fname in self.extra_si:
+            return self.extra_si[fname](self, args, bare)
+        if fname in ("compute_int_scratchmem", "print_block", "print_scalar", "test_print_block", "print_static_array"):
             return                                   # integral-engine scratch sizing / output: nothing on this path
         if fname in ("set_ijk_aab", "set_ijk_aaa"):  # occupied-triplet batches of the (T) programs: host logic
             self.tables[bare[0]] = set_ijk_aab(self.be.moa_seg_ranges(), self.constants["baocc"], self.constants["eaocc"],
@@ -1064,7 +1129,7 @@ class Walker:
             bare = [bare[0], self.be.value(self.scalars[bare[1]])]
         blocks = [self._read(n, labs)[0] if self._is_remote(n) and not self._own_static(n) else self._write(n, labs) for n, labs in args]
         kinds = [[self._kind(x) for x in labs] for _, labs in args]
-        segs = [tuple(self.idx[x] + self.index_base.get(k, 0) for x, k in zip(labs, ks))
+        segs = [tuple(self.idx[x] + (self._range_lo[k] - 1 if k in self._range_lo else self.index_base.get(k, 0)) for x, k in zip(labs, ks))
                 for (_, labs), ks in zip(args, kinds)]
         self.be.execute(fname, blocks, segs, kinds, bare)
 
@@ -1187,6 +1252,9 @@ class DeviceBackend:
 
     def increment(self, b, v):
         b.increment(v)
+
+    def add_sub(self, d, l, r, sign):
+        d.set_add_sub(l, r, sign)
 
     def copy(self, d, dlabs, s, slabs):
         if tuple(dlabs) == tuple(slabs):

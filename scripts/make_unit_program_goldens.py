@@ -1,0 +1,19 @@
+"""Copies the SIAL programs of the reference's block-operation unit tests (src/sialx/test/*.sialx, driven by
+test/test_basic_sial.cpp and test/test_sial.cpp: the known-answer tests of SURVEY.md section 8c) into
+tests/golden/ref_unit_programs/ VERBATIM, under a two-line header -- TEST INPUTS of the SIAL front-end
+(tests/test_reference_unit_programs_cpu.py, tests/test_gpu_z_reference_unit_programs.py), generated in the build container where
+/root/reference exists:   python scripts/make_unit_program_goldens.py"""
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = "/root/reference/src/sialx/test/"
+NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "transpose4d_tmp", "transpose4d_square_tmp",
+         "contract_to_scalar", "sum_op_test", "self_multiply_test", "put_test", "get_mpi", "put_accumulate_mpi",
+         "put_accumulate_stress", "tmp_arrays", "tmp_arrays_2", "block_scale_assign")
+os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
+for name in NAMES:
+    text = open(SRC + name + ".sialx", errors="replace").read()
+    head = (f"# tests/golden/ref_unit_programs/{name}.sialx -- the reference's src/sialx/test/{name}.sialx, verbatim, as a TEST INPUT of the\n"
+            "# SIAL front-end (copied by scripts/make_unit_program_goldens.py)\n")
+    open(os.path.join(ROOT, "tests", "golden", "ref_unit_programs", name + ".sialx"), "w").write(head + text)
+print(len(NAMES), "programs")

@@ -76,6 +76,10 @@ class FakeApi:
                 self.a[...] = api.o.block_add(self.a, other.a, f)[0]
                 return self._op()
 
+            def set_add_sub(self, l, r, sign):
+                self.a[...] = l.a + r.a if sign > 0 else l.a - r.a
+                return self._op()
+
             def accumulate(self, other):
                 return self.axpy(other, 1.0)
 

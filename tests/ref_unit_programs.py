@@ -1,0 +1,174 @@
+"""The reference's block-operation unit tests (test/test_basic_sial.cpp, test/test_sial.cpp: the known-answer tests of SURVEY.md
+section 8c) driven from THEIR OWN SIAL programs -- tests/golden/ref_unit_programs/*.sialx = src/sialx/test/*.sialx verbatim
+(scripts/make_unit_program_goldens.py) -- through the SIAL front-end on a backend, with the segment tables and constants each C++
+test sets up and the assertions it makes (restated from the C++ loops).  Shared by the CPU (oracle backend) and GPU (libsipgpu)
+test files; `make_backend(arrays)` builds the backend, `to_numpy(handle)` reads a block back."""
+import itertools
+import os
+
+import numpy as np
+
+from aces4_b200.sial_frontend import Program, Walker
+from oracle import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def text(name):
+    return open(os.path.join(HERE, "golden", "ref_unit_programs", name + ".sialx")).read()
+
+
+def _fill(kind):
+    """the reference's test super-instructions fill_block_cyclic / fill_block_sequential (super_instructions/.../fill_block_*.f):
+    element n (column-major, 0-based) = ((n + start - 1) mod 20) + 1  /  start + n"""
+    def si(w, args, bare):
+        name, labs = args[0]
+        start = float(bare[0]) if bare[0].replace(".", "", 1).replace("-", "", 1).isdigit() else w.be.value(w.scalars[bare[0]])
+        h = w._write(name, labs)
+        shape = w._shape(labs)
+        w.be.set_from_host(h, (oracle.fill_cyclic if kind == "cyclic" else oracle.fill_sequential)(shape, start))
+    return si
+
+
+EXTRA_SI = {"fill_block_cyclic": _fill("cyclic"), "fill_block_sequential": _fill("sequential"),
+            "list_blocks_with_number": lambda w, a, b: None, "list_block_map": lambda w, a, b: None,
+            "one_arg_no_op": lambda w, a, b: None}
+
+
+def dim_segments(prog, label, seg_tables, constants):
+    """segment extents of the range a declared index `label` runs over (a simple index: as many one-element segments as values)"""
+    kind = prog.index_kind[label]
+    val = lambda x: int(x) if str(x).isdigit() else int(constants[x])      # noqa: E731
+    if kind == "s":
+        lo, hi = prog.simple_range[label]
+        return [1] * (val(hi) - val(lo) + 1)
+    if ":" in kind:
+        typ, lo, hi = kind.split(":")
+        return list(seg_tables[typ][val(lo) - 1: val(hi)])
+    if kind == "ao":
+        return list(seg_tables["ao"][: val("norb")] if "norb" in constants else seg_tables["ao"])
+    lo, hi = {"o": ("baocc", "eaocc"), "v": ("bavirt", "eavirt"), "p": ("baocc", "eavirt"), "pa": (1, "eavirt")}[kind]
+    return list(seg_tables["mo"][val(lo) - 1: val(hi)])
+
+
+def run(name, make_backend, ao=None, mo=None, constants=None, arrays=()):
+    prog = Program(text(name))
+    be = make_backend(prog, {"ao": ao or [], "mo": mo or []}, constants or {})
+    segs = {"ao": list(ao or []), "pa": list(mo or [])}
+    c = dict(constants or {})
+    if mo and "baocc" in c:
+        segs["o"] = mo[c["baocc"] - 1: c["eaocc"]]
+        segs["v"] = mo[c["bavirt"] - 1: c["eavirt"]]
+    w = Walker(prog, be, segs, constants=c, seg_tables={"ao": ao or [], "mo": mo or []}, extra_si=EXTRA_SI,
+               index_base={"o": c.get("baocc", 1) - 1, "v": c.get("bavirt", 1) - 1})
+    w.run()
+    return w, be
+
+
+# ---- the tests (each returns nothing, asserts) ----------------------------------------------------------------------
+def contraction_small_test(make_backend, to_numpy):
+    """BasicSial.contraction_small_test (test_basic_sial.cpp:695-770): c[i,l] = a[i,j,k,l]*b[j,k], segment 15"""
+    w, _ = run("contraction_small_test", make_backend, ao=[15, 15, 15, 15, 15, 15, 15, 15, 14, 14, 14, 14, 12, 12])
+    c_data = to_numpy(w.block_of("c", (1, 1))).ravel(order="F")
+    n = 15
+    a = ((np.arange(n ** 4) % 20) + 1).astype(float).reshape(n, n, n, n)      # the C++ test's row-major arrays
+    b = ((np.arange(n ** 2) % 20) + 1).astype(float).reshape(n, n)
+    for i in range(n):
+        for l in range(n):
+            assert np.sum(a[i, :, :, l] * b) == c_data[i * n + l]
+
+
+def contraction_small_test2(make_backend, to_numpy):
+    """BasicSial.contraction_small_test2 (:773-815) + test/test_contraction_small2.F: c[mu,i1,a1,i] = b[lambda,a1]*a[mu,i1,i,lambda];
+    ao 9, moa {5, 4} (occupied = segment 1, virtual = segment 2)"""
+    w, _ = run("contraction_small_test2", make_backend, ao=[9], mo=[5, 4], constants={"baocc": 1, "eaocc": 1, "bavirt": 2, "eavirt": 2})
+    c = to_numpy(w.block_of("c", (1, 1, 1, 1)))
+    a = oracle.fill_cyclic((9, 5, 5, 9), 1.0)
+    b = oracle.fill_cyclic((9, 4), 1.0)
+    assert np.array_equal(c, np.einsum("mxyq,qz->mxzy", a, b))
+
+
+def transpose_tmp(make_backend, to_numpy):
+    """BasicSial.transpose_tmp (:653-693) + test_transpose_op.F: b[j,k,i] = a[i,j,k], 8 x 8 x 8, sequential from 53"""
+    w, _ = run("transpose_tmp", make_backend, ao=[8, 12, 10], constants={"norb": 3})
+    b = to_numpy(w.block_of("b", (1, 1, 1)))
+    a = oracle.fill_sequential((8, 8, 8), 53.0)
+    assert np.array_equal(b, np.transpose(a, (1, 2, 0)))
+
+
+def transpose4d_tmp(make_backend, to_numpy):
+    """BasicSial.transpose4d_tmp (:1285-1327) + test_transpose4d_op.F: b[k,j,i,l] = a[i,j,k,l]; moa {1, 5, 4}: occupied = segment 1
+    (one orbital), virtual = segment 2 (five): the block the test reads is b[2,1,2,1]"""
+    w, _ = run("transpose4d_tmp", make_backend, mo=[1, 5, 4], constants={"norb": 3, "baocc": 1, "eaocc": 1, "bavirt": 2, "eavirt": 2})
+    b = to_numpy(w.block_of("b", (1, 1, 1, 1)))          # (first virtual, first occupied, ...) = absolute segments (2, 1, 2, 1)
+    a = oracle.fill_sequential((5, 1, 5, 1), 53.0)
+    assert b.shape == (5, 1, 5, 1) and np.array_equal(b, np.transpose(a, (2, 1, 0, 3)))
+
+
+def transpose4d_square_tmp(make_backend, to_numpy):
+    """BasicSial.transpose4d_square_tmp (:1329-1406): 8^4 cyclic; esum1 = a*a, esum2 = b*b, esum3 = a[i,j,k,l]*b[k,j,i,l]"""
+    w, be = run("transpose4d_square_tmp", make_backend, ao=[8, 8, 8], constants={"norb": 3})
+    for k in ("esum1", "esum2", "esum3"):
+        assert be.value(w.scalars[k]) == 204 * 2870 + 1496 == 586976.0
+
+
+def contract_to_scalar(make_backend, to_numpy):
+    """BasicSial.contract_to_scalar (:1037-1084): x = a[i,j]*b[i,j], 8 x 8, a cyclic from 1, b cyclic from 5"""
+    w, be = run("contract_to_scalar", make_backend, ao=[8, 8], constants={"norb": 2})
+    assert be.value(w.scalars["x"]) == float(sum((((c % 20) + 1) * (((c + 4) % 20) + 1)) for c in range(64)))
+
+
+def sum_op(make_backend, to_numpy):
+    """BasicSial.sum_op (:817-916): d = a + c; e = d - c; 20 x 20, sequential from 100 / 50"""
+    w, _ = run("sum_op_test", make_backend, ao=[20, 5], constants={"norb": 2})
+    n = np.arange(400).reshape((20, 20), order="F")
+    assert np.array_equal(to_numpy(w.block_of("d", (1, 1))), 150.0 + 2 * n)
+    assert np.array_equal(to_numpy(w.block_of("e", (1, 1))), 100.0 + n)
+
+
+def self_multiply_test(make_backend, to_numpy):
+    """BasicSial.self_multiply_test (:1111-1160): a sequential from 100; a += a; a *= 1.5  ->  3 (100 + n)"""
+    w, _ = run("self_multiply_test", make_backend, ao=[20, 5], constants={"norb": 2})
+    n = np.arange(400).reshape((20, 20), order="F")
+    assert np.array_equal(to_numpy(w.block_of("a", (1, 1))), 3.0 * (100.0 + n))
+
+
+def put_test(make_backend, to_numpy):
+    """Sial.put_test (test_sial.cpp:282-318): put a[i,j] = k; get; x = a*a -> result[k] = k^2 seg_i seg_j"""
+    segs = [2, 3, 2]
+    w, _ = run("put_test", make_backend, ao=segs, constants={"norb": 3, "norb_squared": 9})
+    for i, j in itertools.product(range(3), repeat=2):
+        k = i * 3 + j + 1
+        assert to_numpy(w.block_of("result", (k,))).ravel()[0] == float(k * k * segs[i] * segs[j])
+
+
+def get_mpi(make_backend, to_numpy):
+    """Sial.get_mpi (:485-520): put b = a; put c = 0; put c += a twice; barrier; get; a = b + c = 126 in every element"""
+    segs = [2, 3, 4, 2]
+    w, _ = run("get_mpi", make_backend, ao=segs, constants={"norb": 4})
+    for i, j in itertools.product(range(1, 5), repeat=2):
+        blk = to_numpy(w.block_of("a", (i, j)))
+        assert blk.shape == (segs[i - 1], segs[j - 1]) and np.all(blk == 126.0)
+
+
+def put_accumulate_stress(make_backend, to_numpy):
+    """Sial.put_accumulate_stress (:1072-1113): pardo k = 1..20: put c[i,j] += a, += aa, += a, += aa with a = i, aa = j:
+    every element of c[i,j] = 20 (2 i + 2 j) -- many-writer accumulate correctness"""
+    segs = [2, 3, 2, 2]
+    w, _ = run("put_accumulate_stress", make_backend, ao=segs, constants={"norb": 4, "kmax": 20})
+    for i, j in itertools.product(range(1, 5), repeat=2):
+        blk = to_numpy(w.block_of("a", (i, j)))
+        assert blk.shape == (segs[i - 1], segs[j - 1]) and np.all(blk == 20.0 * (2 * i + 2 * j))
+
+
+def runs_to_completion(make_backend, to_numpy):
+    """BasicSial.tmp_arrays / tmp_arrays_2 / block_scale_assign (:526-650), Sial.put_accumulate_mpi: the reference compares printed
+    output; here: the programs run to completion through the same statements (block fill / scale / add / subtract / copy with
+    permutation, scalar-valued fills from index casts)"""
+    for name, ao, c in (("tmp_arrays", [2, 3, 4], {"norb": 3}), ("tmp_arrays_2", [2, 3, 4], {"norb": 3}),
+                        ("block_scale_assign", [2, 3, 4], {"norb": 3}), ("put_accumulate_mpi", [2, 3, 4, 2], {"norb": 4})):
+        run(name, make_backend, ao=ao, constants=c)
+
+
+ALL = (contraction_small_test, contraction_small_test2, transpose_tmp, transpose4d_tmp, transpose4d_square_tmp, contract_to_scalar,
+       sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, runs_to_completion)

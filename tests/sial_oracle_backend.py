@@ -50,6 +50,10 @@ class OracleBackend:
         b.a *= f
         self.calls += 1
 
+    def add_sub(self, d, l, r, sign):
+        d.a[...] = l.a + r.a if sign > 0 else l.a - r.a
+        self.calls += 1
+
     def increment(self, b, v):
         b.a += v
         self.calls += 1

@@ -70,6 +70,13 @@ def test_reference_cc_programs_device_test_bodies_on_the_fake_api(oracle):
     cc.test_reference_cis_and_cis_d_programs_on_the_device(FakeApi(oracle))
 
 
+def test_reference_unit_program_device_test_bodies_on_the_fake_api(oracle):
+    import ref_unit_programs as rp
+    import test_gpu_z_reference_unit_programs as up
+    for case in rp.ALL:
+        up.test_reference_unit_program_on_the_device(FakeApi(oracle), case, True)
+
+
 def test_cross_product_test_bodies_on_the_fake_api(oracle):
     """tests/test_gpu_z_cross_product.py at a block size the CPU finishes in seconds"""
     xp.test_full_cross_product_s16_against_the_oracle(FakeApi(oracle), oracle, s=3)

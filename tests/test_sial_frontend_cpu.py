@@ -82,8 +82,8 @@ def test_parser_reads_the_lccd_fragment():
     assert inner[2] == ("put", "t2new_ab", ("a", "i", "b", "j"), "+=", "taibj", ("a", "i", "b", "j"))
 
 
-@pytest.mark.parametrize("bad", ["pardo a\n  Taibj[a] = 1.0\n", "x[i] = y[i] + z[i]\n", "where a ** b\n",
-                                 "moaindex q = 1: 7\n", "enddo i\n", "prepare A[i] -= T[i]\n"])
+@pytest.mark.parametrize("bad", ["pardo a\n  Taibj[a] = 1.0\n", "x[i] = y[i] / z[i]\n", "where a ** b\n",
+                                 "moaindex q = 1 7\n", "enddo i\n", "prepare A[i] -= T[i]\n"])
 def test_parser_rejects_what_it_does_not_understand(bad):
     with pytest.raises(SialSyntaxError):
         Program(bad)
