@@ -237,8 +237,10 @@ class Program:
     def _parse(self, line, low, tok):
         kw = tok[0]
         if kw in ("sial", "endsial", "import", "print", "println", "create", "delete", "destroy", "special", "broadcast_from", "assert_same",
-                  "gpu_on", "gpu_off"):
+                  "gpu_on", "gpu_off", "gpu_put", "gpu_get", "gpu_allocate", "gpu_free"):
             return None           # arrays exist (zero) from the start; nothing is printed; super-instruction signatures are not
+                                  # needed; the gpu_* statements of the reference's dormant CUDA path (host <-> device moves of one
+                                  # block, interpreter.cpp:636-651) have nothing to do: every block is resident;
                                   # needed; broadcast_from / assert_same: every worker computes the replicated statics itself
         if kw == "predefined":
             if len(tok) < 3 or tok[1] not in ("int", "scalar"):
@@ -326,6 +328,9 @@ class Program:
             m = re.match(r"\w+\s+" + _REF + r"\s*\*=\s*(.+)$", line)
             if m:     # `prepare RB1_a[davidson,a,i] *= etemp`: the owner scales its block
                 return ("put_scale", m.group(1).lower(), _labels(m.group(2)), parse_expr(m.group(3)))
+            m = re.match(r"\w+\s+" + _REF + r"\s*(\+?=)\s*([^\[\]]+)$", line)
+            if m:     # `put a[i,j] = x` / `put a[i,j] += x` with a scalar: put_initialize / put_increment (sial_ops_parallel.cpp:412-528)
+                return ("put_value", m.group(1).lower(), _labels(m.group(2)), m.group(3), parse_expr(m.group(4)))
             m = re.match(r"\w+\s+" + _REF + r"\s*(\+?=)\s*" + _REF + r"\s*$", line)
             if not m:
                 raise SialSyntaxError("bad put/prepare")
@@ -995,6 +1000,13 @@ class Walker:
     def _x_put_scale(self, arr, alabs, e):
         self.be.put_scale(arr, self._array_segs(arr, alabs), self._shape(alabs), self._eval(e))
 
+    def _x_put_value(self, arr, alabs, op, e):
+        v = self._eval(e)
+        if op == "=":
+            self.be.put_initialize(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
+        else:
+            self.be.put_increment(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
+
     def _x_put_init(self, arr, alabs, v):
         self.be.put_initialize(arr, self._array_segs(arr, alabs), self._shape(alabs), v)
 
@@ -1283,6 +1295,9 @@ class DeviceBackend:
 
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr].put_initialize(segs, v)
+
+    def put_increment(self, arr, segs, shape, v):
+        self.arrays[arr].put_increment(segs, v)
 
     def put_scale(self, arr, segs, shape, f):
         """`prepare A[...] *= s`: the block is scaled where it lives (one writer per block and section, like `put`)"""

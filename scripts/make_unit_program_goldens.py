@@ -9,7 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/src/sialx/test/"
 NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "transpose4d_tmp", "transpose4d_square_tmp",
          "contract_to_scalar", "sum_op_test", "self_multiply_test", "put_test", "get_mpi", "put_accumulate_mpi",
-         "put_accumulate_stress", "tmp_arrays", "tmp_arrays_2", "block_scale_assign")
+         "put_accumulate_stress", "tmp_arrays", "tmp_arrays_2", "block_scale_assign",
+         # the programs of the reference's dormant CUDA path: the same operations between gpu_on / gpu_put / gpu_allocate / gpu_get /
+         # gpu_free / gpu_off statements
+         "gpu_contraction_small_test", "gpu_sum_op_test", "gpu_self_multiply_test", "gpu_transpose_tmp", "gpu_contract_to_scalar",
+         "gpu_ops", "put_initialize", "put_increment")
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
 for name in NAMES:
     text = open(SRC + name + ".sialx", errors="replace").read()

@@ -114,6 +114,9 @@ class FakeApi:
             def put_accumulate(self, idx, blk):
                 self.block_view(idx).accumulate(blk)
 
+            def put_increment(self, idx, d):
+                self.block_view(idx).increment(d)
+
             def put_scale(self, idx, f):
                 self.block_view(idx).scale(f)
 

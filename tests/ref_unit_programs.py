@@ -32,7 +32,8 @@ def _fill(kind):
 
 EXTRA_SI = {"fill_block_cyclic": _fill("cyclic"), "fill_block_sequential": _fill("sequential"),
             "list_blocks_with_number": lambda w, a, b: None, "list_block_map": lambda w, a, b: None,
-            "one_arg_no_op": lambda w, a, b: None}
+            "one_arg_no_op": lambda w, a, b: None, "enable_all_rank_print": lambda w, a, b: None,
+            "disable_all_rank_print": lambda w, a, b: None}
 
 
 def dim_segments(prog, label, seg_tables, constants):
@@ -161,6 +162,38 @@ def put_accumulate_stress(make_backend, to_numpy):
         assert blk.shape == (segs[i - 1], segs[j - 1]) and np.all(blk == 20.0 * (2 * i + 2 * j))
 
 
+def gpu_path_programs(make_backend, to_numpy):
+    """the programs of the reference's dormant CUDA path (src/sialx/test/gpu_*.sialx: the same operations between gpu_on / gpu_put /
+    gpu_allocate / gpu_get / gpu_free / gpu_off): the answers of their host twins"""
+    w, _ = run("gpu_contraction_small_test", make_backend, ao=[15, 15, 15, 15, 15, 15, 15, 15, 14, 14, 14, 14, 12, 12])
+    a, b = oracle.fill_cyclic((15,) * 4, 1.0), oracle.fill_cyclic((15, 15), 1.0)
+    assert np.array_equal(to_numpy(w.block_of("c", (1, 1))), np.einsum("ijkl,jk->il", a, b))
+    w, _ = run("gpu_transpose_tmp", make_backend, ao=[8, 12, 10], constants={"norb": 3})
+    assert np.array_equal(to_numpy(w.block_of("b", (1, 1, 1))), np.transpose(oracle.fill_sequential((8, 8, 8), 53.0), (1, 2, 0)))
+    w, be = run("gpu_contract_to_scalar", make_backend, ao=[8, 8], constants={"norb": 2})
+    assert be.value(w.scalars["x"]) == float(sum((((c % 20) + 1) * (((c + 4) % 20) + 1)) for c in range(64)))
+    n = np.arange(400).reshape((20, 20), order="F")
+    w, _ = run("gpu_self_multiply_test", make_backend, ao=[20, 5], constants={"norb": 2})
+    assert np.array_equal(to_numpy(w.block_of("a", (1, 1))), 3.0 * (100.0 + n))
+    w, _ = run("gpu_sum_op_test", make_backend, ao=[20, 5], constants={"norb": 2})
+    assert np.array_equal(to_numpy(w.block_of("a", (1, 1))), 100.0 + n) and np.array_equal(to_numpy(w.block_of("c", (1, 1))), 50.0 + n)
+    run("gpu_ops", make_backend, ao=[3, 4])
+
+
+def put_initialize_and_increment(make_backend, to_numpy):
+    """Sial.put_initialize / put_increment (test_sial.cpp:322-420): `put a[i,j] = x`, `put a[i,j] += x`, `put a[i,j] *= -1.0` with a scalar
+    (SialOpsParallel::put_initialize / put_increment / put_scale): result[k] = k^2 seg_i seg_j; every element of a[i,j] = -k"""
+    segs = [2, 3, 2]
+    w, _ = run("put_initialize", make_backend, ao=segs, constants={"norb": 3, "norb_squared": 9})
+    for i, j in itertools.product(range(3), repeat=2):
+        k = i * 3 + j + 1
+        assert to_numpy(w.block_of("result", (k,))).ravel()[0] == float(k * k * segs[i] * segs[j])
+    w, be = run("put_increment", make_backend, ao=segs, constants={"norb": 3, "norb_squared": 9})
+    for i, j in itertools.product(range(3), repeat=2):
+        blk = to_numpy(be.array_block("a", (i + 1, j + 1), (segs[i], segs[j])))
+        assert np.all(blk == -float(i * 3 + j + 1))
+
+
 def runs_to_completion(make_backend, to_numpy):
     """BasicSial.tmp_arrays / tmp_arrays_2 / block_scale_assign (:526-650), Sial.put_accumulate_mpi: the reference compares printed
     output; here: the programs run to completion through the same statements (block fill / scale / add / subtract / copy with
@@ -171,4 +204,5 @@ def runs_to_completion(make_backend, to_numpy):
 
 
 ALL = (contraction_small_test, contraction_small_test2, transpose_tmp, transpose4d_tmp, transpose4d_square_tmp, contract_to_scalar,
-       sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, runs_to_completion)
+       sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, put_initialize_and_increment, gpu_path_programs,
+       runs_to_completion)

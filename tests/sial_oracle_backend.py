@@ -91,6 +91,12 @@ class OracleBackend:
     def put_initialize(self, arr, segs, shape, v):
         self.arrays[arr][segs] = np.full(shape, float(v), order="F")
 
+    def put_increment(self, arr, segs, shape, v):
+        A = self.arrays[arr]
+        if segs not in A:
+            A[segs] = np.zeros(shape, order="F")
+        A[segs] = A[segs] + float(v)
+
     def put_scale(self, arr, segs, shape, f):
         A = self.arrays[arr]
         if segs not in A:
