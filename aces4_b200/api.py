@@ -133,6 +133,8 @@ def lib():
         L.sipgpu_array_get.argtypes = [C.c_void_p, c_int_p, C.c_void_p]
         L.sipgpu_array_put.argtypes = [C.c_void_p, c_int_p, C.c_void_p]
         L.sipgpu_array_put_accumulate.argtypes = [C.c_void_p, c_int_p, C.c_void_p]
+        L.sipgpu_array_get_many.argtypes = [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_void_p)]
+        L.sipgpu_array_put_accumulate_many.argtypes = [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_void_p)]
         L.sipgpu_array_fill_local.argtypes = [C.c_void_p, C.c_double]
         for name in ("put_initialize", "put_increment", "put_scale"):
             getattr(L, "sipgpu_array_" + name).argtypes = [C.c_void_p, c_int_p, C.c_double]
@@ -900,6 +902,20 @@ class DistArray:
 
     def put_accumulate(self, idx, blk):
         _check(lib().sipgpu_array_put_accumulate(self.h, _ia(idx), blk.ptr), "sipgpu_array_put_accumulate")
+
+    def section(self, idxs, blocks):
+        """marshalled arguments of get_many / put_accumulate_many (build once, reuse per section)"""
+        flat = [int(v) for ix in idxs for v in ix]
+        return len(idxs), (C.c_int * len(flat))(*flat), (C.c_void_p * len(blocks))(*[b.ptr for b in blocks])
+
+    def get_many(self, idxs=None, blocks=None, section=None):
+        """one barrier section's worth of gets as one launch"""
+        n, ia, pa = section or self.section(idxs, blocks)
+        _check(lib().sipgpu_array_get_many(self.h, n, ia, pa), "sipgpu_array_get_many")
+
+    def put_accumulate_many(self, idxs=None, blocks=None, section=None):
+        n, ia, pa = section or self.section(idxs, blocks)
+        _check(lib().sipgpu_array_put_accumulate_many(self.h, n, ia, pa), "sipgpu_array_put_accumulate_many")
 
     def put_initialize(self, idx, v):
         _check(lib().sipgpu_array_put_initialize(self.h, _ia(idx), float(v)), "sipgpu_array_put_initialize")

@@ -213,6 +213,34 @@ int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g
     if (wl_active()) return wl_rec_ew(WL_REDADD, dst, g_src, nullptr, sipgpu_array_block_size(a, idx), 1.0, a->world == 1);
     return ew_red_add(dst, g_src, sipgpu_array_block_size(a, idx));
 }
+// One barrier section's worth of get / put += in ONE call and ONE launch: the n blocks become n descriptors of the batched
+// elementwise kernel (16-byte peer loads for get, red.global.add.f64 into the owner's slab for put +=).  The reference
+// issues these one MPI message per block (sial_ops_parallel.cpp:132-171, 332-408); a pardo body that prefetches its section
+// (or a section's worth of accumulates at its end) maps onto this.  Inside an open recording the ops just join it.
+static int array_many(sipgpu_array* a, int n, const int* idx, double* const* blk, bool get) {
+    if (!a || n < 0 || (n > 0 && (!idx || !blk))) return SIPGPU_E_ARG;
+    if (n == 0) return SIPGPU_OK;
+    const bool own = !wl_active();
+    if (own) SIP_TRY(sipgpu_wl_begin(0));
+    int rc = SIPGPU_OK;
+    for (int i = 0; i < n && rc == SIPGPU_OK; ++i) {
+        const int* ix = idx + (size_t)i * a->rank;
+        rc = get ? sipgpu_array_get(a, ix, blk[i]) : sipgpu_array_put_accumulate(a, ix, blk[i]);
+    }
+    if (own) {
+        const int rc2 = sipgpu_wl_end();
+        if (rc == SIPGPU_OK) rc = rc2;
+    }
+    return rc;
+}
+int sipgpu_array_get_many(sipgpu_array* a, int n, const int* idx, double* const* g_dst) {
+    SIP_TRACE("sipgpu_array_get_many");
+    return array_many(a, n, idx, g_dst, true);
+}
+int sipgpu_array_put_accumulate_many(sipgpu_array* a, int n, const int* idx, const double* const* g_src) {
+    SIP_TRACE("sipgpu_array_put_accumulate_many");
+    return array_many(a, n, idx, const_cast<double* const*>(g_src), false);
+}
 // put_initialize / put_increment / put_scale (sial_ops_parallel.cpp:412-528): one scalar applied to one block at its
 // owner.  The reference sends {value, block id} to the server, which runs a serial loop; here the elementwise kernel
 // runs on the caller's stream directly on the owner's (possibly peer-mapped) block.  For the race detector they count

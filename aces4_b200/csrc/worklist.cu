@@ -328,7 +328,166 @@ __global__ void __launch_bounds__(kEwThreads) ew_batched_kernel(const EwDesc* __
     }
 }
 
+// ---- block copies as TMA bulk transfers -----------------------------------------------------------------------------
+// A section of `get`s (and every other whole-block copy of a level) is a list of contiguous runs.  One thread per CTA
+// drives them: cp.async.bulk global -> shared into a ring of 32 KB stages (completion on the stage's mbarrier), then
+// cp.async.bulk shared -> global out of it; the loads run kBulkAhead stages ahead of the stores, so ~128 KB per SM is in
+// flight towards the source -- which is what a peer slab behind NVLink needs (a warp of LDG.128 has 2 KB in flight and
+// stalls on each batch).  No registers, no LSU traffic; runs must be 16-byte aligned with an even element count.
+constexpr int kBulkStageElems = 4096, kBulkStages = 6, kBulkAhead = 4;
+constexpr int kBulkPiecesPerChunk = kEwChunk / kBulkStageElems;
+static_assert(kEwChunk % kBulkStageElems == 0, "a chunk is a whole number of stages");
+
+struct BulkCursor {   // walks the pieces of a CTA's range in order
+    const EwDesc* desc;
+    int ndesc, idx;
+    long long piece, first, next_first;   // pieces of desc[idx] start at `first`; desc[idx + 1]'s at `next_first`
+    __device__ void seek(const EwDesc* d, int n, long long p) {
+        desc = d; ndesc = n; piece = p;
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)d[mid].chunk0 * kBulkPiecesPerChunk <= p) lo = mid; else hi = mid - 1;
+        }
+        idx = lo;
+        load();
+    }
+    __device__ void load() {
+        first = (long long)desc[idx].chunk0 * kBulkPiecesPerChunk;
+        next_first = idx + 1 < ndesc ? (long long)desc[idx + 1].chunk0 * kBulkPiecesPerChunk : (1LL << 62);
+    }
+    __device__ bool reduce() const { return desc[idx].op == WL_REDADD; }
+    __device__ unsigned get(const double** src, double** dst) const {   // bytes of this piece (0: past the end of the run)
+        const long long base = (piece - first) * kBulkStageElems, left = desc[idx].n - base;
+        *src = desc[idx].a + base;
+        *dst = desc[idx].d + base;
+        return left <= 0 ? 0u : (unsigned)(8 * (left < kBulkStageElems ? left : kBulkStageElems));
+    }
+    __device__ void advance() {
+        if (++piece >= next_first) { ++idx; load(); }
+    }
+};
+
+__global__ void __launch_bounds__(32) copy_bulk_kernel(const EwDesc* __restrict__ desc, int ndesc, long long npieces) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ unsigned long long bar[kBulkStages];
+    if (threadIdx.x != 0) return;
+    const long long per = (npieces + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = p0 + per < npieces ? p0 + per : npieces;
+    if (p0 >= p1) return;
+    for (int s = 0; s < kBulkStages; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar + s)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    const int n = (int)(p1 - p0);
+    BulkCursor ld, st;
+    ld.seek(desc, ndesc, p0);
+    st = ld;
+    auto issue_load = [&](int it) {
+        const int s = it % kBulkStages;
+        const double* src; double* dst;
+        const unsigned bytes = ld.get(&src, &dst);
+        const unsigned b = (unsigned)__cvta_generic_to_shared(bar + s);
+        asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(b), "r"(bytes) : "memory");
+        if (bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(bulk_smem + (size_t)s * kBulkStageElems * 8)),
+                         "l"(src), "r"(bytes), "r"(b)
+                         : "memory");
+        ld.advance();
+    };
+    for (int it = 0; it < kBulkAhead && it < n; ++it) issue_load(it);
+    for (int it = 0; it < n; ++it) {
+        if (it + kBulkAhead < n) {
+            // the stage that load goes into was drained by the store of piece it + kBulkAhead - kBulkStages (two groups back)
+            asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(kBulkStages - kBulkAhead - 1) : "memory");
+            issue_load(it + kBulkAhead);
+        }
+        const int s = it % kBulkStages;
+        const unsigned b = (unsigned)__cvta_generic_to_shared(bar + s), parity = (unsigned)((it / kBulkStages) & 1);
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            " @!p bra W;\n}\n" ::"r"(b), "r"(parity)
+            : "memory");
+        const double* src; double* dst;
+        const unsigned bytes = st.get(&src, &dst);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        const unsigned sm = (unsigned)__cvta_generic_to_shared(bulk_smem + (size_t)s * kBulkStageElems * 8);
+        if (bytes && !st.reduce())
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(sm), "r"(bytes) : "memory");
+        else if (bytes)   // put +=: element-wise atomic adds performed at the owner's L2, one bulk transfer per stage
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(dst), "r"(sm), "r"(bytes)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        st.advance();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
+int g_copy_bulk = -1;   // -1: SIPGPU_COPY_BULK from the environment (default 3); bit 0: copies, bit 1: put += (bulk reduce)
+int copy_bulk_mode() {
+    if (g_copy_bulk < 0) {
+        const char* e = getenv("SIPGPU_COPY_BULK");
+        g_copy_bulk = e ? (atoi(e) & 3) : 3;
+    }
+    return g_copy_bulk;
+}
+bool bulk_copy_eligible(const Op& o, int mode) {
+    const bool copy = (mode & 1) && o.ewop == WL_SCALE_COPY && o.f == 1.0, red = (mode & 2) && o.ewop == WL_REDADD;
+    return (copy || red) && o.a && !o.b && o.dn >= 2 * kBulkStageElems && (o.dn & 1) == 0 &&
+           ((((uintptr_t)o.D | (uintptr_t)o.a) & 15) == 0);
+}
+
+int launch_bulk_copies(const std::vector<const Op*>& list) {
+    size_t k = 0;
+    static bool attr_set = false;
+    const int smem = kBulkStages * kBulkStageElems * 8;
+    if (!attr_set) {
+        SIP_CUDA(cudaFuncSetAttribute(copy_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    while (k < list.size()) {
+        std::vector<EwDesc> descs;
+        long long chunks = 0;
+        for (; k < list.size() && descs.size() < 32768 && chunks < (1 << 28); ++k) {
+            const Op& o = *list[k];
+            descs.push_back(EwDesc{o.D, o.a, nullptr, o.dn, 1.0, o.ewop, (int)chunks});
+            chunks += (o.dn + kEwChunk - 1) / kEwChunk;
+        }
+        void *h, *d;
+        SIP_TRY(desc_alloc(sizeof(EwDesc) * descs.size(), &h, &d));
+        memcpy(h, descs.data(), sizeof(EwDesc) * descs.size());
+        SIP_TRY(desc_commit(h, d, sizeof(EwDesc) * descs.size()));
+        const long long npieces = chunks * kBulkPiecesPerChunk;
+        const int grid = (int)std::min<long long>(npieces, (long long)ctx().num_sms);
+        const int nd = (int)descs.size();
+        auto go = [d, nd, npieces, grid, smem]() -> int {
+            copy_bulk_kernel<<<grid, 32, smem, ctx().stream>>>((const EwDesc*)d, nd, npieces);
+            SIP_CUDA(cudaGetLastError());
+            count_launch();
+            return SIPGPU_OK;
+        };
+        if (Capture* cap = capture()) {
+            cap->steps.push_back(go);
+        } else {
+            SIP_TRY(go());
+            g.st_launches++;
+        }
+    }
+    return SIPGPU_OK;
+}
+
+int launch_ew_batch_generic(const std::vector<const Op*>& list);
 int launch_ew_batch(const std::vector<const Op*>& list) {
+    const int mode = copy_bulk_mode();
+    if (!mode) return launch_ew_batch_generic(list);
+    std::vector<const Op*> bulk, rest;
+    for (const Op* o : list) (bulk_copy_eligible(*o, mode) ? bulk : rest).push_back(o);
+    if (!bulk.empty()) SIP_TRY(launch_bulk_copies(bulk));
+    return rest.empty() ? SIPGPU_OK : launch_ew_batch_generic(rest);
+}
+
+int launch_ew_batch_generic(const std::vector<const Op*>& list) {
     size_t k = 0;
     while (k < list.size()) {
         std::vector<EwDesc> descs;
@@ -839,6 +998,7 @@ void wl_replay_cache_clear() {
     g_replays.clear();
 }
 void wl_tuning_changed() { ++g_tuning_epoch; }
+void wl_set_copy_bulk(int mode) { g_copy_bulk = mode < 0 ? -1 : (mode & 3); }
 
 int wl_rec_ew(int op, double* d, const double* a, const double* b, long long n, double f, bool exclusive) {
     if (n < 0 || !d) return SIPGPU_E_ARG;

@@ -23,6 +23,7 @@ bool wl_dry();     // recording without a device (host-only planning, CPU tests)
 // Schedule and launch everything recorded so far; recording stays on.  Blocking entry points call this first.
 int wl_flush();
 void wl_replay_cache_clear();  // drops every captured stream (finalize; descriptors live in pool memory)
+void wl_set_copy_bulk(int on);  // whole-block copies as TMA bulk transfers (-1: environment / default on)
 void wl_tuning_changed();       // launch policy changed: captured streams of the old policy must not be replayed
 
 // exclusive: a WL_REDADD whose destination no other process can reach (single-rank array) -- the scheduler may turn it

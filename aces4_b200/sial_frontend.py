@@ -917,6 +917,9 @@ class Walker:
     def _x_restore_persistent(self, name, label):
         if self._is_table(name):
             self.tables[name] = dict(self.host_registry.pop(label))
+        elif self.p.arrays.get(name, ("",))[0] == "static" and label in self.host_registry:      # a static array a program filled itself
+            self.own_static[name] = self.host_registry.pop(label)
+            self._own_memo[name] = True
         elif name in self.p.scalars:
             self.scalars[name] = self.be.restore_scalar(label)
         elif self._is_remote(name):

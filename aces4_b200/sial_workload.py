@@ -240,6 +240,8 @@ class SyntheticCCSD:
     def store_t2new_to_host(self, h_slab_ptr):
         api._check(api.lib().sipgpu_d2h(h_slab_ptr, self.T2new.local_base(), self.T2new.local_bytes() // 8), "sipgpu_d2h")
 
+    _t2old_section = None
+
     def iterate(self):
         """One iteration; returns the (global) energy-like scalar.  All device work is asynchronous on the library's
         compute stream until the final scalar read-back.  The per-block traffic of a barrier section (get, put +=, the
@@ -249,9 +251,9 @@ class SyntheticCCSD:
         # (0) request T2old: fetch every block into the per-GPU replica (peer reads over NVLink when remote) -- one
         # gather launch for the whole section
         rep = self.arr["T2old"]
-        with api.recording():
-            for blk in self.blocks:
-                self.T2old.get(blk, out=rep.block_view(blk))
+        if self._t2old_section is None:      # marshalled once: the replica's block addresses do not change
+            self._t2old_section = self.T2old.section(self.blocks, [rep.block_view(blk) for blk in self.blocks])
+        self.T2old.get_many(section=self._t2old_section)
         # (1) W[c,k,a,i] = T2old[c,k,a,i] - T2old[c,i,a,k]   (rlccd_rhf.sialx:517-522): one slab copy, then one fused
         # permute-accumulate launch per block-shape class (W += -1 * T2old[c,i,a,k] permuted)
         W = self.arr["W"]

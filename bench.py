@@ -457,15 +457,14 @@ def main():
         nbytes_blk = 8.0 * int(np.prod(w.T2old.block_shape(peer_blocks[0])))
         tmp_blocks = [api.DeviceBlock(w.T2old.block_shape(b)) for b in peer_blocks]
 
-        def do_get():        # one section's worth of gets: recorded, so ONE gather launch over the peer-mapped slabs
-            with api.recording():
-                for b, t in zip(peer_blocks, tmp_blocks):
-                    w.T2old.get(b, out=t)
+        sec_get = w.T2old.section(peer_blocks, tmp_blocks)
+        sec_put = w.Xs.section(peer_blocks, tmp_blocks)
+
+        def do_get():        # one section's worth of gets in one C-ABI call: ONE gather launch over the peer-mapped slabs
+            w.T2old.get_many(section=sec_get)
 
         def do_put_acc():    # ONE red.global.add.f64 launch into the neighbour's slab
-            with api.recording():
-                for b, t in zip(peer_blocks, tmp_blocks):
-                    w.Xs.put_accumulate(b, t)
+            w.Xs.put_accumulate_many(section=sec_put)
 
         def do_get_eager():
             for b, t in zip(peer_blocks, tmp_blocks):
@@ -483,9 +482,10 @@ def main():
         nvlink = {"get_GBps_per_gpu": vol / (ms_get * 1e-3) / 1e9, "put_accumulate_GBps_per_gpu": vol / (ms_put * 1e-3) / 1e9,
                   "get_per_block_memcpy_GBps_per_gpu": vol / (ms_get_eager * 1e-3) / 1e9,
                   "blocks": len(peer_blocks), "block_bytes": nbytes_blk,
-                  "how": "one section of gets / put += towards rank+1 issued inside a recording: one descriptor-driven launch "
-                         "of 16-byte peer loads (get) / red.global.add.f64 into the owner's IPC-mapped slab (put +=); all "
-                         "ranks concurrently, max over ranks of the elapsed time; per_block_memcpy = the same gets as one "
+                  "how": "one section of gets / put += towards rank+1 through sipgpu_array_get_many / _put_accumulate_many: one descriptor-driven launch "
+                         "of TMA bulk transfers through a shared-memory ring: cp.async.bulk from the owner's IPC-mapped slab (get) / "
+                         "cp.reduce.async.bulk add.f64 into it (put +=); all ranks concurrently (two-way traffic: the wire's ceiling "
+                         "with 128 B packets is 686 / 720 GB/s, profiles/r02_nvlink_counters.txt), max over ranks of the elapsed time; per_block_memcpy = the same gets as one "
                          "cudaMemcpyAsync per block"}
         del tmp_blocks
 

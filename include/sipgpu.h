@@ -353,6 +353,9 @@ double* sipgpu_array_block_ptr(sipgpu_array* a, const int* idx);
 int sipgpu_array_get(sipgpu_array* a, const int* idx, double* g_dst);            /* SialOpsParallel::get            */
 int sipgpu_array_put(sipgpu_array* a, const int* idx, const double* g_src);      /* ::put_replace                   */
 int sipgpu_array_put_accumulate(sipgpu_array* a, const int* idx, const double* g_src); /* ::put_accumulate (atomic)  */
+/* a barrier section's worth of get / put += as ONE launch: idx = n x rank segment numbers, one block pointer per entry */
+int sipgpu_array_get_many(sipgpu_array* a, int n, const int* idx, double* const* g_dst);
+int sipgpu_array_put_accumulate_many(sipgpu_array* a, int n, const int* idx, const double* const* g_src);
 int sipgpu_array_put_initialize(sipgpu_array* a, const int* idx, double value);  /* ::put_initialize :412-446, block = v */
 int sipgpu_array_put_increment(sipgpu_array* a, const int* idx, double delta);   /* ::put_increment  :448-487, block += d */
 int sipgpu_array_put_scale(sipgpu_array* a, const int* idx, double factor);      /* ::put_scale      :489-528, block *= f */

@@ -13,7 +13,10 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          # the programs of the reference's dormant CUDA path: the same operations between gpu_on / gpu_put / gpu_allocate / gpu_get /
          # gpu_free / gpu_off statements
          "gpu_contraction_small_test", "gpu_sum_op_test", "gpu_self_multiply_test", "gpu_transpose_tmp", "gpu_contract_to_scalar",
-         "gpu_ops", "put_initialize", "put_increment")
+         "gpu_ops", "put_initialize", "put_increment",
+         # persistence between consecutive programs
+         "persistent_distributed_array_mpi1", "persistent_distributed_array_mpi2", "persistent_scalars_1", "persistent_scalars_2",
+         "persistent_static_array_test1", "persistent_static_array_test2")
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
 for name in NAMES:
     text = open(SRC + name + ".sialx", errors="replace").read()

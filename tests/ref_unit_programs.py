@@ -52,9 +52,9 @@ def dim_segments(prog, label, seg_tables, constants):
     return list(seg_tables["mo"][val(lo) - 1: val(hi)])
 
 
-def run(name, make_backend, ao=None, mo=None, constants=None, arrays=()):
+def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend=None):
     prog = Program(text(name))
-    be = make_backend(prog, {"ao": ao or [], "mo": mo or []}, constants or {})
+    be = backend or make_backend(prog, {"ao": ao or [], "mo": mo or []}, constants or {})
     segs = {"ao": list(ao or []), "pa": list(mo or [])}
     c = dict(constants or {})
     if mo and "baocc" in c:
@@ -194,6 +194,28 @@ def put_initialize_and_increment(make_backend, to_numpy):
         assert np.all(blk == -float(i * 3 + j + 1))
 
 
+def persistence_between_programs(make_backend, to_numpy):
+    """Sial.persistent_distributed_array_mpi (test_sial.cpp:640-700): program 1 fills b (put) and c (put += twice) and persists them, program 2
+    restores them: a = b + c = 3 x (sequential values from (i-1) norb + j); BasicSial.persistent_static_array_test and
+    persistent_scalars (test_basic_sial.cpp): a static array the first program filled and a scalar, restored by the second"""
+    segs = [2, 3]
+    run("persistent_distributed_array_mpi1", make_backend, ao=segs, constants={"norb": 2})
+    w, _ = run("persistent_distributed_array_mpi2", make_backend, ao=segs, constants={"norb": 2})
+    for i, j in itertools.product((1, 2), repeat=2):
+        blk = to_numpy(w.block_of("a", (i, j)))
+        first = (i - 1) * 2 + j
+        assert np.array_equal(blk.ravel(order="F"), 3.0 * (first + np.arange(blk.size)))
+        assert np.array_equal(to_numpy(w.block_of("lb", (i, j))).ravel(order="F"), 1.0 * (first + np.arange(blk.size)))
+    run("persistent_static_array_test1", make_backend, ao=segs, constants={"norb": 2})
+    w, _ = run("persistent_static_array_test2", make_backend, ao=segs, constants={"norb": 2})
+    for i, j in itertools.product((1, 2), repeat=2):
+        blk = to_numpy(w.block_of("lb", (i, j)))
+        assert np.array_equal(blk.ravel(order="F"), 1.0 + np.arange(blk.size))
+    run("persistent_scalars_1", make_backend, constants={"x": 3.456, "y": -0.1})
+    w, be = run("persistent_scalars_2", make_backend, constants={"y": -0.1})
+    assert be.value(w.scalars["e"]) == 6.0 and abs(be.value(w.scalars["x"]) - 4.456) < 1e-15
+
+
 def runs_to_completion(make_backend, to_numpy):
     """BasicSial.tmp_arrays / tmp_arrays_2 / block_scale_assign (:526-650), Sial.put_accumulate_mpi: the reference compares printed
     output; here: the programs run to completion through the same statements (block fill / scale / add / subtract / copy with
@@ -205,4 +227,4 @@ def runs_to_completion(make_backend, to_numpy):
 
 ALL = (contraction_small_test, contraction_small_test2, transpose_tmp, transpose4d_tmp, transpose4d_square_tmp, contract_to_scalar,
        sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, put_initialize_and_increment, gpu_path_programs,
-       runs_to_completion)
+       persistence_between_programs, runs_to_completion)

@@ -96,6 +96,18 @@ def _worker(rank, world, port, q):
                 assert np.all(got == expect[k]), (rank, recorded, idx, got.ravel()[:3], expect[k])
             dist.barrier()
             A.section_reset()
+        # one section's worth of put += and of gets in one call each (sipgpu_array_put_accumulate_many / _get_many: one launch)
+        srcs = [api.DeviceBlock(A.block_shape(idx)).fill(1.0 + k) for k, idx in enumerate(blocks)]
+        A.put_accumulate_many(blocks, srcs)
+        api.sync()
+        dist.barrier()
+        outs = [api.DeviceBlock(A.block_shape(idx)) for idx in blocks]
+        A.get_many(blocks, outs)
+        api.sync()
+        for k, o in enumerate(outs):
+            assert np.all(o.to_numpy() == expect[k] + 2 * (1.0 + k)), (rank, k)
+        dist.barrier()
+        A.section_reset()
         # create -> first remote put with no barrier in between: the owner's zero fill must already have landed
         B = api.DistArray([[64, 64], [64]], rank, world, exchange)
         for idx in ((1, 1), (2, 1)):

@@ -331,3 +331,34 @@ def test_repeated_stream_is_replayed_not_rescheduled(sip, oracle):
             replays.append(sip.wl_replays())
         assert rel(dest.to_numpy(), want) <= TOL, it
     assert replays[0] == 0 and replays[2] == 1 and replays[3] == 1 and replays[last] == 0, replays
+
+
+@pytest.mark.parametrize("mode", [0, 3], ids=["ldg_red", "tma_bulk"])
+def test_section_of_gets_and_accumulates_in_one_call(sip, mode):
+    """sipgpu_array_get_many / _put_accumulate_many: a barrier section's worth of block traffic as one launch.  With
+    copy_bulk = 3 whole blocks travel as TMA bulk transfers (cp.async.bulk into a shared-memory ring and out again;
+    put += as cp.reduce.async.bulk add.f64), with 0 as LDG.128 / red.global.add.f64.  Run lengths straddle the 32 KB
+    stages (one element short, odd counts and runs under the 64 KB minimum fall back to the register kernel)."""
+    sizes = [8192, 8194, 8191, 12290, 4096, 20482, 40960, 3, 65536 + 2, 16384]
+    a = sip.DistArray([sizes])
+    rng = np.random.default_rng(5)
+    want = [rng.standard_normal(n) for n in sizes]
+    blocks = [(k + 1,) for k in range(len(sizes))]
+    sip.set_tuning("copy_bulk", mode)
+    try:
+        for b, wv in zip(blocks, want):
+            a.put(b, sip.DeviceBlock.from_numpy(wv))
+        outs = [sip.DeviceBlock((n,)) for n in sizes]
+        l0 = sip.kernel_launches()
+        a.get_many(blocks, outs)
+        assert 1 <= sip.kernel_launches() - l0 <= 2          # bulk-eligible runs + the rest
+        for o, wv in zip(outs, want):
+            assert np.array_equal(o.to_numpy().ravel(), wv)
+        adds = [sip.DeviceBlock.from_numpy(np.full(n, 0.5 + k)) for k, n in enumerate(sizes)]
+        a.put_accumulate_many(blocks, adds)
+        a.put_accumulate_many(blocks, adds)
+        for k, (b, wv) in enumerate(zip(blocks, want)):
+            assert np.array_equal(a.get(b).to_numpy().ravel(), (wv + (0.5 + k)) + (0.5 + k))
+    finally:
+        sip.set_tuning("copy_bulk", -1)
+        a.destroy()
