@@ -137,7 +137,9 @@ int build_shape_strided(const int* ptrn, int lrank, const int* lext, const int* 
     }
     // Order of the contracted group is free (any order consistent between L and R gives the same sums up to
     // rounding).  Put the stride-1 dimension of an operand first so that its K-runs are contiguous: R's if R's
-    // fastest (non-unit) dimension is contracted, else L's.  m and n groups already ascend in L / R stride.
+    // fastest (non-unit) dimension is contracted, else L's; when BOTH operands have a contracted fastest dimension and
+    // their orders disagree (D[a,b] = L[c,d,b,a]*R[d,c]: a matrix-vector product whose big operand would be read with a
+    // stride of one segment), the order of the larger operand wins.  m and n groups already ascend in L / R stride.
     auto min_stride = [](const Dim* d, int n, bool second) {
         int best = INT32_MAX;
         for (int i = 0; i < n; ++i)
@@ -147,7 +149,8 @@ int build_shape_strided(const int* ptrn, int lrank, const int* lext, const int* 
     const int kminL = min_stride(kd, nk, false), kminR = min_stride(kd, nk, true);
     const int mminL = min_stride(md, nm, false), nminR = min_stride(nd, nn, false);
     const bool r_k_fast = kminR < nminR, l_k_fast = kminL < mminL;
-    if (!r_k_fast && l_k_fast)
+    static const bool by_size = [] { const char* e = getenv("SIPGPU_KORDER_BY_SIZE"); return !e || atoi(e) != 0; }();
+    if (l_k_fast && (!r_k_fast || (by_size && M > N)))
         std::stable_sort(kd, kd + nk, [](const Dim& a, const Dim& b) { return a.s0 < b.s0; });
     nm = tidy(md, nm);
     nn = tidy(nd, nn);

@@ -43,6 +43,8 @@ rows = []
 for d, l, r, kinds, where in sial_patterns():
     if not d:
         continue  # scalar-valued contractions are dot products (elementwise.cu), not this kernel
+    if os.environ.get("SWEEP_RANKS") and f"{len(d)}{len(l)}{len(r)}" not in os.environ["SWEEP_RANKS"].split(","):
+        continue
     labs = []
     for c in d + l + r:
         if c not in labs:
