@@ -1165,6 +1165,7 @@ int sipgpu_set_tuning(const char* key, double value) {
     if (!strcmp(key, "permute_bulk")) { permute_set_bulk((int)value); wl_tuning_changed(); return SIPGPU_OK; }
     if (!strcmp(key, "copy_bulk")) { wl_set_copy_bulk((int)value); wl_tuning_changed(); return SIPGPU_OK; }
     if (!strcmp(key, "permute_vec")) { permute_set_vec((int)value); wl_tuning_changed(); return SIPGPU_OK; }
+    if (!strcmp(key, "lowint_slab")) { lowint_set_slab((int)value); wl_tuning_changed(); return SIPGPU_OK; }
     if (!strcmp(key, "lowint_scope")) { lowint_set_scope((int)value); wl_tuning_changed(); return SIPGPU_OK; }
     set_error("sipgpu_set_tuning: unknown key '%s'", key);
     return SIPGPU_E_ARG;

@@ -46,6 +46,7 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
                   double alpha, double beta, bool dense_d);
 void lowint_cache_clear();
 void lowint_set_max_intensity(double flops_per_byte);  // negative: the kernel is never chosen
+void lowint_set_slab(int on);   // TMA-fed slab path for small results of long contractions (default on)
 void lowint_set_scope(int scope);  // 0 never, 1 where it wins (default), 2 every shape with N <= 64 below the intensity limit
 
 }  // namespace sipgpu

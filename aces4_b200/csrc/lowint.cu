@@ -400,6 +400,211 @@ __global__ void __launch_bounds__(kDotT) dotk_kernel(const __grid_constant__ Dot
     }
 }
 
+// ---- slab path: small result, long contracted range, operands that arrive as CONTIGUOUS SLABS ----------------------------
+// D[a,b] = L[a,c,d,e] * R[b,c,d,e] and its relatives (rank-2 results of rank-4 blocks, M, N <= 64, K = 10^4..10^5) sit on the
+// ridge of the roofline: the kernel above spends ~90 instructions per cp.async on table-driven gathers (ncu: 20 instructions
+// per DMMA, `wait` + `selected` stalls, DMMA pipe 36 %).  When a chunk of KC values of ONE contracted dimension q, taken
+// together with all the free dimensions, is a handful of contiguous runs in BOTH operands (L[a,c | d,e]: 50 x 20 doubles in
+// one run), the chunk is moved by TMA: one cp.async.bulk per run (<= 32 runs, one per lane of warp 0) into a ring of stages,
+// completion on the stage's mbarrier -- the staged layout IS the memory layout, the fragment loads address it through a
+// per-row offset kept in registers and a constant k stride.  No table look-ups and no address arithmetic in the loop:
+// 4 LDS-sized loads + the DMMAs.  Small tiles (<= 3 x 7 fragments) give every warp the whole tile and a quarter of the k
+// steps (reduced through shared memory in a fixed order at the end of an item); larger ones split N over the warps.
+constexpr int kSlabMaxRuns = 32, kSlabMaxStages = 6;
+struct SlabArgs {
+    const LowProb* probs;
+    const Pair* pairs;
+    const int2* mtab;   // .y = offset in D of row m
+    const int2* ntab;   // .y = offset in D of column n
+    const int2* ctab;   // [cpp] {offset in L, offset in R} of a chunk
+    int nprob, M, N, KC, cpp, nslice, atomic, stages;
+    int a_sk, b_sk;            // stride of k inside a staged operand
+    int a_elems, stage_elems;  // doubles (both even)
+    int a_nruns, b_nruns, a_runlen, b_runlen;
+    int a_run[kSlabMaxRuns], b_run[kSlabMaxRuns];  // offset of run r inside the chunk of the operand (elements)
+    short a_moff[64], b_noff[64];                  // staged offset of row m / column n (0 beyond M / N)
+    double alpha, beta;
+    LowProb p0;
+    Pair pair0;
+};
+
+struct SlabCursor {
+    int w, c, c_end, pair, kc;
+    double* D;
+};
+__device__ __forceinline__ void slab_cursor_load(SlabCursor& q, const SlabArgs& a, int w, int nwork) {
+    for (;; w += gridDim.x) {
+        q.w = w;
+        if (w >= nwork) { q.c = q.c_end = 0; return; }
+        const int s = w % a.nslice, p = w / a.nslice;
+        LowProb pr;
+        if (a.probs) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.probs + p));
+            memcpy(&pr, &raw, sizeof(pr));
+        } else {
+            pr = a.p0;
+        }
+        const long long T = (long long)pr.pair_len * a.cpp;
+        q.c = (int)(s * T / a.nslice);
+        q.c_end = (int)((s + 1) * T / a.nslice);
+        const int pr0 = q.c / a.cpp;
+        q.kc = q.c - pr0 * a.cpp;
+        q.pair = pr.pair_begin + pr0;
+        q.D = pr.D;
+        if (q.c < q.c_end) return;
+    }
+}
+__device__ __forceinline__ void slab_cursor_next(SlabCursor& q, const SlabArgs& a) {
+    ++q.c;
+    if (++q.kc == a.cpp) { q.kc = 0; ++q.pair; }
+}
+
+template <int MF, int NF, bool KSPLIT>
+__global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ unsigned long long full[kSlabMaxStages];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int ncol0 = KSPLIT ? 0 : warp * NF * 8;
+    const int nwork = a.nprob * a.nslice;
+    double* red = sm + (size_t)a.stages * a.stage_elems;   // KSPLIT: MF * NF * 64 doubles for the reduction over the warps
+    int moff[MF], noff[NF];
+#pragma unroll
+    for (int i = 0; i < MF; ++i) moff[i] = a.a_moff[8 * i + g];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) noff[j] = a.a_elems + a.b_noff[ncol0 + 8 * j + g];
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(full + s)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    SlabCursor pf, cp;
+    slab_cursor_load(cp, a, blockIdx.x, nwork);
+    pf = cp;
+    const unsigned stage_bytes = 8u * (unsigned)(a.a_nruns * a.a_runlen + a.b_nruns * a.b_runlen);
+    auto issue = [&](int stage) {   // warp 0: the chunk at the prefetch cursor -> stage; then the cursor moves on
+        if (pf.w >= nwork) return;
+        Pair pq;
+        if (a.probs) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.pairs + pf.pair));
+            memcpy(&pq, &raw, sizeof(pq));
+        } else {
+            pq = a.pair0;
+        }
+        const int2 co = __ldg(a.ctab + pf.kc);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(full + stage);
+        if (lane == 0) asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(stage_bytes) : "memory");
+        __syncwarp();
+        double* st = sm + (size_t)stage * a.stage_elems;
+        if (lane < a.a_nruns)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(st + lane * a.a_runlen)),
+                         "l"(pq.L + co.x + a.a_run[lane]), "r"(8u * (unsigned)a.a_runlen), "r"(bar)
+                         : "memory");
+        if (lane < a.b_nruns)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(st + a.a_elems + lane * a.b_runlen)),
+                         "l"(pq.R + co.y + a.b_run[lane]), "r"(8u * (unsigned)a.b_runlen), "r"(bar)
+                         : "memory");
+        slab_cursor_next(pf, a);
+        if (pf.c == pf.c_end) slab_cursor_load(pf, a, pf.w + gridDim.x, nwork);
+    };
+    if (warp == 0)
+        for (int s = 0; s < a.stages; ++s) issue(s);
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nks = (a.KC + 3) >> 2;
+    const bool unit_alpha = a.alpha == 1.0;
+    int stage = 0;
+    unsigned parity = 0;
+    int rot = warp;   // KSPLIT: the k steps are dealt round-robin over the warps, continuing across chunks
+    while (cp.w < nwork) {
+        {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(full + stage);
+            asm volatile(
+                "{\n .reg .pred p;\n"
+                "WS: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                " @!p bra WS;\n}\n" ::"r"(bar), "r"(parity)
+                : "memory");
+        }
+        const double* st = sm + (size_t)stage * a.stage_elems;
+        for (int ks = KSPLIT ? rot : 0; ks < nks; ks += KSPLIT ? 4 : 1) {
+            const int k = 4 * ks + t4;
+            const bool kv = k < a.KC;
+            const double* Ap = st + k * a.a_sk;
+            const double* Bp = st + k * a.b_sk;
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) af[i] = kv ? Ap[moff[i]] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NF; ++j) bf[j] = kv ? Bp[noff[j]] : 0.0;
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (KSPLIT) rot = (rot + 4 - (nks & 3)) & 3;
+        slab_cursor_next(cp, a);
+        const bool item_done = cp.c == cp.c_end;
+        __syncthreads();   // every warp is done with the stage
+        if (warp == 0) issue(stage);
+        if (++stage == a.stages) { stage = 0; parity ^= 1; }
+        if (!item_done) continue;
+        // ---- end of the item: (KSPLIT: sum the four warps' partial tiles in a fixed order) and write D ----
+        if (KSPLIT) {
+            for (int w = 1; w < 4; ++w) {
+                if (warp == w) {
+#pragma unroll
+                    for (int i = 0; i < MF; ++i)
+#pragma unroll
+                        for (int j = 0; j < NF; ++j)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                double* r = red + ((i * NF + j) * 2 + c) * 32 + lane;
+                                *r = w == 1 ? acc[i][j][c] : *r + acc[i][j][c];
+                            }
+                }
+                __syncthreads();
+            }
+        }
+        if (!KSPLIT || warp == 0) {
+            double* __restrict__ Dp = cp.D;
+#pragma unroll
+            for (int i = 0; i < MF; ++i) {
+                const int row = 8 * i + g;
+                const int mo = row < a.M ? __ldg(&a.mtab[row].y) : -1;
+#pragma unroll
+                for (int j = 0; j < NF; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = ncol0 + 8 * j + 2 * t4 + c;
+                        const int no = col < a.N ? __ldg(&a.ntab[col].y) : -1;
+                        if ((mo | no) < 0) continue;
+                        double v = acc[i][j][c];
+                        if (KSPLIT) v += red[((i * NF + j) * 2 + c) * 32 + lane];
+                        if (!unit_alpha) v *= a.alpha;
+                        double* dst = Dp + (size_t)(mo + no);
+                        if (a.atomic) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+                        else if (a.beta == 0.0) *dst = v;
+                        else *dst = v + a.beta * *dst;
+                    }
+            }
+        }
+        if (KSPLIT) __syncthreads();   // the reduction buffer is free again
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+            for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        slab_cursor_load(cp, a, cp.w + gridDim.x, nwork);
+    }
+}
+
 // ---- host: offset tables per shape, cached on the device ----
 struct Tables {
     int2 *mtab = nullptr, *ntab = nullptr, *ktab = nullptr;
@@ -502,9 +707,248 @@ int launch_low(LowArgs& a, size_t smem, long long nwork0, bool may_split, long l
     return go();
 }
 
+
+// ---- slab path, host side ----
+struct SlabPlan {
+    bool ok = false;
+    int q = -1, KC = 0, cpp = 0;
+    int a_sk = 0, b_sk = 0, a_elems = 0, b_elems = 0;
+    int a_nruns = 0, b_nruns = 0, a_runlen = 0, b_runlen = 0;
+    int a_run[kSlabMaxRuns], b_run[kSlabMaxRuns];
+    short a_moff[64], b_noff[64];
+    int2* ctab = nullptr;   // device
+};
+struct SlabDim {
+    int ext, gs;   // extent inside a chunk, stride in the operand
+    int kind;      // 0: free dimension i of the group, 1: the contracted dimension q
+    int idx;
+    int cs;        // compact (staged) stride
+};
+// one operand's view of a chunk: `nf` free dimensions (ext, stride) + KC values of a contracted dimension of stride qs and
+// full extent qext.  Runs = the leading dimensions (in memory order) that are complete; everything else enumerates runs.
+bool slab_operand(int nf, const int* fext, const int* fs, int qs, int qext, int KC, int X, int* runlen, int* nruns, int* run,
+                  int* sk, short* xoff, int* elems) {
+    SlabDim d[kMaxRank + 1];
+    int n = 0;
+    for (int i = 0; i < nf; ++i) d[n++] = SlabDim{fext[i], fs[i], 0, i, 0};
+    d[n++] = SlabDim{KC, qs, 1, 0, 0};
+    for (int i = 1; i < n; ++i)   // by memory stride (a handful of entries)
+        for (int j = i; j > 0 && d[j].gs < d[j - 1].gs; --j) std::swap(d[j], d[j - 1]);
+    long long cs = 1;
+    for (int i = 0; i < n; ++i) { d[i].cs = (int)cs; cs *= d[i].ext; }
+    if (cs > 32767) return false;   // staged offsets are shorts
+    *elems = (int)cs;
+    // the run: leading dimensions whose memory stride equals the staged stride (nothing of the block lies between)
+    long long rl = 1;
+    int lead = 0;
+    for (; lead < n; ++lead) {
+        if (d[lead].gs != d[lead].cs) break;
+        rl *= d[lead].ext;
+        if (d[lead].kind == 1 && KC != qext) { ++lead; break; }   // a partial contracted dimension ends the run
+    }
+    if (lead == 0 || (rl & 1) || rl < 128) return false;           // 16-byte granules; runs of at least 1 KB (a 400-byte bulk
+                                                                   // copy costs the TMA unit as much as an 8 KB one: measured 2x slower)
+    long long nr = 1;
+    for (int i = lead; i < n; ++i) nr *= d[i].ext;
+    if (nr > kSlabMaxRuns) return false;
+    *runlen = (int)rl;
+    *nruns = (int)nr;
+    for (int r = 0; r < (int)nr; ++r) {   // run r: the non-leading dimensions counted in staged order
+        int lin = r, off = 0;
+        for (int i = lead; i < n; ++i) { off += (lin % d[i].ext) * d[i].gs; lin /= d[i].ext; }
+        run[r] = off;
+        if (off & 1) return false;        // 16-byte aligned sources
+    }
+    for (int i = 0; i < n; ++i)
+        if (d[i].kind == 1) *sk = d[i].cs;
+    for (int x = 0; x < 64; ++x) {
+        int off = 0;
+        if (x < X) {
+            int lin = x;
+            for (int i = 0; i < nf; ++i) {   // x enumerates the free group in the Shape's order
+                const int r = lin % fext[i];
+                lin /= fext[i];
+                for (int j = 0; j < n; ++j)
+                    if (d[j].kind == 0 && d[j].idx == i) off += r * d[j].cs;
+            }
+        }
+        xoff[x] = (short)off;
+    }
+    return true;
+}
+
+std::unordered_map<std::string, SlabPlan>& slab_cache() {
+    static std::unordered_map<std::string, SlabPlan> c;
+    return c;
+}
+
+int& slab_mode() {
+    static int v = [] { const char* e = getenv("SIPGPU_LOWINT_SLAB"); return e ? atoi(e) : 1; }();
+    return v;
+}
+
+// menu of warp arrangements: KSPLIT (every warp the whole tile, a quarter of the k steps) and N split over the 4 warps
+struct SlabVariant { int mf, nf; bool ksplit; };
+const SlabVariant kSlabMenu[] = {{2, 2, true}, {3, 3, true}, {4, 4, true}, {3, 7, true}, {7, 3, true},
+                                 {5, 2, false}, {6, 2, false}, {7, 2, false}, {8, 2, false}};
+const SlabVariant* slab_variant(int M, int N) {
+    const int mf = (M + 7) / 8, nf = (N + 7) / 8;
+    const SlabVariant* best = nullptr;
+    double best_cost = 1e30;
+    for (const SlabVariant& v : kSlabMenu) {
+        const bool covers = v.ksplit ? (v.mf >= mf && v.nf >= nf) : (v.mf >= mf && 4 * v.nf >= nf);
+        if (!covers) continue;
+        const double cost = v.ksplit ? v.mf * v.nf / 4.0 : v.mf * v.nf;
+        if (cost < best_cost) { best_cost = cost; best = &v; }
+    }
+    return best;
+}
+
+// the plan of a shape (cached): which contracted dimension is chunked and how; ok = false: not a slab shape
+const SlabPlan& slab_plan(const Shape& s) {
+    std::string key(reinterpret_cast<const char*>(&s), offsetof(Shape, a_kc));
+    auto it = slab_cache().find(key);
+    if (it != slab_cache().end()) return it->second;
+    SlabPlan best;
+    long long best_score = -1;
+    if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= 1024 && slab_variant(s.M, s.N)) {
+        const long long perk = 8LL * (s.M + s.N);
+        for (int q = 0; q < s.nk; ++q) {
+            for (int KC = std::min(s.kext[q], 128); KC >= 8; --KC) {
+                if (s.kext[q] % KC) continue;
+                if (perk * KC > 40 * 1024) continue;
+                SlabPlan p;
+                p.q = q; p.KC = KC;
+                if (!slab_operand(s.nm, s.mext, s.msL, s.ksL[q], s.kext[q], KC, s.M, &p.a_runlen, &p.a_nruns, p.a_run, &p.a_sk, p.a_moff, &p.a_elems)) continue;
+                if (!slab_operand(s.nn, s.next, s.nsR, s.ksR[q], s.kext[q], KC, s.N, &p.b_runlen, &p.b_nruns, p.b_run, &p.b_sk, p.b_noff, &p.b_elems)) continue;
+                // prefer long runs, then long chunks (fewer barriers per byte), then few wasted k steps
+                const long long score = (long long)std::min(std::min(p.a_runlen, p.b_runlen), 512) * 1000000 + (long long)std::min(perk * KC, 24LL * 1024) * 10 + (KC % 4 == 0 ? 1 : 0);
+                if (score > best_score) { best_score = score; best = p; best.ok = true; }
+            }
+        }
+    }
+    if (best.ok) {
+        best.cpp = s.K / best.KC;
+        std::vector<int2> h((size_t)best.cpp);
+        // chunk c: sub-range j of dimension q fastest, then the other contracted dimensions in the Shape's order
+        const int nj = s.kext[best.q] / best.KC;
+        for (int c = 0; c < best.cpp; ++c) {
+            int lin = c;
+            const int j = lin % nj;
+            lin /= nj;
+            int oL = j * best.KC * s.ksL[best.q], oR = j * best.KC * s.ksR[best.q];
+            for (int i = 0; i < s.nk; ++i) {
+                if (i == best.q) continue;
+                const int r = lin % s.kext[i];
+                lin /= s.kext[i];
+                oL += r * s.ksL[i];
+                oR += r * s.ksR[i];
+            }
+            if ((oL | oR) & 1) { best.ok = false; break; }
+            h[c] = make_int2(oL, oR);
+        }
+        if (best.ok) {
+            best.ctab = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * h.size(), true));
+            if (!best.ctab) best.ok = false;
+            else if (cudaMemcpyAsync(best.ctab, h.data(), sizeof(int2) * h.size(), cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess ||
+                     cudaStreamSynchronize(ctx().stream) != cudaSuccess) best.ok = false;
+        }
+    }
+    return slab_cache().emplace(key, best).first->second;
+}
+
+template <int MF, int NF, bool KSPLIT>
+int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total_chunks, const std::function<int()>& prescale) {
+    auto* kern = slab_kernel<MF, NF, KSPLIT>;
+    static bool attr = false;
+    if (!attr) {
+        SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr = true;
+    }
+    const size_t red_bytes = KSPLIT ? (size_t)MF * NF * 64 * 8 : 0;
+    // ring depth: two CTAs per SM when the stages are small (<= 96 KB per CTA), else one
+    int stages = (int)std::min<size_t>(kSlabMaxStages, (96 * 1024 - red_bytes) / stage_bytes);
+    if (stages < 3) stages = (int)std::min<size_t>(kSlabMaxStages, (200 * 1024 - red_bytes) / stage_bytes);
+    if (stages < 2) return SIPGPU_E_ARG;
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + red_bytes;
+    int occ = 1;
+    SIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLT, smem));
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)ctx().num_sms * occ;
+    long long ns = 1;
+    if (a.nprob < slots && may_split) {   // (a launch that fills the slots is never cut: its sums stay bit-reproducible)
+        // cut along K so that the items fill whole waves of CTA slots (items are dealt round-robin: 600 items on 296 slots
+        // take as long as 888): the slice count with the best fill, every slice streaming at least ~256 KB
+        const long long min_chunks = std::max<long long>(1, (256 * 1024) / (long long)stage_bytes);
+        const long long avg_chunks = std::max<long long>(1, total_chunks / std::max(1, a.nprob));
+        const long long cap = std::min<long long>(std::max<long long>(1, avg_chunks / min_chunks), (6 * slots + a.nprob - 1) / a.nprob);
+        double best = -1.0;
+        for (long long k = 1; k <= cap; ++k) {
+            const long long items = (long long)a.nprob * k, waves = (items + slots - 1) / slots;
+            const double fill = (double)items / (double)(waves * slots) - 0.002 * k;   // ties: fewer slices
+            if (fill > best) { best = fill; ns = k; }
+        }
+    }
+    a.nslice = (int)ns;
+    a.atomic = ns > 1;
+    if (a.atomic) SIP_TRY(prescale());
+    const long long nwork = (long long)a.nprob * ns;
+    if (nwork >= (1LL << 31)) return SIPGPU_E_ARG;
+    const int grid = (int)std::min<long long>(nwork, slots);
+    auto go = [a, grid, smem, kern]() -> int {
+        kern<<<grid, kLT, smem, ctx().stream>>>(a);
+        SIP_CUDA(cudaGetLastError());
+        count_launch();
+        return SIPGPU_OK;
+    };
+    if (Capture* cap = capture()) { cap->steps.push_back(go); return SIPGPU_OK; }
+    return go();
+}
+
+// true + launched, or false: not a slab shape / operands not 16-byte aligned (the caller goes on with the gather kernel)
+int slab_try(const Shape& s, const Tables& t, int n, const std::vector<Pair>& pairs, const LowProb* d_probs, const Pair* d_pairs,
+             const std::vector<LowProb>& probs, long long total_pairs, double alpha, double beta, bool dense_d,
+             const std::function<int()>& run_prescale, bool* done) {
+    *done = false;
+    if (slab_mode() <= 0) return SIPGPU_OK;
+    const SlabPlan& p = slab_plan(s);
+    if (!p.ok) return SIPGPU_OK;
+    for (const Pair& pr : pairs)
+        if (((uintptr_t)pr.L | (uintptr_t)pr.R) & 15) return SIPGPU_OK;
+    const SlabVariant* v = slab_variant(s.M, s.N);
+    SlabArgs a;
+    memset(&a, 0, sizeof(a));
+    a.probs = d_probs; a.pairs = d_pairs;
+    a.mtab = t.mtab; a.ntab = t.ntab; a.ctab = p.ctab;
+    a.nprob = n; a.M = s.M; a.N = s.N; a.KC = p.KC; a.cpp = p.cpp;
+    a.a_sk = p.a_sk; a.b_sk = p.b_sk;
+    a.a_elems = (p.a_elems + 1) & ~1;
+    a.stage_elems = (a.a_elems + p.b_elems + 15) & ~15;
+    a.a_nruns = p.a_nruns; a.b_nruns = p.b_nruns; a.a_runlen = p.a_runlen; a.b_runlen = p.b_runlen;
+    memcpy(a.a_run, p.a_run, sizeof(a.a_run));
+    memcpy(a.b_run, p.b_run, sizeof(a.b_run));
+    memcpy(a.a_moff, p.a_moff, sizeof(a.a_moff));
+    memcpy(a.b_noff, p.b_noff, sizeof(a.b_noff));
+    a.alpha = alpha; a.beta = beta;
+    a.p0 = probs[0]; a.pair0 = pairs[0];
+    const size_t stage_bytes = (size_t)a.stage_elems * 8;
+    const long long total_chunks = total_pairs * p.cpp;
+    *done = true;
+#define SLAB_CASE(MF_, NF_, KS_) \
+    if (v->mf == MF_ && v->nf == NF_ && v->ksplit == KS_) return launch_slab<MF_, NF_, KS_>(a, stage_bytes, dense_d, total_chunks, run_prescale)
+    SLAB_CASE(2, 2, true); SLAB_CASE(3, 3, true); SLAB_CASE(4, 4, true); SLAB_CASE(3, 7, true); SLAB_CASE(7, 3, true);
+    SLAB_CASE(5, 2, false); SLAB_CASE(6, 2, false); SLAB_CASE(7, 2, false); SLAB_CASE(8, 2, false);
+#undef SLAB_CASE
+    *done = false;
+    return SIPGPU_OK;
+}
+
 }  // namespace
 
-void lowint_cache_clear() { table_cache().clear(); }
+void lowint_cache_clear() { table_cache().clear(); slab_cache().clear(); }
+void lowint_set_slab(int on) { slab_mode() = on; }
 
 static double& lowint_max_intensity() {
     static double v = [] {
@@ -536,6 +980,7 @@ bool lowint_eligible(const Shape& s) {
     const double flops = 2.0 * s.M * s.N * s.K, bytes = 8.0 * ((double)s.M * s.K + (double)s.N * s.K + (double)s.M * s.N);
     if (flops / bytes > maxi) return false;
     if (scope >= 2) return true;
+    if (slab_mode() > 0 && slab_plan(s).ok) return true;   // contiguous-slab shapes: TMA-fed, see slab_kernel
     return s.M <= 64 && ((long long)s.M * s.N <= 512 || s.K <= 64);
 }
 
@@ -582,6 +1027,11 @@ int lowint_launch(const Shape& s, int n, const std::vector<Pair>& pairs, const s
         return prescale();
     };
 
+    if (!is_dot) {
+        bool done = false;
+        SIP_TRY(slab_try(s, t, n, pairs, d_probs, d_pairs, probs, total_pairs, alpha, beta, dense_d, run_prescale, &done));
+        if (done) return SIPGPU_OK;
+    }
     if (is_dot) {
         DotArgs a;
         memset(&a, 0, sizeof(a));

@@ -193,3 +193,102 @@ def test_prepared_plans_replay_the_launches(sip, oracle):
             assert np.max(np.abs(Ds[b].to_numpy().reshape(refs[b].shape))) <= 1e-9 * max(1.0, np.max(np.abs(refs[b])))
         bc.destroy()
     sip.set_tuning("lowint_scope", 1)
+
+
+# ---- the TMA-fed slab path (slab_kernel): small results of long contractions whose chunks are contiguous runs ----
+SLAB_CASES = [
+    ("50x50, free index fastest", "ab", "acde", "bcde", dict(a=50, b=50, c=20, d=10, e=6)),
+    ("20x20, contracted index fastest", "ab", "cade", "cbde", dict(a=20, b=20, c=50, d=6, e=5)),
+    ("20x50, different orders of the outer contracted indices", "ab", "acde", "cbed", dict(a=20, b=50, c=20, d=10, e=8)),
+    ("50x50, one operand in many runs", "ab", "acde", "bedc", dict(a=50, b=50, c=20, d=4, e=16)),
+    ("50x20", "ab", "acde", "bcde", dict(a=50, b=20, c=20, d=10, e=6)),
+    ("16x16", "ab", "acde", "bcde", dict(a=16, b=16, c=16, d=16, e=8)),
+    ("32x32", "ab", "acde", "bcde", dict(a=32, b=32, c=8, d=8, e=16)),
+    ("40x40", "ab", "acde", "bcde", dict(a=40, b=40, c=10, d=12, e=10)),
+    ("64x64", "ab", "acde", "bcde", dict(a=64, b=64, c=16, d=8, e=8)),
+    ("56x24", "ab", "acde", "bcde", dict(a=56, b=24, c=12, d=10, e=10)),
+    ("12x60", "ab", "acde", "bcde", dict(a=12, b=60, c=12, d=10, e=10)),
+    ("odd extents (gather kernel)", "ab", "acde", "bcde", dict(a=25, b=25, c=11, d=10, e=10)),
+    ("rank-5 operands", "ab", "xacde", "xbcde", dict(a=20, b=20, c=10, d=10, e=6, x=2)),
+]
+
+
+@pytest.mark.parametrize("slab", [1, 0], ids=["slab", "gather"])
+@pytest.mark.parametrize("case", SLAB_CASES, ids=[c[0] for c in SLAB_CASES])
+def test_slab_shapes_single_block_split_along_k(sip, oracle, case, slab):
+    """one destination: the launch is cut along K into slices that meet through red.add (beta by a pre-scale)"""
+    sip.set_tuning("lowint_scope", 1)
+    sip.set_tuning("lowint_slab", slab)
+    try:
+        name, d, l, r, ext = case
+        labs = sorted(set(d + l + r))
+        num = {c: i + 1 for i, c in enumerate(labs)}
+        rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000)
+        L = rand_block(rng, tuple(ext[c] for c in l))
+        R = rand_block(rng, tuple(ext[c] for c in r))
+        dext = [ext[c] for c in d]
+        ref, ierr = oracle.contract_labels([num[c] for c in d], dext, [num[c] for c in l], L, [num[c] for c in r], R)
+        assert ierr == 0
+        dL, dR = sip.DeviceBlock.from_numpy(L), sip.DeviceBlock.from_numpy(R)
+        got = sip.contract_labels([num[c] for c in d], dext, [num[c] for c in l], dL, [num[c] for c in r], dR).to_numpy()
+        assert relerr(got.reshape(ref.shape), ref) <= TOL, name
+        D0 = rand_block(rng, tuple(dext))
+        out = sip.DeviceBlock.from_numpy(D0)
+        sip.contract_labels([num[c] for c in d], dext, [num[c] for c in l], dL, [num[c] for c in r], dR, out=out, alpha=-0.5, beta=2.0)
+        assert relerr(out.to_numpy().reshape(ref.shape), -0.5 * ref + 2.0 * D0) <= TOL, name
+    finally:
+        sip.set_tuning("lowint_slab", 1)
+
+
+@pytest.mark.parametrize("nblocks,chain_max", [(2, 5), (37, 3), (400, 2)])
+@pytest.mark.parametrize("case", SLAB_CASES[:5] + SLAB_CASES[7:9], ids=lambda c: c[0])
+def test_slab_shapes_work_lists_with_chains(sip, oracle, case, nblocks, chain_max):
+    """many destinations (one item per CTA slot, the ring running across item boundaries), chains of unequal length, the
+    deterministic reduction over the four warps of the K-split variants: two launches give identical bits"""
+    sip.set_tuning("lowint_scope", 1)
+    sip.set_tuning("lowint_slab", 1)
+    name, d, l, r, ext = case
+    labs = sorted(set(d + l + r))
+    num = {c: i + 1 for i, c in enumerate(labs)}
+    dl_, ll_, rl_ = [num[c] for c in d], [num[c] for c in l], [num[c] for c in r]
+    ptrn, ierr = sip.get_contraction_ptrn(dl_, ll_, rl_)
+    assert ierr == 0
+    rng = np.random.default_rng(nblocks * 31 + chain_max)
+    lsh, rsh, dsh = tuple(ext[c] for c in l), tuple(ext[c] for c in r), tuple(ext[c] for c in d)
+    npool = 6
+    Lh = [rand_block(rng, lsh) for _ in range(npool)]
+    Rh = [rand_block(rng, rsh) for _ in range(npool)]
+    Ld, Rd = [sip.DeviceBlock.from_numpy(x) for x in Lh], [sip.DeviceBlock.from_numpy(x) for x in Rh]
+    prod = {}
+
+    def pair_product(i, j):
+        if (i, j) not in prod:
+            prod[(i, j)], e = oracle.contract_labels(dl_, list(dsh), ll_, Lh[i], rl_, Rh[j])
+            assert e == 0
+        return prod[(i, j)]
+
+    lp, rp, chain, refs, Ds = [], [], [0], [], []
+    for b in range(nblocks):
+        n = 1 + (b * 7) % chain_max
+        ref = np.zeros(dsh, order="F")
+        for c in range(n):
+            i, j = (b * 3 + c) % npool, (b * 5 + 2 * c + 1) % npool
+            lp.append(Ld[i].ptr), rp.append(Rd[j].ptr)
+            ref = ref + pair_product(i, j)
+        chain.append(len(lp))
+        refs.append(ref)
+        Ds.append(sip.DeviceBlock(dsh))
+    bc = sip.BatchedContraction(ptrn, [lsh] * nblocks, [rsh] * nblocks, [dsh] * nblocks, lp, rp, [x.ptr for x in Ds], chain_start=chain)
+    bc.launch()
+    step = max(1, nblocks // 25)
+    first = {}
+    for b in range(0, nblocks, step):
+        first[b] = Ds[b].to_numpy()
+        assert relerr(first[b].reshape(refs[b].shape), refs[b]) <= TOL, (name, b)
+    if nblocks >= 400:      # no split along K: bit-identical from launch to launch
+        bc.launch()
+        for b in range(0, nblocks, step):
+            assert np.array_equal(Ds[b].to_numpy(), first[b]), (name, b)
+    bc.launch(alpha=0.25, beta=1.0)
+    for b in range(0, nblocks, step):
+        assert relerr(Ds[b].to_numpy().reshape(refs[b].shape), 1.25 * refs[b]) <= TOL, (name, b)
