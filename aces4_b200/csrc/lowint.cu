@@ -820,7 +820,8 @@ const SlabPlan& slab_plan(const Shape& s) {
     if (it != slab_cache().end()) return it->second;
     SlabPlan best;
     long long best_score = -1;
-    if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= 1024 && slab_variant(s.M, s.N)) {
+    static const int min_k = [] { const char* e = getenv("SIPGPU_SLAB_MINK"); return e ? atoi(e) : 1024; }();
+    if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= min_k && slab_variant(s.M, s.N)) {
         const long long perk = 8LL * (s.M + s.N);
         for (int q = 0; q < s.nk; ++q) {
             for (int KC = std::min(s.kext[q], 128); KC >= 8; --KC) {

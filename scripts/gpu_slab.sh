@@ -1,8 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_lowint.py -x -q 2>&1 | tail -3
-for p in "ab=acde*bcde vvovo 100" "ab=cade*bced vvoov 100" "ab=acde*cbed vvovo 100"; do
-  set -- $p
-  SIPGPU_LOWINT_SLAB=1 timeout 120 python scripts/ncu_pattern.py "$1" $2 $3
-done
-bash scripts/gpu_ncu_pattern.sh "ab=acde*bcde" vvovo 100 slab77_vvovo 2>&1 | tail -1
+SIPGPU_SLAB_MINK=16 timeout 900 python -m pytest tests/test_gpu_lowint.py tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+SWEEP_RANKS=222 SIPGPU_SLAB_MINK=1024 SWEEP_OUT=sweep_mink1024.json timeout 600 python scripts/sweep_patterns.py 2>&1 | tail -14
+SWEEP_RANKS=222 SIPGPU_SLAB_MINK=16 SWEEP_OUT=sweep_mink16.json timeout 600 python scripts/sweep_patterns.py 2>&1 | tail -14
