@@ -52,6 +52,7 @@ it for the `do kiter` loop of a CC program, whose `if`/`exit` are not in the sub
 procedures only (a fragment) is run in textual order.
 """
 import itertools
+import math
 import re
 
 
@@ -91,8 +92,8 @@ def parse_expr(text):
     ('neg', e) | (op, l, r) with op in + - * / **   (SIAL casts are prefix: `(int)Xijk[NT,i7]`, `tcomb/(scalar)nsects`)"""
     toks = []
     for num, name, br, other in _TOK.findall(text.strip().lower()):
-        if num:
-            toks.append(("num", float(num.replace("d", "e"))))
+        if num:      # `42` is an int, `42.0` / `1.d-3` a scalar (int / int truncates as in the SIP: sial_math / interpreter.cpp)
+            toks.append(("num", int(num) if num.isdigit() else float(num.lower().replace("d", "e"))))
         elif name:
             toks.append(("name", name))
         elif br:
@@ -113,6 +114,8 @@ def parse_expr(text):
         if k == "num":
             return ("num", v)
         if k == "name":
+            if v in ("sqrt", "abs") and peek()[0] in ("num", "name") or v in ("sqrt", "abs") and peek() == ("op", "("):
+                return ("fn", v, primary())      # `sr0 = sqrt 256.0`
             if peek()[0] == "br":
                 return ("elem", v, take()[1])
             return ("var", v)
@@ -173,6 +176,7 @@ class Program:
 
     def __init__(self, text):
         self.index_kind, self.arrays, self.scalars = {}, {}, set()
+        self.ints = set()         # names declared `int` (integer arithmetic: `/` truncates, `(int)` rounds like lrint)
         self.simple_range = {}    # simple index name -> (lo, hi) as written (numbers or predefined constants such as naocc)
         self.procs = {}           # name -> statement list (textual order kept: dicts are ordered)
         self.predefined = set()   # `predefined int|scalar X`: the value comes with the job (the .dat file), Walker(constants=...)
@@ -223,6 +227,13 @@ class Program:
                 stack[-1].append(st)
                 stack.append(st[-1])
                 opens.append(st[0])
+            elif st[0] == "else":
+                if not opens or opens[-1] != "if":
+                    raise SialSyntaxError(f"line {ln}: else outside an if")
+                stack.pop()
+                st = ("else", [])
+                stack[-1].append(st)
+                stack.append(st[-1])
             elif st[0] in ("endpardo", "enddo", "endif"):
                 if not opens or opens.pop() != st[0][3:]:
                     raise SialSyntaxError(f"line {ln}: unbalanced {st[0]}")
@@ -247,6 +258,8 @@ class Program:
                 raise SialSyntaxError("bad predefined declaration")
             self.predefined.add(tok[2])
             self.scalars.add(tok[2])
+            if tok[1] == "int":
+                self.ints.add(tok[2])
             return None
         if kw == "contiguous":     # a dense local array addressed by ranges; the programs here address it block by block (`x:x`)
             m = re.match(r"contiguous\s+local\s+" + _REF, line, re.I)
@@ -261,14 +274,17 @@ class Program:
                 raise SialSyntaxError("bad " + kw + " contiguous")
             return (kw, m.group(1).lower(), ("*",))
         if kw == "index":
-            m = re.match(r"index\s+(\w+)\s*=\s*(\w+)\s*:\s*(\w+)", line, re.I)
+            m = re.match(r"index\s+(\w+)\s*=\s*(-?\s*\w+)\s*:\s*(-?\s*\w+)", line, re.I)
             if not m:
                 raise SialSyntaxError("bad simple index declaration")
             self.index_kind[m.group(1).lower()] = "s"
-            self.simple_range[m.group(1).lower()] = (m.group(2).lower(), m.group(3).lower())
+            self.simple_range[m.group(1).lower()] = (m.group(2).lower().replace(" ", ""), m.group(3).lower().replace(" ", ""))
             return None
         if kw == "int":
             self.scalars.add(tok[1])
+            self.ints.add(tok[1])
+            if "=" in low:      # `int e0 = 77`
+                return ("sexpr", tok[1], "=", parse_expr(low.split("=", 1)[1]))
             return None
         if kw == "if":
             m = re.match(r"if\s+(.+?)\s*(<=|>=|==|!=|<|>)\s*(.+)$", low)
@@ -277,6 +293,8 @@ class Program:
             return ("if", parse_expr(m.group(1)), m.group(2), parse_expr(m.group(3)))
         if kw == "endif":
             return ("endif",)
+        if kw == "else" and len(tok) == 1:
+            return ("else",)
         if kw == "exit":
             return ("exit",)
         if kw in ("proc", "call"):
@@ -303,9 +321,11 @@ class Program:
             return None
         if kw == "scalar":
             self.scalars.add(tok[1])
+            if "=" in low:      # `scalar total = 0.0`
+                return ("sexpr", tok[1], "=", parse_expr(low.split("=", 1)[1]))
             return None
         if kw == "pardo" or kw == "do":
-            return (kw, _labels(line.split(None, 1)[1]))
+            return (kw, _labels(re.sub(r'"[^"]*"', "", line.split(None, 1)[1])))     # `pardo i, j "pragma text"`
         if kw in ("endpardo", "enddo"):
             return (kw,)
         if kw == "where":
@@ -357,7 +377,7 @@ class Program:
         if kw in ("sip_barrier", "server_barrier"):
             return ("barrier",)
         if kw == "collective":
-            m = re.match(r"collective\s+(\w+)\s*\+=\s*(\w+)", low)
+            m = re.match(r"collective\s+(\w+)\s*\+=\s*(?:\(\s*(?:scalar|int)\s*\)\s*)?(\w+)\s*$", low)
             if not m:
                 raise SialSyntaxError("bad collective")
             return ("collective", m.group(1), m.group(2))
@@ -606,7 +626,7 @@ class Walker:
         """the values a loop over `lab` takes: segment numbers 1..nseg, or lo..hi of a simple index"""
         if self._kind(lab) != "s":
             return range(1, self._nseg(lab) + 1)
-        lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[lab])
+        lo, hi = (int(x) if x.lstrip('-').isdigit() else self.constants[x] for x in self.p.simple_range[lab])
         return range(lo, hi + 1)
 
     def _core(self, labs):
@@ -628,7 +648,8 @@ class Walker:
             if n in self.idx:
                 return self.idx[n]
             if n in self.scalars:
-                return self.be.value(self.scalars[n])
+                v = self.be.value(self.scalars[n])
+                return int(round(v)) if n in self.p.ints and float(v).is_integer() else v
             if n in self.constants:
                 return self.constants[n]
             raise SialSyntaxError(f"undefined name {n} in expression")
@@ -638,10 +659,15 @@ class Walker:
             return self.tables.get(e[1], {}).get(tuple(self.idx[x] for x in e[2]), 0.0)
         if k == "cast":
             v = self._eval(e[2])
-            return float(int(v)) if e[1] == "int" else float(v)
+            return int(round(v)) if e[1] == "int" else float(v)      # cast_double_to_int = lrint (sial_math.cpp:39)
         if k == "neg":
             return -self._eval(e[1])
+        if k == "fn":
+            v = self._eval(e[2])
+            return math.sqrt(v) if e[1] == "sqrt" else abs(v)
         a, b = self._eval(e[1]), self._eval(e[2])
+        if k == "/" and type(a) is int and type(b) is int:
+            return int(math.copysign(abs(a) // abs(b), a * b)) if b else a / b      # C integer division
         return a + b if k == "+" else a - b if k == "-" else a * b if k == "*" else a ** b if k == "**" else a / b
 
     def _segs_of(self, labs):
@@ -688,7 +714,7 @@ class Walker:
                     plan.append((lab, self.index_base.get("v", len(self.segs["o"])) if k == "v" else base))
                 elif dk == "s" and k == "s":       # block coordinate = value - first value + 1
                     lo = self.p.simple_range[d][0]
-                    plan.append((lab, 1 - (int(lo) if lo.isdigit() else self.constants[lo])))
+                    plan.append((lab, 1 - (int(lo) if lo.lstrip('-').isdigit() else self.constants[lo])))
                 elif dk == k or (dk == "p" and k == "o"):
                     plan.append((lab, 0))
                 elif (":" in dk or dk == "ao") and (":" in k or k == "ao") and dk.split(":")[0] == k.split(":")[0]:
@@ -871,8 +897,15 @@ class Walker:
 
     def _x_if(self, lhs, op, rhs, body):
         va, vb = self._eval(lhs), self._eval(rhs)
-        if {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]:
-            return self._block(body)   # a false `where` inside propagates
+        self._if_taken = taken = {"<": va < vb, "<=": va <= vb, ">": va > vb, ">=": va >= vb, "==": va == vb, "!=": va != vb}[op]
+        if taken:
+            res = self._block(body)   # a false `where` inside propagates
+            self._if_taken = True     # (an if / else inside the body has used the flag)
+            return res
+
+    def _x_else(self, body):          # directly follows its `if` in the statement list
+        if not self._if_taken:
+            return self._block(body)
 
     def _x_exit(self):
         raise _Exit()
@@ -1101,7 +1134,7 @@ class Walker:
             return
         if fname == "compute_diis":                  # the DIIS equations of the CC iterations: host LAPACK (dgesv), as in the reference
             B = bare[0]
-            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[B][1][1]])
+            lo, hi = (int(x) if x.lstrip('-').isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[B][1][1]])
             n = hi - lo + 1
             t = self.tables.setdefault(B, {})
             c = compute_diis([[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)])
@@ -1110,7 +1143,7 @@ class Walker:
             return
         if fname == "eigen_calc":                    # dsyev of the (symmetric) CIS subspace matrix: host LAPACK, as in the reference
             G, V = bare
-            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
+            lo, hi = (int(x) if x.lstrip('-').isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
             n = hi - lo + 1
             t = self.tables.get(G, {})
             a_out, vec = eigen_calc([[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)])
@@ -1125,7 +1158,7 @@ class Walker:
             return
         if fname == "gen_eigen_calc":                # dgeev of the Davidson subspace matrix: host LAPACK, as in the reference
             G, L, R, E = bare
-            lo, hi = (int(x) if x.isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
+            lo, hi = (int(x) if x.lstrip('-').isdigit() else self.constants[x] for x in self.p.simple_range[self.p.arrays[G][1][0]])
             n = hi - lo + 1
             t = self.tables.get(G, {})
             A = [[t.get((i + lo, j + lo), 0.0) for j in range(n)] for i in range(n)]

@@ -52,7 +52,7 @@ def dim_segments(prog, label, seg_tables, constants):
     return list(seg_tables["mo"][val(lo) - 1: val(hi)])
 
 
-def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend=None):
+def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend=None, rank=0, world=1):
     prog = Program(text(name))
     be = backend or make_backend(prog, {"ao": ao or [], "mo": mo or []}, constants or {})
     segs = {"ao": list(ao or []), "pa": list(mo or [])}
@@ -60,7 +60,7 @@ def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend
     if mo and "baocc" in c:
         segs["o"] = mo[c["baocc"] - 1: c["eaocc"]]
         segs["v"] = mo[c["bavirt"] - 1: c["eavirt"]]
-    w = Walker(prog, be, segs, constants=c, seg_tables={"ao": ao or [], "mo": mo or []}, extra_si=EXTRA_SI,
+    w = Walker(prog, be, segs, rank=rank, world=world, constants=c, seg_tables={"ao": ao or [], "mo": mo or []}, extra_si=EXTRA_SI,
                index_base={"o": c.get("baocc", 1) - 1, "v": c.get("bavirt", 1) - 1})
     w.run()
     return w, be
@@ -214,6 +214,64 @@ def persistence_between_programs(make_backend, to_numpy):
     run("persistent_scalars_1", make_backend, constants={"x": 3.456, "y": -0.1})
     w, be = run("persistent_scalars_2", make_backend, constants={"y": -0.1})
     assert be.value(w.scalars["e"]) == 6.0 and abs(be.value(w.scalars["x"]) - 4.456) < 1e-15
+
+
+# ---- host-only programs (the pardo work distribution and the interpreter's arithmetic: no block operation is issued) ----
+def pardo_loops(make_backend, to_numpy):
+    """Sial.pardo_loop / pardo_loop_corner_case / pardo_loop_with_pragma (test_sial.cpp:82-216): pardo_loop_<n>d counts its
+    iterations per worker and sums the counters with `collective total += (scalar)counter`: total == prod(upper - lower + 1)
+    for every number of workers (the work distribution of BalancedTaskAllocParallelPardoLoop::do_update: every iteration on
+    exactly one worker).  The collective is the sum over the emulated ranks."""
+    for lower, upper in (([3, 2, 4, 1, 99, -1], [7, 6, 5, 1, 101, 2]), ([1] * 6, [1] * 6)):
+        for nd in range(1, 7):
+            consts = {f"lower{i}": lower[i] for i in range(nd)} | {f"upper{i}": upper[i] for i in range(nd)}
+            want = int(np.prod([upper[i] - lower[i] + 1 for i in range(nd)]))
+            for world in (1, 2, 3, 7):
+                total = 0
+                for rank in range(world):
+                    w, be = run(f"pardo_loop_{nd}d", make_backend, constants=consts, rank=rank, world=world)
+                    assert be.value(w.scalars["total"]) == be.value(w.scalars["counter"])      # one rank's share
+                    total += int(be.value(w.scalars["counter"]))
+                assert total == want, (nd, world, total, want)
+    for world in (1, 3):
+        counts = []
+        for r in range(world):
+            w, be = run("pardo_loop_with_pragma", make_backend, rank=r, world=world,
+                        constants={"lower0": 3, "upper0": 7, "lower1": 2, "upper1": 6, "lower2": 4, "upper2": 5})
+            counts.append(int(be.value(w.scalars["counter"])))
+        assert sum(counts) == 5 * 5 * 2
+    w, be = run("pardo_loop", make_backend)
+    assert int(be.value(w.scalars["counter"])) == 5 * 4 * 4
+    # pardo_with_where (test_sial.cpp:1039-1070: runs to completion) -- here also: the where clauses leave the
+    # mu < nu, lambda < sigma, mu < lambda, all-different quadruples, each on exactly one of 3 workers
+    seen = []
+    for r in range(3):
+        w, _ = run("pardo_with_where", make_backend, ao=[2, 3, 2, 2], constants={"norb": 4}, rank=r, world=3)
+        seen.append(w.iteration)
+    assert len(set(seen)) == 1     # every worker counts every where-true iteration of the section
+
+
+def interpreter_arithmetic(make_backend, to_numpy):
+    """BasicSial.scalar_ops, int_ops, int_self_ops, ifelse, index_scalar_cast (test_basic_sial.cpp:285-296, 451-524, 1477-1499)"""
+    w, be = run("scalar_ops", make_backend)
+    val = lambda n: be.value(w.scalars[n])      # noqa: E731
+    for name, want in (("l", 42.0), ("nl", -42.0), ("s0", 0.0), ("si0", 0.0), ("sd", 21.0), ("sr0", 16), ("sr1", 4), ("e0", 16),
+                       ("ci0", 4), ("ci1", 16), ("ci2", -28), ("re1", 1), ("re2", -1), ("rgt2", 2), ("rgt3", 15), ("rgt4", 15),
+                       ("rgt5", 10), ("rgt6", 10), ("rgt7", 10), ("rgt8", 10), ("rgt9", 10)):
+        assert val(name) == want, (name, val(name), want)      # ci0 = (int) 3.75 = 4: the SIP's cast is lrint (sial_math.cpp:39)
+    w, be = run("int_ops", make_backend)
+    for name, want in dict(l=42, nl=-42, s0=0, si0=0, sd=21, sr0=10, sr1=-2, e0=77, ci0=4, ci1=12, ci2=3, re1=1, re2=-1, rgt2=2, rgt3=15,
+                           rgt4=15, rgt5=10, rgt6=10, rgt7=10, rgt8=15, rgt9=10).items():
+        assert be.value(w.scalars[name]) == want, (name, be.value(w.scalars[name]), want)      # int / int truncates
+    w, be = run("ifelse", make_backend)
+    assert be.value(w.scalars["eq_counter"]) == 4 and be.value(w.scalars["neq_counter"]) == 20
+    w, be = run("int_self_ops", make_backend)
+    assert [be.value(w.scalars[n]) for n in "xyzw"] == [76, 44, -28, 15200]
+    w, be = run("index_scalar_cast", make_backend, ao=[2, 2, 1, 3], constants={"norb": 4})
+    assert be.value(w.scalars["count"]) == 4 and be.value(w.scalars["count2"]) == 1
+
+
+HOST_ONLY = (pardo_loops, interpreter_arithmetic)
 
 
 def runs_to_completion(make_backend, to_numpy):

@@ -15,3 +15,10 @@ def make_backend(prog, seg_tables, constants):
 @pytest.mark.parametrize("case", rp.ALL, ids=lambda f: f.__name__)
 def test_reference_unit_program(case):
     case(make_backend, lambda h: h.a)
+
+
+@pytest.mark.parametrize("case", rp.HOST_ONLY, ids=lambda f: f.__name__)
+def test_reference_host_only_unit_program(case):
+    """the pardo work distribution (SURVEY 8a: BalancedTaskAllocParallelPardoLoop::do_update) and the interpreter's scalar / int /
+    if-else arithmetic through the reference's own test programs: no block operation, so no device twin"""
+    case(make_backend, lambda h: h.a)
