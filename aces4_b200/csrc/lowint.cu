@@ -423,6 +423,12 @@ struct SlabArgs {
     int a_nruns, b_nruns, a_runlen, b_runlen;
     int a_run[kSlabMaxRuns], b_run[kSlabMaxRuns];  // offset of run r inside the chunk of the operand (elements)
     short a_moff[64], b_noff[64];                  // staged offset of row m / column n (0 beyond M / N)
+    // hybrid: an operand whose chunk is NOT a few long runs (R[b,e,d,c] next to L[a,c,d,e]: 400-byte pieces) is gathered by
+    // the 128 threads instead -- one cp.async per table item {offset in the chunk, staged offset}, the table built once per
+    // shape in the operand's memory order; its completion arrives on the same mbarrier (cp.async.mbarrier.arrive.noinc)
+    const int2* a_items;   // nullptr: operand A travels as TMA runs
+    const int2* b_items;
+    int a_nitems, b_nitems, a_vec, b_vec;          // vec: 16-byte items
     double alpha, beta;
     LowProb p0;
     Pair pair0;
@@ -473,9 +479,11 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
     for (int i = 0; i < MF; ++i) moff[i] = a.a_moff[8 * i + g];
 #pragma unroll
     for (int j = 0; j < NF; ++j) noff[j] = a.a_elems + a.b_noff[ncol0 + 8 * j + g];
+    const bool gather = a.a_items != nullptr || a.b_items != nullptr;
     if (tid == 0) {
+        const int count = gather ? 1 + kLT : 1;   // the expect_tx arrival (+ one asynchronous arrival per gathering thread)
         for (int s = 0; s < a.stages; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(full + s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(full + s)), "r"(count) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -483,9 +491,10 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
     SlabCursor pf, cp;
     slab_cursor_load(cp, a, blockIdx.x, nwork);
     pf = cp;
-    const unsigned stage_bytes = 8u * (unsigned)(a.a_nruns * a.a_runlen + a.b_nruns * a.b_runlen);
-    auto issue = [&](int stage) {   // warp 0: the chunk at the prefetch cursor -> stage; then the cursor moves on
+    const unsigned stage_bytes = 8u * (unsigned)((a.a_items ? 0 : a.a_nruns * a.a_runlen) + (a.b_items ? 0 : a.b_nruns * a.b_runlen));
+    auto issue = [&](int stage) {   // the chunk at the prefetch cursor -> stage (warp 0: TMA runs; everybody: gathers); cursor moves on
         if (pf.w >= nwork) return;
+        if (warp != 0 && !gather) return;
         Pair pq;
         if (a.probs) {
             const int4 raw = __ldg(reinterpret_cast<const int4*>(a.pairs + pf.pair));
@@ -495,24 +504,42 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         }
         const int2 co = __ldg(a.ctab + pf.kc);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(full + stage);
+        double* st = sm + (size_t)stage * a.stage_elems;
+        if (gather) {
+            if (a.a_items) {
+                const double* base = pq.L + co.x;
+                for (int i = tid; i < a.a_nitems; i += kLT) {
+                    const int2 e = __ldg(a.a_items + i);
+                    if (a.a_vec) cpa16(st + e.y, base + e.x, true); else cpa8(st + e.y, base + e.x, true);
+                }
+            }
+            if (a.b_items) {
+                const double* base = pq.R + co.y;
+                for (int i = tid; i < a.b_nitems; i += kLT) {
+                    const int2 e = __ldg(a.b_items + i);
+                    if (a.b_vec) cpa16(st + a.a_elems + e.y, base + e.x, true); else cpa8(st + a.a_elems + e.y, base + e.x, true);
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+        }
+        if (warp == 0) {
         if (lane == 0) asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(stage_bytes) : "memory");
         __syncwarp();
-        double* st = sm + (size_t)stage * a.stage_elems;
-        if (lane < a.a_nruns)
+        if (!a.a_items && lane < a.a_nruns)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                              (unsigned)__cvta_generic_to_shared(st + lane * a.a_runlen)),
                          "l"(pq.L + co.x + a.a_run[lane]), "r"(8u * (unsigned)a.a_runlen), "r"(bar)
                          : "memory");
-        if (lane < a.b_nruns)
+        if (!a.b_items && lane < a.b_nruns)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                              (unsigned)__cvta_generic_to_shared(st + a.a_elems + lane * a.b_runlen)),
                          "l"(pq.R + co.y + a.b_run[lane]), "r"(8u * (unsigned)a.b_runlen), "r"(bar)
                          : "memory");
+        }
         slab_cursor_next(pf, a);
         if (pf.c == pf.c_end) slab_cursor_load(pf, a, pf.w + gridDim.x, nwork);
     };
-    if (warp == 0)
-        for (int s = 0; s < a.stages; ++s) issue(s);
+    for (int s = 0; s < a.stages; ++s) issue(s);
 
     double acc[MF][NF][2];
 #pragma unroll
@@ -553,7 +580,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         slab_cursor_next(cp, a);
         const bool item_done = cp.c == cp.c_end;
         __syncthreads();   // every warp is done with the stage
-        if (warp == 0) issue(stage);
+        issue(stage);
         if (++stage == a.stages) { stage = 0; parity ^= 1; }
         if (!item_done) continue;
         // ---- end of the item: (KSPLIT: sum the four warps' partial tiles in a fixed order) and write D ----
@@ -724,6 +751,10 @@ struct SlabPlan {
     int a_run[kSlabMaxRuns], b_run[kSlabMaxRuns];
     short a_moff[64], b_noff[64];
     int2* ctab = nullptr;   // device
+    // hybrid: the operand that is gathered by the threads (host copy of its item table until the plan is chosen)
+    std::vector<int2> a_items_h, b_items_h;
+    int2 *a_items = nullptr, *b_items = nullptr;   // device
+    int a_vec = 0, b_vec = 0;
 };
 struct SlabDim {
     int ext, gs;   // extent inside a chunk, stride in the operand
@@ -784,6 +815,44 @@ bool slab_operand(int nf, const int* fext, const int* fs, int qs, int qext, int 
     return true;
 }
 
+// the other way to bring an operand's chunk in: the 128 threads gather it with cp.async, one table item {offset inside the
+// chunk, staged offset} per 16-byte (or 8-byte) piece, walking the operand's memory order.  Staged [k][x] when a free index is
+// the operand's fastest (x contiguous), [x][k] when the chunked contracted index is; the leading dimension is 4 (mod 8)
+// doubles, so the fragment loads of a half-warp fall on 16 different banks.  false: neither is the fastest (8-byte pieces
+// scattered over sectors -- leave the shape to the gather kernel).
+bool slab_gather(int nf, const int* fext, const int* fs, int qs, int KC, int X, std::vector<int2>* items, int* vec, int* sk,
+                 short* xoff, int* elems) {
+    auto pad4 = [](int n) { int v = n; while (v % 8 != 4) ++v; return v; };
+    std::vector<int> xg((size_t)X);
+    for (int x = 0; x < X; ++x) {
+        int lin = x, off = 0;
+        for (int i = 0; i < nf; ++i) { off += (lin % fext[i]) * fs[i]; lin /= fext[i]; }
+        xg[x] = off;
+    }
+    auto all_even = [&](int from) { for (int i = from; i < nf; ++i) if (fs[i] & 1) return false; return true; };
+    items->clear();
+    if (nf >= 1 && fs[0] == 1) {           // a free index is fastest: [k][x]
+        const int ld = pad4((X + 7) & ~7);
+        *vec = fext[0] % 2 == 0 && all_even(1) && qs % 2 == 0;
+        for (int k = 0; k < KC; ++k)
+            for (int x = 0; x < X; x += *vec ? 2 : 1) items->push_back(make_int2(k * qs + xg[x], k * ld + x));
+        *sk = ld;
+        for (int x = 0; x < 64; ++x) xoff[x] = (short)(x < X ? x : 0);
+        *elems = KC * ld;
+    } else if (qs == 1) {                  // the chunked contracted index is fastest: [x][k]
+        const int ld = pad4(KC);
+        *vec = KC % 2 == 0 && all_even(0);
+        for (int x = 0; x < X; ++x)
+            for (int k = 0; k < KC; k += *vec ? 2 : 1) items->push_back(make_int2(xg[x] + k, x * ld + k));
+        *sk = 1;
+        for (int x = 0; x < 64; ++x) xoff[x] = (short)(x < X ? x * ld : 0);
+        *elems = X * ld;
+    } else {
+        return false;
+    }
+    return *elems <= 32767;
+}
+
 std::unordered_map<std::string, SlabPlan>& slab_cache() {
     static std::unordered_map<std::string, SlabPlan> c;
     return c;
@@ -821,6 +890,7 @@ const SlabPlan& slab_plan(const Shape& s) {
     SlabPlan best;
     long long best_score = -1;
     static const int min_k = [] { const char* e = getenv("SIPGPU_SLAB_MINK"); return e ? atoi(e) : 1024; }();
+    static const int hybrid = [] { const char* e = getenv("SIPGPU_SLAB_HYBRID"); return e ? atoi(e) : 1; }();
     if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= min_k && slab_variant(s.M, s.N)) {
         const long long perk = 8LL * (s.M + s.N);
         for (int q = 0; q < s.nk; ++q) {
@@ -829,10 +899,21 @@ const SlabPlan& slab_plan(const Shape& s) {
                 if (perk * KC > 40 * 1024) continue;
                 SlabPlan p;
                 p.q = q; p.KC = KC;
-                if (!slab_operand(s.nm, s.mext, s.msL, s.ksL[q], s.kext[q], KC, s.M, &p.a_runlen, &p.a_nruns, p.a_run, &p.a_sk, p.a_moff, &p.a_elems)) continue;
-                if (!slab_operand(s.nn, s.next, s.nsR, s.ksR[q], s.kext[q], KC, s.N, &p.b_runlen, &p.b_nruns, p.b_run, &p.b_sk, p.b_noff, &p.b_elems)) continue;
-                // prefer long runs, then long chunks (fewer barriers per byte), then few wasted k steps
-                const long long score = (long long)std::min(std::min(p.a_runlen, p.b_runlen), 512) * 1000000 + (long long)std::min(perk * KC, 24LL * 1024) * 10 + (KC % 4 == 0 ? 1 : 0);
+                const bool a_tma = slab_operand(s.nm, s.mext, s.msL, s.ksL[q], s.kext[q], KC, s.M, &p.a_runlen, &p.a_nruns, p.a_run, &p.a_sk, p.a_moff, &p.a_elems);
+                const bool b_tma = slab_operand(s.nn, s.next, s.nsR, s.ksR[q], s.kext[q], KC, s.N, &p.b_runlen, &p.b_nruns, p.b_run, &p.b_sk, p.b_noff, &p.b_elems);
+                if (!a_tma && !b_tma && hybrid < 2) continue;   // (2: both operands gathered through item tables -- measured
+                                                               //  SLOWER than the gather kernel: 2.16 vs 1.31 ms, 1.95 vs 1.21 ms)
+                if (!a_tma || !b_tma) {   // hybrid: the other operand is gathered by the threads
+                    if (hybrid <= 0) continue;
+                    if (!a_tma && !slab_gather(s.nm, s.mext, s.msL, s.ksL[q], KC, s.M, &p.a_items_h, &p.a_vec, &p.a_sk, p.a_moff, &p.a_elems)) continue;
+                    if (!b_tma && !slab_gather(s.nn, s.next, s.nsR, s.ksR[q], KC, s.N, &p.b_items_h, &p.b_vec, &p.b_sk, p.b_noff, &p.b_elems)) continue;
+                    if (!a_tma) { p.a_nruns = 0; p.a_runlen = 1 << 20; }
+                    if (!b_tma) { p.b_nruns = 0; p.b_runlen = 1 << 20; }
+                    if (8LL * (p.a_elems + p.b_elems) > 48 * 1024) continue;   // the padded staging of the gathered operand counts
+                }
+                // prefer both operands by TMA, long runs, then long chunks (fewer barriers per byte), then few wasted k steps
+                const long long score = (a_tma && b_tma ? 8000000000LL : a_tma || b_tma ? 4000000000LL : 0) + (long long)std::min(std::min(p.a_runlen, p.b_runlen), 512) * 1000000 +
+                                        (long long)std::min(perk * KC, 24LL * 1024) * 10 + (KC % 4 == 0 ? 1 : 0);
                 if (score > best_score) { best_score = score; best = p; best.ok = true; }
             }
         }
@@ -858,10 +939,15 @@ const SlabPlan& slab_plan(const Shape& s) {
             h[c] = make_int2(oL, oR);
         }
         if (best.ok) {
-            best.ctab = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * h.size(), true));
-            if (!best.ctab) best.ok = false;
-            else if (cudaMemcpyAsync(best.ctab, h.data(), sizeof(int2) * h.size(), cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess ||
-                     cudaStreamSynchronize(ctx().stream) != cudaSuccess) best.ok = false;
+            auto upload = [&](const std::vector<int2>& v) -> int2* {
+                int2* d = reinterpret_cast<int2*>(pool_alloc(sizeof(int2) * v.size(), true));
+                if (!d || cudaMemcpyAsync(d, v.data(), sizeof(int2) * v.size(), cudaMemcpyHostToDevice, ctx().stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx().stream) != cudaSuccess) { best.ok = false; return nullptr; }
+                return d;
+            };
+            best.ctab = upload(h);
+            if (best.ok && !best.a_items_h.empty()) best.a_items = upload(best.a_items_h);
+            if (best.ok && !best.b_items_h.empty()) best.b_items = upload(best.b_items_h);
         }
     }
     return slab_cache().emplace(key, best).first->second;
@@ -941,6 +1027,9 @@ int slab_try(const Shape& s, const Tables& t, int n, const std::vector<Pair>& pa
     memcpy(a.b_run, p.b_run, sizeof(a.b_run));
     memcpy(a.a_moff, p.a_moff, sizeof(a.a_moff));
     memcpy(a.b_noff, p.b_noff, sizeof(a.b_noff));
+    a.a_items = p.a_items; a.b_items = p.b_items;
+    a.a_nitems = (int)p.a_items_h.size(); a.b_nitems = (int)p.b_items_h.size();
+    a.a_vec = p.a_vec; a.b_vec = p.b_vec;
     a.alpha = alpha; a.beta = beta;
     a.p0 = probs[0]; a.pair0 = pairs[0];
     const size_t stage_bytes = (size_t)a.stage_elems * 8;

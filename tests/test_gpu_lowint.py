@@ -209,6 +209,9 @@ SLAB_CASES = [
     ("56x24", "ab", "acde", "bcde", dict(a=56, b=24, c=12, d=10, e=10)),
     ("12x60", "ab", "acde", "bcde", dict(a=12, b=60, c=12, d=10, e=10)),
     ("odd extents (gather kernel)", "ab", "acde", "bcde", dict(a=25, b=25, c=11, d=10, e=10)),
+    ("20x50, hybrid: gathered operand contracted-fastest", "ab", "acde", "cdeb", dict(a=20, b=50, c=10, d=12, e=10)),
+    ("50x25, hybrid: gathered operand in 8-byte items", "ab", "acde", "bedc", dict(a=50, b=25, c=20, d=4, e=16)),
+    ("20x20, hybrid: gathered operand on the left", "ab", "aedc", "bcde", dict(a=20, b=20, c=20, d=6, e=10)),
     ("rank-5 operands", "ab", "xacde", "xbcde", dict(a=20, b=20, c=10, d=10, e=6, x=2)),
 ]
 
@@ -241,7 +244,7 @@ def test_slab_shapes_single_block_split_along_k(sip, oracle, case, slab):
 
 
 @pytest.mark.parametrize("nblocks,chain_max", [(2, 5), (37, 3), (400, 2)])
-@pytest.mark.parametrize("case", SLAB_CASES[:5] + SLAB_CASES[7:9], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", SLAB_CASES[:5] + SLAB_CASES[7:9] + SLAB_CASES[12:15], ids=lambda c: c[0])
 def test_slab_shapes_work_lists_with_chains(sip, oracle, case, nblocks, chain_max):
     """many destinations (one item per CTA slot, the ring running across item boundaries), chains of unequal length, the
     deterministic reduction over the four warps of the K-split variants: two launches give identical bits"""
