@@ -135,6 +135,27 @@ def config4_cases():
     return cases
 
 
+def slab_cases():
+    """rank-2 results of rank-4 blocks with a long contracted range at CCSD segment sizes (occupied 20, virtual 50, 8 MB operands):
+    the shapes the TMA-fed slab kernel takes (lowint.cu: both operands in contiguous runs; one operand gathered; K order of the
+    larger operand for the matrix-vector shapes) -- the reference's legacy backend permutes both operands and calls cuBLAS"""
+    o, v = 20, 50
+    cases = []
+    for k, (d, l, r, ext) in enumerate((
+            ("ab", "cade", "cbde", dict(a=o, b=o, c=v, d=v, e=o)),      # K-fast operands, 20 x 20
+            ("ab", "acde", "bcde", dict(a=v, b=v, c=o, d=v, e=o)),      # M-fast operands, 50 x 50
+            ("ab", "acde", "cbed", dict(a=o, b=v, c=o, d=v, e=o)),      # outer contracted indices in different orders
+            ("ab", "acde", "cdeb", dict(a=o, b=v, c=v, d=v, e=o)),      # hybrid: one operand gathered
+            ("ab", "acde", "bedc", dict(a=v, b=v, c=o, d=v, e=o)),      # hybrid: 400-byte pieces
+            ("ab", "cdba", "dc", dict(a=o, b=v, c=v, d=v)))):           # matrix-vector, big operand K-fast
+        labs = sorted(set(d + l + r))
+        num = {c: i + 1 for i, c in enumerate(labs)}
+        cases.append({"kind": "contract", "seed": 4000 + k, "where": f"slab {d}={l}*{r}",
+                      "y": ([ext[c] for c in d], [num[c] for c in d]), "x1": ([ext[c] for c in l], [num[c] for c in l]),
+                      "x2": ([ext[c] for c in r], [num[c] for c in r])})
+    return cases
+
+
 def run_reference(ref_gpu, cases):
     try:
         return ref_gpu.run_cases(cases, timeout=240)[0]
@@ -178,3 +199,11 @@ def test_config4_shapes_equal_the_reference_cuda_backend(sip, ref_gpu):
     for case, w in zip(cases, want):
         err = relerr(product_case(sip, ref_gpu, case), w)
         assert err <= TOL, (case["where"], case["y"], case["x1"], case["x2"], err)
+
+
+def test_slab_shapes_equal_the_reference_cuda_backend(sip, ref_gpu):
+    cases = slab_cases()
+    want = run_reference(ref_gpu, cases)
+    for case, w in zip(cases, want):
+        err = relerr(product_case(sip, ref_gpu, case), w)
+        assert err <= TOL, (case["where"], err)
