@@ -30,8 +30,23 @@ def run_pt(oracle, case, which):
         be2 = OracleBackend(oracle, {n: {} for n in lw.pt_array_kinds(prog)}, fock=inp["fock"], moa_seg_ranges=inp["moa_seg_ranges"])
         sc = Walker(prog, be2, inp["segs"], index_base=inp["index_base"], constants=lw.pt_constants(inp)).run()
         out.update({k: be2.value(sc[k]) for k in (("eaaa", "esaaa") if name == "aaa" else ("eaab", "esaab"))})
+        if name == "aaa":
+            out["esaaa_left_in_sai"] = 0.5 * float(np.sum(dense_vo(be2, "t1as_old", inp["segs"]) * dense_vo(be2, "sai", inp["segs"])))
         calls += be2.calls
     return out, hist, calls
+
+
+def dense_vo(be, name, segs):
+    """a distributed [virtual segment, occupied segment OR occupied orbital] array of the triples program as one matrix"""
+    vo, oo = np.cumsum([0] + list(segs["v"])), np.cumsum([0] + list(segs["o"]))
+    A = np.zeros((vo[-1], oo[-1]))
+    for (a, i), blk in be.arrays.get(name, {}).items():
+        arr = blk.a if hasattr(blk, "a") else np.asarray(blk)
+        if arr.size == segs["v"][a - 1]:          # `xai[a,ii]`, `t1as_old[a,ii]`: ii is a simple index = one orbital
+            A[vo[a - 1]:vo[a], i - 1] = arr.ravel()
+        else:                                     # `sai[a,i1]`: i1 is an occupied SEGMENT
+            A[vo[a - 1]:vo[a], oo[i - 1]:oo[i]] = arr.reshape((segs["v"][a - 1], segs["o"][i - 1]), order="F")
+    return A
 
 
 # the reference's configuration (one occupied segment) and the same orbitals with the virtual space cut into 2 + 4
@@ -44,7 +59,7 @@ def test_reference_triples_programs_reproduce_the_four_components_of_second_ccsd
     got, hist, calls = run_pt(oracle, case, ("aaa", "aab"))
     for name in ("eaaa", "esaaa", "eaab", "esaab"):      # measured: 6e-15, 7e-15, 2.6e-13, 1.1e-13 (both segmentations)
         assert abs(got[name] - g[name]) < 1e-11, (name, got[name], g[name])
-    e_t = sum(got.values())
+    e_t = sum(got[k] for k in ("eaaa", "esaaa", "eaab", "esaab"))
     assert abs(e_t - (g["ccsdpt_energy"] - g["ccsd_energy"])) < 1e-11
     assert calls > 5000
 
@@ -52,15 +67,23 @@ def test_reference_triples_programs_reproduce_the_four_components_of_second_ccsd
 def test_reference_triples_programs_with_two_occupied_segments(oracle):
     """occupied 2 + 3, virtual 2 + 4 (several batches of the set_ijk table, stripi across segment boundaries): eaab, esaab and
     eaaa equal the goldens as before.  esaaa -- the singles part of the AAA program -- comes out 1.0e-9 off (2.4022e-06 vs
-    2.4012e-06), by an amount that depends on how the occupied space is cut (3 + 2: -1.9e-8) while every other component and
-    the single-occupied-segment runs are exact; the restated textbook (T) gives the golden at every segmentation.  The
-    reference only ever tests one occupied segment; whether the deviation is the reference program's or this front-end's is
-    open, so it is recorded here at the size observed, not asserted away."""
+    2.4012e-06), by an amount that depends on how the occupied space is cut.  Cause (settled in round 2): the REFERENCE program
+    accumulates part of the singles intermediate into `Sai[a2,k1]` (k1 an occupied segment: `PUT Sai[a2,k1] += tpp[a2,k1]`,
+    rccsdpt_aaa.sialx:3935 ff) and the rest into `Xai[a,ii]` (ii an orbital), but its energy loop reads `Xai` only -- the lines
+    that read `Sai` are commented out (rccsdpt_aaa.sialx:6001-6002).  With ONE occupied segment, which is all the reference
+    ever tests, the `Sai` branches contribute exactly nothing; with several they hold what is missing: adding
+    1/2 sum t1as_old * Sai restores the golden to 1e-16, at every segmentation.  The front-end reproduces the program as written."""
     g = lw.GOLDEN["hf"]
     got, hist, calls = run_pt(oracle, "hf_fine", ("aaa", "aab"))
     for name in ("eaaa", "eaab", "esaab"):
         assert abs(got[name] - g[name]) < 1e-11, (name, got[name], g[name])
-    assert abs(got["esaaa"] - g["esaaa"]) < 2e-9, got["esaaa"]
+    assert 5e-10 < abs(got["esaaa"] - g["esaaa"]) < 2e-9, got["esaaa"]                      # the program as written
+    assert abs(got["esaaa"] + got["esaaa_left_in_sai"] - g["esaaa"]) < 1e-13, got          # ... and with what it leaves in Sai
+
+
+def test_one_occupied_segment_leaves_nothing_in_sai(oracle):
+    got, _, _ = run_pt(oracle, "hf_dat", ("aaa",))
+    assert got["esaaa_left_in_sai"] == 0.0 and abs(got["esaaa"] - lw.GOLDEN["hf"]["esaaa"]) < 1e-11
 
 
 def test_reference_aab_program_reproduces_the_goldens_of_ccsdpt_test_dat(oracle):
