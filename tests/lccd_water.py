@@ -259,6 +259,9 @@ PROGRAM_RLCCD = open(os.path.join(HERE, "golden", "rlccd_rhf_program.sialx")).re
 PROGRAM_RLCCSD = open(os.path.join(HERE, "golden", "rlccsd_rhf_program.sialx")).read()
 PROGRAM_RLAMBDA = open(os.path.join(HERE, "golden", "rlambda_rhf_program.sialx")).read()   # src/sialx/qm/cc/rlambda_rhf.sialx
 CASES["hf_fc_virt_fine"] = ("lamccsdpt_test.dat", {"moa": [1, 4, 2, 4], "occ": (2, 2), "virt": (3, 4), "ao": [3, 6, 2]})
+# two ACTIVE occupied segments of two orbitals each (hf_fc_fine above cuts them 3 + 1: a one-orbital segment, which the reference's
+# energy_denominator_rhf.F takes for a simple index)
+CASES["hf_fc_occ22"] = ("lamccsdpt_test.dat", {"moa": [1, 2, 2, 2, 4], "occ": (2, 3), "virt": (4, 5), "ao": [3, 6, 2]})
 CASES["lam_dat"] = ("rlambda_test.dat", None)       # hydrogen fluoride / 3-21G, cc_conv 1e-12 (the reference's rlambda_test)
 CASES["lam_fine"] = ("rlambda_test.dat", {"moa": [2, 3, 2, 4], "occ": (1, 2), "virt": (3, 4), "ao": [3, 6, 2]})
 PROGRAM_RLAMPT_AAA = open(os.path.join(HERE, "golden", "rlamccsdpt_aaa_program.sialx")).read()   # src/sialx/qm/cc/rlamccsdpt_aaa.sialx

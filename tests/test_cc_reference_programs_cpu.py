@@ -145,7 +145,7 @@ def test_reference_lambda_program_reproduces_rlambda_test(oracle, case):
     assert {"l1a_old", "L2old_aa", "L2old_ab", "t1a_old", "T2old_ab"} <= set(OracleBackend.registry)
 
 
-@pytest.mark.parametrize("case", ["hf_fc_dat", "hf_fc_virt_fine"])
+@pytest.mark.parametrize("case", ["hf_fc_dat", "hf_fc_virt_fine", "hf_fc_occ22"])
 def test_reference_lambda_ccsdpt_programs_reproduce_lamccsdpt_test(oracle, case):
     """The reference's ENABLED lamccsdpt_test (test/test_qm.cpp:798-869; hydrogen fluoride / 3-21G, frozen core): scf ->
     tran_rhf_no4v -> rccsd_rhf -> rlambda_rhf -> rlamccsdpt_aaa -> rlamccsdpt_aab, every program the reference's text with the one
@@ -153,9 +153,9 @@ def test_reference_lambda_ccsdpt_programs_reproduce_lamccsdpt_test(oracle, case)
     stripi / one-segment-contraction / rank-6 accumulate inner loops of the (T) programs with lambda amplitudes on the left.
     Every number the test asserts (1e-10).  measured: ccsd_energy 7e-13, eaaa 5e-16, esaaa 1e-15, eaab 2e-15, esaab 1e-16,
     ccsdpt_energy 1e-12.  hf_fc_virt_fine: the virtual space cut into 2 + 4 (AO 3 + 6 + 2), the occupied space in ONE segment like in
-    every setup the reference ships -- with two active occupied segments the AAA programs' batch logic (set_ijk_aaa pieces across
-    segment boundaries) gives eaaa 1e-7 off, as observed for rccsdpt_aaa in tests/test_ccsdpt_reference_programs_cpu.py; whether
-    that is the reference program's or this front-end's is open, the reference never runs such a segmentation."""
+    every setup the reference ships.  hf_fc_occ22: the four active occupied orbitals in TWO segments of two (eaaa 5e-16, esaaa 1.5e-15:
+    set_ijk_aaa pieces across segment boundaries are fine).  The 1e-7 deviation seen earlier at a 3 + 1 cut is the one-orbital
+    segment: energy_denominator_rhf.F takes any extent-1 dimension of a rank-6 block for a simple index."""
     g = lw.GOLDEN["lamccsdpt_test"]
     W.host_registry.clear()
     run_cc_program(oracle, "tran_rhf_no4v", case)

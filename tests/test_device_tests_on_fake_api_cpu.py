@@ -66,7 +66,7 @@ def test_reference_cc_programs_device_test_bodies_on_the_fake_api(oracle):
     cc.test_config_1_from_ao_integrals_on_the_device(FakeApi(oracle))
     cc.test_reference_cis_program_on_the_device(FakeApi(oracle))
     cc.test_reference_lambda_program_on_the_device(FakeApi(oracle))
-    cc.test_reference_lambda_ccsdpt_programs_on_the_device(FakeApi(oracle))
+    cc.test_reference_lambda_ccsdpt_programs_on_the_device(FakeApi(oracle), "hf_fc_dat")
     cc.test_reference_cis_and_cis_d_programs_on_the_device(FakeApi(oracle))
 
 

@@ -93,10 +93,11 @@ def test_reference_lambda_program_on_the_device(sip):
 
 
 @pytest.mark.timeout(900, method="thread")
-def test_reference_lambda_ccsdpt_programs_on_the_device(sip):
+@pytest.mark.parametrize("case", ["hf_fc_dat", "hf_fc_occ22"])
+def test_reference_lambda_ccsdpt_programs_on_the_device(sip, case):
     """the reference's enabled lamccsdpt_test on libsipgpu (hydrogen fluoride / 3-21G, frozen core): tran_rhf_no4v -> rccsd_rhf ->
-    rlambda_rhf -> rlamccsdpt_aaa -> rlamccsdpt_aab verbatim; every number the test asserts, at its 1e-10"""
-    case = "hf_fc_dat"
+    rlambda_rhf -> rlamccsdpt_aaa -> rlamccsdpt_aab verbatim; every number the test asserts, at its 1e-10 -- at the setup's
+    segmentation and with the active occupied orbitals in two segments (the triples batches cross segment boundaries)"""
     inp = lw.inputs(case)
     g = lw.GOLDEN["lamccsdpt_test"]
     seg_ext, aoint, fock = dc.hand_over_scf_and_transformation(sip, case, inp, transformed=False)
