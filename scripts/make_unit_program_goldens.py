@@ -19,7 +19,9 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          "persistent_static_array_test1", "persistent_static_array_test2",
          # the pardo work distribution and the interpreter's scalar / int / if-else arithmetic (no block operations)
          "pardo_loop", "pardo_loop_1d", "pardo_loop_2d", "pardo_loop_3d", "pardo_loop_4d", "pardo_loop_5d", "pardo_loop_6d",
-         "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast")
+         "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast",
+         # programs whose printed blocks the reference compares with fixture files (test/expected_output/*.txt)
+         "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays")
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
 for name in NAMES:
     text = open(SRC + name + ".sialx", errors="replace").read()
@@ -27,3 +29,9 @@ for name in NAMES:
             "# SIAL front-end (copied by scripts/make_unit_program_goldens.py)\n")
     open(os.path.join(ROOT, "tests", "golden", "ref_unit_programs", name + ".sialx"), "w").write(head + text)
 print(len(NAMES), "programs")
+
+# the reference's expected-output fixtures (printed blocks) for those programs, verbatim
+FIX = "/root/reference/test/expected_output/"
+os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_expected_output"), exist_ok=True)
+for name in ("static_array_test", "tmp_arrays", "tmp_arrays_2", "scalar_valued_blocks", "local_arrays"):
+    open(os.path.join(ROOT, "tests", "golden", "ref_expected_output", name + ".txt"), "w").write(open(FIX + name + ".txt").read())

@@ -22,6 +22,11 @@ def _fill(kind):
     """the reference's test super-instructions fill_block_cyclic / fill_block_sequential (super_instructions/.../fill_block_*.f):
     element n (column-major, 0-based) = ((n + start - 1) mod 20) + 1  /  start + n"""
     def si(w, args, bare):
+        if not args:      # `execute fill_block_sequential a 1.0`: a whole static array, contiguous in the SIP (static_array_test.sialx)
+            name, start = bare[0], float(bare[1])
+            _, dims = w._static_blocks(name)
+            w._static_scatter(name, (oracle.fill_cyclic if kind == "cyclic" else oracle.fill_sequential)(tuple(dims), start))
+            return
         name, labs = args[0]
         start = float(bare[0]) if bare[0].replace(".", "", 1).replace("-", "", 1).isdigit() else w.be.value(w.scalars[bare[0]])
         h = w._write(name, labs)
@@ -52,7 +57,29 @@ def dim_segments(prog, label, seg_tables, constants):
     return list(seg_tables["mo"][val(lo) - 1: val(hi)])
 
 
-def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend=None, rank=0, world=1):
+def expected_blocks(name):
+    """the blocks the reference's expected-output fixture of a test holds (test/expected_output/<name>.txt, copied verbatim into
+    tests/golden/ref_expected_output/): [(array, index values, values in memory order)] in the order printed"""
+    import re
+    out, cur = [], None
+    for line in open(os.path.join(HERE, "golden", "ref_expected_output", name + ".txt")):
+        m = re.match(r"\s*\d+:\s+printing (\d+) of (\d+) elements of (block|contiguous array) (\w+)(?:\[([\d,\s]*)\])? in the order stored", line)
+        if m:
+            cur = (m.group(4), tuple(int(x) for x in m.group(5).split(",")) if m.group(5) else (), [])
+            out.append(cur)
+            assert m.group(1) == m.group(2)
+            want = int(m.group(1))
+            continue
+        if cur is not None and len(cur[2]) < want:
+            try:
+                cur[2].extend(float(x) for x in line.split())
+            except ValueError:
+                cur = None
+    assert all(len(v) > 0 for _, _, v in out)
+    return out
+
+
+def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend=None, rank=0, world=1, print_hook=None):
     prog = Program(text(name))
     be = backend or make_backend(prog, {"ao": ao or [], "mo": mo or []}, constants or {})
     segs = {"ao": list(ao or []), "pa": list(mo or [])}
@@ -62,6 +89,7 @@ def run(name, make_backend, ao=None, mo=None, constants=None, arrays=(), backend
         segs["v"] = mo[c["bavirt"] - 1: c["eavirt"]]
     w = Walker(prog, be, segs, rank=rank, world=world, constants=c, seg_tables={"ao": ao or [], "mo": mo or []}, extra_si=EXTRA_SI,
                index_base={"o": c.get("baocc", 1) - 1, "v": c.get("bavirt", 1) - 1})
+    w.print_hook = print_hook
     w.run()
     return w, be
 
@@ -274,6 +302,32 @@ def interpreter_arithmetic(make_backend, to_numpy):
 HOST_ONLY = (pardo_loops, interpreter_arithmetic)
 
 
+def printed_blocks_equal_the_reference_fixtures(make_backend, to_numpy):
+    """BasicSial.static_array_test (blocks extracted from a static array that was filled as ONE contiguous array, test_basic_sial.cpp:918-940),
+    tmp_arrays, tmp_arrays_2 (:526-579), local_arrays: the reference compares what the program PRINTS with a fixture file
+    (`EXPECT_EQ(controller.expectedOutput(), output.str())`); here every printed block is compared, in order, with the blocks of that
+    same fixture"""
+    for name, ao, consts in (("static_array_test", [3, 4], {"norb": 2, "x": 3.456}), ("tmp_arrays", [2, 3, 4], {"norb": 3, "x": 3.456}),
+                             ("tmp_arrays_2", [2, 3, 4], {"norb": 3, "x": 3.456}), ("local_arrays", [2, 3], {"norb": 2, "x": 3.456})):
+        printed = []
+        w, be = run(name, make_backend, ao=ao, constants=consts,
+                    print_hook=lambda arr, idx, a: printed.append((arr, idx, np.asarray(a).ravel(order="F").copy())))
+        want = [b for b in expected_blocks(name) if b[1]]
+        assert len(printed) == len(want) > 0, (name, len(printed), len(want))
+        for (arr, idx, vals), (warr, widx, wvals) in zip(printed, want):
+            assert (arr, idx) == (warr, widx) and np.array_equal(vals, np.array(wvals)), (name, arr, idx)
+        if name == "static_array_test":      # `print a`: the whole contiguous array, in memory order
+            whole = [b for b in expected_blocks(name) if not b[1]]
+            assert len(whole) == 1 and np.array_equal(w._static_dense("a").ravel(order="F"), np.array(whole[0][2]))
+    # scalar_valued_blocks (test_basic_sial.cpp:581-621): one-element blocks over simple indices read and written as numbers
+    printed = []
+    run("scalar_valued_blocks", make_backend, print_hook=lambda arr, idx, a: printed.append(float(np.asarray(a).ravel()[0])))
+    assert printed == [1.0, 2.0, 3.0] + [float(j + k) for k in (1, 2, 3) for j in (1, 2, 3, 4, 5)]
+    # simple_indices_assignments (:1086-1109)
+    w, be = run("simple_indices_assignments", make_backend, ao=[8, 8], constants={"norb": 2, "x": 3.456})
+    assert be.value(w.scalars["x"]) == 50 and be.value(w.scalars["y"]) == 50
+
+
 def runs_to_completion(make_backend, to_numpy):
     """BasicSial.tmp_arrays / tmp_arrays_2 / block_scale_assign (:526-650), Sial.put_accumulate_mpi: the reference compares printed
     output; here: the programs run to completion through the same statements (block fill / scale / add / subtract / copy with
@@ -285,4 +339,4 @@ def runs_to_completion(make_backend, to_numpy):
 
 ALL = (contraction_small_test, contraction_small_test2, transpose_tmp, transpose4d_tmp, transpose4d_square_tmp, contract_to_scalar,
        sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, put_initialize_and_increment, gpu_path_programs,
-       persistence_between_programs, runs_to_completion)
+       persistence_between_programs, printed_blocks_equal_the_reference_fixtures, runs_to_completion)
