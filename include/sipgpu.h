@@ -232,9 +232,12 @@ int sipgpu_trace_report(int cap, const char** names, long long* calls, double* h
  * path).  "lowint_max_intensity": contractions with N <= 64 and at most this many flops per algorithmic byte run on the
  * bandwidth-shaped kernel (lowint.cu; default 7.0 = just above the roofline ridge of 5.7; negative: never).
  * "lowint_scope": 0 never, 1 (default) dot products + single-tile destinations where that kernel measured faster than the
- * 128-wide tiles, 2 every eligible shape (tests, A/B).  "permute_bulk": 1 (default) permutes whose input runs are 16-byte
- * aligned fetch their tiles with TMA bulk copies (cp.async.bulk), 0 the register-staged kernel only.  Returns SIPGPU_E_ARG
- * for an unknown key.  Host-only. */
+ * 128-wide tiles, 2 every eligible shape (tests, A/B).  "lowint_slab": 1 (default) small results of long contractions whose
+ * chunks are contiguous runs are fed by TMA bulk copies (slab_kernel), 0 never.  "permute_bulk": which permute kernel --
+ * 0 register-staged, 1 TMA bulk runs, 2 cp.async ring, 3 (default) chosen per launch.  "permute_vec": -1 (default) / 0 / 1
+ * 16-byte accesses in the ring kernel.  "copy_bulk": bit 0 whole-block copies (get / put), bit 1 put += travel as TMA bulk
+ * transfers (default 3), 0 LDG.128 / red.global.add.f64; -1 back to the environment / default.  Returns SIPGPU_E_ARG for an
+ * unknown key.  Host-only. */
 int sipgpu_set_tuning(const char* key, double value);
 
 /* host-only views of the planner (no device needed; used by the CPU tests of the host logic) */
