@@ -465,7 +465,9 @@ __device__ __forceinline__ void slab_cursor_next(SlabCursor& q, const SlabArgs& 
     if (++q.kc == a.cpp) { q.kc = 0; ++q.pair; }
 }
 
-template <int MF, int NF, bool KSPLIT>
+// GATHER: one operand is gathered by the threads (hybrid).  A separate instantiation: with the gather code compiled into the
+// all-TMA kernel the K-split variants lost 15-20 % (0.63 -> 0.77 ms on 50 x 20 results), although none of it executes there.
+template <int MF, int NF, bool KSPLIT, bool GATHER>
 __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabArgs a) {
     extern __shared__ __align__(16) double sm[];
     __shared__ unsigned long long full[kSlabMaxStages];
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
     for (int i = 0; i < MF; ++i) moff[i] = a.a_moff[8 * i + g];
 #pragma unroll
     for (int j = 0; j < NF; ++j) noff[j] = a.a_elems + a.b_noff[ncol0 + 8 * j + g];
-    const bool gather = a.a_items != nullptr || a.b_items != nullptr;
+    constexpr bool gather = GATHER;
     if (tid == 0) {
         const int count = gather ? 1 + kLT : 1;   // the expect_tx arrival (+ one asynchronous arrival per gathering thread)
         for (int s = 0; s < a.stages; ++s)
@@ -494,7 +496,6 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
     const unsigned stage_bytes = 8u * (unsigned)((a.a_items ? 0 : a.a_nruns * a.a_runlen) + (a.b_items ? 0 : a.b_nruns * a.b_runlen));
     auto issue = [&](int stage) {   // the chunk at the prefetch cursor -> stage (warp 0: TMA runs; everybody: gathers); cursor moves on
         if (pf.w >= nwork) return;
-        if (warp != 0 && !gather) return;
         Pair pq;
         if (a.probs) {
             const int4 raw = __ldg(reinterpret_cast<const int4*>(a.pairs + pf.pair));
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         const int2 co = __ldg(a.ctab + pf.kc);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(full + stage);
         double* st = sm + (size_t)stage * a.stage_elems;
-        if (gather) {
+        if constexpr (GATHER) {
             if (a.a_items) {
                 const double* base = pq.L + co.x;
                 for (int i = tid; i < a.a_nitems; i += kLT) {
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
         }
-        if (warp == 0) {
+        if (!GATHER || warp == 0) {
         if (lane == 0) asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(stage_bytes) : "memory");
         __syncwarp();
         if (!a.a_items && lane < a.a_nruns)
@@ -539,7 +540,8 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         slab_cursor_next(pf, a);
         if (pf.c == pf.c_end) slab_cursor_load(pf, a, pf.w + gridDim.x, nwork);
     };
-    for (int s = 0; s < a.stages; ++s) issue(s);
+    if (GATHER || warp == 0)
+        for (int s = 0; s < a.stages; ++s) issue(s);
 
     double acc[MF][NF][2];
 #pragma unroll
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         slab_cursor_next(cp, a);
         const bool item_done = cp.c == cp.c_end;
         __syncthreads();   // every warp is done with the stage
-        issue(stage);
+        if (GATHER || warp == 0) issue(stage);
         if (++stage == a.stages) { stage = 0; parity ^= 1; }
         if (!item_done) continue;
         // ---- end of the item: (KSPLIT: sum the four warps' partial tiles in a fixed order) and write D ----
@@ -953,9 +955,9 @@ const SlabPlan& slab_plan(const Shape& s) {
     return slab_cache().emplace(key, best).first->second;
 }
 
-template <int MF, int NF, bool KSPLIT>
+template <int MF, int NF, bool KSPLIT, bool GATHER>
 int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total_chunks, const std::function<int()>& prescale) {
-    auto* kern = slab_kernel<MF, NF, KSPLIT>;
+    auto* kern = slab_kernel<MF, NF, KSPLIT, GATHER>;
     static bool attr = false;
     if (!attr) {
         SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -964,7 +966,11 @@ int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total
     }
     const size_t red_bytes = KSPLIT ? (size_t)MF * NF * 64 * 8 : 0;
     // ring depth: two CTAs per SM when the stages are small (<= 96 KB per CTA), else one
-    int stages = (int)std::min<size_t>(kSlabMaxStages, (96 * 1024 - red_bytes) / stage_bytes);
+    static const int ring_kb = [] { const char* e = getenv("SIPGPU_SLAB_RING_KB"); return e ? atoi(e) : 96; }();
+    // three stages, not as many as fit: occupancy beats ring depth (20 x 20 results, 16 KB stages: 6 stages = 2 CTAs per SM
+    // 0.85 ms, 3 stages = 4 CTAs per SM 0.63 ms = 6.3 TB/s; the 28-32 KB stages of the larger tiles get 3 either way)
+    static const int max_st = [] { const char* e = getenv("SIPGPU_SLAB_MAX_STAGES"); return e ? std::min(atoi(e), kSlabMaxStages) : 3; }();
+    int stages = (int)std::min<size_t>(max_st, ((size_t)ring_kb * 1024 - red_bytes) / stage_bytes);
     if (stages < 3) stages = (int)std::min<size_t>(kSlabMaxStages, (200 * 1024 - red_bytes) / stage_bytes);
     if (stages < 2) return SIPGPU_E_ARG;
     a.stages = stages;
@@ -1036,7 +1042,9 @@ int slab_try(const Shape& s, const Tables& t, int n, const std::vector<Pair>& pa
     const long long total_chunks = total_pairs * p.cpp;
     *done = true;
 #define SLAB_CASE(MF_, NF_, KS_) \
-    if (v->mf == MF_ && v->nf == NF_ && v->ksplit == KS_) return launch_slab<MF_, NF_, KS_>(a, stage_bytes, dense_d, total_chunks, run_prescale)
+    if (v->mf == MF_ && v->nf == NF_ && v->ksplit == KS_)                                                                   \
+        return (a.a_items || a.b_items) ? launch_slab<MF_, NF_, KS_, true>(a, stage_bytes, dense_d, total_chunks, run_prescale) \
+                                        : launch_slab<MF_, NF_, KS_, false>(a, stage_bytes, dense_d, total_chunks, run_prescale)
     SLAB_CASE(2, 2, true); SLAB_CASE(3, 3, true); SLAB_CASE(4, 4, true); SLAB_CASE(3, 7, true); SLAB_CASE(7, 3, true);
     SLAB_CASE(5, 2, false); SLAB_CASE(6, 2, false); SLAB_CASE(7, 2, false); SLAB_CASE(8, 2, false);
 #undef SLAB_CASE
