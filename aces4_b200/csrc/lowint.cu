@@ -893,12 +893,14 @@ const SlabPlan& slab_plan(const Shape& s) {
     long long best_score = -1;
     static const int min_k = [] { const char* e = getenv("SIPGPU_SLAB_MINK"); return e ? atoi(e) : 1024; }();
     static const int hybrid = [] { const char* e = getenv("SIPGPU_SLAB_HYBRID"); return e ? atoi(e) : 1; }();
+    static const long long chunk_cap = [] { const char* e = getenv("SIPGPU_SLAB_CHUNK_KB"); return (e ? atoll(e) : 24LL) * 1024; }();
+    static const long long stage_cap = [] { const char* e = getenv("SIPGPU_SLAB_STAGE_KB"); return (e ? atoll(e) : 40LL) * 1024; }();
     if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= min_k && slab_variant(s.M, s.N)) {
         const long long perk = 8LL * (s.M + s.N);
         for (int q = 0; q < s.nk; ++q) {
             for (int KC = std::min(s.kext[q], 128); KC >= 8; --KC) {
                 if (s.kext[q] % KC) continue;
-                if (perk * KC > 40 * 1024) continue;
+                if (perk * KC > stage_cap) continue;
                 SlabPlan p;
                 p.q = q; p.KC = KC;
                 const bool a_tma = slab_operand(s.nm, s.mext, s.msL, s.ksL[q], s.kext[q], KC, s.M, &p.a_runlen, &p.a_nruns, p.a_run, &p.a_sk, p.a_moff, &p.a_elems);
@@ -915,7 +917,7 @@ const SlabPlan& slab_plan(const Shape& s) {
                 }
                 // prefer both operands by TMA, long runs, then long chunks (fewer barriers per byte), then few wasted k steps
                 const long long score = (a_tma && b_tma ? 8000000000LL : a_tma || b_tma ? 4000000000LL : 0) + (long long)std::min(std::min(p.a_runlen, p.b_runlen), 512) * 1000000 +
-                                        (long long)std::min(perk * KC, 24LL * 1024) * 10 + (KC % 4 == 0 ? 1 : 0);
+                                        (long long)std::min(perk * KC, chunk_cap) * 10 + (KC % 4 == 0 ? 1 : 0);
                 if (score > best_score) { best_score = score; best = p; best.ok = true; }
             }
         }
