@@ -467,8 +467,11 @@ __device__ __forceinline__ void slab_cursor_next(SlabCursor& q, const SlabArgs& 
 
 // GATHER: one operand is gathered by the threads (hybrid).  A separate instantiation: with the gather code compiled into the
 // all-TMA kernel the K-split variants lost 15-20 % (0.63 -> 0.77 ms on 50 x 20 results), although none of it executes there.
-template <int MF, int NF, bool KSPLIT, bool GATHER>
-__global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabArgs a) {
+// NW: warps per CTA.  4, or 1 for tiny matrices (K <= 64: every item is ONE chunk, so a CTA-wide barrier and the cross-warp sum
+// per item would cost more than the item; a single warp owns the whole tile and only ever waits for its own copies)
+template <int MF, int NF, bool KSPLIT, bool GATHER, int NW>
+__global__ void __launch_bounds__(32 * NW) slab_kernel(const __grid_constant__ SlabArgs a) {
+    static_assert(NW == 4 || (NW == 1 && !KSPLIT), "one warp holds the whole tile");
     extern __shared__ __align__(16) double sm[];
     __shared__ unsigned long long full[kSlabMaxStages];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
     for (int j = 0; j < NF; ++j) noff[j] = a.a_elems + a.b_noff[ncol0 + 8 * j + g];
     constexpr bool gather = GATHER;
     if (tid == 0) {
-        const int count = gather ? 1 + kLT : 1;   // the expect_tx arrival (+ one asynchronous arrival per gathering thread)
+        const int count = gather ? 1 + 32 * NW : 1;   // the expect_tx arrival (+ one asynchronous arrival per gathering thread)
         for (int s = 0; s < a.stages; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(full + s)), "r"(count) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -509,14 +512,14 @@ __global__ void __launch_bounds__(kLT) slab_kernel(const __grid_constant__ SlabA
         if constexpr (GATHER) {
             if (a.a_items) {
                 const double* base = pq.L + co.x;
-                for (int i = tid; i < a.a_nitems; i += kLT) {
+                for (int i = tid; i < a.a_nitems; i += 32 * NW) {
                     const int2 e = __ldg(a.a_items + i);
                     if (a.a_vec) cpa16(st + e.y, base + e.x, true); else cpa8(st + e.y, base + e.x, true);
                 }
             }
             if (a.b_items) {
                 const double* base = pq.R + co.y;
-                for (int i = tid; i < a.b_nitems; i += kLT) {
+                for (int i = tid; i < a.b_nitems; i += 32 * NW) {
                     const int2 e = __ldg(a.b_items + i);
                     if (a.b_vec) cpa16(st + a.a_elems + e.y, base + e.x, true); else cpa8(st + a.a_elems + e.y, base + e.x, true);
                 }
@@ -748,6 +751,7 @@ int launch_low(LowArgs& a, size_t smem, long long nwork0, bool may_split, long l
 struct SlabPlan {
     bool ok = false;
     int q = -1, KC = 0, cpp = 0;
+    bool tiny = false;   // K <= 64: one chunk per item, single-warp CTAs
     int a_sk = 0, b_sk = 0, a_elems = 0, b_elems = 0;
     int a_nruns = 0, b_nruns = 0, a_runlen = 0, b_runlen = 0;
     int a_run[kSlabMaxRuns], b_run[kSlabMaxRuns];
@@ -868,15 +872,18 @@ int& slab_mode() {
 // menu of warp arrangements: KSPLIT (every warp the whole tile, a quarter of the k steps) and N split over the 4 warps.
 // (KSPLIT 7 x 7 for 50 x 50 was tried: 254 registers, one CTA per SM, every warp reading the whole staged tile -- 0.88 ms
 // against 0.58 ms for the N split with its 8 padded columns.)
-struct SlabVariant { int mf, nf; bool ksplit; };
-const SlabVariant kSlabMenu[] = {{2, 2, true}, {3, 3, true}, {4, 4, true}, {3, 7, true}, {7, 3, true},
-                                 {5, 2, false}, {6, 2, false}, {7, 2, false}, {8, 2, false}};
-const SlabVariant* slab_variant(int M, int N) {
+struct SlabVariant { int mf, nf; bool ksplit; int nw; };
+const SlabVariant kSlabMenu[] = {{2, 2, true, 4}, {3, 3, true, 4}, {4, 4, true, 4}, {3, 7, true, 4}, {7, 3, true, 4},
+                                 {5, 2, false, 4}, {6, 2, false, 4}, {7, 2, false, 4}, {8, 2, false, 4},
+                                 {3, 3, false, 1}, {3, 7, false, 1}, {7, 3, false, 1}};   // tiny matrices: one warp per CTA
+// (7 x 7 fragments in one warp: 1.68 ms against 0.51 ms for 16 384 blocks of 50 x 50 x 50 on the gather kernel -- not on the menu)
+const SlabVariant* slab_variant(int M, int N, bool tiny = false) {
     const int mf = (M + 7) / 8, nf = (N + 7) / 8;
     const SlabVariant* best = nullptr;
     double best_cost = 1e30;
     for (const SlabVariant& v : kSlabMenu) {
-        const bool covers = v.ksplit ? (v.mf >= mf && v.nf >= nf) : (v.mf >= mf && 4 * v.nf >= nf);
+        if ((v.nw == 1) != tiny) continue;
+        const bool covers = (v.ksplit || v.nw == 1) ? (v.mf >= mf && v.nf >= nf) : (v.mf >= mf && 4 * v.nf >= nf);
         if (!covers) continue;
         const double cost = v.ksplit ? v.mf * v.nf / 4.0 : v.mf * v.nf;
         if (cost < best_cost) { best_cost = cost; best = &v; }
@@ -895,14 +902,19 @@ const SlabPlan& slab_plan(const Shape& s) {
     static const int hybrid = [] { const char* e = getenv("SIPGPU_SLAB_HYBRID"); return e ? atoi(e) : 1; }();
     static const long long chunk_cap = [] { const char* e = getenv("SIPGPU_SLAB_CHUNK_KB"); return (e ? atoll(e) : 24LL) * 1024; }();
     static const long long stage_cap = [] { const char* e = getenv("SIPGPU_SLAB_STAGE_KB"); return (e ? atoll(e) : 40LL) * 1024; }();
-    if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && s.K >= min_k && slab_variant(s.M, s.N)) {
+    // tiny matrices (D[a,b] = L[a,c]*R[c,b], a few hundred elements): measured against the gather kernel at 16 384 blocks per launch
+    // 20 x 20 x 50: 118 vs 201 us, 20 x 50 x 20: 155-163 vs 204-287 us, 20 x 50 x 50: 304-310 vs 287-370 us (SIPGPU_SLAB_TINY=0: off)
+    static const int tiny_on = [] { const char* e = getenv("SIPGPU_SLAB_TINY"); return e ? atoi(e) : 1; }();
+    const bool tiny = tiny_on > 0 && s.K < min_k && s.nk == 1 && s.K >= 8 && s.K <= 64;   // one chunk per item, one warp per CTA
+    if (s.M <= 64 && s.N <= 64 && s.M >= 2 && s.N >= 2 && (s.K >= min_k || tiny) && slab_variant(s.M, s.N, tiny)) {
         const long long perk = 8LL * (s.M + s.N);
         for (int q = 0; q < s.nk; ++q) {
             for (int KC = std::min(s.kext[q], 128); KC >= 8; --KC) {
                 if (s.kext[q] % KC) continue;
+                if (tiny && KC != s.K) continue;
                 if (perk * KC > stage_cap) continue;
                 SlabPlan p;
-                p.q = q; p.KC = KC;
+                p.q = q; p.KC = KC; p.tiny = tiny;
                 const bool a_tma = slab_operand(s.nm, s.mext, s.msL, s.ksL[q], s.kext[q], KC, s.M, &p.a_runlen, &p.a_nruns, p.a_run, &p.a_sk, p.a_moff, &p.a_elems);
                 const bool b_tma = slab_operand(s.nn, s.next, s.nsR, s.ksR[q], s.kext[q], KC, s.N, &p.b_runlen, &p.b_nruns, p.b_run, &p.b_sk, p.b_noff, &p.b_elems);
                 if (!a_tma && !b_tma && hybrid < 2) continue;   // (2: both operands gathered through item tables -- measured
@@ -957,9 +969,9 @@ const SlabPlan& slab_plan(const Shape& s) {
     return slab_cache().emplace(key, best).first->second;
 }
 
-template <int MF, int NF, bool KSPLIT, bool GATHER>
+template <int MF, int NF, bool KSPLIT, bool GATHER, int NW>
 int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total_chunks, const std::function<int()>& prescale) {
-    auto* kern = slab_kernel<MF, NF, KSPLIT, GATHER>;
+    auto* kern = slab_kernel<MF, NF, KSPLIT, GATHER, NW>;
     static bool attr = false;
     if (!attr) {
         SIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -973,12 +985,13 @@ int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total
     // 0.85 ms, 3 stages = 4 CTAs per SM 0.63 ms = 6.3 TB/s; the 28-32 KB stages of the larger tiles get 3 either way)
     static const int max_st = [] { const char* e = getenv("SIPGPU_SLAB_MAX_STAGES"); return e ? std::min(atoi(e), kSlabMaxStages) : 3; }();
     int stages = (int)std::min<size_t>(max_st, ((size_t)ring_kb * 1024 - red_bytes) / stage_bytes);
-    if (stages < 3) stages = (int)std::min<size_t>(kSlabMaxStages, (200 * 1024 - red_bytes) / stage_bytes);
+    if (NW == 1) stages = 2;   // one chunk per item: the next item's chunk in flight is all there is to overlap
+    if (stages < 3 && NW != 1) stages = (int)std::min<size_t>(kSlabMaxStages, (200 * 1024 - red_bytes) / stage_bytes);
     if (stages < 2) return SIPGPU_E_ARG;
     a.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + red_bytes;
     int occ = 1;
-    SIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLT, smem));
+    SIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NW, smem));
     if (occ < 1) occ = 1;
     const long long slots = (long long)ctx().num_sms * occ;
     long long ns = 1;
@@ -1002,7 +1015,7 @@ int launch_slab(SlabArgs& a, size_t stage_bytes, bool may_split, long long total
     if (nwork >= (1LL << 31)) return SIPGPU_E_ARG;
     const int grid = (int)std::min<long long>(nwork, slots);
     auto go = [a, grid, smem, kern]() -> int {
-        kern<<<grid, kLT, smem, ctx().stream>>>(a);
+        kern<<<grid, 32 * NW, smem, ctx().stream>>>(a);
         SIP_CUDA(cudaGetLastError());
         count_launch();
         return SIPGPU_OK;
@@ -1021,7 +1034,7 @@ int slab_try(const Shape& s, const Tables& t, int n, const std::vector<Pair>& pa
     if (!p.ok) return SIPGPU_OK;
     for (const Pair& pr : pairs)
         if (((uintptr_t)pr.L | (uintptr_t)pr.R) & 15) return SIPGPU_OK;
-    const SlabVariant* v = slab_variant(s.M, s.N);
+    const SlabVariant* v = slab_variant(s.M, s.N, p.tiny);
     SlabArgs a;
     memset(&a, 0, sizeof(a));
     a.probs = d_probs; a.pairs = d_pairs;
@@ -1043,12 +1056,13 @@ int slab_try(const Shape& s, const Tables& t, int n, const std::vector<Pair>& pa
     const size_t stage_bytes = (size_t)a.stage_elems * 8;
     const long long total_chunks = total_pairs * p.cpp;
     *done = true;
-#define SLAB_CASE(MF_, NF_, KS_) \
-    if (v->mf == MF_ && v->nf == NF_ && v->ksplit == KS_)                                                                   \
-        return (a.a_items || a.b_items) ? launch_slab<MF_, NF_, KS_, true>(a, stage_bytes, dense_d, total_chunks, run_prescale) \
-                                        : launch_slab<MF_, NF_, KS_, false>(a, stage_bytes, dense_d, total_chunks, run_prescale)
-    SLAB_CASE(2, 2, true); SLAB_CASE(3, 3, true); SLAB_CASE(4, 4, true); SLAB_CASE(3, 7, true); SLAB_CASE(7, 3, true);
-    SLAB_CASE(5, 2, false); SLAB_CASE(6, 2, false); SLAB_CASE(7, 2, false); SLAB_CASE(8, 2, false);
+#define SLAB_CASE(MF_, NF_, KS_, NW_) \
+    if (v->mf == MF_ && v->nf == NF_ && v->ksplit == KS_ && v->nw == NW_)                                                            \
+        return (a.a_items || a.b_items) ? launch_slab<MF_, NF_, KS_, true, NW_>(a, stage_bytes, dense_d, total_chunks, run_prescale) \
+                                        : launch_slab<MF_, NF_, KS_, false, NW_>(a, stage_bytes, dense_d, total_chunks, run_prescale)
+    SLAB_CASE(2, 2, true, 4); SLAB_CASE(3, 3, true, 4); SLAB_CASE(4, 4, true, 4); SLAB_CASE(3, 7, true, 4); SLAB_CASE(7, 3, true, 4);
+    SLAB_CASE(5, 2, false, 4); SLAB_CASE(6, 2, false, 4); SLAB_CASE(7, 2, false, 4); SLAB_CASE(8, 2, false, 4);
+    SLAB_CASE(3, 3, false, 1); SLAB_CASE(3, 7, false, 1); SLAB_CASE(7, 3, false, 1);
 #undef SLAB_CASE
     *done = false;
     return SIPGPU_OK;

@@ -58,7 +58,7 @@ for d, l, r, kinds, where in sial_patterns():
     ptrn, ierr = api.get_contraction_ptrn([num[c] for c in d], [num[c] for c in l], [num[c] for c in r])
     if ierr != 0:
         continue
-    nb = int(max(8, min(1024, max(np.ceil(10e9 / flops), np.ceil(1.5e9 / byts)))))
+    nb = int(max(8, min(int(os.environ.get("SWEEP_NB_CAP", "1024")), max(np.ceil(10e9 / flops), np.ceil(1.5e9 / byts)))))
     def pool(shape, tag):
         n = int(max(1, min(nb, 1.5e9 // (8 * np.prod(shape)))))
         return [api.DeviceBlock(shape).fill_hash(tag, i, 1.0) for i in range(n)]
