@@ -26,6 +26,7 @@ def test_ccsd_device_test_body_on_the_fake_api(oracle):
     dev.test_ccsd_energy_on_the_device_matches_the_reference_golden(FakeApi(oracle), "all_dat", True)
 
 
+@pytest.mark.skipif(not os.environ.get("SIPGPU_SLOW_TESTS"), reason="a twin of a test that runs anyway; SIPGPU_SLOW_TESTS=1 (keeps the CPU suite at a few minutes)")
 def test_ccsd_t_device_test_body_on_the_fake_api(oracle):
     dev.test_ccsd_t_energy_of_hydrogen_fluoride_on_the_device(FakeApi(oracle), "hf_dat", True)
     dev.test_ccsd_energy_of_hydrogen_fluoride_on_the_device(FakeApi(oracle))
@@ -53,6 +54,7 @@ def test_reference_triples_programs_device_test_body_on_the_fake_api(oracle):
     pt.test_reference_triples_programs_on_the_device(FakeApi(oracle), "hf_dat", True)
 
 
+@pytest.mark.skipif(not os.environ.get("SIPGPU_SLOW_TESTS"), reason="a twin of a test that runs anyway; SIPGPU_SLOW_TESTS=1 (keeps the CPU suite at a few minutes)")
 def test_reference_eom_program_device_test_body_on_the_fake_api(oracle):
     import test_gpu_z_eom_ccsd as eom
     # (without the left-hand program, 25 s more: its CPU twin is tests/test_eom_ccsd_cpu.py::test_eom_ccsd_water_test_in_full)
