@@ -656,6 +656,28 @@ int schedule_and_launch() {
     }
     auto aliased = [&](const void* p) { return g_aliased.count((uintptr_t)p) != 0; };
 
+    // ---- pass A0: `T = L*R; T *= f` (phladder_ab of rlccd_rhf.sialx: `T1 *= -1.0` before the permuted accumulate): the scale that
+    // directly follows its producer on the same whole block folds into the producer's alpha -- one read-modify-write pass over the
+    // block less ----
+    static const bool fold_scale = [] { const char* e = getenv("SIPGPU_WL_FOLD_SCALE"); return !e || atoi(e) != 0; }();
+    for (int i = 0; fold_scale && i < n; ++i) {
+        Op& p = ops[i];
+        if (p.dead || (p.kind != K_CONTRACT && p.kind != K_PERMUTE) || p.beta != 0.0 || aliased(p.D)) continue;
+        auto it = touch.find((uintptr_t)p.D);
+        if (it == touch.end()) continue;
+        TouchList& tl = it->second;
+        size_t k = 0;
+        while (k < tl.size() && tl[k].op != i) ++k;
+        if (k + 1 >= tl.size()) continue;
+        const int j = tl[k + 1].op;
+        Op& c = ops[j];
+        if (c.dead || c.kind != K_EW || c.ewop != WL_SCALE || c.D != p.D || c.dn != p.dn) continue;
+        p.alpha *= c.f;
+        c.dead = true;
+        g.last_unit[j] = i;
+        tl.erase(tl.begin() + (long)(k + 1));
+    }
+
     // ---- pass A: forward a temp produced by a contraction / permute into its single accumulating consumer ----
     for (int i = 0; i < n; ++i) {
         Op& p = ops[i];
