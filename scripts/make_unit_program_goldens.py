@@ -17,6 +17,7 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          # persistence between consecutive programs
          "persistent_distributed_array_mpi1", "persistent_distributed_array_mpi2", "persistent_scalars_1", "persistent_scalars_2",
          "persistent_static_array_test1", "persistent_static_array_test2",
+         "persistent_distributed_array_one_of_three", "persistent_distributed_array_two_of_three", "persistent_distributed_array_three_of_three",
          # the pardo work distribution and the interpreter's scalar / int / if-else arithmetic (no block operations)
          "pardo_loop", "pardo_loop_1d", "pardo_loop_2d", "pardo_loop_3d", "pardo_loop_4d", "pardo_loop_5d", "pardo_loop_6d",
          "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast",
