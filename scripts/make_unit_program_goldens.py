@@ -22,7 +22,9 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          "pardo_loop", "pardo_loop_1d", "pardo_loop_2d", "pardo_loop_3d", "pardo_loop_4d", "pardo_loop_5d", "pardo_loop_6d",
          "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast",
          # programs whose printed blocks the reference compares with fixture files (test/expected_output/*.txt)
-         "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays")
+         "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays",
+         # rank-5 served arrays with a leading simple index through a contiguous local array (the EOM programs' idiom)
+         "contig_local3")
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
 for name in NAMES:
     text = open(SRC + name + ".sialx", errors="replace").read()

@@ -345,6 +345,20 @@ def printed_blocks_equal_the_reference_fixtures(make_backend, to_numpy):
     assert be.value(w.scalars["x"]) == 50 and be.value(w.scalars["y"]) == 50
 
 
+def eom_idiom_contiguous_local(make_backend, to_numpy):
+    """Sial.contig_local3 (test_sial.cpp:667-697; the reference only runs it -- it is the regression test of a crash at "line 6289" of
+    the EOM program): rank-5 served arrays with a leading simple index, prepared / requested block by block and staged through a
+    contiguous local array `CLRB2_aa[1:eom_subspc, a:a, i:i, a1:a1, i1:i1]`.  Closed form of what it prints: slot ksub of every
+    (a,i,a1,i1) block holds (scalar)ksub for ksub <= eom_roots and the zeros of the fresh allocation above"""
+    printed = []
+    run("contig_local3", make_backend, mo=[2, 3, 4, 1, 4, 4, 4, 4],
+        constants=dict(eom_roots=4, eom_subspc=8, baocc=1, eaocc=3, bavirt=4, eavirt=8, norb=8),
+        print_hook=lambda n, idx, a: printed.append((idx[0], np.asarray(a))))
+    assert len(printed) == 8 * 5 * 3 * 5 * 3
+    for ksub, a in printed:
+        assert np.all(a == (float(ksub) if ksub <= 4 else 0.0)), ksub
+
+
 def runs_to_completion(make_backend, to_numpy):
     """BasicSial.tmp_arrays / tmp_arrays_2 / block_scale_assign (:526-650), Sial.put_accumulate_mpi: the reference compares printed
     output; here: the programs run to completion through the same statements (block fill / scale / add / subtract / copy with
@@ -356,4 +370,4 @@ def runs_to_completion(make_backend, to_numpy):
 
 ALL = (contraction_small_test, contraction_small_test2, transpose_tmp, transpose4d_tmp, transpose4d_square_tmp, contract_to_scalar,
        sum_op, self_multiply_test, put_test, get_mpi, put_accumulate_stress, put_initialize_and_increment, gpu_path_programs,
-       persistence_between_programs, printed_blocks_equal_the_reference_fixtures, runs_to_completion)
+       persistence_between_programs, printed_blocks_equal_the_reference_fixtures, eom_idiom_contiguous_local, runs_to_completion)
