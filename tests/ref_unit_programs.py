@@ -312,6 +312,8 @@ def interpreter_arithmetic(make_backend, to_numpy):
     assert be.value(w.scalars["eq_counter"]) == 4 and be.value(w.scalars["neq_counter"]) == 20
     w, be = run("int_self_ops", make_backend)
     assert [be.value(w.scalars[n]) for n in "xyzw"] == [76, 44, -28, 15200]
+    w, be = run("exit_statement_test", make_backend, ao=[2, 3, 4] * 5, constants={"norb": 3})      # :623-650: `exit` leaves ONE loop
+    assert be.value(w.scalars["counter_j"]) == 12 and be.value(w.scalars["counter_i"]) == 4
     w, be = run("index_scalar_cast", make_backend, ao=[2, 2, 1, 3], constants={"norb": 4})
     assert be.value(w.scalars["count"]) == 4 and be.value(w.scalars["count2"]) == 1
 
