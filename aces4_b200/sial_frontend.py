@@ -76,6 +76,9 @@ def _labels(s):
         x = x.strip().lower()
         if not x:
             continue
+        m = re.match(r"\(\s*index\s*\)\s*(\w+)$", x)
+        if m:      # `a[(index)j]`: the VALUE of j addresses a simple-index dimension (cast_indices_to_simple.sialx)
+            x = "@" + m.group(1)
         if ":" in x:
             lo, hi = (y.strip() for y in x.split(":", 1))
             if lo == hi:
@@ -604,7 +607,7 @@ class Walker:
                 self.segs[kind] = list(full[lo - 1: hi])
                 self._range_lo[kind] = lo
         self.tables = {}         # static arrays over simple indices only (index tables such as Xijk): {(i, j): value}
-        self.idx = {}            # index name -> current segment number (1-based)
+        self.idx = _Idx()        # index name -> current segment number (1-based)
         self.scopes = [dict()]   # temp blocks per open loop iteration: (name, segs) -> handle
         self.locals = {}         # allocated local arrays: name -> {segs: handle}
         self._aseg_plan, self._ext_of, self._segkey_plan = {}, {}, {}   # memoised label resolution (per distinct reference in the text)
@@ -619,6 +622,8 @@ class Walker:
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _kind(self, lab):
+        if lab[0] == "@":        # `(index)j`
+            return "s"
         try:
             return self.p.index_kind[lab]
         except KeyError:
@@ -736,7 +741,7 @@ class Walker:
         """handle of the block of a local / static array at the given values of its DECLARED indices (what the reference's test
         controllers read with `local_block(name, indices)`), or None"""
         decl = self.p.arrays[name][1]
-        saved = dict(self.idx)
+        saved = self.idx.copy()
         self.idx.update(dict(zip(decl, values)))
         try:
             key = self._segs_of(decl)
@@ -1001,7 +1006,7 @@ class Walker:
             ranges.append(vals)
             starts.append([sum(ext[:k]) for k in range(len(vals))])
             dims.append(sum(ext))
-        saved = dict(self.idx)
+        saved = self.idx.copy()
         out = []
         for combo in itertools.product(*[range(len(r)) for r in ranges]):
             for d, r, k in zip(decl, ranges, combo):
@@ -1226,6 +1231,18 @@ class Walker:
 
     def _x_collective(self, a, b):
         self.scalars[a] = self.be.collective_sum(self.scalars[a], self.scalars[b])
+
+
+class _Idx(dict):
+    """index name -> current value; `@j` (an `(index)j` cast) reads j"""
+
+    def __missing__(self, key):
+        if key[:1] == "@":
+            return self[key[1:]]
+        raise KeyError(key)
+
+    def copy(self):
+        return _Idx(self)
 
 
 _LABEL_NUMBERS = {}

@@ -342,6 +342,10 @@ def printed_blocks_equal_the_reference_fixtures(make_backend, to_numpy):
     printed = []
     run("scalar_valued_blocks", make_backend, print_hook=lambda arr, idx, a: printed.append(float(np.asarray(a).ravel()[0])))
     assert printed == [1.0, 2.0, 3.0] + [float(j + k) for k in (1, 2, 3) for j in (1, 2, 3, 4, 5)]
+    # cast_indices_to_simple (:1428-1466): `s = a[(index)j]` -- the value of a segment index addresses a simple-index dimension
+    w, be = run("cast_indices_to_simple", make_backend, ao=[2, 2, 5, 5, 5], constants={"norb": 5})
+    for j, ext in enumerate([2, 2, 5, 5, 5], start=1):
+        assert np.array_equal(to_numpy(w.block_of("b", (j,))).ravel(), np.full(ext, 5.0 - j))
     # simple_indices_assignments (:1086-1109)
     w, be = run("simple_indices_assignments", make_backend, ao=[8, 8], constants={"norb": 2, "x": 3.456})
     assert be.value(w.scalars["x"]) == 50 and be.value(w.scalars["y"]) == 50
