@@ -940,7 +940,9 @@ class Walker:
     def _x_allocate(self, name, labs):
         if self.p.arrays.get(name, ("",))[0] != "local":
             raise SialSyntaxError(f"allocate of {name}: not a local array")
-        if "*" not in labs:      # one block, named by the current index values (rccsdpt_aab.sialx:2447): created on first touch
+        if "*" not in labs or any(x != "*" for x in labs):
+            # one block, named by the current index values (rccsdpt_aab.sialx:2447), or one row of blocks (`allocate a[i,*]` inside
+            # `do i`, local_arrays_wild.sialx): created, zero-filled, on first touch
             self.locals.setdefault(name, {})
             return
         if name in self.locals:

@@ -23,7 +23,7 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast",
          "exit_statement_test",
          # programs whose printed blocks the reference compares with fixture files (test/expected_output/*.txt)
-         "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays", "cast_indices_to_simple",
+         "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays", "local_arrays_wild", "cast_indices_to_simple",
          # rank-5 served arrays with a leading simple index through a contiguous local array (the EOM programs' idiom)
          "contig_local3")
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_unit_programs"), exist_ok=True)
@@ -37,5 +37,5 @@ print(len(NAMES), "programs")
 # the reference's expected-output fixtures (printed blocks) for those programs, verbatim
 FIX = "/root/reference/test/expected_output/"
 os.makedirs(os.path.join(ROOT, "tests", "golden", "ref_expected_output"), exist_ok=True)
-for name in ("static_array_test", "tmp_arrays", "tmp_arrays_2", "scalar_valued_blocks", "local_arrays"):
+for name in ("static_array_test", "tmp_arrays", "tmp_arrays_2", "scalar_valued_blocks", "local_arrays", "local_arrays_wild"):
     open(os.path.join(ROOT, "tests", "golden", "ref_expected_output", name + ".txt"), "w").write(open(FIX + name + ".txt").read())

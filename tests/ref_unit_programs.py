@@ -323,11 +323,12 @@ HOST_ONLY = (pardo_loops, interpreter_arithmetic)
 
 def printed_blocks_equal_the_reference_fixtures(make_backend, to_numpy):
     """BasicSial.static_array_test (blocks extracted from a static array that was filled as ONE contiguous array, test_basic_sial.cpp:918-940),
-    tmp_arrays, tmp_arrays_2 (:526-579), local_arrays: the reference compares what the program PRINTS with a fixture file
+    tmp_arrays, tmp_arrays_2 (:526-579), local_arrays, local_arrays_wild (test_simple.cpp:785-830): the reference compares what the program PRINTS with a fixture file
     (`EXPECT_EQ(controller.expectedOutput(), output.str())`); here every printed block is compared, in order, with the blocks of that
     same fixture"""
     for name, ao, consts in (("static_array_test", [3, 4], {"norb": 2, "x": 3.456}), ("tmp_arrays", [2, 3, 4], {"norb": 3, "x": 3.456}),
-                             ("tmp_arrays_2", [2, 3, 4], {"norb": 3, "x": 3.456}), ("local_arrays", [2, 3], {"norb": 2, "x": 3.456})):
+                             ("tmp_arrays_2", [2, 3, 4], {"norb": 3, "x": 3.456}), ("local_arrays", [2, 3], {"norb": 2, "x": 3.456}),
+                             ("local_arrays_wild", [2, 3], {"norb": 2, "x": 3.456})):      # `allocate a[i,*]` row by row
         printed = []
         w, be = run(name, make_backend, ao=ao, constants=consts,
                     print_hook=lambda arr, idx, a: printed.append((arr, idx, np.asarray(a).ravel(order="F").copy())))
