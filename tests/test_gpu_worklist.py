@@ -362,3 +362,44 @@ def test_section_of_gets_and_accumulates_in_one_call(sip, mode):
     finally:
         sip.set_tuning("copy_bulk", -1)
         a.destroy()
+
+
+def test_scale_after_its_producer_folds_into_alpha(sip, oracle):
+    """scheduler pass A0 on numbers: `T = L*R; T *= -2; D1 += T; T2 = permute(T); D2 += T2` (the ph-ring body of rlccd_rhf.sialx)
+    recorded == op-at-a-time == oracle"""
+    rng = np.random.default_rng(11)
+    v, o = 7, 5
+    dl, ll, rl = [1, 2, 3, 4], [1, 5, 6, 4], [3, 6, 5, 2]
+    ptrn, ierr = sip.get_contraction_ptrn(dl, ll, rl)
+    assert ierr == 0
+    L = np.asfortranarray(rng.uniform(-1, 1, (v, o, v, o)))
+    R = np.asfortranarray(rng.uniform(-1, 1, (v, v, o, o)))
+    ref, e = oracle.contract_labels(dl, [v, o, v, o], ll, L, rl, R)
+    assert e == 0
+    ref = -2.0 * ref.reshape((v, o, v, o), order="F")
+    out = {}
+    for mode in ("recorded", "eager"):
+        dL, dR = sip.DeviceBlock.from_numpy(L), sip.DeviceBlock.from_numpy(R)
+        D1, D2 = sip.DeviceBlock((v, o, v, o)).fill(1.0), sip.DeviceBlock((v, o, v, o)).fill(2.0)
+
+        def body():
+            T = sip.DeviceBlock((v, o, v, o))
+            sip.contract(ptrn, dL, dR, (v, o, v, o), out=T)
+            T.scale(-2.0)
+            T2 = sip.DeviceBlock((v, o, v, o))
+            sip.permute_labels([3, 4, 1, 2], [1, 2, 3, 4], T, out=T2)
+            D1.accumulate(T)
+            D2.accumulate(T2)
+            T.free()
+            T2.free()
+        if mode == "recorded":
+            with sip.recording() as rec:
+                body()
+            assert rec.stats["scheduled"] <= 3      # contraction (alpha = -2), D1 += T, fused permute-accumulate into D2
+        else:
+            body()
+        out[mode] = (D1.to_numpy(), D2.to_numpy())
+    for mode in out:
+        assert np.max(np.abs(out[mode][0] - (1.0 + ref))) < 1e-12
+        assert np.max(np.abs(out[mode][1] - (2.0 + ref.transpose(2, 3, 0, 1)))) < 1e-12
+    assert np.array_equal(out["recorded"][0], out["eager"][0]) and np.array_equal(out["recorded"][1], out["eager"][1])

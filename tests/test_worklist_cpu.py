@@ -292,3 +292,33 @@ def test_lccd_pardo_stream_dry_recording_counts_and_host_cost(sip, tmp_path):
     assert out["fused_accumulates"] == 8748 and out["chains"] == 324
     assert out["ops_scheduled"] < out["ops_recorded"]
     assert out["us_per_op"] < 5.0, out
+
+
+def test_scale_directly_after_its_producer_folds_into_alpha(sip):
+    """pass A0: `T = L*R; T *= -1; D += T` (phladder_ab of rlccd_rhf.sialx) -- the whole-block scale is absorbed by the contraction,
+    after which T has a single consumer and the accumulate fuses too: ONE scheduled op.  A scale that does not directly follow the
+    producer (another reader in between) stays."""
+    v = 6
+    ptrn, _ = sip.get_contraction_ptrn([1, 2], [1, 3], [3, 2])
+    with sip.recording(dry=True):
+        A, B, D = (sip.DeviceBlock((v, v)) for _ in range(3))
+        T = sip.DeviceBlock((v, v))
+        sip.contract(ptrn, A, B, (v, v), out=T)
+        T.scale(-1.0)
+        D.accumulate(T)
+        T.free()
+        sip.wl_flush()
+        level, unit = sip.wl_last_plan()
+        st = sip.wl_stats()
+    assert st["scheduled"] == 1 and st["fused_accumulates"] == 1 and unit[1] == unit[0] == 2, (st, unit)
+    with sip.recording(dry=True):
+        A, B, D, E = (sip.DeviceBlock((v, v)) for _ in range(4))
+        T = sip.DeviceBlock((v, v))
+        sip.contract(ptrn, A, B, (v, v), out=T)
+        E.accumulate(T)       # reads the unscaled T first
+        T.scale(-1.0)
+        D.accumulate(T)
+        T.free()
+        sip.wl_flush()
+        st = sip.wl_stats()
+    assert st["scheduled"] == 4 and st["fused_accumulates"] == 0, st
