@@ -1195,6 +1195,10 @@ class Walker:
             v = self.tables.get(name, {}).get(tuple(self.idx[x] for x in labs), 0.0)
             self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), v)
             return
+        if fname == "return_sval" and args and all(self._kind(x) == "s" for x in args[0][1]):     # a one-element block of a local array
+            v = self.be.block_value(self._read(args[0][0], tuple(args[0][1]))[0])
+            self.scalars[bare[0]] = self.be.scalar_set(self.scalars.get(bare[0]), v)
+            return
         if fname == "energy_ty_denominator_rhf":     # `execute energy_ty_denominator_rhf T[a,i,b,j] fock_a shift`: shift by value
             bare = [bare[0], self.be.value(self.scalars[bare[1]])]
         blocks = [self._read(n, labs)[0] if self._is_remote(n) and not self._own_static(n) else self._write(n, labs) for n, labs in args]

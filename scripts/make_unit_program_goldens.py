@@ -21,7 +21,7 @@ NAMES = ("contraction_small_test", "contraction_small_test2", "transpose_tmp", "
          # the pardo work distribution and the interpreter's scalar / int / if-else arithmetic (no block operations)
          "pardo_loop", "pardo_loop_1d", "pardo_loop_2d", "pardo_loop_3d", "pardo_loop_4d", "pardo_loop_5d", "pardo_loop_6d",
          "pardo_loop_with_pragma", "pardo_with_where", "scalar_ops", "int_ops", "int_self_ops", "ifelse", "index_scalar_cast",
-         "exit_statement_test",
+         "exit_statement_test", "return_sval_test",
          # programs whose printed blocks the reference compares with fixture files (test/expected_output/*.txt)
          "static_array_test", "scalar_valued_blocks", "simple_indices_assignments", "local_arrays", "local_arrays_wild", "cast_indices_to_simple",
          # rank-5 served arrays with a leading simple index through a contiguous local array (the EOM programs' idiom)

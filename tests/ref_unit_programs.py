@@ -314,6 +314,8 @@ def interpreter_arithmetic(make_backend, to_numpy):
     assert [be.value(w.scalars[n]) for n in "xyzw"] == [76, 44, -28, 15200]
     w, be = run("exit_statement_test", make_backend, ao=[2, 3, 4] * 5, constants={"norb": 3})      # :623-650: `exit` leaves ONE loop
     assert be.value(w.scalars["counter_j"]) == 12 and be.value(w.scalars["counter_i"]) == 4
+    w, be = run("return_sval_test", make_backend)      # :1469-1475 (runs): `x = a[i,j]` and `execute return_sval a[i,j] y` agree
+    assert be.value(w.scalars["x"]) == be.value(w.scalars["y"]) == 4 * 4 + 3
     w, be = run("index_scalar_cast", make_backend, ao=[2, 2, 1, 3], constants={"norb": 4})
     assert be.value(w.scalars["count"]) == 4 and be.value(w.scalars["count2"]) == 1
 
